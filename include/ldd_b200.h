@@ -1,0 +1,168 @@
+/* ldd_b200.h -- C ABI of libldd_b200.so: the B200 (sm_100a) implementation of ld-decode's RF
+ * demodulation + sync + TBC hot path.
+ *
+ * The reference (wondras/ld-decode) has no FFI layer for this path: the boundary is the Python
+ * class surface of lddecode_core.py (RFDecode.demodblock / demod / audio_phase2, Field.get_syncpeaks,
+ * Field.downscale, lddutils.scale / load_packed_data_*).  Each entry point below names the reference
+ * code it replaces; INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "dev" is a device pointer owned by the caller
+ *     (e.g. torch.Tensor.data_ptr()); tables passed to ldd_set_filter are host pointers.
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*) unless noted.
+ *   - return 0 on success, negative LDD_E* otherwise; ldd_last_error() gives the text.
+ *   - one handle per (GPU, stream user); a handle is not thread-safe.
+ *   - there is no CPU fallback: without a CUDA device ldd_create fails with LDD_ECUDA.
+ *
+ * Plane convention (device, float32, structure of arrays): the reference returns a float64
+ * record array in Hz (lddecode_core.py:314-316).  Here each field is its own float32 plane and
+ * the two planes that ride on the carrier offset are stored RELATIVE to ire0 to keep sub-Hz
+ * resolution in float32:
+ *     plane[LDD_P_DEMOD]    = demod    - ire0      (Hz)
+ *     plane[LDD_P_DEMOD05]  = demod_05 - ire0      (Hz)
+ *     plane[LDD_P_SYNC]     = demod_sync           (0..1)
+ *     plane[LDD_P_BURST]    = demod_burst          (Hz, zero-centred)
+ *     plane[LDD_P_PILOT]    = demod_pilot          (Hz, zero-centred; PAL only)
+ * Analog audio is float64 in absolute Hz, as the reference's rv_audio (lddecode_core.py:322-328).
+ */
+#ifndef LDD_B200_H
+#define LDD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDD_ABI_VERSION 1
+
+#define LDD_SYSTEM_NTSC 0
+#define LDD_SYSTEM_PAL 1
+
+/* capture sample formats (lddutils.py:131-229, ddunpack.c) */
+#define LDD_FMT_U8 0       /* load_unpacked_data_u8: one byte per sample */
+#define LDD_FMT_S16 1      /* load_unpacked_data_s16 */
+#define LDD_FMT_U16 2      /* already unpacked 10-bit samples, 0..1023 */
+#define LDD_FMT_R30 3      /* 3 x 10 bit in a little-endian u32 (ddpack.c); decoded as load_packed_data_3_32: raw 0..1023 */
+#define LDD_FMT_LDS40 4    /* 4 x 10 bit in 5 bytes, MSB first (load_packed_data_4_40) */
+
+/* filter tables built on the host exactly as RFDecode.computefilters does (lddecode_core.py:147-279) */
+#define LDD_F_RFVIDEO 0    /* Filters['RFVideo'] * Filters['MTF']**mtf_level, blocklen complex128 */
+#define LDD_F_VIDEO 1      /* Filters['FVideo'] */
+#define LDD_F_VIDEO05 2    /* Filters['FVideo05'] (the np.roll by F05_offset is applied by the library) */
+#define LDD_F_BURST 3      /* Filters['FVideoBurst'] */
+#define LDD_F_PILOT 4      /* Filters['FVideoPilot'] (PAL) */
+#define LDD_F_AUDIO_L 5    /* Filters['audio_lfilt'], already sliced: 2*blocklen/audio_fdiv1 entries */
+#define LDD_F_AUDIO_R 6    /* Filters['audio_rfilt'] */
+#define LDD_F_AUDIO_LPF2 7 /* Filters['audio_lpf2'], blocklen/4 entries */
+
+#define LDD_P_DEMOD 0
+#define LDD_P_DEMOD05 1
+#define LDD_P_SYNC 2
+#define LDD_P_BURST 3
+#define LDD_P_PILOT 4
+
+#define LDD_PREC_F64 0     /* every transform in float64: the lane whose sync decisions are reference-exact */
+#define LDD_PREC_F32 1     /* float32 shared-memory lane */
+
+#define LDD_OK 0
+#define LDD_EINVAL (-1)
+#define LDD_ESHORT (-2)    /* capture too short for the request; the reference returns None (lddecode_core.py:386-392) */
+#define LDD_ECUDA (-3)
+#define LDD_ENOMEM (-4)
+#define LDD_ECAP (-5)      /* caller buffer too small */
+
+typedef struct ldd_handle ldd_handle;
+
+/* Mirrors the state RFDecode.__init__ derives (lddecode_core.py:120-145, 223-279). */
+typedef struct ldd_config {
+    int abi_version;        /* LDD_ABI_VERSION */
+    int device;             /* CUDA device ordinal */
+    int system;             /* LDD_SYSTEM_* */
+    int blocklen;           /* RFDecode.blocklen, power of two, 4096..262144 */
+    int blockcut;           /* RFDecode.blockcut (1024) */
+    int blockcut_end;       /* RFDecode.blockcut_end = Filters['F05_offset'] (32) */
+    int f05_offset;         /* Filters['F05_offset'] */
+    int precision;          /* LDD_PREC_* */
+    int decode_analog_audio;
+    int audio_slice_lo;     /* Filters['audio_fdslice_lo'].start */
+    int audio_slice_hi;     /* Filters['audio_fdslice_lo'].stop  */
+    int linelen;            /* RFDecode.linelen */
+    int outlinelen;         /* SysParams['outlinelen'] */
+    double freq_hz;         /* RFDecode.freq_hz */
+    double freq_arf;        /* Filters['freq_arf'] */
+    double audio_lowfreq;   /* Filters['audio_lowfreq'] */
+    double ire0;            /* SysParams['ire0'] */
+    double hz_ire;          /* SysParams['hz_ire'] */
+    double vsync_ire;       /* SysParams['vsync_ire'] */
+    double sync_lo_hz;      /* iretohz(-55) (lddecode_core.py:308) */
+    double sync_hi_hz;      /* iretohz(-25) */
+    double fpsync_b0;       /* butter(1, 0.05/freq_half) numerator/denominator (lddecode_core.py:213) */
+    double fpsync_b1;
+    double fpsync_a1;
+} ldd_config;
+
+int ldd_abi_version(void);
+/* number of CUDA devices visible (0 when there is none); never fails */
+int ldd_device_count(void);
+
+int ldd_create(const ldd_config* cfg, ldd_handle** out);
+void ldd_destroy(ldd_handle* h);
+const char* ldd_last_error(ldd_handle* h);
+
+/* Upload one host-built frequency-domain table (interleaved re,im float64, n complex entries).
+ * Synchronous.  Re-upload LDD_F_RFVIDEO whenever mtf_level changes (lddecode_core.py:292-293). */
+int ldd_set_filter(ldd_handle* h, int id, const double* table, int n);
+
+/* ---- kernel (1): unpack.  Replaces ddunpack.c:11-36 and lddutils.py:150-229. ------------------ */
+/* words[nwords] (LE u32, dev) -> out[3*nwords] int16 = ((field)-512)<<6, exactly ddunpack.c */
+int ldd_unpack_r30_ddunpack(const uint32_t* words_dev, size_t nwords, int16_t* out_dev, void* stream);
+/* samples [first, first+n) of a packed capture -> int16/uint16 raw 0..1023 (the Python loaders) or float32 */
+int ldd_unpack_raw(const void* src_dev, int fmt, size_t first_sample, size_t n, uint16_t* out_dev, void* stream);
+int ldd_unpack_f32(const void* src_dev, int fmt, size_t first_sample, size_t n, float* out_dev, void* stream);
+
+/* ---- kernels (2)+(3)+(4a): block demodulation.  Replaces RFDecode.demodblock + the stitching of
+ * RFDecode.demod (lddecode_core.py:288-330, 373-427) and lddutils.unwrap_hilbert (:320-334). ---- */
+
+/* Geometry of demod(start, length) as the reference computes it (lddecode_core.py:374-385, 400, 417). */
+typedef struct ldd_range {
+    long long first_sample;   /* capture index of output sample 0 (start - blockcut, or 0) */
+    long long nblocks;
+    long long total_out;      /* len(output) */
+    long long audio1_len;     /* len(output_audio) before phase 2; 0 when audio is off */
+    long long audio2_len;     /* len(audio_phase2(output_audio)) */
+    long long last_needed;    /* one past the last capture sample any block reads */
+} ldd_range;
+int ldd_demod_range_query(ldd_handle* h, long long start, long long length, ldd_range* out);
+
+/* Demodulate demod(start, length).  rf_dev holds the capture (or a window of it) in format fmt;
+ * rf_base is the capture sample index of rf_dev[0] and rf_len the number of samples available
+ * from there.  planes_dev[LDD_P_*] each hold r.total_out floats; audio1_* hold r.audio1_len
+ * doubles (may be NULL when audio is off).  Returns LDD_ESHORT when a block would read past
+ * rf_base+rf_len (the reference's loader returns None there). */
+int ldd_demod_range(ldd_handle* h, const void* rf_dev, int fmt, long long rf_base, long long rf_len,
+                    long long start, long long length,
+                    float* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev, void* stream);
+
+/* The same kernel on an explicit block grid: nblocks blocks, block j reads capture samples
+ * [first_sample + j*stride, +blocklen) and contributes output samples [j*stride, j*stride+copylen). */
+int ldd_demod_blocks(ldd_handle* h, const void* rf_dev, int fmt, long long rf_base, long long rf_len,
+                     long long first_sample, long long nblocks, long long total_out,
+                     float* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev,
+                     long long audio1_len, void* stream);
+
+/* RFDecode.demodblock (lddecode_core.py:288-330) on one block: rf_dev holds >= blocklen samples;
+ * every plane receives all blocklen samples (nothing cut), audio_* receive 2*blocklen/audio_fdiv1
+ * float64 samples (may be NULL). */
+int ldd_demodblock(ldd_handle* h, const void* rf_dev, int fmt, long long rf_len,
+                   float* const* planes_dev, double* audio_l_dev, double* audio_r_dev, void* stream);
+
+/* RFDecode.audio_phase2 (lddecode_core.py:335-371): in[len] -> out[len/4], float64, dev. */
+int ldd_audio_phase2(ldd_handle* h, const double* in_l_dev, const double* in_r_dev, long long len,
+                     double* out_l_dev, double* out_r_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,88 @@
+"""ctypes binding of libldd_b200.so (C ABI declared in include/ldd_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is visible the
+package raises.  (tests/emu builds a CPU emulation of the same sources for GPU-less unit tests
+and injects it through the private `path=` argument; the package itself never looks for it.)
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_PATH = os.path.join(HERE, "libldd_b200.so")
+
+ABI_VERSION = 1
+SYSTEM = {"NTSC": 0, "PAL": 1}
+FMT_U8, FMT_S16, FMT_U16, FMT_R30, FMT_LDS40 = range(5)
+F_RFVIDEO, F_VIDEO, F_VIDEO05, F_BURST, F_PILOT, F_AUDIO_L, F_AUDIO_R, F_AUDIO_LPF2 = range(8)
+P_DEMOD, P_DEMOD05, P_SYNC, P_BURST, P_PILOT = range(5)
+PREC_F64, PREC_F32 = 0, 1
+OK, EINVAL, ESHORT, ECUDA, ENOMEM, ECAP = 0, -1, -2, -3, -4, -5
+
+
+class LddError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("ldd_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int), ("device", C.c_int), ("system", C.c_int), ("blocklen", C.c_int),
+        ("blockcut", C.c_int), ("blockcut_end", C.c_int), ("f05_offset", C.c_int), ("precision", C.c_int),
+        ("decode_analog_audio", C.c_int), ("audio_slice_lo", C.c_int), ("audio_slice_hi", C.c_int),
+        ("linelen", C.c_int), ("outlinelen", C.c_int),
+        ("freq_hz", C.c_double), ("freq_arf", C.c_double), ("audio_lowfreq", C.c_double),
+        ("ire0", C.c_double), ("hz_ire", C.c_double), ("vsync_ire", C.c_double),
+        ("sync_lo_hz", C.c_double), ("sync_hi_hz", C.c_double),
+        ("fpsync_b0", C.c_double), ("fpsync_b1", C.c_double), ("fpsync_a1", C.c_double),
+    ]
+
+
+class Range(C.Structure):
+    _fields_ = [("first_sample", C.c_longlong), ("nblocks", C.c_longlong), ("total_out", C.c_longlong),
+                ("audio1_len", C.c_longlong), ("audio2_len", C.c_longlong), ("last_needed", C.c_longlong)]
+
+
+# name -> (restype, argtypes); every symbol include/ldd_b200.h declares
+SIGNATURES = {
+    "ldd_abi_version": (C.c_int, []),
+    "ldd_device_count": (C.c_int, []),
+    "ldd_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "ldd_destroy": (None, [C.c_void_p]),
+    "ldd_last_error": (C.c_char_p, [C.c_void_p]),
+    "ldd_set_filter": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "ldd_unpack_r30_ddunpack": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "ldd_unpack_raw": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "ldd_unpack_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "ldd_demod_range_query": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.POINTER(Range)]),
+    "ldd_demod_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_longlong,
+                                  C.c_longlong, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldd_demod_blocks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_longlong,
+                                   C.c_longlong, C.c_longlong, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
+                                   C.c_longlong, C.c_void_p]),
+    "ldd_demodblock": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.POINTER(C.c_void_p), C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
+    "ldd_audio_phase2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_cache = {}
+
+
+def load(path=None):
+    """Loads the shared library and declares every entry point.  Raises if it is missing."""
+    path = os.path.abspath(path or DEFAULT_PATH)
+    if path in _cache:
+        return _cache[path]
+    if not os.path.exists(path):
+        raise ImportError(
+            "%s not found: build it with `python lddecode_b200/csrc/build.py` (nvcc, sm_100a). "
+            "lddecode_b200 has no CPU fallback." % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ldd_abi_version() != ABI_VERSION:
+        raise ImportError("ABI version mismatch in " + path)
+    _cache[path] = lib
+    return lib

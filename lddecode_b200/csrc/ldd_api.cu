@@ -1,0 +1,326 @@
+// C-ABI glue of libldd_b200.so: handle, table upload, range geometry, launches.
+#include "ldd_internal.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+using namespace ldd;
+
+namespace {
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int fail(ldd_handle* h, int code, const char* fmt, ...) {
+    if (h) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        h->err = buf;
+    }
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                  \
+    do {                                                                                   \
+        cudaError_t e_ = (expr);                                                           \
+        if (e_ != cudaSuccess) return fail((h), LDD_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+// Upload a complex table given in double to a fp64 and a fp32 device copy.
+int upload_both(ldd_handle* h, const std::vector<Cx<double>>& t, void** slot /*[2]*/) {
+    size_t n = t.size();
+    for (int i = 0; i < 2; ++i)
+        if (slot[i]) { cudaFree(slot[i]); slot[i] = nullptr; }
+    CUDA_TRY(h, cudaMalloc(&slot[0], n * sizeof(Cx<double>)));
+    CUDA_TRY(h, cudaMalloc(&slot[1], n * sizeof(Cx<float>)));
+    std::vector<Cx<float>> f(n);
+    for (size_t i = 0; i < n; ++i) f[i] = mk<float>((float)t[i].x, (float)t[i].y);
+    CUDA_TRY(h, cudaMemcpy(slot[0], t.data(), n * sizeof(Cx<double>), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(slot[1], f.data(), n * sizeof(Cx<float>), cudaMemcpyHostToDevice));
+    return LDD_OK;
+}
+
+std::vector<Cx<double>> roots(int n, int count) {
+    std::vector<Cx<double>> t(count);
+    for (int k = 0; k < count; ++k) {
+        long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+        t[k] = mk<double>((double)cosl(a), (double)sinl(a));
+    }
+    return t;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ldd_abi_version(void) { return LDD_ABI_VERSION; }
+
+int ldd_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char* ldd_last_error(ldd_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int ldd_create(const ldd_config* cfg, ldd_handle** out) {
+    if (!cfg || !out) return LDD_EINVAL;
+    *out = nullptr;
+    if (cfg->abi_version != LDD_ABI_VERSION) return LDD_EINVAL;
+    if (!is_pow2(cfg->blocklen) || cfg->blocklen < 4096 || cfg->blocklen > 262144) return LDD_EINVAL;
+    if (cfg->blockcut < 0 || cfg->blockcut_end < 0 || cfg->blockcut + cfg->blockcut_end >= cfg->blocklen / 2) return LDD_EINVAL;
+    if (cfg->system != LDD_SYSTEM_NTSC && cfg->system != LDD_SYSTEM_PAL) return LDD_EINVAL;
+    if (ldd_device_count() <= cfg->device) return LDD_ECUDA;
+    ldd_handle* h = new (std::nothrow) ldd_handle();
+    if (!h) return LDD_ENOMEM;
+    h->cfg = *cfg;
+    h->device = cfg->device;
+    memset(h->d_WM, 0, sizeof h->d_WM);
+    memset(h->d_WN, 0, sizeof h->d_WN);
+    memset(h->d_Hv, 0, sizeof h->d_Hv);
+    memset(h->d_F, 0, sizeof h->d_F);
+    memset(h->d_AL, 0, sizeof h->d_AL);
+    memset(h->d_AR, 0, sizeof h->d_AR);
+    memset(h->have_filter, 0, sizeof h->have_filter);
+    h->scratch = nullptr;
+    h->scratch_bytes = 0;
+    h->d_lpf2 = nullptr;
+    h->d_WNfull = nullptr;
+    *out = h;                       // from here on the caller can read the error text
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(h, LDD_ECUDA, "cudaSetDevice(%d) failed", cfg->device);
+    cudaDeviceProp prop;
+    CUDA_TRY(h, cudaGetDeviceProperties(&prop, cfg->device));
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    const int N = cfg->blocklen, M = N / 2;
+    h->A = 0;
+    if (cfg->decode_analog_audio) {
+        int w = cfg->audio_slice_hi - cfg->audio_slice_lo;
+        if (w <= 0 || !is_pow2(2 * w) || cfg->audio_slice_lo < 1 || cfg->audio_slice_hi >= M || 2 * w > M / 2)
+            return fail(h, LDD_EINVAL, "audio slice [%d,%d) unsupported", cfg->audio_slice_lo, cfg->audio_slice_hi);
+        h->A = 2 * w;
+        int ds = N / h->A;
+        long long stride = N - cfg->blockcut - cfg->blockcut_end;
+        if (cfg->blockcut % ds || stride % ds)
+            return fail(h, LDD_EINVAL, "blockcut/stride not a multiple of the audio decimation %d", ds);
+    }
+    int rc = upload_both(h, roots(M, M), h->d_WM);
+    if (rc) return rc;
+    rc = upload_both(h, roots(N, M), h->d_WN);
+    if (rc) return rc;
+    {
+        std::vector<Cx<double>> t = roots(N, N);
+        CUDA_TRY(h, cudaMalloc(&h->d_WNfull, (size_t)N * sizeof(Cx<double>)));
+        CUDA_TRY(h, cudaMemcpy(h->d_WNfull, t.data(), (size_t)N * sizeof(Cx<double>), cudaMemcpyHostToDevice));
+    }
+    // launch geometry / scratch of the demodulation kernel
+    const char* env = getenv("LDD_CTAS_PER_SM");
+    int per_sm = env ? atoi(env) : 2;
+    if (per_sm < 1) per_sm = 1;
+    size_t esz = cfg->precision == LDD_PREC_F64 ? sizeof(Cx<double>) : sizeof(Cx<float>);
+    size_t per_cta = (size_t)3 * M * esz;
+    bool smem_lane = cfg->precision == LDD_PREC_F32 && per_cta + 1024 <= h->smem_optin;
+    h->grid = smem_lane ? h->sm_count : h->sm_count * per_sm;
+    h->scratch_per_cta = smem_lane ? 0 : per_cta;
+    // audio phase 2 runs out of the same scratch: two length-N complex128 buffers per CTA
+    size_t per_cta_a2 = (size_t)2 * N * sizeof(Cx<double>);
+    size_t need = (size_t)h->grid * (h->scratch_per_cta > per_cta_a2 ? h->scratch_per_cta : per_cta_a2);
+    CUDA_TRY(h, cudaMalloc(&h->scratch, need));
+    h->scratch_bytes = need;
+    return LDD_OK;
+}
+
+void ldd_destroy(ldd_handle* h) {
+    if (!h) return;
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(h->d_WM[i]); cudaFree(h->d_WN[i]); cudaFree(h->d_Hv[i]); cudaFree(h->d_AL[i]); cudaFree(h->d_AR[i]);
+        for (int m = 0; m < 4; ++m) cudaFree(h->d_F[m][i]);
+    }
+    cudaFree(h->scratch);
+    cudaFree(h->d_lpf2);
+    cudaFree(h->d_WNfull);
+    delete h;
+}
+
+int ldd_set_filter(ldd_handle* h, int id, const double* table, int n) {
+    if (!h || !table) return LDD_EINVAL;
+    const int N = h->cfg.blocklen, M = N / 2;
+    const Cx<double>* src = (const Cx<double>*)table;
+    std::vector<Cx<double>> t;
+    switch (id) {
+        case LDD_F_RFVIDEO: {
+            if (n != N) return fail(h, LDD_EINVAL, "RFVideo table needs %d entries", N);
+            t.assign(src, src + N);
+            int rc = upload_both(h, t, h->d_Hv);
+            if (rc) return rc;
+            break;
+        }
+        case LDD_F_VIDEO: case LDD_F_VIDEO05: case LDD_F_BURST: case LDD_F_PILOT: {
+            if (n != N) return fail(h, LDD_EINVAL, "post filter table needs %d entries", N);
+            int m = id - LDD_F_VIDEO;
+            t.resize(M + 1);
+            const long double twopi = 2.0L * 3.14159265358979323846264338327950288L;
+            for (int k = 0; k <= M; ++k) {
+                Cx<double> v = src[k];
+                if (id == LDD_F_VIDEO05 && h->cfg.f05_offset) {
+                    // np.roll(x, -off)  <=>  X[k] * e^{+2 pi i off k / N}   (lddecode_core.py:303)
+                    long long kk = ((long long)k * h->cfg.f05_offset) % N;
+                    long double a = twopi * (long double)kk / (long double)N;
+                    v = v * mk<double>((double)cosl(a), (double)sinl(a));
+                }
+                t[k] = scale(v, 1.0 / (double)M);
+            }
+            h->dc[m] = src[0].x;
+            int rc = upload_both(h, t, h->d_F[m]);
+            if (rc) return rc;
+            break;
+        }
+        case LDD_F_AUDIO_L: case LDD_F_AUDIO_R: {
+            if (n != h->A || h->A == 0) return fail(h, LDD_EINVAL, "audio filter needs %d entries", h->A);
+            t.assign(src, src + n);
+            int rc = upload_both(h, t, id == LDD_F_AUDIO_L ? h->d_AL : h->d_AR);
+            if (rc) return rc;
+            break;
+        }
+        case LDD_F_AUDIO_LPF2: {
+            if (n != N / 4) return fail(h, LDD_EINVAL, "audio_lpf2 needs %d entries", N / 4);
+            if (h->d_lpf2) cudaFree(h->d_lpf2);
+            CUDA_TRY(h, cudaMalloc(&h->d_lpf2, (size_t)n * sizeof(Cx<double>)));
+            CUDA_TRY(h, cudaMemcpy(h->d_lpf2, table, (size_t)n * sizeof(Cx<double>), cudaMemcpyHostToDevice));
+            break;
+        }
+        default:
+            return fail(h, LDD_EINVAL, "unknown filter id %d", id);
+    }
+    h->have_filter[id] = true;
+    return LDD_OK;
+}
+
+int ldd_demod_range_query(ldd_handle* h, long long start, long long length, ldd_range* out) {
+    if (!h || !out || length < 0 || start < 0) return LDD_EINVAL;
+    const int N = h->cfg.blocklen;
+    const long long S = N - h->cfg.blockcut - h->cfg.blockcut_end;
+    long long end = start + length + 1;                              // lddecode_core.py:374
+    long long s0 = start > h->cfg.blockcut ? start - h->cfg.blockcut : 0;   // :376-379
+    out->first_sample = s0;
+    out->nblocks = (end - s0 + S - 1) / S;                           // range(start, end, S), :385
+    out->total_out = end - s0 + 1;                                   // :400
+    out->audio1_len = 0;
+    out->audio2_len = 0;
+    if (h->A) {
+        int ds = N / h->A;
+        out->audio1_len = (end - s0) / ds + 1;                       // :417
+        out->audio2_len = out->audio1_len / 4;                       // :350
+    }
+    out->last_needed = s0 + (out->nblocks - 1) * S + N;
+    return LDD_OK;
+}
+
+static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_base, long long rf_len,
+                     long long first_sample, long long nblocks, long long total_out, int blockcut, long long S,
+                     float* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev,
+                     long long audio1_len, void* stream) {
+    if (!h || !rf_dev || !planes_dev || nblocks < 0 || total_out < 0) return LDD_EINVAL;
+    const ldd_config& c = h->cfg;
+    const int N = c.blocklen, M = N / 2;
+    const bool pal = c.system == LDD_SYSTEM_PAL;
+    const int nfilt = pal ? 4 : 3;
+    for (int m = 0; m < nfilt; ++m)
+        if (!h->have_filter[LDD_F_VIDEO + m]) return fail(h, LDD_EINVAL, "filter %d not set", LDD_F_VIDEO + m);
+    if (!h->have_filter[LDD_F_RFVIDEO]) return fail(h, LDD_EINVAL, "RFVideo filter not set");
+    const bool audio = h->A > 0 && audio1_l_dev && audio1_r_dev;
+    if (audio && (!h->have_filter[LDD_F_AUDIO_L] || !h->have_filter[LDD_F_AUDIO_R]))
+        return fail(h, LDD_EINVAL, "audio filters not set");
+    if (fmt < LDD_FMT_U8 || fmt > LDD_FMT_LDS40) return fail(h, LDD_EINVAL, "bad format %d", fmt);
+    int group = fmt == LDD_FMT_R30 ? 3 : (fmt == LDD_FMT_LDS40 ? 4 : 1);
+    if (rf_base % group) return fail(h, LDD_EINVAL, "rf_base must be a multiple of %d for this format", group);
+    if (nblocks == 0) return LDD_OK;
+    long long last_needed = first_sample + (nblocks - 1) * S + N;
+    if (first_sample < rf_base || last_needed > rf_base + rf_len)
+        return fail(h, LDD_ESHORT, "capture too short: need [%lld,%lld), have [%lld,%lld)", first_sample, last_needed,
+                    rf_base, rf_base + rf_len);
+    for (int pidx = 0; pidx < (pal ? 5 : 4); ++pidx)
+        if (!planes_dev[pidx]) return fail(h, LDD_EINVAL, "plane %d is NULL", pidx);
+
+    const int lane = c.precision == LDD_PREC_F64 ? 0 : 1;
+    DemodParams p;
+    memset(&p, 0, sizeof p);
+    p.N = N; p.M = M; p.A = audio ? h->A : 0;
+    p.blockcut = blockcut;
+    p.nfilt = nfilt;
+    p.plan_m = make_plan(M);
+    if (p.A) { p.plan_a = make_plan(p.A); p.wstride_a = M / p.A; p.audio_ds = N / p.A; }
+    p.rf = rf_dev; p.fmt = fmt;
+    p.first_sample = first_sample - rf_base;
+    p.stride = S;
+    p.nblocks = (int)nblocks;
+    p.WM = h->d_WM[lane]; p.WN = h->d_WN[lane]; p.Hv = h->d_Hv[lane];
+    const double rel[4] = {1.0, 1.0, 0.0, 0.0};
+    for (int m = 0; m < nfilt; ++m) {
+        p.F[m] = h->d_F[m][lane];
+        p.addc[m] = c.ire0 * (h->dc[m] - rel[m]);
+    }
+    p.AL = h->d_AL[lane]; p.AR = h->d_AR[lane];
+    p.a_lo = c.audio_slice_lo; p.a_hi = c.audio_slice_hi;
+    const double twopi = 6.283185307179586476925286766559;
+    p.audio_scale = c.freq_arf / twopi;
+    p.audio_lowfreq = c.audio_lowfreq;
+    p.hz_per_rad = c.freq_hz / twopi;
+    p.ire0 = c.ire0;
+    p.sync_lo = c.sync_lo_hz; p.sync_hi = c.sync_hi_hz;
+    p.sync_ref = c.ire0;
+    p.fp_b0 = c.fpsync_b0; p.fp_b1 = c.fpsync_b1; p.fp_c = -c.fpsync_a1;
+    for (int i = 0; i < 5; ++i) p.plane[i] = planes_dev[i];
+    p.total_out = total_out;
+    p.audio_l = audio1_l_dev; p.audio_r = audio1_r_dev; p.audio_total = audio1_len;
+    p.scratch = h->scratch_per_cta ? h->scratch : nullptr;
+    p.scratch_per_cta = h->scratch_per_cta;
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = (int)(nblocks < h->grid ? nblocks : h->grid);
+    if (audio) {
+        // the reference leaves the unwritten tail of output_audio at zero (lddecode_core.py:417-422)
+        CUDA_TRY(h, cudaMemsetAsync(audio1_l_dev, 0, (size_t)audio1_len * sizeof(double), st));
+        CUDA_TRY(h, cudaMemsetAsync(audio1_r_dev, 0, (size_t)audio1_len * sizeof(double), st));
+    }
+    int rc;
+    if (lane == 0) rc = launch_demod_f64(p, grid, st);
+    else rc = launch_demod_f32(p, grid, st, h->scratch_per_cta ? 0 : (size_t)3 * M * sizeof(Cx<float>));
+    if (rc) return fail(h, rc, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return LDD_OK;
+}
+
+int ldd_demod_blocks(ldd_handle* h, const void* rf_dev, int fmt, long long rf_base, long long rf_len,
+                     long long first_sample, long long nblocks, long long total_out,
+                     float* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev,
+                     long long audio1_len, void* stream) {
+    if (!h) return LDD_EINVAL;
+    const long long S = h->cfg.blocklen - h->cfg.blockcut - h->cfg.blockcut_end;
+    return run_demod(h, rf_dev, fmt, rf_base, rf_len, first_sample, nblocks, total_out, h->cfg.blockcut, S,
+                     planes_dev, audio1_l_dev, audio1_r_dev, audio1_len, stream);
+}
+
+int ldd_demodblock(ldd_handle* h, const void* rf_dev, int fmt, long long rf_len,
+                   float* const* planes_dev, double* audio_l_dev, double* audio_r_dev, void* stream) {
+    if (!h) return LDD_EINVAL;
+    const int N = h->cfg.blocklen;
+    return run_demod(h, rf_dev, fmt, 0, rf_len, 0, 1, N, 0, N, planes_dev, audio_l_dev, audio_r_dev,
+                     h->A, stream);
+}
+
+int ldd_demod_range(ldd_handle* h, const void* rf_dev, int fmt, long long rf_base, long long rf_len,
+                    long long start, long long length,
+                    float* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev, void* stream) {
+    ldd_range r;
+    int rc = ldd_demod_range_query(h, start, length, &r);
+    if (rc) return rc;
+    return ldd_demod_blocks(h, rf_dev, fmt, rf_base, rf_len, r.first_sample, r.nblocks, r.total_out,
+                            planes_dev, audio1_l_dev, audio1_r_dev, r.audio1_len, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,349 @@
+// Fused block demodulation: unpack -> FFT -> RF filter -> inverse FFT -> FM discriminator ->
+// FFT -> post filters -> inverse FFTs -> sync threshold + circular 1-pole scan -> stitched stores.
+// One CTA carries one block of N samples through the whole chain; nothing but the raw samples
+// is read from HBM and nothing but the kept region of the output planes is written.
+//
+// Restates RFDecode.demodblock (lddecode_core.py:288-330) and the overlap-save stitching of
+// RFDecode.demod (:385-422) with these algebraic changes (all exact up to rounding, checked
+// against the oracle in tests/):
+//   * real-input transforms run as length-M = N/2 complex transforms + an untangle step;
+//   * ifft(X * RFVideo) is split into its even and odd output samples (decimation in frequency)
+//     so that it is two length-M transforms as well;
+//   * the demodulated signal has ire0 subtracted before its forward transform and the filters'
+//     DC gain times ire0 added back at the store (keeps float32 planes at sub-Hz resolution);
+//   * np.roll(., -F05_offset) is a phase ramp folded into the FVideo05 table;
+//   * ifft(fft(sync) * FPsync) is evaluated as the circular first-order recursion it equals,
+//     by a three-phase scan (thread-local, warp-shuffle, cross-warp) in float64.
+#include "ldd_internal.h"
+
+namespace ldd {
+
+template <class T> struct Math;
+template <> struct Math<double> {
+    static __device__ inline double atan2(double y, double x) { return ::atan2(y, x); }
+};
+template <> struct Math<float> {
+    static __device__ inline float atan2(float y, float x) { return ::atan2f(y, x); }
+};
+
+// ---- raw sample fetch with the unpackers fused in (ddunpack.c / lddutils.py:131-229) -----------
+__device__ inline int fetch_sample(const void* rf, int fmt, long long s) {
+    switch (fmt) {
+        case LDD_FMT_U8: return (int)((const unsigned char*)rf)[s];
+        case LDD_FMT_S16: return (int)((const short*)rf)[s];
+        case LDD_FMT_U16: return (int)((const unsigned short*)rf)[s];
+        case LDD_FMT_R30: {
+            long long w = s / 3;
+            int f = (int)(s - w * 3);
+            unsigned v = ((const unsigned*)rf)[w];
+            return (int)((v >> (10 * f)) & 0x3ffu);
+        }
+        default: {   // LDD_FMT_LDS40
+            long long g = s >> 2;
+            int f = (int)(s & 3);
+            const unsigned char* b = (const unsigned char*)rf + g * 5;
+            unsigned hi = b[f], lo = b[f + 1];
+            // s0 = b0<<2 | b1>>6 ; s1 = (b1&0x3f)<<4 | b2>>4 ; s2 = (b2&0xf)<<6 | b3>>2 ; s3 = (b3&3)<<8 | b4
+            return (int)(((hi << (2 + 2 * f)) | (lo >> (6 - 2 * f))) & 0x3ffu);
+        }
+    }
+}
+
+// ---- untangle: length-M FFT of z[n] = x[2n] + j x[2n+1]  ->  X[k], k = 0..M (X[M] packed in X[0].y)
+template <class T>
+__device__ inline void untangle(Cx<T>* Z, int M, const Cx<T>* __restrict__ WN, int tid, int nthr) {
+    const T half = (T)0.5;
+    for (int k = tid; k <= M / 2; k += nthr) {
+        if (k == 0) {
+            Cx<T> z = Z[0];
+            Z[0] = mk<T>(z.x + z.y, z.x - z.y);
+        } else {
+            Cx<T> a = Z[k], b = conj(Z[M - k]);
+            Cx<T> E = scale(a + b, half);
+            Cx<T> Od = scale(mul_mj(a - b), half);
+            Cx<T> Tw = WN[k] * Od;
+            Z[k] = E + Tw;
+            Z[M - k] = conj(E - Tw);
+        }
+    }
+}
+
+// ---- tangle: conj-symmetric spectrum Y = D * F (k = 0..M)  ->  conj(Q), whose forward length-M
+// FFT r gives the real signal: y[2n] = r.x, y[2n+1] = -r.y (F carries the 1/M).
+template <class T>
+__device__ inline void tangle(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __restrict__ F, int M,
+                              const Cx<T>* __restrict__ WN, int tid, int nthr) {
+    const T half = (T)0.5;
+    for (int k = tid; k <= M / 2; k += nthr) {
+        if (k == 0) {
+            Cx<T> d = D[0];
+            T y0 = d.x * F[0].x, ym = d.y * F[M].x;
+            Q[0] = mk<T>((y0 + ym) * half, -(y0 - ym) * half);
+        } else {
+            Cx<T> a = D[k] * F[k], b = conj(D[M - k] * F[M - k]);
+            Cx<T> E = scale(a + b, half);
+            Cx<T> Od = mulc(scale(a - b, half), WN[k]);      // * W_N^{-k}
+            Cx<T> q = E + mul_pj(Od);
+            Cx<T> qm = conj(E) + mul_pj(conj(Od));
+            Q[k] = conj(q);
+            Q[M - k] = conj(qm);
+        }
+    }
+}
+
+template <class T, int NT>
+__global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int N = p.N, M = p.M;
+    const Cx<T>* WM = (const Cx<T>*)p.WM;
+    const Cx<T>* WN = (const Cx<T>*)p.WN;
+    const Cx<T>* Hv = (const Cx<T>*)p.Hv;
+
+    Cx<T>* b0;
+    if (p.scratch) {
+        b0 = (Cx<T>*)((char*)p.scratch + (size_t)blockIdx.x * p.scratch_per_cta);
+    } else {
+        LDD_DYN_SMEM(smem);
+        b0 = (Cx<T>*)smem;
+    }
+    Cx<T>* b1 = b0 + M;
+    Cx<T>* b2 = b1 + M;
+    __shared__ double s_warp[32];
+    __shared__ double s_total;
+
+    for (int blk = blockIdx.x; blk < p.nblocks; blk += gridDim.x) {
+        const long long in0 = p.first_sample + (long long)blk * p.stride;
+        const long long o = (long long)blk * p.stride;
+        long long copylen = p.stride;
+        if (o + (N - p.blockcut) > p.total_out) copylen = p.total_out - o;
+        if (copylen > N - p.blockcut) copylen = N - p.blockcut;
+        if (copylen < 0) copylen = 0;
+        const int keep0 = p.blockcut, keep1 = p.blockcut + (int)copylen;
+
+        // A. samples -> z[n] = x[2n] + j x[2n+1]
+        for (int n = tid; n < M; n += nthr) {
+            int s0 = fetch_sample(p.rf, p.fmt, in0 + 2 * n);
+            int s1 = fetch_sample(p.rf, p.fmt, in0 + 2 * n + 1);
+            b0[n] = mk<T>((T)s0, (T)s1);
+        }
+        __syncthreads();
+
+        // B/C. X = rfft(x)
+        Cx<T>* X = fft_run<T>(b0, b1, p.plan_m, WM, 1, tid, nthr);
+        Cx<T>* f1 = (X == b0) ? b1 : b0;      // free
+        Cx<T>* f2 = b2;                        // free
+        untangle<T>(X, M, WN, tid, nthr);
+        __syncthreads();
+
+        // D. analog audio, phase 1 (lddecode_core.py:322-326): two length-A inverse transforms of a
+        //    slice of X, FM discriminator at freq_arf, + audio_lowfreq.
+        if (p.A > 0) {
+            const int A = p.A, hA = A / 2;
+            const Cx<T>* AL = (const Cx<T>*)p.AL;
+            const Cx<T>* AR = (const Cx<T>*)p.AR;
+            Cx<T>* gl = f1;
+            Cx<T>* gr = f2;
+            for (int j = tid; j < A; j += nthr) {
+                Cx<T> xa = (j < hA) ? X[p.a_lo + j] : conj(X[p.a_hi - (j - hA)]);
+                gl[j] = conj(xa * AL[j]);
+                gr[j] = conj(xa * AR[j]);
+            }
+            __syncthreads();
+            Cx<T>* rl = fft_run<T>(gl, gl + A, p.plan_a, WM, p.wstride_a, tid, nthr);
+            Cx<T>* rr = fft_run<T>(gr, gr + A, p.plan_a, WM, p.wstride_a, tid, nthr);
+            // angles in place (x: left, y: right of the same sample) then neighbour difference
+            Cx<T>* ang = (rl == gl) ? gl + A : gl;   // the other half of f1
+            for (int j = tid; j < A; j += nthr)
+                ang[j] = mk<T>(Math<T>::atan2(-rl[j].y, rl[j].x), Math<T>::atan2(-rr[j].y, rr[j].x));
+            __syncthreads();
+            const int a0 = keep0 / p.audio_ds, a1 = keep1 / p.audio_ds;
+            const long long ao = o / p.audio_ds;
+            const double twopi = 6.283185307179586476925286766559;
+            for (int j = a0 + tid; j < a1; j += nthr) {
+                double dl = 0.0, dr = 0.0;
+                if (j > 0) {
+                    dl = (double)ang[j].x - (double)ang[j - 1].x;
+                    dr = (double)ang[j].y - (double)ang[j - 1].y;
+                    if (dl < 0) dl += twopi;
+                    if (dr < 0) dr += twopi;
+                }
+                long long oi = ao + (j - a0);
+                if (oi < p.audio_total) {
+                    p.audio_l[oi] = dl * p.audio_scale + p.audio_lowfreq;
+                    p.audio_r[oi] = dr * p.audio_scale + p.audio_lowfreq;
+                }
+            }
+            __syncthreads();
+        }
+
+        // E. Y = X_full * Hv, split into even/odd output samples: U[k] = Y[k] + Y[k+M],
+        //    V[k] = (Y[k] - Y[k+M]) W_N^{-k}; stored conjugated for inverse-by-forward.
+        Cx<T>* U = f1;
+        Cx<T>* V = f2;
+        for (int k = tid; k <= M / 2; k += nthr) {
+            if (k == 0) {
+                Cx<T> x = X[0];
+                Cx<T> y0 = scale(Hv[0], x.x), y1 = scale(Hv[M], x.y);
+                U[0] = conj(y0 + y1);
+                V[0] = conj(y0 - y1);
+            } else {
+                Cx<T> xa = X[k], xb = X[M - k];
+                Cx<T> y0 = xa * Hv[k], y1 = conj(xb) * Hv[k + M];
+                U[k] = conj(y0 + y1);
+                V[k] = conj(mulc(y0 - y1, WN[k]));
+                if (k != M - k) {
+                    Cx<T> z0 = xb * Hv[M - k], z1 = conj(xa) * Hv[2 * M - k];
+                    U[M - k] = conj(z0 + z1);
+                    // W_N^{-(M-k)} = -conj(W_N^{-k}) = -W_N^{k}
+                    Cx<T> d = z0 - z1;
+                    V[M - k] = conj(mk<T>(-d.x, -d.y) * WN[k]);
+                }
+            }
+        }
+        __syncthreads();
+
+        // F. h[2n] = conj(ru[n]), h[2n+1] = conj(rv[n]) (up to a positive scale)
+        Cx<T>* ru = fft_run<T>(U, X, p.plan_m, WM, 1, tid, nthr);
+        Cx<T>* fu = (ru == U) ? X : U;
+        Cx<T>* rv = fft_run<T>(V, fu, p.plan_m, WM, 1, tid, nthr);
+        Cx<T>* fv = (rv == V) ? fu : V;
+
+        // G. FM discriminator (lddutils.py:320-334): angle, neighbour difference, fold to [0, 2pi),
+        //    scale to Hz; minus ire0; packed for the next real transform.
+        for (int n = tid; n < M; n += nthr)
+            ru[n] = mk<T>(Math<T>::atan2(-ru[n].y, ru[n].x), Math<T>::atan2(-rv[n].y, rv[n].x));
+        __syncthreads();
+        {
+            const T twopi = (T)6.283185307179586476925286766559;
+            const T hz = (T)p.hz_per_rad, ire0 = (T)p.ire0;
+            for (int n = tid; n < M; n += nthr) {
+                Cx<T> a = ru[n];
+                T d0 = (T)0;
+                if (n > 0) {
+                    d0 = a.x - ru[n - 1].y;
+                    if (d0 < 0) d0 += twopi;
+                }
+                T d1 = a.y - a.x;
+                if (d1 < 0) d1 += twopi;
+                rv[n] = mk<T>(d0 * hz - ire0, d1 * hz - ire0);
+            }
+        }
+        __syncthreads();
+
+        // H. D = rfft(demod - ire0)
+        Cx<T>* D = fft_run<T>(rv, ru, p.plan_m, WM, 1, tid, nthr);
+        Cx<T>* g1 = (D == rv) ? ru : rv;
+        Cx<T>* g2 = fv;
+        untangle<T>(D, M, WN, tid, nthr);
+        __syncthreads();
+
+        // I. post filters.  Order: video, burst, (pilot), video05 last because its whole block feeds the sync scan.
+        const int order[4] = {0, 2, 3, 1};
+        const int pl_of[4] = {LDD_P_DEMOD, LDD_P_DEMOD05, LDD_P_BURST, LDD_P_PILOT};
+        Cx<T>* r05 = nullptr;
+        for (int oi = 0; oi < 4; ++oi) {
+            const int m = order[oi];
+            if (m >= p.nfilt && m != 1) continue;
+            tangle<T>(D, g1, (const Cx<T>*)p.F[m], M, WN, tid, nthr);
+            __syncthreads();
+            Cx<T>* r = fft_run<T>(g1, g2, p.plan_m, WM, 1, tid, nthr);
+            float* out = p.plane[pl_of[m]];
+            const T addc = (T)p.addc[m];
+            // kept samples 2n, 2n+1 -> out[o + 2n - keep0]; keep0, o and copylen parity: handle singly
+            for (int n = tid; n < M; n += nthr) {
+                Cx<T> v = r[n];
+                int i0 = 2 * n, i1 = 2 * n + 1;
+                float v0 = (float)(v.x + addc), v1 = (float)(-v.y + addc);
+                if (i0 >= keep0 && i0 < keep1) out[o + (i0 - keep0)] = v0;
+                if (i1 >= keep0 && i1 < keep1) out[o + (i1 - keep0)] = v1;
+            }
+            if (m == 1) r05 = r;
+            __syncthreads();
+        }
+
+        // J. sync: s[n] = lo <= demod_05[n] <= hi (lddecode_core.py:308); demod_sync = circular
+        //    y[n] = b0 s[n] + b1 s[n-1] + c y[n-1]  (== ifft(fft(s) * FPsync), :310).
+        {
+            const T* x05 = (const T*)r05;     // interleaved: sample 2n = r.x, 2n+1 = -r.y
+            const double add = p.addc[1] + p.sync_ref;
+            const int CH = N / nthr;           // N and nthr are powers of two, CH >= 1
+            const int n0 = tid * CH;
+            auto insync = [&](int n) -> double {
+                n = (n + N) & (N - 1);
+                double v = (double)x05[n];
+                if (n & 1) v = -v;
+                v += add;
+                return (v >= p.sync_lo && v <= p.sync_hi) ? 1.0 : 0.0;
+            };
+            const double c = p.fp_c;
+            double sprev = insync(n0 - 1);
+            const double sprev0 = sprev;
+            double acc = 0.0;
+            for (int i = 0; i < CH; ++i) {
+                double s = insync(n0 + i);
+                acc = c * acc + (p.fp_b0 * s + p.fp_b1 * sprev);
+                sprev = s;
+            }
+            // inclusive scan of the affine maps y -> Ach*y + acc over threads
+            const double Ach = pow(c, (double)CH);
+            const int lane = tid & 31, warp = tid >> 5;
+            double incl = acc, mult = Ach;
+            for (int d = 1; d < 32; d <<= 1) {
+                double up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += mult * up;
+                mult *= mult;
+            }
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            const double A32 = pow(Ach, 32.0);
+            const int nwarp = nthr >> 5;
+            double carry = 0.0;                 // state entering this warp (zero initial state)
+            for (int w = 0; w < warp; ++w) carry = A32 * carry + s_warp[w];
+            if (tid == nthr - 1) {
+                double tot = pow(Ach, (double)(lane + 1)) * carry + incl;
+                s_total = tot / (1.0 - pow(c, (double)N));     // periodic steady state y[-1]
+            }
+            __syncthreads();
+            (void)nwarp;
+            // state entering this thread's chunk
+            double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            double st = (lane == 0 ? 0.0 : excl) + pow(Ach, (double)lane) * carry + pow(c, (double)n0) * s_total;
+            float* out = p.plane[LDD_P_SYNC];
+            sprev = sprev0;
+            for (int i = 0; i < CH; ++i) {
+                int n = n0 + i;
+                double s = insync(n);
+                st = c * st + (p.fp_b0 * s + p.fp_b1 * sprev);
+                sprev = s;
+                if (n >= keep0 && n < keep1) out[o + (n - keep0)] = (float)st;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        (void)what;
+        return LDD_ECUDA;
+    }
+    return LDD_OK;
+}
+
+int launch_demod_f64(const DemodParams& p, int grid, cudaStream_t st) {
+    void (*kern)(const DemodParams) = demod_kernel<double, 256>;
+    LDD_LAUNCH(kern, dim3(grid), dim3(256), 0, st, p);
+    return check_launch("demod_kernel<double>");
+}
+
+int launch_demod_f32(const DemodParams& p, int grid, cudaStream_t st, size_t smem_bytes) {
+    void (*kern)(const DemodParams) = demod_kernel<float, 512>;
+    if (smem_bytes) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    }
+    LDD_LAUNCH(kern, dim3(grid), dim3(512), smem_bytes, st, p);
+    return check_launch("demod_kernel<float>");
+}
+
+}  // namespace ldd

@@ -1,0 +1,152 @@
+// Block-cooperative Stockham autosort FFT (radix 2/4/8/16), templated on the real type.
+//
+// One CTA transforms one length-M complex sequence that lives either in shared memory (fp32
+// fast lane) or in an L2-resident global scratch slice (fp64 exact lane); the code only sees
+// generic pointers.  Every pass is out of place (src -> dst) followed by a CTA barrier, so a
+// transform ping-pongs between two buffers.  Only the forward transform exists; inverses are
+// taken as conj(FFT(conj(x))) with the conjugations folded into the fused stages around it
+// (ldd_demod.cu).  Replaces numpy.fft.fft/ifft as called at lddecode_core.py:289-313, 322-326.
+#pragma once
+#include "ldd_platform.h"
+
+namespace ldd {
+
+template <class T>
+struct alignas(2 * sizeof(T)) Cx {
+    T x, y;
+};
+
+template <class T> LDD_HD inline Cx<T> mk(T a, T b) { Cx<T> r; r.x = a; r.y = b; return r; }
+template <class T> LDD_HD inline Cx<T> operator+(Cx<T> a, Cx<T> b) { return mk<T>(a.x + b.x, a.y + b.y); }
+template <class T> LDD_HD inline Cx<T> operator-(Cx<T> a, Cx<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
+template <class T> LDD_HD inline Cx<T> operator*(Cx<T> a, Cx<T> b) { return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+template <class T> LDD_HD inline Cx<T> conj(Cx<T> a) { return mk<T>(a.x, -a.y); }
+template <class T> LDD_HD inline Cx<T> scale(Cx<T> a, T s) { return mk<T>(a.x * s, a.y * s); }
+// a * conj(b)
+template <class T> LDD_HD inline Cx<T> mulc(Cx<T> a, Cx<T> b) { return mk<T>(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+// multiply by -j / +j
+template <class T> LDD_HD inline Cx<T> mul_mj(Cx<T> a) { return mk<T>(a.y, -a.x); }
+template <class T> LDD_HD inline Cx<T> mul_pj(Cx<T> a) { return mk<T>(-a.y, a.x); }
+
+// ---- in-register DFTs, natural order in and out (forward, e^{-2 pi i nk/R}) -------------------
+template <class T, int R> struct Dft;
+
+template <class T> struct Dft<T, 2> {
+    static LDD_HD inline void run(Cx<T>* v) {
+        Cx<T> a = v[0], b = v[1];
+        v[0] = a + b;
+        v[1] = a - b;
+    }
+};
+template <class T> struct Dft<T, 4> {
+    static LDD_HD inline void run(Cx<T>* v) {
+        Cx<T> t0 = v[0] + v[2], t1 = v[0] - v[2], t2 = v[1] + v[3], t3 = mul_mj(v[1] - v[3]);
+        v[0] = t0 + t2;
+        v[1] = t1 + t3;
+        v[2] = t0 - t2;
+        v[3] = t1 - t3;
+    }
+};
+template <class T> struct Dft<T, 8> {
+    static LDD_HD inline void run(Cx<T>* v) {
+        Cx<T> e[4] = {v[0], v[2], v[4], v[6]};
+        Cx<T> o[4] = {v[1], v[3], v[5], v[7]};
+        Dft<T, 4>::run(e);
+        Dft<T, 4>::run(o);
+        const T h = (T)0.70710678118654752440;
+        Cx<T> w1 = mk<T>((o[1].x + o[1].y) * h, (o[1].y - o[1].x) * h);     // * (1-j)/sqrt2
+        Cx<T> w2 = mul_mj(o[2]);
+        Cx<T> w3 = mk<T>((o[3].y - o[3].x) * h, -(o[3].x + o[3].y) * h);    // * (-1-j)/sqrt2
+        v[0] = e[0] + o[0]; v[4] = e[0] - o[0];
+        v[1] = e[1] + w1;   v[5] = e[1] - w1;
+        v[2] = e[2] + w2;   v[6] = e[2] - w2;
+        v[3] = e[3] + w3;   v[7] = e[3] - w3;
+    }
+};
+template <class T> struct Dft<T, 16> {
+    static LDD_HD inline void run(Cx<T>* v) {
+        Cx<T> e[8], o[8];
+        LDD_UNROLL
+        for (int i = 0; i < 8; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+        Dft<T, 8>::run(e);
+        Dft<T, 8>::run(o);
+        const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173;   // cos, sin(pi/8)
+        const T h = (T)0.70710678118654752440;
+        Cx<T> w[8];
+        w[0] = o[0];
+        w[1] = o[1] * mk<T>(c1, -s1);
+        w[2] = mk<T>((o[2].x + o[2].y) * h, (o[2].y - o[2].x) * h);
+        w[3] = o[3] * mk<T>(s1, -c1);
+        w[4] = mul_mj(o[4]);
+        w[5] = o[5] * mk<T>(-s1, -c1);
+        w[6] = mk<T>((o[6].y - o[6].x) * h, -(o[6].x + o[6].y) * h);
+        w[7] = o[7] * mk<T>(-c1, -s1);
+        LDD_UNROLL
+        for (int i = 0; i < 8; ++i) { v[i] = e[i] + w[i]; v[i + 8] = e[i] - w[i]; }
+    }
+};
+
+// ---- one Stockham pass -------------------------------------------------------------------------
+// src, dst: length-M sequences.  Ns: product of the radices of the passes already done.
+// W: table of e^{-2 pi i k / Mtab}, k in [0, Mtab); wstride = Mtab / M.
+template <class T, int R>
+__device__ inline void fft_pass(const Cx<T>* src, Cx<T>* dst, int M, int Ns,
+                                const Cx<T>* __restrict__ W, int wstride, int tid, int nthr) {
+    const int nb = M / R;
+    for (int j = tid; j < nb; j += nthr) {
+        Cx<T> v[R];
+        LDD_UNROLL
+        for (int r = 0; r < R; ++r) v[r] = src[j + r * nb];
+        const int k = j & (Ns - 1);
+        if (Ns > 1) {
+            // w^r by repeated squaring / short products from one table lookup (<= 4 products deep)
+            Cx<T> p[R];
+            p[1] = W[(size_t)k * (size_t)(nb / Ns) * (size_t)wstride];
+            LDD_UNROLL
+            for (int r = 2; r < R; ++r) p[r] = (r & 1) ? p[r - 1] * p[1] : p[r / 2] * p[r / 2];
+            LDD_UNROLL
+            for (int r = 1; r < R; ++r) v[r] = v[r] * p[r];
+        }
+        Dft<T, R>::run(v);
+        const int j0 = (j - k) * R + k;
+        LDD_UNROLL
+        for (int r = 0; r < R; ++r) dst[j0 + r * Ns] = v[r];
+    }
+}
+
+struct FftPlan {
+    int n;            // transform length (power of two)
+    int npass;
+    int radix[8];
+};
+
+inline FftPlan make_plan(int n) {
+    FftPlan p;
+    p.n = n;
+    p.npass = 0;
+    int rem = n;
+    while (rem >= 16 && p.npass < 8) { p.radix[p.npass++] = 16; rem /= 16; }
+    if (rem > 1) p.radix[p.npass++] = rem;       // 2, 4 or 8
+    return p;
+}
+
+// Runs all passes; the result is in the returned pointer (a or b).  Ends with a barrier.
+template <class T>
+__device__ inline Cx<T>* fft_run(Cx<T>* a, Cx<T>* b, const FftPlan& plan, const Cx<T>* __restrict__ W,
+                                 int wstride, int tid, int nthr) {
+    int Ns = 1;
+    for (int p = 0; p < plan.npass; ++p) {
+        switch (plan.radix[p]) {
+            case 16: fft_pass<T, 16>(a, b, plan.n, Ns, W, wstride, tid, nthr); break;
+            case 8: fft_pass<T, 8>(a, b, plan.n, Ns, W, wstride, tid, nthr); break;
+            case 4: fft_pass<T, 4>(a, b, plan.n, Ns, W, wstride, tid, nthr); break;
+            default: fft_pass<T, 2>(a, b, plan.n, Ns, W, wstride, tid, nthr); break;
+        }
+        Ns *= plan.radix[p];
+        Cx<T>* t = a; a = b; b = t;
+        __syncthreads();
+    }
+    return a;
+}
+
+}  // namespace ldd

@@ -1,0 +1,82 @@
+// Internal declarations shared by the translation units of libldd_b200.so.
+#pragma once
+#include "ldd_fft.cuh"
+#include "../../include/ldd_b200.h"
+
+#include <string>
+#include <vector>
+
+namespace ldd {
+
+// Everything the fused demodulation kernel needs, passed by value.
+struct DemodParams {
+    // geometry
+    int N, M, A;                 // block length, N/2, audio transform length (0: audio off)
+    int blockcut;                // leading samples of every block that are discarded (1024)
+    int nfilt;                   // 3 NTSC (video, video05, burst), 4 PAL (+pilot)
+    FftPlan plan_m, plan_a;
+    int wstride_a;               // M / A
+    // input
+    const void* rf;              // device pointer to the capture (format fmt)
+    int fmt;
+    long long first_sample;      // capture sample index of block 0
+    long long stride;            // N - blockcut - blockcut_end
+    int nblocks;
+    // tables (Cx<T>, device)
+    const void* WM;              // e^{-2 pi i k/M}, k<M
+    const void* WN;              // e^{-2 pi i k/N}, k<M
+    const void* Hv;              // RFVideo * MTF^level, N entries
+    const void* F[4];            // FVideo, FVideo05 (pre-rolled), FVideoBurst, FVideoPilot; k<=M; scaled 1/M
+    const void* AL;              // audio_lfilt / audio_rfilt, A entries
+    const void* AR;
+    double addc[4];              // added to the inverse transform of filter m before the store
+    int a_lo, a_hi;              // audio_fdslice_lo = [a_lo, a_hi)
+    double audio_scale;          // freq_arf / 2 pi
+    double audio_lowfreq;
+    // constants
+    double hz_per_rad;           // freq_hz / 2 pi
+    double ire0;
+    double sync_lo, sync_hi;     // iretohz(-55), iretohz(-25), compared against (plane05 + sync_ref)
+    double sync_ref;             // value to add to the stored demod_05 plane to get absolute Hz
+    double fp_b0, fp_b1, fp_c;   // FPsync: y[n] = b0 s[n] + b1 s[n-1] + c y[n-1]
+    // outputs (device)
+    float* plane[5];             // demod, demod_05, demod_sync, demod_burst, demod_pilot
+    long long total_out;         // length of each plane
+    double* audio_l;
+    double* audio_r;
+    long long audio_total;
+    int audio_ds;                // N / A
+    // scratch for the global-memory lane
+    void* scratch;
+    size_t scratch_per_cta;      // bytes
+};
+
+int launch_demod_f64(const DemodParams& p, int grid, cudaStream_t st);
+int launch_demod_f32(const DemodParams& p, int grid, cudaStream_t st, size_t smem_optin);
+
+}  // namespace ldd
+
+struct ldd_handle {
+    ldd_config cfg;
+    int device;
+    int sm_count;
+    size_t smem_optin;
+    std::string err;
+    // device tables, fp64 and fp32 copies
+    void* d_WM[2];
+    void* d_WN[2];
+    void* d_Hv[2];
+    void* d_F[4][2];
+    void* d_AL[2];
+    void* d_AR[2];
+    double dc[4];
+    bool have_filter[16];
+    int A;
+    void* scratch;
+    size_t scratch_bytes;
+    size_t scratch_per_cta;
+    int grid;
+    // audio phase 2
+    void* d_lpf2;     // Cx<double>[N/4]
+    void* d_WNfull;   // e^{-2 pi i k/N}, k<N (double) for the phase-2 transforms
+};

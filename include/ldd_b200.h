@@ -20,7 +20,8 @@
  * resolution in float32:
  *     plane[LDD_P_DEMOD]    = demod    - ire0      (Hz)
  *     plane[LDD_P_DEMOD05]  = demod_05 - ire0      (Hz)
- *     plane[LDD_P_SYNC]     = demod_sync           (0..1)
+ *     plane[LDD_P_SYNC]     = demod_sync           (0..1)  -- FLOAT64: the greedy peak search compares
+ *                                                     neighbouring samples, so it must see the reference's ordering
  *     plane[LDD_P_BURST]    = demod_burst          (Hz, zero-centred)
  *     plane[LDD_P_PILOT]    = demod_pilot          (Hz, zero-centred; PAL only)
  * Analog audio is float64 in absolute Hz, as the reference's rv_audio (lddecode_core.py:322-328).
@@ -138,29 +139,56 @@ int ldd_demod_range_query(ldd_handle* h, long long start, long long length, ldd_
 
 /* Demodulate demod(start, length).  rf_dev holds the capture (or a window of it) in format fmt;
  * rf_base is the capture sample index of rf_dev[0] and rf_len the number of samples available
- * from there.  planes_dev[LDD_P_*] each hold r.total_out floats; audio1_* hold r.audio1_len
+ * from there.  planes_dev[LDD_P_*] each hold r.total_out float32 (float64 for LDD_P_SYNC); audio1_* hold r.audio1_len
  * doubles (may be NULL when audio is off).  Returns LDD_ESHORT when a block would read past
  * rf_base+rf_len (the reference's loader returns None there). */
 int ldd_demod_range(ldd_handle* h, const void* rf_dev, int fmt, long long rf_base, long long rf_len,
                     long long start, long long length,
-                    float* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev, void* stream);
+                    void* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev, void* stream);
 
 /* The same kernel on an explicit block grid: nblocks blocks, block j reads capture samples
  * [first_sample + j*stride, +blocklen) and contributes output samples [j*stride, j*stride+copylen). */
 int ldd_demod_blocks(ldd_handle* h, const void* rf_dev, int fmt, long long rf_base, long long rf_len,
                      long long first_sample, long long nblocks, long long total_out,
-                     float* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev,
+                     void* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev,
                      long long audio1_len, void* stream);
 
 /* RFDecode.demodblock (lddecode_core.py:288-330) on one block: rf_dev holds >= blocklen samples;
  * every plane receives all blocklen samples (nothing cut), audio_* receive 2*blocklen/audio_fdiv1
  * float64 samples (may be NULL). */
 int ldd_demodblock(ldd_handle* h, const void* rf_dev, int fmt, long long rf_len,
-                   float* const* planes_dev, double* audio_l_dev, double* audio_r_dev, void* stream);
+                   void* const* planes_dev, double* audio_l_dev, double* audio_r_dev, void* stream);
 
 /* RFDecode.audio_phase2 (lddecode_core.py:335-371): in[len] -> out[len/4], float64, dev. */
 int ldd_audio_phase2(ldd_handle* h, const double* in_l_dev, const double* in_r_dev, long long len,
                      double* out_l_dev, double* out_r_dev, void* stream);
+
+/* ---- kernel (4): sync-pulse peak list.  Bit-exact Field.get_syncpeaks (lddecode_core.py:497-516)
+ * over sync_dev[0..n) (the float64 demod_sync plane) starting at index `start`, with the handle's
+ * linelen.  peaks_dev/vals_dev receive up to `cap` peak indices and ds[peak] values; count_dev[0]
+ * receives the number of peaks found (if > cap the list is truncated: call again with a larger
+ * buffer), count_dev[1] the number of chase steps the stitching pass had to take itself. */
+int ldd_sync_peaks(ldd_handle* h, const double* sync_dev, long long n, long long start,
+                   long long* peaks_dev, double* vals_dev, int cap, int* count_dev, void* stream);
+
+/* ---- kernel (5): per-line TBC resampling.  Field.downscale + lddutils.scale (not-a-knot cubic
+ * spline per line) + the uint16 quantisation of FieldNTSC/FieldPAL.downscale(final=True)
+ * (lddecode_core.py:789-812, 1023-1035, 1135-1159; lddutils.py:83-97), batched over fields.
+ *   plane_dev[n]           float32 plane; plane value + plane_add = Hz (ire0 for LDD_P_DEMOD, 0 for LDD_P_BURST)
+ *   linelocs_dev           [nfields][ll_stride] float64 line positions (plane coordinates); output line k of a
+ *                          field spans linelocs[lineoffset+k] .. linelocs[lineoffset+k+1]
+ *   linecount_dev          [nfields] lines to produce per field (<= max_linecount)
+ *   mode 0                 out_dev = float64 Hz, exactly what Field.downscale returns (dsout)
+ *   mode 1                 out_dev = uint16 TBC samples; when burstlevel_dev (float32 [nfields][ll_stride]) is
+ *                          given the NTSC burst markers are written into samples 0/1 of lines 1..linecount-2
+ *   out_stride             elements between consecutive fields in out_dev
+ *   status_dev             [nfields] int, caller-zeroed; bit 0 set when a line's window leaves the plane or
+ *                          is degenerate (the reference raises and marks the field invalid) */
+int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n, double plane_add,
+                   const double* linelocs_dev, int ll_stride, const int* linecount_dev, int nfields,
+                   int max_linecount, int lineoffset, int outwidth, int wow, int mode,
+                   void* out_dev, long long out_stride, const float* burstlevel_dev, double colorlevel,
+                   int* status_dev, void* stream);
 
 #ifdef __cplusplus
 }

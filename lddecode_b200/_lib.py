@@ -63,6 +63,11 @@ SIGNATURES = {
     "ldd_demodblock": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.POINTER(C.c_void_p), C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
     "ldd_audio_phase2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldd_sync_peaks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int,
+                                 C.c_void_p, C.c_void_p]),
+    "ldd_tbc_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p,
+                                 C.c_double, C.c_void_p, C.c_void_p]),
 }
 
 _cache = {}

@@ -145,6 +145,7 @@ void ldd_destroy(ldd_handle* h) {
     cudaFree(h->scratch);
     cudaFree(h->d_lpf2);
     cudaFree(h->d_WNfull);
+    cudaFree(h->peak_ws);
     delete h;
 }
 
@@ -224,7 +225,7 @@ int ldd_demod_range_query(ldd_handle* h, long long start, long long length, ldd_
 
 static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_base, long long rf_len,
                      long long first_sample, long long nblocks, long long total_out, int blockcut, long long S,
-                     float* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev,
+                     void* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev,
                      long long audio1_len, void* stream) {
     if (!h || !rf_dev || !planes_dev || nblocks < 0 || total_out < 0) return LDD_EINVAL;
     const ldd_config& c = h->cfg;
@@ -297,7 +298,7 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
 
 int ldd_demod_blocks(ldd_handle* h, const void* rf_dev, int fmt, long long rf_base, long long rf_len,
                      long long first_sample, long long nblocks, long long total_out,
-                     float* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev,
+                     void* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev,
                      long long audio1_len, void* stream) {
     if (!h) return LDD_EINVAL;
     const long long S = h->cfg.blocklen - h->cfg.blockcut - h->cfg.blockcut_end;
@@ -306,7 +307,7 @@ int ldd_demod_blocks(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
 }
 
 int ldd_demodblock(ldd_handle* h, const void* rf_dev, int fmt, long long rf_len,
-                   float* const* planes_dev, double* audio_l_dev, double* audio_r_dev, void* stream) {
+                   void* const* planes_dev, double* audio_l_dev, double* audio_r_dev, void* stream) {
     if (!h) return LDD_EINVAL;
     const int N = h->cfg.blocklen;
     return run_demod(h, rf_dev, fmt, 0, rf_len, 0, 1, N, 0, N, planes_dev, audio_l_dev, audio_r_dev,
@@ -315,7 +316,7 @@ int ldd_demodblock(ldd_handle* h, const void* rf_dev, int fmt, long long rf_len,
 
 int ldd_demod_range(ldd_handle* h, const void* rf_dev, int fmt, long long rf_base, long long rf_len,
                     long long start, long long length,
-                    float* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev, void* stream) {
+                    void* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev, void* stream) {
     ldd_range r;
     int rc = ldd_demod_range_query(h, start, length, &r);
     if (rc) return rc;

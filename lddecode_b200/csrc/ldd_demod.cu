@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
             tangle<T>(D, g1, (const Cx<T>*)p.F[m], M, WN, tid, nthr);
             __syncthreads();
             Cx<T>* r = fft_run<T>(g1, g2, p.plan_m, WM, 1, tid, nthr);
-            float* out = p.plane[pl_of[m]];
+            float* out = (float*)p.plane[pl_of[m]];
             const T addc = (T)p.addc[m];
             // kept samples 2n, 2n+1 -> out[o + 2n - keep0]; keep0, o and copylen parity: handle singly
             for (int n = tid; n < M; n += nthr) {
@@ -308,14 +308,14 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
             // state entering this thread's chunk
             double excl = __shfl_up_sync(0xffffffffu, incl, 1);
             double st = (lane == 0 ? 0.0 : excl) + pow(Ach, (double)lane) * carry + pow(c, (double)n0) * s_total;
-            float* out = p.plane[LDD_P_SYNC];
+            double* out = (double*)p.plane[LDD_P_SYNC];     // float64: peak search must see the reference's ordering
             sprev = sprev0;
             for (int i = 0; i < CH; ++i) {
                 int n = n0 + i;
                 double s = insync(n);
                 st = c * st + (p.fp_b0 * s + p.fp_b1 * sprev);
                 sprev = s;
-                if (n >= keep0 && n < keep1) out[o + (n - keep0)] = (float)st;
+                if (n >= keep0 && n < keep1) out[o + (n - keep0)] = st;
             }
         }
         __syncthreads();

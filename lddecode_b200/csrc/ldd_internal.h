@@ -40,7 +40,7 @@ struct DemodParams {
     double sync_ref;             // value to add to the stored demod_05 plane to get absolute Hz
     double fp_b0, fp_b1, fp_c;   // FPsync: y[n] = b0 s[n] + b1 s[n-1] + c y[n-1]
     // outputs (device)
-    float* plane[5];             // demod, demod_05, demod_sync, demod_burst, demod_pilot
+    void* plane[5];              // demod, demod_05, demod_sync (float64!), demod_burst, demod_pilot (float32)
     long long total_out;         // length of each plane
     double* audio_l;
     double* audio_r;
@@ -79,4 +79,7 @@ struct ldd_handle {
     // audio phase 2
     void* d_lpf2;     // Cx<double>[N/4]
     void* d_WNfull;   // e^{-2 pi i k/N}, k<N (double) for the phase-2 transforms
+    // workspace of the peak search (grown on demand)
+    void* peak_ws = nullptr;
+    size_t peak_ws_bytes = 0;
 };

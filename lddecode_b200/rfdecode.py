@@ -284,7 +284,7 @@ class RFDecode:
 
     def _alloc_planes(self, total):
         names = VIDEO_FIELDS[self.system]
-        bufs = {n: self._be.empty(total, np.float32) for n in names}
+        bufs = {n: self._be.empty(total, np.float64 if n == 'demod_sync' else np.float32) for n in names}
         arr = (C.c_void_p * 5)()
         for n in names:
             arr[_PLANE_OF[n]] = self._be.ptr(bufs[n])

@@ -5,8 +5,9 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
@@ -24,3 +25,24 @@ def golden():
         return cache[name]
 
     return load
+
+
+def _cuda_backend():
+    from lddecode_b200._backend import CudaBackend
+    return CudaBackend()
+
+
+# Kernel tests are written once against the C ABI and run on two targets:
+#   "cuda": the real library on the GPU (-m gpu; the parity tests proper)
+#   "emu" : the same .cu sources compiled for the CPU by tests/emu (-m "not gpu"; small cases)
+@pytest.fixture(scope="session", params=[pytest.param("emu"), pytest.param("cuda", marks=pytest.mark.gpu)])
+def backend(request):
+    if request.param == "cuda":
+        return _cuda_backend()
+    from emu_util import emu_backend
+    return emu_backend()
+
+
+@pytest.fixture(scope="session")
+def cuda_backend():
+    return _cuda_backend()

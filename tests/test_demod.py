@@ -1,0 +1,143 @@
+"""Kernels (1)-(3) + the sync scan of (4): demodblock / demod / audio_phase2 through the C ABI
+against the golden vectors recorded from the reference and against the oracle on fresh seeds.
+
+Tolerances (BASELINE.json north_star): demodulated Hz within 1e-4 relative of the float64
+reference -- the float64 lane is held to 1e-7 here (float32 plane storage relative to ire0 is
+the only loss); demod_sync within 1e-6 absolute; audio within 1e-4 relative (held to 1e-9)."""
+import numpy as np
+import pytest
+
+from lddecode_b200 import rfdecode, synth
+from oracle import ldd_oracle as O
+
+RTOL_HZ = 1e-7
+
+
+def _system(g):
+    return "PAL" if "demod_pilot" in list(g["planes"]) else "NTSC"
+
+
+def _mem_loader(cap):
+    def ld(infile, sample, n):
+        if sample + n > len(cap):
+            return None
+        return cap[sample:sample + n]
+    return ld
+
+
+def _close_hz(actual, desired, rtol=RTOL_HZ):
+    np.testing.assert_allclose(actual, desired, rtol=rtol, atol=0.2)
+
+
+@pytest.mark.parametrize("name", ["ntsc", "pal", "ntsc10"])
+def test_demodblock_golden(backend, golden, name):
+    g = golden(name)
+    rf = rfdecode.RFDecode(float(g["fs_mhz"]), _system(g), int(g["blocklen"]), _backend=backend)
+    cap = g["capture"]
+    for bi in range(3):
+        pos, mtf = int(g["blk%d_pos" % bi]), float(g["blk%d_mtf" % bi])
+        v, a = rf.demodblock(cap[pos:pos + rf.blocklen], mtf)
+        for p in g["planes"]:
+            ref = g["blk%d_%s" % (bi, p)]
+            if p == "demod_sync":
+                np.testing.assert_allclose(v[p], ref, rtol=0, atol=1e-6)
+            else:
+                _close_hz(v[p], ref)
+        np.testing.assert_allclose(a["audio_left"], g["blk%d_audio_left" % bi], rtol=1e-9)
+        np.testing.assert_allclose(a["audio_right"], g["blk%d_audio_right" % bi], rtol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["ntsc", "pal", "ntsc10"])
+def test_demod_stitched_golden(backend, golden, name):
+    g = golden(name)
+    N = int(g["blocklen"])
+    rf = rfdecode.RFDecode(float(g["fs_mhz"]), _system(g), N, _backend=backend)
+    cap = g["capture"]
+    rfdecode.loader = _mem_loader(cap)
+    video, audio = rf.demod(None, 0, int(g["demod_length"]), 1)
+    sp = int(g["sparse"])
+    assert len(video) == int(g["demod_len"])
+    for p in g["planes"]:
+        tol = dict(rtol=0, atol=1e-6) if p == "demod_sync" else dict(rtol=RTOL_HZ, atol=0.2)
+        np.testing.assert_allclose(video[p][::sp], g["demod_sparse_" + p], **tol)
+        np.testing.assert_allclose(video[p][N - 1056 - 2048:N - 1056 + 2048], g["demod_seam_" + p], **tol)
+        np.testing.assert_allclose(video[p][-4096:], g["demod_tail_" + p], **tol)
+    np.testing.assert_allclose(audio["audio_left"], g["audio_left"], rtol=1e-9)
+    np.testing.assert_allclose(audio["audio_right"], g["audio_right"], rtol=1e-9)
+    # start > blockcut and mtf_level = 0 (lddecode_core.py:376-379)
+    v2, a2 = rf.demod(None, 54321, 300000, 0)
+    assert len(v2) == int(g["demod2_len"])
+    for p in g["planes"]:
+        tol = dict(rtol=0, atol=1e-6) if p == "demod_sync" else dict(rtol=RTOL_HZ, atol=0.2)
+        np.testing.assert_allclose(v2[p][::sp], g["demod2_sparse_" + p], **tol)
+    np.testing.assert_allclose(a2["audio_left"], g["demod2_audio_left"], rtol=1e-9)
+    # short read -> None, like the reference (lddecode_core.py:386-392)
+    assert rf.demod(None, len(cap) - 5000, 100000, 0) is None
+
+
+def test_sync_decisions_bit_exact_vs_oracle(backend):
+    """The binary sync decision behind demod_sync (lddecode_core.py:308) must be the reference's,
+    sample for sample: recover it from demod_05 and compare with the oracle on a fresh seed."""
+    fs = 8 * 315 / 88
+    cap = synth.SynthRF("NTSC", fs, seed=11).generate(200000)
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, _backend=backend)
+    rfdecode.loader = _mem_loader(cap)
+    video, _ = rf.demod(None, 0, 150000, 0)
+    dec = O.Decoder(fs, "NTSC", 16384)
+    ov, _ = O.demod(dec, lambda s, n: cap[s:s + n] if s + n <= len(cap) else None, 0, 150000, 0)
+    np.testing.assert_allclose(video["demod_sync"], ov["demod_sync"], rtol=0, atol=1e-6)
+    assert np.array_equal(O.sync_peaks(video["demod_sync"], 0, rf.linelen), O.sync_peaks(ov["demod_sync"], 0, dec.linelen))
+
+
+@pytest.mark.parametrize("fmt", ["r30", "lds"])
+def test_packed_input_formats(backend, fmt):
+    """10-bit packed captures demodulate straight from the packed bytes (unpack fused into the
+    block load) to the same planes as the unpacked samples."""
+    import ctypes as C
+    from lddecode_b200 import _lib
+    fs = 8 * 315 / 88
+    s10 = synth.SynthRF("NTSC", fs, seed=5, bits=10).generate(60000)
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, _backend=backend)
+    start, length = 4000, 30000
+    ref = rf.demod_device(backend.to_device(s10), _lib.FMT_U16, 0, len(s10), start, length, 0, phase2=False).to_recarrays()
+    if fmt == "r30":
+        packed, f = synth.pack_r30(s10), _lib.FMT_R30
+    else:
+        packed, f = synth.pack_lds(s10), _lib.FMT_LDS40
+    out = rf.demod_device(backend.to_device(packed), f, 0, len(s10) // 12 * 12, start, length, 0, phase2=False).to_recarrays()
+    for p in ("demod", "demod_05", "demod_sync", "demod_burst"):
+        assert np.array_equal(out[0][p], ref[0][p]), p
+    assert np.array_equal(out[1]["audio_left"], ref[1]["audio_left"])
+
+
+def test_unpack_kernels_bit_exact(backend, golden):
+    import ctypes as C
+    from lddecode_b200 import _lib
+    g = golden("unpack")
+    lib = backend.lib
+    words = backend.to_device(g["r30_words"])
+    out = backend.empty(len(g["r30_words"]) * 3, np.int16)
+    assert lib.ldd_unpack_r30_ddunpack(backend.ptr(words), len(g["r30_words"]), backend.ptr(out), backend.stream()) == 0
+    backend.synchronize()
+    assert np.array_equal(backend.to_host(out), g["r30_ddunpack_i16"])          # == compiled ddunpack.c
+    for s, exp in zip(g["r30_py_starts"], g["r30_py"]):
+        o = backend.empty(1000, np.uint16)
+        assert lib.ldd_unpack_raw(backend.ptr(words), _lib.FMT_R30, int(s), 1000, backend.ptr(o), backend.stream()) == 0
+        backend.synchronize()
+        assert np.array_equal(backend.to_host(o).astype(np.int16), exp)        # == load_packed_data_3_32
+    lds = backend.to_device(g["lds_bytes"])
+    for s, exp in zip(g["lds_py_starts"], g["lds_py"]):
+        o = backend.empty(1000, np.uint16)
+        assert lib.ldd_unpack_raw(backend.ptr(lds), _lib.FMT_LDS40, int(s), 1000, backend.ptr(o), backend.stream()) == 0
+        backend.synchronize()
+        assert np.array_equal(backend.to_host(o), exp)                         # == load_packed_data_4_40
+        of = backend.empty(1001, np.float32)
+        assert lib.ldd_unpack_f32(backend.ptr(lds), _lib.FMT_LDS40, int(s), 999, backend.ptr(of), backend.stream()) == 0
+        backend.synchronize()
+        assert np.array_equal(backend.to_host(of)[:999], exp[:999].astype(np.float32))
+    # ragged tail and empty input
+    o = backend.zeros(16, np.int16)
+    assert lib.ldd_unpack_r30_ddunpack(backend.ptr(words), 5, backend.ptr(o), backend.stream()) == 0
+    backend.synchronize()
+    assert np.array_equal(backend.to_host(o)[:15], g["r30_ddunpack_i16"][:15]) and backend.to_host(o)[15] == 0
+    assert lib.ldd_unpack_r30_ddunpack(backend.ptr(words), 0, backend.ptr(o), backend.stream()) == 0

@@ -171,12 +171,63 @@ int ldd_audio_phase2(ldd_handle* h, const double* in_l_dev, const double* in_r_d
 int ldd_sync_peaks(ldd_handle* h, const double* sync_dev, long long n, long long start,
                    long long* peaks_dev, double* vals_dev, int cap, int* count_dev, void* stream);
 
+/* ---- field location (lddecode_core.py:518-787, 889-957, 962-1021, 1054-1133) -------------------- */
+#define LDD_FIELD_NOVSYNC 0    /* len(vsyncs) == 0: not a field, nextfieldoffset = start + 200 lines          */
+#define LDD_FIELD_SHORT 1      /* one vsync / too few peaks after the second: jump, not valid                 */
+#define LDD_FIELD_LOCATED 2    /* linelocs1 / linebad produced                                                */
+#define LDD_FIELD_BADLINES 3   /* compute_linelocs raised in the reference: field invalid                     */
+#define LDD_FIELD_CRASH 4      /* the reference itself raises out of Field.__init__ (vsync in the first 11 peaks) */
+
+typedef struct ldd_field {
+    int stage;                 /* LDD_FIELD_* */
+    int istop;
+    int linecount;             /* 262/263 NTSC, 312/313 PAL */
+    int npeaks;
+    int nvsyncs;
+    int vsyncs[4][3];          /* first four rows of Field.vsyncs: (peak index, line0 peak index, istop) */
+    long long nextfieldoffset; /* Field.nextfieldoffset */
+    long long tbcstart;        /* Field.tbcstart */
+    double med_hsync;
+    double hsync_tolerance;
+} ldd_field;
+
+/* HOST function (no device work): Field.determine_vsyncs / determine_field / compute_linelocs and the
+ * early-outs of Field.__init__ on one field window.  peaks/vals are HOST arrays: the window's peak
+ * list (indices relative to the window) and demod_sync at those peaks; window_len = len(demod_sync)
+ * of the window; start = Field.start.  linelocs1/linebad (HOST, ll_cap >= linecount+4 entries)
+ * receive Field.linelocs1 / Field.linebad when stage == LDD_FIELD_LOCATED. */
+int ldd_field_locate(ldd_handle* h, const long long* peaks, const double* vals, int npeaks,
+                     long long window_len, long long start, ldd_field* out,
+                     double* linelocs1, unsigned char* linebad, int ll_cap);
+
+/* Field.refine_linelocs_hsync, batched: field f works on the window that starts at plane index
+ * base_dev[f] and is winlen_dev[f] long; line tables are [nfields][ll_stride]; status_dev[f] (caller
+ * zeroed) gets bit 1 when the reference would have raised (field invalid). */
+int ldd_refine_hsync(ldd_handle* h, const float* d05_dev, long long n, const long long* base_dev,
+                     const long long* winlen_dev, const int* linecount_dev, int nfields, int ll_stride,
+                     const double* linelocs1_dev, const unsigned char* linebad_dev, double* linelocs2_dev,
+                     unsigned char* linebad_out_dev, int* status_dev, void* stream);
+
+/* FieldNTSC.refine_linelocs_burst (one pass; the reference runs it twice): linelocs_in -> linelocs_out,
+ * burstlevel_dev float32 [nfields][ll_stride].  status bit 2: a line's geometry was not covered. */
+int ldd_refine_burst(ldd_handle* h, const float* burst_dev, long long n, const long long* base_dev,
+                     const int* linecount_dev, int nfields, int ll_stride, const double* linelocs_in_dev,
+                     double* linelocs_out_dev, float* burstlevel_dev, int* status_dev, void* stream);
+
+/* FieldPAL.refine_linelocs_pilot.  status bit 3: window outside the plane / too many crossings. */
+int ldd_refine_pilot(ldd_handle* h, const float* demod_dev, const float* d05_dev, long long n,
+                     const long long* base_dev, const int* linecount_dev, int nfields, int ll_stride,
+                     const double* linelocs_in_dev, double* linelocs_out_dev, int* status_dev, void* stream);
+
 /* ---- kernel (5): per-line TBC resampling.  Field.downscale + lddutils.scale (not-a-knot cubic
  * spline per line) + the uint16 quantisation of FieldNTSC/FieldPAL.downscale(final=True)
  * (lddecode_core.py:789-812, 1023-1035, 1135-1159; lddutils.py:83-97), batched over fields.
  *   plane_dev[n]           float32 plane; plane value + plane_add = Hz (ire0 for LDD_P_DEMOD, 0 for LDD_P_BURST)
- *   linelocs_dev           [nfields][ll_stride] float64 line positions (plane coordinates); output line k of a
- *                          field spans linelocs[lineoffset+k] .. linelocs[lineoffset+k+1]
+ *   base_dev               [nfields] plane index of each field window's sample 0 (NULL: all 0)
+ *   linelocs_dev           [nfields][ll_stride] float64 line positions relative to the window; output line k of
+ *                          a field spans linelocs[lineoffset+k] .. linelocs[lineoffset+k+1]
+ *   lineloc_add            constant added to every line position first (FieldNTSC.apply_offsets,
+ *                          lddecode_core.py:1161-1162, 1186); 0 otherwise
  *   linecount_dev          [nfields] lines to produce per field (<= max_linecount)
  *   mode 0                 out_dev = float64 Hz, exactly what Field.downscale returns (dsout)
  *   mode 1                 out_dev = uint16 TBC samples; when burstlevel_dev (float32 [nfields][ll_stride]) is
@@ -184,9 +235,9 @@ int ldd_sync_peaks(ldd_handle* h, const double* sync_dev, long long n, long long
  *   out_stride             elements between consecutive fields in out_dev
  *   status_dev             [nfields] int, caller-zeroed; bit 0 set when a line's window leaves the plane or
  *                          is degenerate (the reference raises and marks the field invalid) */
-int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n, double plane_add,
+int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n, double plane_add, const long long* base_dev,
                    const double* linelocs_dev, int ll_stride, const int* linecount_dev, int nfields,
-                   int max_linecount, int lineoffset, int outwidth, int wow, int mode,
+                   int max_linecount, int lineoffset, double lineloc_add, int outwidth, int wow, int mode,
                    void* out_dev, long long out_stride, const float* burstlevel_dev, double colorlevel,
                    int* status_dev, void* stream);
 

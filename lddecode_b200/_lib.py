@@ -65,10 +65,27 @@ SIGNATURES = {
     "ldd_audio_phase2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldd_sync_peaks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int,
                                  C.c_void_p, C.c_void_p]),
-    "ldd_tbc_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
-                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p,
+    "ldd_tbc_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                 C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p,
                                  C.c_double, C.c_void_p, C.c_void_p]),
+    "ldd_field_locate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int]),
+    "ldd_refine_hsync": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldd_refine_burst": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldd_refine_pilot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
+
+
+class FieldInfo(C.Structure):
+    _fields_ = [("stage", C.c_int), ("istop", C.c_int), ("linecount", C.c_int), ("npeaks", C.c_int), ("nvsyncs", C.c_int),
+                ("vsyncs", (C.c_int * 3) * 4), ("nextfieldoffset", C.c_longlong), ("tbcstart", C.c_longlong),
+                ("med_hsync", C.c_double), ("hsync_tolerance", C.c_double)]
+
+
+FIELD_NOVSYNC, FIELD_SHORT, FIELD_LOCATED, FIELD_BADLINES, FIELD_CRASH = range(5)
 
 _cache = {}
 

@@ -146,6 +146,7 @@ void ldd_destroy(ldd_handle* h) {
     cudaFree(h->d_lpf2);
     cudaFree(h->d_WNfull);
     cudaFree(h->peak_ws);
+    cudaFree(h->pilot_ws);
     delete h;
 }
 

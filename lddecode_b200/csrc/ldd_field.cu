@@ -1,0 +1,723 @@
+// Field location: what Field.__init__ / FieldNTSC / FieldPAL do between the peak list and the
+// final resample (lddecode_core.py:518-787, 889-957, 962-1021, 1054-1133).
+//
+//   ldd_field_locate      HOST.  vsync detection, field parity, integer line numbering, gap
+//                         interpolation (get_hsync_median .. compute_linelocs, Field.__init__
+//                         early-outs).  Scalar decisions over <= ~600 peaks per field: SURVEY.md
+//                         section 8 (A7, A12) keeps this on the host; it reads only peak indices and
+//                         their demod_sync values.
+//   ldd_refine_hsync      DEVICE, one CTA per field: refine_linelocs_hsync (A8).
+//   ldd_refine_burst      DEVICE, one CTA per field: FieldNTSC.refine_linelocs_burst (A9), including
+//                         the spline resample of the burst plane at the 40 samples it looks at.
+//   ldd_refine_pilot      DEVICE, one CTA per field: FieldPAL.refine_linelocs_pilot (A10).
+//
+// numpy details that decide thresholds are reproduced: pairwise summation order of np.mean/np.std,
+// round-half-even of np.round, float32 burst levels.
+#include "ldd_internal.h"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace ldd {
+
+// numpy's pairwise summation (umath loops, PW_BLOCKSIZE = 128), which np.mean / np.std use.
+LDD_HD inline double np_sum(const double* a, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res += a[i];
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_sum(a, n2) + np_sum(a + n2, n - n2);
+}
+
+LDD_HD inline double np_mean(const double* a, int n) { return np_sum(a, n) / (double)n; }
+
+// lddutils.calczc on a window accessor: data(k) for k in [0, len).  Returns false for None.
+template <class F>
+LDD_HD inline bool calczc(F data, long long len, long long start, double target, int count, double* out) {
+    if (start < 0 || start >= len) return false;
+    long long end = start + (long long)count + 1;
+    if (end > len) end = len;
+    bool rising = data(start) < target;
+    long long x = -1;
+    for (long long k = start; k < end; ++k) {
+        double v = data(k);
+        if (rising ? (v >= target) : (v <= target)) { x = k; break; }
+    }
+    if (x < 0 || x == 0) return false;
+    double a = data(x - 1) - target, b = data(x) - target;
+    double y = -a / (-a + b);
+    *out = (double)(x - 1) + y;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A8: refine_linelocs_hsync (lddecode_core.py:715-787).  Threads own lines; thread 0 finishes the
+// sequential fix-ups.
+struct HsyncParams {
+    const float* d05;          // demod_05 plane (relative to ire0)
+    long long n;               // plane length
+    double ire0, hz_ire, freq; // freq in MHz
+    int linelen;
+    const long long* base;     // [nfields] plane index of the field window's sample 0
+    const long long* winlen;   // [nfields] window length (len(ds) of the reference)
+    const int* linecount;      // [nfields]
+    int ll_stride;
+    const double* linelocs1;   // [nfields][ll_stride]
+    const unsigned char* linebad_in;
+    double* linelocs2;
+    unsigned char* linebad_out;
+    int* status;               // bit 1: the reference would have raised (field invalid)
+};
+
+__global__ void __launch_bounds__(128) refine_hsync_kernel(const HsyncParams p) {
+    const int f = blockIdx.x;
+    const int nll = p.linecount[f] + 4;
+    const long long base = p.base[f], wlen = p.winlen[f];
+    const double* l1 = p.linelocs1 + (size_t)f * p.ll_stride;
+    const unsigned char* bad_in = p.linebad_in + (size_t)f * p.ll_stride;
+    double* l2 = p.linelocs2 + (size_t)f * p.ll_stride;
+    unsigned char* bad = p.linebad_out + (size_t)f * p.ll_stride;
+    const double fq = p.freq;
+    auto hz = [&](double ire) { return p.ire0 + p.hz_ire * ire; };
+    auto d = [&](long long k) -> double { return (double)p.d05[base + k] + p.ire0; };
+    // window length visible to the reference = min(wlen, plane end)
+    long long len = wlen;
+    if (base + len > p.n) len = p.n - base;
+
+    for (int i = threadIdx.x; i < nll; i += blockDim.x) {
+        double ll = l1[i];
+        if (i < 9) ll -= 200;
+        const double ll1 = ll;
+        bool isbad = bad_in[i] != 0;
+        double zc;
+        bool have = calczc(d, len, (long long)ll, hz(-20), 400, &zc);
+        double out = ll;
+        if (have && !isbad) {
+            out = zc;
+            if (i >= 10) {
+                long long a1 = (long long)(ll1 - fq * 2), b1 = (long long)(ll1 + fq * 2);
+                long long a = (long long)(zc - fq * 1), b = (long long)(zc + fq * 3);
+                long long ab = (long long)(zc + fq * 1);
+                if (a1 < 0 || a < 0) { atomicOr(&p.status[f], 2); a1 = a1 < 0 ? 0 : a1; a = a < 0 ? 0 : a; }
+                if (b1 > len) b1 = len;
+                if (b > len) b = len;
+                double mn = 1e300, mx = -1e300, mn1 = 1e300, mx1 = -1e300, mnb = 1e300, mxb = -1e300;
+                for (long long k = a; k < b; ++k) {
+                    double v = d(k);
+                    mn = v < mn ? v : mn; mx = v > mx ? v : mx;
+                    if (k >= ab) { mnb = v < mnb ? v : mnb; mxb = v > mxb ? v : mxb; }
+                }
+                for (long long k = a1; k < b1; ++k) { double v = d(k); mn1 = v < mn1 ? v : mn1; mx1 = v > mx1 ? v : mx1; }
+                if ((mn < hz(-60) || mx > hz(20)) || (mn1 < hz(-60) || mx1 > hz(100)) || (mnb < hz(-10) || mxb > hz(10))) {
+                    isbad = true;
+                } else {
+                    const long long wl = b - a;
+                    double tmp[20];
+                    int n0 = (int)(wl < 20 ? wl : 20);
+                    for (int k = 0; k < n0; ++k) tmp[k] = d(a + k);
+                    double low = np_mean(tmp, n0);
+                    int n1 = (int)(wl < 100 ? 0 : (wl < 120 ? wl - 100 : 20));
+                    for (int k = 0; k < n1; ++k) tmp[k] = d(a + 100 + k);
+                    double high = np_mean(tmp, n1);
+                    auto w = [&](long long k) -> double { return d(a + k); };
+                    double zc2;
+                    if (!calczc(w, wl, 0, (low + high) / 2, (int)wl, &zc2)) {
+                        atomicOr(&p.status[f], 2);          // reference: TypeError -> field invalid
+                        isbad = true;
+                    } else {
+                        zc2 += (double)(long long)zc - fq * 1;
+                        if (fabs(zc2 - zc) < fq / 4) out = zc2; else isbad = true;
+                    }
+                }
+            }
+        } else {
+            isbad = true;
+        }
+        if (i < 10) out += fq * 4.72;
+        l2[i] = out;
+        bad[i] = isbad ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 11; i < nll; ++i)
+            if (bad[i]) { double gap = l2[i - 1] - l2[i - 2]; l2[i] = l2[i - 1] + gap; }
+        const double lo = p.linelen - fq * .2, hi = p.linelen + fq * .2;
+        for (int i = 9; i >= 0; --i) {
+            double gap = l2[i + 1] - l2[i];
+            if (!(gap >= lo && gap <= hi)) gap = p.linelen;
+            l2[i] = l2[i + 1] - gap;
+        }
+        for (int i = nll - 10; i < nll; ++i) {
+            double gap = l2[i] - l2[i - 1];
+            if (!(gap >= lo && gap <= hi)) gap = p.linelen;
+            l2[i] = l2[i - 1] + gap;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A9: FieldNTSC.refine_linelocs_burst (lddecode_core.py:1054-1133).
+struct BurstParams {
+    const float* burst;        // demod_burst plane (absolute Hz)
+    long long n;
+    double freq;
+    int linelen, outwidth;
+    const long long* base;
+    const int* linecount;
+    int ll_stride;
+    const double* linelocs_in;   // linelocs2 (first pass) or linelocs3 (second pass)
+    double* linelocs_out;
+    float* burstlevel;           // [nfields][ll_stride]
+    int* status;
+};
+
+constexpr int BURST_K = 32;          // same Green's function reach as the TBC kernel
+constexpr int BURST_FIRST = 20, BURST_N = 40;
+constexpr int BURST_WIN = 256;       // input samples staged per line (>= 2*(FIRST+N)*max step + K + margin)
+
+__global__ void __launch_bounds__(256) refine_burst_kernel(const BurstParams p) {
+    __shared__ double ys[8][BURST_WIN];
+    __shared__ double Ms[8][BURST_WIN];
+    __shared__ double bas[8][BURST_N];
+    __shared__ double taps[2 * BURST_K + 3];
+    __shared__ double phase[2][512];
+    __shared__ unsigned char haveph[512];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int linecount = p.linecount[f], nll = linecount + 4;
+    const long long base = p.base[f];
+    const double* lin = p.linelocs_in + (size_t)f * p.ll_stride;
+    double* lout = p.linelocs_out + (size_t)f * p.ll_stride;
+    float* level = p.burstlevel + (size_t)f * p.ll_stride;
+    const double r = -0.26794919243112270647, c = 0.28867513459481288225;
+    for (int m = tid; m <= 2 * (BURST_K + 1); m += blockDim.x) {
+        int k = m - (BURST_K + 1);
+        auto g = [&](int q) -> double { int a = q < 0 ? -q : q; return a > BURST_K ? 0.0 : c * pow(r, (double)a); };
+        taps[m] = 6.0 * (g(k - 1) - 2.0 * g(k) + g(k + 1));
+    }
+    for (int i = tid; i < 512; i += blockDim.x) { phase[0][i] = 0.0; phase[1][i] = 0.0; haveph[i] = 0; }
+    for (int i = tid; i < nll; i += blockDim.x) level[i] = 0.f;
+    __syncthreads();
+    const double hz_ire = 1700000.0 / 140.0;
+    const int W = p.outwidth;
+    for (int l = warp; l < linecount; l += 8) {
+        const double b = lin[l], e = lin[l + 1];
+        const long long ib = (long long)b, ie = (long long)e;
+        const int dist = (int)(ie - ib);
+        const double fb = b - (double)ib;
+        const double step = (((e - b) + fb) - fb) / (double)W;
+        const double wowf = (e - b) / (double)p.linelen;
+        // input samples needed: x in [fb + 20 step, fb + 59 step] -> indices i0..i1+1, M needs +-(K+1) more
+        const int i0 = (int)(fb + BURST_FIRST * step), i1 = (int)(fb + (BURST_FIRST + BURST_N - 1) * step) + 1;
+        const int s0 = i0 - (BURST_K + 1);                 // first staged sample (line-relative, may be < 0)
+        const int ns = (i1 - i0 + 1) + 2 * (BURST_K + 1);
+        bool ok = (b >= 0.0) && dist >= 3 && ns <= BURST_WIN && i1 <= dist && i0 >= 30 && ib + dist + 1 <= p.n;
+        if (!ok) {
+            // geometry the fast path does not cover (or the reference would raise): flag, leave the line "no burst"
+            if (lane == 0) atomicOr(&p.status[f], 4);
+            continue;
+        }
+        for (int k = lane; k < ns; k += 32) {
+            long long s = base + ib + s0 + k;
+            s = s < 0 ? 0 : (s >= p.n ? p.n - 1 : s);
+            ys[warp][k] = (double)p.burst[s];
+        }
+        __syncwarp();
+        const int nm = i1 - i0 + 1;                         // M[i0 .. i1]
+        for (int k = lane; k < nm; k += 32) {
+            double acc = 0.0;
+            const double* y = &ys[warp][k];                 // y[(i0+k) - (K+1)] is ys[k]
+            for (int m = 0; m <= 2 * (BURST_K + 1); ++m) acc += taps[m] * y[m];
+            Ms[warp][k] = acc;
+        }
+        __syncwarp();
+        for (int j = lane; j < BURST_N; j += 32) {
+            double x = (double)(BURST_FIRST + j) * step + fb;
+            int i = (int)x;
+            double t = x - (double)i, u = 1.0 - t;
+            double Mi = Ms[warp][i - i0], Mj = Ms[warp][i + 1 - i0];
+            double yi = ys[warp][i - s0], yj = ys[warp][i + 1 - s0];
+            double S = Mi * u * u * u / 6.0 + Mj * t * t * t / 6.0 + (yi - Mi / 6.0) * u + (yj - Mj / 6.0) * t;
+            bas[warp][j] = S * wowf;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double* ba = bas[warp];
+            double mean = np_mean(ba, BURST_N);
+            for (int k = 0; k < BURST_N; ++k) ba[k] -= mean;
+            double mx = 0.0;
+            for (int k = 0; k < BURST_N; ++k) mx = fabs(ba[k]) > mx ? fabs(ba[k]) : mx;
+            float lev = (float)mx;
+            // np.std(ba): mean again, deviations, pairwise sum of squares
+            double m2 = np_mean(ba, BURST_N);
+            double dev[BURST_N];
+            for (int k = 0; k < BURST_N; ++k) { double q = ba[k] - m2; dev[k] = q * q; }
+            double sd = sqrt(np_sum(dev, BURST_N) / (double)BURST_N);
+            const float hz_ire32 = (float)hz_ire;
+            if ((lev / hz_ire32) > 30.f || (sd / hz_ire) < 3) {
+                level[l] = 0.f;
+            } else {
+                level[l] = lev;
+                const double thr = (double)(lev * 0.6f);
+                double offF[BURST_N], offT[BURST_N];
+                int nF = 0, nT = 0;
+                auto dat = [&](long long k) -> double { return ba[k]; };
+                int bi = 0;
+                while (bi < BURST_N) {
+                    if (fabs(ba[bi]) > thr) {
+                        double zc;
+                        if (calczc(dat, BURST_N, bi, 0.0, 10, &zc)) {
+                            double off = zc - ((floor(zc / 4) * 4) - 1);
+                            if (off > 3.5) off -= 4;
+                            if (ba[bi] > 0) offT[nT++] = off; else offF[nF++] = off;
+                            bi = (int)zc;
+                        }
+                    }
+                    ++bi;
+                }
+                if (nF >= 3 && nT >= 3) {
+                    double mF = np_mean(offF + 1, nF - 2), mT = np_mean(offT + 1, nT - 2);
+                    if (l % 2) { phase[0][l] = 2 - mT; phase[1][l] = 2 - mF; }
+                    else { phase[0][l] = 2 - mF; phase[1][l] = 2 - mT; }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // medians of both columns over lines that produced a phase (lddecode_core.py:1112-1117)
+        double col[2][512];
+        int nc = 0;
+        for (int l = 0; l < nll; ++l)
+            if (phase[0][l] != 0 || phase[1][l] != 0) { col[0][nc] = phase[0][l]; col[1][nc] = phase[1][l]; ++nc; }
+        int group = 1;
+        if (nc > 0) {
+            double med[2];
+            for (int q = 0; q < 2; ++q) {
+                // insertion sort (nc <= 267)
+                for (int i = 1; i < nc; ++i) {
+                    double v = col[q][i];
+                    int j = i - 1;
+                    while (j >= 0 && col[q][j] > v) { col[q][j + 1] = col[q][j]; --j; }
+                    col[q][j + 1] = v;
+                }
+                med[q] = (nc & 1) ? col[q][nc / 2] : (col[q][nc / 2 - 1] + col[q][nc / 2]) / 2.0;
+            }
+            group = fabs(med[0]) < fabs(med[1]) ? 0 : 1;
+        }
+        for (int l = group; l < nll; l += 2) level[l] = -level[l];
+        const double k4 = p.freq / (4.0 * 315.0 / 88.0);
+        for (int l = 0; l < nll; ++l) {
+            double adj = phase[group][l];
+            double v = lin[l];
+            if (fabs(adj) > 2) level[l] = 0.f; else v -= adj * k4 * 1;
+            lout[l] = v;
+        }
+        for (int l = 2; l < nll - 1; ++l)
+            if (level[l] == 0.f) lout[l] = (lout[l - 1] + lout[l + 1]) / 2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A10: FieldPAL.refine_linelocs_pilot (lddecode_core.py:962-1021).
+struct PilotParams {
+    const float* demod;        // relative to ire0
+    const float* d05;          // relative to ire0
+    long long n;
+    double freq;
+    int linelen;
+    const long long* base;
+    const int* linecount;
+    int ll_stride;
+    const double* linelocs_in;
+    double* linelocs_out;
+    int* status;
+};
+
+constexpr int PILOT_MAXOFF = 48;     // zero crossings kept per line (4.7 us of a 3.75 MHz pilot: ~17)
+constexpr int PILOT_MAXLEN = 256;    // samples in 4.7 us (<= 54 MSPS)
+
+__global__ void __launch_bounds__(128) refine_pilot_kernel(const PilotParams p, double* ws_offsets /*[nfields][ll_stride][MAXOFF]*/,
+                                                           int* ws_count /*[nfields][ll_stride]*/) {
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int nll = p.linecount[f] + 4;
+    const long long base = p.base[f];
+    const double* lin = p.linelocs_in + (size_t)f * p.ll_stride;
+    double* lout = p.linelocs_out + (size_t)f * p.ll_stride;
+    double* offs = ws_offsets + (size_t)f * p.ll_stride * PILOT_MAXOFF;
+    int* cnt = ws_count + (size_t)f * p.ll_stride;
+    const double fq = p.freq;
+    for (int l = tid; l < nll; l += blockDim.x) {
+        long long a = (long long)(lin[l] - fq * 4.7), b = (long long)lin[l];
+        int len = (int)(b - a);
+        int n = 0;
+        double* my = offs + (size_t)l * PILOT_MAXOFF;
+        if (len <= 0 || len > PILOT_MAXLEN || base + a < 0 || base + b > p.n) {
+            atomicOr(&p.status[f], 8);
+            cnt[l] = 0;
+            continue;
+        }
+        // pilot = flip(demod - demod_05): pilot[i] = x[b-1-i]
+        auto pil = [&](long long i) -> double {
+            long long s = base + b - 1 - i;
+            return ((double)p.demod[s]) - ((double)p.d05[s]);       // the two ire0 offsets cancel
+        };
+        double adjfreq = fq;
+        if (l > 1) adjfreq /= (lin[l] - lin[l - 1]) / p.linelen;
+        int i = 0;
+        while (i < len) {
+            double v = pil(i);
+            if (v >= -300000 && v <= -100000) {
+                double zc;
+                if (calczc(pil, len, i, 0.0, 10, &zc)) {
+                    double zcp = zc / (adjfreq / 3.75);
+                    if (n < PILOT_MAXOFF) my[n] = zcp - floor(zcp);
+                    ++n;
+                    i = (int)(zc + 1);
+                }
+            }
+            ++i;
+        }
+        if (n > PILOT_MAXOFF) { atomicOr(&p.status[f], 8); n = PILOT_MAXOFF; }
+        // "if len(offsets) >= 3": the dict has l+1 entries at this point
+        if (l + 1 >= 3) {
+            // offsets[l] = offsets[l][1:-1]
+            int m = n >= 2 ? n - 2 : 0;
+            for (int k = 0; k < m; ++k) my[k] = my[k + 1];
+            n = m;
+        } else {
+            n = 0;
+        }
+        cnt[l] = n;
+    }
+    __syncthreads();
+    // median of all offsets (np.median(alloffsets)): exact order statistics by bisection on the value
+    // (offsets are fractional parts in [0, 1)), the counting spread over the CTA.
+    __shared__ int s_cnt;
+    __shared__ double s_min[128];
+    __shared__ double s_tgt;
+    int total = 0;
+    for (int l = 0; l < nll; ++l) total += cnt[l];
+    auto kth = [&](int k) -> double {
+        double lo = -1.0, hi = 1.0;
+        for (int it = 0; it < 70; ++it) {
+            double mid = 0.5 * (lo + hi);
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            int c = 0;
+            for (int l = tid; l < nll; l += blockDim.x) {
+                const double* my = offs + (size_t)l * PILOT_MAXOFF;
+                for (int q = 0; q < cnt[l]; ++q) c += my[q] <= mid;
+            }
+            atomicAdd(&s_cnt, c);
+            __syncthreads();
+            if (s_cnt >= k + 1) hi = mid; else lo = mid;
+            __syncthreads();
+        }
+        double best = 2.0;
+        for (int l = tid; l < nll; l += blockDim.x) {
+            const double* my = offs + (size_t)l * PILOT_MAXOFF;
+            for (int q = 0; q < cnt[l]; ++q) if (my[q] > lo && my[q] < best) best = my[q];
+        }
+        s_min[tid] = best;
+        __syncthreads();
+        for (int i = 0; i < (int)blockDim.x; ++i) best = s_min[i] < best ? s_min[i] : best;
+        __syncthreads();
+        return best;
+    };
+    double tgt = 0;
+    if (total > 0) {
+        double med = (total & 1) ? kth(total / 2) : (kth(total / 2 - 1) + kth(total / 2)) / 2.0;
+        if (med >= 0.25 && med <= 0.75) tgt = .5;
+    }
+    if (tid == 0) s_tgt = tgt;
+    __syncthreads();
+    tgt = s_tgt;
+    for (int l = tid; l < nll; l += blockDim.x) {
+        double v = lin[l];
+        int n = cnt[l];
+        if (n > 0) {
+            double* my = offs + (size_t)l * PILOT_MAXOFF;
+            for (int i = 1; i < n; ++i) {          // sort the (short) list for its median
+                double x = my[i];
+                int j = i - 1;
+                while (j >= 0 && my[j] > x) { my[j + 1] = my[j]; --j; }
+                my[j + 1] = x;
+            }
+            double med = (n & 1) ? my[n / 2] : (my[n / 2 - 1] + my[n / 2]) / 2.0;
+            v += (tgt - med) * (fq / 3.75) * .25;
+        }
+        lout[l] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host: A7 + the early-outs of Field.__init__.
+namespace {
+
+double median_of(std::vector<double> v) {
+    size_t n = v.size();
+    if (n == 0) return NAN;
+    std::sort(v.begin(), v.end());
+    return (n & 1) ? v[n / 2] : (v[n / 2 - 1] + v[n / 2]) / 2.0;
+}
+
+struct Locator {
+    const long long* pk;     // window-relative peak positions
+    const double* val;
+    int np;
+    long long wlen;
+    int linelen;
+    bool pal;
+    double med = 0, tol = 0;
+
+    bool regular(long long k) const {          // is_regular_hsync, lddecode_core.py:534-542
+        if (k < 0) k += np;                    // python negative index (never reached in practice)
+        if (k < 0 || k >= np) return false;
+        if (pk[k] > wlen) return false;
+        return val[k] >= med - tol && val[k] <= med + tol;
+    }
+};
+
+}  // namespace
+}  // namespace ldd
+
+using namespace ldd;
+
+extern "C" int ldd_field_locate(ldd_handle* h, const long long* peaks, const double* vals, int npeaks,
+                                long long window_len, long long start, ldd_field* out,
+                                double* linelocs1, unsigned char* linebad, int ll_cap) {
+    if (!h || !peaks || !vals || !out || npeaks < 0) return LDD_EINVAL;
+    const ldd_config& c = h->cfg;
+    memset(out, 0, sizeof *out);
+    out->npeaks = npeaks;
+    const int L = c.linelen;
+    Locator lc{peaks, vals, npeaks, window_len, L, c.system == LDD_SYSTEM_PAL};
+    // --- determine_vsyncs (lddecode_core.py:590-636)
+    std::vector<std::array<long long, 3>> vs;
+    if (npeaks >= 200) {
+        std::vector<double> lv;
+        for (int i = 0; i < npeaks; ++i)
+            if (vals[i] >= 0.6 && vals[i] <= 0.8) lv.push_back(vals[i]);
+        lc.med = median_of(lv);
+        double sd = NAN;
+        if (!lv.empty()) {
+            double mean = np_mean(lv.data(), (int)lv.size());
+            std::vector<double> dev(lv.size());
+            for (size_t i = 0; i < lv.size(); ++i) { double q = lv[i] - mean; dev[i] = q * q; }
+            sd = std::sqrt(np_sum(dev.data(), (int)dev.size()) / (double)dev.size());
+        }
+        lc.tol = std::max(sd * 2, .01);          // python max(nan, .01) == nan; std::max(nan, .01) == nan too (first arg kept)
+        out->med_hsync = lc.med;
+        out->hsync_tolerance = lc.tol;
+        double prev = 1.0;
+        for (int i = 0; i < npeaks; ++i) {
+            double v = vals[i];
+            if (v > .9 && prev < lc.med - lc.tol * 2) {
+                // determine_field (lddecode_core.py:544-588)
+                if (i < 11) { out->stage = LDD_FIELD_CRASH; return LDD_OK; }      // the reference raises TypeError here
+                int vote = 0;
+                long long line0 = -1;
+                bool have0 = false;
+                for (int k = i - 1; k > i - 20; --k) {
+                    if (lc.regular(k)) {
+                        line0 = k; have0 = true;
+                        long long kk = k < 0 ? k + npeaks : k;
+                        if (kk + 1 < npeaks && (peaks[kk + 1] - peaks[kk]) > L * .75) vote -= 1;
+                        break;
+                    }
+                }
+                for (int k = i; k < i + 20; ++k) {
+                    if (lc.regular(k)) {
+                        if (k >= 1 && (peaks[k] - peaks[k - 1]) > L * .75) vote += lc.pal ? -1 : 1;
+                        break;
+                    }
+                }
+                if (lc.pal) vote += 1;
+                if (have0) vs.push_back({(long long)i, line0, (long long)vote});
+            }
+            prev = v;
+        }
+        if (vs.size() >= 2) {
+            std::vector<std::array<long long, 3>> raw = vs;
+            for (size_t i = 0; i < vs.size(); ++i) {
+                if (vs[i][2] == 0) {
+                    vs[i][1] = -1;
+                    if (i + 1 < vs.size() && raw[i + 1][2] != 0) vs[i][2] = -vs[i + 1][2];
+                    else if (i >= 1 && raw[i - 1][2] != 0) vs[i][2] = -vs[i - 1][2];
+                }
+                if (vs[i][1] <= 0) vs[i][1] = vs[i][0] - (lc.pal ? 6 : 7);
+                vs[i][2] = vs[i][2] < 0 ? 1 : 0;
+            }
+        }
+    }
+    out->nvsyncs = (int)vs.size();
+    for (size_t i = 0; i < vs.size() && i < 4; ++i)
+        for (int q = 0; q < 3; ++q) out->vsyncs[i][q] = (int)vs[i][q];
+    // --- Field.__init__ early-outs (lddecode_core.py:909-926)
+    if (vs.empty()) {
+        out->stage = LDD_FIELD_NOVSYNC;
+        out->nextfieldoffset = start + (long long)L * 200;
+        return LDD_OK;
+    }
+    auto pyidx = [&](long long k) -> long long { return k < 0 ? k + npeaks : k; };
+    if (vs.size() == 1 || npeaks < vs[1][1] + 4) {
+        long long k = pyidx(vs[0][1] - 10);
+        long long jump = (k >= 0 && k < npeaks) ? peaks[k] : 0;
+        out->stage = LDD_FIELD_SHORT;
+        out->nextfieldoffset = jump != 0 ? start + jump : start + (long long)L * 240;
+        return LDD_OK;
+    }
+    {
+        long long k = pyidx(vs[1][1] - 10);
+        if (k < 0 || k >= npeaks) { out->stage = LDD_FIELD_CRASH; return LDD_OK; }
+        out->nextfieldoffset = peaks[k];
+        out->tbcstart = peaks[k];
+    }
+    // the raw vote sign of vsync 0 decides the parity (after the loop above it is 0/1 when there were >= 2)
+    out->istop = (int)vs[0][2];
+    const int frame_lines = lc.pal ? 625 : 525;
+    out->linecount = frame_lines / 2 + (out->istop ? 1 : 0);
+    const int nll = out->linecount + 4;
+    if (!linelocs1 || !linebad || ll_cap < nll) return LDD_ECAP;
+    // --- compute_linelocs (lddecode_core.py:638-713)
+    std::vector<double> found(nll + 64, 0.0);
+    std::vector<char> has(nll + 64, 0);
+    // line numbers can be negative (lines before line0) or beyond the table: keep a map for the ones we need
+    std::vector<std::pair<long long, double>> extra;          // (linenum, loc) outside [0, nll+63]
+    auto setloc = [&](long long n, double v) {
+        if (n >= 0 && n < (long long)found.size()) { found[n] = v; has[n] = 1; }
+        else {
+            for (auto& e : extra) if (e.first == n) { e.second = v; return; }
+            extra.push_back({n, v});
+        }
+    };
+    auto getloc = [&](long long n, double* v) -> bool {
+        if (n >= 0 && n < (long long)found.size()) { if (has[n]) { *v = found[n]; return true; } return false; }
+        for (auto& e : extra) if (e.first == n) { *v = e.second; return true; }
+        return false;
+    };
+    std::vector<double> lens{(double)L};
+    long long prev_i = -1, prev_n = 0;
+    const long long v0line0 = pyidx(vs[0][1]);
+    if (v0line0 < 0 || v0line0 >= npeaks) { out->stage = LDD_FIELD_BADLINES; return LDD_OK; }
+    for (long long i = 0; i < vs[1][1]; ++i) {
+        size_t m = lens.size() < 25 ? lens.size() : 25;
+        double medlen = median_of(std::vector<double>(lens.end() - m, lens.end()));
+        if (!lc.regular(i)) continue;
+        long long n;
+        if (prev_i >= 0) {
+            long long gap = peaks[i] - peaks[prev_i];
+            double ratio = (double)gap / (double)L;
+            if (ratio >= .98 && ratio <= 1.02) { lens.push_back((double)gap); n = prev_n + 1; }
+            else n = prev_n + (long long)std::nearbyint((double)gap / medlen);
+        } else {
+            n = (long long)std::nearbyint((double)(peaks[i] - peaks[v0line0]) / medlen);
+        }
+        setloc(n, (double)peaks[i]);
+        prev_i = i; prev_n = n;
+    }
+    std::vector<double> filled(nll + 1, 0.0);
+    std::vector<char> wasfound(nll + 1, 0);
+    for (int l = 1; l < out->linecount + 5; ++l) {
+        double v;
+        if (getloc(l, &v)) { filled[l] = v; wasfound[l] = 1; continue; }
+        bool hb = false, ha = false;
+        long long before = 0, after = 0;
+        double vb = 0, va = 0;
+        for (long long i = l; i > -10; --i) if (getloc(i, &vb)) { before = i; hb = true; break; }
+        for (long long i = l; i < out->linecount + 1; ++i) if (getloc(i, &va)) { after = i; ha = true; break; }
+        if (!hb) {
+            if (!ha) { out->stage = LDD_FIELD_BADLINES; return LDD_OK; }      // reference: KeyError -> "unable to decode frame"
+            filled[l] = va - (double)L * (double)(after - l);
+        } else if (ha) {
+            double avg = (va - vb) / (double)(after - before);
+            filled[l] = vb + avg * (double)(l - before);
+        } else {
+            // avglen = linelocs[prev_valid] - linelocs2[prev_valid - 1]
+            double pm1;
+            long long q = before - 1;
+            if (q >= 1 && q <= nll) pm1 = filled[q];
+            else if (!getloc(q, &pm1)) { out->stage = LDD_FIELD_BADLINES; return LDD_OK; }
+            double avg = vb - pm1;
+            filled[l] = vb + avg * (double)(l - before);
+        }
+    }
+    for (int l = 1; l < out->linecount + 5; ++l) {
+        linelocs1[l - 1] = filled[l];
+        linebad[l - 1] = wasfound[l] ? 0 : 1;
+    }
+    for (int i = 0; i < 10 && i < nll; ++i) linebad[i] = 0;
+    out->stage = LDD_FIELD_LOCATED;
+    return LDD_OK;
+}
+
+extern "C" int ldd_refine_hsync(ldd_handle* h, const float* d05_dev, long long n, const long long* base_dev,
+                                const long long* winlen_dev, const int* linecount_dev, int nfields, int ll_stride,
+                                const double* linelocs1_dev, const unsigned char* linebad_dev, double* linelocs2_dev,
+                                unsigned char* linebad_out_dev, int* status_dev, void* stream) {
+    if (!h || !d05_dev || !base_dev || !winlen_dev || !linecount_dev || !linelocs1_dev || !linebad_dev || !linelocs2_dev ||
+        !linebad_out_dev || !status_dev) return LDD_EINVAL;
+    if (nfields <= 0) return LDD_OK;
+    HsyncParams p;
+    p.d05 = d05_dev; p.n = n; p.ire0 = h->cfg.ire0; p.hz_ire = h->cfg.hz_ire; p.freq = h->cfg.freq_hz / 1e6;
+    p.linelen = h->cfg.linelen; p.base = base_dev; p.winlen = winlen_dev; p.linecount = linecount_dev; p.ll_stride = ll_stride;
+    p.linelocs1 = linelocs1_dev; p.linebad_in = linebad_dev; p.linelocs2 = linelocs2_dev; p.linebad_out = linebad_out_dev;
+    p.status = status_dev;
+    LDD_LAUNCH(refine_hsync_kernel, dim3(nfields), dim3(128), 0, (cudaStream_t)stream, p);
+    return cudaGetLastError() == cudaSuccess ? LDD_OK : LDD_ECUDA;
+}
+
+extern "C" int ldd_refine_burst(ldd_handle* h, const float* burst_dev, long long n, const long long* base_dev,
+                                const int* linecount_dev, int nfields, int ll_stride, const double* linelocs_in_dev,
+                                double* linelocs_out_dev, float* burstlevel_dev, int* status_dev, void* stream) {
+    if (!h || !burst_dev || !base_dev || !linecount_dev || !linelocs_in_dev || !linelocs_out_dev || !burstlevel_dev || !status_dev)
+        return LDD_EINVAL;
+    if (nfields <= 0) return LDD_OK;
+    if (ll_stride > 512) return LDD_EINVAL;
+    BurstParams p;
+    p.burst = burst_dev; p.n = n; p.freq = h->cfg.freq_hz / 1e6; p.linelen = h->cfg.linelen; p.outwidth = h->cfg.outlinelen;
+    p.base = base_dev; p.linecount = linecount_dev; p.ll_stride = ll_stride; p.linelocs_in = linelocs_in_dev;
+    p.linelocs_out = linelocs_out_dev; p.burstlevel = burstlevel_dev; p.status = status_dev;
+    LDD_LAUNCH(refine_burst_kernel, dim3(nfields), dim3(256), 0, (cudaStream_t)stream, p);
+    return cudaGetLastError() == cudaSuccess ? LDD_OK : LDD_ECUDA;
+}
+
+extern "C" int ldd_refine_pilot(ldd_handle* h, const float* demod_dev, const float* d05_dev, long long n,
+                                const long long* base_dev, const int* linecount_dev, int nfields, int ll_stride,
+                                const double* linelocs_in_dev, double* linelocs_out_dev, int* status_dev, void* stream) {
+    if (!h || !demod_dev || !d05_dev || !base_dev || !linecount_dev || !linelocs_in_dev || !linelocs_out_dev || !status_dev)
+        return LDD_EINVAL;
+    if (nfields <= 0) return LDD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t need = (size_t)nfields * ll_stride * (PILOT_MAXOFF * sizeof(double) + sizeof(int)) + 64;
+    if (need > h->pilot_ws_bytes) {
+        if (h->pilot_ws) { cudaStreamSynchronize(st); cudaFree(h->pilot_ws); h->pilot_ws = nullptr; }
+        if (cudaMalloc(&h->pilot_ws, need) != cudaSuccess) { h->pilot_ws_bytes = 0; h->err = "cudaMalloc pilot workspace"; return LDD_ENOMEM; }
+        h->pilot_ws_bytes = need;
+    }
+    double* offs = (double*)h->pilot_ws;
+    int* cnt = (int*)((char*)h->pilot_ws + (size_t)nfields * ll_stride * PILOT_MAXOFF * sizeof(double));
+    PilotParams p;
+    p.demod = demod_dev; p.d05 = d05_dev; p.n = n; p.freq = h->cfg.freq_hz / 1e6; p.linelen = h->cfg.linelen;
+    p.base = base_dev; p.linecount = linecount_dev; p.ll_stride = ll_stride; p.linelocs_in = linelocs_in_dev;
+    p.linelocs_out = linelocs_out_dev; p.status = status_dev;
+    LDD_LAUNCH(refine_pilot_kernel, dim3(nfields), dim3(128), 0, st, p, offs, cnt);
+    return cudaGetLastError() == cudaSuccess ? LDD_OK : LDD_ECUDA;
+}

@@ -82,4 +82,6 @@ struct ldd_handle {
     // workspace of the peak search (grown on demand)
     void* peak_ws = nullptr;
     size_t peak_ws_bytes = 0;
+    void* pilot_ws = nullptr;
+    size_t pilot_ws_bytes = 0;
 };

@@ -23,10 +23,12 @@ struct TbcParams {
     const float* plane;       // input plane
     long long n;              // its length
     double plane_add;         // plane value + plane_add = Hz (ire0 for demod/demod_05, 0 otherwise)
-    const double* linelocs;   // [nfields][ll_stride] line positions in plane coordinates
+    const long long* base;    // [nfields] plane index of the field window's sample 0 (or NULL)
+    const double* linelocs;   // [nfields][ll_stride] line positions relative to the window
     const int* linecount;     // [nfields]
     int ll_stride;
     int lineoffset;           // first line = linelocs[lineoffset]
+    double lineloc_add;       // added to every line position (FieldNTSC.apply_offsets, lddecode_core.py:1161-1162)
     int outwidth;
     int wow;                  // multiply by (e-b)/linelen
     int linelen;
@@ -51,12 +53,13 @@ __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
     const int linecount = p.linecount[field];
     if (line >= linecount) return;
     const double* ll = p.linelocs + (size_t)field * p.ll_stride;
-    const double b = ll[p.lineoffset + line], e = ll[p.lineoffset + line + 1];
+    const double b = ll[p.lineoffset + line] + p.lineloc_add, e = ll[p.lineoffset + line + 1] + p.lineloc_add;
     const long long ib = (long long)b, ie = (long long)e;
     const int dist = (int)(ie - ib);
     const int W = p.outwidth;
     char* outbase = (char*)p.out;
-    if (!(b >= 0.0) || dist < 3 || dist > TBC_MAXD || ib + dist + 1 > p.n) {
+    const long long base = p.base ? p.base[field] : 0;
+    if (!(b >= 0.0) || dist < 3 || dist > TBC_MAXD || base + ib + dist + 1 > p.n || base + ib < 0) {
         if (tid == 0) atomicOr(&p.status[field], 1);
         return;
     }
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
     }
     // stage the samples (relative values; the spline is linear so plane_add is added at the end)
     for (int i = tid; i < dist + 1 + 2 * TBC_H; i += TBC_THREADS) {
-        long long s = ib - TBC_H + i;
+        long long s = base + ib - TBC_H + i;
         s = s < 0 ? 0 : (s >= p.n ? p.n - 1 : s);
         ys[i] = (double)p.plane[s];
     }
@@ -143,8 +146,8 @@ __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
 using namespace ldd;
 
 extern "C" int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n, double plane_add,
-                              const double* linelocs_dev, int ll_stride, const int* linecount_dev, int nfields,
-                              int max_linecount, int lineoffset, int outwidth, int wow, int mode,
+                              const long long* base_dev, const double* linelocs_dev, int ll_stride, const int* linecount_dev, int nfields,
+                              int max_linecount, int lineoffset, double lineloc_add, int outwidth, int wow, int mode,
                               void* out_dev, long long out_stride, const float* burstlevel_dev, double colorlevel,
                               int* status_dev, void* stream) {
     if (!h || !plane_dev || !linelocs_dev || !linecount_dev || !out_dev || !status_dev) return LDD_EINVAL;
@@ -153,8 +156,9 @@ extern "C" int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n
     const ldd_config& c = h->cfg;
     TbcParams p;
     p.plane = plane_dev; p.n = n; p.plane_add = plane_add;
+    p.base = base_dev;
     p.linelocs = linelocs_dev; p.linecount = linecount_dev; p.ll_stride = ll_stride;
-    p.lineoffset = lineoffset; p.outwidth = outwidth; p.wow = wow; p.linelen = c.linelen; p.mode = mode;
+    p.lineoffset = lineoffset; p.lineloc_add = lineloc_add; p.outwidth = outwidth; p.wow = wow; p.linelen = c.linelen; p.mode = mode;
     p.ire0 = c.ire0; p.hz_ire = c.hz_ire; p.vsync_ire = c.vsync_ire;
     if (c.system == LDD_SYSTEM_NTSC) {            // lddecode_core.py:1141-1142
         p.out_scale = (double)(0xc800 - 0x0400) / (100.0 - c.vsync_ire);

@@ -1,0 +1,388 @@
+"""Field / FieldNTSC / FieldPAL: host-side mirrors of the reference's field classes
+(lddecode_core.py:489-1191) on top of the CUDA kernels, plus the batched core they share with the
+whole-capture pipeline (pipeline.py).
+
+What runs where:
+  sync-peak chase (get_syncpeaks)                         -> ldd_sync_peaks      (device)
+  vsync detection / parity / line numbering (A7)           -> ldd_field_locate    (host C++, scalar)
+  refine_linelocs_hsync                                    -> ldd_refine_hsync    (device)
+  FieldNTSC.refine_linelocs_burst x2                       -> ldd_refine_burst    (device)
+  FieldPAL.refine_linelocs_pilot                           -> ldd_refine_pilot    (device)
+  downscale / scale / uint16 quantisation                  -> ldd_tbc_fields      (device)
+  Philips code (VBI) decode, 3 lines per field             -> host numpy on three fetched line windows
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .rfdecode import DeviceDemod
+
+LL_STRIDE = 320          # >= linecount + 4 (PAL: 317)
+
+
+def _h(x):
+    return x.ctypes.data_as(C.c_void_p)
+
+
+class FieldBatch:
+    """Per-field tables of a batch of fields that share one set of device planes."""
+
+    def __init__(self, rf, nfields):
+        self.rf = rf
+        self.n = nfields
+        self.info = [None] * nfields
+        self.base = np.zeros(nfields, dtype=np.int64)        # plane index of each window's sample 0
+        self.winlen = np.zeros(nfields, dtype=np.int64)
+        self.linecount = np.zeros(nfields, dtype=np.int32)
+        self.linelocs1 = np.zeros((nfields, LL_STRIDE), dtype=np.float64)
+        self.linebad = np.zeros((nfields, LL_STRIDE), dtype=np.uint8)
+        self.peaks = [None] * nfields                         # window-relative peak lists (host)
+        self.vals = [None] * nfields
+
+
+def sync_peaks_device(rf, sync_buf, n, start=0):
+    """Field.get_syncpeaks on a device float64 demod_sync plane -> (peaks int64, values float64) on the host."""
+    be = rf._be
+    cap = int(n // int(rf.linelen * .4)) + 8
+    pk = be.empty(cap, np.int64)
+    vl = be.empty(cap, np.float64)
+    cnt = be.zeros(2, np.int32)
+    rf._check(be.lib.ldd_sync_peaks(rf._h, be.ptr(sync_buf), int(n), int(start), be.ptr(pk), be.ptr(vl), cap,
+                                    be.ptr(cnt), be.stream()))
+    be.synchronize()
+    c = int(be.to_host(cnt)[0])
+    return be.to_host(pk)[:c].copy(), be.to_host(vl)[:c].copy()
+
+
+def locate(rf, peaks, vals, window_len, start=0):
+    """ldd_field_locate for one window -> (FieldInfo, linelocs1, linebad)."""
+    info = _lib.FieldInfo()
+    peaks = np.ascontiguousarray(peaks, dtype=np.int64)
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    ll = np.zeros(LL_STRIDE, dtype=np.float64)
+    bad = np.zeros(LL_STRIDE, dtype=np.uint8)
+    rf._check(rf._be.lib.ldd_field_locate(rf._h, _h(peaks), _h(vals), len(peaks), int(window_len), int(start),
+                                          C.byref(info), _h(ll), _h(bad), LL_STRIDE))
+    return info, ll, bad
+
+
+class RefinedBatch:
+    pass
+
+
+def refine_and_tbc(rf, planes, plane_len, batch, colorlevel=1.45, colorphase=91.5, want_intermediates=True):
+    """Device part of FieldNTSC/FieldPAL.__init__ for every located field of `batch`.
+
+    planes: dict name -> device buffer (as in DeviceDemod.planes).  Returns a RefinedBatch with
+    device buffers (dspicture uint16 [n][out_stride]) and, when asked, host copies of the line tables."""
+    be, lib = rf._be, rf._be.lib
+    n = batch.n
+    out = RefinedBatch()
+    W = rf.SysParams['outlinelen']
+    maxlc = int(batch.linecount.max()) if n else 0
+    out.out_stride = (rf.SysParams['frame_lines'] // 2 + 1) * W
+    d_base = be.to_device(batch.base)
+    d_win = be.to_device(batch.winlen)
+    d_lc = be.to_device(batch.linecount)
+    d_l1 = be.to_device(batch.linelocs1.reshape(-1))
+    d_bad = be.to_device(batch.linebad.reshape(-1))
+    d_l2 = be.empty(n * LL_STRIDE, np.float64)
+    d_bad2 = be.empty(n * LL_STRIDE, np.uint8)
+    d_status = be.zeros(n, np.int32)
+    st = be.stream()
+    rf._check(lib.ldd_refine_hsync(rf._h, be.ptr(planes['demod_05']), int(plane_len), be.ptr(d_base), be.ptr(d_win),
+                                   be.ptr(d_lc), n, LL_STRIDE, be.ptr(d_l1), be.ptr(d_bad), be.ptr(d_l2), be.ptr(d_bad2),
+                                   be.ptr(d_status), st))
+    out.d_linelocs2, out.d_linebad = d_l2, d_bad2
+    d_pic = be.empty(n * out.out_stride, np.uint16)
+    ire0 = float(rf.SysParams['ire0'])
+    if rf.system == 'NTSC':
+        d_l3 = be.empty(n * LL_STRIDE, np.float64)
+        d_l4 = be.empty(n * LL_STRIDE, np.float64)
+        d_bl = be.empty(n * LL_STRIDE, np.float32)
+        for src, dst in ((d_l2, d_l3), (d_l3, d_l4)):
+            rf._check(lib.ldd_refine_burst(rf._h, be.ptr(planes['demod_burst']), int(plane_len), be.ptr(d_base), be.ptr(d_lc),
+                                           n, LL_STRIDE, be.ptr(src), be.ptr(dst), be.ptr(d_bl), be.ptr(d_status), st))
+        # apply_offsets(linelocs4, shift33 - 8) (lddecode_core.py:1161-1162, 1185-1186)
+        shift33 = colorphase * (np.pi / 180)
+        out.lineloc_add = (shift33 - 8) * (rf.freq / (4 * 315 / 88))
+        rf._check(lib.ldd_tbc_fields(rf._h, be.ptr(planes['demod']), int(plane_len), ire0, be.ptr(d_base), be.ptr(d_l4),
+                                     LL_STRIDE, be.ptr(d_lc), n, maxlc, 1, out.lineloc_add, W, 1, 1, be.ptr(d_pic),
+                                     out.out_stride, be.ptr(d_bl), float(colorlevel), be.ptr(d_status), st))
+        out.d_linelocs3, out.d_linelocs4, out.d_burstlevel, out.d_final = d_l3, d_l4, d_bl, d_l4
+    else:
+        d_lp = be.empty(n * LL_STRIDE, np.float64)
+        rf._check(lib.ldd_refine_pilot(rf._h, be.ptr(planes['demod']), be.ptr(planes['demod_05']), int(plane_len),
+                                       be.ptr(d_base), be.ptr(d_lc), n, LL_STRIDE, be.ptr(d_l2), be.ptr(d_lp),
+                                       be.ptr(d_status), st))
+        out.lineloc_add = 0.0
+        rf._check(lib.ldd_tbc_fields(rf._h, be.ptr(planes['demod']), int(plane_len), ire0, be.ptr(d_base), be.ptr(d_lp),
+                                     LL_STRIDE, be.ptr(d_lc), n, maxlc, 3, 0.0, W, 1, 1, be.ptr(d_pic), out.out_stride,
+                                     None, float(colorlevel), be.ptr(d_status), st))
+        out.d_final = d_lp
+    out.d_pic, out.d_status, out.d_base, out.d_lc = d_pic, d_status, d_base, d_lc
+    if want_intermediates:
+        be.synchronize()
+        out.status = be.to_host(d_status)
+        out.linelocs2 = be.to_host(d_l2).reshape(n, LL_STRIDE)
+        out.linebad = be.to_host(d_bad2).reshape(n, LL_STRIDE)
+        out.final = be.to_host(out.d_final).reshape(n, LL_STRIDE)
+        if rf.system == 'NTSC':
+            out.linelocs3 = be.to_host(d_l3).reshape(n, LL_STRIDE)
+            out.linelocs4 = be.to_host(d_l4).reshape(n, LL_STRIDE)
+            out.burstlevel = be.to_host(d_bl).reshape(n, LL_STRIDE)
+    return out
+
+
+# ---- VBI (lddecode_core.py:814-884): scalar host code on three fetched lines per field -----------
+def _calczc(data, start, target, count=10):
+    s = int(start)
+    n = int(count + 1)
+    if s < 0 or s >= len(data):
+        return None
+    rising = data[s] < target
+    win = data[s:s + n]
+    hits = np.where(win >= target)[0] if rising else np.where(win <= target)[0]
+    if len(hits) == 0:
+        return None
+    x = s + hits[0]
+    if x == 0:
+        return None
+    a = data[x - 1] - target
+    b = data[x] - target
+    return x - 1 + (-a / (-a + b))
+
+
+def decode_philips_line(rf, seg, seg_start, linestart):
+    """decodephillipscode on `seg`, a host copy of demod[seg_start : ...] (absolute Hz)."""
+    fq = rf.freq
+    thr = rf.iretohz(50)
+    rel = linestart - seg_start
+    cur = _calczc(seg, int(rel + 2 * fq), thr, count=int(12 * fq))
+    zcs = []
+    while cur is not None:
+        zcs.append((cur, seg[int(cur - 0.5 * fq)] < thr))
+        cur = _calczc(seg, cur + 1.9 * fq, thr, count=int(0.2 * fq))
+    if len(zcs) != 24:
+        return None
+    gaps = np.diff([z[0] for z in zcs]) / fq
+    if not (np.min(gaps) > 1.85 and np.max(gaps) < 2.15):
+        return None
+    bits = [int(z[1]) for z in zcs]
+    return [bits[b] * 8 + bits[b + 1] * 4 + bits[b + 2] * 2 + bits[b + 3] for b in range(0, 24, 4)]
+
+
+def process_philips(rf, linecode):
+    """processphilipscode (lddecode_core.py:836-884)."""
+    vbi = {'minutes': None, 'seconds': None, 'clvframe': None, 'framenr': None, 'statuscode': None, 'status': None,
+           'isclv': False}
+    for l in rf.SysParams['philips_codelines']:
+        lc = linecode.get(l)
+        if lc is None:
+            continue
+        if lc[0] == 15 and lc[2] == 13:
+            vbi['minutes'] = 60 * lc[1] + lc[4] * 10 + lc[5]
+            vbi['isclv'] = True
+        elif lc[0] == 15:
+            vbi['framenr'] = (lc[1] & 7) * 10000 + lc[2] * 1000 + lc[3] * 100 + lc[4] * 10 + lc[5]
+        else:
+            h = (lc[0] << 20) | (lc[1] << 16) | (lc[2] << 12) | (lc[3] << 8) | (lc[4] << 4) | lc[5]
+            if lc[2] == 0xE:
+                vbi['seconds'] = (lc[1] - 10) * 10 + lc[3]
+                vbi['clvframe'] = lc[4] * 10 + lc[5]
+                vbi['isclv'] = True
+            htop = h >> 12
+            if htop == 0x8dc or htop == 0x8ba:
+                vbi['status'] = h
+            if h == 0x87ffff:
+                vbi['isclv'] = True
+    return vbi
+
+
+# ---- drop-in classes -----------------------------------------------------------------------------
+class Field:
+    """Field(rf, rawdecode, start, audio_offset=0): rawdecode is what RFDecode.demod_device returned
+    (device resident, preferred) or the (video, audio) record arrays of RFDecode.demod."""
+
+    full = False
+
+    def __init__(self, rf, rawdecode, start, audio_offset=0, keepraw=True, colorlevel=1.45, colorphase=91.5):
+        if rawdecode is None:
+            return
+        self.rf = rf
+        self.data = rawdecode
+        self.start = start
+        self.inlinelen = rf.linelen
+        self.outlinelen = rf.SysParams['outlinelen']
+        self.valid = False
+        self.dspicture = None
+        self.dsaudio = None
+        self.audio_next_offset = audio_offset
+        self.colorlevel, self.colorphase = colorlevel, colorphase
+        self.burstlevel = None
+        self._planes, self._n = self._device_planes(rawdecode)
+        be = rf._be
+
+        self.peaklist, self._peakvals = self.get_syncpeaks(with_values=True)
+        info, ll1, bad = locate(rf, self.peaklist, self._peakvals, self._n, start)
+        self._info = info
+        self.vsyncs = [[info.vsyncs[i][q] for q in range(3)] for i in range(min(info.nvsyncs, 4))]
+        if info.stage == _lib.FIELD_CRASH:
+            raise TypeError("cannot unpack non-iterable NoneType object")      # what the reference does here
+        self.nextfieldoffset = int(info.nextfieldoffset)
+        if info.stage in (_lib.FIELD_NOVSYNC, _lib.FIELD_SHORT):
+            return
+        self.med_hsync, self.hsync_tolerance = info.med_hsync, info.hsync_tolerance
+        self.istop = info.istop
+        self.linecount = info.linecount
+        if info.stage == _lib.FIELD_BADLINES:
+            print('unable to decode frame')
+            return
+        nll = self.linecount + 4
+        self.linelocs1 = list(ll1[:nll])
+        batch = FieldBatch(rf, 1)
+        batch.linecount[0] = self.linecount
+        batch.winlen[0] = self._n
+        batch.linelocs1[0] = ll1
+        batch.linebad[0] = bad
+        self._batch = batch
+        ref = refine_and_tbc(rf, self._planes, self._n, batch, colorlevel, colorphase) if self.full else \
+            self._refine_hsync_only(batch)
+        self.linebad = [bool(x) for x in ref.linebad[0][:nll]]
+        self.linelocs2 = list(ref.linelocs2[0][:nll])
+        if ref.status[0] & 2:
+            print('unable to decode frame')
+            return
+        self.linelocs = self.linelocs2
+        self._decode_vbi()
+        self.valid = True
+        self.tbcstart = int(info.tbcstart)
+        if self.full:
+            self._finish(ref, nll)
+
+    # -- plumbing
+    def _device_planes(self, rawdecode):
+        rf, be = self.rf, self.rf._be
+        if isinstance(rawdecode, DeviceDemod):
+            return rawdecode.planes, rawdecode.length
+        video = rawdecode[0]
+        ire0 = rf.SysParams['ire0']
+        planes = {}
+        for name in video.dtype.names:
+            v = np.asarray(video[name], dtype=np.float64)
+            if name == 'demod_sync':
+                planes[name] = be.to_device(v)
+            else:
+                planes[name] = be.to_device((v - ire0 if name in ('demod', 'demod_05') else v).astype(np.float32))
+        return planes, len(video)
+
+    def _refine_hsync_only(self, batch):
+        rf, be, lib = self.rf, self.rf._be, self.rf._be.lib
+        out = RefinedBatch()
+        d = {k: be.to_device(getattr(batch, k).reshape(-1)) for k in ('base', 'winlen', 'linecount', 'linelocs1', 'linebad')}
+        d_l2 = be.empty(LL_STRIDE, np.float64)
+        d_bad2 = be.empty(LL_STRIDE, np.uint8)
+        d_status = be.zeros(1, np.int32)
+        rf._check(lib.ldd_refine_hsync(rf._h, be.ptr(self._planes['demod_05']), int(self._n), be.ptr(d['base']),
+                                       be.ptr(d['winlen']), be.ptr(d['linecount']), 1, LL_STRIDE, be.ptr(d['linelocs1']),
+                                       be.ptr(d['linebad']), be.ptr(d_l2), be.ptr(d_bad2), be.ptr(d_status), be.stream()))
+        be.synchronize()
+        out.status = be.to_host(d_status)
+        out.linelocs2 = be.to_host(d_l2).reshape(1, LL_STRIDE)
+        out.linebad = be.to_host(d_bad2).reshape(1, LL_STRIDE)
+        return out
+
+    def _plane_slice_host(self, name, a, b):
+        """Host float64 copy of plane[a:b] in the reference's units."""
+        be = self.rf._be
+        a, b = max(int(a), 0), min(int(b), self._n)
+        v = be.to_host(self._planes[name][a:b]).astype(np.float64)
+        if name in ('demod', 'demod_05'):
+            v += self.rf.SysParams['ire0']
+        return v
+
+    def _decode_vbi(self):
+        rf = self.rf
+        self.isclv = False
+        self.linecode = {}
+        self.framenr = None
+        for l in rf.SysParams['philips_codelines']:
+            ls = self.linelocs[l]
+            a = int(ls) - 64
+            seg = self._plane_slice_host('demod', a, a + rf.linelen + 128)
+            try:
+                self.linecode[l] = decode_philips_line(rf, seg, max(a, 0), ls)
+            except IndexError:
+                self.linecode[l] = None
+        self.vbi = process_philips(rf, self.linecode)
+
+    # -- reference API
+    def usectoinpx(self, x):
+        return x * self.rf.freq
+
+    def inpxtousec(self, x):
+        return x / self.rf.freq
+
+    def get_syncpeaks(self, with_values=False):
+        pk, vl = sync_peaks_device(self.rf, self._planes['demod_sync'], self._n, self.start)
+        return (list(pk), vl) if with_values else list(pk)
+
+    def downscale(self, lineoffset=1, lineinfo=None, outwidth=None, wow=True, channel='demod', audio=False):
+        """Field.downscale (lddecode_core.py:789-812): float64 Hz, linecount * outwidth samples."""
+        rf, be = self.rf, self.rf._be
+        if lineinfo is None:
+            lineinfo = self.linelocs
+        if outwidth is None:
+            outwidth = self.outlinelen
+        ll = np.zeros(LL_STRIDE, dtype=np.float64)
+        ll[:len(lineinfo)] = lineinfo
+        d_ll = be.to_device(ll)
+        d_lc = be.to_device(np.array([self.linecount], dtype=np.int32))
+        d_st = be.zeros(1, np.int32)
+        out = be.empty(self.linecount * outwidth, np.float64)
+        add = float(rf.SysParams['ire0']) if channel in ('demod', 'demod_05') else 0.0
+        rf._check(be.lib.ldd_tbc_fields(rf._h, be.ptr(self._planes[channel]), int(self._n), add, None, be.ptr(d_ll), LL_STRIDE,
+                                        be.ptr(d_lc), 1, self.linecount, int(lineoffset), 0.0, int(outwidth), int(bool(wow)), 0,
+                                        be.ptr(out), self.linecount * outwidth, None, 1.0, be.ptr(d_st), be.stream()))
+        be.synchronize()
+        if be.to_host(d_st)[0] & 1:
+            raise ValueError("line window outside the decoded data")
+        return be.to_host(out), self.dsaudio
+
+    def _finish(self, ref, nll):
+        pass
+
+
+class FieldNTSC(Field):
+    full = True
+
+    def _finish(self, ref, nll):
+        be = self.rf._be
+        if ref.status[0] & (1 | 4):
+            print("ERROR: Unable to decode frame, skipping")
+            self.valid = False
+            return
+        self.linelocs3 = ref.linelocs3[0][:nll].copy()
+        self.linelocs4 = ref.linelocs4[0][:nll].copy()
+        self.burstlevel = ref.burstlevel[0][:nll].copy()
+        self.linelocs = self.linelocs4 + ref.lineloc_add
+        W = self.outlinelen
+        self.dspicture = be.to_host(ref.d_pic)[:self.linecount * W].copy()
+
+    def apply_offsets(self, linelocs, phaseoffset, picoffset=0):
+        return np.array(linelocs) + picoffset + (phaseoffset * (self.rf.freq / (4 * 315 / 88)))
+
+
+class FieldPAL(Field):
+    full = True
+
+    def _finish(self, ref, nll):
+        be = self.rf._be
+        if ref.status[0] & (1 | 8):
+            print("ERROR: Unable to decode frame, skipping")
+            self.valid = False
+            return
+        self.linelocs = ref.final[0][:nll].copy()
+        W = self.outlinelen
+        self.dspicture = be.to_host(ref.d_pic)[:self.linecount * W].copy()

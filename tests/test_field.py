@@ -1,0 +1,114 @@
+"""Kernels (4) and (5) and the field chain through the drop-in Field classes, against the golden
+vectors recorded from the reference's FieldNTSC / FieldPAL (lddecode_core.py:489-1191).
+
+Bars (BASELINE.json north_star): sync-peak indices bit-exact; TBC output within +-1 LSB of uint16.
+Line positions are held to 1e-5 samples, burst levels to 2 float32 ulps."""
+import os
+
+import numpy as np
+import pytest
+
+from lddecode_b200 import _lib, field, rfdecode
+from oracle import ldd_oracle as O
+
+
+def _setup(backend, g, name):
+    system = "PAL" if name == "pal" else "NTSC"
+    rf = rfdecode.RFDecode(float(g["fs_mhz"]), system, int(g["blocklen"]), _backend=backend)
+    cap = g["capture"]
+    fmt = _lib.FMT_U8 if cap.dtype == np.uint8 else _lib.FMT_U16
+    dd = rf.demod_device(backend.to_device(cap), fmt, 0, len(cap), 0, int(g["demod_length"]), 1)
+    return rf, dd, system
+
+
+@pytest.mark.parametrize("name", ["ntsc", "pal", "ntsc10"])
+def test_field_golden(backend, golden, name):
+    g = golden(name)
+    rf, dd, system = _setup(backend, g, name)
+    f = (field.FieldNTSC if system == "NTSC" else field.FieldPAL)(rf, dd, 0)
+    assert f.valid == bool(g["field_valid"])
+    assert np.array_equal(np.array(f.peaklist), g["field_peaklist"])                 # bit-exact peak indices
+    assert np.array_equal(np.array(f.vsyncs), g["field_vsyncs"])
+    assert f.nextfieldoffset == int(g["field_nextfieldoffset"]) and f.tbcstart == int(g["field_tbcstart"])
+    assert int(f.istop) == int(g["field_istop"]) and f.linecount == int(g["field_linecount"])
+    np.testing.assert_allclose(f.med_hsync, g["field_med_hsync"], rtol=1e-12)
+    np.testing.assert_allclose(f.hsync_tolerance, g["field_hsync_tolerance"], rtol=1e-9)
+    np.testing.assert_array_equal(np.array(f.linelocs1), g["field_linelocs1"])
+    assert np.array_equal(np.array(f.linebad, dtype=np.int8), g["field_linebad"])
+    np.testing.assert_allclose(f.linelocs2, g["field_linelocs2"], rtol=0, atol=1e-5)
+    if system == "NTSC":
+        np.testing.assert_allclose(f.linelocs3, g["field_linelocs3"], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(f.linelocs4, g["field_linelocs4"], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(f.burstlevel, g["field_burstlevel"], rtol=3e-7, atol=0)
+    np.testing.assert_allclose(f.linelocs, g["field_linelocs"], rtol=0, atol=1e-5)
+    d = f.dspicture.astype(np.int64) - g["field_dspicture"].astype(np.int64)
+    assert np.abs(d).max() <= 1                                                      # +-1 LSB of uint16
+    assert np.count_nonzero(d) < 0.002 * d.size
+    codes = [[-1] * 6 if f.linecode[l] is None else f.linecode[l] for l in rf.SysParams["philips_codelines"]]
+    assert np.array_equal(np.array(codes), g["field_linecode"])
+    assert f.vbi["framenr"] == int(g["field_framenr"])
+
+
+@pytest.mark.parametrize("name", ["ntsc", "pal"])
+def test_downscale_float_matches_scale(backend, golden, name):
+    """Field.downscale in float64 mode equals the reference's lddutils.scale per line."""
+    g = golden(name)
+    rf, dd, system = _setup(backend, g, name)
+    f = field.Field(rf, dd, 0)
+    f.linecount = int(g["field_linecount"])
+    W = rf.SysParams["outlinelen"]
+    out, _ = f.downscale(lineoffset=0, lineinfo=g["field_linelocs"], wow=False, channel="demod")
+    for k, l in enumerate(g["scale_lines"]):
+        np.testing.assert_allclose(out[l * W:(l + 1) * W], g["scale_out"][k], rtol=0, atol=0.25)     # Hz
+    if system == "NTSC":
+        sb, _ = f.downscale(lineoffset=0, lineinfo=g["field_linelocs2"], channel="demod_burst")
+        np.testing.assert_allclose(sb[::7], g["field_scaledburst_sparse"], rtol=0, atol=0.05)
+
+
+def test_sync_peaks_bit_exact_random_planes(backend):
+    """get_syncpeaks against the oracle on planes that make chains merge late or never:
+    noise, silence, and a real sync plane, for several segment sizes and start offsets."""
+    fs = 8 * 315 / 88
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, _backend=backend)
+    rng = np.random.default_rng(7)
+    planes = [rng.uniform(0, 0.5, 300000), np.zeros(100000), rng.uniform(0, 0.21, 200000),
+              np.clip(np.sin(np.arange(250000) * 0.00345) + rng.normal(0, .05, 250000), 0, 1)]
+    old = os.environ.get("LDD_PEAK_SEG_LINES")
+    try:
+        for seg in ("4", "48"):
+            os.environ["LDD_PEAK_SEG_LINES"] = seg
+            for ds in planes:
+                for start in (0, 777):
+                    buf = backend.to_device(np.ascontiguousarray(ds))
+                    pk, vl = field.sync_peaks_device(rf, buf, len(ds), start)
+                    ref = O.sync_peaks(ds, start, rf.linelen)
+                    assert np.array_equal(pk, np.array(ref, dtype=np.int64))
+                    assert np.array_equal(vl, ds[ref] if len(ref) else np.zeros(0))
+        # shorter than two lines: empty list
+        buf = backend.to_device(np.ones(3000))
+        pk, _ = field.sync_peaks_device(rf, buf, 3000, 0)
+        assert len(pk) == 0
+    finally:
+        if old is None:
+            os.environ.pop("LDD_PEAK_SEG_LINES", None)
+        else:
+            os.environ["LDD_PEAK_SEG_LINES"] = old
+
+
+def test_field_early_outs(backend):
+    """No vsync in the window / a single vsync: same nextfieldoffset rules as Field.__init__
+    (lddecode_core.py:909-924), checked against the oracle."""
+    from lddecode_b200 import synth
+    fs = 8 * 315 / 88
+    cap = synth.SynthRF("NTSC", fs, seed=2, lead_lines=120).generate(700000)
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=False, _backend=backend)
+    dec = O.Decoder(fs, "NTSC", 16384, analog_audio=False)
+    ld = lambda s, n: cap[s:s + n] if s + n <= len(cap) else None
+    for length in (150000, 500000):          # no vsync at all / exactly one vsync
+        dd = rf.demod_device(backend.to_device(cap), _lib.FMT_U8, 0, len(cap), 0, length, 0)
+        f = field.FieldNTSC(rf, dd, 0)
+        ov, _ = O.demod(dec, ld, 0, length, 0)
+        of = O.decode_field(dec, ov, 0)
+        assert not f.valid and not of.valid
+        assert f.nextfieldoffset == of.nextfieldoffset
+        assert np.array_equal(f.peaklist, of.peaklist)

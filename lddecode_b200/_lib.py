@@ -70,6 +70,9 @@ SIGNATURES = {
                                  C.c_double, C.c_void_p, C.c_void_p]),
     "ldd_field_locate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int]),
+    "ldd_field_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_longlong,
+                                  C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ldd_refine_hsync": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldd_refine_burst": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
@@ -84,6 +87,9 @@ class FieldInfo(C.Structure):
                 ("vsyncs", (C.c_int * 3) * 4), ("nextfieldoffset", C.c_longlong), ("tbcstart", C.c_longlong),
                 ("med_hsync", C.c_double), ("hsync_tolerance", C.c_double)]
 
+
+WINDOW_PEAKS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.POINTER(C.c_void_p),
+                              C.POINTER(C.c_void_p), C.POINTER(C.c_int))
 
 FIELD_NOVSYNC, FIELD_SHORT, FIELD_LOCATED, FIELD_BADLINES, FIELD_CRASH = range(5)
 

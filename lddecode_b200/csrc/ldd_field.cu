@@ -471,6 +471,11 @@ __global__ void __launch_bounds__(128) refine_pilot_kernel(const PilotParams p, 
 // Host: A7 + the early-outs of Field.__init__.
 namespace {
 
+int fail_msg(ldd_handle* h, int code, const char* msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
 double median_of(std::vector<double> v) {
     size_t n = v.size();
     if (n == 0) return NAN;
@@ -720,4 +725,112 @@ extern "C" int ldd_refine_pilot(ldd_handle* h, const float* demod_dev, const flo
     p.linelocs_out = linelocs_out_dev; p.status = status_dev;
     LDD_LAUNCH(refine_pilot_kernel, dim3(nfields), dim3(128), 0, st, p, offs, cnt);
     return cudaGetLastError() == cudaSuccess ? LDD_OK : LDD_ECUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host: the field-to-field walk of Framer.readfield (lddecode_core.py:1194-1223) over a capture
+// whose planes were demodulated on ONE global block grid (plane index k <-> capture sample
+// k + blockcut).  Each window is what rf.demod(infile, readsample, readlen) would have covered;
+// its peak list is cut out of the global chase when the window starts on a peak of that chase
+// (the normal case: nextfieldoffset is a peak), otherwise the callback runs the chase for that
+// window on the device.
+namespace {
+
+// Peaks of the chase started at window_start, taken from the global chase.  Returns false when the
+// window does not start on a global peak.
+bool window_from_global(const long long* gp, int ngp, long long b, long long wl, int L, int* k0_out, int* k1_out) {
+    const long long half = L / 2, skip = (long long)(L * .4);
+    const long long limit = b + wl - 2LL * L;
+    int k0 = (int)(std::lower_bound(gp, gp + ngp, b) - gp);
+    if (k0 >= ngp || gp[k0] != b) return false;
+    // a peak belongs to the window's list iff the step that found it started below `limit`:
+    // steps after peak p start at p + skip, then advance by `half` until the next peak is inside
+    int k = k0 + 1;
+    for (; k < ngp; ++k) {
+        long long i0 = gp[k - 1] + skip;
+        long long m = (gp[k] - i0) / half;
+        long long istep = i0 + m * half;
+        if (istep >= limit) break;
+    }
+    *k0_out = k0;
+    *k1_out = k;
+    return true;
+}
+
+}  // namespace
+
+extern "C" int ldd_field_chain(ldd_handle* h, const long long* gpeaks, const double* gvals, int ngpeaks,
+                               long long plane_len, long long ncap, long long readlen, long long first_readsample,
+                               int max_fields, ldd_window_peaks_fn cb, void* ctx,
+                               ldd_field* fields, long long* base, long long* winlen, long long* readsample_out,
+                               double* linelocs1, unsigned char* linebad, int ll_stride, int* nfields_out) {
+    if (!h || !gpeaks || !gvals || !fields || !base || !winlen || !readsample_out || !linelocs1 || !linebad || !nfields_out)
+        return LDD_EINVAL;
+    const ldd_config& c = h->cfg;
+    const int L = c.linelen;
+    long long readsample = first_readsample;
+    int nf = 0;
+    std::vector<long long> rel;
+    while (nf < max_fields) {
+        ldd_range r;
+        int rc = ldd_demod_range_query(h, readsample, readlen, &r);
+        if (rc) return rc;
+        if (r.last_needed > ncap) break;                               // rf.demod returns None -> readfield returns None
+        // plane index of the window's sample 0: output[j] <-> capture first_sample + blockcut + j
+        long long b = r.first_sample;                                  // == (first_sample + blockcut) - blockcut
+        long long wl = r.total_out;
+        if (b + wl > plane_len) break;
+        const long long* pk = nullptr;
+        const double* vl = nullptr;
+        int np = 0;
+        int k0 = 0, k1 = 0;
+        bool fast = (b == 0 && first_readsample == 0 && nf == 0) ? true : false;
+        if (fast) {
+            // the global chase itself started here
+            long long limit = wl - 2LL * L, half = L / 2, skip = (long long)(L * .4);
+            k0 = 0;
+            int k = 0;
+            long long iprev = 0;
+            for (; k < ngpeaks; ++k) {
+                long long i0 = k == 0 ? 0 : gpeaks[k - 1] + skip;
+                long long m = (gpeaks[k] - i0) / half;
+                if (i0 + m * half >= limit) break;
+                iprev = i0;
+            }
+            (void)iprev;
+            k1 = k;
+        } else {
+            fast = window_from_global(gpeaks, ngpeaks, b, wl, L, &k0, &k1);
+        }
+        if (fast) {
+            rel.resize(k1 - k0);
+            for (int k = k0; k < k1; ++k) rel[k - k0] = gpeaks[k] - b;
+            pk = rel.data();
+            vl = gvals + k0;
+            np = k1 - k0;
+        } else {
+            if (!cb) return fail_msg(h, LDD_EINVAL, "window does not start on a peak and no callback given");
+            rc = cb(ctx, b, wl, &pk, &vl, &np);
+            if (rc) return rc;
+        }
+        ldd_field* f = &fields[nf];
+        rc = ldd_field_locate(h, pk, vl, np, wl, 0, f, linelocs1 + (size_t)nf * ll_stride, linebad + (size_t)nf * ll_stride, ll_stride);
+        if (rc) return rc;
+        base[nf] = b;
+        winlen[nf] = wl;
+        readsample_out[nf] = readsample;
+        ++nf;
+        if (f->stage == LDD_FIELD_CRASH) break;                        // the reference raises here
+        // Framer.readfield: where the next read starts (lddecode_core.py:1204-1212)
+        long long next = readsample + f->nextfieldoffset;
+        bool valid_so_far = f->stage == LDD_FIELD_LOCATED;
+        if (!valid_so_far) {
+            if (np < 100) next = readsample + (long long)(c.freq_hz * 10);
+            else if (f->nvsyncs == 0) next = readsample + (long long)(c.freq_hz * 1);
+        }
+        if (next <= readsample) break;                                 // would loop forever (the reference does)
+        readsample = next;
+    }
+    *nfields_out = nf;
+    return LDD_OK;
 }

@@ -1,0 +1,378 @@
+#!/usr/bin/env python3
+"""bench.py -- RF Msamples/s demodulated + TBC on B200 (BASELINE.json metric), and the CPU arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--system PAL|NTSC] [--audio]
+
+A step is one pass of the hot path (demodulate -> sync peaks -> locate fields -> refine -> TBC to
+uint16) over one synthetic capture.  Workload at N=1: BASELINE.json configs[1], "PAL synthetic
+8-bit RF 1 s (8fsc PAL) video demod + TBC on 1xB200"; for N>1 every rank decodes its own one-second
+shard (weak scaling, no data-path collective) and the per-field outputs are gathered to rank 0 over
+NCCL inside the timed region.
+
+Printed JSON (one line, rank 0): value = whole-job Msamples/s with the capture resident in HBM;
+e2e = the same through the public API from pinned host memory with H2D of the capture and D2H of the
+uint16 fields inside the timed region; roofline = the dominant kernel (fused block demodulation)
+against the measured HBM peak; cpu_baseline = the oracle port of the reference timed on this box.
+--impl reference times the reference's CPU algorithm (oracle port: same numpy/scipy calls) on all
+host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS = {"NTSC": 8 * 315 / 88, "PAL": 35.46895}
+BLOCKLEN = 16384                     # the reference's default blocklen_ (lddecode_core.py:120)
+TAIL = 1100000                       # so the last 1e6-sample read succeeds
+
+
+def one_second(system):
+    return int(round(FS[system] * 1e6))
+
+
+def synth_capture(system, n, seed):
+    """Seeded synthetic capture, cached under gpurun_out/cache (generation is ~1.2 s per Msample)."""
+    from lddecode_b200 import synth
+    cdir = os.path.join(ROOT, "gpurun_out", "cache")
+    path = os.path.join(cdir, "%s_%d_%d.npy" % (system, n, seed))
+    if os.path.exists(path):
+        try:
+            return np.load(path)
+        except Exception:
+            pass
+    cap = synth.SynthRF(system, FS[system], seed=seed).generate(n)
+    try:
+        os.makedirs(cdir, exist_ok=True)
+        tmp = path + ".%d.tmp.npy" % os.getpid()
+        np.save(tmp, cap)
+        os.replace(tmp, path)
+    except Exception:
+        pass
+    return cap
+
+
+# ---- CPU arm: the oracle port of the reference ------------------------------------------------------
+def _cpu_decode_fields(args):
+    """Framer.readfield's loop with the oracle on one capture: returns (samples consumed, seconds)."""
+    system, audio, cap, nfields = args
+    from oracle import ldd_oracle as O
+    dec = O.Decoder(FS[system], system, BLOCKLEN, analog_audio=audio)
+    ld = lambda s, n: cap[s:s + n] if s + n <= len(cap) else None
+    t0 = time.perf_counter()
+    readsample, done = 0, 0
+    while done < nfields:
+        d = O.demod(dec, ld, readsample, 1000000, 1)
+        if d is None:
+            break
+        f = O.decode_field(dec, d[0], 0)
+        readsample += f.nextfieldoffset
+        done += 1
+    return readsample, time.perf_counter() - t0
+
+
+def cpu_baseline(system, audio, budget_s=12.0):
+    """Single-core oracle port on a bounded sample (whole fields until ~budget_s of CPU work)."""
+    nf = 6
+    field = one_second(system) // (60 if system == "NTSC" else 50)
+    cap = synth_capture(system, field * (nf + 3), 0)
+    consumed, secs, fields = 0, 0.0, 0
+    readsample = 0
+    from oracle import ldd_oracle as O
+    dec = O.Decoder(FS[system], system, BLOCKLEN, analog_audio=audio)
+    ld = lambda s, n: cap[s:s + n] if s + n <= len(cap) else None
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        d = O.demod(dec, ld, readsample, 1000000, 1)
+        if d is None:
+            readsample = 0
+            continue
+        f = O.decode_field(dec, d[0], 0)
+        consumed += f.nextfieldoffset
+        readsample += f.nextfieldoffset
+        fields += 1
+    secs = time.perf_counter() - t0
+    return dict(value=consumed / secs / 1e6, unit="Msamples/s", cores=1, kind="port",
+                sample="%d %s fields (Framer.readfield loop: demod 1e6 + Field decode each) in %.1f s, oracle port of "
+                       "lddecode_core on 1 core" % (fields, system, secs))
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    system, audio = a.system, a.audio
+    cores = os.cpu_count() or 1
+    field = one_second(system) // (60 if system == "NTSC" else 50)
+    nfields = 2
+    cap = synth_capture(system, field * (nfields + 3), 0)
+    ctx = mp.get_context("fork")
+    times = []
+    consumed = 0
+    with ctx.Pool(cores) as pool:
+        for step in range(a.warmup + a.steps):
+            t0 = time.perf_counter()
+            outs = pool.map(_cpu_decode_fields, [(system, audio, cap, nfields)] * cores)
+            dt = time.perf_counter() - t0
+            if step >= a.warmup:
+                times.append(dt)
+                consumed = sum(o[0] for o in outs)
+    ms = 1e3 * sum(times) / len(times)
+    value = consumed / (ms / 1e3) / 1e6
+    sample = "%d processes x %d %s fields per step (identical captures; demod 1e6 + Field decode per field)" % (cores, nfields, system)
+    line = dict(impl="reference", metric="rf_msamples_per_s_demod_tbc", value=value, unit="Msamples/s", n_gpus=a.gpus,
+                steps=a.steps, warmup=a.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f64", data="synthetic", config=workload_config(system, audio, a.gpus),
+                cpu_baseline=dict(value=value, unit="Msamples/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit="Msamples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                realtime_x=value / FS[system])
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(system, audio, gpus):
+    return dict(workload="%s synthetic 8-bit RF, 1 s at 8fsc (%.3f MSPS) per GPU, %s demod + sync + TBC to uint16 4fsc"
+                         % (system, FS[system], "video+audio" if audio else "video"),
+                blocklen=BLOCKLEN, readlen=1000000, parallelism="block-range shards, one 1-s shard per GPU (x%d)" % gpus,
+                l2="per step 36 MB in + ~0.9 GB of planes written: working set exceeds the 126 MB L2, no flush needed")
+
+
+# ---- clocks -----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ---- our arm ----------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from lddecode_b200 import _lib, parallel, pipeline, rfdecode
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (a.gpus, a.gpus))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    system, audio = a.system, a.audio
+    ncap = one_second(system) + TAIL
+    cap = synth_capture(system, ncap, 1 + rank if system == "PAL" else rank)
+    rf = rfdecode.RFDecode(FS[system], system, BLOCKLEN, decode_analog_audio=audio, device=local, precision=a.precision)
+    cd = pipeline.CaptureDecoder(rf, max_fields=256)
+    be = rf._be
+    cap_dev = torch.from_numpy(cap).cuda()
+    cap_pin = torch.from_numpy(cap).pin_memory()
+    stream = torch.cuda.current_stream()
+    max_fields = 80
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        res = cd.decode(cap_dev, _lib.FMT_U8, ncap)
+        if world > 1:
+            parallel.gather_fields(cd, res, rank, world, max_fields, dist)
+        return res
+
+    def step_e2e(out_pin):
+        d = cap_pin.cuda(non_blocking=True)                         # H2D of the step's input
+        res = cd.decode(d, _lib.FMT_U8, ncap)
+        n = len(res.located) * res.out_stride
+        out_pin[:n].copy_(res.d_pic[:n], non_blocking=True)         # D2H of the step's result
+        if res.audio is not None:
+            res.audio_host = (res.audio['audio_left'].cpu(), res.audio['audio_right'].cpu())
+        if world > 1:
+            parallel.gather_fields(cd, res, rank, world, max_fields, dist)
+        torch.cuda.current_stream().synchronize()
+        return res, n
+
+    # warm-up
+    res = None
+    for _ in range(max(a.warmup, 3)):
+        res = step_resident()
+    torch.cuda.synchronize()
+    nfields = len(res.located)
+    consumed = res.plane_len                      # samples demodulated once each (overlap re-reads not counted)
+    out_pin = torch.empty(max_fields * res.out_stride, dtype=torch.uint16).pin_memory()
+
+    # resident timing
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+
+    # end-to-end timing (host buffers)
+    for _ in range(2):
+        step_e2e(out_pin)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(a.steps):
+        _, npic = step_e2e(out_pin)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+
+    # dominant kernel alone: the fused block demodulation
+    planes_total = demod_only(cd, cap_dev, ncap)
+    planes_total = demod_only(cd, cap_dev, ncap)
+    torch.cuda.synchronize()
+    kt = []
+    for _ in range(max(a.steps, 5)):
+        e0.record()
+        planes_total = demod_only(cd, cap_dev, ncap)
+        e1.record()
+        torch.cuda.synchronize()
+        kt.append(e0.elapsed_time(e1))
+    k_ms = float(np.mean(kt))
+
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(t[0]), float(t[1])
+        c = torch.tensor([float(consumed)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        consumed_all = float(c[0])
+    else:
+        consumed_all = float(consumed)
+
+    if rank == 0:
+        ms_step = ms_total / a.steps
+        value = consumed_all / (ms_step / 1e3) / 1e6
+        e2e_val = consumed_all / (ms_e2e / a.steps / 1e3) / 1e6
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        nplanes32 = 4 if system == "PAL" else 3
+        N, S = BLOCKLEN, BLOCKLEN - 1056
+        bytes_per_sample = N / S + 4 * nplanes32 + 8 + (2 * 8 / (16 if system == "PAL" else 8) if audio else 0)
+        achieved = bytes_per_sample * planes_total / (k_ms / 1e3) / 1e9
+        launches_per_step = 1 + 2 + 1 + (1 if system == "PAL" else 2) + 1 + (2 if audio else 0)
+        line = dict(metric="rf_msamples_per_s_demod_tbc", value=value, unit="Msamples/s", n_gpus=world, steps=a.steps,
+                    warmup=max(a.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype=a.precision, data="synthetic", config=workload_config(system, audio, world),
+                    realtime_x=value / FS[system] / world, fields_per_step=nfields * world,
+                    e2e=dict(value=e2e_val, unit="Msamples/s", h2d_bytes_per_step=int(ncap),
+                             d2h_bytes_per_step=int(npic * 2), wall_ms_per_step=wall_e2e / a.steps),
+                    gpu_launches=launches_per_step * a.steps,
+                    roofline=dict(bound="hbm", kernel="demod_kernel (fused unpack+FFT+filter+IFFT+FM discriminator+post filters+sync scan)",
+                                  achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                                  bytes_per_sample=bytes_per_sample, kernel_ms=k_ms, kernel_msamples_per_s=planes_total / k_ms / 1e3,
+                                  peak_source="MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"),
+                    clocks=clk)
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline(system, audio)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def demod_only(cd, cap_dev, ncap):
+    """One launch of the demodulation kernel over the whole capture (what the roofline entry times)."""
+    rf, be = cd.rf, cd.rf._be
+    S, N = cd.stride, rf.blocklen
+    first_block, nblocks, _ = cd.plan_range(ncap, 0, ncap + 1)
+    while nblocks > 0 and first_block + (nblocks - 1) * S + N > ncap:
+        nblocks -= 1
+    total = nblocks * S
+    if not hasattr(cd, "_bench_planes") or cd._bench_planes[1] != total:
+        cd._bench_planes = (rf._alloc_planes(total), total)
+    (planes, parr), _ = cd._bench_planes
+    a1 = None
+    alen = 0
+    if rf.decode_analog_audio:
+        ds = N // len(rf.Filters['audio_lfilt'])
+        alen = total // ds
+        if not hasattr(cd, "_bench_audio"):
+            cd._bench_audio = (be.empty(alen, np.float64), be.empty(alen, np.float64))
+        a1 = cd._bench_audio
+    from lddecode_b200 import _lib
+    rf._check(be.lib.ldd_demod_blocks(rf._h, be.ptr(cap_dev), _lib.FMT_U8, 0, int(ncap), 0, int(nblocks), int(total), parr,
+                                      be.ptr(a1[0]) if a1 else None, be.ptr(a1[1]) if a1 else None, int(alen), be.stream()))
+    return total
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--system", default="PAL", choices=["PAL", "NTSC"])
+    ap.add_argument("--audio", action="store_true", help="also demodulate the two analog FM audio channels")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

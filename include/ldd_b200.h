@@ -201,9 +201,13 @@ int ldd_field_locate(ldd_handle* h, const long long* peaks, const double* vals, 
                      double* linelocs1, unsigned char* linebad, int ll_cap);
 
 /* HOST function: the field-to-field walk of Framer.readfield (lddecode_core.py:1194-1223) over planes
- * that were demodulated on one global block grid (ldd_demod_blocks with first_sample = 0, so that
- * plane index k <-> capture sample k + blockcut).  gpeaks/gvals: the peak list of ldd_sync_peaks over
- * the whole sync plane from 0.  For every window the reference would have read it fills fields[i],
+ * that were demodulated on one block grid (ldd_demod_blocks with first_sample = plane_origin, so that
+ * plane index k <-> capture sample plane_origin + blockcut + k).  gpeaks/gvals: the peak list of
+ * ldd_sync_peaks over the whole sync plane from 0.  The walk starts at first_readsample and stops when
+ * readsample >= stop_readsample, when a window leaves the planes, or when the capture (ncap samples)
+ * is too short for the next read.  tolerant != 0: a window on which the reference itself raises
+ * (LDD_FIELD_CRASH) is stepped over by 20 lines instead of ending the walk (range starts that are
+ * not field-aligned: shards, chunks).  For every window the reference would have read it fills fields[i],
  * base[i] (plane index of the window start), winlen[i], readsample[i] (capture coordinates) and, for
  * LDD_FIELD_LOCATED fields, linelocs1/linebad rows.  A window that does not start on a peak of the
  * global chase gets its own peak list from `cb` (window-relative indices, host arrays that stay
@@ -211,7 +215,8 @@ int ldd_field_locate(ldd_handle* h, const long long* peaks, const double* vals, 
 typedef int (*ldd_window_peaks_fn)(void* ctx, long long plane_start, long long window_len,
                                    const long long** peaks, const double** vals, int* npeaks);
 int ldd_field_chain(ldd_handle* h, const long long* gpeaks, const double* gvals, int ngpeaks,
-                    long long plane_len, long long ncap, long long readlen, long long first_readsample,
+                    long long plane_len, long long plane_origin, long long ncap, long long readlen,
+                    long long first_readsample, long long stop_readsample, int tolerant,
                     int max_fields, ldd_window_peaks_fn cb, void* ctx,
                     ldd_field* fields, long long* base, long long* winlen, long long* readsample_out,
                     double* linelocs1, unsigned char* linebad, int ll_stride, int* nfields_out);

@@ -760,7 +760,8 @@ bool window_from_global(const long long* gp, int ngp, long long b, long long wl,
 }  // namespace
 
 extern "C" int ldd_field_chain(ldd_handle* h, const long long* gpeaks, const double* gvals, int ngpeaks,
-                               long long plane_len, long long ncap, long long readlen, long long first_readsample,
+                               long long plane_len, long long plane_origin, long long ncap, long long readlen,
+                               long long first_readsample, long long stop_readsample, int tolerant,
                                int max_fields, ldd_window_peaks_fn cb, void* ctx,
                                ldd_field* fields, long long* base, long long* winlen, long long* readsample_out,
                                double* linelocs1, unsigned char* linebad, int ll_stride, int* nfields_out) {
@@ -771,20 +772,20 @@ extern "C" int ldd_field_chain(ldd_handle* h, const long long* gpeaks, const dou
     long long readsample = first_readsample;
     int nf = 0;
     std::vector<long long> rel;
-    while (nf < max_fields) {
+    while (nf < max_fields && readsample < stop_readsample) {
         ldd_range r;
         int rc = ldd_demod_range_query(h, readsample, readlen, &r);
         if (rc) return rc;
         if (r.last_needed > ncap) break;                               // rf.demod returns None -> readfield returns None
-        // plane index of the window's sample 0: output[j] <-> capture first_sample + blockcut + j
-        long long b = r.first_sample;                                  // == (first_sample + blockcut) - blockcut
+        // window output[j] <-> capture r.first_sample + blockcut + j; plane k <-> capture plane_origin + blockcut + k
+        long long b = r.first_sample - plane_origin;
         long long wl = r.total_out;
-        if (b + wl > plane_len) break;
+        if (b < 0 || b + wl > plane_len) break;
         const long long* pk = nullptr;
         const double* vl = nullptr;
         int np = 0;
         int k0 = 0, k1 = 0;
-        bool fast = (b == 0 && first_readsample == 0 && nf == 0) ? true : false;
+        bool fast = (b == 0 && plane_origin == 0 && first_readsample == 0 && nf == 0) ? true : false;
         if (fast) {
             // the global chase itself started here
             long long limit = wl - 2LL * L, half = L / 2, skip = (long long)(L * .4);
@@ -820,7 +821,13 @@ extern "C" int ldd_field_chain(ldd_handle* h, const long long* gpeaks, const dou
         winlen[nf] = wl;
         readsample_out[nf] = readsample;
         ++nf;
-        if (f->stage == LDD_FIELD_CRASH) break;                        // the reference raises here
+        if (f->stage == LDD_FIELD_CRASH) {
+            // the reference raises here (vsync inside the first 11 peaks).  A range that starts at an
+            // arbitrary place (shard / chunk start) steps forward instead and tries again.
+            if (!tolerant) break;
+            readsample += 20LL * L;
+            continue;
+        }
         // Framer.readfield: where the next read starts (lddecode_core.py:1204-1212)
         long long next = readsample + f->nextfieldoffset;
         bool valid_so_far = f->stage == LDD_FIELD_LOCATED;

@@ -2,11 +2,19 @@
 
 The reference walks a capture field by field (Framer.readfield, lddecode_core.py:1194-1223): every
 field re-reads and re-demodulates 1e6 samples (2.1x redundant) and the next read position comes out
-of the previous field.  Here the capture is demodulated ONCE on a fixed global block grid
-(blocks are independent given the 1024/32-sample halos), one global sync-peak
-chase replaces the per-field ones, the field-to-field walk runs on the host over the ~16 K peaks per
-second of video (ldd_field_chain), and all located fields are refined and resampled in a handful of
-batched launches.  Only the peak list crosses to the host in the middle.
+of the previous field.  Here a range of the capture is demodulated ONCE on the fixed global block
+grid (blocks start at multiples of blocklen-1056; they are independent given the 1024/32-sample
+halos), one sync-peak chase covers the whole range, the field-to-field walk
+runs on the host over the ~16 K peaks per second of video (ldd_field_chain), and all located fields
+are refined and resampled in a handful of batched launches.  Only the peak list crosses to the host
+in the middle.
+
+Ranges make the same code serve a single GPU (one range), captures larger than HBM (ranges one
+after the other) and multi-GPU sharding (one range per rank, parallel.py): a range owns the
+fields whose read position lies in [r0, r1); it starts walking 1.6 fields early so that its read
+positions are those of the sequential walk by the time it reaches r0, and it demodulates one read
+length beyond r1 so every owned field completes locally.  Because all ranges use the same global
+block grid, a sharded decode is bit-identical to the single-range decode.
 
 Differences from calling Field() per window, by construction: planes come from one block grid
 instead of one grid per field, so demod_sync differs by the FPsync wrap term (< 3e-5 absolute);
@@ -22,25 +30,52 @@ from . import field as F
 READLEN = 1000000        # Framer.readlen (lddecode_core.py:1319, 1324)
 
 
-class CaptureResult:
+class RangeResult:
+    """Fields owned by one range.  Device buffers: d_pic uint16 [nfields][out_stride], d_status."""
     pass
 
 
 class CaptureDecoder:
-    def __init__(self, rf, readlen=READLEN, mtf_level=1, colorlevel=1.45, colorphase=91.5, max_fields=4096):
+    def __init__(self, rf, readlen=READLEN, mtf_level=1, colorlevel=1.45, colorphase=91.5, max_fields=8192):
         self.rf = rf
         self.readlen = readlen
         self.mtf_level = mtf_level          # Framer starts at 1 (lddecode_core.py:1334)
         self.colorlevel, self.colorphase = colorlevel, colorphase
         self.max_fields = max_fields
+        self.field_samples = int(rf.freq_hz / rf.SysParams['FPS'] / 2)
 
-    # -- stage 1: planes + peaks on the device
-    def demod_all(self, cap_dev, fmt, ncap, rf_base=0):
+    @property
+    def stride(self):
+        rf = self.rf
+        return rf.blocklen - rf.blockcut - rf.blockcut_end
+
+    def plan_range(self, ncap_total, r0, r1):
+        """Block grid for the range owning read positions [r0, r1): (first_block, nblocks, walk_start)."""
+        rf = self.rf
+        S, N, bc = self.stride, rf.blocklen, rf.blockcut
+        walk_start = 0 if r0 <= 0 else max(0, r0 - int(1.6 * self.field_samples))
+        first_block = (max(walk_start - bc, 0) // S) * S
+        # last capture sample any owned window can need: the reads of rf.demod(r1 - 1, readlen)
+        need_end = min(ncap_total, r1 + self.readlen + 2 * N + bc)
+        nblocks = max(0, (need_end - first_block - N) // S + 1)
+        return first_block, nblocks, walk_start
+
+    def decode_range(self, cap_dev, fmt, cap_base, cap_len, ncap_total, r0, r1, want_tables=False, audio_phase2=True):
+        """Decode the fields whose read position lies in [r0, r1).
+
+        cap_dev holds capture samples [cap_base, cap_base + cap_len) in format fmt; ncap_total is the
+        length of the whole capture (the reference stops when a read would pass its end)."""
         rf, be = self.rf, self.rf._be
-        N = rf.blocklen
-        S = N - rf.blockcut - rf.blockcut_end
-        nblocks = (ncap - N) // S + 1 if ncap >= N else 0
+        S, N = self.stride, rf.blocklen
+        first_block, nblocks, walk_start = self.plan_range(ncap_total, r0, r1)
+        avail_end = min(cap_base + cap_len, ncap_total)
+        while nblocks > 0 and first_block + (nblocks - 1) * S + N > avail_end:
+            nblocks -= 1
+        if first_block < cap_base:
+            raise ValueError("capture window does not cover the range's halo")
         total = nblocks * S
+        res = RangeResult()
+        res.r0, res.r1, res.plane_origin, res.plane_len = r0, r1, first_block, total
         rf._set_mtf(self.mtf_level)
         planes, parr = rf._alloc_planes(max(total, 1))
         a1l = a1r = None
@@ -50,46 +85,48 @@ class CaptureDecoder:
             alen = total // ds
             a1l, a1r = be.empty(max(alen, 1), np.float64), be.empty(max(alen, 1), np.float64)
         if nblocks:
-            rf._check(be.lib.ldd_demod_blocks(rf._h, be.ptr(cap_dev), fmt, int(rf_base), int(ncap), int(rf_base), int(nblocks),
-                                              int(total), parr, be.ptr(a1l) if a1l is not None else None,
+            rf._check(be.lib.ldd_demod_blocks(rf._h, be.ptr(cap_dev), fmt, int(cap_base), int(cap_len), int(first_block),
+                                              int(nblocks), int(total), parr, be.ptr(a1l) if a1l is not None else None,
                                               be.ptr(a1r) if a1r is not None else None, int(alen), be.stream()))
-        return planes, total, (a1l, a1r, alen)
-
-    def decode(self, cap_dev, fmt, ncap, want_tables=False, audio_phase2=True):
-        """cap_dev: device buffer with the whole capture (format fmt, ncap samples)."""
-        rf, be = self.rf, self.rf._be
-        res = CaptureResult()
-        planes, total, (a1l, a1r, alen) = self.demod_all(cap_dev, fmt, ncap)
-        res.planes, res.plane_len = planes, total
+        res.planes = planes
         res.audio = None
-        if rf.decode_analog_audio and audio_phase2 and alen > rf.blocklen:
-            res.audio = rf._audio_phase2_device(a1l, a1r, alen)
-        elif rf.decode_analog_audio:
-            res.audio = {'audio_left': a1l, 'audio_right': a1r}
-        # global peak chase, then the only device->host hop of the path: ~16 K peaks per second of video
+        if rf.decode_analog_audio:
+            if audio_phase2 and alen > rf.blocklen:
+                res.audio = rf._audio_phase2_device(a1l, a1r, alen)
+            else:
+                res.audio = {'audio_left': a1l, 'audio_right': a1r}
+        # sync-peak chase over the whole plane, then the only device->host hop of the path
         gpk, gvl = F.sync_peaks_device(rf, planes['demod_sync'], total, 0)
         res.gpeaks = gpk
-        batch, infos, readsamples = self._walk(planes, total, ncap, gpk, gvl)
-        res.infos, res.readsamples = infos, readsamples
-        res.nwindows = len(infos)
-        located = [i for i, f in enumerate(infos) if f.stage == _lib.FIELD_LOCATED]
+        batch, infos, readsamples = self._walk(planes, total, first_block, ncap_total, walk_start, r1, r0 > 0, gpk, gvl)
+        owned = [i for i in range(len(infos)) if r0 <= readsamples[i] < r1]
+        res.infos = [infos[i] for i in owned]
+        res.readsamples = readsamples[owned] if len(owned) else np.zeros(0, dtype=np.int64)
+        res.base = batch.base[owned] if len(owned) else np.zeros(0, dtype=np.int64)
+        res.linelocs1 = batch.linelocs1[owned] if len(owned) else np.zeros((0, F.LL_STRIDE))
+        res.nwindows = len(owned)
+        located = [j for j, i in enumerate(owned) if infos[i].stage == _lib.FIELD_LOCATED]
         res.located = located
-        res.batch = batch
+        res.refined = None
+        res.d_pic = res.d_status = None
+        res.out_stride = (rf.SysParams['frame_lines'] // 2 + 1) * rf.SysParams['outlinelen']
         if located:
             sub = F.FieldBatch(rf, len(located))
-            for j, i in enumerate(located):
-                sub.base[j], sub.winlen[j], sub.linecount[j] = batch.base[i], batch.winlen[i], infos[i].linecount
-                sub.linelocs1[j], sub.linebad[j] = batch.linelocs1[i], batch.linebad[i]
+            for k, j in enumerate(located):
+                i = owned[j]
+                sub.base[k], sub.winlen[k], sub.linecount[k] = batch.base[i], batch.winlen[i], infos[i].linecount
+                sub.linelocs1[k], sub.linebad[k] = batch.linelocs1[i], batch.linebad[i]
             ref = F.refine_and_tbc(rf, planes, total, sub, self.colorlevel, self.colorphase, want_intermediates=want_tables)
             res.refined = ref
-            res.d_pic, res.out_stride, res.d_status = ref.d_pic, ref.out_stride, ref.d_status
-        else:
-            res.refined = None
-            res.d_pic = None
+            res.d_pic, res.d_status = ref.d_pic, ref.d_status
         return res
 
-    # -- stage 2: host walk
-    def _walk(self, planes, total, ncap, gpk, gvl):
+    def decode(self, cap_dev, fmt, ncap, want_tables=False, audio_phase2=True):
+        """The whole capture as one range."""
+        return self.decode_range(cap_dev, fmt, 0, ncap, ncap, 0, ncap + 1, want_tables, audio_phase2)
+
+    # -- host walk
+    def _walk(self, planes, total, plane_origin, ncap_total, first_readsample, stop_readsample, tolerant, gpk, gvl):
         rf, be = self.rf, self.rf._be
         mf = self.max_fields
         fields = (_lib.FieldInfo * mf)()
@@ -99,7 +136,7 @@ class CaptureDecoder:
         keep = {}
 
         def window_peaks(ctx, b, wl, ppk, pvl, pn):
-            # slow path: this window does not start on a peak of the global chase
+            # this window does not start on a peak of the range's chase: chase it by itself
             sync = planes['demod_sync'][int(b):int(b + wl)]
             pk, vl = F.sync_peaks_device(rf, sync, int(wl), 0)
             keep['pk'], keep['vl'] = np.ascontiguousarray(pk), np.ascontiguousarray(vl)
@@ -111,7 +148,8 @@ class CaptureDecoder:
         cb = _lib.WINDOW_PEAKS_FN(window_peaks)
         gpk = np.ascontiguousarray(gpk, dtype=np.int64)
         gvl = np.ascontiguousarray(gvl, dtype=np.float64)
-        rf._check(be.lib.ldd_field_chain(rf._h, F._h(gpk), F._h(gvl), len(gpk), int(total), int(ncap), int(self.readlen), 0, mf,
+        rf._check(be.lib.ldd_field_chain(rf._h, F._h(gpk), F._h(gvl), len(gpk), int(total), int(plane_origin), int(ncap_total),
+                                         int(self.readlen), int(first_readsample), int(stop_readsample), int(bool(tolerant)), mf,
                                          C.cast(cb, C.c_void_p), None, C.cast(fields, C.c_void_p), F._h(batch.base),
                                          F._h(batch.winlen), F._h(readsample), F._h(batch.linelocs1.reshape(-1)),
                                          F._h(batch.linebad.reshape(-1)), F.LL_STRIDE, C.byref(nf)))
@@ -121,7 +159,7 @@ class CaptureDecoder:
 
     # -- host copies
     def pictures(self, res):
-        """uint16 TBC fields of all located windows -> list of (window index, array linecount*outlinelen)."""
+        """uint16 TBC fields of the located windows -> list of (readsample, istop, array | None)."""
         rf, be = self.rf, self.rf._be
         if res.d_pic is None:
             return []
@@ -130,7 +168,8 @@ class CaptureDecoder:
         st = be.to_host(res.d_status)
         W = rf.SysParams['outlinelen']
         out = []
-        for j, i in enumerate(res.located):
-            ok = (st[j] & (1 | 2 | 4 | 8)) == 0
-            out.append((i, pic[j, :res.infos[i].linecount * W].copy() if ok else None))
+        for k, j in enumerate(res.located):
+            ok = (st[k] & (1 | 2 | 4 | 8)) == 0
+            info = res.infos[j]
+            out.append((int(res.readsamples[j]), int(info.istop), pic[k, :info.linecount * W].copy() if ok else None))
         return out

@@ -1,0 +1,84 @@
+"""Whole-capture pipeline against the reference's field-by-field flow (oracle), and sharding."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from lddecode_b200 import _lib, pipeline, rfdecode, synth
+from oracle import ldd_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle_walk(dec, cap, nmax=10):
+    """Framer.readfield's loop (lddecode_core.py:1194-1223) with the oracle: list of FieldResult."""
+    ld = lambda s, n: cap[s:s + n] if s + n <= len(cap) else None
+    out, readsample = [], 0
+    while len(out) < nmax:
+        d = O.demod(dec, ld, readsample, 1000000, 1)
+        if d is None:
+            break
+        f = O.decode_field(dec, d[0], 0)
+        out.append((readsample, f))
+        readsample += f.nextfieldoffset
+    return out
+
+
+@pytest.mark.parametrize("system", ["NTSC", "PAL"])
+def test_pipeline_matches_reference_flow(backend, system):
+    fs = 8 * 315 / 88 if system == "NTSC" else 35.46895
+    ncap = 2100000 if system == "NTSC" else 2600000
+    cap = synth.SynthRF(system, fs, seed=9).generate(ncap)
+    rf = rfdecode.RFDecode(fs, system, 16384, decode_analog_audio=False, _backend=backend)
+    dec = O.Decoder(fs, system, 16384, analog_audio=False)
+    cd = pipeline.CaptureDecoder(rf)
+    res = cd.decode(backend.to_device(cap), _lib.FMT_U8, ncap, want_tables=True)
+    pics = cd.pictures(res)
+    ref = _oracle_walk(dec, cap)
+    assert res.nwindows == len(ref) == 3
+    for k, (readsample, f) in enumerate(ref):
+        info = res.infos[k]
+        assert int(res.readsamples[k]) == readsample
+        assert info.stage == _lib.FIELD_LOCATED and f.valid
+        assert info.nextfieldoffset == f.nextfieldoffset and info.npeaks == len(f.peaklist)
+        assert [[info.vsyncs[i][q] for q in range(3)] for i in range(2)] == [list(v) for v in f.vsyncs[:2]]
+        nll = f.linecount + 4
+        np.testing.assert_array_equal(res.linelocs1[k][:nll], np.array(f.linelocs1))
+        j = res.located.index(k)
+        np.testing.assert_allclose(res.refined.linelocs2[j][:nll], f.linelocs2, rtol=0, atol=1e-5)
+        np.testing.assert_allclose(res.refined.final[j][:nll] + res.refined.lineloc_add, f.linelocs, rtol=0, atol=1e-5)
+        d = pics[j][2].astype(np.int64) - f.dspicture.astype(np.int64)
+        assert np.abs(d).max() <= 1 and np.count_nonzero(d) < 0.002 * d.size
+
+
+def test_ranges_are_bit_identical_to_one_range(backend):
+    """Two read-position ranges (what two GPUs or two chunks would do), the second holding only the
+    part of the capture it needs, give exactly the fields of the single-range decode."""
+    from lddecode_b200 import parallel
+    fs = 8 * 315 / 88
+    ncap = 2600000
+    cap = synth.SynthRF("NTSC", fs, seed=9).generate(ncap)
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=False, _backend=backend)
+    cd = pipeline.CaptureDecoder(rf)
+    one = cd.pictures(cd.decode(backend.to_device(cap), _lib.FMT_U8, ncap))
+    parts = []
+    for r0, r1 in parallel.shard_bounds(ncap, 2):
+        lo, hi = parallel.needed_window(cd, ncap, r0, r1)
+        res = cd.decode_range(backend.to_device(cap[lo:hi]), _lib.FMT_U8, lo, hi - lo, ncap, r0, r1)
+        parts += cd.pictures(res)
+    assert len(parts) == len(one) == 4
+    for a, b in zip(parts, one):
+        assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2])
+
+
+def test_two_rank_gloo_gather():
+    """world_size 2 over gloo on the CPU (emulated kernels): shard, decode, gather on rank 0."""
+    script = os.path.join(ROOT, "tests", "dist_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", script],
+                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "GATHER_OK 4" in r.stdout, r.stdout[-3000:]

@@ -39,9 +39,9 @@ def one_second(system):
 
 
 def synth_capture(system, n, seed):
-    """Seeded synthetic capture, cached under gpurun_out/cache (generation is ~1.2 s per Msample)."""
+    """Seeded synthetic capture, cached under .bench_cache/ (generation is ~1.2 s per Msample)."""
     from lddecode_b200 import synth
-    cdir = os.path.join(ROOT, "gpurun_out", "cache")
+    cdir = os.path.join(ROOT, ".bench_cache")
     path = os.path.join(cdir, "%s_%d_%d.npy" % (system, n, seed))
     if os.path.exists(path):
         try:
@@ -325,7 +325,7 @@ def run_ours(a):
                                   bytes_per_sample=bytes_per_sample, kernel_ms=k_ms, kernel_msamples_per_s=planes_total / k_ms / 1e3,
                                   peak_source="MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"),
                     clocks=clk)
-        if world == 1:
+        if world == 1 and not a.skip_cpu:
             line["cpu_baseline"] = cpu_baseline(system, audio)
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -367,6 +367,7 @@ def main():
     ap.add_argument("--system", default="PAL", choices=["PAL", "NTSC"])
     ap.add_argument("--audio", action="store_true", help="also demodulate the two analog FM audio channels")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -24,26 +24,32 @@
 namespace ldd {
 
 // numpy's pairwise summation (umath loops, PW_BLOCKSIZE = 128), which np.mean / np.std use.
-LDD_HD inline double np_sum(const double* a, int n) {
+// Device code only ever sums <= 128 values, so the device-callable part has no recursion (a
+// recursive device function hides its stack need from the launch and overflows the frame).
+LDD_HD inline double np_sum_block(const double* a, int n) {       // n <= 128
     if (n < 8) {
         double res = 0.0;
         for (int i = 0; i < n; ++i) res += a[i];
         return res;
     }
-    if (n <= 128) {
-        double r[8];
-        for (int j = 0; j < 8; ++j) r[j] = a[j];
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8)
-            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
-        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-        for (; i < n; ++i) res += a[i];
-        return res;
-    }
+    double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i];
+    return res;
+}
+
+inline double np_sum_host(const double* a, int n) {              // any n (host)
+    if (n <= 128) return np_sum_block(a, n);
     int n2 = n / 2;
     n2 -= n2 % 8;
-    return np_sum(a, n2) + np_sum(a + n2, n - n2);
+    return np_sum_host(a, n2) + np_sum_host(a + n2, n - n2);
 }
+
+LDD_HD inline double np_sum(const double* a, int n) { return np_sum_block(a, n); }
 
 LDD_HD inline double np_mean(const double* a, int n) { return np_sum(a, n) / (double)n; }
 
@@ -197,7 +203,6 @@ __global__ void __launch_bounds__(256) refine_burst_kernel(const BurstParams p) 
     __shared__ double bas[8][BURST_N];
     __shared__ double taps[2 * BURST_K + 3];
     __shared__ double phase[2][512];
-    __shared__ unsigned char haveph[512];
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int linecount = p.linecount[f], nll = linecount + 4;
     const long long base = p.base[f];
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(256) refine_burst_kernel(const BurstParams p) 
         auto g = [&](int q) -> double { int a = q < 0 ? -q : q; return a > BURST_K ? 0.0 : c * pow(r, (double)a); };
         taps[m] = 6.0 * (g(k - 1) - 2.0 * g(k) + g(k + 1));
     }
-    for (int i = tid; i < 512; i += blockDim.x) { phase[0][i] = 0.0; phase[1][i] = 0.0; haveph[i] = 0; }
+    for (int i = tid; i < 512; i += blockDim.x) { phase[0][i] = 0.0; phase[1][i] = 0.0; }
     for (int i = tid; i < nll; i += blockDim.x) level[i] = 0.f;
     __syncthreads();
     const double hz_ire = 1700000.0 / 140.0;
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(256) refine_burst_kernel(const BurstParams p) 
     __syncthreads();
     if (tid == 0) {
         // medians of both columns over lines that produced a phase (lddecode_core.py:1112-1117)
-        double col[2][512];
+        double* col[2] = {&ys[0][0], &ys[4][0]};          // the staging buffers are free now: 2 x 1024 doubles
         int nc = 0;
         for (int l = 0; l < nll; ++l)
             if (phase[0][l] != 0 || phase[1][l] != 0) { col[0][nc] = phase[0][l]; col[1][nc] = phase[1][l]; ++nc; }
@@ -523,10 +528,10 @@ extern "C" int ldd_field_locate(ldd_handle* h, const long long* peaks, const dou
         lc.med = median_of(lv);
         double sd = NAN;
         if (!lv.empty()) {
-            double mean = np_mean(lv.data(), (int)lv.size());
+            double mean = np_sum_host(lv.data(), (int)lv.size()) / (double)lv.size();
             std::vector<double> dev(lv.size());
             for (size_t i = 0; i < lv.size(); ++i) { double q = lv[i] - mean; dev[i] = q * q; }
-            sd = std::sqrt(np_sum(dev.data(), (int)dev.size()) / (double)dev.size());
+            sd = std::sqrt(np_sum_host(dev.data(), (int)dev.size()) / (double)dev.size());
         }
         lc.tol = std::max(sd * 2, .01);          // python max(nan, .01) == nan; std::max(nan, .01) == nan too (first arg kept)
         out->med_hsync = lc.med;
@@ -686,7 +691,7 @@ extern "C" int ldd_refine_hsync(ldd_handle* h, const float* d05_dev, long long n
     p.linelocs1 = linelocs1_dev; p.linebad_in = linebad_dev; p.linelocs2 = linelocs2_dev; p.linebad_out = linebad_out_dev;
     p.status = status_dev;
     LDD_LAUNCH(refine_hsync_kernel, dim3(nfields), dim3(128), 0, (cudaStream_t)stream, p);
-    return cudaGetLastError() == cudaSuccess ? LDD_OK : LDD_ECUDA;
+    return launch_status(h, "refine_hsync_kernel");
 }
 
 extern "C" int ldd_refine_burst(ldd_handle* h, const float* burst_dev, long long n, const long long* base_dev,
@@ -701,7 +706,7 @@ extern "C" int ldd_refine_burst(ldd_handle* h, const float* burst_dev, long long
     p.base = base_dev; p.linecount = linecount_dev; p.ll_stride = ll_stride; p.linelocs_in = linelocs_in_dev;
     p.linelocs_out = linelocs_out_dev; p.burstlevel = burstlevel_dev; p.status = status_dev;
     LDD_LAUNCH(refine_burst_kernel, dim3(nfields), dim3(256), 0, (cudaStream_t)stream, p);
-    return cudaGetLastError() == cudaSuccess ? LDD_OK : LDD_ECUDA;
+    return launch_status(h, "refine_burst_kernel");
 }
 
 extern "C" int ldd_refine_pilot(ldd_handle* h, const float* demod_dev, const float* d05_dev, long long n,
@@ -724,7 +729,7 @@ extern "C" int ldd_refine_pilot(ldd_handle* h, const float* demod_dev, const flo
     p.base = base_dev; p.linecount = linecount_dev; p.ll_stride = ll_stride; p.linelocs_in = linelocs_in_dev;
     p.linelocs_out = linelocs_out_dev; p.status = status_dev;
     LDD_LAUNCH(refine_pilot_kernel, dim3(nfields), dim3(128), 0, st, p, offs, cnt);
-    return cudaGetLastError() == cudaSuccess ? LDD_OK : LDD_ECUDA;
+    return launch_status(h, "refine_pilot_kernel");
 }
 
 // ---------------------------------------------------------------------------------------------

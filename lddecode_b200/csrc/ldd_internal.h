@@ -6,6 +6,8 @@
 #include <string>
 #include <vector>
 
+struct ldd_handle;
+
 namespace ldd {
 
 // Everything the fused demodulation kernel needs, passed by value.
@@ -51,6 +53,9 @@ struct DemodParams {
     size_t scratch_per_cta;      // bytes
 };
 
+// cudaGetLastError() after a launch -> LDD_OK / LDD_ECUDA with the CUDA error text in h->err
+inline int launch_status(ldd_handle* h, const char* what);
+
 int launch_demod_f64(const DemodParams& p, int grid, cudaStream_t st);
 int launch_demod_f32(const DemodParams& p, int grid, cudaStream_t st, size_t smem_optin);
 
@@ -85,3 +90,10 @@ struct ldd_handle {
     void* pilot_ws = nullptr;
     size_t pilot_ws_bytes = 0;
 };
+
+inline int ldd::launch_status(ldd_handle* h, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return LDD_OK;
+    if (h) h->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return LDD_ECUDA;
+}

@@ -182,6 +182,5 @@ extern "C" int ldd_sync_peaks(ldd_handle* h, const double* sync_dev, long long n
     LDD_LAUNCH(peaks_phase1, dim3((g.nseg + warps - 1) / warps), dim3(32 * warps), 0, st, sync_dev, g, pos, val, cnt, iend);
     LDD_LAUNCH(peaks_phase2, dim3(1), dim3(32), 0, st, sync_dev, g, (const long long*)pos, (const double*)val,
                (const int*)cnt, (const long long*)iend, peaks_dev, vals_dev, cap, count_dev);
-    if (cudaGetLastError() != cudaSuccess) { h->err = "peak kernels failed to launch"; return LDD_ECUDA; }
-    return LDD_OK;
+    return launch_status(h, "peaks_phase1/2");
 }

@@ -177,6 +177,5 @@ extern "C" int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n
     cudaFuncSetAttribute(tbc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaStream_t st = (cudaStream_t)stream;
     LDD_LAUNCH(tbc_kernel, dim3(max_linecount, nfields), dim3(TBC_THREADS), smem, st, p);
-    if (cudaGetLastError() != cudaSuccess) { h->err = "tbc kernel failed to launch"; return LDD_ECUDA; }
-    return LDD_OK;
+    return launch_status(h, "tbc_kernel");
 }

@@ -166,15 +166,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken between wall-clock times t0 and t1 (the timed region)."""
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for (t, r) in self.rows if (t0 is None or t >= t0 - 0.11) and (t1 is None or t <= t1 + 0.11)]
+        for r in rows:
             p = [x.strip() for x in r.split(",")]
             if len(p) < 6:
                 continue
@@ -239,6 +241,11 @@ def run_ours(a):
         torch.cuda.current_stream().synchronize()
         return res, n
 
+    # the sampler is started before the warm-up: nvidia-smi's start-up stalls the driver for ~100 ms
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.5)
     # warm-up
     res = None
     for _ in range(max(a.warmup, 3)):
@@ -249,18 +256,16 @@ def run_ours(a):
     out_pin = torch.empty(max_fields * res.out_stride, dtype=torch.uint16).pin_memory()
 
     # resident timing
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.time()
     e0.record()
     for _ in range(a.steps):
         step_resident()
     e1.record()
     barrier()
+    tw1 = time.time()
     ms_total = e0.elapsed_time(e1)
-    clk = clocks.stop() if rank == 0 else None
 
     # end-to-end timing (host buffers)
     for _ in range(2):
@@ -274,6 +279,7 @@ def run_ours(a):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
     wall_e2e = (time.perf_counter() - t0) * 1e3
+    clk = clocks.stop(tw0, time.time()) if rank == 0 else None
 
     # dominant kernel alone: the fused block demodulation
     planes_total = demod_only(cd, cap_dev, ncap)

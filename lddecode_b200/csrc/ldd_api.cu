@@ -119,13 +119,24 @@ int ldd_create(const ldd_config* cfg, ldd_handle** out) {
         CUDA_TRY(h, cudaMalloc(&h->d_WNfull, (size_t)N * sizeof(Cx<double>)));
         CUDA_TRY(h, cudaMemcpy(h->d_WNfull, t.data(), (size_t)N * sizeof(Cx<double>), cudaMemcpyHostToDevice));
     }
-    // launch geometry / scratch of the demodulation kernel
+    // launch geometry / scratch of the demodulation kernel.  Tunables (development): LDD_THREADS,
+    // LDD_RADIX_MAX, LDD_CTAS_PER_SM.
+    const bool f64 = cfg->precision == LDD_PREC_F64;
     const char* env = getenv("LDD_CTAS_PER_SM");
-    int per_sm = env ? atoi(env) : 2;
+    int per_sm = env ? atoi(env) : 1;
     if (per_sm < 1) per_sm = 1;
-    size_t esz = cfg->precision == LDD_PREC_F64 ? sizeof(Cx<double>) : sizeof(Cx<float>);
+    env = getenv("LDD_THREADS");
+    h->threads = env ? atoi(env) : (f64 ? 256 : 512);
+    if (f64) { if (h->threads != 256 && h->threads != 512 && h->threads != 1024) h->threads = 256; }
+    else { if (h->threads != 512 && h->threads != 1024) h->threads = 512; }
+    env = getenv("LDD_RADIX_MAX");
+    h->radix_max = env ? atoi(env) : 16;
+    if (h->radix_max != 4 && h->radix_max != 8 && h->radix_max != 16) h->radix_max = 16;
+    size_t esz = f64 ? sizeof(Cx<double>) : sizeof(Cx<float>);
     size_t per_cta = (size_t)3 * M * esz;
-    bool smem_lane = cfg->precision == LDD_PREC_F32 && per_cta + 1024 <= h->smem_optin;
+    size_t per_cta_padded = (size_t)3 * pspan<true>(M) * esz;
+    bool smem_lane = !f64 && per_cta_padded + 2048 <= h->smem_optin;
+    h->smem_bytes = smem_lane ? per_cta_padded : 0;
     h->grid = smem_lane ? h->sm_count : h->sm_count * per_sm;
     h->scratch_per_cta = smem_lane ? 0 : per_cta;
     // audio phase 2 runs out of the same scratch: two length-N complex128 buffers per CTA
@@ -256,8 +267,8 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
     p.N = N; p.M = M; p.A = audio ? h->A : 0;
     p.blockcut = blockcut;
     p.nfilt = nfilt;
-    p.plan_m = make_plan(M);
-    if (p.A) { p.plan_a = make_plan(p.A); p.wstride_a = M / p.A; p.audio_ds = N / p.A; }
+    p.plan_m = make_plan(M, h->radix_max);
+    if (p.A) { p.plan_a = make_plan(p.A, h->radix_max); p.wstride_a = M / p.A; p.audio_ds = N / p.A; }
     p.rf = rf_dev; p.fmt = fmt;
     p.first_sample = first_sample - rf_base;
     p.stride = S;
@@ -291,8 +302,8 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
         CUDA_TRY(h, cudaMemsetAsync(audio1_r_dev, 0, (size_t)audio1_len * sizeof(double), st));
     }
     int rc;
-    if (lane == 0) rc = launch_demod_f64(p, grid, st);
-    else rc = launch_demod_f32(p, grid, st, h->scratch_per_cta ? 0 : (size_t)3 * M * sizeof(Cx<float>));
+    if (lane == 0) rc = launch_demod_f64(p, grid, h->threads, st);
+    else rc = launch_demod_f32(p, grid, h->threads, st, h->smem_bytes);
     if (rc) return fail(h, rc, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return LDD_OK;
 }

@@ -28,14 +28,14 @@ audio2_kernel(const double* __restrict__ in_l, const double* __restrict__ in_r, 
         double* out = job.ch ? out_r : out_l;
         for (int i = tid; i < N; i += nthr) b0[i] = mk<double>(in[job.in_start + i], 0.0);
         __syncthreads();
-        Cx<double>* spec = fft_run<double>(b0, b1, plan_n, WN, 1, tid, nthr);
+        Cx<double>* spec = fft_run<double, false>(b0, b1, plan_n, WN, 1, tid, nthr);
         Cx<double>* fr = (spec == b0) ? b1 : b0;
         for (int i = tid; i < Q; i += nthr) {
             Cx<double> s = (i < E) ? spec[i] : spec[N - Q + i];
             fr[i] = conj(s * lpf2[i]);
         }
         __syncthreads();
-        Cx<double>* r = fft_run<double>(fr, fr + Q, plan_q, WN, 4, tid, nthr);
+        Cx<double>* r = fft_run<double, false>(fr, fr + Q, plan_q, WN, 4, tid, nthr);
         const double sc = 1.0 / (double)N;       // 1/(N/4) of the inverse transform, / audio_fdiv2 = 4
         for (int i = job.skip + tid; i < Q; i += nthr) {
             long long o = job.out_pos + (i - job.skip);

@@ -50,7 +50,7 @@ __device__ inline int fetch_sample(const void* rf, int fmt, long long s) {
 }
 
 // ---- untangle: length-M FFT of z[n] = x[2n] + j x[2n+1]  ->  X[k], k = 0..M (X[M] packed in X[0].y)
-template <class T>
+template <class T, bool PAD>
 __device__ inline void untangle(Cx<T>* Z, int M, const Cx<T>* __restrict__ WN, int tid, int nthr) {
     const T half = (T)0.5;
     for (int k = tid; k <= M / 2; k += nthr) {
@@ -58,19 +58,20 @@ __device__ inline void untangle(Cx<T>* Z, int M, const Cx<T>* __restrict__ WN, i
             Cx<T> z = Z[0];
             Z[0] = mk<T>(z.x + z.y, z.x - z.y);
         } else {
-            Cx<T> a = Z[k], b = conj(Z[M - k]);
+            const int ik = pidx<PAD>(k), im = pidx<PAD>(M - k);
+            Cx<T> a = Z[ik], b = conj(Z[im]);
             Cx<T> E = scale(a + b, half);
             Cx<T> Od = scale(mul_mj(a - b), half);
             Cx<T> Tw = WN[k] * Od;
-            Z[k] = E + Tw;
-            Z[M - k] = conj(E - Tw);
+            Z[ik] = E + Tw;
+            Z[im] = conj(E - Tw);
         }
     }
 }
 
 // ---- tangle: conj-symmetric spectrum Y = D * F (k = 0..M)  ->  conj(Q), whose forward length-M
 // FFT r gives the real signal: y[2n] = r.x, y[2n+1] = -r.y (F carries the 1/M).
-template <class T>
+template <class T, bool PAD>
 __device__ inline void tangle(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __restrict__ F, int M,
                               const Cx<T>* __restrict__ WN, int tid, int nthr) {
     const T half = (T)0.5;
@@ -80,18 +81,19 @@ __device__ inline void tangle(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __restrict_
             T y0 = d.x * F[0].x, ym = d.y * F[M].x;
             Q[0] = mk<T>((y0 + ym) * half, -(y0 - ym) * half);
         } else {
-            Cx<T> a = D[k] * F[k], b = conj(D[M - k] * F[M - k]);
+            const int ik = pidx<PAD>(k), im = pidx<PAD>(M - k);
+            Cx<T> a = D[ik] * F[k], b = conj(D[im] * F[M - k]);
             Cx<T> E = scale(a + b, half);
             Cx<T> Od = mulc(scale(a - b, half), WN[k]);      // * W_N^{-k}
             Cx<T> q = E + mul_pj(Od);
             Cx<T> qm = conj(E) + mul_pj(conj(Od));
-            Q[k] = conj(q);
-            Q[M - k] = conj(qm);
+            Q[ik] = conj(q);
+            Q[im] = conj(qm);
         }
     }
 }
 
-template <class T, int NT>
+template <class T, int NT, bool PAD>
 __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int N = p.N, M = p.M;
@@ -106,8 +108,9 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
         LDD_DYN_SMEM(smem);
         b0 = (Cx<T>*)smem;
     }
-    Cx<T>* b1 = b0 + M;
-    Cx<T>* b2 = b1 + M;
+    Cx<T>* b1 = b0 + pspan<PAD>(M);
+    Cx<T>* b2 = b1 + pspan<PAD>(M);
+#define IX(i) pidx<PAD>(i)
     __shared__ double s_warp[32];
     __shared__ double s_total;
 
@@ -124,15 +127,15 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
         for (int n = tid; n < M; n += nthr) {
             int s0 = fetch_sample(p.rf, p.fmt, in0 + 2 * n);
             int s1 = fetch_sample(p.rf, p.fmt, in0 + 2 * n + 1);
-            b0[n] = mk<T>((T)s0, (T)s1);
+            b0[IX(n)] = mk<T>((T)s0, (T)s1);
         }
         __syncthreads();
 
         // B/C. X = rfft(x)
-        Cx<T>* X = fft_run<T>(b0, b1, p.plan_m, WM, 1, tid, nthr);
+        Cx<T>* X = fft_run<T, PAD>(b0, b1, p.plan_m, WM, 1, tid, nthr);
         Cx<T>* f1 = (X == b0) ? b1 : b0;      // free
         Cx<T>* f2 = b2;                        // free
-        untangle<T>(X, M, WN, tid, nthr);
+        untangle<T, PAD>(X, M, WN, tid, nthr);
         __syncthreads();
 
         // D. analog audio, phase 1 (lddecode_core.py:322-326): two length-A inverse transforms of a
@@ -144,17 +147,19 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
             Cx<T>* gl = f1;
             Cx<T>* gr = f2;
             for (int j = tid; j < A; j += nthr) {
-                Cx<T> xa = (j < hA) ? X[p.a_lo + j] : conj(X[p.a_hi - (j - hA)]);
-                gl[j] = conj(xa * AL[j]);
-                gr[j] = conj(xa * AR[j]);
+                Cx<T> xa = (j < hA) ? X[IX(p.a_lo + j)] : conj(X[IX(p.a_hi - (j - hA))]);
+                gl[IX(j)] = conj(xa * AL[j]);
+                gr[IX(j)] = conj(xa * AR[j]);
             }
             __syncthreads();
-            Cx<T>* rl = fft_run<T>(gl, gl + A, p.plan_a, WM, p.wstride_a, tid, nthr);
-            Cx<T>* rr = fft_run<T>(gr, gr + A, p.plan_a, WM, p.wstride_a, tid, nthr);
+            Cx<T>* rl = fft_run<T, PAD>(gl, gl + pspan<PAD>(A), p.plan_a, WM, p.wstride_a, tid, nthr);
+            Cx<T>* rr = fft_run<T, PAD>(gr, gr + pspan<PAD>(A), p.plan_a, WM, p.wstride_a, tid, nthr);
             // angles in place (x: left, y: right of the same sample) then neighbour difference
-            Cx<T>* ang = (rl == gl) ? gl + A : gl;   // the other half of f1
-            for (int j = tid; j < A; j += nthr)
-                ang[j] = mk<T>(Math<T>::atan2(-rl[j].y, rl[j].x), Math<T>::atan2(-rr[j].y, rr[j].x));
+            Cx<T>* ang = (rl == gl) ? gl + pspan<PAD>(A) : gl;   // the other half of f1
+            for (int j = tid; j < A; j += nthr) {
+                Cx<T> l = rl[IX(j)], r = rr[IX(j)];
+                ang[IX(j)] = mk<T>(Math<T>::atan2(-l.y, l.x), Math<T>::atan2(-r.y, r.x));
+            }
             __syncthreads();
             const int a0 = keep0 / p.audio_ds, a1 = keep1 / p.audio_ds;
             const long long ao = o / p.audio_ds;
@@ -162,8 +167,9 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
             for (int j = a0 + tid; j < a1; j += nthr) {
                 double dl = 0.0, dr = 0.0;
                 if (j > 0) {
-                    dl = (double)ang[j].x - (double)ang[j - 1].x;
-                    dr = (double)ang[j].y - (double)ang[j - 1].y;
+                    Cx<T> c1 = ang[IX(j)], c0 = ang[IX(j - 1)];
+                    dl = (double)c1.x - (double)c0.x;
+                    dr = (double)c1.y - (double)c0.y;
                     if (dl < 0) dl += twopi;
                     if (dr < 0) dr += twopi;
                 }
@@ -187,54 +193,57 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
                 U[0] = conj(y0 + y1);
                 V[0] = conj(y0 - y1);
             } else {
-                Cx<T> xa = X[k], xb = X[M - k];
+                const int ik = IX(k), im = IX(M - k);
+                Cx<T> xa = X[ik], xb = X[im];
                 Cx<T> y0 = xa * Hv[k], y1 = conj(xb) * Hv[k + M];
-                U[k] = conj(y0 + y1);
-                V[k] = conj(mulc(y0 - y1, WN[k]));
+                U[ik] = conj(y0 + y1);
+                V[ik] = conj(mulc(y0 - y1, WN[k]));
                 if (k != M - k) {
                     Cx<T> z0 = xb * Hv[M - k], z1 = conj(xa) * Hv[2 * M - k];
-                    U[M - k] = conj(z0 + z1);
+                    U[im] = conj(z0 + z1);
                     // W_N^{-(M-k)} = -conj(W_N^{-k}) = -W_N^{k}
                     Cx<T> d = z0 - z1;
-                    V[M - k] = conj(mk<T>(-d.x, -d.y) * WN[k]);
+                    V[im] = conj(mk<T>(-d.x, -d.y) * WN[k]);
                 }
             }
         }
         __syncthreads();
 
         // F. h[2n] = conj(ru[n]), h[2n+1] = conj(rv[n]) (up to a positive scale)
-        Cx<T>* ru = fft_run<T>(U, X, p.plan_m, WM, 1, tid, nthr);
+        Cx<T>* ru = fft_run<T, PAD>(U, X, p.plan_m, WM, 1, tid, nthr);
         Cx<T>* fu = (ru == U) ? X : U;
-        Cx<T>* rv = fft_run<T>(V, fu, p.plan_m, WM, 1, tid, nthr);
+        Cx<T>* rv = fft_run<T, PAD>(V, fu, p.plan_m, WM, 1, tid, nthr);
         Cx<T>* fv = (rv == V) ? fu : V;
 
         // G. FM discriminator (lddutils.py:320-334): angle, neighbour difference, fold to [0, 2pi),
         //    scale to Hz; minus ire0; packed for the next real transform.
-        for (int n = tid; n < M; n += nthr)
-            ru[n] = mk<T>(Math<T>::atan2(-ru[n].y, ru[n].x), Math<T>::atan2(-rv[n].y, rv[n].x));
+        for (int n = tid; n < M; n += nthr) {
+            Cx<T> a = ru[IX(n)], b = rv[IX(n)];
+            ru[IX(n)] = mk<T>(Math<T>::atan2(-a.y, a.x), Math<T>::atan2(-b.y, b.x));
+        }
         __syncthreads();
         {
             const T twopi = (T)6.283185307179586476925286766559;
             const T hz = (T)p.hz_per_rad, ire0 = (T)p.ire0;
             for (int n = tid; n < M; n += nthr) {
-                Cx<T> a = ru[n];
+                Cx<T> a = ru[IX(n)];
                 T d0 = (T)0;
                 if (n > 0) {
-                    d0 = a.x - ru[n - 1].y;
+                    d0 = a.x - ru[IX(n - 1)].y;
                     if (d0 < 0) d0 += twopi;
                 }
                 T d1 = a.y - a.x;
                 if (d1 < 0) d1 += twopi;
-                rv[n] = mk<T>(d0 * hz - ire0, d1 * hz - ire0);
+                rv[IX(n)] = mk<T>(d0 * hz - ire0, d1 * hz - ire0);
             }
         }
         __syncthreads();
 
         // H. D = rfft(demod - ire0)
-        Cx<T>* D = fft_run<T>(rv, ru, p.plan_m, WM, 1, tid, nthr);
+        Cx<T>* D = fft_run<T, PAD>(rv, ru, p.plan_m, WM, 1, tid, nthr);
         Cx<T>* g1 = (D == rv) ? ru : rv;
         Cx<T>* g2 = fv;
-        untangle<T>(D, M, WN, tid, nthr);
+        untangle<T, PAD>(D, M, WN, tid, nthr);
         __syncthreads();
 
         // I. post filters.  Order: video, burst, (pilot), video05 last because its whole block feeds the sync scan.
@@ -244,14 +253,14 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
         for (int oi = 0; oi < 4; ++oi) {
             const int m = order[oi];
             if (m >= p.nfilt && m != 1) continue;
-            tangle<T>(D, g1, (const Cx<T>*)p.F[m], M, WN, tid, nthr);
+            tangle<T, PAD>(D, g1, (const Cx<T>*)p.F[m], M, WN, tid, nthr);
             __syncthreads();
-            Cx<T>* r = fft_run<T>(g1, g2, p.plan_m, WM, 1, tid, nthr);
+            Cx<T>* r = fft_run<T, PAD>(g1, g2, p.plan_m, WM, 1, tid, nthr);
             float* out = (float*)p.plane[pl_of[m]];
             const T addc = (T)p.addc[m];
             // kept samples 2n, 2n+1 -> out[o + 2n - keep0]; keep0, o and copylen parity: handle singly
             for (int n = tid; n < M; n += nthr) {
-                Cx<T> v = r[n];
+                Cx<T> v = r[IX(n)];
                 int i0 = 2 * n, i1 = 2 * n + 1;
                 float v0 = (float)(v.x + addc), v1 = (float)(-v.y + addc);
                 if (i0 >= keep0 && i0 < keep1) out[o + (i0 - keep0)] = v0;
@@ -270,7 +279,7 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
             const int n0 = tid * CH;
             auto insync = [&](int n) -> double {
                 n = (n + N) & (N - 1);
-                double v = (double)x05[n];
+                double v = (double)x05[2 * IX(n >> 1) + (n & 1)];
                 if (n & 1) v = -v;
                 v += add;
                 return (v >= p.sync_lo && v <= p.sync_hi) ? 1.0 : 0.0;
@@ -331,19 +340,29 @@ static int check_launch(const char* what) {
     return LDD_OK;
 }
 
-int launch_demod_f64(const DemodParams& p, int grid, cudaStream_t st) {
-    void (*kern)(const DemodParams) = demod_kernel<double, 256>;
-    LDD_LAUNCH(kern, dim3(grid), dim3(256), 0, st, p);
-    return check_launch("demod_kernel<double>");
+template <class T, int NT, bool PAD>
+static int launch_variant(const DemodParams& p, int grid, cudaStream_t st, size_t smem_bytes) {
+    void (*kern)(const DemodParams) = demod_kernel<T, NT, PAD>;
+    if (smem_bytes) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    LDD_LAUNCH(kern, dim3(grid), dim3(NT), smem_bytes, st, p);
+    return check_launch("demod_kernel");
 }
 
-int launch_demod_f32(const DemodParams& p, int grid, cudaStream_t st, size_t smem_bytes) {
-    void (*kern)(const DemodParams) = demod_kernel<float, 512>;
-    if (smem_bytes) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+int launch_demod_f64(const DemodParams& p, int grid, int threads, cudaStream_t st) {
+    switch (threads) {
+        case 1024: return launch_variant<double, 1024, false>(p, grid, st, 0);
+        case 512: return launch_variant<double, 512, false>(p, grid, st, 0);
+        default: return launch_variant<double, 256, false>(p, grid, st, 0);
     }
-    LDD_LAUNCH(kern, dim3(grid), dim3(512), smem_bytes, st, p);
-    return check_launch("demod_kernel<float>");
+}
+
+int launch_demod_f32(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t smem_bytes) {
+    if (smem_bytes) {
+        if (threads == 1024) return launch_variant<float, 1024, true>(p, grid, st, smem_bytes);
+        return launch_variant<float, 512, true>(p, grid, st, smem_bytes);
+    }
+    if (threads == 1024) return launch_variant<float, 1024, false>(p, grid, st, 0);
+    return launch_variant<float, 512, false>(p, grid, st, 0);
 }
 
 }  // namespace ldd

@@ -86,17 +86,23 @@ template <class T> struct Dft<T, 16> {
     }
 };
 
+// Shared-memory lane: one padding element after every 16 keeps the stride-R stores of the first
+// Stockham passes off a single bank pair (a complex64 spans two banks; stride 16 elements = 128 B
+// would put all 32 lanes on the same two banks).  Global-memory lane: identity.
+template <bool PAD> LDD_HD inline int pidx(int i) { return PAD ? i + (i >> 4) : i; }
+template <bool PAD> LDD_HD inline int pspan(int n) { return PAD ? n + (n >> 4) : n; }
+
 // ---- one Stockham pass -------------------------------------------------------------------------
 // src, dst: length-M sequences.  Ns: product of the radices of the passes already done.
 // W: table of e^{-2 pi i k / Mtab}, k in [0, Mtab); wstride = Mtab / M.
-template <class T, int R>
+template <class T, int R, bool PAD>
 __device__ inline void fft_pass(const Cx<T>* src, Cx<T>* dst, int M, int Ns,
                                 const Cx<T>* __restrict__ W, int wstride, int tid, int nthr) {
     const int nb = M / R;
     for (int j = tid; j < nb; j += nthr) {
         Cx<T> v[R];
         LDD_UNROLL
-        for (int r = 0; r < R; ++r) v[r] = src[j + r * nb];
+        for (int r = 0; r < R; ++r) v[r] = src[pidx<PAD>(j + r * nb)];
         const int k = j & (Ns - 1);
         if (Ns > 1) {
             // w^r by repeated squaring / short products from one table lookup (<= 4 products deep)
@@ -110,37 +116,37 @@ __device__ inline void fft_pass(const Cx<T>* src, Cx<T>* dst, int M, int Ns,
         Dft<T, R>::run(v);
         const int j0 = (j - k) * R + k;
         LDD_UNROLL
-        for (int r = 0; r < R; ++r) dst[j0 + r * Ns] = v[r];
+        for (int r = 0; r < R; ++r) dst[pidx<PAD>(j0 + r * Ns)] = v[r];
     }
 }
 
 struct FftPlan {
     int n;            // transform length (power of two)
     int npass;
-    int radix[8];
+    int radix[16];
 };
 
-inline FftPlan make_plan(int n) {
+inline FftPlan make_plan(int n, int rmax = 16) {
     FftPlan p;
     p.n = n;
     p.npass = 0;
     int rem = n;
-    while (rem >= 16 && p.npass < 8) { p.radix[p.npass++] = 16; rem /= 16; }
-    if (rem > 1) p.radix[p.npass++] = rem;       // 2, 4 or 8
+    while (rem >= rmax && p.npass < 15) { p.radix[p.npass++] = rmax; rem /= rmax; }
+    if (rem > 1) p.radix[p.npass++] = rem;       // a smaller power of two
     return p;
 }
 
 // Runs all passes; the result is in the returned pointer (a or b).  Ends with a barrier.
-template <class T>
+template <class T, bool PAD>
 __device__ inline Cx<T>* fft_run(Cx<T>* a, Cx<T>* b, const FftPlan& plan, const Cx<T>* __restrict__ W,
                                  int wstride, int tid, int nthr) {
     int Ns = 1;
     for (int p = 0; p < plan.npass; ++p) {
         switch (plan.radix[p]) {
-            case 16: fft_pass<T, 16>(a, b, plan.n, Ns, W, wstride, tid, nthr); break;
-            case 8: fft_pass<T, 8>(a, b, plan.n, Ns, W, wstride, tid, nthr); break;
-            case 4: fft_pass<T, 4>(a, b, plan.n, Ns, W, wstride, tid, nthr); break;
-            default: fft_pass<T, 2>(a, b, plan.n, Ns, W, wstride, tid, nthr); break;
+            case 16: fft_pass<T, 16, PAD>(a, b, plan.n, Ns, W, wstride, tid, nthr); break;
+            case 8: fft_pass<T, 8, PAD>(a, b, plan.n, Ns, W, wstride, tid, nthr); break;
+            case 4: fft_pass<T, 4, PAD>(a, b, plan.n, Ns, W, wstride, tid, nthr); break;
+            default: fft_pass<T, 2, PAD>(a, b, plan.n, Ns, W, wstride, tid, nthr); break;
         }
         Ns *= plan.radix[p];
         Cx<T>* t = a; a = b; b = t;

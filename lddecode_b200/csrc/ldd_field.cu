@@ -412,39 +412,82 @@ __global__ void __launch_bounds__(128) refine_pilot_kernel(const PilotParams p, 
         cnt[l] = n;
     }
     __syncthreads();
-    // median of all offsets (np.median(alloffsets)): exact order statistics by bisection on the value
-    // (offsets are fractional parts in [0, 1)), the counting spread over the CTA.
-    __shared__ int s_cnt;
-    __shared__ double s_min[128];
+    // median of all offsets (np.median(alloffsets)): exact order statistics by multi-level histogram
+    // selection (offsets are fractional parts in [0, 1)): 4096 bins over the current range, descend
+    // into the bin holding the k-th value until it holds few enough values to sort.
+    __shared__ int s_hist[4096];
+    __shared__ double s_list[256];
+    __shared__ int s_n, s_bin, s_before;
     __shared__ double s_tgt;
     int total = 0;
     for (int l = 0; l < nll; ++l) total += cnt[l];
     auto kth = [&](int k) -> double {
-        double lo = -1.0, hi = 1.0;
-        for (int it = 0; it < 70; ++it) {
-            double mid = 0.5 * (lo + hi);
-            if (tid == 0) s_cnt = 0;
+        double lo = 0.0, width = 1.0;          // current range [lo, lo + width)
+        int kk = k;                              // rank inside the range
+        double result = 0.0;
+        for (int level = 0; level < 6; ++level) {
+            for (int i = tid; i < 4096; i += blockDim.x) s_hist[i] = 0;
+            if (tid == 0) s_n = 0;
             __syncthreads();
-            int c = 0;
+            const double scale = 4096.0 / width;
             for (int l = tid; l < nll; l += blockDim.x) {
                 const double* my = offs + (size_t)l * PILOT_MAXOFF;
-                for (int q = 0; q < cnt[l]; ++q) c += my[q] <= mid;
+                for (int q = 0; q < cnt[l]; ++q) {
+                    double v = my[q];
+                    if (v >= lo && v < lo + width) {
+                        int b = (int)((v - lo) * scale);
+                        b = b > 4095 ? 4095 : b;
+                        atomicAdd(&s_hist[b], 1);
+                    }
+                }
             }
-            atomicAdd(&s_cnt, c);
             __syncthreads();
-            if (s_cnt >= k + 1) hi = mid; else lo = mid;
+            if (tid == 0) {
+                int cum = 0, b = 0;
+                for (; b < 4096; ++b) { if (cum + s_hist[b] > kk) break; cum += s_hist[b]; }
+                s_bin = b > 4095 ? 4095 : b;
+                s_before = cum;
+            }
+            __syncthreads();
+            const int bin = s_bin, inbin = s_hist[bin];
+            const double blo = lo + (double)bin / scale, bhi = lo + (double)(bin + 1) / scale;
+            if (inbin <= 256 || level == 5) {
+                // gather the bin's values (re-binning decides membership, so edges are consistent)
+                for (int l = tid; l < nll; l += blockDim.x) {
+                    const double* my = offs + (size_t)l * PILOT_MAXOFF;
+                    for (int q = 0; q < cnt[l]; ++q) {
+                        double v = my[q];
+                        if (v >= lo && v < lo + width) {
+                            int b = (int)((v - lo) * scale);
+                            b = b > 4095 ? 4095 : b;
+                            if (b == bin) { int at = atomicAdd(&s_n, 1); if (at < 256) s_list[at] = v; }
+                        }
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int n = s_n < 256 ? s_n : 256;
+                    for (int i = 1; i < n; ++i) {
+                        double x = s_list[i];
+                        int j = i - 1;
+                        while (j >= 0 && s_list[j] > x) { s_list[j + 1] = s_list[j]; --j; }
+                        s_list[j + 1] = x;
+                    }
+                    int r = kk - s_before;
+                    r = r < 0 ? 0 : (r >= n ? n - 1 : r);
+                    s_list[0] = s_list[r];
+                }
+                __syncthreads();
+                result = s_list[0];
+                __syncthreads();
+                return result;
+            }
+            kk -= s_before;
+            lo = blo;
+            width = bhi - blo;
             __syncthreads();
         }
-        double best = 2.0;
-        for (int l = tid; l < nll; l += blockDim.x) {
-            const double* my = offs + (size_t)l * PILOT_MAXOFF;
-            for (int q = 0; q < cnt[l]; ++q) if (my[q] > lo && my[q] < best) best = my[q];
-        }
-        s_min[tid] = best;
-        __syncthreads();
-        for (int i = 0; i < (int)blockDim.x; ++i) best = s_min[i] < best ? s_min[i] : best;
-        __syncthreads();
-        return best;
+        return result;
     };
     double tgt = 0;
     if (total > 0) {

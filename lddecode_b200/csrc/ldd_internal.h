@@ -56,8 +56,8 @@ struct DemodParams {
 // cudaGetLastError() after a launch -> LDD_OK / LDD_ECUDA with the CUDA error text in h->err
 inline int launch_status(ldd_handle* h, const char* what);
 
-int launch_demod_f64(const DemodParams& p, int grid, cudaStream_t st);
-int launch_demod_f32(const DemodParams& p, int grid, cudaStream_t st, size_t smem_optin);
+int launch_demod_f64(const DemodParams& p, int grid, int threads, cudaStream_t st);
+int launch_demod_f32(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t smem_bytes);
 
 }  // namespace ldd
 
@@ -81,6 +81,9 @@ struct ldd_handle {
     size_t scratch_bytes;
     size_t scratch_per_cta;
     int grid;
+    int threads;      // CTA size of the demodulation kernel
+    int radix_max;    // largest Stockham radix used
+    size_t smem_bytes;
     // audio phase 2
     void* d_lpf2;     // Cx<double>[N/4]
     void* d_WNfull;   // e^{-2 pi i k/N}, k<N (double) for the phase-2 transforms

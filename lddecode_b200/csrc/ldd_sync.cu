@@ -24,7 +24,15 @@ __device__ inline ArgMax warp_argmax(const double* __restrict__ ds, long long i,
     ArgMax b;
     b.v = -1e300;
     b.idx = 0x7fffffff;
-    for (int k = lane; k < len; k += 32) {
+    int k = lane;
+    for (; k + 96 < len; k += 128) {            // four independent loads in flight per lane
+        double v0 = ds[i + k], v1 = ds[i + k + 32], v2 = ds[i + k + 64], v3 = ds[i + k + 96];
+        if (v0 > b.v) { b.v = v0; b.idx = k; }
+        if (v1 > b.v) { b.v = v1; b.idx = k + 32; }
+        if (v2 > b.v) { b.v = v2; b.idx = k + 64; }
+        if (v3 > b.v) { b.v = v3; b.idx = k + 96; }
+    }
+    for (; k < len; k += 32) {
         double v = ds[i + k];
         if (v > b.v) { b.v = v; b.idx = k; }
     }
@@ -69,13 +77,84 @@ __global__ void __launch_bounds__(128) peaks_phase1(const double* __restrict__ d
     if (lane == 0) { cnt[s] = c < g.cap_seg ? c : g.cap_seg; iend[s] = i; }
 }
 
-// Phase 2: one warp, warp-uniform control flow.  out_count[0] = number of peaks (may exceed cap:
-// then only the first cap are stored), out_count[1] = number of chase steps taken here (0 when
-// every chain merged inside its overlap).
+// Phase 2a: one thread per segment boundary finds where the chain of segment s and the chain of
+// segment s+1 first share a peak (they are identical from there on).  hi[s] = number of peaks of
+// segment s that belong to the true chain, lo[s+1] = index of the shared peak in segment s+1's list;
+// merged[s] = 0 when the two chains did not meet inside the overlap.
+__global__ void __launch_bounds__(128) peaks_merge(PeakGeom g, const long long* __restrict__ pos, const int* __restrict__ cnt,
+                                                   int* __restrict__ hi, int* __restrict__ lo, int* __restrict__ merged,
+                                                   int* __restrict__ any_unmerged) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) lo[0] = 0;
+    if (s >= g.nseg) return;
+    const long long* p = pos + (size_t)s * g.cap_seg;
+    const int c = cnt[s];
+    if (s == g.nseg - 1) { hi[s] = c; merged[s] = 1; return; }
+    const long long* q = pos + (size_t)(s + 1) * g.cap_seg;
+    const int cq = cnt[s + 1];
+    const long long xt = g.start + (long long)(s + 1) * g.seg;
+    // first peak of this chain at or beyond the next segment's start (binary search)
+    int a0 = 0, a1 = c;
+    while (a0 < a1) { int m = (a0 + a1) >> 1; if (p[m] < xt) a0 = m + 1; else a1 = m; }
+    int a = a0, b = 0, ok = 0;
+    while (a < c && b < cq) {
+        long long pa = p[a], qb = q[b];
+        if (pa == qb) { ok = 1; break; }
+        if (pa < qb) ++a; else ++b;
+    }
+    hi[s] = ok ? a : c;
+    lo[s + 1] = ok ? b : 0;
+    merged[s] = ok;
+    if (!ok) atomicOr(any_unmerged, 1);
+}
+
+// Phase 2b (all chains merged -- the normal case): prefix sum of the per-segment counts by one
+// warp, then every thread block copies its share.  One CTA.
+__global__ void __launch_bounds__(1024) peaks_gather(PeakGeom g, const long long* __restrict__ pos, const double* __restrict__ val,
+                                                     const int* __restrict__ hi, const int* __restrict__ lo,
+                                                     const int* __restrict__ any_unmerged, int* __restrict__ offs,
+                                                     long long* __restrict__ out_pos, double* __restrict__ out_val, int cap,
+                                                     int* __restrict__ out_count) {
+    if (*any_unmerged) return;                  // the sequential kernel below produces the list instead
+    const int tid = threadIdx.x;
+    if (tid < 32) {
+        int run = 0;
+        for (int base = 0; base < g.nseg; base += 32) {
+            int s = base + tid;
+            int n = 0;
+            if (s < g.nseg) { n = hi[s] - lo[s]; n = n > 0 ? n : 0; }
+            int incl = n;
+            for (int d = 1; d < 32; d <<= 1) {
+                int up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (tid >= d) incl += up;
+            }
+            if (s < g.nseg) offs[s] = run + incl - n;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (tid == 0) { out_count[0] = run; out_count[1] = 0; }
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+    for (int s = warp; s < g.nseg; s += nwarp) {
+        const long long* p = pos + (size_t)s * g.cap_seg;
+        const double* v = val + (size_t)s * g.cap_seg;
+        const int l = lo[s], h = hi[s], o = offs[s];
+        for (int k = l + lane; k < h; k += 32) {
+            int d = o + (k - l);
+            if (d < cap) { out_pos[d] = p[k]; out_val[d] = v[k]; }
+        }
+    }
+}
+
+// Phase 2 (general): one warp, warp-uniform control flow; runs only when some chain did not merge
+// inside its overlap.  out_count[0] = number of peaks (may exceed cap: then only the first cap are
+// stored), out_count[1] = number of chase steps taken here.
 __global__ void __launch_bounds__(32) peaks_phase2(const double* __restrict__ ds, PeakGeom g, const long long* __restrict__ pos,
                                                    const double* __restrict__ val, const int* __restrict__ cnt,
-                                                   const long long* __restrict__ iend, long long* __restrict__ out_pos,
+                                                   const long long* __restrict__ iend, const int* __restrict__ any_unmerged,
+                                                   long long* __restrict__ out_pos,
                                                    double* __restrict__ out_val, int cap, int* __restrict__ out_count) {
+    if (!*any_unmerged) return;
     const int lane = threadIdx.x;
     int n_out = 0, extra = 0;
     int s = 0, lo = 0;
@@ -94,7 +173,7 @@ __global__ void __launch_bounds__(32) peaks_phase2(const double* __restrict__ ds
         long long xt = g.start + (long long)t * g.seg;
         int a = lo;
         while (a < c && p[a] < xt) ++a;
-        int a_first = a, b = 0;
+        int b = 0;
         bool merged = false;
         {
             const long long* q = pos + (size_t)t * g.cap_seg;
@@ -104,7 +183,6 @@ __global__ void __launch_bounds__(32) peaks_phase2(const double* __restrict__ ds
                 if (p[a] < q[b]) ++a; else ++b;
             }
         }
-        (void)a_first;
         int hi = merged ? a : c;
         for (int k = lo + lane; k < hi; k += 32)
             if (n_out + (k - lo) < cap) { out_pos[n_out + (k - lo)] = p[k]; out_val[n_out + (k - lo)] = v[k]; }
@@ -158,15 +236,16 @@ extern "C" int ldd_sync_peaks(ldd_handle* h, const double* sync_dev, long long n
         return LDD_OK;
     }
     const char* env = getenv("LDD_PEAK_SEG_LINES");
-    long long seg_lines = env ? atoll(env) : 48;
+    long long seg_lines = env ? atoll(env) : 12;
     if (seg_lines < 4) seg_lines = 4;
     g.seg = seg_lines * L;
     g.ov = 6LL * L;
+    if (g.ov > g.seg) g.ov = g.seg;      // a chain must merge before the next boundary for the boundaries to be independent
     long long span = g.limit - start;
     g.nseg = (int)((span + g.seg - 1) / g.seg);
     if (g.nseg < 1) g.nseg = 1;
     g.cap_seg = (int)((g.seg + g.ov) / (g.skip > 0 ? g.skip : 1)) + 4;
-    size_t need = (size_t)g.nseg * g.cap_seg * (sizeof(long long) + sizeof(double)) + (size_t)g.nseg * (sizeof(int) + sizeof(long long)) + 64;
+    size_t need = (size_t)g.nseg * g.cap_seg * (sizeof(long long) + sizeof(double)) + (size_t)g.nseg * (5 * sizeof(int) + sizeof(long long)) + 128;
     if (need > h->peak_ws_bytes) {
         if (h->peak_ws) { cudaStreamSynchronize(st); cudaFree(h->peak_ws); h->peak_ws = nullptr; }
         size_t grow = need + need / 2;
@@ -177,10 +256,20 @@ extern "C" int ldd_sync_peaks(ldd_handle* h, const double* sync_dev, long long n
     long long* pos = (long long*)w;                 w += (size_t)g.nseg * g.cap_seg * sizeof(long long);
     double* val = (double*)w;                       w += (size_t)g.nseg * g.cap_seg * sizeof(double);
     long long* iend = (long long*)w;                w += (size_t)g.nseg * sizeof(long long);
-    int* cnt = (int*)w;
+    int* cnt = (int*)w;                             w += (size_t)g.nseg * sizeof(int);
+    int* hi = (int*)w;                              w += (size_t)g.nseg * sizeof(int);
+    int* lo = (int*)w;                              w += (size_t)g.nseg * sizeof(int);
+    int* merged = (int*)w;                          w += (size_t)g.nseg * sizeof(int);
+    int* offs = (int*)w;                            w += (size_t)g.nseg * sizeof(int);
+    int* any_unmerged = (int*)w;
     const int warps = 4;
+    cudaMemsetAsync(any_unmerged, 0, sizeof(int), st);
     LDD_LAUNCH(peaks_phase1, dim3((g.nseg + warps - 1) / warps), dim3(32 * warps), 0, st, sync_dev, g, pos, val, cnt, iend);
+    LDD_LAUNCH(peaks_merge, dim3((g.nseg + 127) / 128), dim3(128), 0, st, g, (const long long*)pos, (const int*)cnt, hi, lo, merged,
+               any_unmerged);
+    LDD_LAUNCH(peaks_gather, dim3(1), dim3(1024), 0, st, g, (const long long*)pos, (const double*)val, (const int*)hi,
+               (const int*)lo, (const int*)any_unmerged, offs, peaks_dev, vals_dev, cap, count_dev);
     LDD_LAUNCH(peaks_phase2, dim3(1), dim3(32), 0, st, sync_dev, g, (const long long*)pos, (const double*)val,
-               (const int*)cnt, (const long long*)iend, peaks_dev, vals_dev, cap, count_dev);
+               (const int*)cnt, (const long long*)iend, (const int*)any_unmerged, peaks_dev, vals_dev, cap, count_dev);
     return launch_status(h, "peaks_phase1/2");
 }

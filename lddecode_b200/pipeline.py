@@ -134,20 +134,42 @@ class CaptureDecoder:
         readsample = np.zeros(mf, dtype=np.int64)
         nf = C.c_int(0)
         keep = {}
+        gpk = np.ascontiguousarray(gpk, dtype=np.int64)
+        gvl = np.ascontiguousarray(gvl, dtype=np.float64)
+
+        L = rf.linelen
+        half, skip = L // 2, int(L * .4)
 
         def window_peaks(ctx, b, wl, ppk, pvl, pn):
-            # this window does not start on a peak of the range's chase: chase it by itself
-            sync = planes['demod_sync'][int(b):int(b + wl)]
-            pk, vl = F.sync_peaks_device(rf, sync, int(wl), 0)
-            keep['pk'], keep['vl'] = np.ascontiguousarray(pk), np.ascontiguousarray(vl)
+            # This window does not start on a peak of the range's chase (second read of a capture,
+            # range starts).  Chase a short prefix by itself; from the first peak it shares with the
+            # range's chase on, the two lists are the same, cut at the reference's loop bound.
+            b, wl = int(b), int(wl)
+            pk = vl = None
+            npre = min(wl, 40 * L)
+            spk, svl = F.sync_peaks_device(rf, planes['demod_sync'][b:b + npre], npre, 0)
+            common = np.nonzero(np.isin(spk + b, gpk))[0]
+            if len(common):
+                k = int(common[0])
+                m = int(np.searchsorted(gpk, spk[k] + b))
+                pk = np.concatenate([spk[:k], gpk[m:] - b])
+                vl = np.concatenate([svl[:k], gvl[m:]])
+                # a peak belongs to the window's list iff the step that found it started below the bound
+                limit = wl - 2 * L
+                i0 = np.concatenate([[0], pk[:-1] + skip])
+                istep = i0 + ((pk - i0) // half) * half
+                stop = np.nonzero(istep >= limit)[0]
+                n = int(stop[0]) if len(stop) else len(pk)
+                pk, vl = pk[:n], vl[:n]
+            else:
+                pk, vl = F.sync_peaks_device(rf, planes['demod_sync'][b:b + wl], wl, 0)
+            keep['pk'], keep['vl'] = np.ascontiguousarray(pk, dtype=np.int64), np.ascontiguousarray(vl, dtype=np.float64)
             ppk[0] = keep['pk'].ctypes.data
             pvl[0] = keep['vl'].ctypes.data
             pn[0] = len(pk)
             return 0
 
         cb = _lib.WINDOW_PEAKS_FN(window_peaks)
-        gpk = np.ascontiguousarray(gpk, dtype=np.int64)
-        gvl = np.ascontiguousarray(gvl, dtype=np.float64)
         rf._check(be.lib.ldd_field_chain(rf._h, F._h(gpk), F._h(gvl), len(gpk), int(total), int(plane_origin), int(ncap_total),
                                          int(self.readlen), int(first_readsample), int(stop_readsample), int(bool(tolerant)), mf,
                                          C.cast(cb, C.c_void_p), None, C.cast(fields, C.c_void_p), F._h(batch.base),

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Quick GPU probe of the demod kernel (development aid): Msamples/s of ldd_demod_blocks for both
-precision lanes over a synthetic capture resident in HBM."""
+"""Quick GPU probe of the demod kernel variants (development aid): Msamples/s of ldd_demod_blocks
+over a synthetic capture resident in HBM, for precision x CTA size x max radix."""
 import json
 import os
 import sys
@@ -15,7 +15,10 @@ import torch  # noqa: E402
 from lddecode_b200 import _lib, rfdecode, synth  # noqa: E402
 
 
-def run(system, fs, N, prec, cap_dev, ncap, audio, reps=5):
+def run(system, fs, N, prec, cap_dev, ncap, audio, threads, radix, ctas=1, reps=5):
+    os.environ["LDD_THREADS"] = str(threads)
+    os.environ["LDD_RADIX_MAX"] = str(radix)
+    os.environ["LDD_CTAS_PER_SM"] = str(ctas)
     rf = rfdecode.RFDecode(fs, system, N, decode_analog_audio=audio, precision=prec)
     length = ncap - 2 * N - 2048
     for i in range(2):
@@ -30,27 +33,30 @@ def run(system, fs, N, prec, cap_dev, ncap, audio, reps=5):
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     ms = min(ts)
-    return dict(system=system, N=N, prec=prec, audio=audio, ms=ms, msps=length / ms / 1e3, ctas=os.environ.get("LDD_CTAS_PER_SM", "2"))
+    del out
+    return dict(system=system, N=N, prec=prec, audio=audio, threads=threads, radix=radix, ctas=ctas, ms=round(ms, 3),
+                msps=round(length / ms / 1e3, 1))
 
 
 def main():
-    fs = 8 * 315 / 88
-    n = int(os.environ.get("NSAMP", 12000000))
-    t = time.time()
-    one = synth.SynthRF("NTSC", fs, seed=0).generate(2000000)
+    system = os.environ.get("SYSTEM", "PAL")
+    fs = 8 * 315 / 88 if system == "NTSC" else 35.46895
+    n = int(os.environ.get("NSAMP", 36000000))
+    one = synth.SynthRF(system, fs, seed=0).generate(2000000)
     cap = np.tile(one, n // len(one))
-    print("gen", time.time() - t, len(cap))
     cap_dev = torch.from_numpy(cap).cuda()
     res = []
-    for prec in ("f64", "f32"):
-        for N in (16384, 32768, 65536):
-            for audio in (True, False):
-                try:
-                    r = run("NTSC", fs, N, prec, cap_dev, len(cap), audio)
-                except Exception as e:
-                    r = dict(N=N, prec=prec, audio=audio, error=str(e))
-                print(json.dumps(r), flush=True)
-                res.append(r)
+    variants = [("f64", 256, 16, 1), ("f64", 512, 16, 1), ("f64", 512, 8, 1), ("f64", 1024, 8, 1), ("f64", 1024, 4, 1),
+                ("f64", 256, 8, 2), ("f64", 512, 8, 2),
+                ("f32", 512, 16, 1), ("f32", 512, 8, 1), ("f32", 1024, 8, 1), ("f32", 1024, 4, 1)]
+    for N in (16384, 32768):
+        for prec, thr, rad, ctas in variants:
+            try:
+                r = run(system, fs, N, prec, cap_dev, len(cap), False, thr, rad, ctas)
+            except Exception as e:
+                r = dict(N=N, prec=prec, threads=thr, radix=rad, error=str(e)[:200])
+            print(json.dumps(r), flush=True)
+            res.append(r)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "quick.json"), "w"), indent=1)
 
 

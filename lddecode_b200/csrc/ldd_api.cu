@@ -126,7 +126,7 @@ int ldd_create(const ldd_config* cfg, ldd_handle** out) {
     int per_sm = env ? atoi(env) : 1;
     if (per_sm < 1) per_sm = 1;
     env = getenv("LDD_THREADS");
-    h->threads = env ? atoi(env) : (f64 ? 256 : 512);
+    h->threads = env ? atoi(env) : 512;
     if (f64) { if (h->threads != 256 && h->threads != 512 && h->threads != 1024) h->threads = 256; }
     else { if (h->threads != 512 && h->threads != 1024) h->threads = 512; }
     env = getenv("LDD_RADIX_MAX");

@@ -527,8 +527,11 @@ int fail_msg(ldd_handle* h, int code, const char* msg) {
 double median_of(std::vector<double> v) {
     size_t n = v.size();
     if (n == 0) return NAN;
-    std::sort(v.begin(), v.end());
-    return (n & 1) ? v[n / 2] : (v[n / 2 - 1] + v[n / 2]) / 2.0;
+    std::nth_element(v.begin(), v.begin() + n / 2, v.end());
+    double hi = v[n / 2];
+    if (n & 1) return hi;
+    double lo = *std::max_element(v.begin(), v.begin() + n / 2);
+    return (lo + hi) / 2.0;
 }
 
 struct Locator {
@@ -670,18 +673,26 @@ extern "C" int ldd_field_locate(ldd_handle* h, const long long* peaks, const dou
     long long prev_i = -1, prev_n = 0;
     const long long v0line0 = pyidx(vs[0][1]);
     if (v0line0 < 0 || v0line0 >= npeaks) { out->stage = LDD_FIELD_BADLINES; return LDD_OK; }
-    for (long long i = 0; i < vs[1][1]; ++i) {
+    // np.median(linelens[-25:]) is recomputed by the reference on every iteration but only used for
+    // the first line and for irregular gaps: evaluate it lazily (same value, the list is unchanged
+    // between the top of the iteration and the point of use).
+    auto medlen_now = [&]() -> double {
         size_t m = lens.size() < 25 ? lens.size() : 25;
-        double medlen = median_of(std::vector<double>(lens.end() - m, lens.end()));
+        double tmp[25];
+        std::copy(lens.end() - m, lens.end(), tmp);
+        std::sort(tmp, tmp + m);
+        return (m & 1) ? tmp[m / 2] : (tmp[m / 2 - 1] + tmp[m / 2]) / 2.0;
+    };
+    for (long long i = 0; i < vs[1][1]; ++i) {
         if (!lc.regular(i)) continue;
         long long n;
         if (prev_i >= 0) {
             long long gap = peaks[i] - peaks[prev_i];
             double ratio = (double)gap / (double)L;
             if (ratio >= .98 && ratio <= 1.02) { lens.push_back((double)gap); n = prev_n + 1; }
-            else n = prev_n + (long long)std::nearbyint((double)gap / medlen);
+            else n = prev_n + (long long)std::nearbyint((double)gap / medlen_now());
         } else {
-            n = (long long)std::nearbyint((double)(peaks[i] - peaks[v0line0]) / medlen);
+            n = (long long)std::nearbyint((double)(peaks[i] - peaks[v0line0]) / medlen_now());
         }
         setloc(n, (double)peaks[i]);
         prev_i = i; prev_n = n;

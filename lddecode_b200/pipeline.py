@@ -43,6 +43,20 @@ class CaptureDecoder:
         self.colorlevel, self.colorphase = colorlevel, colorphase
         self.max_fields = max_fields
         self.field_samples = int(rf.freq_hz / rf.SysParams['FPS'] / 2)
+        # Plane / audio buffers are kept and reused across calls (a 1-s PAL range needs 0.9 GB of
+        # planes; re-allocating that per call stalls on cudaMalloc).  Results of decode_range
+        # therefore stay valid until the next call on the same CaptureDecoder.
+        self._ws = {}
+
+    def _buf(self, tag, n, dtype):
+        key = (tag, np.dtype(dtype).str)
+        b = self._ws.get(key)
+        if b is None or len(b) < n:
+            b = None
+            self._ws.pop(key, None)
+            b = self.rf._be.empty(int(n * 1.02) + 16, dtype)
+            self._ws[key] = b
+        return b[:n]
 
     @property
     def stride(self):
@@ -77,13 +91,13 @@ class CaptureDecoder:
         res = RangeResult()
         res.r0, res.r1, res.plane_origin, res.plane_len = r0, r1, first_block, total
         rf._set_mtf(self.mtf_level)
-        planes, parr = rf._alloc_planes(max(total, 1))
+        planes, parr = rf._alloc_planes(max(total, 1), alloc=lambda name, n, dt: self._buf("plane_" + name, n, dt))
         a1l = a1r = None
         alen = 0
         if rf.decode_analog_audio:
             ds = N // len(rf.Filters['audio_lfilt'])
             alen = total // ds
-            a1l, a1r = be.empty(max(alen, 1), np.float64), be.empty(max(alen, 1), np.float64)
+            a1l, a1r = self._buf("a1l", max(alen, 1), np.float64), self._buf("a1r", max(alen, 1), np.float64)
         if nblocks:
             rf._check(be.lib.ldd_demod_blocks(rf._h, be.ptr(cap_dev), fmt, int(cap_base), int(cap_len), int(first_block),
                                               int(nblocks), int(total), parr, be.ptr(a1l) if a1l is not None else None,

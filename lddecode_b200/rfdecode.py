@@ -282,9 +282,11 @@ class RFDecode:
         self._check(self._be.lib.ldd_demod_range_query(self._h, int(start), int(length), C.byref(r)))
         return r
 
-    def _alloc_planes(self, total):
+    def _alloc_planes(self, total, alloc=None):
         names = VIDEO_FIELDS[self.system]
-        bufs = {n: self._be.empty(total, np.float64 if n == 'demod_sync' else np.float32) for n in names}
+        if alloc is None:
+            alloc = lambda name, n, dt: self._be.empty(n, dt)
+        bufs = {n: alloc(n, total, np.float64 if n == 'demod_sync' else np.float32) for n in names}
         arr = (C.c_void_p * 5)()
         for n in names:
             arr[_PLANE_OF[n]] = self._be.ptr(bufs[n])

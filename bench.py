@@ -223,10 +223,12 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    gatherer = parallel.FieldGatherer(cd, rank, world, max_fields, dist) if world > 1 else None
+
     def step_resident():
         res = cd.decode(cap_dev, _lib.FMT_U8, ncap)
         if world > 1:
-            parallel.gather_fields(cd, res, rank, world, max_fields, dist)
+            gatherer.gather(res)        # NCCL gather of the uint16 fields + positions into rank 0's HBM
         return res
 
     def step_e2e(out_pin):
@@ -237,7 +239,7 @@ def run_ours(a):
         if res.audio is not None:
             res.audio_host = (res.audio['audio_left'].cpu(), res.audio['audio_right'].cpu())
         if world > 1:
-            parallel.gather_fields(cd, res, rank, world, max_fields, dist)
+            gatherer.gather(res)
         torch.cuda.current_stream().synchronize()
         return res, n
 

@@ -2,8 +2,8 @@
 
 Every rank decodes the fields whose read position falls in its range (pipeline.CaptureDecoder.
 decode_range: own block range + halos, no data-path collective); the only exchange is the gather
-of the per-field outputs (uint16 TBC fields, read positions, parity) to rank 0, over NCCL on
-NVLink when the backend is CUDA (gloo in the CPU tests).  SURVEY.md section 8e.
+of the per-field outputs (uint16 TBC fields, read positions, parity, status) to rank 0, over NCCL
+on NVLink when the backend is CUDA (gloo in the CPU tests).  SURVEY.md section 8e.
 """
 import numpy as np
 
@@ -24,52 +24,71 @@ def needed_window(cd, ncap, r0, r1):
     return first_block, hi
 
 
-def gather_fields(cd, res, rank, world, max_fields, dist=None):
-    """Gather (readsample, istop, linecount, ok) and the uint16 pictures of every rank on rank 0.
+class FieldGatherer:
+    """Gathers the located fields of every rank on rank 0.  Buffers are allocated once; gather()
+    only enqueues device work (a copy into the send buffer and two collectives), to_host() turns the
+    gathered buffers into a list of (readsample, istop, picture | None) ordered by read position."""
 
-    Returns on rank 0 a list of (readsample, istop, picture) ordered by read position; None elsewhere."""
-    rf, be = cd.rf, cd.rf._be
-    torch = None
-    W = rf.SysParams['outlinelen']
-    stride = res.out_stride
-    nloc = len(res.located)
-    if nloc > max_fields:
-        raise ValueError("max_fields too small")
-    meta = np.zeros((max_fields, 4), dtype=np.int64)
-    st = be.to_host(res.d_status) if nloc else np.zeros(0, dtype=np.int32)
-    for k, j in enumerate(res.located):
-        info = res.infos[j]
-        meta[k] = (res.readsamples[j], info.istop, info.linecount, int((st[k] & 15) == 0))
-    meta[nloc:, 0] = -1
-    import torch
-    if be.name == "cuda":
-        dev = be.device
-        pic = torch.zeros(max_fields * stride, dtype=torch.uint16, device=dev)
-        if nloc:
-            pic[:nloc * stride] = res.d_pic[:nloc * stride]
-        tmeta = torch.from_numpy(meta).to(dev)
-    else:
-        pic = torch.zeros(max_fields * stride, dtype=torch.int16)
-        if nloc:
-            pic[:nloc * stride] = torch.from_numpy(be.to_host(res.d_pic)[:nloc * stride].view(np.int16))
-        tmeta = torch.from_numpy(meta)
-    if world == 1:
-        pics, metas = [pic], [tmeta]
-    else:
-        pv = pic.view(torch.uint8)             # bytes: NCCL and gloo have no uint16
-        pics = [torch.empty_like(pv) for _ in range(world)] if rank == 0 else None
-        metas = [torch.empty_like(tmeta) for _ in range(world)] if rank == 0 else None
-        dist.gather(pv, pics, dst=0)
-        dist.gather(tmeta, metas, dst=0)
-    if rank != 0:
-        return None
-    out = []
-    for g in range(world):
-        m = metas[g].cpu().numpy()
-        p = pics[g].cpu().contiguous().view(torch.uint8).numpy().view(np.uint16).reshape(max_fields, stride)
-        for k in range(max_fields):
-            if m[k, 0] < 0:
-                break
-            out.append((int(m[k, 0]), int(m[k, 1]), p[k, :m[k, 2] * W].copy() if m[k, 3] else None))
-    out.sort(key=lambda t: t[0])
-    return out
+    def __init__(self, cd, rank, world, max_fields, dist=None):
+        import torch
+        self.torch = torch
+        self.cd, self.rank, self.world, self.max_fields, self.dist = cd, rank, world, max_fields, dist
+        rf = cd.rf
+        self.be = rf._be
+        self.W = rf.SysParams['outlinelen']
+        self.stride = (rf.SysParams['frame_lines'] // 2 + 1) * self.W
+        self.cuda = self.be.name == "cuda"
+        dev = self.be.device if self.cuda else "cpu"
+        self.pic = torch.zeros(max_fields * self.stride * 2, dtype=torch.uint8, device=dev)       # uint16 as bytes
+        self.meta = torch.zeros((max_fields, 4), dtype=torch.int64, device=dev)                   # readsample, istop, linecount, status
+        if rank == 0 and world > 1:
+            self.pics = [torch.empty_like(self.pic) for _ in range(world)]
+            self.metas = [torch.empty_like(self.meta) for _ in range(world)]
+        else:
+            self.pics, self.metas = [self.pic], [self.meta]
+
+    def gather(self, res):
+        torch = self.torch
+        nloc = len(res.located)
+        if nloc > self.max_fields:
+            raise ValueError("max_fields too small")
+        meta = np.full((self.max_fields, 4), -1, dtype=np.int64)
+        for k, j in enumerate(res.located):
+            info = res.infos[j]
+            meta[k] = (res.readsamples[j], info.istop, info.linecount, 0)
+        tm = torch.from_numpy(meta)
+        if self.cuda:
+            self.meta.copy_(tm, non_blocking=True)
+            if nloc:
+                self.meta[:nloc, 3] = res.d_status[:nloc].to(torch.int64)
+                self.pic[:nloc * self.stride * 2] = res.d_pic[:nloc * self.stride].view(torch.uint8)
+        else:
+            if nloc:
+                tm[:nloc, 3] = torch.from_numpy(np.asarray(self.be.to_host(res.d_status)[:nloc], dtype=np.int64))
+                self.pic[:nloc * self.stride * 2] = torch.from_numpy(self.be.to_host(res.d_pic)[:nloc * self.stride].view(np.uint8))
+            self.meta.copy_(tm)
+        if self.world > 1:
+            self.dist.gather(self.pic, self.pics if self.rank == 0 else None, dst=0)
+            self.dist.gather(self.meta, self.metas if self.rank == 0 else None, dst=0)
+
+    def to_host(self):
+        if self.rank != 0:
+            return None
+        out = []
+        for g in range(len(self.pics)):
+            m = self.metas[g].cpu().numpy()
+            p = self.pics[g].cpu().numpy().view(np.uint16).reshape(self.max_fields, self.stride)
+            for k in range(self.max_fields):
+                if m[k, 0] < 0:
+                    break
+                ok = (m[k, 3] & 15) == 0
+                out.append((int(m[k, 0]), int(m[k, 1]), p[k, :m[k, 2] * self.W].copy() if ok else None))
+        out.sort(key=lambda t: t[0])
+        return out
+
+
+def gather_fields(cd, res, rank, world, max_fields, dist=None):
+    """One-shot convenience wrapper: gather and return the host list on rank 0 (None elsewhere)."""
+    g = FieldGatherer(cd, rank, world, max_fields, dist)
+    g.gather(res)
+    return g.to_host()

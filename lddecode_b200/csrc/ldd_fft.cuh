@@ -155,4 +155,75 @@ __device__ inline Cx<T>* fft_run(Cx<T>* a, Cx<T>* b, const FftPlan& plan, const 
     return a;
 }
 
+// ---- in-place variant: 16 elements per thread --------------------------------------------------
+// For n == 16 * (number of active threads) every pass can run in place: each active thread loads
+// the 16 elements of its 16/R butterflies into registers, the CTA synchronises, then it stores its
+// outputs.  One buffer is enough, so a float64 transform of M = 8192 points fits a 136 KB padded
+// shared-memory work buffer while the arrays it reads from / writes to stay in the L2-resident
+// global scratch (PIO: padding of src/dst, PW: padding of the work buffer).  src may equal dst.
+template <class T, int R, bool PIN, bool POUT>
+__device__ inline void fft_pass16(const Cx<T>* in, Cx<T>* out, int n, int Ns, const Cx<T>* __restrict__ W,
+                                  int wstride, int tid) {
+    constexpr int C = 16 / R;
+    const int nact = n >> 4, nb = n / R;
+    const bool act = tid < nact;
+    Cx<T> v[16];
+    if (act) {
+        LDD_UNROLL
+        for (int c = 0; c < C; ++c) {
+            const int j = tid + c * nact;
+            LDD_UNROLL
+            for (int r = 0; r < R; ++r) v[c * R + r] = in[pidx<PIN>(j + r * nb)];
+        }
+    }
+    __syncthreads();
+    if (act) {
+        LDD_UNROLL
+        for (int c = 0; c < C; ++c) {
+            const int j = tid + c * nact;
+            const int k = j & (Ns - 1);
+            Cx<T>* b = v + c * R;
+            if (Ns > 1) {
+                Cx<T> p[R];
+                p[1] = W[(size_t)k * (size_t)(nb / Ns) * (size_t)wstride];
+                LDD_UNROLL
+                for (int r = 2; r < R; ++r) p[r] = (r & 1) ? p[r - 1] * p[1] : p[r / 2] * p[r / 2];
+                LDD_UNROLL
+                for (int r = 1; r < R; ++r) b[r] = b[r] * p[r];
+            }
+            Dft<T, R>::run(b);
+            const int j0 = (j - k) * R + k;
+            LDD_UNROLL
+            for (int r = 0; r < R; ++r) out[pidx<POUT>(j0 + r * Ns)] = b[r];
+        }
+    }
+    __syncthreads();
+}
+
+template <class T, bool PIN, bool POUT>
+__device__ inline void fft_pass16_any(int R, const Cx<T>* in, Cx<T>* out, int n, int Ns, const Cx<T>* __restrict__ W,
+                                      int wstride, int tid) {
+    switch (R) {
+        case 16: fft_pass16<T, 16, PIN, POUT>(in, out, n, Ns, W, wstride, tid); break;
+        case 8: fft_pass16<T, 8, PIN, POUT>(in, out, n, Ns, W, wstride, tid); break;
+        case 4: fft_pass16<T, 4, PIN, POUT>(in, out, n, Ns, W, wstride, tid); break;
+        default: fft_pass16<T, 2, PIN, POUT>(in, out, n, Ns, W, wstride, tid); break;
+    }
+}
+
+// src -> (work ...) -> dst; needs plan.npass >= 2.  Every thread of the CTA must call it.
+template <class T, bool PIO, bool PW>
+__device__ inline void fft16(const Cx<T>* src, Cx<T>* work, Cx<T>* dst, const FftPlan& plan,
+                             const Cx<T>* __restrict__ W, int wstride, int tid) {
+    int Ns = 1;
+    const int last = plan.npass - 1;
+    for (int ps = 0; ps <= last; ++ps) {
+        const int R = plan.radix[ps];
+        if (ps == 0) fft_pass16_any<T, PIO, PW>(R, src, work, plan.n, Ns, W, wstride, tid);
+        else if (ps == last) fft_pass16_any<T, PW, PIO>(R, work, dst, plan.n, Ns, W, wstride, tid);
+        else fft_pass16_any<T, PW, PW>(R, work, work, plan.n, Ns, W, wstride, tid);
+        Ns *= R;
+    }
+}
+
 }  // namespace ldd

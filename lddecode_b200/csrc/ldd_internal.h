@@ -58,6 +58,7 @@ inline int launch_status(ldd_handle* h, const char* what);
 
 int launch_demod_f64(const DemodParams& p, int grid, int threads, cudaStream_t st);
 int launch_demod_f32(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t smem_bytes);
+int launch_demod_v2(const DemodParams& p, int grid, bool f64, cudaStream_t st, size_t smem_bytes);
 
 }  // namespace ldd
 
@@ -84,6 +85,7 @@ struct ldd_handle {
     int threads;      // CTA size of the demodulation kernel
     int radix_max;    // largest Stockham radix used
     size_t smem_bytes;
+    bool v2;          // in-place 16-elements-per-thread kernel (N == 16384)
     // audio phase 2
     void* d_lpf2;     // Cx<double>[N/4]
     void* d_WNfull;   // e^{-2 pi i k/N}, k<N (double) for the phase-2 transforms

@@ -15,7 +15,8 @@ import torch  # noqa: E402
 from lddecode_b200 import _lib, rfdecode, synth  # noqa: E402
 
 
-def run(system, fs, N, prec, cap_dev, ncap, audio, threads, radix, ctas=1, reps=5):
+def run(system, fs, N, prec, cap_dev, ncap, audio, threads, radix, ctas=1, reps=5, kernel=2):
+    os.environ["LDD_KERNEL"] = str(kernel)
     os.environ["LDD_THREADS"] = str(threads)
     os.environ["LDD_RADIX_MAX"] = str(radix)
     os.environ["LDD_CTAS_PER_SM"] = str(ctas)
@@ -34,7 +35,7 @@ def run(system, fs, N, prec, cap_dev, ncap, audio, threads, radix, ctas=1, reps=
         ts.append(e0.elapsed_time(e1))
     ms = min(ts)
     del out
-    return dict(system=system, N=N, prec=prec, audio=audio, threads=threads, radix=radix, ctas=ctas, ms=round(ms, 3),
+    return dict(system=system, N=N, prec=prec, audio=audio, kernel=kernel, threads=threads, radix=radix, ctas=ctas, ms=round(ms, 3),
                 msps=round(length / ms / 1e3, 1))
 
 
@@ -46,13 +47,11 @@ def main():
     cap = np.tile(one, n // len(one))
     cap_dev = torch.from_numpy(cap).cuda()
     res = []
-    variants = [("f64", 256, 16, 1), ("f64", 512, 16, 1), ("f64", 512, 8, 1), ("f64", 1024, 8, 1), ("f64", 1024, 4, 1),
-                ("f64", 256, 8, 2), ("f64", 512, 8, 2),
-                ("f32", 512, 16, 1), ("f32", 512, 8, 1), ("f32", 1024, 8, 1), ("f32", 1024, 4, 1)]
-    for N in (16384, 32768):
-        for prec, thr, rad, ctas in variants:
+    variants = [("f64", 512, 16, 1, 1), ("f64", 512, 16, 1, 2), ("f32", 512, 16, 1, 1), ("f32", 512, 16, 1, 2)]
+    for N in (16384,):
+        for prec, thr, rad, ctas, kern in variants:
             try:
-                r = run(system, fs, N, prec, cap_dev, len(cap), False, thr, rad, ctas)
+                r = run(system, fs, N, prec, cap_dev, len(cap), False, thr, rad, ctas, kernel=kern)
             except Exception as e:
                 r = dict(N=N, prec=prec, threads=thr, radix=rad, error=str(e)[:200])
             print(json.dumps(r), flush=True)

@@ -163,6 +163,20 @@ int ldd_create(const ldd_config* cfg, ldd_handle** out) {
     size_t need = (size_t)h->grid * (h->scratch_per_cta > per_cta_a2 ? h->scratch_per_cta : per_cta_a2);
     CUDA_TRY(h, cudaMalloc(&h->scratch, need));
     h->scratch_bytes = need;
+#ifndef LDD_EMU
+    // keep the scratch slices resident in L2 (persisting lines) while the planes stream through
+    h->l2_window = 0;
+    if (h->scratch_per_cta && !getenv("LDD_NO_L2_PERSIST")) {
+        size_t want = (size_t)h->grid * h->scratch_per_cta;
+        size_t cap = (size_t)prop.persistingL2CacheMaxSize;
+        size_t win = (size_t)prop.accessPolicyMaxWindowSize;
+        if (cap > 0 && win > 0) {
+            size_t lim = want < cap ? want : cap;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim) == cudaSuccess) h->l2_window = want < win ? want : win;
+            h->l2_ratio = want <= lim ? 1.0f : (float)lim / (float)want;
+        }
+    }
+#endif
     return LDD_OK;
 }
 
@@ -320,10 +334,28 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
         CUDA_TRY(h, cudaMemsetAsync(audio1_l_dev, 0, (size_t)audio1_len * sizeof(double), st));
         CUDA_TRY(h, cudaMemsetAsync(audio1_r_dev, 0, (size_t)audio1_len * sizeof(double), st));
     }
+#ifndef LDD_EMU
+    cudaStreamAttrValue l2attr;
+    if (h->l2_window) {
+        memset(&l2attr, 0, sizeof l2attr);
+        l2attr.accessPolicyWindow.base_ptr = h->scratch;
+        l2attr.accessPolicyWindow.num_bytes = h->l2_window;
+        l2attr.accessPolicyWindow.hitRatio = h->l2_ratio;
+        l2attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        l2attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &l2attr);
+    }
+#endif
     int rc;
     if (h->v2) rc = launch_demod_v2(p, grid, lane == 0, st, h->smem_bytes);
     else if (lane == 0) rc = launch_demod_f64(p, grid, h->threads, st);
     else rc = launch_demod_f32(p, grid, h->threads, st, h->smem_bytes);
+#ifndef LDD_EMU
+    if (h->l2_window) {
+        l2attr.accessPolicyWindow.num_bytes = 0;        // later kernels on this stream are not affected
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &l2attr);
+    }
+#endif
     if (rc) return fail(h, rc, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return LDD_OK;
 }

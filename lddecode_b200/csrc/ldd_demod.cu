@@ -18,6 +18,15 @@
 
 namespace ldd {
 
+// The planes are written once and never re-read by this kernel: store them with the streaming
+// (evict-first) hint so that ~0.9 GB of output per second of video does not push the L2-resident
+// scratch slices out to DRAM.
+#ifdef LDD_EMU
+template <class U> __device__ inline void st_stream(U* p, U v) { *p = v; }
+#else
+template <class U> __device__ inline void st_stream(U* p, U v) { __stcs(p, v); }
+#endif
+
 template <class T> struct Math;
 template <> struct Math<double> {
     static __device__ inline double atan2(double y, double x) { return ::atan2(y, x); }
@@ -124,10 +133,18 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
         const int keep0 = p.blockcut, keep1 = p.blockcut + (int)copylen;
 
         // A. samples -> z[n] = x[2n] + j x[2n+1]
-        for (int n = tid; n < M; n += nthr) {
-            int s0 = fetch_sample(p.rf, p.fmt, in0 + 2 * n);
-            int s1 = fetch_sample(p.rf, p.fmt, in0 + 2 * n + 1);
-            b0[IX(n)] = mk<T>((T)s0, (T)s1);
+        if (p.fmt == LDD_FMT_U8 && ((in0 & 1) == 0) && ((((uintptr_t)p.rf) & 1) == 0)) {
+            const unsigned short* r16 = (const unsigned short*)((const unsigned char*)p.rf + in0);
+            for (int n = tid; n < M; n += nthr) {
+                unsigned v = r16[n];
+                b0[IX(n)] = mk<T>((T)(int)(v & 0xffu), (T)(int)(v >> 8));
+            }
+        } else {
+            for (int n = tid; n < M; n += nthr) {
+                int s0 = fetch_sample(p.rf, p.fmt, in0 + 2 * n);
+                int s1 = fetch_sample(p.rf, p.fmt, in0 + 2 * n + 1);
+                b0[IX(n)] = mk<T>((T)s0, (T)s1);
+            }
         }
         __syncthreads();
 
@@ -259,12 +276,21 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
             float* out = (float*)p.plane[pl_of[m]];
             const T addc = (T)p.addc[m];
             // kept samples 2n, 2n+1 -> out[o + 2n - keep0]; keep0, o and copylen parity: handle singly
-            for (int n = tid; n < M; n += nthr) {
-                Cx<T> v = r[IX(n)];
-                int i0 = 2 * n, i1 = 2 * n + 1;
-                float v0 = (float)(v.x + addc), v1 = (float)(-v.y + addc);
-                if (i0 >= keep0 && i0 < keep1) out[o + (i0 - keep0)] = v0;
-                if (i1 >= keep0 && i1 < keep1) out[o + (i1 - keep0)] = v1;
+            if (((keep0 | keep1) & 1) == 0 && ((o & 1) == 0) && ((((uintptr_t)out) & 7) == 0)) {
+                // whole (even, odd) sample pairs inside the kept region: one 8-byte streaming store each
+                float2* out2 = (float2*)(out + o) - keep0 / 2;
+                for (int n = keep0 / 2 + tid; n < keep1 / 2; n += nthr) {
+                    Cx<T> v = r[IX(n)];
+                    st_stream(&out2[n], make_float2((float)(v.x + addc), (float)(-v.y + addc)));
+                }
+            } else {
+                for (int n = tid; n < M; n += nthr) {
+                    Cx<T> v = r[IX(n)];
+                    int i0 = 2 * n, i1 = 2 * n + 1;
+                    float v0 = (float)(v.x + addc), v1 = (float)(-v.y + addc);
+                    if (i0 >= keep0 && i0 < keep1) st_stream(&out[o + (i0 - keep0)], v0);
+                    if (i1 >= keep0 && i1 < keep1) st_stream(&out[o + (i1 - keep0)], v1);
+                }
             }
             if (m == 1) r05 = r;
             __syncthreads();
@@ -287,9 +313,13 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
             const double c = p.fp_c;
             double sprev = insync(n0 - 1);
             const double sprev0 = sprev;
+            // the binary decisions of this thread's chunk, evaluated once (CH <= 64), else re-evaluated
+            const bool use_mask = CH <= 64;
+            unsigned long long mask = 0ull;
             double acc = 0.0;
             for (int i = 0; i < CH; ++i) {
                 double s = insync(n0 + i);
+                if (use_mask && s != 0.0) mask |= (1ull << i);
                 acc = c * acc + (p.fp_b0 * s + p.fp_b1 * sprev);
                 sprev = s;
             }
@@ -305,7 +335,6 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
             if (lane == 31) s_warp[warp] = incl;
             __syncthreads();
             const double A32 = pow(Ach, 32.0);
-            const int nwarp = nthr >> 5;
             double carry = 0.0;                 // state entering this warp (zero initial state)
             for (int w = 0; w < warp; ++w) carry = A32 * carry + s_warp[w];
             if (tid == nthr - 1) {
@@ -313,7 +342,6 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
                 s_total = tot / (1.0 - pow(c, (double)N));     // periodic steady state y[-1]
             }
             __syncthreads();
-            (void)nwarp;
             // state entering this thread's chunk
             double excl = __shfl_up_sync(0xffffffffu, incl, 1);
             double st = (lane == 0 ? 0.0 : excl) + pow(Ach, (double)lane) * carry + pow(c, (double)n0) * s_total;
@@ -321,10 +349,10 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
             sprev = sprev0;
             for (int i = 0; i < CH; ++i) {
                 int n = n0 + i;
-                double s = insync(n);
+                double s = use_mask ? (double)((mask >> i) & 1ull) : insync(n);
                 st = c * st + (p.fp_b0 * s + p.fp_b1 * sprev);
                 sprev = s;
-                if (n >= keep0 && n < keep1) out[o + (n - keep0)] = st;
+                if (n >= keep0 && n < keep1) st_stream(&out[o + (n - keep0)], st);
             }
         }
         __syncthreads();
@@ -503,8 +531,8 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel_v2(const DemodParams p) {
                 Cx<T> v = r[JX(n)];
                 int i0 = 2 * n, i1 = 2 * n + 1;
                 float v0 = (float)(v.x + addc), v1 = (float)(-v.y + addc);
-                if (i0 >= keep0 && i0 < keep1) out[o + (i0 - keep0)] = v0;
-                if (i1 >= keep0 && i1 < keep1) out[o + (i1 - keep0)] = v1;
+                if (i0 >= keep0 && i0 < keep1) st_stream(&out[o + (i0 - keep0)], v0);
+                if (i1 >= keep0 && i1 < keep1) st_stream(&out[o + (i1 - keep0)], v1);
             }
             __syncthreads();
         }
@@ -558,7 +586,7 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel_v2(const DemodParams p) {
                 double s = insync(n);
                 st = c * st + (p.fp_b0 * s + p.fp_b1 * sprev);
                 sprev = s;
-                if (n >= keep0 && n < keep1) out[o + (n - keep0)] = st;
+                if (n >= keep0 && n < keep1) st_stream(&out[o + (n - keep0)], st);
             }
         }
         __syncthreads();

@@ -86,6 +86,8 @@ struct ldd_handle {
     int radix_max;    // largest Stockham radix used
     size_t smem_bytes;
     bool v2;          // in-place 16-elements-per-thread kernel (N == 16384)
+    size_t l2_window = 0;   // bytes of scratch covered by a persisting-L2 access policy window
+    float l2_ratio = 1.0f;
     // audio phase 2
     void* d_lpf2;     // Cx<double>[N/4]
     void* d_WNfull;   // e^{-2 pi i k/N}, k<N (double) for the phase-2 transforms

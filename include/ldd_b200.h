@@ -66,6 +66,9 @@ extern "C" {
 
 #define LDD_PREC_F64 0     /* every transform in float64: the lane whose sync decisions are reference-exact */
 #define LDD_PREC_F32 1     /* float32 shared-memory lane */
+#define LDD_PREC_MIXED 2   /* float32 lane, then float64 re-run of every block that holds a demod_05 sample within
+                              a guard band (16 Hz, 8x the largest float32 error measured) of a sync threshold: the sync
+                              decisions, hence demod_sync and the peak indices, are the float64 lane's */
 
 #define LDD_OK 0
 #define LDD_EINVAL (-1)
@@ -158,6 +161,9 @@ int ldd_demod_blocks(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
  * float64 samples (may be NULL). */
 int ldd_demodblock(ldd_handle* h, const void* rf_dev, int fmt, long long rf_len,
                    void* const* planes_dev, double* audio_l_dev, double* audio_r_dev, void* stream);
+
+/* LDD_PREC_MIXED only, synchronous: how many blocks of the last ldd_demod_* call were re-run in float64. */
+int ldd_mixed_stats(ldd_handle* h, long long* flagged_blocks, long long* total_blocks);
 
 /* RFDecode.audio_phase2 (lddecode_core.py:335-371): in[len] -> out[len/4], float64, dev. */
 int ldd_audio_phase2(ldd_handle* h, const double* in_l_dev, const double* in_r_dev, long long len,

@@ -15,7 +15,7 @@ SYSTEM = {"NTSC": 0, "PAL": 1}
 FMT_U8, FMT_S16, FMT_U16, FMT_R30, FMT_LDS40 = range(5)
 F_RFVIDEO, F_VIDEO, F_VIDEO05, F_BURST, F_PILOT, F_AUDIO_L, F_AUDIO_R, F_AUDIO_LPF2 = range(8)
 P_DEMOD, P_DEMOD05, P_SYNC, P_BURST, P_PILOT = range(5)
-PREC_F64, PREC_F32 = 0, 1
+PREC_F64, PREC_F32, PREC_MIXED = 0, 1, 2
 OK, EINVAL, ESHORT, ECUDA, ENOMEM, ECAP = 0, -1, -2, -3, -4, -5
 
 
@@ -62,6 +62,7 @@ SIGNATURES = {
                                    C.c_longlong, C.c_void_p]),
     "ldd_demodblock": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.POINTER(C.c_void_p), C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
+    "ldd_mixed_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "ldd_audio_phase2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldd_sync_peaks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int,
                                  C.c_void_p, C.c_void_p]),

@@ -122,6 +122,8 @@ int ldd_create(const ldd_config* cfg, ldd_handle** out) {
     // launch geometry / scratch of the demodulation kernel.  Tunables (development): LDD_THREADS,
     // LDD_RADIX_MAX, LDD_CTAS_PER_SM.
     const bool f64 = cfg->precision == LDD_PREC_F64;
+    const bool mixed = cfg->precision == LDD_PREC_MIXED;
+    if (cfg->precision < LDD_PREC_F64 || cfg->precision > LDD_PREC_MIXED) return fail(h, LDD_EINVAL, "bad precision %d", cfg->precision);
     const char* env = getenv("LDD_CTAS_PER_SM");
     int per_sm = env ? atoi(env) : 1;
     if (per_sm < 1) per_sm = 1;
@@ -163,6 +165,13 @@ int ldd_create(const ldd_config* cfg, ldd_handle** out) {
     size_t need = (size_t)h->grid * (h->scratch_per_cta > per_cta_a2 ? h->scratch_per_cta : per_cta_a2);
     CUDA_TRY(h, cudaMalloc(&h->scratch, need));
     h->scratch_bytes = need;
+    if (mixed) {
+        // second pass of the mixed lane: float64, global scratch, one CTA per SM
+        h->scratch64_per_cta = (size_t)3 * M * sizeof(Cx<double>);
+        CUDA_TRY(h, cudaMalloc(&h->scratch64, (size_t)h->sm_count * h->scratch64_per_cta));
+        const char* em = getenv("LDD_FLAG_MARGIN_HZ");
+        if (em) h->flag_margin = atof(em);
+    }
 #ifndef LDD_EMU
     // keep the scratch slices resident in L2 (persisting lines) while the planes stream through
     h->l2_window = 0;
@@ -189,6 +198,8 @@ void ldd_destroy(ldd_handle* h) {
     cudaFree(h->scratch);
     cudaFree(h->d_lpf2);
     cudaFree(h->d_WNfull);
+    cudaFree(h->scratch64);
+    cudaFree(h->d_flags);
     cudaFree(h->peak_ws);
     cudaFree(h->pilot_ws);
     delete h;
@@ -295,6 +306,7 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
         if (!planes_dev[pidx]) return fail(h, LDD_EINVAL, "plane %d is NULL", pidx);
 
     const int lane = c.precision == LDD_PREC_F64 ? 0 : 1;
+    const bool mixed = c.precision == LDD_PREC_MIXED;
     DemodParams p;
     memset(&p, 0, sizeof p);
     p.N = N; p.M = M; p.A = audio ? h->A : 0;
@@ -346,10 +358,36 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
         cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &l2attr);
     }
 #endif
+    h->last_nblocks = nblocks;
+    if (mixed) {
+        if ((size_t)nblocks + 1 > h->flags_cap) {
+            if (h->d_flags) { cudaStreamSynchronize(st); cudaFree(h->d_flags); h->d_flags = nullptr; }
+            size_t cap = (size_t)nblocks + 1024;
+            CUDA_TRY(h, cudaMalloc((void**)&h->d_flags, cap * sizeof(int)));
+            h->flags_cap = cap;
+        }
+        CUDA_TRY(h, cudaMemsetAsync(h->d_flags, 0, sizeof(int), st));
+        p.flag_count = h->d_flags;
+        p.flag_list = h->d_flags + 1;
+        p.flag_margin = h->flag_margin;
+    }
     int rc;
     if (h->v2) rc = launch_demod_v2(p, grid, lane == 0, st, h->smem_bytes);
     else if (lane == 0) rc = launch_demod_f64(p, grid, h->threads, st);
     else rc = launch_demod_f32(p, grid, h->threads, st, h->smem_bytes);
+    if (mixed && rc == LDD_OK) {
+        // second pass: float64 over the flagged blocks only; the list is read on the device, so there
+        // is no host round trip -- an idle launch costs a few microseconds when nothing was flagged
+        DemodParams q = p;
+        q.WM = h->d_WM[0]; q.WN = h->d_WN[0]; q.Hv = h->d_Hv[0];
+        for (int m = 0; m < nfilt; ++m) q.F[m] = h->d_F[m][0];
+        q.AL = h->d_AL[0]; q.AR = h->d_AR[0];
+        q.scratch = h->scratch64; q.scratch_per_cta = h->scratch64_per_cta;
+        q.flag_list = nullptr; q.flag_count = nullptr;
+        q.block_count = h->d_flags; q.block_list = h->d_flags + 1;
+        int g64 = (int)(nblocks < h->sm_count ? nblocks : h->sm_count);
+        rc = launch_demod_f64(q, g64, 512, st);
+    }
 #ifndef LDD_EMU
     if (h->l2_window) {
         l2attr.accessPolicyWindow.num_bytes = 0;        // later kernels on this stream are not affected
@@ -357,6 +395,17 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
     }
 #endif
     if (rc) return fail(h, rc, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return LDD_OK;
+}
+
+int ldd_mixed_stats(ldd_handle* h, long long* flagged_blocks, long long* total_blocks) {
+    if (!h || !flagged_blocks || !total_blocks) return LDD_EINVAL;
+    *flagged_blocks = 0;
+    *total_blocks = h->last_nblocks;
+    if (h->cfg.precision != LDD_PREC_MIXED || !h->d_flags) return LDD_OK;
+    int n = 0;
+    CUDA_TRY(h, cudaMemcpy(&n, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost));
+    *flagged_blocks = n;
     return LDD_OK;
 }
 

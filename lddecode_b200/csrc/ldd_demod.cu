@@ -123,7 +123,9 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
     __shared__ double s_warp[32];
     __shared__ double s_total;
 
-    for (int blk = blockIdx.x; blk < p.nblocks; blk += gridDim.x) {
+    const int nwork = p.block_list ? *p.block_count : p.nblocks;
+    for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+        const int blk = p.block_list ? p.block_list[wi] : wi;
         const long long in0 = p.first_sample + (long long)blk * p.stride;
         const long long o = (long long)blk * p.stride;
         long long copylen = p.stride;
@@ -317,11 +319,24 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
             const bool use_mask = CH <= 64;
             unsigned long long mask = 0ull;
             double acc = 0.0;
+            int near = 0;
             for (int i = 0; i < CH; ++i) {
                 double s = insync(n0 + i);
                 if (use_mask && s != 0.0) mask |= (1ull << i);
                 acc = c * acc + (p.fp_b0 * s + p.fp_b1 * sprev);
                 sprev = s;
+                if (p.flag_list) {
+                    // mixed lane: is this float32 sample close enough to a threshold that float64 could decide otherwise?
+                    int nn = (n0 + i) & (N - 1);
+                    double v = (double)x05[2 * IX(nn >> 1) + (nn & 1)];
+                    if (nn & 1) v = -v;
+                    v += add;
+                    near |= (fabs(v - p.sync_lo) < p.flag_margin) | (fabs(v - p.sync_hi) < p.flag_margin);
+                }
+            }
+            if (p.flag_list) {
+                int any = __syncthreads_or(near);
+                if (any && tid == 0) { int at = atomicAdd(p.flag_count, 1); p.flag_list[at] = blk; }
             }
             // inclusive scan of the affine maps y -> Ach*y + acc over threads
             const double Ach = pow(c, (double)CH);

@@ -51,6 +51,14 @@ struct DemodParams {
     // scratch for the global-memory lane
     void* scratch;
     size_t scratch_per_cta;      // bytes
+    // mixed-precision lane: the float32 pass appends to flag_list the blocks that hold a demod_05 sample
+    // within flag_margin Hz of a sync threshold; the float64 pass then works through block_list instead
+    // of 0..nblocks-1 (both NULL otherwise)
+    int* flag_list;
+    int* flag_count;
+    double flag_margin;
+    const int* block_list;
+    const int* block_count;
 };
 
 // cudaGetLastError() after a launch -> LDD_OK / LDD_ECUDA with the CUDA error text in h->err
@@ -86,6 +94,12 @@ struct ldd_handle {
     int radix_max;    // largest Stockham radix used
     size_t smem_bytes;
     bool v2;          // in-place 16-elements-per-thread kernel (N == 16384)
+    void* scratch64 = nullptr;       // float64 scratch of the mixed lane's second pass
+    size_t scratch64_per_cta = 0;
+    int* d_flags = nullptr;          // [0] = count, [1..] = block indices
+    size_t flags_cap = 0;
+    double flag_margin = 16.0;       // Hz
+    long long last_nblocks = 0;
     size_t l2_window = 0;   // bytes of scratch covered by a persisting-L2 access policy window
     float l2_ratio = 1.0f;
     // audio phase 2

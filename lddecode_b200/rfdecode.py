@@ -224,7 +224,7 @@ class RFDecode:
         cfg.system = _lib.SYSTEM[self.system]
         cfg.blocklen, cfg.blockcut, cfg.blockcut_end = self.blocklen, self.blockcut, self.blockcut_end
         cfg.f05_offset = SF['F05_offset']
-        cfg.precision = {'f64': _lib.PREC_F64, 'f32': _lib.PREC_F32}[self.precision]
+        cfg.precision = {'f64': _lib.PREC_F64, 'f32': _lib.PREC_F32, 'mixed': _lib.PREC_MIXED}[self.precision]
         cfg.decode_analog_audio = int(bool(self.decode_analog_audio))
         if self.decode_analog_audio:
             cfg.audio_slice_lo, cfg.audio_slice_hi = SF['audio_fdslice_lo'].start, SF['audio_fdslice_lo'].stop
@@ -317,6 +317,13 @@ class RFDecode:
             else:
                 audio = {'audio_left': a1l, 'audio_right': a1r}
         return DeviceDemod(self, planes, audio, r)
+
+    def mixed_stats(self):
+        """(blocks re-run in float64, blocks) of the last demodulation in precision='mixed'."""
+        self._be.synchronize()
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        self._check(self._be.lib.ldd_mixed_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def _audio_phase2_device(self, a1l, a1r, n):
         outl = self._be.empty(n // 4, np.float64)

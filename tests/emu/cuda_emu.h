@@ -71,6 +71,16 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 
 static inline void __syncthreads() { emu::barrier(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier(); }
+static inline int __syncthreads_or(int pred) {
+    static int acc;
+    if (emu::threadIdx_.x == 0 && emu::threadIdx_.y == 0 && emu::threadIdx_.z == 0) acc = 0;
+    emu::barrier();
+    if (pred) acc = 1;
+    emu::barrier();
+    int r = acc;
+    emu::barrier();
+    return r;
+}
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 

@@ -141,3 +141,29 @@ def test_unpack_kernels_bit_exact(backend, golden):
     backend.synchronize()
     assert np.array_equal(backend.to_host(o)[:15], g["r30_ddunpack_i16"][:15]) and backend.to_host(o)[15] == 0
     assert lib.ldd_unpack_r30_ddunpack(backend.ptr(words), 0, backend.ptr(o), backend.stream()) == 0
+
+
+@pytest.mark.parametrize("name", ["ntsc", "pal"])
+def test_mixed_lane_sync_is_the_float64_lane(backend, golden, name):
+    """precision='mixed' (float32 shared-memory pass + float64 re-run of every block with a demod_05
+    sample within the 16 Hz guard band of a sync threshold): demod_sync must be BIT-identical to the
+    float64 lane, the float32 error must stay far inside the guard band, and the Hz planes inside
+    the 1e-4 relative bar."""
+    from lddecode_b200 import _lib
+    g = golden(name)
+    cap = g["capture"]
+    capd = backend.to_device(cap)
+    out = {}
+    for prec in ("f64", "mixed"):
+        rf = rfdecode.RFDecode(float(g["fs_mhz"]), _system(g), int(g["blocklen"]), precision=prec, _backend=backend)
+        dd = rf.demod_device(capd, _lib.FMT_U8, 0, len(cap), 0, int(g["demod_length"]), 1, phase2=False)
+        out[prec] = {k: backend.to_host(v) for k, v in dd.planes.items()}
+        if prec == "mixed":
+            flagged, total = rf.mixed_stats()
+            assert 0 <= flagged <= total // 4
+    assert np.array_equal(out["mixed"]["demod_sync"], out["f64"]["demod_sync"])
+    err05 = np.abs(out["mixed"]["demod_05"].astype(np.float64) - out["f64"]["demod_05"])
+    assert err05.max() < 4.0                      # Hz; guard band is 16 Hz
+    ire0 = 8100000.0 if _system(g) == "NTSC" else 7100000.0
+    rel = np.abs(out["mixed"]["demod"].astype(np.float64) - out["f64"]["demod"]) / (np.abs(out["f64"]["demod"].astype(np.float64) + ire0))
+    assert rel.max() < 1e-6                       # bar: 1e-4

@@ -34,8 +34,9 @@ def run(system, fs, N, prec, cap_dev, ncap, audio, threads, radix, ctas=1, reps=
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     ms = min(ts)
+    extra = rf.mixed_stats() if prec == "mixed" else None
     del out
-    return dict(system=system, N=N, prec=prec, audio=audio, kernel=kernel, threads=threads, radix=radix, ctas=ctas, ms=round(ms, 3),
+    return dict(flagged=extra, system=system, N=N, prec=prec, audio=audio, kernel=kernel, threads=threads, radix=radix, ctas=ctas, ms=round(ms, 3),
                 msps=round(length / ms / 1e3, 1))
 
 
@@ -47,7 +48,7 @@ def main():
     cap = np.tile(one, n // len(one))
     cap_dev = torch.from_numpy(cap).cuda()
     res = []
-    variants = [("f64", 512, 16, 1, 1), ("f32", 512, 16, 1, 1)]
+    variants = [("f64", 512, 16, 1, 1), ("f32", 512, 16, 1, 1), ("mixed", 512, 16, 1, 1)]
     for N in (16384,):
         for prec, thr, rad, ctas, kern in variants:
             try:

@@ -374,7 +374,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--system", default="PAL", choices=["PAL", "NTSC"])
     ap.add_argument("--audio", action="store_true", help="also demodulate the two analog FM audio channels")
-    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32", "mixed"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     a = ap.parse_args()
     if a.impl == "reference":

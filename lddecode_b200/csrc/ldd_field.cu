@@ -195,14 +195,17 @@ struct BurstParams {
 
 constexpr int BURST_K = 32;          // same Green's function reach as the TBC kernel
 constexpr int BURST_FIRST = 20, BURST_N = 40;
-constexpr int BURST_WIN = 256;       // input samples staged per line (>= 2*(FIRST+N)*max step + K + margin)
+constexpr int BURST_WIN = 192;       // input samples staged per line (>= 2*(FIRST+N)*max step + K + margin)
+constexpr int BURST_WARPS = 32;      // one warp per line in flight, 1024 threads per field
 
-__global__ void __launch_bounds__(256) refine_burst_kernel(const BurstParams p) {
-    __shared__ double ys[8][BURST_WIN];
-    __shared__ double Ms[8][BURST_WIN];
-    __shared__ double bas[8][BURST_N];
+__global__ void __launch_bounds__(32 * BURST_WARPS) refine_burst_kernel(const BurstParams p) {
+    LDD_DYN_SMEM(bsm);
+    double (*ys)[BURST_WIN] = (double (*)[BURST_WIN])bsm;
+    double (*Ms)[BURST_WIN] = ys + BURST_WARPS;
+    double (*bas)[BURST_N] = (double (*)[BURST_N])(Ms + BURST_WARPS);
     __shared__ double taps[2 * BURST_K + 3];
     __shared__ double phase[2][512];
+    __shared__ int s_group;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int linecount = p.linecount[f], nll = linecount + 4;
     const long long base = p.base[f];
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(256) refine_burst_kernel(const BurstParams p) 
     __syncthreads();
     const double hz_ire = 1700000.0 / 140.0;
     const int W = p.outwidth;
-    for (int l = warp; l < linecount; l += 8) {
+    for (int l = warp; l < linecount; l += BURST_WARPS) {
         const double b = lin[l], e = lin[l + 1];
         const long long ib = (long long)b, ie = (long long)e;
         const int dist = (int)(ie - ib);
@@ -305,35 +308,54 @@ __global__ void __launch_bounds__(256) refine_burst_kernel(const BurstParams p) 
         __syncwarp();
     }
     __syncthreads();
+    // medians of both columns over lines that produced a phase (lddecode_core.py:1112-1117): compact,
+    // then rank-sort in parallel (each thread places one element), thread 0 reads the middles.
+    double* col0 = &ys[0][0];                 // the staging buffers are free now
+    double* col1 = col0 + 512;
+    double* srt0 = col1 + 512;
+    double* srt1 = srt0 + 512;
+    __shared__ int s_nc;
     if (tid == 0) {
-        // medians of both columns over lines that produced a phase (lddecode_core.py:1112-1117)
-        double* col[2] = {&ys[0][0], &ys[4][0]};          // the staging buffers are free now: 2 x 1024 doubles
         int nc = 0;
         for (int l = 0; l < nll; ++l)
-            if (phase[0][l] != 0 || phase[1][l] != 0) { col[0][nc] = phase[0][l]; col[1][nc] = phase[1][l]; ++nc; }
+            if (phase[0][l] != 0 || phase[1][l] != 0) { col0[nc] = phase[0][l]; col1[nc] = phase[1][l]; ++nc; }
+        s_nc = nc;
+    }
+    __syncthreads();
+    const int nc = s_nc;
+    for (int t = tid; t < 2 * nc; t += blockDim.x) {
+        const double* c = t < nc ? col0 : col1;
+        double* d = t < nc ? srt0 : srt1;
+        const int me = t < nc ? t : t - nc;
+        const double v = c[me];
+        int rank = 0;
+        for (int i = 0; i < nc; ++i) rank += (c[i] < v) || (c[i] == v && i < me);
+        d[rank] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
         int group = 1;
         if (nc > 0) {
-            double med[2];
-            for (int q = 0; q < 2; ++q) {
-                // insertion sort (nc <= 267)
-                for (int i = 1; i < nc; ++i) {
-                    double v = col[q][i];
-                    int j = i - 1;
-                    while (j >= 0 && col[q][j] > v) { col[q][j + 1] = col[q][j]; --j; }
-                    col[q][j + 1] = v;
-                }
-                med[q] = (nc & 1) ? col[q][nc / 2] : (col[q][nc / 2 - 1] + col[q][nc / 2]) / 2.0;
-            }
-            group = fabs(med[0]) < fabs(med[1]) ? 0 : 1;
+            double m0 = (nc & 1) ? srt0[nc / 2] : (srt0[nc / 2 - 1] + srt0[nc / 2]) / 2.0;
+            double m1 = (nc & 1) ? srt1[nc / 2] : (srt1[nc / 2 - 1] + srt1[nc / 2]) / 2.0;
+            group = fabs(m0) < fabs(m1) ? 0 : 1;
         }
-        for (int l = group; l < nll; l += 2) level[l] = -level[l];
-        const double k4 = p.freq / (4.0 * 315.0 / 88.0);
-        for (int l = 0; l < nll; ++l) {
-            double adj = phase[group][l];
-            double v = lin[l];
-            if (fabs(adj) > 2) level[l] = 0.f; else v -= adj * k4 * 1;
-            lout[l] = v;
-        }
+        s_group = group;
+    }
+    __syncthreads();
+    const int group = s_group;
+    const double k4 = p.freq / (4.0 * 315.0 / 88.0);
+    for (int l = tid; l < nll; l += blockDim.x) {
+        float lv = level[l];
+        if ((l & 1) == (group & 1)) lv = -lv;          // burstlevel[phasegroup::2] = -burstlevel[phasegroup::2]
+        double adj = phase[group][l];
+        double v = lin[l];
+        if (fabs(adj) > 2) lv = 0.f; else v -= adj * k4 * 1;
+        level[l] = lv;
+        lout[l] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
         for (int l = 2; l < nll - 1; ++l)
             if (level[l] == 0.f) lout[l] = (lout[l - 1] + lout[l + 1]) / 2;
     }
@@ -759,7 +781,9 @@ extern "C" int ldd_refine_burst(ldd_handle* h, const float* burst_dev, long long
     p.burst = burst_dev; p.n = n; p.freq = h->cfg.freq_hz / 1e6; p.linelen = h->cfg.linelen; p.outwidth = h->cfg.outlinelen;
     p.base = base_dev; p.linecount = linecount_dev; p.ll_stride = ll_stride; p.linelocs_in = linelocs_in_dev;
     p.linelocs_out = linelocs_out_dev; p.burstlevel = burstlevel_dev; p.status = status_dev;
-    LDD_LAUNCH(refine_burst_kernel, dim3(nfields), dim3(256), 0, (cudaStream_t)stream, p);
+    size_t bsmem = (size_t)BURST_WARPS * (2 * BURST_WIN + BURST_N) * sizeof(double);
+    cudaFuncSetAttribute(refine_burst_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+    LDD_LAUNCH(refine_burst_kernel, dim3(nfields), dim3(32 * BURST_WARPS), bsmem, (cudaStream_t)stream, p);
     return launch_status(h, "refine_burst_kernel");
 }
 

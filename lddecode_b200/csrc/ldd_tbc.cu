@@ -18,6 +18,12 @@ constexpr int TBC_K = 24;                 // reach of the Green's function FIR: 
 constexpr int TBC_H = TBC_K + 1;          // halo samples needed on each side
 constexpr int TBC_MAXD = 4032;            // longest input line span supported
 constexpr int TBC_THREADS = 256;
+constexpr int TBC_NTAPS = 2 * TBC_H + 1;  // taps of the y -> P filter
+constexpr int TBC_OPT = 8;                // outputs per thread and sweep of the register-tiled FIR
+
+// w[m] = 6 (g[m-1] - 2 g[m] + g[m+1]), g[k] = r^|k| / (2 sqrt 3) truncated to |k| <= K: set once per
+// process.  Constant memory lets the fully unrolled FIR take its taps as immediate constant-bank operands.
+__constant__ double c_tbc_taps[TBC_NTAPS];
 
 struct TbcParams {
     const float* plane;       // input plane
@@ -44,8 +50,7 @@ struct TbcParams {
 __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
     LDD_DYN_SMEM(smem_raw);
     double* ys = (double*)smem_raw;                       // y[-H .. dist+H]
-    double* Ms = ys + (TBC_MAXD + 2 * TBC_H + 2);         // M[0 .. dist]
-    __shared__ double taps[2 * TBC_H + 1];
+    double* Ms = ys + (TBC_MAXD + 2 * TBC_H + TBC_OPT + 2);   // M[0 .. dist]
     __shared__ double s_ab[2];
 
     const int tid = threadIdx.x;
@@ -65,25 +70,32 @@ __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
     }
     const double r = -0.26794919243112270647;      // sqrt(3) - 2
     const double c = 0.28867513459481288225;       // 1 / (2 sqrt 3)
-    // taps of P = w * y, w[m] = 6 (g[m-1] - 2 g[m] + g[m+1]) with g truncated to |k| <= K
-    for (int m = tid; m <= 2 * TBC_H; m += TBC_THREADS) {
-        int k = m - TBC_H;
-        auto g = [&](int q) -> double { int a = q < 0 ? -q : q; return a > TBC_K ? 0.0 : c * pow(r, (double)a); };
-        taps[m] = 6.0 * (g(k - 1) - 2.0 * g(k) + g(k + 1));
-    }
     // stage the samples (relative values; the spline is linear so plane_add is added at the end)
-    for (int i = tid; i < dist + 1 + 2 * TBC_H; i += TBC_THREADS) {
+    for (int i = tid; i < dist + 1 + 2 * TBC_H + TBC_OPT; i += TBC_THREADS) {
         long long s = base + ib - TBC_H + i;
         s = s < 0 ? 0 : (s >= p.n ? p.n - 1 : s);
         ys[i] = (double)p.plane[s];
     }
     __syncthreads();
-    for (int i = tid; i <= dist; i += TBC_THREADS) {
-        double acc = 0.0;
-        const double* y = ys + i;                         // y[i-H] ... y[i+H]
+    // P = w * y, register tiled: one shared-memory load feeds up to TBC_OPT accumulators, the taps are
+    // constant-bank operands (a plain tap-by-tap loop is bound by shared-memory bandwidth: 2 loads per FMA)
+    for (int i0 = tid * TBC_OPT; i0 <= dist; i0 += TBC_THREADS * TBC_OPT) {
+        double acc[TBC_OPT];
         LDD_UNROLL
-        for (int m = 0; m <= 2 * TBC_H; ++m) acc = fma(taps[m], y[m], acc);
-        Ms[i] = acc;
+        for (int o = 0; o < TBC_OPT; ++o) acc[o] = 0.0;
+        const double* y = ys + i0;                        // y[i0-H] ... ; output o uses y[o + m], m = 0..NTAPS-1
+        LDD_UNROLL
+        for (int t = 0; t < TBC_NTAPS + TBC_OPT - 1; ++t) {
+            const double yv = y[t];
+            LDD_UNROLL
+            for (int o = 0; o < TBC_OPT; ++o) {
+                const int m = t - o;
+                if (m >= 0 && m < TBC_NTAPS) acc[o] = fma(c_tbc_taps[m], yv, acc[o]);
+            }
+        }
+        LDD_UNROLL
+        for (int o = 0; o < TBC_OPT; ++o)
+            if (i0 + o <= dist) Ms[i0 + o] = acc[o];
     }
     __syncthreads();
     if (tid == 0) {
@@ -173,7 +185,15 @@ extern "C" int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n
     double clevel = (1.0 / colorlevel) / (1700000.0 / 140.0);
     p.clevel_k = (float)(327.67 * clevel);
     p.status = status_dev;
-    size_t smem = (size_t)(TBC_MAXD + 2 * TBC_H + 2 + TBC_MAXD + 2) * sizeof(double);
+    size_t smem = (size_t)(TBC_MAXD + 2 * TBC_H + TBC_OPT + 2 + TBC_MAXD + TBC_OPT + 2) * sizeof(double);
+    if (!h->tbc_taps_set) {
+        const double r = -0.26794919243112270647, c = 0.28867513459481288225;
+        double taps[TBC_NTAPS];
+        auto g = [&](int q) -> double { int a = q < 0 ? -q : q; return a > TBC_K ? 0.0 : c * pow(r, (double)a); };
+        for (int m = 0; m < TBC_NTAPS; ++m) { int k = m - TBC_H; taps[m] = 6.0 * (g(k - 1) - 2.0 * g(k) + g(k + 1)); }
+        cudaMemcpyToSymbol(c_tbc_taps, taps, sizeof taps);
+        h->tbc_taps_set = true;
+    }
     cudaFuncSetAttribute(tbc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaStream_t st = (cudaStream_t)stream;
     LDD_LAUNCH(tbc_kernel, dim3(max_linecount, nfields), dim3(TBC_THREADS), smem, st, p);

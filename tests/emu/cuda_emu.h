@@ -196,6 +196,11 @@ static inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc
 static inline cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { std::memmove(d, s, n); return cudaSuccess; }
+template <class S>
+static inline cudaError_t cudaMemcpyToSymbol(S& sym, const void* src, size_t n, size_t off = 0, cudaMemcpyKind = cudaMemcpyHostToDevice) {
+    std::memcpy((char*)&sym + off, src, n);
+    return cudaSuccess;
+}
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { std::memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }

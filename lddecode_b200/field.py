@@ -218,6 +218,7 @@ class Field:
         self.valid = False
         self.dspicture = None
         self.dsaudio = None
+        self.audio_rec = None
         self.audio_next_offset = audio_offset
         self.colorlevel, self.colorphase = colorlevel, colorphase
         self.burstlevel = None

@@ -162,10 +162,11 @@ class CaptureDecoder:
             pk = vl = None
             npre = min(wl, 40 * L)
             spk, svl = F.sync_peaks_device(rf, planes['demod_sync'][b:b + npre], npre, 0)
-            common = np.nonzero(np.isin(spk + b, gpk))[0]
+            pos = np.searchsorted(gpk, spk + b)
+            common = np.nonzero(gpk[np.minimum(pos, len(gpk) - 1)] == spk + b)[0] if len(gpk) else np.zeros(0, dtype=np.int64)
             if len(common):
                 k = int(common[0])
-                m = int(np.searchsorted(gpk, spk[k] + b))
+                m = int(pos[k])
                 pk = np.concatenate([spk[:k], gpk[m:] - b])
                 vl = np.concatenate([svl[:k], gvl[m:]])
                 # a peak belongs to the window's list iff the step that found it started below the bound

@@ -90,6 +90,12 @@ class DeviceDemod:
             v += self.rf.SysParams['ire0']
         return v
 
+    def audio_recarray(self):
+        if self.audio is None:
+            return None
+        return np.rec.array([self.rf._be.to_host(self.audio['audio_left']), self.rf._be.to_host(self.audio['audio_right'])],
+                            names=['audio_left', 'audio_right'])
+
     def to_recarrays(self):
         names = VIDEO_FIELDS[self.rf.system]
         video = np.rec.array([self.plane_host(n) for n in names], names=names)
@@ -241,6 +247,15 @@ class RFDecode:
         self._check(rc)
         self._upload_filters()
 
+    def set_blockcut(self, blockcut):
+        """RFDecode.blockcut is a plain instance attribute in the reference (lddecode_core.py:122); here the
+        device handle has to follow it."""
+        self.blockcut = int(blockcut)
+        if self._h is not None:
+            self._be.lib.ldd_destroy(self._h)
+            self._h = None
+        self._create_handle()
+
     def _set_filter(self, fid, table):
         t = np.ascontiguousarray(table, dtype=np.complex128)
         self._check(self._be.lib.ldd_set_filter(self._h, fid, t.ctypes.data_as(C.c_void_p), len(t)))
@@ -337,6 +352,13 @@ class RFDecode:
 
         The samples of all blocks are fetched with one call of the module-global `loader`
         (same contract as the reference's, lddutils.py:117-129) instead of one call per block."""
+        out = self.demod_raw(infile, start, length, mtf_level)
+        if out is None:
+            return None
+        return out.to_recarrays()
+
+    def demod_raw(self, infile, start, length, mtf_level=0):
+        """Like demod() but the result stays in device memory (a DeviceDemod, which Field accepts)."""
         r = self.range_query(start, length)
         need = int(r.last_needed - r.first_sample)
         try:
@@ -349,11 +371,7 @@ class RFDecode:
         if data.dtype not in _FMT_OF_DTYPE:
             data = data.astype(np.int16)
         dev = self._be.to_device(data)
-        out = self.demod_device(dev, _FMT_OF_DTYPE[data.dtype], r.first_sample, need, start, length, mtf_level)
-        if out is None:
-            return None
-        video, audio = out.to_recarrays()
-        return video, audio
+        return self.demod_device(dev, _FMT_OF_DTYPE[data.dtype], r.first_sample, need, start, length, mtf_level)
 
     def demodblock(self, data, mtf_level=0):
         """RFDecode.demodblock (lddecode_core.py:288-330) for one block of `blocklen` samples:

@@ -9,6 +9,7 @@ ddunpack.c compiled by oracle/Makefile) on seeded synthetic RF from lddecode_b20
 The captures themselves are stored too, so the vectors do not depend on libm/SIMD details of the
 machine that replays them.
 """
+import io
 import os
 import subprocess
 import sys
@@ -112,6 +113,22 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, "peaks", len(f.peaklist), "vsyncs", np.array(f.vsyncs).tolist(), "framenr", f.vbi["framenr"],
               "size", os.path.getsize(os.path.join(HERE, name + ".npz")))
+
+    # --- one whole frame through Framer.readframe, as lddecode.py:88-98 does
+    system, fs, N = "NTSC", 8 * 315 / 88, 16384
+    cap = synth.SynthRF(system, fs, seed=3).generate(1530000)
+    ref.loader = refshim.make_array_loader(cap)
+    rf = ref.RFDecode(inputfreq=fs, system=system, blocklen_=N)
+    fr = ref.Framer(rf)
+    import contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        combined, conaudio, nextsample, fields = fr.readframe(refshim.MemFile(), 0, True)
+    np.savez_compressed(os.path.join(HERE, "ntsc_frame.npz"), capture=cap, fs_mhz=np.array(fs), blocklen=np.array(N),
+                        combined=combined, conaudio=conaudio, nextsample=np.array(nextsample),
+                        framenr=np.array(fr.vbi["framenr"]), mtf_level=np.array(fr.mtf_level),
+                        audio_offset=np.array(fr.audio_offset),
+                        field_readlens=np.array([f.linecount for f in fields]))
+    print("frame: framenr", fr.vbi["framenr"], "nextsample", nextsample, "audio", None if conaudio is None else len(conaudio))
 
     # --- integer unpackers
     rng = np.random.default_rng(42)

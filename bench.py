@@ -30,6 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FS = {"NTSC": 8 * 315 / 88, "PAL": 35.46895}
+RANGES = [2]
 BLOCKLEN = 16384                     # the reference's default blocklen_ (lddecode_core.py:120)
 TAIL = 1100000                       # so the last 1e6-sample read succeeds
 
@@ -141,7 +142,7 @@ def run_reference(a):
 def workload_config(system, audio, gpus):
     return dict(workload="%s synthetic 8-bit RF, 1 s at 8fsc (%.3f MSPS) per GPU, %s demod + sync + TBC to uint16 4fsc"
                          % (system, FS[system], "video+audio" if audio else "video"),
-                blocklen=BLOCKLEN, readlen=1000000, parallelism="block-range shards, one 1-s shard per GPU (x%d)" % gpus,
+                blocklen=BLOCKLEN, readlen=1000000, ranges_per_step=RANGES[0], parallelism="block-range shards, one 1-s shard per GPU (x%d)" % gpus,
                 l2="per step 36 MB in + ~0.9 GB of planes written: working set exceeds the 126 MB L2, no flush needed")
 
 
@@ -225,19 +226,29 @@ def run_ours(a):
 
     gatherer = parallel.FieldGatherer(cd, rank, world, max_fields, dist) if world > 1 else None
 
+    def decode(dev):
+        # one capture per step; inside the step it is split into read-position ranges whose host walks
+        # overlap the device work of the other ranges (bit-identical to the single-range decode)
+        if a.ranges > 1:
+            return cd.decode_pipelined(dev, _lib.FMT_U8, ncap, a.ranges)
+        return [cd.decode(dev, _lib.FMT_U8, ncap)]
+
     def step_resident():
-        res = cd.decode(cap_dev, _lib.FMT_U8, ncap)
+        res = decode(cap_dev)
         if world > 1:
             gatherer.gather(res)        # NCCL gather of the uint16 fields + positions into rank 0's HBM
         return res
 
     def step_e2e(out_pin):
         d = cap_pin.cuda(non_blocking=True)                         # H2D of the step's input
-        res = cd.decode(d, _lib.FMT_U8, ncap)
-        n = len(res.located) * res.out_stride
-        out_pin[:n].copy_(res.d_pic[:n], non_blocking=True)         # D2H of the step's result
-        if res.audio is not None:
-            res.audio_host = (res.audio['audio_left'].cpu(), res.audio['audio_right'].cpu())
+        res = decode(d)
+        n = 0
+        for r in res:
+            m = len(r.located) * r.out_stride
+            out_pin[n:n + m].copy_(r.d_pic[:m], non_blocking=True)  # D2H of the step's result
+            n += m
+            if r.audio is not None:
+                r.audio_host = (r.audio['audio_left'].cpu(), r.audio['audio_right'].cpu())
         if world > 1:
             gatherer.gather(res)
         torch.cuda.current_stream().synchronize()
@@ -253,9 +264,12 @@ def run_ours(a):
     for _ in range(max(a.warmup, 3)):
         res = step_resident()
     torch.cuda.synchronize()
-    nfields = len(res.located)
-    consumed = res.plane_len                      # samples demodulated once each (overlap re-reads not counted)
-    out_pin = torch.empty(max_fields * res.out_stride, dtype=torch.uint16).pin_memory()
+    nfields = sum(len(r.located) for r in res)
+    # samples of the capture demodulated and decoded per step (each counted once: neither the block
+    # overlaps nor the halos that neighbouring ranges demodulate twice are counted)
+    S_ = cd.stride
+    consumed = ((ncap - BLOCKLEN) // S_ + 1) * S_
+    out_pin = torch.empty(max_fields * res[0].out_stride, dtype=torch.uint16).pin_memory()
 
     # resident timing
     barrier()
@@ -320,7 +334,8 @@ def run_ours(a):
         N, S = BLOCKLEN, BLOCKLEN - 1056
         bytes_per_sample = N / S + 4 * nplanes32 + 8 + (2 * 8 / (16 if system == "PAL" else 8) if audio else 0)
         achieved = bytes_per_sample * planes_total / (k_ms / 1e3) / 1e9
-        launches_per_step = 1 + 2 + 1 + (1 if system == "PAL" else 2) + 1 + (2 if audio else 0)
+        # per range: demod, 4 peak kernels (+4 for the one window that starts off a peak), hsync, pilot | 2x burst, tbc, 2 audio
+        launches_per_step = a.ranges * (1 + 4 + 1 + (1 if system == "PAL" else 2) + 1 + (2 if audio else 0)) + 4
         line = dict(metric="rf_msamples_per_s_demod_tbc", value=value, unit="Msamples/s", n_gpus=world, steps=a.steps,
                     warmup=max(a.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype=a.precision, data="synthetic", config=workload_config(system, audio, world),
@@ -376,7 +391,9 @@ def main():
     ap.add_argument("--audio", action="store_true", help="also demodulate the two analog FM audio channels")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32", "mixed"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--ranges", type=int, default=2, help="read-position ranges a step's capture is pipelined over")
     a = ap.parse_args()
+    RANGES[0] = a.ranges
     if a.impl == "reference":
         run_reference(a)
     else:

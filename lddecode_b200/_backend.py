@@ -55,6 +55,44 @@ class CudaBackend:
     def is_device_buffer(self, x):
         return self.torch.is_tensor(x) and x.is_cuda
 
+    # -- streams / events / pinned staging (whole-capture pipeline)
+    def new_stream(self):
+        return self.torch.cuda.Stream(self.device)
+
+    def stream_ctx(self, stream):
+        return self.torch.cuda.stream(stream)
+
+    def current_stream_obj(self):
+        return self.torch.cuda.current_stream(self.device)
+
+    def wait_stream(self, waiter, other):
+        waiter.wait_stream(other)
+
+    def pinned(self, n, dtype):
+        return self.torch.empty(int(n), dtype=_NP2TORCH[np.dtype(dtype)]).pin_memory()
+
+    def copy_async(self, dst, src):
+        dst.copy_(src, non_blocking=True)
+
+    def record_event(self):
+        ev = self.torch.cuda.Event()
+        ev.record(self.torch.cuda.current_stream(self.device))
+        return ev
+
+    def wait_event(self, ev):
+        ev.synchronize()
+
+    def host_view(self, pinned_buf):
+        return pinned_buf.numpy()
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
 
 class EmuBackend:
     """numpy buffers + the g++-compiled emulation library.  Tests only."""
@@ -87,3 +125,31 @@ class EmuBackend:
 
     def is_device_buffer(self, x):
         return False
+
+    # -- streams / events: everything is synchronous in the emulation
+    def new_stream(self):
+        return None
+
+    def stream_ctx(self, stream):
+        return _NullCtx()
+
+    def current_stream_obj(self):
+        return None
+
+    def wait_stream(self, waiter, other):
+        pass
+
+    def pinned(self, n, dtype):
+        return np.empty(int(n), dtype=dtype)
+
+    def copy_async(self, dst, src):
+        dst[...] = src
+
+    def record_event(self):
+        return None
+
+    def wait_event(self, ev):
+        pass
+
+    def host_view(self, pinned_buf):
+        return pinned_buf

@@ -41,18 +41,41 @@ class FieldBatch:
         self.vals = [None] * nfields
 
 
-def sync_peaks_device(rf, sync_buf, n, start=0):
-    """Field.get_syncpeaks on a device float64 demod_sync plane -> (peaks int64, values float64) on the host."""
+class PendingPeaks:
+    """An enqueued peak chase whose results are on their way to pinned host memory."""
+
+    def __init__(self, be, ev, h_pk, h_vl, h_cnt, keep):
+        self.be, self.ev, self.h_pk, self.h_vl, self.h_cnt, self.keep = be, ev, h_pk, h_vl, h_cnt, keep
+
+    def result(self):
+        be = self.be
+        be.wait_event(self.ev)
+        c = int(be.host_view(self.h_cnt)[0])
+        return be.host_view(self.h_pk)[:c].copy(), be.host_view(self.h_vl)[:c].copy()
+
+
+def sync_peaks_launch(rf, sync_buf, n, start=0, staging=None):
+    """Enqueue Field.get_syncpeaks on a device float64 demod_sync plane and the device->host copy of its
+    result (asynchronous); returns a PendingPeaks.  `staging`: dict reused across calls for the buffers."""
     be = rf._be
     cap = int(n // int(rf.linelen * .4)) + 8
-    pk = be.empty(cap, np.int64)
-    vl = be.empty(cap, np.float64)
-    cnt = be.zeros(2, np.int32)
-    rf._check(be.lib.ldd_sync_peaks(rf._h, be.ptr(sync_buf), int(n), int(start), be.ptr(pk), be.ptr(vl), cap,
+    st = staging if staging is not None else {}
+    if st.get('cap', 0) < cap:
+        st['cap'] = cap
+        st['pk'], st['vl'], st['cnt'] = be.empty(cap, np.int64), be.empty(cap, np.float64), be.zeros(2, np.int32)
+        st['h_pk'], st['h_vl'], st['h_cnt'] = be.pinned(cap, np.int64), be.pinned(cap, np.float64), be.pinned(2, np.int32)
+    pk, vl, cnt = st['pk'], st['vl'], st['cnt']
+    rf._check(be.lib.ldd_sync_peaks(rf._h, be.ptr(sync_buf), int(n), int(start), be.ptr(pk), be.ptr(vl), st['cap'],
                                     be.ptr(cnt), be.stream()))
-    be.synchronize()
-    c = int(be.to_host(cnt)[0])
-    return be.to_host(pk)[:c].copy(), be.to_host(vl)[:c].copy()
+    be.copy_async(st['h_cnt'], cnt)
+    be.copy_async(st['h_pk'][:cap], pk[:cap])
+    be.copy_async(st['h_vl'][:cap], vl[:cap])
+    return PendingPeaks(be, be.record_event(), st['h_pk'], st['h_vl'], st['h_cnt'], st)
+
+
+def sync_peaks_device(rf, sync_buf, n, start=0, staging=None):
+    """Field.get_syncpeaks on a device float64 demod_sync plane -> (peaks int64, values float64) on the host."""
+    return sync_peaks_launch(rf, sync_buf, n, start, staging).result()
 
 
 def locate(rf, peaks, vals, window_len, start=0):

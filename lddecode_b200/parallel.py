@@ -47,25 +47,36 @@ class FieldGatherer:
         else:
             self.pics, self.metas = [self.pic], [self.meta]
 
-    def gather(self, res):
+    def gather(self, results):
+        """results: one RangeResult or the list decode_pipelined returns."""
         torch = self.torch
-        nloc = len(res.located)
-        if nloc > self.max_fields:
-            raise ValueError("max_fields too small")
+        if not isinstance(results, (list, tuple)):
+            results = [results]
         meta = np.full((self.max_fields, 4), -1, dtype=np.int64)
-        for k, j in enumerate(res.located):
-            info = res.infos[j]
-            meta[k] = (res.readsamples[j], info.istop, info.linecount, 0)
+        k0 = 0
+        spans = []
+        for res in results:
+            nloc = len(res.located)
+            if k0 + nloc > self.max_fields:
+                raise ValueError("max_fields too small")
+            for k, j in enumerate(res.located):
+                info = res.infos[j]
+                meta[k0 + k] = (res.readsamples[j], info.istop, info.linecount, 0)
+            spans.append((k0, nloc, res))
+            k0 += nloc
         tm = torch.from_numpy(meta)
         if self.cuda:
             self.meta.copy_(tm, non_blocking=True)
-            if nloc:
-                self.meta[:nloc, 3] = res.d_status[:nloc].to(torch.int64)
-                self.pic[:nloc * self.stride * 2] = res.d_pic[:nloc * self.stride].view(torch.uint8)
+            for k0, nloc, res in spans:
+                if nloc:
+                    self.meta[k0:k0 + nloc, 3] = res.d_status[:nloc].to(torch.int64)
+                    self.pic[k0 * self.stride * 2:(k0 + nloc) * self.stride * 2] = res.d_pic[:nloc * self.stride].view(torch.uint8)
         else:
-            if nloc:
-                tm[:nloc, 3] = torch.from_numpy(np.asarray(self.be.to_host(res.d_status)[:nloc], dtype=np.int64))
-                self.pic[:nloc * self.stride * 2] = torch.from_numpy(self.be.to_host(res.d_pic)[:nloc * self.stride].view(np.uint8))
+            for k0, nloc, res in spans:
+                if nloc:
+                    tm[k0:k0 + nloc, 3] = torch.from_numpy(np.asarray(self.be.to_host(res.d_status)[:nloc], dtype=np.int64))
+                    self.pic[k0 * self.stride * 2:(k0 + nloc) * self.stride * 2] = \
+                        torch.from_numpy(self.be.to_host(res.d_pic)[:nloc * self.stride].view(np.uint8))
             self.meta.copy_(tm)
         if self.world > 1:
             self.dist.gather(self.pic, self.pics if self.rank == 0 else None, dst=0)

@@ -47,15 +47,18 @@ class CaptureDecoder:
         # planes; re-allocating that per call stalls on cudaMalloc).  Results of decode_range
         # therefore stay valid until the next call on the same CaptureDecoder.
         self._ws = {}
+        self._staging = {}
+        self._lanes = None          # extra (RFDecode, stream, workspace, staging) sets of decode_pipelined
 
-    def _buf(self, tag, n, dtype):
+    def _buf(self, tag, n, dtype, ws=None):
+        ws = self._ws if ws is None else ws
         key = (tag, np.dtype(dtype).str)
-        b = self._ws.get(key)
+        b = ws.get(key)
         if b is None or len(b) < n:
             b = None
-            self._ws.pop(key, None)
+            ws.pop(key, None)
             b = self.rf._be.empty(int(n * 1.02) + 16, dtype)
-            self._ws[key] = b
+            ws[key] = b
         return b[:n]
 
     @property
@@ -79,7 +82,14 @@ class CaptureDecoder:
 
         cap_dev holds capture samples [cap_base, cap_base + cap_len) in format fmt; ncap_total is the
         length of the whole capture (the reference stops when a read would pass its end)."""
-        rf, be = self.rf, self.rf._be
+        pend = self._launch_demod(self.rf, self._ws, self._staging, cap_dev, fmt, cap_base, cap_len, ncap_total, r0, r1,
+                                  audio_phase2)
+        return self._finish_range(self.rf, pend, want_tables)
+
+    def _launch_demod(self, rf, ws, staging, cap_dev, fmt, cap_base, cap_len, ncap_total, r0, r1, audio_phase2=True):
+        """Stage 1 (asynchronous): demodulate the range's blocks, chase the sync peaks, start their copy
+        to pinned host memory."""
+        be = rf._be
         S, N = self.stride, rf.blocklen
         first_block, nblocks, walk_start = self.plan_range(ncap_total, r0, r1)
         avail_end = min(cap_base + cap_len, ncap_total)
@@ -90,29 +100,41 @@ class CaptureDecoder:
         total = nblocks * S
         res = RangeResult()
         res.r0, res.r1, res.plane_origin, res.plane_len = r0, r1, first_block, total
+        res.ncap_total, res.walk_start = ncap_total, walk_start
+        res.staging = staging
         rf._set_mtf(self.mtf_level)
-        planes, parr = rf._alloc_planes(max(total, 1), alloc=lambda name, n, dt: self._buf("plane_" + name, n, dt))
+        planes, parr = rf._alloc_planes(max(total, 1), alloc=lambda name, n, dt: self._buf("plane_" + name, n, dt, ws))
         a1l = a1r = None
         alen = 0
         if rf.decode_analog_audio:
             ds = N // len(rf.Filters['audio_lfilt'])
             alen = total // ds
-            a1l, a1r = self._buf("a1l", max(alen, 1), np.float64), self._buf("a1r", max(alen, 1), np.float64)
+            a1l, a1r = self._buf("a1l", max(alen, 1), np.float64, ws), self._buf("a1r", max(alen, 1), np.float64, ws)
         if nblocks:
             rf._check(be.lib.ldd_demod_blocks(rf._h, be.ptr(cap_dev), fmt, int(cap_base), int(cap_len), int(first_block),
                                               int(nblocks), int(total), parr, be.ptr(a1l) if a1l is not None else None,
                                               be.ptr(a1r) if a1r is not None else None, int(alen), be.stream()))
         res.planes = planes
+        # sync-peak chase over the whole plane; its result is the only device->host hop of the path
+        res.pending_peaks = F.sync_peaks_launch(rf, planes['demod_sync'], total, 0, staging)
+        # the second audio stage does not depend on the walk: enqueue it behind the chase so that it
+        # runs while the host walks the fields
         res.audio = None
         if rf.decode_analog_audio:
             if audio_phase2 and alen > rf.blocklen:
                 res.audio = rf._audio_phase2_device(a1l, a1r, alen)
             else:
                 res.audio = {'audio_left': a1l, 'audio_right': a1r}
-        # sync-peak chase over the whole plane, then the only device->host hop of the path
-        gpk, gvl = F.sync_peaks_device(rf, planes['demod_sync'], total, 0)
+        return res
+
+    def _finish_range(self, rf, res, want_tables=False):
+        """Stage 2: host walk over the peak list, then the batched refine + TBC launches."""
+        planes, total, r0, r1 = res.planes, res.plane_len, res.r0, res.r1
+        gpk, gvl = res.pending_peaks.result()
+        res.pending_peaks = None
         res.gpeaks = gpk
-        batch, infos, readsamples = self._walk(planes, total, first_block, ncap_total, walk_start, r1, r0 > 0, gpk, gvl)
+        batch, infos, readsamples = self._walk(rf, planes, total, res.plane_origin, res.ncap_total, res.walk_start, r1,
+                                               r0 > 0, gpk, gvl, res.staging)
         owned = [i for i in range(len(infos)) if r0 <= readsamples[i] < r1]
         res.infos = [infos[i] for i in owned]
         res.readsamples = readsamples[owned] if len(owned) else np.zeros(0, dtype=np.int64)
@@ -135,13 +157,47 @@ class CaptureDecoder:
             res.d_pic, res.d_status = ref.d_pic, ref.d_status
         return res
 
+    def decode_pipelined(self, cap_dev, fmt, ncap, nranges=2):
+        """The whole capture as `nranges` read-position ranges on their own streams and handles, so that
+        the host walk of one range overlaps the demodulation / resampling of the others.  The union of
+        the ranges' fields is bit-identical to decode() (same global block grid).  Returns the list of
+        RangeResults in capture order."""
+        from . import parallel, rfdecode
+        rf0, be = self.rf, self.rf._be
+        if self._lanes is None or len(self._lanes) < nranges:
+            lanes = [(rf0, None, self._ws, self._staging)] if self._lanes is None else self._lanes
+            while len(lanes) < nranges:
+                rfk = rfdecode.RFDecode(rf0.freq, rf0.system, rf0.blocklen, rf0.decode_analog_audio, precision=rf0.precision,
+                                        _backend=be)
+                lanes.append((rfk, be.new_stream(), {}, {}))
+            if lanes[0][1] is None:
+                lanes[0] = (rf0, be.new_stream(), self._ws, self._staging)
+            self._lanes = lanes
+        main = be.current_stream_obj()
+        bounds = parallel.shard_bounds(ncap, nranges)
+        pend = []
+        for (rfk, sk, ws, stg), (r0, r1) in zip(self._lanes, bounds):
+            if sk is not None:
+                be.wait_stream(sk, main)
+            with be.stream_ctx(sk):
+                pend.append(self._launch_demod(rfk, ws, stg, cap_dev, fmt, 0, ncap, ncap, r0, r1))
+        out = []
+        for (rfk, sk, ws, stg), p in zip(self._lanes, pend):
+            with be.stream_ctx(sk):
+                out.append(self._finish_range(rfk, p))
+            if sk is not None:
+                be.wait_stream(main, sk)
+        return out
+
     def decode(self, cap_dev, fmt, ncap, want_tables=False, audio_phase2=True):
         """The whole capture as one range."""
         return self.decode_range(cap_dev, fmt, 0, ncap, ncap, 0, ncap + 1, want_tables, audio_phase2)
 
     # -- host walk
-    def _walk(self, planes, total, plane_origin, ncap_total, first_readsample, stop_readsample, tolerant, gpk, gvl):
-        rf, be = self.rf, self.rf._be
+    def _walk(self, rf, planes, total, plane_origin, ncap_total, first_readsample, stop_readsample, tolerant, gpk, gvl,
+              staging=None):
+        be = rf._be
+        cb_staging = staging.setdefault('cb', {}) if staging is not None else {}
         mf = self.max_fields
         fields = (_lib.FieldInfo * mf)()
         batch = F.FieldBatch(rf, mf)
@@ -161,7 +217,7 @@ class CaptureDecoder:
             b, wl = int(b), int(wl)
             pk = vl = None
             npre = min(wl, 40 * L)
-            spk, svl = F.sync_peaks_device(rf, planes['demod_sync'][b:b + npre], npre, 0)
+            spk, svl = F.sync_peaks_device(rf, planes['demod_sync'][b:b + npre], npre, 0, cb_staging)
             pos = np.searchsorted(gpk, spk + b)
             common = np.nonzero(gpk[np.minimum(pos, len(gpk) - 1)] == spk + b)[0] if len(gpk) else np.zeros(0, dtype=np.int64)
             if len(common):

@@ -73,6 +73,24 @@ def test_ranges_are_bit_identical_to_one_range(backend):
         assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2])
 
 
+def test_pipelined_ranges_equal_single_decode(backend):
+    """decode_pipelined (ranges on their own handles / streams, host walk overlapped with device work)
+    returns exactly the fields of decode()."""
+    fs = 8 * 315 / 88
+    ncap = 2600000
+    cap = synth.SynthRF("NTSC", fs, seed=9).generate(ncap)
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=False, _backend=backend)
+    cd = pipeline.CaptureDecoder(rf)
+    capd = backend.to_device(cap)
+    one = cd.pictures(cd.decode(capd, _lib.FMT_U8, ncap))
+    parts = []
+    for res in cd.decode_pipelined(capd, _lib.FMT_U8, ncap, nranges=2):
+        parts += cd.pictures(res)
+    assert len(parts) == len(one) == 4
+    for a, b in zip(parts, one):
+        assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2])
+
+
 def test_two_rank_gloo_gather():
     """world_size 2 over gloo on the CPU (emulated kernels): shard, decode, gather on rank 0."""
     script = os.path.join(ROOT, "tests", "dist_worker.py")

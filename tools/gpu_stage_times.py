@@ -39,7 +39,7 @@ for it in range(4):
     if audio:
         timed("audio phase2", lambda: rf._audio_phase2_device(a1[0], a1[1], alen), acc)
     gpk, gvl = timed("peaks (+D2H)", lambda: F.sync_peaks_device(rf, planes['demod_sync'], total, 0), acc)
-    batch, infos, rs = timed("host walk", lambda: cd._walk(planes, total, 0, ncap, 0, ncap + 1, False, gpk, gvl), acc)
+    batch, infos, rs = timed("host walk", lambda: cd._walk(rf, planes, total, 0, ncap, 0, ncap + 1, False, gpk, gvl), acc)
     located = [i for i, f in enumerate(infos) if f.stage == _lib.FIELD_LOCATED]
     def mk():
         sub = F.FieldBatch(rf, len(located))

@@ -25,7 +25,7 @@ for it in range(5):
     torch.cuda.synchronize()
     t0 = time.perf_counter(); gpk, gvl = orig(rf, planes['demod_sync'], total, 0); t1 = time.perf_counter()
     F.sync_peaks_device = timed_spd; tcb.clear()
-    batch, infos, rs = cd._walk(planes, total, 0, ncap, 0, ncap + 1, False, gpk, gvl)
+    batch, infos, rs = cd._walk(rf, planes, total, 0, ncap, 0, ncap + 1, False, gpk, gvl)
     F.sync_peaks_device = orig
     t2 = time.perf_counter()
     print("peaks+D2H %.2f ms | walk %.2f ms (of which device chase in callback %.2f ms, calls %d) | fields %d" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, sum(tcb), len(tcb), len(infos)))

@@ -30,7 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FS = {"NTSC": 8 * 315 / 88, "PAL": 35.46895}
-RANGES = [2]
+RANGES = [1]
 BLOCKLEN = 16384                     # the reference's default blocklen_ (lddecode_core.py:120)
 TAIL = 1100000                       # so the last 1e6-sample read succeeds
 
@@ -391,7 +391,9 @@ def main():
     ap.add_argument("--audio", action="store_true", help="also demodulate the two analog FM audio channels")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32", "mixed"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--ranges", type=int, default=2, help="read-position ranges a step's capture is pipelined over")
+    ap.add_argument("--ranges", type=int, default=1,
+                    help="read-position ranges a step's capture is pipelined over (measured on B200: 1 is fastest -- the "
+                         "persistent demodulation kernel of one range blocks the small kernels of the other)")
     a = ap.parse_args()
     RANGES[0] = a.ranges
     if a.impl == "reference":

@@ -359,6 +359,7 @@ def run_ours(a):
 def demod_only(cd, cap_dev, ncap):
     """One launch of the demodulation kernel over the whole capture (what the roofline entry times)."""
     rf, be = cd.rf, cd.rf._be
+    rf._set_mtf(cd.mtf_level)
     S, N = cd.stride, rf.blocklen
     first_block, nblocks, _ = cd.plan_range(ncap, 0, ncap + 1)
     while nblocks > 0 and first_block + (nblocks - 1) * S + N > ncap:

@@ -95,6 +95,80 @@ __global__ void __launch_bounds__(256) unpack_f32_kernel(const void* __restrict_
     }
 }
 
+// ---- aligned fast paths: whole packing groups per thread, 16-byte loads and stores ---------------
+// .r30: 4 words (16 B) -> 12 samples.  first % 12 == 0 at the caller.
+template <class OUT>
+__global__ void __launch_bounds__(256) unpack_r30_vec_kernel(const uint4* __restrict__ w, size_t nquads, OUT* __restrict__ out) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nquads) return;
+    uint4 q = w[t];
+    unsigned ww[4] = {q.x, q.y, q.z, q.w};
+    unsigned v[12];
+    LDD_UNROLL
+    for (int i = 0; i < 4; ++i) { v[3 * i] = ww[i] & 0x3ffu; v[3 * i + 1] = (ww[i] >> 10) & 0x3ffu; v[3 * i + 2] = (ww[i] >> 20) & 0x3ffu; }
+    if (sizeof(OUT) == 4) {
+        float4* o = (float4*)out + t * 3;
+        LDD_UNROLL
+        for (int k = 0; k < 3; ++k) o[k] = make_float4((float)v[4 * k], (float)v[4 * k + 1], (float)v[4 * k + 2], (float)v[4 * k + 3]);
+    } else {
+        uint2* o = (uint2*)out + t * 3;            // 12 uint16 = 24 B = three 8-byte stores
+        LDD_UNROLL
+        for (int k = 0; k < 3; ++k) { uint2 u; u.x = v[4 * k] | (v[4 * k + 1] << 16); u.y = v[4 * k + 2] | (v[4 * k + 3] << 16); o[k] = u; }
+    }
+}
+
+// .lds: 80 bytes (five 16-byte loads) -> 64 samples.  first % 64 == 0 at the caller.
+template <class OUT>
+__global__ void __launch_bounds__(128) unpack_lds_vec_kernel(const uint4* __restrict__ src, size_t ngroups, OUT* __restrict__ out) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ngroups) return;
+    unsigned wd[20];
+    LDD_UNROLL
+    for (int i = 0; i < 5; ++i) { uint4 q = src[t * 5 + i]; wd[4 * i] = q.x; wd[4 * i + 1] = q.y; wd[4 * i + 2] = q.z; wd[4 * i + 3] = q.w; }
+    auto byte_at = [&](int b) -> unsigned { return (wd[b >> 2] >> (8 * (b & 3))) & 0xffu; };
+    unsigned v[64];
+    LDD_UNROLL
+    for (int g = 0; g < 16; ++g) {
+        unsigned b0 = byte_at(5 * g), b1 = byte_at(5 * g + 1), b2 = byte_at(5 * g + 2), b3 = byte_at(5 * g + 3), b4 = byte_at(5 * g + 4);
+        v[4 * g] = (b0 << 2) | (b1 >> 6);
+        v[4 * g + 1] = ((b1 & 0x3fu) << 4) | (b2 >> 4);
+        v[4 * g + 2] = ((b2 & 0x0fu) << 6) | (b3 >> 2);
+        v[4 * g + 3] = ((b3 & 0x03u) << 8) | b4;
+    }
+    if (sizeof(OUT) == 4) {
+        float4* o = (float4*)out + t * 16;
+        LDD_UNROLL
+        for (int k = 0; k < 16; ++k) o[k] = make_float4((float)v[4 * k], (float)v[4 * k + 1], (float)v[4 * k + 2], (float)v[4 * k + 3]);
+    } else {
+        uint4* o = (uint4*)out + t * 8;
+        LDD_UNROLL
+        for (int k = 0; k < 8; ++k)
+            o[k] = make_uint4(v[8 * k] | (v[8 * k + 1] << 16), v[8 * k + 2] | (v[8 * k + 3] << 16),
+                              v[8 * k + 4] | (v[8 * k + 5] << 16), v[8 * k + 6] | (v[8 * k + 7] << 16));
+    }
+}
+
+// Runs the aligned bulk of [first, first+n) through a vector kernel; returns how many samples it covered.
+template <class OUT>
+static size_t unpack_bulk(const void* src, int fmt, size_t first, size_t n, OUT* out, cudaStream_t st) {
+    if ((((uintptr_t)src) | ((uintptr_t)out)) & 15) return 0;
+    if (fmt == LDD_FMT_R30 && first % 12 == 0) {
+        size_t nq = n / 12;
+        if (!nq) return 0;
+        const uint4* w = (const uint4*)((const char*)src + first / 3 * 4);
+        LDD_LAUNCH(unpack_r30_vec_kernel<OUT>, dim3((unsigned)((nq + 255) / 256)), dim3(256), 0, st, w, nq, out);
+        return nq * 12;
+    }
+    if (fmt == LDD_FMT_LDS40 && first % 64 == 0) {
+        size_t ng = n / 64;
+        if (!ng) return 0;
+        const uint4* w = (const uint4*)((const char*)src + first / 4 * 5);
+        LDD_LAUNCH(unpack_lds_vec_kernel<OUT>, dim3((unsigned)((ng + 127) / 128)), dim3(128), 0, st, w, ng, out);
+        return ng * 64;
+    }
+    return 0;
+}
+
 }  // namespace ldd
 
 using namespace ldd;
@@ -113,6 +187,9 @@ int ldd_unpack_r30_ddunpack(const uint32_t* words_dev, size_t nwords, int16_t* o
 int ldd_unpack_raw(const void* src_dev, int fmt, size_t first_sample, size_t n, uint16_t* out_dev, void* stream) {
     if (!src_dev || !out_dev || fmt < LDD_FMT_U8 || fmt > LDD_FMT_LDS40) return LDD_EINVAL;
     if (n == 0) return LDD_OK;
+    size_t done = unpack_bulk<uint16_t>(src_dev, fmt, first_sample, n, out_dev, (cudaStream_t)stream);
+    first_sample += done; n -= done; out_dev += done;
+    if (n == 0) return cudaGetLastError() == cudaSuccess ? LDD_OK : LDD_ECUDA;
     size_t threads = (n + 7) / 8;
     unsigned grid = (unsigned)((threads + 255) / 256);
     LDD_LAUNCH(unpack_raw_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, src_dev, fmt, first_sample, n, out_dev);
@@ -122,6 +199,9 @@ int ldd_unpack_raw(const void* src_dev, int fmt, size_t first_sample, size_t n, 
 int ldd_unpack_f32(const void* src_dev, int fmt, size_t first_sample, size_t n, float* out_dev, void* stream) {
     if (!src_dev || !out_dev || fmt < LDD_FMT_U8 || fmt > LDD_FMT_LDS40) return LDD_EINVAL;
     if (n == 0) return LDD_OK;
+    size_t done = unpack_bulk<float>(src_dev, fmt, first_sample, n, out_dev, (cudaStream_t)stream);
+    first_sample += done; n -= done; out_dev += done;
+    if (n == 0) return cudaGetLastError() == cudaSuccess ? LDD_OK : LDD_ECUDA;
     size_t threads = (n + 3) / 4;
     unsigned grid = (unsigned)((threads + 255) / 256);
     LDD_LAUNCH(unpack_f32_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, src_dev, fmt, first_sample, n, out_dev);

@@ -135,6 +135,19 @@ def test_unpack_kernels_bit_exact(backend, golden):
         assert lib.ldd_unpack_f32(backend.ptr(lds), _lib.FMT_LDS40, int(s), 999, backend.ptr(of), backend.stream()) == 0
         backend.synchronize()
         assert np.array_equal(backend.to_host(of)[:999], exp[:999].astype(np.float32))
+    # aligned bulk path (whole packing groups, vector kernels) + ragged remainder, against the oracle
+    rng = np.random.default_rng(3)
+    s10 = rng.integers(0, 1024, 12 * 64 * 5 + 7, dtype=np.uint16)
+    for fmt, packed, first in ((_lib.FMT_R30, synth.pack_r30(s10), 24), (_lib.FMT_LDS40, synth.pack_lds(s10), 128)):
+        pk = backend.to_device(packed)
+        n = len(s10) - first - 3
+        o = backend.empty(n, np.uint16)
+        assert lib.ldd_unpack_raw(backend.ptr(pk), fmt, first, n, backend.ptr(o), backend.stream()) == 0
+        of = backend.empty(n, np.float32)
+        assert lib.ldd_unpack_f32(backend.ptr(pk), fmt, first, n, backend.ptr(of), backend.stream()) == 0
+        backend.synchronize()
+        assert np.array_equal(backend.to_host(o), s10[first:first + n])
+        assert np.array_equal(backend.to_host(of), s10[first:first + n].astype(np.float32))
     # ragged tail and empty input
     o = backend.zeros(16, np.int16)
     assert lib.ldd_unpack_r30_ddunpack(backend.ptr(words), 5, backend.ptr(o), backend.stream()) == 0

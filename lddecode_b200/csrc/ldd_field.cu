@@ -380,9 +380,12 @@ struct PilotParams {
 constexpr int PILOT_MAXOFF = 48;     // zero crossings kept per line (4.7 us of a 3.75 MHz pilot: ~17)
 constexpr int PILOT_MAXLEN = 256;    // samples in 4.7 us (<= 54 MSPS)
 
-__global__ void __launch_bounds__(128) refine_pilot_kernel(const PilotParams p, double* ws_offsets /*[nfields][ll_stride][MAXOFF]*/,
-                                                           int* ws_count /*[nfields][ll_stride]*/) {
-    const int f = blockIdx.x, tid = threadIdx.x;
+constexpr int PILOT_WARPS = 16;
+
+__global__ void __launch_bounds__(32 * PILOT_WARPS) refine_pilot_kernel(const PilotParams p, double* ws_offsets /*[nfields][ll_stride][MAXOFF]*/,
+                                                                       int* ws_count /*[nfields][ll_stride]*/) {
+    __shared__ float s_pil[PILOT_WARPS][PILOT_MAXLEN];      // pilot = flip(demod - demod_05), staged per warp
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nll = p.linecount[f] + 4;
     const long long base = p.base[f];
     const double* lin = p.linelocs_in + (size_t)f * p.ll_stride;
@@ -390,48 +393,60 @@ __global__ void __launch_bounds__(128) refine_pilot_kernel(const PilotParams p, 
     double* offs = ws_offsets + (size_t)f * p.ll_stride * PILOT_MAXOFF;
     int* cnt = ws_count + (size_t)f * p.ll_stride;
     const double fq = p.freq;
-    for (int l = tid; l < nll; l += blockDim.x) {
+    for (int l = warp; l < nll; l += PILOT_WARPS) {
         long long a = (long long)(lin[l] - fq * 4.7), b = (long long)lin[l];
         int len = (int)(b - a);
-        int n = 0;
         double* my = offs + (size_t)l * PILOT_MAXOFF;
         if (len <= 0 || len > PILOT_MAXLEN || base + a < 0 || base + b > p.n) {
-            atomicOr(&p.status[f], 8);
-            cnt[l] = 0;
+            if (lane == 0) { atomicOr(&p.status[f], 8); cnt[l] = 0; }
             continue;
         }
-        // pilot = flip(demod - demod_05): pilot[i] = x[b-1-i]
-        auto pil = [&](long long i) -> double {
+        // coalesced staging; the two ire0 offsets cancel, the subtraction is done in float64 like the reference
+        for (int i = lane; i < len; i += 32) {
             long long s = base + b - 1 - i;
-            return ((double)p.demod[s]) - ((double)p.d05[s]);       // the two ire0 offsets cancel
-        };
-        double adjfreq = fq;
-        if (l > 1) adjfreq /= (lin[l] - lin[l - 1]) / p.linelen;
-        int i = 0;
-        while (i < len) {
-            double v = pil(i);
-            if (v >= -300000 && v <= -100000) {
-                double zc;
-                if (calczc(pil, len, i, 0.0, 10, &zc)) {
-                    double zcp = zc / (adjfreq / 3.75);
-                    if (n < PILOT_MAXOFF) my[n] = zcp - floor(zcp);
-                    ++n;
-                    i = (int)(zc + 1);
+            s_pil[warp][i] = (float)(((double)p.demod[s]) - ((double)p.d05[s]));
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int n = 0;
+            auto pil = [&](long long i) -> double {
+                long long s = base + b - 1 - i;
+                return ((double)p.demod[s]) - ((double)p.d05[s]);
+            };
+            double adjfreq = fq;
+            if (l > 1) adjfreq /= (lin[l] - lin[l - 1]) / p.linelen;
+            int i = 0;
+            while (i < len) {
+                // cheap float32 pre-test from the staged copy (the band is 200 kHz wide, float32 rounds at 0.02 Hz);
+                // samples near the band edges are re-tested in float64
+                float vf = s_pil[warp][i];
+                bool maybe = vf >= -300001.f && vf <= -99999.f;
+                if (maybe) {
+                    double v = pil(i);
+                    if (v >= -300000 && v <= -100000) {
+                        double zc;
+                        if (calczc(pil, len, i, 0.0, 10, &zc)) {
+                            double zcp = zc / (adjfreq / 3.75);
+                            if (n < PILOT_MAXOFF) my[n] = zcp - floor(zcp);
+                            ++n;
+                            i = (int)(zc + 1);
+                        }
+                    }
                 }
+                ++i;
             }
-            ++i;
+            if (n > PILOT_MAXOFF) { atomicOr(&p.status[f], 8); n = PILOT_MAXOFF; }
+            // "if len(offsets) >= 3": the dict has l+1 entries at this point
+            if (l + 1 >= 3) {
+                int m = n >= 2 ? n - 2 : 0;
+                for (int k = 0; k < m; ++k) my[k] = my[k + 1];
+                n = m;
+            } else {
+                n = 0;
+            }
+            cnt[l] = n;
         }
-        if (n > PILOT_MAXOFF) { atomicOr(&p.status[f], 8); n = PILOT_MAXOFF; }
-        // "if len(offsets) >= 3": the dict has l+1 entries at this point
-        if (l + 1 >= 3) {
-            // offsets[l] = offsets[l][1:-1]
-            int m = n >= 2 ? n - 2 : 0;
-            for (int k = 0; k < m; ++k) my[k] = my[k + 1];
-            n = m;
-        } else {
-            n = 0;
-        }
-        cnt[l] = n;
+        __syncwarp();
     }
     __syncthreads();
     // median of all offsets (np.median(alloffsets)): exact order statistics by multi-level histogram
@@ -806,7 +821,7 @@ extern "C" int ldd_refine_pilot(ldd_handle* h, const float* demod_dev, const flo
     p.demod = demod_dev; p.d05 = d05_dev; p.n = n; p.freq = h->cfg.freq_hz / 1e6; p.linelen = h->cfg.linelen;
     p.base = base_dev; p.linecount = linecount_dev; p.ll_stride = ll_stride; p.linelocs_in = linelocs_in_dev;
     p.linelocs_out = linelocs_out_dev; p.status = status_dev;
-    LDD_LAUNCH(refine_pilot_kernel, dim3(nfields), dim3(128), 0, st, p, offs, cnt);
+    LDD_LAUNCH(refine_pilot_kernel, dim3(nfields), dim3(32 * PILOT_WARPS), 0, st, p, offs, cnt);
     return launch_status(h, "refine_pilot_kernel");
 }
 

@@ -19,7 +19,7 @@ constexpr int TBC_H = TBC_K + 1;          // halo samples needed on each side
 constexpr int TBC_MAXD = 4032;            // longest input line span supported
 constexpr int TBC_THREADS = 256;
 constexpr int TBC_NTAPS = 2 * TBC_H + 1;  // taps of the y -> P filter
-constexpr int TBC_OPT = 8;                // outputs per thread and sweep of the register-tiled FIR
+constexpr int TBC_OPT = 9;                // outputs per thread and sweep of the register-tiled FIR (2271/9 < 256 threads)
 
 // w[m] = 6 (g[m-1] - 2 g[m] + g[m+1]), g[k] = r^|k| / (2 sqrt 3) truncated to |k| <= K: set once per
 // process.  Constant memory lets the fully unrolled FIR take its taps as immediate constant-bank operands.

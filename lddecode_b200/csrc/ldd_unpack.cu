@@ -117,18 +117,19 @@ __global__ void __launch_bounds__(256) unpack_r30_vec_kernel(const uint4* __rest
     }
 }
 
-// .lds: 80 bytes (five 16-byte loads) -> 64 samples.  first % 64 == 0 at the caller.
+// .lds: 20 bytes (five 4-byte loads) -> 16 samples -> two 16-byte (uint16) or four 16-byte (float32)
+// stores.  first % 16 == 0 at the caller, so every thread's 20 bytes start on a 4-byte boundary.
 template <class OUT>
-__global__ void __launch_bounds__(128) unpack_lds_vec_kernel(const uint4* __restrict__ src, size_t ngroups, OUT* __restrict__ out) {
+__global__ void __launch_bounds__(256) unpack_lds_vec_kernel(const unsigned* __restrict__ src, size_t ngroups, OUT* __restrict__ out) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ngroups) return;
-    unsigned wd[20];
+    unsigned wd[5];
     LDD_UNROLL
-    for (int i = 0; i < 5; ++i) { uint4 q = src[t * 5 + i]; wd[4 * i] = q.x; wd[4 * i + 1] = q.y; wd[4 * i + 2] = q.z; wd[4 * i + 3] = q.w; }
+    for (int i = 0; i < 5; ++i) wd[i] = src[t * 5 + i];
     auto byte_at = [&](int b) -> unsigned { return (wd[b >> 2] >> (8 * (b & 3))) & 0xffu; };
-    unsigned v[64];
+    unsigned v[16];
     LDD_UNROLL
-    for (int g = 0; g < 16; ++g) {
+    for (int g = 0; g < 4; ++g) {
         unsigned b0 = byte_at(5 * g), b1 = byte_at(5 * g + 1), b2 = byte_at(5 * g + 2), b3 = byte_at(5 * g + 3), b4 = byte_at(5 * g + 4);
         v[4 * g] = (b0 << 2) | (b1 >> 6);
         v[4 * g + 1] = ((b1 & 0x3fu) << 4) | (b2 >> 4);
@@ -136,13 +137,13 @@ __global__ void __launch_bounds__(128) unpack_lds_vec_kernel(const uint4* __rest
         v[4 * g + 3] = ((b3 & 0x03u) << 8) | b4;
     }
     if (sizeof(OUT) == 4) {
-        float4* o = (float4*)out + t * 16;
+        float4* o = (float4*)out + t * 4;
         LDD_UNROLL
-        for (int k = 0; k < 16; ++k) o[k] = make_float4((float)v[4 * k], (float)v[4 * k + 1], (float)v[4 * k + 2], (float)v[4 * k + 3]);
+        for (int k = 0; k < 4; ++k) o[k] = make_float4((float)v[4 * k], (float)v[4 * k + 1], (float)v[4 * k + 2], (float)v[4 * k + 3]);
     } else {
-        uint4* o = (uint4*)out + t * 8;
+        uint4* o = (uint4*)out + t * 2;
         LDD_UNROLL
-        for (int k = 0; k < 8; ++k)
+        for (int k = 0; k < 2; ++k)
             o[k] = make_uint4(v[8 * k] | (v[8 * k + 1] << 16), v[8 * k + 2] | (v[8 * k + 3] << 16),
                               v[8 * k + 4] | (v[8 * k + 5] << 16), v[8 * k + 6] | (v[8 * k + 7] << 16));
     }
@@ -159,12 +160,12 @@ static size_t unpack_bulk(const void* src, int fmt, size_t first, size_t n, OUT*
         LDD_LAUNCH(unpack_r30_vec_kernel<OUT>, dim3((unsigned)((nq + 255) / 256)), dim3(256), 0, st, w, nq, out);
         return nq * 12;
     }
-    if (fmt == LDD_FMT_LDS40 && first % 64 == 0) {
-        size_t ng = n / 64;
+    if (fmt == LDD_FMT_LDS40 && first % 16 == 0) {
+        size_t ng = n / 16;
         if (!ng) return 0;
-        const uint4* w = (const uint4*)((const char*)src + first / 4 * 5);
-        LDD_LAUNCH(unpack_lds_vec_kernel<OUT>, dim3((unsigned)((ng + 127) / 128)), dim3(128), 0, st, w, ng, out);
-        return ng * 64;
+        const unsigned* w = (const unsigned*)((const char*)src + first / 4 * 5);
+        LDD_LAUNCH(unpack_lds_vec_kernel<OUT>, dim3((unsigned)((ng + 255) / 256)), dim3(256), 0, st, w, ng, out);
+        return ng * 16;
     }
     return 0;
 }

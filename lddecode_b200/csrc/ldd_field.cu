@@ -378,9 +378,9 @@ struct PilotParams {
 };
 
 constexpr int PILOT_MAXOFF = 48;     // zero crossings kept per line (4.7 us of a 3.75 MHz pilot: ~17)
-constexpr int PILOT_MAXLEN = 256;    // samples in 4.7 us (<= 54 MSPS)
+constexpr int PILOT_MAXLEN = 192;    // samples in 4.7 us (<= 40 MSPS)
 
-constexpr int PILOT_WARPS = 16;
+constexpr int PILOT_WARPS = 32;
 
 __global__ void __launch_bounds__(32 * PILOT_WARPS) refine_pilot_kernel(const PilotParams p, double* ws_offsets /*[nfields][ll_stride][MAXOFF]*/,
                                                                        int* ws_count /*[nfields][ll_stride]*/) {
@@ -479,11 +479,27 @@ __global__ void __launch_bounds__(32 * PILOT_WARPS) refine_pilot_kernel(const Pi
                 }
             }
             __syncthreads();
-            if (tid == 0) {
-                int cum = 0, b = 0;
-                for (; b < 4096; ++b) { if (cum + s_hist[b] > kk) break; cum += s_hist[b]; }
-                s_bin = b > 4095 ? 4095 : b;
-                s_before = cum;
+            if (tid < 32) {
+                // warp 0: each lane sums 128 consecutive bins, exclusive prefix over lanes, then the lane
+                // whose span holds rank kk walks its bins
+                int part = 0;
+                for (int b = tid * 128; b < tid * 128 + 128; ++b) part += s_hist[b];
+                int incl = part;
+                for (int d = 1; d < 32; d <<= 1) {
+                    int up = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (tid >= d) incl += up;
+                }
+                int excl = incl - part;
+                bool mine = kk >= excl && kk < incl;
+                unsigned who = __ballot_sync(0xffffffffu, mine);
+                if (who == 0) {
+                    if (tid == 0) { s_bin = 4095; s_before = incl; }       // rank beyond the range's population
+                } else if (mine) {
+                    int cum = excl, b = tid * 128;
+                    for (; b < tid * 128 + 127; ++b) { if (cum + s_hist[b] > kk) break; cum += s_hist[b]; }
+                    s_bin = b;
+                    s_before = cum;
+                }
             }
             __syncthreads();
             const int bin = s_bin, inbin = s_hist[bin];

@@ -129,7 +129,7 @@ int ldd_create(const ldd_config* cfg, ldd_handle** out) {
     if (per_sm < 1) per_sm = 1;
     env = getenv("LDD_THREADS");
     h->threads = env ? atoi(env) : 512;
-    if (f64) { if (h->threads != 256 && h->threads != 512 && h->threads != 1024) h->threads = 256; }
+    if (f64) { if (h->threads != 256 && h->threads != 512 && h->threads != 1024 && h->threads != 2256) h->threads = 512; }
     else { if (h->threads != 512 && h->threads != 1024) h->threads = 512; }
     env = getenv("LDD_RADIX_MAX");
     h->radix_max = env ? atoi(env) : 16;
@@ -141,6 +141,13 @@ int ldd_create(const ldd_config* cfg, ldd_handle** out) {
     h->smem_bytes = smem_lane ? per_cta_padded : 0;
     h->grid = smem_lane ? h->sm_count : h->sm_count * per_sm;
     h->scratch_per_cta = smem_lane ? 0 : per_cta;
+    // float64 lane(s): a padded shared-memory buffer as the ping-pong partner of the length-M transforms when it fits
+    {
+        size_t want = (size_t)pspan<true>(M) * sizeof(Cx<double>);
+        bool uses_f64 = f64 || mixed;
+        if (uses_f64 && want + 2048 <= h->smem_optin && !getenv("LDD_NO_SMEM_PARTNER") && (f64 ? h->threads == 512 : true))
+            h->sp_bytes = want;
+    }
     // v2 kernel: M == 16 * 512 threads, radix plan (16,16,16,2); audio transform >= 256 points
     env = getenv("LDD_KERNEL");
     // (measured on B200: the v2 kernel is slower than v1 -- 7.1 vs 4.2 ms float64, 2.8 vs 2.3 ms float32 for
@@ -373,7 +380,7 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
     }
     int rc;
     if (h->v2) rc = launch_demod_v2(p, grid, lane == 0, st, h->smem_bytes);
-    else if (lane == 0) rc = launch_demod_f64(p, grid, h->threads, st);
+    else if (lane == 0) rc = launch_demod_f64(p, grid, h->threads, st, h->sp_bytes);
     else rc = launch_demod_f32(p, grid, h->threads, st, h->smem_bytes);
     if (mixed && rc == LDD_OK) {
         // second pass: float64 over the flagged blocks only; the list is read on the device, so there
@@ -386,7 +393,7 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
         q.flag_list = nullptr; q.flag_count = nullptr;
         q.block_count = h->d_flags; q.block_list = h->d_flags + 1;
         int g64 = (int)(nblocks < h->sm_count ? nblocks : h->sm_count);
-        rc = launch_demod_f64(q, g64, 512, st);
+        rc = launch_demod_f64(q, g64, 512, st, h->sp_bytes);
     }
 #ifndef LDD_EMU
     if (h->l2_window) {

@@ -102,8 +102,11 @@ __device__ inline void tangle(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __restrict_
     }
 }
 
-template <class T, int NT, bool PAD>
-__global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
+// SP: the block arrays live in the global scratch and a padded shared-memory buffer is the ping-pong
+// partner of every length-M transform (every second Stockham pass stays on chip: the float64 lane is
+// bound by L2 traffic, ~7 TB/s chip-wide at 9 Gsamples/s).
+template <class T, int NT, bool PAD, int MINB = 1, bool SP = false>
+__global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int N = p.N, M = p.M;
     const Cx<T>* WM = (const Cx<T>*)p.WM;
@@ -111,12 +114,23 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
     const Cx<T>* Hv = (const Cx<T>*)p.Hv;
 
     Cx<T>* b0;
+    Cx<T>* sp = nullptr;
     if (p.scratch) {
         b0 = (Cx<T>*)((char*)p.scratch + (size_t)blockIdx.x * p.scratch_per_cta);
+        if (SP) {
+            LDD_DYN_SMEM(smem);
+            sp = (Cx<T>*)smem;
+        }
     } else {
         LDD_DYN_SMEM(smem);
         b0 = (Cx<T>*)smem;
     }
+    const bool sp_ok = SP && (p.plan_m.npass & 1) == 0;
+    // length-M transform of `a`; `other` is a free array usable as the partner when shared memory is not
+    auto FFTM = [&](Cx<T>* a, Cx<T>* other) -> Cx<T>* {
+        if (SP && sp_ok) return fft_run<T, PAD, true>(a, sp, p.plan_m, WM, 1, tid, nthr);
+        return fft_run<T, PAD>(a, other, p.plan_m, WM, 1, tid, nthr);
+    };
     Cx<T>* b1 = b0 + pspan<PAD>(M);
     Cx<T>* b2 = b1 + pspan<PAD>(M);
 #define IX(i) pidx<PAD>(i)
@@ -151,7 +165,7 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
         __syncthreads();
 
         // B/C. X = rfft(x)
-        Cx<T>* X = fft_run<T, PAD>(b0, b1, p.plan_m, WM, 1, tid, nthr);
+        Cx<T>* X = FFTM(b0, b1);
         Cx<T>* f1 = (X == b0) ? b1 : b0;      // free
         Cx<T>* f2 = b2;                        // free
         untangle<T, PAD>(X, M, WN, tid, nthr);
@@ -229,9 +243,9 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
         __syncthreads();
 
         // F. h[2n] = conj(ru[n]), h[2n+1] = conj(rv[n]) (up to a positive scale)
-        Cx<T>* ru = fft_run<T, PAD>(U, X, p.plan_m, WM, 1, tid, nthr);
+        Cx<T>* ru = FFTM(U, X);
         Cx<T>* fu = (ru == U) ? X : U;
-        Cx<T>* rv = fft_run<T, PAD>(V, fu, p.plan_m, WM, 1, tid, nthr);
+        Cx<T>* rv = FFTM(V, fu);
         Cx<T>* fv = (rv == V) ? fu : V;
 
         // G. FM discriminator (lddutils.py:320-334): angle, neighbour difference, fold to [0, 2pi),
@@ -259,7 +273,7 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
         __syncthreads();
 
         // H. D = rfft(demod - ire0)
-        Cx<T>* D = fft_run<T, PAD>(rv, ru, p.plan_m, WM, 1, tid, nthr);
+        Cx<T>* D = FFTM(rv, ru);
         Cx<T>* g1 = (D == rv) ? ru : rv;
         Cx<T>* g2 = fv;
         untangle<T, PAD>(D, M, WN, tid, nthr);
@@ -274,7 +288,7 @@ __global__ void __launch_bounds__(NT, 1) demod_kernel(const DemodParams p) {
             if (m >= p.nfilt && m != 1) continue;
             tangle<T, PAD>(D, g1, (const Cx<T>*)p.F[m], M, WN, tid, nthr);
             __syncthreads();
-            Cx<T>* r = fft_run<T, PAD>(g1, g2, p.plan_m, WM, 1, tid, nthr);
+            Cx<T>* r = FFTM(g1, g2);
             float* out = (float*)p.plane[pl_of[m]];
             const T addc = (T)p.addc[m];
             // kept samples 2n, 2n+1 -> out[o + 2n - keep0]; keep0, o and copylen parity: handle singly
@@ -618,9 +632,9 @@ static int check_launch(const char* what) {
     return LDD_OK;
 }
 
-template <class T, int NT, bool PAD>
+template <class T, int NT, bool PAD, int MINB = 1, bool SP = false>
 static int launch_variant(const DemodParams& p, int grid, cudaStream_t st, size_t smem_bytes) {
-    void (*kern)(const DemodParams) = demod_kernel<T, NT, PAD>;
+    void (*kern)(const DemodParams) = demod_kernel<T, NT, PAD, MINB, SP>;
     if (smem_bytes) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     LDD_LAUNCH(kern, dim3(grid), dim3(NT), smem_bytes, st, p);
     return check_launch("demod_kernel");
@@ -639,10 +653,12 @@ int launch_demod_v2(const DemodParams& p, int grid, bool f64, cudaStream_t st, s
     return launch_v2<float, 512, true>(p, grid, st, smem_bytes);
 }
 
-int launch_demod_f64(const DemodParams& p, int grid, int threads, cudaStream_t st) {
+int launch_demod_f64(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t sp_bytes) {
+    if (sp_bytes && threads == 512) return launch_variant<double, 512, false, 1, true>(p, grid, st, sp_bytes);
     switch (threads) {
         case 1024: return launch_variant<double, 1024, false>(p, grid, st, 0);
         case 512: return launch_variant<double, 512, false>(p, grid, st, 0);
+        case 2256: return launch_variant<double, 256, false, 2>(p, grid, st, 0);      // 2 CTAs of 256 threads per SM
         default: return launch_variant<double, 256, false>(p, grid, st, 0);
     }
 }

@@ -95,14 +95,14 @@ template <bool PAD> LDD_HD inline int pspan(int n) { return PAD ? n + (n >> 4) :
 // ---- one Stockham pass -------------------------------------------------------------------------
 // src, dst: length-M sequences.  Ns: product of the radices of the passes already done.
 // W: table of e^{-2 pi i k / Mtab}, k in [0, Mtab); wstride = Mtab / M.
-template <class T, int R, bool PAD>
+template <class T, int R, bool PIN, bool POUT>
 __device__ inline void fft_pass(const Cx<T>* src, Cx<T>* dst, int M, int Ns,
                                 const Cx<T>* __restrict__ W, int wstride, int tid, int nthr) {
     const int nb = M / R;
     for (int j = tid; j < nb; j += nthr) {
         Cx<T> v[R];
         LDD_UNROLL
-        for (int r = 0; r < R; ++r) v[r] = src[pidx<PAD>(j + r * nb)];
+        for (int r = 0; r < R; ++r) v[r] = src[pidx<PIN>(j + r * nb)];
         const int k = j & (Ns - 1);
         if (Ns > 1) {
             // w^r by repeated squaring / short products from one table lookup (<= 4 products deep)
@@ -116,7 +116,18 @@ __device__ inline void fft_pass(const Cx<T>* src, Cx<T>* dst, int M, int Ns,
         Dft<T, R>::run(v);
         const int j0 = (j - k) * R + k;
         LDD_UNROLL
-        for (int r = 0; r < R; ++r) dst[pidx<PAD>(j0 + r * Ns)] = v[r];
+        for (int r = 0; r < R; ++r) dst[pidx<POUT>(j0 + r * Ns)] = v[r];
+    }
+}
+
+template <class T, bool PIN, bool POUT>
+__device__ inline void fft_pass_any(int R, const Cx<T>* src, Cx<T>* dst, int M, int Ns, const Cx<T>* __restrict__ W,
+                                    int wstride, int tid, int nthr) {
+    switch (R) {
+        case 16: fft_pass<T, 16, PIN, POUT>(src, dst, M, Ns, W, wstride, tid, nthr); break;
+        case 8: fft_pass<T, 8, PIN, POUT>(src, dst, M, Ns, W, wstride, tid, nthr); break;
+        case 4: fft_pass<T, 4, PIN, POUT>(src, dst, M, Ns, W, wstride, tid, nthr); break;
+        default: fft_pass<T, 2, PIN, POUT>(src, dst, M, Ns, W, wstride, tid, nthr); break;
     }
 }
 
@@ -136,23 +147,20 @@ inline FftPlan make_plan(int n, int rmax = 16) {
     return p;
 }
 
-// Runs all passes; the result is in the returned pointer (a or b).  Ends with a barrier.
-template <class T, bool PAD>
+// Runs all passes, ping-ponging between a (padding PA) and b (padding PB); the result is in the
+// returned pointer (a after an even number of passes).  Ends with a barrier.  With a in the global
+// scratch and b in shared memory every second pass stays on chip.
+template <class T, bool PA, bool PB = PA>
 __device__ inline Cx<T>* fft_run(Cx<T>* a, Cx<T>* b, const FftPlan& plan, const Cx<T>* __restrict__ W,
                                  int wstride, int tid, int nthr) {
     int Ns = 1;
     for (int p = 0; p < plan.npass; ++p) {
-        switch (plan.radix[p]) {
-            case 16: fft_pass<T, 16, PAD>(a, b, plan.n, Ns, W, wstride, tid, nthr); break;
-            case 8: fft_pass<T, 8, PAD>(a, b, plan.n, Ns, W, wstride, tid, nthr); break;
-            case 4: fft_pass<T, 4, PAD>(a, b, plan.n, Ns, W, wstride, tid, nthr); break;
-            default: fft_pass<T, 2, PAD>(a, b, plan.n, Ns, W, wstride, tid, nthr); break;
-        }
+        if ((p & 1) == 0) fft_pass_any<T, PA, PB>(plan.radix[p], a, b, plan.n, Ns, W, wstride, tid, nthr);
+        else fft_pass_any<T, PB, PA>(plan.radix[p], b, a, plan.n, Ns, W, wstride, tid, nthr);
         Ns *= plan.radix[p];
-        Cx<T>* t = a; a = b; b = t;
         __syncthreads();
     }
-    return a;
+    return (plan.npass & 1) ? b : a;
 }
 
 // ---- in-place variant: 16 elements per thread --------------------------------------------------

@@ -64,7 +64,7 @@ struct DemodParams {
 // cudaGetLastError() after a launch -> LDD_OK / LDD_ECUDA with the CUDA error text in h->err
 inline int launch_status(ldd_handle* h, const char* what);
 
-int launch_demod_f64(const DemodParams& p, int grid, int threads, cudaStream_t st);
+int launch_demod_f64(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t sp_bytes);
 int launch_demod_f32(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t smem_bytes);
 int launch_demod_v2(const DemodParams& p, int grid, bool f64, cudaStream_t st, size_t smem_bytes);
 
@@ -94,6 +94,7 @@ struct ldd_handle {
     int radix_max;    // largest Stockham radix used
     size_t smem_bytes;
     bool v2;          // in-place 16-elements-per-thread kernel (N == 16384)
+    size_t sp_bytes = 0;    // float64 lane: bytes of the shared-memory ping-pong partner (0: not used)
     void* scratch64 = nullptr;       // float64 scratch of the mixed lane's second pass
     size_t scratch64_per_cta = 0;
     int* d_flags = nullptr;          // [0] = count, [1..] = block indices

@@ -48,7 +48,7 @@ def main():
     cap = np.tile(one, n // len(one))
     cap_dev = torch.from_numpy(cap).cuda()
     res = []
-    variants = [("f64", 512, 16, 1, 1), ("f32", 512, 16, 1, 1), ("mixed", 512, 16, 1, 1)]
+    variants = [("f64", 512, 16, 1, 1), ("mixed", 512, 16, 1, 1), ("f32", 512, 16, 1, 1)]
     for N in (16384,):
         for prec, thr, rad, ctas, kern in variants:
             try:

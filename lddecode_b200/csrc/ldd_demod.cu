@@ -243,10 +243,20 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         __syncthreads();
 
         // F. h[2n] = conj(ru[n]), h[2n+1] = conj(rv[n]) (up to a positive scale)
-        Cx<T>* ru = FFTM(U, X);
-        Cx<T>* fu = (ru == U) ? X : U;
-        Cx<T>* rv = FFTM(V, fu);
-        Cx<T>* fv = (rv == V) ? fu : V;
+        Cx<T>* ru;
+        Cx<T>* fu;
+        Cx<T>* rv;
+        Cx<T>* fv;
+        if (SP && sp_ok) {
+            // the two transforms are independent: run them pass by pass with one barrier per pass pair
+            fft_run_pair<T, PAD, true, PAD>(U, sp, V, X, p.plan_m, WM, 1, tid, nthr);
+            ru = U; rv = V; fu = X; fv = X;
+        } else {
+            ru = FFTM(U, X);
+            fu = (ru == U) ? X : U;
+            rv = FFTM(V, fu);
+            fv = (rv == V) ? fu : V;
+        }
 
         // G. FM discriminator (lddutils.py:320-334): angle, neighbour difference, fold to [0, 2pi),
         //    scale to Hz; minus ire0; packed for the next real transform.

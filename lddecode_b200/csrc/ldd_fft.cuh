@@ -163,6 +163,27 @@ __device__ inline Cx<T>* fft_run(Cx<T>* a, Cx<T>* b, const FftPlan& plan, const 
     return (plan.npass & 1) ? b : a;
 }
 
+// Two independent transforms with the same plan, pass by pass, ONE barrier per pass pair: a warp that
+// finishes its butterfly of the first transform starts loading for the second while slower warps
+// still compute, so the L2 latency of one overlaps the arithmetic of the other.  (a1 <-> b1 with
+// paddings PA/PB1, a2 <-> b2 with PA/PB2.)  Results as fft_run: in a* after an even number of passes.
+template <class T, bool PA, bool PB1, bool PB2>
+__device__ inline void fft_run_pair(Cx<T>* a1, Cx<T>* b1, Cx<T>* a2, Cx<T>* b2, const FftPlan& plan,
+                                    const Cx<T>* __restrict__ W, int wstride, int tid, int nthr) {
+    int Ns = 1;
+    for (int p = 0; p < plan.npass; ++p) {
+        if ((p & 1) == 0) {
+            fft_pass_any<T, PA, PB1>(plan.radix[p], a1, b1, plan.n, Ns, W, wstride, tid, nthr);
+            fft_pass_any<T, PA, PB2>(plan.radix[p], a2, b2, plan.n, Ns, W, wstride, tid, nthr);
+        } else {
+            fft_pass_any<T, PB1, PA>(plan.radix[p], b1, a1, plan.n, Ns, W, wstride, tid, nthr);
+            fft_pass_any<T, PB2, PA>(plan.radix[p], b2, a2, plan.n, Ns, W, wstride, tid, nthr);
+        }
+        Ns *= plan.radix[p];
+        __syncthreads();
+    }
+}
+
 // ---- in-place variant: 16 elements per thread --------------------------------------------------
 // For n == 16 * (number of active threads) every pass can run in place: each active thread loads
 // the 16 elements of its 16/R butterflies into registers, the CTA synchronises, then it stores its

@@ -9,12 +9,15 @@ Filter tables are built on the host with scipy exactly as the reference does and
 all per-sample work runs in the CUDA kernels.  PyTorch is used for device buffers only.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import scipy.signal as sps
 
 from . import _lib
 from ._backend import CudaBackend
+
+DEFAULT_PRECISION = 'f64'
 
 # module-global loader, as in the reference (lddecode_core.py:387, assigned at lddecode.py:53-58):
 # loader(infile, sample, readlen) -> array | None
@@ -109,7 +112,7 @@ class DeviceDemod:
 
 class RFDecode:
     def __init__(self, inputfreq=40, system='NTSC', blocklen_=16384, decode_analog_audio=True,
-                 have_analog_audio=True, device=None, precision='f64', _backend=None):
+                 have_analog_audio=True, device=None, precision=None, _backend=None):
         self.blocklen = blocklen_
         self.blockcut = 1024
         self.system = system
@@ -125,7 +128,9 @@ class RFDecode:
             raise ValueError("system must be 'NTSC' or 'PAL'")
         self.linelen = int(np.round(self.freq_hz / (1000000.0 / self.SysParams['line_period'])))
         self.decode_analog_audio = decode_analog_audio
-        self.precision = precision
+        # precision lanes: 'f64' exact, 'f32' fast, 'mixed' = f32 + f64 re-run of the
+        # blocks whose sync decisions float32 could get wrong (sync plane bit-identical to 'f64')
+        self.precision = precision or os.environ.get("LDD_PRECISION", DEFAULT_PRECISION)
         self._be = _backend if _backend is not None else CudaBackend(device)
         self._h = None
         self._mtf_uploaded = None

@@ -148,25 +148,6 @@ int ldd_create(const ldd_config* cfg, ldd_handle** out) {
         if (uses_f64 && want + 2048 <= h->smem_optin && !getenv("LDD_NO_SMEM_PARTNER") && (f64 ? h->threads == 512 : true))
             h->sp_bytes = want;
     }
-    // v2 kernel: M == 16 * 512 threads, radix plan (16,16,16,2); audio transform >= 256 points
-    env = getenv("LDD_KERNEL");
-    // (measured on B200: the v2 kernel is slower than v1 -- 7.1 vs 4.2 ms float64, 2.8 vs 2.3 ms float32 for
-    //  36 M samples -- because holding 16 elements across a barrier spills and doubles the barriers; it stays
-    //  selectable with LDD_KERNEL=2 for experiments only)
-    h->v2 = M == 16 * 512 && h->radix_max == 16 && (env && atoi(env) == 2) && (h->A == 0 || h->A >= 256);
-    if (h->v2) {
-        h->threads = 512;
-        if (f64) {
-            h->smem_bytes = (size_t)pspan<true>(M) * sizeof(Cx<double>);      // the shared work buffer
-            h->grid = h->sm_count;
-            h->scratch_per_cta = per_cta;
-        } else {
-            h->smem_bytes = per_cta_padded;
-            h->grid = h->sm_count;
-            h->scratch_per_cta = 0;
-        }
-        if (h->smem_bytes + 1024 > h->smem_optin) h->v2 = false;
-    }
     // audio phase 2 runs out of the same scratch: two length-N complex128 buffers per CTA
     size_t per_cta_a2 = (size_t)2 * N * sizeof(Cx<double>);
     size_t need = (size_t)h->grid * (h->scratch_per_cta > per_cta_a2 ? h->scratch_per_cta : per_cta_a2);
@@ -379,8 +360,7 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
         p.flag_margin = h->flag_margin;
     }
     int rc;
-    if (h->v2) rc = launch_demod_v2(p, grid, lane == 0, st, h->smem_bytes);
-    else if (lane == 0) rc = launch_demod_f64(p, grid, h->threads, st, h->sp_bytes);
+    if (lane == 0) rc = launch_demod_f64(p, grid, h->threads, st, h->sp_bytes);
     else rc = launch_demod_f32(p, grid, h->threads, st, h->smem_bytes);
     if (mixed && rc == LDD_OK) {
         // second pass: float64 over the flagged blocks only; the list is read on the device, so there

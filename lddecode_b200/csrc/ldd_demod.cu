@@ -148,24 +148,41 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         if (copylen < 0) copylen = 0;
         const int keep0 = p.blockcut, keep1 = p.blockcut + (int)copylen;
 
-        // A. samples -> z[n] = x[2n] + j x[2n+1]
-        if (p.fmt == LDD_FMT_U8 && ((in0 & 1) == 0) && ((((uintptr_t)p.rf) & 1) == 0)) {
+        // A+B. X = rfft(x): the samples are read and converted inside the first Stockham pass
+        //      (z[n] = x[2n] + j x[2n+1]); no separate pass writes z.
+        Cx<T>* X;
+        {
+            const bool fast8 = p.fmt == LDD_FMT_U8 && ((in0 & 1) == 0) && ((((uintptr_t)p.rf) & 1) == 0);
             const unsigned short* r16 = (const unsigned short*)((const unsigned char*)p.rf + in0);
-            for (int n = tid; n < M; n += nthr) {
-                unsigned v = r16[n];
-                b0[IX(n)] = mk<T>((T)(int)(v & 0xffu), (T)(int)(v >> 8));
-            }
-        } else {
-            for (int n = tid; n < M; n += nthr) {
+            auto ld_raw = [&](int n) -> Cx<T> {
+                if (fast8) {
+                    unsigned v = r16[n];
+                    return mk<T>((T)(int)(v & 0xffu), (T)(int)(v >> 8));
+                }
                 int s0 = fetch_sample(p.rf, p.fmt, in0 + 2 * n);
                 int s1 = fetch_sample(p.rf, p.fmt, in0 + 2 * n + 1);
-                b0[IX(n)] = mk<T>((T)s0, (T)s1);
+                return mk<T>((T)s0, (T)s1);
+            };
+            if (p.plan_m.npass >= 2) {
+                // first pass: raw -> partner; last pass lands in b0 (even pass count) or in the partner (odd)
+                Cx<T>* partner = (SP && sp_ok) ? sp : b1;
+                const bool even = (p.plan_m.npass & 1) == 0;
+                if (SP && sp_ok) {
+                    fft_run_fn<T, PAD, true>(ld_raw, b0, partner, ArrStore<T, PAD>{b0}, p.plan_m, WM, 1, tid, nthr);
+                    X = b0;
+                } else if (even) {
+                    fft_run_fn<T, PAD, PAD>(ld_raw, b0, partner, ArrStore<T, PAD>{b0}, p.plan_m, WM, 1, tid, nthr);
+                    X = b0;
+                } else {
+                    fft_run_fn<T, PAD, PAD>(ld_raw, b0, partner, ArrStore<T, PAD>{b1}, p.plan_m, WM, 1, tid, nthr);
+                    X = b1;
+                }
+            } else {
+                for (int n = tid; n < M; n += nthr) b0[IX(n)] = ld_raw(n);
+                __syncthreads();
+                X = FFTM(b0, b1);
             }
         }
-        __syncthreads();
-
-        // B/C. X = rfft(x)
-        Cx<T>* X = FFTM(b0, b1);
         Cx<T>* f1 = (X == b0) ? b1 : b0;      // free
         Cx<T>* f2 = b2;                        // free
         untangle<T, PAD>(X, M, WN, tid, nthr);
@@ -243,48 +260,42 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         __syncthreads();
 
         // F. h[2n] = conj(ru[n]), h[2n+1] = conj(rv[n]) (up to a positive scale)
-        Cx<T>* ru;
-        Cx<T>* fu;
-        Cx<T>* rv;
-        Cx<T>* fv;
-        if (SP && sp_ok) {
-            // the two transforms are independent: run them pass by pass with one barrier per pass pair
-            fft_run_pair<T, PAD, true, PAD>(U, sp, V, X, p.plan_m, WM, 1, tid, nthr);
-            ru = U; rv = V; fu = X; fv = X;
-        } else {
-            ru = FFTM(U, X);
-            fu = (ru == U) ? X : U;
-            rv = FFTM(V, fu);
-            fv = (rv == V) ? fu : V;
-        }
+        Cx<T>* ru = FFTM(U, X);
+        Cx<T>* fu = (ru == U) ? X : U;
+        Cx<T>* rv = FFTM(V, fu);
+        Cx<T>* fv = (rv == V) ? fu : V;
 
         // G. FM discriminator (lddutils.py:320-334): angle, neighbour difference, fold to [0, 2pi),
-        //    scale to Hz; minus ire0; packed for the next real transform.
-        for (int n = tid; n < M; n += nthr) {
-            Cx<T> a = ru[IX(n)], b = rv[IX(n)];
-            ru[IX(n)] = mk<T>(Math<T>::atan2(-a.y, a.x), Math<T>::atan2(-b.y, b.x));
-        }
-        __syncthreads();
+        //    scale to Hz; minus ire0; packed for the next real transform.  One pass: the angle of the
+        //    odd sample to the left comes from the lane below by warp shuffle (lane 0 recomputes it).
+        //    The result overwrites ru; rv stays intact because the warp above still reads it.
         {
             const T twopi = (T)6.283185307179586476925286766559;
             const T hz = (T)p.hz_per_rad, ire0 = (T)p.ire0;
+            const int lane = tid & 31;
             for (int n = tid; n < M; n += nthr) {
-                Cx<T> a = ru[IX(n)];
+                Cx<T> a = ru[IX(n)], b = rv[IX(n)];
+                T ae = Math<T>::atan2(-a.y, a.x), ao = Math<T>::atan2(-b.y, b.x);
+                T prev = __shfl_up_sync(0xffffffffu, ao, 1);
+                if (lane == 0 && n > 0) {
+                    Cx<T> q = rv[IX(n - 1)];
+                    prev = Math<T>::atan2(-q.y, q.x);
+                }
                 T d0 = (T)0;
                 if (n > 0) {
-                    d0 = a.x - ru[IX(n - 1)].y;
+                    d0 = ae - prev;
                     if (d0 < 0) d0 += twopi;
                 }
-                T d1 = a.y - a.x;
+                T d1 = ao - ae;
                 if (d1 < 0) d1 += twopi;
-                rv[IX(n)] = mk<T>(d0 * hz - ire0, d1 * hz - ire0);
+                ru[IX(n)] = mk<T>(d0 * hz - ire0, d1 * hz - ire0);
             }
         }
         __syncthreads();
 
         // H. D = rfft(demod - ire0)
-        Cx<T>* D = FFTM(rv, ru);
-        Cx<T>* g1 = (D == rv) ? ru : rv;
+        Cx<T>* D = FFTM(ru, rv);
+        Cx<T>* g1 = (D == ru) ? rv : ru;
         Cx<T>* g2 = fv;
         untangle<T, PAD>(D, M, WN, tid, nthr);
         __syncthreads();
@@ -298,10 +309,29 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
             if (m >= p.nfilt && m != 1) continue;
             tangle<T, PAD>(D, g1, (const Cx<T>*)p.F[m], M, WN, tid, nthr);
             __syncthreads();
-            Cx<T>* r = FFTM(g1, g2);
             float* out = (float*)p.plane[pl_of[m]];
             const T addc = (T)p.addc[m];
-            // kept samples 2n, 2n+1 -> out[o + 2n - keep0]; keep0, o and copylen parity: handle singly
+            if (m != 1 && p.plan_m.npass >= 2) {
+                // the last pass hands every output element to the plane store: element n carries samples
+                // 2n (re) and 2n+1 (-im); the result array is never written
+                const bool pairs = ((keep0 | keep1) & 1) == 0 && ((o & 1) == 0) && ((((uintptr_t)out) & 7) == 0);
+                float2* out2 = (float2*)(out + o) - keep0 / 2;
+                auto st_plane = [&](int n, Cx<T> v) {
+                    float v0 = (float)(v.x + addc), v1 = (float)(-v.y + addc);
+                    if (pairs) {
+                        if (2 * n >= keep0 && 2 * n < keep1) st_stream(&out2[n], make_float2(v0, v1));
+                    } else {
+                        int i0 = 2 * n, i1 = 2 * n + 1;
+                        if (i0 >= keep0 && i0 < keep1) st_stream(&out[o + (i0 - keep0)], v0);
+                        if (i1 >= keep0 && i1 < keep1) st_stream(&out[o + (i1 - keep0)], v1);
+                    }
+                };
+                auto ld_q = ArrLoad<T, PAD>{g1};
+                if (SP && sp_ok) fft_run_fn<T, PAD, true>(ld_q, g1, sp, st_plane, p.plan_m, WM, 1, tid, nthr);
+                else fft_run_fn<T, PAD, PAD>(ld_q, g1, g2, st_plane, p.plan_m, WM, 1, tid, nthr);
+                continue;
+            }
+            Cx<T>* r = FFTM(g1, g2);
             if (((keep0 | keep1) & 1) == 0 && ((o & 1) == 0) && ((((uintptr_t)out) & 7) == 0)) {
                 // whole (even, odd) sample pairs inside the kept region: one 8-byte streaming store each
                 float2* out2 = (float2*)(out + o) - keep0 / 2;
@@ -398,241 +428,6 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
     }
 }
 
-// ---- v2: 16 elements per thread, transforms in place -------------------------------------------
-// Requires M == 16 * NT (N = 16384 with 512 threads).  float64: the three block arrays stay in the
-// L2-resident global scratch and every transform runs through one padded shared-memory work buffer
-// (first pass global -> shared, middle passes in place in shared, last pass shared -> global), which
-// cuts the L2 traffic of the transforms by 4x and takes their latency off the critical path.
-// float32: the three arrays themselves live in (padded) shared memory and are transformed in place.
-// The FM discriminator takes its left neighbour's angle by warp shuffle.
-template <class T, int NT, bool SMEM_ARRAYS>
-__global__ void __launch_bounds__(NT, 1) demod_kernel_v2(const DemodParams p) {
-    constexpr bool PA = SMEM_ARRAYS;           // padding of the block arrays
-    const int tid = threadIdx.x, nthr = NT;
-    const int N = p.N, M = p.M;
-    const Cx<T>* WM = (const Cx<T>*)p.WM;
-    const Cx<T>* WN = (const Cx<T>*)p.WN;
-    const Cx<T>* Hv = (const Cx<T>*)p.Hv;
-    LDD_DYN_SMEM(smem);
-    Cx<T>* b0;
-    Cx<T>* work;
-    if (SMEM_ARRAYS) {
-        b0 = (Cx<T>*)smem;
-        work = nullptr;
-    } else {
-        b0 = (Cx<T>*)((char*)p.scratch + (size_t)blockIdx.x * p.scratch_per_cta);
-        work = (Cx<T>*)smem;
-    }
-    Cx<T>* b1 = b0 + pspan<PA>(M);
-    Cx<T>* b2 = b1 + pspan<PA>(M);
-    __shared__ double s_warp[32];
-    __shared__ double s_total;
-#define JX(i) pidx<PA>(i)
-    auto FFT = [&](Cx<T>* buf, const FftPlan& pl, int ws) {
-        fft16<T, PA, true>(buf, SMEM_ARRAYS ? buf : work, buf, pl, WM, ws, tid);
-    };
-
-    for (int blk = blockIdx.x; blk < p.nblocks; blk += gridDim.x) {
-        const long long in0 = p.first_sample + (long long)blk * p.stride;
-        const long long o = (long long)blk * p.stride;
-        long long copylen = p.stride;
-        if (o + (N - p.blockcut) > p.total_out) copylen = p.total_out - o;
-        if (copylen > N - p.blockcut) copylen = N - p.blockcut;
-        if (copylen < 0) copylen = 0;
-        const int keep0 = p.blockcut, keep1 = p.blockcut + (int)copylen;
-
-        // A. samples -> z[n] = x[2n] + j x[2n+1]
-        for (int n = tid; n < M; n += nthr) {
-            int s0 = fetch_sample(p.rf, p.fmt, in0 + 2 * n);
-            int s1 = fetch_sample(p.rf, p.fmt, in0 + 2 * n + 1);
-            b0[JX(n)] = mk<T>((T)s0, (T)s1);
-        }
-        __syncthreads();
-        // B/C. X = rfft(x), in b0
-        FFT(b0, p.plan_m, 1);
-        Cx<T>* X = b0;
-        untangle<T, PA>(X, M, WN, tid, nthr);
-        __syncthreads();
-
-        // D. analog audio, phase 1
-        if (p.A > 0) {
-            const int A = p.A, hA = A / 2;
-            const Cx<T>* AL = (const Cx<T>*)p.AL;
-            const Cx<T>* AR = (const Cx<T>*)p.AR;
-            Cx<T>* gl = b1;
-            Cx<T>* gr = b2;
-            for (int j = tid; j < A; j += nthr) {
-                Cx<T> xa = (j < hA) ? X[JX(p.a_lo + j)] : conj(X[JX(p.a_hi - (j - hA))]);
-                gl[JX(j)] = conj(xa * AL[j]);
-                gr[JX(j)] = conj(xa * AR[j]);
-            }
-            __syncthreads();
-            FFT(gl, p.plan_a, p.wstride_a);
-            FFT(gr, p.plan_a, p.wstride_a);
-            Cx<T>* ang = gl + pspan<PA>(A);
-            for (int j = tid; j < A; j += nthr) {
-                Cx<T> l = gl[JX(j)], r = gr[JX(j)];
-                ang[JX(j)] = mk<T>(Math<T>::atan2(-l.y, l.x), Math<T>::atan2(-r.y, r.x));
-            }
-            __syncthreads();
-            const int a0 = keep0 / p.audio_ds, a1 = keep1 / p.audio_ds;
-            const long long ao = o / p.audio_ds;
-            const double twopi = 6.283185307179586476925286766559;
-            for (int j = a0 + tid; j < a1; j += nthr) {
-                double dl = 0.0, dr = 0.0;
-                if (j > 0) {
-                    Cx<T> c1 = ang[JX(j)], c0 = ang[JX(j - 1)];
-                    dl = (double)c1.x - (double)c0.x;
-                    dr = (double)c1.y - (double)c0.y;
-                    if (dl < 0) dl += twopi;
-                    if (dr < 0) dr += twopi;
-                }
-                long long oi = ao + (j - a0);
-                if (oi < p.audio_total) {
-                    p.audio_l[oi] = dl * p.audio_scale + p.audio_lowfreq;
-                    p.audio_r[oi] = dr * p.audio_scale + p.audio_lowfreq;
-                }
-            }
-            __syncthreads();
-        }
-
-        // E. U, V (even / odd output samples of ifft(X * Hv)), conjugated
-        Cx<T>* U = b1;
-        Cx<T>* V = b2;
-        for (int k = tid; k <= M / 2; k += nthr) {
-            if (k == 0) {
-                Cx<T> x = X[0];
-                Cx<T> y0 = scale(Hv[0], x.x), y1 = scale(Hv[M], x.y);
-                U[0] = conj(y0 + y1);
-                V[0] = conj(y0 - y1);
-            } else {
-                const int ik = JX(k), im = JX(M - k);
-                Cx<T> xa = X[ik], xb = X[im];
-                Cx<T> y0 = xa * Hv[k], y1 = conj(xb) * Hv[k + M];
-                U[ik] = conj(y0 + y1);
-                V[ik] = conj(mulc(y0 - y1, WN[k]));
-                if (k != M - k) {
-                    Cx<T> z0 = xb * Hv[M - k], z1 = conj(xa) * Hv[2 * M - k];
-                    U[im] = conj(z0 + z1);
-                    Cx<T> d = z0 - z1;
-                    V[im] = conj(mk<T>(-d.x, -d.y) * WN[k]);
-                }
-            }
-        }
-        __syncthreads();
-        FFT(U, p.plan_m, 1);
-        FFT(V, p.plan_m, 1);
-
-        // G. FM discriminator; the left neighbour's odd-sample angle comes from the lane below
-        {
-            const T twopi = (T)6.283185307179586476925286766559;
-            const T hz = (T)p.hz_per_rad, ire0 = (T)p.ire0;
-            const int lane = tid & 31;
-            for (int n = tid; n < M; n += nthr) {
-                Cx<T> a = U[JX(n)], b = V[JX(n)];
-                T ae = Math<T>::atan2(-a.y, a.x), ao = Math<T>::atan2(-b.y, b.x);
-                T prev = __shfl_up_sync(0xffffffffu, ao, 1);
-                if (lane == 0 && n > 0) {
-                    Cx<T> q = V[JX(n - 1)];
-                    prev = Math<T>::atan2(-q.y, q.x);
-                }
-                T d0 = (T)0;
-                if (n > 0) {
-                    d0 = ae - prev;
-                    if (d0 < 0) d0 += twopi;
-                }
-                T d1 = ao - ae;
-                if (d1 < 0) d1 += twopi;
-                U[JX(n)] = mk<T>(d0 * hz - ire0, d1 * hz - ire0);       // V is still read by the warp above
-            }
-        }
-        __syncthreads();
-
-        // H. D = rfft(demod - ire0), in b1
-        FFT(U, p.plan_m, 1);
-        Cx<T>* D = U;
-        untangle<T, PA>(D, M, WN, tid, nthr);
-        __syncthreads();
-
-        // I. post filters into b2; video05 last (its whole block feeds the sync scan)
-        const int order[4] = {0, 2, 3, 1};
-        const int pl_of[4] = {LDD_P_DEMOD, LDD_P_DEMOD05, LDD_P_BURST, LDD_P_PILOT};
-        Cx<T>* r = b2;
-        for (int oi = 0; oi < 4; ++oi) {
-            const int m = order[oi];
-            if (m >= p.nfilt && m != 1) continue;
-            tangle<T, PA>(D, r, (const Cx<T>*)p.F[m], M, WN, tid, nthr);
-            __syncthreads();
-            FFT(r, p.plan_m, 1);
-            float* out = (float*)p.plane[pl_of[m]];
-            const T addc = (T)p.addc[m];
-            for (int n = tid; n < M; n += nthr) {
-                Cx<T> v = r[JX(n)];
-                int i0 = 2 * n, i1 = 2 * n + 1;
-                float v0 = (float)(v.x + addc), v1 = (float)(-v.y + addc);
-                if (i0 >= keep0 && i0 < keep1) st_stream(&out[o + (i0 - keep0)], v0);
-                if (i1 >= keep0 && i1 < keep1) st_stream(&out[o + (i1 - keep0)], v1);
-            }
-            __syncthreads();
-        }
-
-        // J. sync scan (same as v1)
-        {
-            const T* x05 = (const T*)r;
-            const double add = p.addc[1] + p.sync_ref;
-            const int CH = N / nthr;
-            const int n0 = tid * CH;
-            auto insync = [&](int n) -> double {
-                n = (n + N) & (N - 1);
-                double v = (double)x05[2 * JX(n >> 1) + (n & 1)];
-                if (n & 1) v = -v;
-                v += add;
-                return (v >= p.sync_lo && v <= p.sync_hi) ? 1.0 : 0.0;
-            };
-            const double c = p.fp_c;
-            double sprev = insync(n0 - 1);
-            const double sprev0 = sprev;
-            double acc = 0.0;
-            for (int i = 0; i < CH; ++i) {
-                double s = insync(n0 + i);
-                acc = c * acc + (p.fp_b0 * s + p.fp_b1 * sprev);
-                sprev = s;
-            }
-            const double Ach = pow(c, (double)CH);
-            const int lane = tid & 31, warp = tid >> 5;
-            double incl = acc, mult = Ach;
-            for (int d = 1; d < 32; d <<= 1) {
-                double up = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += mult * up;
-                mult *= mult;
-            }
-            if (lane == 31) s_warp[warp] = incl;
-            __syncthreads();
-            const double A32 = pow(Ach, 32.0);
-            double carry = 0.0;
-            for (int w = 0; w < warp; ++w) carry = A32 * carry + s_warp[w];
-            if (tid == nthr - 1) {
-                double tot = pow(Ach, (double)(lane + 1)) * carry + incl;
-                s_total = tot / (1.0 - pow(c, (double)N));
-            }
-            __syncthreads();
-            double excl = __shfl_up_sync(0xffffffffu, incl, 1);
-            double st = (lane == 0 ? 0.0 : excl) + pow(Ach, (double)lane) * carry + pow(c, (double)n0) * s_total;
-            double* out = (double*)p.plane[LDD_P_SYNC];
-            sprev = sprev0;
-            for (int i = 0; i < CH; ++i) {
-                int n = n0 + i;
-                double s = insync(n);
-                st = c * st + (p.fp_b0 * s + p.fp_b1 * sprev);
-                sprev = s;
-                if (n >= keep0 && n < keep1) st_stream(&out[o + (n - keep0)], st);
-            }
-        }
-        __syncthreads();
-    }
-#undef JX
-}
-
 static int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -648,19 +443,6 @@ static int launch_variant(const DemodParams& p, int grid, cudaStream_t st, size_
     if (smem_bytes) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     LDD_LAUNCH(kern, dim3(grid), dim3(NT), smem_bytes, st, p);
     return check_launch("demod_kernel");
-}
-
-template <class T, int NT, bool SMEM_ARRAYS>
-static int launch_v2(const DemodParams& p, int grid, cudaStream_t st, size_t smem_bytes) {
-    void (*kern)(const DemodParams) = demod_kernel_v2<T, NT, SMEM_ARRAYS>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    LDD_LAUNCH(kern, dim3(grid), dim3(NT), smem_bytes, st, p);
-    return check_launch("demod_kernel_v2");
-}
-
-int launch_demod_v2(const DemodParams& p, int grid, bool f64, cudaStream_t st, size_t smem_bytes) {
-    if (f64) return launch_v2<double, 512, false>(p, grid, st, smem_bytes);
-    return launch_v2<float, 512, true>(p, grid, st, smem_bytes);
 }
 
 int launch_demod_f64(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t sp_bytes) {

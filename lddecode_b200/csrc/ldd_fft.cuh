@@ -163,6 +163,78 @@ __device__ inline Cx<T>* fft_run(Cx<T>* a, Cx<T>* b, const FftPlan& plan, const 
     return (plan.npass & 1) ? b : a;
 }
 
+// ---- passes whose first load / last store go through functors --------------------------------------
+// ld(i) -> element i of the input sequence, st(i, v) consumes element i of the output sequence.  They let
+// the block load (raw samples -> complex) and the plane stores fuse into the first / last Stockham pass
+// instead of costing a pass over the array each.
+template <class T, bool P> struct ArrLoad {
+    const Cx<T>* p;
+    __device__ inline Cx<T> operator()(int i) const { return p[pidx<P>(i)]; }
+};
+template <class T, bool P> struct ArrStore {
+    Cx<T>* p;
+    __device__ inline void operator()(int i, Cx<T> v) const { p[pidx<P>(i)] = v; }
+};
+
+template <class T, int R, class LD, class ST>
+__device__ inline void fft_pass_fn(LD ld, ST st, int M, int Ns, const Cx<T>* __restrict__ W, int wstride, int tid, int nthr) {
+    const int nb = M / R;
+    for (int j = tid; j < nb; j += nthr) {
+        Cx<T> v[R];
+        LDD_UNROLL
+        for (int r = 0; r < R; ++r) v[r] = ld(j + r * nb);
+        const int k = j & (Ns - 1);
+        if (Ns > 1) {
+            Cx<T> p[R];
+            p[1] = W[(size_t)k * (size_t)(nb / Ns) * (size_t)wstride];
+            LDD_UNROLL
+            for (int r = 2; r < R; ++r) p[r] = (r & 1) ? p[r - 1] * p[1] : p[r / 2] * p[r / 2];
+            LDD_UNROLL
+            for (int r = 1; r < R; ++r) v[r] = v[r] * p[r];
+        }
+        Dft<T, R>::run(v);
+        const int j0 = (j - k) * R + k;
+        LDD_UNROLL
+        for (int r = 0; r < R; ++r) st(j0 + r * Ns, v[r]);
+    }
+}
+
+template <class T, class LD, class ST>
+__device__ inline void fft_pass_fn_any(int R, LD ld, ST st, int M, int Ns, const Cx<T>* __restrict__ W, int wstride,
+                                       int tid, int nthr) {
+    switch (R) {
+        case 16: fft_pass_fn<T, 16>(ld, st, M, Ns, W, wstride, tid, nthr); break;
+        case 8: fft_pass_fn<T, 8>(ld, st, M, Ns, W, wstride, tid, nthr); break;
+        case 4: fft_pass_fn<T, 4>(ld, st, M, Ns, W, wstride, tid, nthr); break;
+        default: fft_pass_fn<T, 2>(ld, st, M, Ns, W, wstride, tid, nthr); break;
+    }
+}
+
+// Like fft_run (a <-> b ping-pong, paddings PA / PB, plan.npass >= 2) but the first pass loads through
+// ld_first and the last pass stores through st_last: nothing is read from a before pass 2 and nothing is
+// written to the array that would hold the result.  Ends with a barrier.
+template <class T, bool PA, bool PB, class LD, class ST>
+__device__ inline void fft_run_fn(LD ld_first, Cx<T>* a, Cx<T>* b, ST st_last, const FftPlan& plan,
+                                  const Cx<T>* __restrict__ W, int wstride, int tid, int nthr) {
+    int Ns = 1;
+    const int last = plan.npass - 1;
+    for (int p = 0; p <= last; ++p) {
+        const int R = plan.radix[p];
+        const bool even = (p & 1) == 0;
+        if (p == 0) {
+            fft_pass_fn_any<T>(R, ld_first, ArrStore<T, PB>{b}, plan.n, Ns, W, wstride, tid, nthr);
+        } else if (p == last) {
+            if (even) fft_pass_fn_any<T>(R, ArrLoad<T, PA>{a}, st_last, plan.n, Ns, W, wstride, tid, nthr);
+            else fft_pass_fn_any<T>(R, ArrLoad<T, PB>{b}, st_last, plan.n, Ns, W, wstride, tid, nthr);
+        } else {
+            if (even) fft_pass_any<T, PA, PB>(R, a, b, plan.n, Ns, W, wstride, tid, nthr);
+            else fft_pass_any<T, PB, PA>(R, b, a, plan.n, Ns, W, wstride, tid, nthr);
+        }
+        Ns *= R;
+        __syncthreads();
+    }
+}
+
 // Two independent transforms with the same plan, pass by pass, ONE barrier per pass pair: a warp that
 // finishes its butterfly of the first transform starts loading for the second while slower warps
 // still compute, so the L2 latency of one overlaps the arithmetic of the other.  (a1 <-> b1 with
@@ -181,77 +253,6 @@ __device__ inline void fft_run_pair(Cx<T>* a1, Cx<T>* b1, Cx<T>* a2, Cx<T>* b2, 
         }
         Ns *= plan.radix[p];
         __syncthreads();
-    }
-}
-
-// ---- in-place variant: 16 elements per thread --------------------------------------------------
-// For n == 16 * (number of active threads) every pass can run in place: each active thread loads
-// the 16 elements of its 16/R butterflies into registers, the CTA synchronises, then it stores its
-// outputs.  One buffer is enough, so a float64 transform of M = 8192 points fits a 136 KB padded
-// shared-memory work buffer while the arrays it reads from / writes to stay in the L2-resident
-// global scratch (PIO: padding of src/dst, PW: padding of the work buffer).  src may equal dst.
-template <class T, int R, bool PIN, bool POUT>
-__device__ inline void fft_pass16(const Cx<T>* in, Cx<T>* out, int n, int Ns, const Cx<T>* __restrict__ W,
-                                  int wstride, int tid) {
-    constexpr int C = 16 / R;
-    const int nact = n >> 4, nb = n / R;
-    const bool act = tid < nact;
-    Cx<T> v[16];
-    if (act) {
-        LDD_UNROLL
-        for (int c = 0; c < C; ++c) {
-            const int j = tid + c * nact;
-            LDD_UNROLL
-            for (int r = 0; r < R; ++r) v[c * R + r] = in[pidx<PIN>(j + r * nb)];
-        }
-    }
-    __syncthreads();
-    if (act) {
-        LDD_UNROLL
-        for (int c = 0; c < C; ++c) {
-            const int j = tid + c * nact;
-            const int k = j & (Ns - 1);
-            Cx<T>* b = v + c * R;
-            if (Ns > 1) {
-                Cx<T> p[R];
-                p[1] = W[(size_t)k * (size_t)(nb / Ns) * (size_t)wstride];
-                LDD_UNROLL
-                for (int r = 2; r < R; ++r) p[r] = (r & 1) ? p[r - 1] * p[1] : p[r / 2] * p[r / 2];
-                LDD_UNROLL
-                for (int r = 1; r < R; ++r) b[r] = b[r] * p[r];
-            }
-            Dft<T, R>::run(b);
-            const int j0 = (j - k) * R + k;
-            LDD_UNROLL
-            for (int r = 0; r < R; ++r) out[pidx<POUT>(j0 + r * Ns)] = b[r];
-        }
-    }
-    __syncthreads();
-}
-
-template <class T, bool PIN, bool POUT>
-__device__ inline void fft_pass16_any(int R, const Cx<T>* in, Cx<T>* out, int n, int Ns, const Cx<T>* __restrict__ W,
-                                      int wstride, int tid) {
-    switch (R) {
-        case 16: fft_pass16<T, 16, PIN, POUT>(in, out, n, Ns, W, wstride, tid); break;
-        case 8: fft_pass16<T, 8, PIN, POUT>(in, out, n, Ns, W, wstride, tid); break;
-        case 4: fft_pass16<T, 4, PIN, POUT>(in, out, n, Ns, W, wstride, tid); break;
-        default: fft_pass16<T, 2, PIN, POUT>(in, out, n, Ns, W, wstride, tid); break;
-    }
-}
-
-// src -> (work ...) -> dst; needs plan.npass >= 2.  Every thread of the CTA must call it.
-template <class T, bool PIO, bool PW>
-__device__ inline void fft16(const Cx<T>* src, Cx<T>* work, Cx<T>* dst, const FftPlan& plan,
-                             const Cx<T>* __restrict__ W, int wstride, int tid) {
-    int Ns = 1;
-    const int last = plan.npass - 1;
-    for (int ps = 0; ps <= last; ++ps) {
-        const int R = plan.radix[ps];
-        if (ps == 0) fft_pass16_any<T, PIO, PW>(R, src, work, plan.n, Ns, W, wstride, tid);
-        else if (ps == last) fft_pass16_any<T, PW, PIO>(R, work, dst, plan.n, Ns, W, wstride, tid);
-        else fft_pass16_any<T, PW, PW>(R, work, work, plan.n, Ns, W, wstride, tid);
-        Ns *= R;
     }
 }
 

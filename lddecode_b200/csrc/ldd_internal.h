@@ -66,7 +66,6 @@ inline int launch_status(ldd_handle* h, const char* what);
 
 int launch_demod_f64(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t sp_bytes);
 int launch_demod_f32(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t smem_bytes);
-int launch_demod_v2(const DemodParams& p, int grid, bool f64, cudaStream_t st, size_t smem_bytes);
 
 }  // namespace ldd
 
@@ -93,7 +92,6 @@ struct ldd_handle {
     int threads;      // CTA size of the demodulation kernel
     int radix_max;    // largest Stockham radix used
     size_t smem_bytes;
-    bool v2;          // in-place 16-elements-per-thread kernel (N == 16384)
     size_t sp_bytes = 0;    // float64 lane: bytes of the shared-memory ping-pong partner (0: not used)
     void* scratch64 = nullptr;       // float64 scratch of the mixed lane's second pass
     size_t scratch64_per_cta = 0;

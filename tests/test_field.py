@@ -112,3 +112,22 @@ def test_field_early_outs(backend):
         assert not f.valid and not of.valid
         assert f.nextfieldoffset == of.nextfieldoffset
         assert np.array_equal(f.peaklist, of.peaklist)
+
+
+@pytest.mark.parametrize("name", ["ntsc", "pal"])
+def test_field_golden_mixed_lane(backend, golden, name):
+    """The mixed-precision lane against the same golden fields, at the north-star bars only: peak
+    indices bit-exact, line tables identical where they are integers, TBC within +-1 LSB."""
+    g = golden(name)
+    system = "PAL" if name == "pal" else "NTSC"
+    rf = rfdecode.RFDecode(float(g["fs_mhz"]), system, int(g["blocklen"]), precision="mixed", _backend=backend)
+    cap = g["capture"]
+    dd = rf.demod_device(backend.to_device(cap), _lib.FMT_U8, 0, len(cap), 0, int(g["demod_length"]), 1)
+    f = (field.FieldNTSC if system == "NTSC" else field.FieldPAL)(rf, dd, 0)
+    assert f.valid
+    assert np.array_equal(np.array(f.peaklist), g["field_peaklist"])
+    assert np.array_equal(np.array(f.vsyncs), g["field_vsyncs"])
+    np.testing.assert_array_equal(np.array(f.linelocs1), g["field_linelocs1"])
+    np.testing.assert_allclose(f.linelocs, g["field_linelocs"], rtol=0, atol=2e-3)
+    d = f.dspicture.astype(np.int64) - g["field_dspicture"].astype(np.int64)
+    assert np.abs(d).max() <= 1

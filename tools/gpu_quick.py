@@ -16,7 +16,6 @@ from lddecode_b200 import _lib, rfdecode, synth  # noqa: E402
 
 
 def run(system, fs, N, prec, cap_dev, ncap, audio, threads, radix, ctas=1, reps=5, kernel=2):
-    os.environ["LDD_KERNEL"] = str(kernel)
     os.environ["LDD_THREADS"] = str(threads)
     os.environ["LDD_RADIX_MAX"] = str(radix)
     os.environ["LDD_CTAS_PER_SM"] = str(ctas)

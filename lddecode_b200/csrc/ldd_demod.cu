@@ -148,41 +148,24 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         if (copylen < 0) copylen = 0;
         const int keep0 = p.blockcut, keep1 = p.blockcut + (int)copylen;
 
-        // A+B. X = rfft(x): the samples are read and converted inside the first Stockham pass
-        //      (z[n] = x[2n] + j x[2n+1]); no separate pass writes z.
-        Cx<T>* X;
-        {
-            const bool fast8 = p.fmt == LDD_FMT_U8 && ((in0 & 1) == 0) && ((((uintptr_t)p.rf) & 1) == 0);
+        // A. samples -> z[n] = x[2n] + j x[2n+1]
+        if (p.fmt == LDD_FMT_U8 && ((in0 & 1) == 0) && ((((uintptr_t)p.rf) & 1) == 0)) {
             const unsigned short* r16 = (const unsigned short*)((const unsigned char*)p.rf + in0);
-            auto ld_raw = [&](int n) -> Cx<T> {
-                if (fast8) {
-                    unsigned v = r16[n];
-                    return mk<T>((T)(int)(v & 0xffu), (T)(int)(v >> 8));
-                }
+            for (int n = tid; n < M; n += nthr) {
+                unsigned v = r16[n];
+                b0[IX(n)] = mk<T>((T)(int)(v & 0xffu), (T)(int)(v >> 8));
+            }
+        } else {
+            for (int n = tid; n < M; n += nthr) {
                 int s0 = fetch_sample(p.rf, p.fmt, in0 + 2 * n);
                 int s1 = fetch_sample(p.rf, p.fmt, in0 + 2 * n + 1);
-                return mk<T>((T)s0, (T)s1);
-            };
-            if (p.plan_m.npass >= 2) {
-                // first pass: raw -> partner; last pass lands in b0 (even pass count) or in the partner (odd)
-                Cx<T>* partner = (SP && sp_ok) ? sp : b1;
-                const bool even = (p.plan_m.npass & 1) == 0;
-                if (SP && sp_ok) {
-                    fft_run_fn<T, PAD, true>(ld_raw, b0, partner, ArrStore<T, PAD>{b0}, p.plan_m, WM, 1, tid, nthr);
-                    X = b0;
-                } else if (even) {
-                    fft_run_fn<T, PAD, PAD>(ld_raw, b0, partner, ArrStore<T, PAD>{b0}, p.plan_m, WM, 1, tid, nthr);
-                    X = b0;
-                } else {
-                    fft_run_fn<T, PAD, PAD>(ld_raw, b0, partner, ArrStore<T, PAD>{b1}, p.plan_m, WM, 1, tid, nthr);
-                    X = b1;
-                }
-            } else {
-                for (int n = tid; n < M; n += nthr) b0[IX(n)] = ld_raw(n);
-                __syncthreads();
-                X = FFTM(b0, b1);
+                b0[IX(n)] = mk<T>((T)s0, (T)s1);
             }
         }
+        __syncthreads();
+
+        // B/C. X = rfft(x)
+        Cx<T>* X = FFTM(b0, b1);
         Cx<T>* f1 = (X == b0) ? b1 : b0;      // free
         Cx<T>* f2 = b2;                        // free
         untangle<T, PAD>(X, M, WN, tid, nthr);
@@ -260,42 +243,48 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         __syncthreads();
 
         // F. h[2n] = conj(ru[n]), h[2n+1] = conj(rv[n]) (up to a positive scale)
-        Cx<T>* ru = FFTM(U, X);
-        Cx<T>* fu = (ru == U) ? X : U;
-        Cx<T>* rv = FFTM(V, fu);
-        Cx<T>* fv = (rv == V) ? fu : V;
+        Cx<T>* ru;
+        Cx<T>* fu;
+        Cx<T>* rv;
+        Cx<T>* fv;
+        if (SP && sp_ok) {
+            // the two transforms are independent: run them pass by pass with one barrier per pass pair
+            fft_run_pair<T, PAD, true, PAD>(U, sp, V, X, p.plan_m, WM, 1, tid, nthr);
+            ru = U; rv = V; fu = X; fv = X;
+        } else {
+            ru = FFTM(U, X);
+            fu = (ru == U) ? X : U;
+            rv = FFTM(V, fu);
+            fv = (rv == V) ? fu : V;
+        }
 
         // G. FM discriminator (lddutils.py:320-334): angle, neighbour difference, fold to [0, 2pi),
-        //    scale to Hz; minus ire0; packed for the next real transform.  One pass: the angle of the
-        //    odd sample to the left comes from the lane below by warp shuffle (lane 0 recomputes it).
-        //    The result overwrites ru; rv stays intact because the warp above still reads it.
+        //    scale to Hz; minus ire0; packed for the next real transform.
+        for (int n = tid; n < M; n += nthr) {
+            Cx<T> a = ru[IX(n)], b = rv[IX(n)];
+            ru[IX(n)] = mk<T>(Math<T>::atan2(-a.y, a.x), Math<T>::atan2(-b.y, b.x));
+        }
+        __syncthreads();
         {
             const T twopi = (T)6.283185307179586476925286766559;
             const T hz = (T)p.hz_per_rad, ire0 = (T)p.ire0;
-            const int lane = tid & 31;
             for (int n = tid; n < M; n += nthr) {
-                Cx<T> a = ru[IX(n)], b = rv[IX(n)];
-                T ae = Math<T>::atan2(-a.y, a.x), ao = Math<T>::atan2(-b.y, b.x);
-                T prev = __shfl_up_sync(0xffffffffu, ao, 1);
-                if (lane == 0 && n > 0) {
-                    Cx<T> q = rv[IX(n - 1)];
-                    prev = Math<T>::atan2(-q.y, q.x);
-                }
+                Cx<T> a = ru[IX(n)];
                 T d0 = (T)0;
                 if (n > 0) {
-                    d0 = ae - prev;
+                    d0 = a.x - ru[IX(n - 1)].y;
                     if (d0 < 0) d0 += twopi;
                 }
-                T d1 = ao - ae;
+                T d1 = a.y - a.x;
                 if (d1 < 0) d1 += twopi;
-                ru[IX(n)] = mk<T>(d0 * hz - ire0, d1 * hz - ire0);
+                rv[IX(n)] = mk<T>(d0 * hz - ire0, d1 * hz - ire0);
             }
         }
         __syncthreads();
 
         // H. D = rfft(demod - ire0)
-        Cx<T>* D = FFTM(ru, rv);
-        Cx<T>* g1 = (D == ru) ? rv : ru;
+        Cx<T>* D = FFTM(rv, ru);
+        Cx<T>* g1 = (D == rv) ? ru : rv;
         Cx<T>* g2 = fv;
         untangle<T, PAD>(D, M, WN, tid, nthr);
         __syncthreads();
@@ -309,29 +298,10 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
             if (m >= p.nfilt && m != 1) continue;
             tangle<T, PAD>(D, g1, (const Cx<T>*)p.F[m], M, WN, tid, nthr);
             __syncthreads();
+            Cx<T>* r = FFTM(g1, g2);
             float* out = (float*)p.plane[pl_of[m]];
             const T addc = (T)p.addc[m];
-            if (m != 1 && p.plan_m.npass >= 2) {
-                // the last pass hands every output element to the plane store: element n carries samples
-                // 2n (re) and 2n+1 (-im); the result array is never written
-                const bool pairs = ((keep0 | keep1) & 1) == 0 && ((o & 1) == 0) && ((((uintptr_t)out) & 7) == 0);
-                float2* out2 = (float2*)(out + o) - keep0 / 2;
-                auto st_plane = [&](int n, Cx<T> v) {
-                    float v0 = (float)(v.x + addc), v1 = (float)(-v.y + addc);
-                    if (pairs) {
-                        if (2 * n >= keep0 && 2 * n < keep1) st_stream(&out2[n], make_float2(v0, v1));
-                    } else {
-                        int i0 = 2 * n, i1 = 2 * n + 1;
-                        if (i0 >= keep0 && i0 < keep1) st_stream(&out[o + (i0 - keep0)], v0);
-                        if (i1 >= keep0 && i1 < keep1) st_stream(&out[o + (i1 - keep0)], v1);
-                    }
-                };
-                auto ld_q = ArrLoad<T, PAD>{g1};
-                if (SP && sp_ok) fft_run_fn<T, PAD, true>(ld_q, g1, sp, st_plane, p.plan_m, WM, 1, tid, nthr);
-                else fft_run_fn<T, PAD, PAD>(ld_q, g1, g2, st_plane, p.plan_m, WM, 1, tid, nthr);
-                continue;
-            }
-            Cx<T>* r = FFTM(g1, g2);
+            // kept samples 2n, 2n+1 -> out[o + 2n - keep0]; keep0, o and copylen parity: handle singly
             if (((keep0 | keep1) & 1) == 0 && ((o & 1) == 0) && ((((uintptr_t)out) & 7) == 0)) {
                 // whole (even, odd) sample pairs inside the kept region: one 8-byte streaming store each
                 float2* out2 = (float2*)(out + o) - keep0 / 2;

@@ -163,78 +163,6 @@ __device__ inline Cx<T>* fft_run(Cx<T>* a, Cx<T>* b, const FftPlan& plan, const 
     return (plan.npass & 1) ? b : a;
 }
 
-// ---- passes whose first load / last store go through functors --------------------------------------
-// ld(i) -> element i of the input sequence, st(i, v) consumes element i of the output sequence.  They let
-// the block load (raw samples -> complex) and the plane stores fuse into the first / last Stockham pass
-// instead of costing a pass over the array each.
-template <class T, bool P> struct ArrLoad {
-    const Cx<T>* p;
-    __device__ inline Cx<T> operator()(int i) const { return p[pidx<P>(i)]; }
-};
-template <class T, bool P> struct ArrStore {
-    Cx<T>* p;
-    __device__ inline void operator()(int i, Cx<T> v) const { p[pidx<P>(i)] = v; }
-};
-
-template <class T, int R, class LD, class ST>
-__device__ inline void fft_pass_fn(LD ld, ST st, int M, int Ns, const Cx<T>* __restrict__ W, int wstride, int tid, int nthr) {
-    const int nb = M / R;
-    for (int j = tid; j < nb; j += nthr) {
-        Cx<T> v[R];
-        LDD_UNROLL
-        for (int r = 0; r < R; ++r) v[r] = ld(j + r * nb);
-        const int k = j & (Ns - 1);
-        if (Ns > 1) {
-            Cx<T> p[R];
-            p[1] = W[(size_t)k * (size_t)(nb / Ns) * (size_t)wstride];
-            LDD_UNROLL
-            for (int r = 2; r < R; ++r) p[r] = (r & 1) ? p[r - 1] * p[1] : p[r / 2] * p[r / 2];
-            LDD_UNROLL
-            for (int r = 1; r < R; ++r) v[r] = v[r] * p[r];
-        }
-        Dft<T, R>::run(v);
-        const int j0 = (j - k) * R + k;
-        LDD_UNROLL
-        for (int r = 0; r < R; ++r) st(j0 + r * Ns, v[r]);
-    }
-}
-
-template <class T, class LD, class ST>
-__device__ inline void fft_pass_fn_any(int R, LD ld, ST st, int M, int Ns, const Cx<T>* __restrict__ W, int wstride,
-                                       int tid, int nthr) {
-    switch (R) {
-        case 16: fft_pass_fn<T, 16>(ld, st, M, Ns, W, wstride, tid, nthr); break;
-        case 8: fft_pass_fn<T, 8>(ld, st, M, Ns, W, wstride, tid, nthr); break;
-        case 4: fft_pass_fn<T, 4>(ld, st, M, Ns, W, wstride, tid, nthr); break;
-        default: fft_pass_fn<T, 2>(ld, st, M, Ns, W, wstride, tid, nthr); break;
-    }
-}
-
-// Like fft_run (a <-> b ping-pong, paddings PA / PB, plan.npass >= 2) but the first pass loads through
-// ld_first and the last pass stores through st_last: nothing is read from a before pass 2 and nothing is
-// written to the array that would hold the result.  Ends with a barrier.
-template <class T, bool PA, bool PB, class LD, class ST>
-__device__ inline void fft_run_fn(LD ld_first, Cx<T>* a, Cx<T>* b, ST st_last, const FftPlan& plan,
-                                  const Cx<T>* __restrict__ W, int wstride, int tid, int nthr) {
-    int Ns = 1;
-    const int last = plan.npass - 1;
-    for (int p = 0; p <= last; ++p) {
-        const int R = plan.radix[p];
-        const bool even = (p & 1) == 0;
-        if (p == 0) {
-            fft_pass_fn_any<T>(R, ld_first, ArrStore<T, PB>{b}, plan.n, Ns, W, wstride, tid, nthr);
-        } else if (p == last) {
-            if (even) fft_pass_fn_any<T>(R, ArrLoad<T, PA>{a}, st_last, plan.n, Ns, W, wstride, tid, nthr);
-            else fft_pass_fn_any<T>(R, ArrLoad<T, PB>{b}, st_last, plan.n, Ns, W, wstride, tid, nthr);
-        } else {
-            if (even) fft_pass_any<T, PA, PB>(R, a, b, plan.n, Ns, W, wstride, tid, nthr);
-            else fft_pass_any<T, PB, PA>(R, b, a, plan.n, Ns, W, wstride, tid, nthr);
-        }
-        Ns *= R;
-        __syncthreads();
-    }
-}
-
 // Two independent transforms with the same plan, pass by pass, ONE barrier per pass pair: a warp that
 // finishes its butterfly of the first transform starts loading for the second while slower warps
 // still compute, so the L2 latency of one overlaps the arithmetic of the other.  (a1 <-> b1 with

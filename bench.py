@@ -240,8 +240,11 @@ def run_ours(a):
         return res
 
     def step_e2e(out_pin):
-        d = cap_pin.cuda(non_blocking=True)                         # H2D of the step's input
-        res = decode(d)
+        if a.ranges == 1 and a.h2d_chunks > 1:
+            res = [cd.decode_host(cap_pin, _lib.FMT_U8, ncap, a.h2d_chunks)]     # H2D in pieces, overlapped with the demodulation
+        else:
+            d = cap_pin.cuda(non_blocking=True)                     # H2D of the step's input
+            res = decode(d)
         n = 0
         for r in res:
             m = len(r.located) * r.out_stride
@@ -392,6 +395,7 @@ def main():
     ap.add_argument("--audio", action="store_true", help="also demodulate the two analog FM audio channels")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32", "mixed"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--h2d-chunks", type=int, default=4, help="e2e: pieces the capture upload is split into (overlapped with the kernel)")
     ap.add_argument("--ranges", type=int, default=1,
                     help="read-position ranges a step's capture is pipelined over (measured on B200: 1 is fastest -- the "
                          "persistent demodulation kernel of one range blocks the small kernels of the other)")

@@ -43,6 +43,9 @@ class CudaBackend:
     def to_host(self, buf):
         return buf.cpu().numpy()
 
+    def dtype_of(self, np_dtype):
+        return _NP2TORCH[np.dtype(np_dtype)]
+
     def ptr(self, buf):
         return C.c_void_p(buf.data_ptr())
 
@@ -113,6 +116,9 @@ class EmuBackend:
 
     def to_host(self, buf):
         return np.array(buf, copy=True)
+
+    def dtype_of(self, np_dtype):
+        return np.dtype(np_dtype)
 
     def ptr(self, buf):
         return C.c_void_p(buf.ctypes.data)

@@ -31,14 +31,21 @@ class FieldBatch:
     def __init__(self, rf, nfields):
         self.rf = rf
         self.n = nfields
-        self.info = [None] * nfields
         self.base = np.zeros(nfields, dtype=np.int64)        # plane index of each window's sample 0
         self.winlen = np.zeros(nfields, dtype=np.int64)
         self.linecount = np.zeros(nfields, dtype=np.int32)
         self.linelocs1 = np.zeros((nfields, LL_STRIDE), dtype=np.float64)
         self.linebad = np.zeros((nfields, LL_STRIDE), dtype=np.uint8)
-        self.peaks = [None] * nfields                         # window-relative peak lists (host)
-        self.vals = [None] * nfields
+
+    @classmethod
+    def view(cls, rf, batch, idx, linecounts):
+        """The rows `idx` of `batch` as a new batch (fancy-indexed copies, no Python loop per field)."""
+        b = cls.__new__(cls)
+        b.rf, b.n = rf, len(idx)
+        b.base, b.winlen = batch.base[idx], batch.winlen[idx]
+        b.linecount = np.ascontiguousarray(linecounts, dtype=np.int32)
+        b.linelocs1, b.linebad = batch.linelocs1[idx], batch.linebad[idx]
+        return b
 
 
 class PendingPeaks:
@@ -105,11 +112,23 @@ def refine_and_tbc(rf, planes, plane_len, batch, colorlevel=1.45, colorphase=91.
     W = rf.SysParams['outlinelen']
     maxlc = int(batch.linecount.max()) if n else 0
     out.out_stride = (rf.SysParams['frame_lines'] // 2 + 1) * W
-    d_base = be.to_device(batch.base)
-    d_win = be.to_device(batch.winlen)
-    d_lc = be.to_device(batch.linecount)
-    d_l1 = be.to_device(batch.linelocs1.reshape(-1))
-    d_bad = be.to_device(batch.linebad.reshape(-1))
+    # one host->device copy for all per-field tables: [base | winlen | linelocs1 | linecount | linebad]
+    pk = np.empty(n * (8 + 8 + 8 * LL_STRIDE + 4 + LL_STRIDE) + 64, dtype=np.uint8)
+    o_base, o_win = 0, 8 * n
+    o_l1 = 16 * n
+    o_lc = o_l1 + 8 * n * LL_STRIDE
+    o_bad = o_lc + 4 * n
+    pk[o_base:o_base + 8 * n] = batch.base.view(np.uint8)
+    pk[o_win:o_win + 8 * n] = batch.winlen.view(np.uint8)
+    pk[o_l1:o_l1 + 8 * n * LL_STRIDE] = np.ascontiguousarray(batch.linelocs1).reshape(-1).view(np.uint8)
+    pk[o_lc:o_lc + 4 * n] = batch.linecount.view(np.uint8)
+    pk[o_bad:o_bad + n * LL_STRIDE] = np.ascontiguousarray(batch.linebad).reshape(-1)
+    d_pk = be.to_device(pk)
+    d_base = d_pk[o_base:o_base + 8 * n].view(be.dtype_of(np.int64))
+    d_win = d_pk[o_win:o_win + 8 * n].view(be.dtype_of(np.int64))
+    d_l1 = d_pk[o_l1:o_l1 + 8 * n * LL_STRIDE].view(be.dtype_of(np.float64))
+    d_lc = d_pk[o_lc:o_lc + 4 * n].view(be.dtype_of(np.int32))
+    d_bad = d_pk[o_bad:o_bad + n * LL_STRIDE]
     d_l2 = be.empty(n * LL_STRIDE, np.float64)
     d_bad2 = be.empty(n * LL_STRIDE, np.uint8)
     d_status = be.zeros(n, np.int32)

@@ -240,11 +240,8 @@ def run_ours(a):
         return res
 
     def step_e2e(out_pin):
-        if a.ranges == 1 and a.h2d_chunks > 1:
-            res = [cd.decode_host(cap_pin, _lib.FMT_U8, ncap, a.h2d_chunks)]     # H2D in pieces, overlapped with the demodulation
-        else:
-            d = cap_pin.cuda(non_blocking=True)                     # H2D of the step's input
-            res = decode(d)
+        d = cap_pin.cuda(non_blocking=True)                         # H2D of the step's input
+        res = decode(d)
         n = 0
         for r in res:
             m = len(r.located) * r.out_stride
@@ -338,6 +335,14 @@ def run_ours(a):
         bytes_per_sample = N / S + 4 * nplanes32 + 8 + (2 * 8 / (16 if system == "PAL" else 8) if audio else 0)
         achieved = bytes_per_sample * planes_total / (k_ms / 1e3) / 1e9
         # per range: demod, 4 peak kernels (+4 for the one window that starts off a peak), hsync, pilot | 2x burst, tbc, 2 audio
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_demod_traffic.json")))
+            key = "%s_%s" % (system, a.precision)
+            if key in tj:
+                traffic = tj[key]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         launches_per_step = a.ranges * (1 + 4 + 1 + (1 if system == "PAL" else 2) + 1 + (2 if audio else 0)) + 4
         line = dict(metric="rf_msamples_per_s_demod_tbc", value=value, unit="Msamples/s", n_gpus=world, steps=a.steps,
                     warmup=max(a.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -347,7 +352,7 @@ def run_ours(a):
                              d2h_bytes_per_step=int(npic * 2), wall_ms_per_step=wall_e2e / a.steps),
                     gpu_launches=launches_per_step * a.steps,
                     roofline=dict(bound="hbm", kernel="demod_kernel (fused unpack+FFT+filter+IFFT+FM discriminator+post filters+sync scan)",
-                                  achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                                  achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
                                   bytes_per_sample=bytes_per_sample, kernel_ms=k_ms, kernel_msamples_per_s=planes_total / k_ms / 1e3,
                                   peak_source="MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"),
                     clocks=clk)
@@ -395,7 +400,6 @@ def main():
     ap.add_argument("--audio", action="store_true", help="also demodulate the two analog FM audio channels")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32", "mixed"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--h2d-chunks", type=int, default=4, help="e2e: pieces the capture upload is split into (overlapped with the kernel)")
     ap.add_argument("--ranges", type=int, default=1,
                     help="read-position ranges a step's capture is pipelined over (measured on B200: 1 is fastest -- the "
                          "persistent demodulation kernel of one range blocks the small kernels of the other)")

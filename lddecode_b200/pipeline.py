@@ -127,69 +127,6 @@ class CaptureDecoder:
                 res.audio = {'audio_left': a1l, 'audio_right': a1r}
         return res
 
-    def decode_host(self, cap_host, fmt, ncap, chunks=4, want_tables=False):
-        """The whole capture from (pinned) HOST memory: the capture is uploaded in `chunks` pieces on a copy
-        stream and the demodulation of the blocks that are complete is launched behind each piece, so the
-        upload overlaps the kernel.  cap_host: pinned host buffer (torch tensor) of unpacked samples
-        (u8 / s16 / u16).  Same result as decode()."""
-        rf, be = self.rf, self.rf._be
-        if be.name != "cuda" or fmt not in (_lib.FMT_U8, _lib.FMT_S16, _lib.FMT_U16) or chunks < 2:
-            dev = be.to_device(be.host_view(cap_host) if be.name == "cuda" else cap_host)
-            return self.decode(dev, fmt, ncap, want_tables)
-        torch = be.torch
-        S, N = self.stride, rf.blocklen
-        first_block, nblocks, walk_start = self.plan_range(ncap, 0, ncap + 1)
-        while nblocks > 0 and first_block + (nblocks - 1) * S + N > ncap:
-            nblocks -= 1
-        total = nblocks * S
-        res = RangeResult()
-        res.r0, res.r1, res.plane_origin, res.plane_len = 0, ncap + 1, 0, total
-        res.ncap_total, res.walk_start, res.staging = ncap, 0, self._staging
-        rf._set_mtf(self.mtf_level)
-        names = list(rf._alloc_planes(1)[0].keys())
-        planes = {nm: self._buf("plane_" + nm, max(total, 1), np.float64 if nm == 'demod_sync' else np.float32) for nm in names}
-        dev = self._buf("capture", ncap, be.host_view(cap_host).dtype)
-        a1l = a1r = None
-        alen, ds = 0, 1
-        if rf.decode_analog_audio:
-            ds = N // len(rf.Filters['audio_lfilt'])
-            alen = total // ds
-            a1l, a1r = self._buf("a1l", max(alen, 1), np.float64), self._buf("a1r", max(alen, 1), np.float64)
-        if "copy_stream" not in self._staging:
-            self._staging["copy_stream"] = be.new_stream()
-        cs = self._staging["copy_stream"]
-        main = be.current_stream_obj()
-        cs.wait_stream(main)
-        from .rfdecode import _PLANE_OF
-        done_blocks = 0
-        for c in range(chunks):
-            lo, hi = (c * ncap) // chunks, ((c + 1) * ncap) // chunks
-            with torch.cuda.stream(cs):
-                dev[lo:hi].copy_(cap_host[lo:hi], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(cs)
-            main.wait_event(ev)
-            # blocks whose last sample has arrived
-            upto = min(nblocks, max(0, (hi - N) // S + 1)) if hi >= N else 0
-            if c == chunks - 1:
-                upto = nblocks
-            nb = upto - done_blocks
-            if nb > 0:
-                k0 = done_blocks * S
-                parr = (C.c_void_p * 5)()
-                for nm in names:
-                    parr[_PLANE_OF[nm]] = be.ptr(planes[nm][k0:])
-                rf._check(be.lib.ldd_demod_blocks(rf._h, be.ptr(dev), fmt, 0, int(ncap), int(done_blocks * S), int(nb), int(total - k0),
-                                                  parr, be.ptr(a1l[k0 // ds:]) if a1l is not None else None,
-                                                  be.ptr(a1r[k0 // ds:]) if a1r is not None else None, int(alen - k0 // ds), be.stream()))
-                done_blocks = upto
-        res.planes = planes
-        res.pending_peaks = F.sync_peaks_launch(rf, planes['demod_sync'], total, 0, self._staging)
-        res.audio = None
-        if rf.decode_analog_audio:
-            res.audio = rf._audio_phase2_device(a1l, a1r, alen) if alen > rf.blocklen else {'audio_left': a1l, 'audio_right': a1r}
-        return self._finish_range(rf, res, want_tables)
-
     def _finish_range(self, rf, res, want_tables=False):
         """Stage 2: host walk over the peak list, then the batched refine + TBC launches."""
         planes, total, r0, r1 = res.planes, res.plane_len, res.r0, res.r1

@@ -346,7 +346,8 @@ def run_ours(a):
         launches_per_step = a.ranges * (1 + 4 + 1 + (1 if system == "PAL" else 2) + 1 + (2 if audio else 0)) + 4
         line = dict(metric="rf_msamples_per_s_demod_tbc", value=value, unit="Msamples/s", n_gpus=world, steps=a.steps,
                     warmup=max(a.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype=a.precision, data="synthetic", config=workload_config(system, audio, world),
+                    dtype={"mixed": "f32+f64", "f64": "f64", "f32": "f32"}[a.precision], data="synthetic",
+                    config=dict(workload_config(system, audio, world), precision=a.precision),
                     realtime_x=value / FS[system] / world, fields_per_step=nfields * world,
                     e2e=dict(value=e2e_val, unit="Msamples/s", h2d_bytes_per_step=int(ncap),
                              d2h_bytes_per_step=int(npic * 2), wall_ms_per_step=wall_e2e / a.steps),
@@ -398,7 +399,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--system", default="PAL", choices=["PAL", "NTSC"])
     ap.add_argument("--audio", action="store_true", help="also demodulate the two analog FM audio channels")
-    ap.add_argument("--precision", default="f64", choices=["f64", "f32", "mixed"])
+    ap.add_argument("--precision", default="mixed", choices=["f64", "f32", "mixed"],
+                    help="demodulation lane (DESIGN.md 3.1); 'mixed' is the library default")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     ap.add_argument("--ranges", type=int, default=1,
                     help="read-position ranges a step's capture is pipelined over (measured on B200: 1 is fastest -- the "

@@ -64,7 +64,7 @@ extern "C" {
 #define LDD_P_BURST 3
 #define LDD_P_PILOT 4
 
-#define LDD_PREC_F64 0     /* every transform in float64: the lane whose sync decisions are reference-exact */
+#define LDD_PREC_F64 0     /* every transform in float64: the reference-exact lane */
 #define LDD_PREC_F32 1     /* float32 shared-memory lane */
 #define LDD_PREC_MIXED 2   /* float32 lane, then float64 re-run of every block that holds a demod_05 sample within
                               a guard band (16 Hz, 8x the largest float32 error measured) of a sync threshold: the sync

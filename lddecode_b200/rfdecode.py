@@ -17,7 +17,7 @@ import scipy.signal as sps
 from . import _lib
 from ._backend import CudaBackend
 
-DEFAULT_PRECISION = 'f64'
+DEFAULT_PRECISION = 'mixed'
 
 # module-global loader, as in the reference (lddecode_core.py:387, assigned at lddecode.py:53-58):
 # loader(infile, sample, readlen) -> array | None

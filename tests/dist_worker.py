@@ -20,7 +20,7 @@ def main():
     fs = 8 * 315 / 88
     ncap = 2600000
     cap = synth.SynthRF("NTSC", fs, seed=9).generate(ncap)
-    rf = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=False, _backend=be)
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=False, _backend=be, precision="f64")
     cd = pipeline.CaptureDecoder(rf)
     r0, r1 = parallel.shard_bounds(ncap, world)[rank]
     lo, hi = parallel.needed_window(cd, ncap, r0, r1)

@@ -32,7 +32,7 @@ def _close_hz(actual, desired, rtol=RTOL_HZ):
 @pytest.mark.parametrize("name", ["ntsc", "pal", "ntsc10"])
 def test_demodblock_golden(backend, golden, name):
     g = golden(name)
-    rf = rfdecode.RFDecode(float(g["fs_mhz"]), _system(g), int(g["blocklen"]), _backend=backend)
+    rf = rfdecode.RFDecode(float(g["fs_mhz"]), _system(g), int(g["blocklen"]), _backend=backend, precision="f64")
     cap = g["capture"]
     for bi in range(3):
         pos, mtf = int(g["blk%d_pos" % bi]), float(g["blk%d_mtf" % bi])
@@ -51,7 +51,7 @@ def test_demodblock_golden(backend, golden, name):
 def test_demod_stitched_golden(backend, golden, name):
     g = golden(name)
     N = int(g["blocklen"])
-    rf = rfdecode.RFDecode(float(g["fs_mhz"]), _system(g), N, _backend=backend)
+    rf = rfdecode.RFDecode(float(g["fs_mhz"]), _system(g), N, _backend=backend, precision="f64")
     cap = g["capture"]
     rfdecode.loader = _mem_loader(cap)
     video, audio = rf.demod(None, 0, int(g["demod_length"]), 1)
@@ -80,7 +80,7 @@ def test_sync_decisions_bit_exact_vs_oracle(backend):
     sample for sample: recover it from demod_05 and compare with the oracle on a fresh seed."""
     fs = 8 * 315 / 88
     cap = synth.SynthRF("NTSC", fs, seed=11).generate(200000)
-    rf = rfdecode.RFDecode(fs, "NTSC", 16384, _backend=backend)
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, _backend=backend, precision="f64")
     rfdecode.loader = _mem_loader(cap)
     video, _ = rf.demod(None, 0, 150000, 0)
     dec = O.Decoder(fs, "NTSC", 16384)
@@ -97,7 +97,7 @@ def test_packed_input_formats(backend, fmt):
     from lddecode_b200 import _lib
     fs = 8 * 315 / 88
     s10 = synth.SynthRF("NTSC", fs, seed=5, bits=10).generate(60000)
-    rf = rfdecode.RFDecode(fs, "NTSC", 16384, _backend=backend)
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, _backend=backend, precision="f64")
     start, length = 4000, 30000
     ref = rf.demod_device(backend.to_device(s10), _lib.FMT_U16, 0, len(s10), start, length, 0, phase2=False).to_recarrays()
     if fmt == "r30":

@@ -14,7 +14,7 @@ from oracle import ldd_oracle as O
 
 def _setup(backend, g, name):
     system = "PAL" if name == "pal" else "NTSC"
-    rf = rfdecode.RFDecode(float(g["fs_mhz"]), system, int(g["blocklen"]), _backend=backend)
+    rf = rfdecode.RFDecode(float(g["fs_mhz"]), system, int(g["blocklen"]), _backend=backend, precision="f64")
     cap = g["capture"]
     fmt = _lib.FMT_U8 if cap.dtype == np.uint8 else _lib.FMT_U16
     dd = rf.demod_device(backend.to_device(cap), fmt, 0, len(cap), 0, int(g["demod_length"]), 1)
@@ -69,7 +69,7 @@ def test_sync_peaks_bit_exact_random_planes(backend):
     """get_syncpeaks against the oracle on planes that make chains merge late or never:
     noise, silence, and a real sync plane, for several segment sizes and start offsets."""
     fs = 8 * 315 / 88
-    rf = rfdecode.RFDecode(fs, "NTSC", 16384, _backend=backend)
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, _backend=backend, precision="f64")
     rng = np.random.default_rng(7)
     planes = [rng.uniform(0, 0.5, 300000), np.zeros(100000), rng.uniform(0, 0.21, 200000),
               np.clip(np.sin(np.arange(250000) * 0.00345) + rng.normal(0, .05, 250000), 0, 1)]
@@ -101,7 +101,7 @@ def test_field_early_outs(backend):
     from lddecode_b200 import synth
     fs = 8 * 315 / 88
     cap = synth.SynthRF("NTSC", fs, seed=2, lead_lines=120).generate(700000)
-    rf = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=False, _backend=backend)
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=False, _backend=backend, precision="f64")
     dec = O.Decoder(fs, "NTSC", 16384, analog_audio=False)
     ld = lambda s, n: cap[s:s + n] if s + n <= len(cap) else None
     for length in (150000, 500000):          # no vsync at all / exactly one vsync

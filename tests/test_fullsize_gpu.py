@@ -23,7 +23,7 @@ def test_one_second_ntsc_properties(cuda_backend, ntsc_second):
     fs, s10 = ntsc_second
     ncap = len(s10) // 12 * 12
     s10 = s10[:ncap]
-    rf = rfdecode.RFDecode(fs, "NTSC", 16384, _backend=be)
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, precision="f64", _backend=be)
     cd = pipeline.CaptureDecoder(rf, max_fields=256)
     dev = be.to_device(s10)
     res = cd.decode(dev, _lib.FMT_U16, ncap)

@@ -26,12 +26,16 @@ def _oracle_walk(dec, cap, nmax=10):
     return out
 
 
+@pytest.mark.parametrize("precision", ["f64", "mixed"])
 @pytest.mark.parametrize("system", ["NTSC", "PAL"])
-def test_pipeline_matches_reference_flow(backend, system):
+def test_pipeline_matches_reference_flow(backend, system, precision):
     fs = 8 * 315 / 88 if system == "NTSC" else 35.46895
     ncap = 2100000 if system == "NTSC" else 2600000
     cap = synth.SynthRF(system, fs, seed=9).generate(ncap)
-    rf = rfdecode.RFDecode(fs, system, 16384, decode_analog_audio=False, _backend=backend)
+    rf = rfdecode.RFDecode(fs, system, 16384, decode_analog_audio=False, _backend=backend, precision=precision)
+    # the exact lane is held to 1e-5 samples / 0.2 % of TBC samples differing; the mixed (default) lane to
+    # the north-star bars: identical peak lists and integer line tables, TBC within +-1 LSB
+    ll_tol, frac = (1e-5, 0.002) if precision == "f64" else (2e-3, 1.0)
     dec = O.Decoder(fs, system, 16384, analog_audio=False)
     cd = pipeline.CaptureDecoder(rf)
     res = cd.decode(backend.to_device(cap), _lib.FMT_U8, ncap, want_tables=True)
@@ -47,10 +51,10 @@ def test_pipeline_matches_reference_flow(backend, system):
         nll = f.linecount + 4
         np.testing.assert_array_equal(res.linelocs1[k][:nll], np.array(f.linelocs1))
         j = res.located.index(k)
-        np.testing.assert_allclose(res.refined.linelocs2[j][:nll], f.linelocs2, rtol=0, atol=1e-5)
-        np.testing.assert_allclose(res.refined.final[j][:nll] + res.refined.lineloc_add, f.linelocs, rtol=0, atol=1e-5)
+        np.testing.assert_allclose(res.refined.linelocs2[j][:nll], f.linelocs2, rtol=0, atol=ll_tol)
+        np.testing.assert_allclose(res.refined.final[j][:nll] + res.refined.lineloc_add, f.linelocs, rtol=0, atol=ll_tol)
         d = pics[j][2].astype(np.int64) - f.dspicture.astype(np.int64)
-        assert np.abs(d).max() <= 1 and np.count_nonzero(d) < 0.002 * d.size
+        assert np.abs(d).max() <= 1 and np.count_nonzero(d) <= frac * d.size
 
 
 def test_ranges_are_bit_identical_to_one_range(backend):
@@ -60,7 +64,7 @@ def test_ranges_are_bit_identical_to_one_range(backend):
     fs = 8 * 315 / 88
     ncap = 2600000
     cap = synth.SynthRF("NTSC", fs, seed=9).generate(ncap)
-    rf = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=False, _backend=backend)
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=False, _backend=backend, precision="f64")
     cd = pipeline.CaptureDecoder(rf)
     one = cd.pictures(cd.decode(backend.to_device(cap), _lib.FMT_U8, ncap))
     parts = []
@@ -79,7 +83,7 @@ def test_pipelined_ranges_equal_single_decode(backend):
     fs = 8 * 315 / 88
     ncap = 2600000
     cap = synth.SynthRF("NTSC", fs, seed=9).generate(ncap)
-    rf = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=False, _backend=backend)
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=False, _backend=backend, precision="f64")
     cd = pipeline.CaptureDecoder(rf)
     capd = backend.to_device(cap)
     one = cd.pictures(cd.decode(capd, _lib.FMT_U8, ncap))

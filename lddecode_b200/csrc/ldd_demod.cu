@@ -113,17 +113,17 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
     const Cx<T>* WN = (const Cx<T>*)p.WN;
     const Cx<T>* Hv = (const Cx<T>*)p.Hv;
 
+    // PAD <=> the block arrays live in shared memory (decided at compile time so that the compiler can
+    // keep every derived pointer in the shared address space: LDS/STS with 32-bit addresses instead of
+    // generic loads with 64-bit address arithmetic)
+    LDD_DYN_SMEM(smem);
     Cx<T>* b0;
     Cx<T>* sp = nullptr;
-    if (p.scratch) {
-        b0 = (Cx<T>*)((char*)p.scratch + (size_t)blockIdx.x * p.scratch_per_cta);
-        if (SP) {
-            LDD_DYN_SMEM(smem);
-            sp = (Cx<T>*)smem;
-        }
-    } else {
-        LDD_DYN_SMEM(smem);
+    if (PAD) {
         b0 = (Cx<T>*)smem;
+    } else {
+        b0 = (Cx<T>*)((char*)p.scratch + (size_t)blockIdx.x * p.scratch_per_cta);
+        if (SP) sp = (Cx<T>*)smem;
     }
     const bool sp_ok = SP && (p.plan_m.npass & 1) == 0;
     // length-M transform of `a`; `other` is a free array usable as the partner when shared memory is not

@@ -217,7 +217,7 @@ def run_ours(a):
     cap_dev = torch.from_numpy(cap).cuda()
     cap_pin = torch.from_numpy(cap).pin_memory()
     stream = torch.cuda.current_stream()
-    max_fields = 80
+    max_fields = 64
 
     def barrier():
         if world > 1:
@@ -226,33 +226,48 @@ def run_ours(a):
 
     gatherer = parallel.FieldGatherer(cd, rank, world, max_fields, dist) if world > 1 else None
 
-    def decode(dev):
-        # one capture per step; inside the step it is split into read-position ranges whose host walks
-        # overlap the device work of the other ranges (bit-identical to the single-range decode)
+    def run_resident(nsteps):
+        # K decodes of the HBM-resident capture through CaptureDecoder.decode_stream: the demodulation of
+        # step k+1 is enqueued before the host walks the fields of step k (same results as decode())
+        res = None
         if a.ranges > 1:
-            return cd.decode_pipelined(dev, _lib.FMT_U8, ncap, a.ranges)
-        return [cd.decode(dev, _lib.FMT_U8, ncap)]
+            for _ in range(nsteps):
+                res = cd.decode_pipelined(cap_dev, _lib.FMT_U8, ncap, a.ranges)
+                if world > 1:
+                    gatherer.gather(res)
+            return res
+        for res in cd.decode_stream((cap_dev, _lib.FMT_U8, ncap) for _ in range(nsteps)):
+            if world > 1:
+                gatherer.gather(res)    # NCCL gather of the uint16 fields + positions into rank 0's HBM
+        return [res]
 
-    def step_resident():
-        res = decode(cap_dev)
-        if world > 1:
-            gatherer.gather(res)        # NCCL gather of the uint16 fields + positions into rank 0's HBM
-        return res
+    # end to end: the public host-buffer API (pipeline.HostStreamDecoder).  Every step uploads its
+    # capture from pinned host memory and downloads its uint16 fields into pinned host memory; the
+    # upload of step k+1 and the download of step k-1 overlap the decode of step k.
+    sd = pipeline.HostStreamDecoder(cd, _lib.FMT_U8, ncap, max_fields)
 
-    def step_e2e(out_pin):
-        d = cap_pin.cuda(non_blocking=True)                         # H2D of the step's input
-        res = decode(d)
-        n = 0
-        for r in res:
-            m = len(r.located) * r.out_stride
-            out_pin[n:n + m].copy_(r.d_pic[:m], non_blocking=True)  # D2H of the step's result
-            n += m
-            if r.audio is not None:
-                r.audio_host = (r.audio['audio_left'].cpu(), r.audio['audio_right'].cpu())
+    def run_e2e(nsteps):
+        npic = 0
+        pend = sd.launch(sd.upload(cap_pin, ncap))                  # H2D of the first step's input
+        t = sd.upload(cap_pin, ncap) if nsteps > 1 else None
+        prev = None
+        for i in range(nsteps):
+            nxt = sd.launch(t) if t is not None else None           # demodulation of step i+1 ...
+            t = sd.upload(cap_pin, ncap) if i + 2 < nsteps else None
+            job = sd.finish(pend)                                   # ... under the host walk of step i; D2H of its fields
+            pend = nxt
+            if job[0].audio is not None:
+                job[0].audio_host = (job[0].audio['audio_left'].cpu(), job[0].audio['audio_right'].cpu())
+            if world > 1:
+                gatherer.gather(job[0])
+            if prev is not None:
+                _, pics = sd.fetch(prev)                            # host reads the previous step's result
+                npic = pics.size
+            prev = job
+        _, pics = sd.fetch(prev)
         if world > 1:
-            gatherer.gather(res)
-        torch.cuda.current_stream().synchronize()
-        return res, n
+            gatherer.wait()
+        return pics.size
 
     # the sampler is started before the warm-up: nvidia-smi's start-up stalls the driver for ~100 ms
     clocks = ClockSampler(local)
@@ -261,36 +276,33 @@ def run_ours(a):
         time.sleep(0.5)
     # warm-up
     res = None
-    for _ in range(max(a.warmup, 3)):
-        res = step_resident()
+    res = run_resident(max(a.warmup, 3))
     torch.cuda.synchronize()
     nfields = sum(len(r.located) for r in res)
     # samples of the capture demodulated and decoded per step (each counted once: neither the block
     # overlaps nor the halos that neighbouring ranges demodulate twice are counted)
     S_ = cd.stride
     consumed = ((ncap - BLOCKLEN) // S_ + 1) * S_
-    out_pin = torch.empty(max_fields * res[0].out_stride, dtype=torch.uint16).pin_memory()
 
     # resident timing
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.time()
     e0.record()
-    for _ in range(a.steps):
-        step_resident()
+    run_resident(a.steps)
+    if world > 1:
+        gatherer.wait()
     e1.record()
     barrier()
     tw1 = time.time()
     ms_total = e0.elapsed_time(e1)
 
     # end-to-end timing (host buffers)
-    for _ in range(2):
-        step_e2e(out_pin)
+    run_e2e(2)
     barrier()
     t0 = time.perf_counter()
     e0.record()
-    for _ in range(a.steps):
-        _, npic = step_e2e(out_pin)
+    npic = run_e2e(a.steps)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)

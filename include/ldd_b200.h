@@ -177,6 +177,12 @@ int ldd_audio_phase2(ldd_handle* h, const double* in_l_dev, const double* in_r_d
 int ldd_sync_peaks(ldd_handle* h, const double* sync_dev, long long n, long long start,
                    long long* peaks_dev, double* vals_dev, int cap, int* count_dev, void* stream);
 
+/* HOST function, same algorithm and result as ldd_sync_peaks for samples that are already in host
+ * memory (sync_host[0..n)); used by the field walk for the short prefix of a window that does not
+ * start on a peak of the capture-wide chase.  count receives the number of peaks found (> cap: truncated). */
+int ldd_sync_peaks_host(ldd_handle* h, const double* sync_host, long long n, long long start,
+                        long long* peaks, double* vals, int cap, int* count);
+
 /* ---- field location (lddecode_core.py:518-787, 889-957, 962-1021, 1054-1133) -------------------- */
 #define LDD_FIELD_NOVSYNC 0    /* len(vsyncs) == 0: not a field, nextfieldoffset = start + 200 lines          */
 #define LDD_FIELD_SHORT 1      /* one vsync / too few peaks after the second: jump, not valid                 */

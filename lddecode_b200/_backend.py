@@ -85,6 +85,9 @@ class CudaBackend:
     def wait_event(self, ev):
         ev.synchronize()
 
+    def stream_wait_event(self, stream, ev):
+        stream.wait_event(ev)
+
     def host_view(self, pinned_buf):
         return pinned_buf.numpy()
 
@@ -155,6 +158,9 @@ class EmuBackend:
         return None
 
     def wait_event(self, ev):
+        pass
+
+    def stream_wait_event(self, stream, ev):
         pass
 
     def host_view(self, pinned_buf):

@@ -273,3 +273,33 @@ extern "C" int ldd_sync_peaks(ldd_handle* h, const double* sync_dev, long long n
                (const int*)cnt, (const long long*)iend, (const int*)any_unmerged, peaks_dev, vals_dev, cap, count_dev);
     return launch_status(h, "peaks_phase1/2");
 }
+
+// HOST restatement of the same chase for short windows whose samples are already in host memory (the
+// field walk's off-peak window starts, pipeline.py): comparisons only, so it returns exactly the list
+// the kernels above return for the same samples.
+extern "C" int ldd_sync_peaks_host(ldd_handle* h, const double* sync_host, long long n, long long start,
+                                   long long* peaks, double* vals, int cap, int* count) {
+    if (!h || !sync_host || !peaks || !vals || !count || n < 0 || start < 0 || cap < 0) return LDD_EINVAL;
+    const int L = h->cfg.linelen;
+    const long long limit = n - 2LL * L;
+    const int half = L / 2, skip = (int)(L * .4);
+    long long i = start;
+    int c = 0;
+    while (i < limit) {
+        const double* w = sync_host + i;
+        double best = -1e300;
+        int at = 0;
+        for (int k = 0; k < half; ++k)
+            if (w[k] > best) { best = w[k]; at = k; }
+        if (best > .2) {
+            if (c < cap) { peaks[c] = i + at; vals[c] = best; }
+            ++c;
+            i += at + skip;
+        } else {
+            i += half;
+        }
+    }
+    *count = c;
+    return LDD_OK;
+}
+

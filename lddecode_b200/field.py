@@ -85,6 +85,31 @@ def sync_peaks_device(rf, sync_buf, n, start=0, staging=None):
     return sync_peaks_launch(rf, sync_buf, n, start, staging).result()
 
 
+def sync_peaks_prefix_host(rf, sync_buf, n, staging):
+    """The same chase for a short stretch of the plane, done on the HOST: the samples come over on a
+    side stream (a copy engine, so the transfer does not queue behind kernels already enqueued on the
+    main stream -- the whole-capture pipeline has the next capture's demodulation in flight at this
+    point) and ldd_sync_peaks_host runs the comparisons.  The caller guarantees that sync_buf[:n] is
+    complete (it has seen the result of a later operation on the producing stream)."""
+    be = rf._be
+    st = staging
+    if st.get('hcap', 0) < n:
+        st['hcap'] = int(n)
+        st['h_sync'] = be.pinned(n, np.float64)
+        st['side'] = st.get('side') or be.new_stream()
+        cap = int(n // int(rf.linelen * .4)) + 8
+        st['hpk'], st['hvl'] = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.float64)
+    with be.stream_ctx(st['side']):
+        be.copy_async(st['h_sync'][:n], sync_buf[:n])
+        ev = be.record_event()
+    be.wait_event(ev)
+    cnt = C.c_int(0)
+    hs = be.host_view(st['h_sync'])
+    rf._check(be.lib.ldd_sync_peaks_host(rf._h, _h(hs), int(n), 0, _h(st['hpk']), _h(st['hvl']), len(st['hpk']), C.byref(cnt)))
+    c = min(cnt.value, len(st['hpk']))
+    return st['hpk'][:c].copy(), st['hvl'][:c].copy()
+
+
 def locate(rf, peaks, vals, window_len, start=0):
     """ldd_field_locate for one window -> (FieldInfo, linelocs1, linebad)."""
     info = _lib.FieldInfo()
@@ -101,7 +126,7 @@ class RefinedBatch:
     pass
 
 
-def refine_and_tbc(rf, planes, plane_len, batch, colorlevel=1.45, colorphase=91.5, want_intermediates=True):
+def refine_and_tbc(rf, planes, plane_len, batch, colorlevel=1.45, colorphase=91.5, want_intermediates=True, staging=None):
     """Device part of FieldNTSC/FieldPAL.__init__ for every located field of `batch`.
 
     planes: dict name -> device buffer (as in DeviceDemod.planes).  Returns a RefinedBatch with
@@ -113,7 +138,18 @@ def refine_and_tbc(rf, planes, plane_len, batch, colorlevel=1.45, colorphase=91.
     maxlc = int(batch.linecount.max()) if n else 0
     out.out_stride = (rf.SysParams['frame_lines'] // 2 + 1) * W
     # one host->device copy for all per-field tables: [base | winlen | linelocs1 | linecount | linebad]
-    pk = np.empty(n * (8 + 8 + 8 * LL_STRIDE + 4 + LL_STRIDE) + 64, dtype=np.uint8)
+    # (through a pinned buffer of `staging` when given, so that the host does not wait for the stream)
+    npk = n * (8 + 8 + 8 * LL_STRIDE + 4 + LL_STRIDE) + 64
+    if staging is not None:
+        if staging.get('tbl_cap', 0) < npk:
+            staging['tbl_cap'] = npk + npk // 2
+            staging['tbl'] = be.pinned(staging['tbl_cap'], np.uint8)
+            staging['tbl_ev'] = None
+        if staging['tbl_ev'] is not None:
+            be.wait_event(staging['tbl_ev'])        # the previous upload from this buffer has been executed
+        pk = be.host_view(staging['tbl'])[:npk]
+    else:
+        pk = np.empty(npk, dtype=np.uint8)
     o_base, o_win = 0, 8 * n
     o_l1 = 16 * n
     o_lc = o_l1 + 8 * n * LL_STRIDE
@@ -123,7 +159,12 @@ def refine_and_tbc(rf, planes, plane_len, batch, colorlevel=1.45, colorphase=91.
     pk[o_l1:o_l1 + 8 * n * LL_STRIDE] = np.ascontiguousarray(batch.linelocs1).reshape(-1).view(np.uint8)
     pk[o_lc:o_lc + 4 * n] = batch.linecount.view(np.uint8)
     pk[o_bad:o_bad + n * LL_STRIDE] = np.ascontiguousarray(batch.linebad).reshape(-1)
-    d_pk = be.to_device(pk)
+    if staging is not None:
+        d_pk = be.empty(npk, np.uint8)
+        be.copy_async(d_pk, staging['tbl'][:npk])
+        staging['tbl_ev'] = be.record_event()
+    else:
+        d_pk = be.to_device(pk)
     d_base = d_pk[o_base:o_base + 8 * n].view(be.dtype_of(np.int64))
     d_win = d_pk[o_win:o_win + 8 * n].view(be.dtype_of(np.int64))
     d_l1 = d_pk[o_l1:o_l1 + 8 * n * LL_STRIDE].view(be.dtype_of(np.float64))

@@ -26,8 +26,9 @@ def needed_window(cd, ncap, r0, r1):
 
 class FieldGatherer:
     """Gathers the located fields of every rank on rank 0.  Buffers are allocated once; gather()
-    only enqueues device work (a copy into the send buffer and two collectives), to_host() turns the
-    gathered buffers into a list of (readsample, istop, picture | None) ordered by read position."""
+    only enqueues device work (a copy into the send buffer and two asynchronous collectives), to_host()
+    turns the gathered buffers into a list of (readsample, istop, picture | None) ordered by read
+    position; call it before the next gather() overwrites them."""
 
     def __init__(self, cd, rank, world, max_fields, dist=None):
         import torch
@@ -46,6 +47,7 @@ class FieldGatherer:
             self.metas = [torch.empty_like(self.meta) for _ in range(world)]
         else:
             self.pics, self.metas = [self.pic], [self.meta]
+        self._work = []
 
     def gather(self, results):
         """results: one RangeResult or the list decode_pipelined returns."""
@@ -65,6 +67,7 @@ class FieldGatherer:
             spans.append((k0, nloc, res))
             k0 += nloc
         tm = torch.from_numpy(meta)
+        self.wait()
         if self.cuda:
             self.meta.copy_(tm, non_blocking=True)
             for k0, nloc, res in spans:
@@ -79,10 +82,21 @@ class FieldGatherer:
                         torch.from_numpy(self.be.to_host(res.d_pic)[:nloc * self.stride].view(np.uint8))
             self.meta.copy_(tm)
         if self.world > 1:
-            self.dist.gather(self.pic, self.pics if self.rank == 0 else None, dst=0)
-            self.dist.gather(self.meta, self.metas if self.rank == 0 else None, dst=0)
+            # asynchronous: the collectives run on the process group's own stream behind the copies
+            # above, so the next range's demodulation overlaps them; wait() orders the caller's
+            # stream (not the host) behind them
+            self._work = [self.dist.gather(self.pic, self.pics if self.rank == 0 else None, dst=0, async_op=True),
+                          self.dist.gather(self.meta, self.metas if self.rank == 0 else None, dst=0, async_op=True)]
+
+    def wait(self):
+        """Order the current stream behind the last gather (called before the send buffers are rewritten
+        and before the gathered buffers are read)."""
+        for w in self._work:
+            w.wait()
+        self._work = []
 
     def to_host(self):
+        self.wait()
         if self.rank != 0:
             return None
         out = []

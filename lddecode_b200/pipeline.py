@@ -35,6 +35,102 @@ class RangeResult:
     pass
 
 
+class HostStreamDecoder:
+    """A sequence of host-resident captures (the chunks a file reader produces) through one
+    CaptureDecoder, software-pipelined: while the host walks the fields of chunk k the GPU already
+    demodulates chunk k+1 (same stream, second plane workspace), and the upload of chunk k+2 and the
+    download of chunk k-1's fields run on their own streams.  Device input, planes and pinned output
+    are double-buffered.  Results are those of CaptureDecoder.decode() of every chunk.
+
+        for res, pics in sd.run(chunks): ...                    # or, step by step:
+        t = sd.upload(buf, n); p = sd.launch(t); job = sd.finish(p); res, pics = sd.fetch(job)
+
+    upload() takes a pinned host buffer (be.pinned).  fetch() returns the RangeResult and a host view
+    [nfields, out_stride] of its uint16 fields that stays valid until the second-next finish(); the
+    RangeResult's device planes stay valid until the second-next launch()."""
+
+    def __init__(self, cd, fmt, ncap_max, max_fields=96, np_dtype=np.uint8):
+        self.cd, self.fmt, self.max_fields = cd, fmt, max_fields
+        rf = cd.rf
+        be = self.be = rf._be
+        self.up, self.down = be.new_stream(), be.new_stream()
+        self.out_stride = (rf.SysParams['frame_lines'] // 2 + 1) * rf.SysParams['outlinelen']
+        self.d_in = [be.empty(ncap_max, np_dtype) for _ in range(2)]
+        self.h_out = [be.pinned(max_fields * self.out_stride, np.uint16) for _ in range(2)]
+        self.h_status = [be.pinned(max_fields, np.int32) for _ in range(2)]
+        self.in_free = [None, None]         # event: the demodulation that read d_in[k] has finished
+        self.nup = self.nlaunch = self.nfin = 0
+
+    def upload(self, host_buf, n):
+        be, k = self.be, self.nup % 2
+        self.nup += 1
+        if self.in_free[k] is not None:
+            be.stream_wait_event(self.up, self.in_free[k])
+        with be.stream_ctx(self.up):
+            be.copy_async(self.d_in[k][:n], host_buf[:n])
+            ev = be.record_event()
+        return (k, int(n), ev)
+
+    def launch(self, ticket):
+        """Enqueue the demodulation and the sync-peak chase of an uploaded chunk."""
+        be, cd = self.be, self.cd
+        k, n, ev = ticket
+        be.stream_wait_event(be.current_stream_obj(), ev)
+        ws, staging = cd._lane(self.nlaunch % 2)
+        self.nlaunch += 1
+        pend = cd._launch_demod(cd.rf, ws, staging, self.d_in[k], self.fmt, 0, n, n, 0, n + 1)
+        self.in_free[k] = be.record_event()
+        return pend
+
+    def finish(self, pend):
+        """Host walk, refinement and TBC of a launched chunk; starts the download of its fields."""
+        be = self.be
+        res = self.cd._finish_range(self.cd.rf, pend)
+        j = self.nfin % 2
+        self.nfin += 1
+        nloc = len(res.located)
+        if nloc > self.max_fields:
+            raise ValueError("max_fields too small")
+        dev = None
+        if nloc:
+            done = be.record_event()
+            be.stream_wait_event(self.down, done)
+            with be.stream_ctx(self.down):
+                be.copy_async(self.h_out[j][:nloc * self.out_stride], res.d_pic[:nloc * self.out_stride])
+                be.copy_async(self.h_status[j][:nloc], res.d_status[:nloc])
+                dev = be.record_event()
+        return (res, j, nloc, dev)
+
+    def decode(self, ticket):
+        return self.finish(self.launch(ticket))
+
+    def fetch(self, job):
+        res, j, nloc, dev = job
+        if dev is not None:
+            self.be.wait_event(dev)
+        res.status_host = self.be.host_view(self.h_status[j])[:nloc]
+        return res, self.be.host_view(self.h_out[j])[:nloc * self.out_stride].reshape(nloc, self.out_stride)
+
+    def run(self, chunks):
+        """chunks: iterable of (pinned host buffer, length).  Yields (RangeResult, host pictures) per chunk."""
+        it = iter(chunks)
+        up = lambda: (lambda c: self.upload(*c) if c is not None else None)(next(it, None))
+        t = up()
+        if t is None:
+            return
+        pend, t = self.launch(t), up()
+        prev = None
+        while pend is not None:
+            nxt = self.launch(t) if t is not None else None     # GPU demodulates chunk k+1 ...
+            if t is not None:
+                t = up()
+            job = self.finish(pend)                              # ... while the host walks chunk k
+            if prev is not None:
+                yield self.fetch(prev)
+            prev, pend = job, nxt
+        yield self.fetch(prev)
+
+
 class CaptureDecoder:
     def __init__(self, rf, readlen=READLEN, mtf_level=1, colorlevel=1.45, colorphase=91.5, max_fields=8192):
         self.rf = rf
@@ -49,6 +145,37 @@ class CaptureDecoder:
         self._ws = {}
         self._staging = {}
         self._lanes = None          # extra (RFDecode, stream, workspace, staging) sets of decode_pipelined
+        self._lane2 = None          # second workspace of decode_stream / HostStreamDecoder
+
+    def _lane(self, i):
+        """Workspace + staging set i (0 = the default one); a second set lets the demodulation of the
+        next capture run while the fields of the current one are still being walked and resampled."""
+        if i == 0:
+            return self._ws, self._staging
+        if self._lane2 is None:
+            self._lane2 = ({}, {})
+        return self._lane2
+
+    def decode_stream(self, captures):
+        """Software-pipelined decode() of a sequence of device-resident captures [(cap_dev, fmt, ncap), ...]:
+        capture k+1 is demodulated while the host walks capture k (one stream, two plane workspaces).
+        Yields one RangeResult per capture; its device buffers stay valid until the second-next launch."""
+        it = iter(captures)
+        k = 0
+
+        def launch(c):
+            nonlocal k
+            ws, staging = self._lane(k % 2)
+            k += 1
+            return self._launch_demod(self.rf, ws, staging, c[0], c[1], 0, c[2], c[2], 0, c[2] + 1)
+
+        c = next(it, None)
+        pend = launch(c) if c is not None else None
+        while pend is not None:
+            c = next(it, None)
+            nxt = launch(c) if c is not None else None
+            yield self._finish_range(self.rf, pend)
+            pend = nxt
 
     def _buf(self, tag, n, dtype, ws=None):
         ws = self._ws if ws is None else ws
@@ -152,7 +279,8 @@ class CaptureDecoder:
         if len(located):
             idx = owned[located]
             sub = F.FieldBatch.view(rf, batch, idx, np.fromiter((infos[i].linecount for i in idx), dtype=np.int32, count=len(idx)))
-            ref = F.refine_and_tbc(rf, planes, total, sub, self.colorlevel, self.colorphase, want_intermediates=want_tables)
+            ref = F.refine_and_tbc(rf, planes, total, sub, self.colorlevel, self.colorphase, want_intermediates=want_tables,
+                                   staging=res.staging)
             res.refined = ref
             res.d_pic, res.d_status = ref.d_pic, ref.d_status
         return res
@@ -217,7 +345,7 @@ class CaptureDecoder:
             b, wl = int(b), int(wl)
             pk = vl = None
             npre = min(wl, 40 * L)
-            spk, svl = F.sync_peaks_device(rf, planes['demod_sync'][b:b + npre], npre, 0, cb_staging)
+            spk, svl = F.sync_peaks_prefix_host(rf, planes['demod_sync'][b:b + npre], npre, cb_staging)
             pos = np.searchsorted(gpk, spk + b)
             common = np.nonzero(gpk[np.minimum(pos, len(gpk) - 1)] == spk + b)[0] if len(gpk) else np.zeros(0, dtype=np.int64)
             if len(common):

@@ -84,6 +84,13 @@ def test_sync_peaks_bit_exact_random_planes(backend):
                     ref = O.sync_peaks(ds, start, rf.linelen)
                     assert np.array_equal(pk, np.array(ref, dtype=np.int64))
                     assert np.array_equal(vl, ds[ref] if len(ref) else np.zeros(0))
+        # the host restatement the field walk uses for short prefixes returns the same lists
+        for ds in planes:
+            buf = backend.to_device(np.ascontiguousarray(ds))
+            n = 90000
+            pk, vl = field.sync_peaks_device(rf, buf[:n], n, 0)
+            hpk, hvl = field.sync_peaks_prefix_host(rf, buf[:n], n, {})
+            assert np.array_equal(pk, hpk) and np.array_equal(vl, hvl)
         # shorter than two lines: empty list
         buf = backend.to_device(np.ones(3000))
         pk, _ = field.sync_peaks_device(rf, buf, 3000, 0)

@@ -95,6 +95,35 @@ def test_pipelined_ranges_equal_single_decode(backend):
         assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2])
 
 
+def test_host_stream_decoder_equals_decode(backend):
+    """HostStreamDecoder (uploads / downloads on their own streams, double-buffered) returns for every
+    chunk exactly what decode() of that chunk returns, also when buffers are reused."""
+    fs = 8 * 315 / 88
+    n = 1300000
+    caps = [synth.SynthRF("NTSC", fs, seed=s).generate(n) for s in (9, 10)]
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=False, _backend=backend, precision="mixed")
+    cd = pipeline.CaptureDecoder(rf)
+    want = cd.pictures(cd.decode(backend.to_device(caps[1]), _lib.FMT_U8, n))
+    pins = []
+    for c in caps:
+        p = backend.pinned(n, np.uint8)
+        backend.host_view(p)[:] = c
+        pins.append(p)
+    sd = pipeline.HostStreamDecoder(cd, _lib.FMT_U8, n, max_fields=8)
+    got = []
+    for res, pics in sd.run([(pins[0], n), (pins[1], n), (pins[0], n)]):
+        assert not np.any(res.status_host & 15)
+        got.append([(int(res.readsamples[j]), int(res.infos[j].istop), pics[k, :res.infos[j].linecount * 910].copy())
+                    for k, j in enumerate(res.located)])
+    assert len(got) == 3 and len(got[1]) == len(want) >= 1
+    for a, b in zip(got[1], want):
+        assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2])
+    assert len(got[0]) == len(got[2])
+    for a, b in zip(got[0], got[2]):
+        assert a[0] == b[0] and np.array_equal(a[2], b[2])
+    assert not np.array_equal(got[0][0][2], got[1][0][2])
+
+
 def test_two_rank_gloo_gather():
     """world_size 2 over gloo on the CPU (emulated kernels): shard, decode, gather on rank 0."""
     script = os.path.join(ROOT, "tests", "dist_worker.py")

@@ -105,10 +105,12 @@ __device__ inline void tangle(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __restrict_
 // SP: the block arrays live in the global scratch and a padded shared-memory buffer is the ping-pong
 // partner of every length-M transform (every second Stockham pass stays on chip: the float64 lane is
 // bound by L2 traffic, ~7 TB/s chip-wide at 9 Gsamples/s).
-template <class T, int NT, bool PAD, int MINB = 1, bool SP = false>
+// CM != 0: the transform length M is the compile-time constant CM (and blockDim.x == NT, plan = radix 16
+// while possible): the default block length gets fully constant-folded indexing.
+template <class T, int NT, bool PAD, int MINB = 1, bool SP = false, int CM = 0>
 __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int N = p.N, M = p.M;
+    const int tid = threadIdx.x, nthr = CM ? NT : (int)blockDim.x;
+    const int M = CM ? CM : p.M, N = CM ? 2 * CM : p.N;
     const Cx<T>* WM = (const Cx<T>*)p.WM;
     const Cx<T>* WN = (const Cx<T>*)p.WN;
     const Cx<T>* Hv = (const Cx<T>*)p.Hv;
@@ -125,17 +127,31 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         b0 = (Cx<T>*)((char*)p.scratch + (size_t)blockIdx.x * p.scratch_per_cta);
         if (SP) sp = (Cx<T>*)smem;
     }
-    const bool sp_ok = SP && (p.plan_m.npass & 1) == 0;
+    const bool sp_ok = SP && ((CM ? static_npass(CM ? CM : 2) : p.plan_m.npass) & 1) == 0;
     // length-M transform of `a`; `other` is a free array usable as the partner when shared memory is not
     auto FFTM = [&](Cx<T>* a, Cx<T>* other) -> Cx<T>* {
-        if (SP && sp_ok) return fft_run<T, PAD, true>(a, sp, p.plan_m, WM, 1, tid, nthr);
-        return fft_run<T, PAD>(a, other, p.plan_m, WM, 1, tid, nthr);
+        if constexpr (CM != 0) {
+            if (SP && sp_ok) return fft_run_static<T, CM, NT, PAD, true>(a, sp, WM, tid);
+            return fft_run_static<T, CM, NT, PAD, PAD>(a, other, WM, tid);
+        } else {
+            if (SP && sp_ok) return fft_run<T, PAD, true>(a, sp, p.plan_m, WM, 1, tid, nthr);
+            return fft_run<T, PAD>(a, other, p.plan_m, WM, 1, tid, nthr);
+        }
     };
     Cx<T>* b1 = b0 + pspan<PAD>(M);
     Cx<T>* b2 = b1 + pspan<PAD>(M);
 #define IX(i) pidx<PAD>(i)
     __shared__ double s_warp[32];
     __shared__ double s_total;
+
+    // constants of the sync scan (step J): a thread owns CH consecutive samples
+    const int CH = N / nthr;           // N and nthr are powers of two, CH >= 1
+    const int lane = tid & 31, warp = tid >> 5;
+    const double c = p.fp_c;
+    const double Ach = pow(c, (double)CH);
+    const double A32 = pow(Ach, 32.0);
+    const double AchLane = pow(Ach, (double)lane), AchLane1 = pow(Ach, (double)(lane + 1));
+    const double cN = pow(c, (double)N), cn0 = pow(c, (double)(tid * CH));
 
     const int nwork = p.block_list ? *p.block_count : p.nblocks;
     for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
@@ -249,7 +265,8 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         Cx<T>* fv;
         if (SP && sp_ok) {
             // the two transforms are independent: run them pass by pass with one barrier per pass pair
-            fft_run_pair<T, PAD, true, PAD>(U, sp, V, X, p.plan_m, WM, 1, tid, nthr);
+            if constexpr (CM != 0) fft_run_pair_static<T, CM, NT, PAD, true, PAD>(U, sp, V, X, WM, tid);
+            else fft_run_pair<T, PAD, true, PAD>(U, sp, V, X, p.plan_m, WM, 1, tid, nthr);
             ru = U; rv = V; fu = X; fv = X;
         } else {
             ru = FFTM(U, X);
@@ -284,22 +301,30 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
 
         // H. D = rfft(demod - ire0)
         Cx<T>* D = FFTM(rv, ru);
+        // the two free arrays; the filtered block lands in g1 for an even number of passes and in g2 for an
+        // odd one: make that an end array (b0 or b2) so that step J finds two adjacent free arrays
         Cx<T>* g1 = (D == rv) ? ru : rv;
         Cx<T>* g2 = fv;
+        if (PAD) {
+            const bool even = ((CM ? static_npass(CM ? CM : 2) : p.plan_m.npass) & 1) == 0;
+            Cx<T>* land = (g1 == b1) ? g2 : g1;
+            Cx<T>* oth = (land == g1) ? g2 : g1;
+            g1 = even ? land : oth;
+            g2 = even ? oth : land;
+        }
         untangle<T, PAD>(D, M, WN, tid, nthr);
         __syncthreads();
 
         // I. post filters.  Order: video, burst, (pilot), video05 last because its whole block feeds the sync scan.
-        const int order[4] = {0, 2, 3, 1};
-        const int pl_of[4] = {LDD_P_DEMOD, LDD_P_DEMOD05, LDD_P_BURST, LDD_P_PILOT};
         Cx<T>* r05 = nullptr;
         for (int oi = 0; oi < 4; ++oi) {
-            const int m = order[oi];
+            const int m = (0x1320 >> (4 * oi)) & 15;           // 0, 2, 3, 1
             if (m >= p.nfilt && m != 1) continue;
             tangle<T, PAD>(D, g1, (const Cx<T>*)p.F[m], M, WN, tid, nthr);
             __syncthreads();
             Cx<T>* r = FFTM(g1, g2);
-            float* out = (float*)p.plane[pl_of[m]];
+            static_assert(LDD_P_DEMOD == 0 && LDD_P_DEMOD05 == 1 && LDD_P_BURST == 3 && LDD_P_PILOT == 4, "plane order");
+            float* out = (float*)p.plane[m < 2 ? m : m + 1];
             const T addc = (T)p.addc[m];
             // kept samples 2n, 2n+1 -> out[o + 2n - keep0]; keep0, o and copylen parity: handle singly
             if (((keep0 | keep1) & 1) == 0 && ((o & 1) == 0) && ((((uintptr_t)out) & 7) == 0)) {
@@ -327,17 +352,15 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         {
             const T* x05 = (const T*)r05;     // interleaved: sample 2n = r.x, 2n+1 = -r.y
             const double add = p.addc[1] + p.sync_ref;
-            const int CH = N / nthr;           // N and nthr are powers of two, CH >= 1
             const int n0 = tid * CH;
-            auto insync = [&](int n) -> double {
+            auto val05 = [&](int n) -> double {
                 n = (n + N) & (N - 1);
                 double v = (double)x05[2 * IX(n >> 1) + (n & 1)];
                 if (n & 1) v = -v;
-                v += add;
-                return (v >= p.sync_lo && v <= p.sync_hi) ? 1.0 : 0.0;
+                return v + add;
             };
-            const double c = p.fp_c;
-            double sprev = insync(n0 - 1);
+            auto insync = [&](double v) -> double { return (v >= p.sync_lo && v <= p.sync_hi) ? 1.0 : 0.0; };
+            double sprev = insync(val05(n0 - 1));
             const double sprev0 = sprev;
             // the binary decisions of this thread's chunk, evaluated once (CH <= 64), else re-evaluated
             const bool use_mask = CH <= 64;
@@ -345,26 +368,19 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
             double acc = 0.0;
             int near = 0;
             for (int i = 0; i < CH; ++i) {
-                double s = insync(n0 + i);
+                const double v = val05(n0 + i);
+                const double s = insync(v);
                 if (use_mask && s != 0.0) mask |= (1ull << i);
                 acc = c * acc + (p.fp_b0 * s + p.fp_b1 * sprev);
                 sprev = s;
-                if (p.flag_list) {
-                    // mixed lane: is this float32 sample close enough to a threshold that float64 could decide otherwise?
-                    int nn = (n0 + i) & (N - 1);
-                    double v = (double)x05[2 * IX(nn >> 1) + (nn & 1)];
-                    if (nn & 1) v = -v;
-                    v += add;
-                    near |= (fabs(v - p.sync_lo) < p.flag_margin) | (fabs(v - p.sync_hi) < p.flag_margin);
-                }
+                // mixed lane: is this float32 sample close enough to a threshold that float64 could decide otherwise?
+                if (p.flag_list) near |= (fabs(v - p.sync_lo) < p.flag_margin) | (fabs(v - p.sync_hi) < p.flag_margin);
             }
             if (p.flag_list) {
                 int any = __syncthreads_or(near);
                 if (any && tid == 0) { int at = atomicAdd(p.flag_count, 1); p.flag_list[at] = blk; }
             }
             // inclusive scan of the affine maps y -> Ach*y + acc over threads
-            const double Ach = pow(c, (double)CH);
-            const int lane = tid & 31, warp = tid >> 5;
             double incl = acc, mult = Ach;
             for (int d = 1; d < 32; d <<= 1) {
                 double up = __shfl_up_sync(0xffffffffu, incl, d);
@@ -373,25 +389,37 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
             }
             if (lane == 31) s_warp[warp] = incl;
             __syncthreads();
-            const double A32 = pow(Ach, 32.0);
             double carry = 0.0;                 // state entering this warp (zero initial state)
             for (int w = 0; w < warp; ++w) carry = A32 * carry + s_warp[w];
             if (tid == nthr - 1) {
-                double tot = pow(Ach, (double)(lane + 1)) * carry + incl;
-                s_total = tot / (1.0 - pow(c, (double)N));     // periodic steady state y[-1]
+                double tot = AchLane1 * carry + incl;
+                s_total = tot / (1.0 - cN);     // periodic steady state y[-1]
             }
             __syncthreads();
             // state entering this thread's chunk
             double excl = __shfl_up_sync(0xffffffffu, incl, 1);
-            double st = (lane == 0 ? 0.0 : excl) + pow(Ach, (double)lane) * carry + pow(c, (double)n0) * s_total;
+            double st = (lane == 0 ? 0.0 : excl) + AchLane * carry + cn0 * s_total;
             double* out = (double*)p.plane[LDD_P_SYNC];     // float64: peak search must see the reference's ordering
+            // A thread's chunk is contiguous, so storing it directly puts the lanes of a warp CH*8 bytes apart
+            // (one sector per lane and store).  When two adjacent block arrays (or the partner buffer) are
+            // free, the chunk goes to shared memory first (one padding slot per 32 keeps that conflict-free)
+            // and the plane is written with fully coalesced stores.
+            double* ys = nullptr;
+            if (PAD) ys = (r05 == b0) ? (double*)b1 : (r05 == b2) ? (double*)b0 : nullptr;
+            else if (SP && (const void*)r05 != (const void*)sp) ys = (double*)sp;
             sprev = sprev0;
             for (int i = 0; i < CH; ++i) {
                 int n = n0 + i;
-                double s = use_mask ? (double)((mask >> i) & 1ull) : insync(n);
+                double s = use_mask ? (double)((mask >> i) & 1ull) : insync(val05(n));
                 st = c * st + (p.fp_b0 * s + p.fp_b1 * sprev);
                 sprev = s;
-                if (n >= keep0 && n < keep1) st_stream(&out[o + (n - keep0)], st);
+                if (ys) ys[n + (n >> 5)] = st;
+                else if (n >= keep0 && n < keep1) st_stream(&out[o + (n - keep0)], st);
+            }
+            if (ys) {
+                __syncthreads();
+                double* outk = out + o - keep0;
+                for (int n = keep0 + tid; n < keep1; n += nthr) st_stream(&outk[n], ys[n + (n >> 5)]);
             }
         }
         __syncthreads();
@@ -407,16 +435,29 @@ static int check_launch(const char* what) {
     return LDD_OK;
 }
 
-template <class T, int NT, bool PAD, int MINB = 1, bool SP = false>
+template <class T, int NT, bool PAD, int MINB = 1, bool SP = false, int CM = 0>
 static int launch_variant(const DemodParams& p, int grid, cudaStream_t st, size_t smem_bytes) {
-    void (*kern)(const DemodParams) = demod_kernel<T, NT, PAD, MINB, SP>;
+    void (*kern)(const DemodParams) = demod_kernel<T, NT, PAD, MINB, SP, CM>;
     if (smem_bytes) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     LDD_LAUNCH(kern, dim3(grid), dim3(NT), smem_bytes, st, p);
     return check_launch("demod_kernel");
 }
 
+// the compile-time variants assume the default plan (radix 16 while possible) for M = m
+static bool static_plan_ok(const DemodParams& p, int m) {
+    if (p.M != m || p.N != 2 * m || getenv("LDD_NO_STATIC_PLAN")) return false;
+    FftPlan d = make_plan(m, 16);
+    if (d.npass != p.plan_m.npass) return false;
+    for (int i = 0; i < d.npass; ++i)
+        if (d.radix[i] != p.plan_m.radix[i]) return false;
+    return true;
+}
+
 int launch_demod_f64(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t sp_bytes) {
-    if (sp_bytes && threads == 512) return launch_variant<double, 512, false, 1, true>(p, grid, st, sp_bytes);
+    if (sp_bytes && threads == 512) {
+        if (static_plan_ok(p, 8192)) return launch_variant<double, 512, false, 1, true, 8192>(p, grid, st, sp_bytes);
+        return launch_variant<double, 512, false, 1, true>(p, grid, st, sp_bytes);
+    }
     switch (threads) {
         case 1024: return launch_variant<double, 1024, false>(p, grid, st, 0);
         case 512: return launch_variant<double, 512, false>(p, grid, st, 0);
@@ -428,6 +469,7 @@ int launch_demod_f64(const DemodParams& p, int grid, int threads, cudaStream_t s
 int launch_demod_f32(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t smem_bytes) {
     if (smem_bytes) {
         if (threads == 1024) return launch_variant<float, 1024, true>(p, grid, st, smem_bytes);
+        if (static_plan_ok(p, 8192)) return launch_variant<float, 512, true, 1, false, 8192>(p, grid, st, smem_bytes);
         return launch_variant<float, 512, true>(p, grid, st, smem_bytes);
     }
     if (threads == 1024) return launch_variant<float, 1024, false>(p, grid, st, 0);

@@ -131,6 +131,42 @@ __device__ inline void fft_pass_any(int R, const Cx<T>* src, Cx<T>* dst, int M, 
     }
 }
 
+// Compile-time plan (radix 16 while possible, then the remaining power of two): every index, stride
+// and trip count of the passes is a constant, which removes the integer work that otherwise outweighs
+// the butterflies.  Same pass sequence as make_plan(M, 16); result pointer as fft_run.
+template <class T, int M, int NT, bool PA, bool PB, int Ns = 1>
+__device__ inline Cx<T>* fft_run_static(Cx<T>* a, Cx<T>* b, const Cx<T>* __restrict__ W, int tid) {
+    constexpr int rem = M / Ns;
+    if constexpr (rem <= 1) {
+        return a;
+    } else {
+        constexpr int R = rem >= 16 ? 16 : rem;
+        fft_pass<T, R, PA, PB>(a, b, M, Ns, W, 1, tid, NT);
+        __syncthreads();
+        return fft_run_static<T, M, NT, PB, PA, Ns * R>(b, a, W, tid);
+    }
+}
+
+// fft_run_pair with the compile-time plan.
+template <class T, int M, int NT, bool PA, bool PB1, bool PB2, int Ns = 1, bool FLIP = false>
+__device__ inline void fft_run_pair_static(Cx<T>* a1, Cx<T>* b1, Cx<T>* a2, Cx<T>* b2, const Cx<T>* __restrict__ W, int tid) {
+    constexpr int rem = M / Ns;
+    if constexpr (rem > 1) {
+        constexpr int R = rem >= 16 ? 16 : rem;
+        if constexpr (!FLIP) {
+            fft_pass<T, R, PA, PB1>(a1, b1, M, Ns, W, 1, tid, NT);
+            fft_pass<T, R, PA, PB2>(a2, b2, M, Ns, W, 1, tid, NT);
+        } else {
+            fft_pass<T, R, PB1, PA>(b1, a1, M, Ns, W, 1, tid, NT);
+            fft_pass<T, R, PB2, PA>(b2, a2, M, Ns, W, 1, tid, NT);
+        }
+        __syncthreads();
+        fft_run_pair_static<T, M, NT, PA, PB1, PB2, Ns * R, !FLIP>(a1, b1, a2, b2, W, tid);
+    }
+}
+
+constexpr int static_npass(int m) { int n = 0; while (m >= 16) { m /= 16; ++n; } return n + (m > 1 ? 1 : 0); }
+
 struct FftPlan {
     int n;            // transform length (power of two)
     int npass;

@@ -372,6 +372,9 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
         q.scratch = h->scratch64; q.scratch_per_cta = h->scratch64_per_cta;
         q.flag_list = nullptr; q.flag_count = nullptr;
         q.block_count = h->d_flags; q.block_list = h->d_flags + 1;
+        // the float32 planes of a flagged block are as good as those of its neighbours: only the sync decision
+        // (demod_05 -> demod_sync) is redone
+        q.only05 = 1; q.A = 0;
         int g64 = (int)(nblocks < h->sm_count ? nblocks : h->sm_count);
         rc = launch_demod_f64(q, g64, 512, st, h->sp_bytes);
     }

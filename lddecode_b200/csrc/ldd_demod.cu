@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         Cx<T>* r05 = nullptr;
         for (int oi = 0; oi < 4; ++oi) {
             const int m = (0x1320 >> (4 * oi)) & 15;           // 0, 2, 3, 1
-            if (m >= p.nfilt && m != 1) continue;
+            if ((m >= p.nfilt || p.only05) && m != 1) continue;
             tangle<T, PAD>(D, g1, (const Cx<T>*)p.F[m], M, WN, tid, nthr);
             __syncthreads();
             Cx<T>* r = FFTM(g1, g2);

@@ -89,11 +89,22 @@ struct HsyncParams {
     double* linelocs2;
     unsigned char* linebad_out;
     int* status;               // bit 1: the reference would have raised (field invalid)
+    int nfields;
 };
 
-__global__ void __launch_bounds__(128) refine_hsync_kernel(const HsyncParams p) {
-    const int f = blockIdx.x;
+constexpr int HS_WARPS = 8;
+constexpr int HS_WIN = 192;        // samples in 4 us (zc - 1 us .. zc + 3 us) at <= 40 MSPS, + slack
+
+// One warp per line: the scans of the reference (first crossing of -20 IRE within 400 samples, min / max
+// over two windows) run 32 samples at a time with coalesced loads; the window around the edge is staged
+// in shared memory for the scalar tail (means, half-level crossing) that lane 0 finishes.
+__global__ void __launch_bounds__(32 * HS_WARPS) refine_hsync_kernel(const HsyncParams p) {
+    __shared__ double s_win[HS_WARPS][HS_WIN];
+    const int f = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nll = p.linecount[f] + 4;
+    const int i = blockIdx.x * HS_WARPS + warp;
+    if (i >= nll) return;
     const long long base = p.base[f], wlen = p.winlen[f];
     const double* l1 = p.linelocs1 + (size_t)f * p.ll_stride;
     const unsigned char* bad_in = p.linebad_in + (size_t)f * p.ll_stride;
@@ -105,75 +116,118 @@ __global__ void __launch_bounds__(128) refine_hsync_kernel(const HsyncParams p) 
     // window length visible to the reference = min(wlen, plane end)
     long long len = wlen;
     if (base + len > p.n) len = p.n - base;
+    const unsigned FULL = 0xffffffffu;
 
-    for (int i = threadIdx.x; i < nll; i += blockDim.x) {
-        double ll = l1[i];
-        if (i < 9) ll -= 200;
-        const double ll1 = ll;
-        bool isbad = bad_in[i] != 0;
-        double zc;
-        bool have = calczc(d, len, (long long)ll, hz(-20), 400, &zc);
-        double out = ll;
-        if (have && !isbad) {
-            out = zc;
-            if (i >= 10) {
-                long long a1 = (long long)(ll1 - fq * 2), b1 = (long long)(ll1 + fq * 2);
-                long long a = (long long)(zc - fq * 1), b = (long long)(zc + fq * 3);
-                long long ab = (long long)(zc + fq * 1);
-                if (a1 < 0 || a < 0) { atomicOr(&p.status[f], 2); a1 = a1 < 0 ? 0 : a1; a = a < 0 ? 0 : a; }
-                if (b1 > len) b1 = len;
-                if (b > len) b = len;
-                double mn = 1e300, mx = -1e300, mn1 = 1e300, mx1 = -1e300, mnb = 1e300, mxb = -1e300;
-                for (long long k = a; k < b; ++k) {
-                    double v = d(k);
-                    mn = v < mn ? v : mn; mx = v > mx ? v : mx;
-                    if (k >= ab) { mnb = v < mnb ? v : mnb; mxb = v > mxb ? v : mxb; }
-                }
-                for (long long k = a1; k < b1; ++k) { double v = d(k); mn1 = v < mn1 ? v : mn1; mx1 = v > mx1 ? v : mx1; }
-                if ((mn < hz(-60) || mx > hz(20)) || (mn1 < hz(-60) || mx1 > hz(100)) || (mnb < hz(-10) || mxb > hz(10))) {
+    double ll = l1[i];
+    if (i < 9) ll -= 200;
+    const double ll1 = ll;
+    bool isbad = bad_in[i] != 0;
+    // calczc(d, len, (long long)ll, hz(-20), 400): first sample at or beyond the target, 32 at a time
+    double zc = 0.0;
+    bool have = false;
+    {
+        const long long start = (long long)ll;
+        const double target = hz(-20);
+        if (start >= 0 && start < len) {
+            long long end = start + 401;
+            if (end > len) end = len;
+            const bool rising = d(start) < target;
+            long long x = -1;
+            for (long long k0 = start; k0 < end; k0 += 32) {
+                long long k = k0 + lane;
+                bool hit = false;
+                if (k < end) { double v = d(k); hit = rising ? (v >= target) : (v <= target); }
+                unsigned m = __ballot_sync(FULL, hit);
+                if (m) { x = k0 + (__ffs(m) - 1); break; }
+            }
+            if (x > 0) {
+                double a = d(x - 1) - target, b = d(x) - target;
+                zc = (double)(x - 1) + (-a / (-a + b));
+                have = true;
+            }
+        }
+    }
+    double out = ll;
+    if (have && !isbad) {
+        out = zc;
+        if (i >= 10) {
+            long long a1 = (long long)(ll1 - fq * 2), b1 = (long long)(ll1 + fq * 2);
+            long long a = (long long)(zc - fq * 1), b = (long long)(zc + fq * 3);
+            long long ab = (long long)(zc + fq * 1);
+            if (a1 < 0 || a < 0) { if (lane == 0) atomicOr(&p.status[f], 2); a1 = a1 < 0 ? 0 : a1; a = a < 0 ? 0 : a; }
+            if (b1 > len) b1 = len;
+            if (b > len) b = len;
+            double mn = 1e300, mx = -1e300, mn1 = 1e300, mx1 = -1e300, mnb = 1e300, mxb = -1e300;
+            const bool staged = (b - a) <= HS_WIN;
+            for (long long k = a + lane; k < b; k += 32) {
+                double v = d(k);
+                if (staged) s_win[warp][k - a] = v;
+                mn = v < mn ? v : mn; mx = v > mx ? v : mx;
+                if (k >= ab) { mnb = v < mnb ? v : mnb; mxb = v > mxb ? v : mxb; }
+            }
+            for (long long k = a1 + lane; k < b1; k += 32) { double v = d(k); mn1 = v < mn1 ? v : mn1; mx1 = v > mx1 ? v : mx1; }
+            for (int sh = 16; sh > 0; sh >>= 1) {
+                double t;
+                t = __shfl_xor_sync(FULL, mn, sh); mn = t < mn ? t : mn;
+                t = __shfl_xor_sync(FULL, mx, sh); mx = t > mx ? t : mx;
+                t = __shfl_xor_sync(FULL, mn1, sh); mn1 = t < mn1 ? t : mn1;
+                t = __shfl_xor_sync(FULL, mx1, sh); mx1 = t > mx1 ? t : mx1;
+                t = __shfl_xor_sync(FULL, mnb, sh); mnb = t < mnb ? t : mnb;
+                t = __shfl_xor_sync(FULL, mxb, sh); mxb = t > mxb ? t : mxb;
+            }
+            __syncwarp();
+            if ((mn < hz(-60) || mx > hz(20)) || (mn1 < hz(-60) || mx1 > hz(100)) || (mnb < hz(-10) || mxb > hz(10))) {
+                isbad = true;
+            } else if (lane == 0) {
+                const long long wl = b - a;
+                auto w = [&](long long k) -> double { return staged ? s_win[warp][k] : d(a + k); };
+                double tmp[20];
+                int n0 = (int)(wl < 20 ? wl : 20);
+                for (int k = 0; k < n0; ++k) tmp[k] = w(k);
+                double low = np_mean(tmp, n0);
+                int n1 = (int)(wl < 100 ? 0 : (wl < 120 ? wl - 100 : 20));
+                for (int k = 0; k < n1; ++k) tmp[k] = w(100 + k);
+                double high = np_mean(tmp, n1);
+                double zc2;
+                if (!calczc(w, wl, 0, (low + high) / 2, (int)wl, &zc2)) {
+                    atomicOr(&p.status[f], 2);          // reference: TypeError -> field invalid
                     isbad = true;
                 } else {
-                    const long long wl = b - a;
-                    double tmp[20];
-                    int n0 = (int)(wl < 20 ? wl : 20);
-                    for (int k = 0; k < n0; ++k) tmp[k] = d(a + k);
-                    double low = np_mean(tmp, n0);
-                    int n1 = (int)(wl < 100 ? 0 : (wl < 120 ? wl - 100 : 20));
-                    for (int k = 0; k < n1; ++k) tmp[k] = d(a + 100 + k);
-                    double high = np_mean(tmp, n1);
-                    auto w = [&](long long k) -> double { return d(a + k); };
-                    double zc2;
-                    if (!calczc(w, wl, 0, (low + high) / 2, (int)wl, &zc2)) {
-                        atomicOr(&p.status[f], 2);          // reference: TypeError -> field invalid
-                        isbad = true;
-                    } else {
-                        zc2 += (double)(long long)zc - fq * 1;
-                        if (fabs(zc2 - zc) < fq / 4) out = zc2; else isbad = true;
-                    }
+                    zc2 += (double)(long long)zc - fq * 1;
+                    if (fabs(zc2 - zc) < fq / 4) out = zc2; else isbad = true;
                 }
             }
-        } else {
-            isbad = true;
         }
+    } else {
+        isbad = true;
+    }
+    if (lane == 0) {
         if (i < 10) out += fq * 4.72;
         l2[i] = out;
         bad[i] = isbad ? 1 : 0;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 11; i < nll; ++i)
-            if (bad[i]) { double gap = l2[i - 1] - l2[i - 2]; l2[i] = l2[i - 1] + gap; }
-        const double lo = p.linelen - fq * .2, hi = p.linelen + fq * .2;
-        for (int i = 9; i >= 0; --i) {
-            double gap = l2[i + 1] - l2[i];
-            if (!(gap >= lo && gap <= hi)) gap = p.linelen;
-            l2[i] = l2[i + 1] - gap;
-        }
-        for (int i = nll - 10; i < nll; ++i) {
-            double gap = l2[i] - l2[i - 1];
-            if (!(gap >= lo && gap <= hi)) gap = p.linelen;
-            l2[i] = l2[i - 1] + gap;
-        }
+}
+
+// The sequential fix-ups of refine_linelocs_hsync (lddecode_core.py:769-787): one thread per field.
+__global__ void __launch_bounds__(32) refine_hsync_fixup_kernel(const HsyncParams p) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= p.nfields) return;
+    const int nll = p.linecount[f] + 4;
+    double* l2 = p.linelocs2 + (size_t)f * p.ll_stride;
+    const unsigned char* bad = p.linebad_out + (size_t)f * p.ll_stride;
+    const double fq = p.freq;
+    for (int i = 11; i < nll; ++i)
+        if (bad[i]) { double gap = l2[i - 1] - l2[i - 2]; l2[i] = l2[i - 1] + gap; }
+    const double lo = p.linelen - fq * .2, hi = p.linelen + fq * .2;
+    for (int i = 9; i >= 0; --i) {
+        double gap = l2[i + 1] - l2[i];
+        if (!(gap >= lo && gap <= hi)) gap = p.linelen;
+        l2[i] = l2[i + 1] - gap;
+    }
+    for (int i = nll - 10; i < nll; ++i) {
+        double gap = l2[i] - l2[i - 1];
+        if (!(gap >= lo && gap <= hi)) gap = p.linelen;
+        l2[i] = l2[i - 1] + gap;
     }
 }
 
@@ -384,7 +438,10 @@ constexpr int PILOT_WARPS = 32;
 
 __global__ void __launch_bounds__(32 * PILOT_WARPS) refine_pilot_kernel(const PilotParams p, double* ws_offsets /*[nfields][ll_stride][MAXOFF]*/,
                                                                        int* ws_count /*[nfields][ll_stride]*/) {
-    __shared__ float s_pil[PILOT_WARPS][PILOT_MAXLEN];      // pilot = flip(demod - demod_05), staged per warp
+    // dynamic shared memory: first the staged pilot windows (float64 [PILOT_WARPS][PILOT_MAXLEN]), later
+    // (after a barrier) the selection histogram and list
+    LDD_DYN_SMEM(psm);
+    double* s_pil = (double*)psm + (size_t)(threadIdx.x >> 5) * PILOT_MAXLEN;   // pilot = flip(demod - demod_05), this warp's line
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nll = p.linecount[f] + 4;
     const long long base = p.base[f];
@@ -404,33 +461,24 @@ __global__ void __launch_bounds__(32 * PILOT_WARPS) refine_pilot_kernel(const Pi
         // coalesced staging; the two ire0 offsets cancel, the subtraction is done in float64 like the reference
         for (int i = lane; i < len; i += 32) {
             long long s = base + b - 1 - i;
-            s_pil[warp][i] = (float)(((double)p.demod[s]) - ((double)p.d05[s]));
+            s_pil[i] = ((double)p.demod[s]) - ((double)p.d05[s]);
         }
         __syncwarp();
         if (lane == 0) {
             int n = 0;
-            auto pil = [&](long long i) -> double {
-                long long s = base + b - 1 - i;
-                return ((double)p.demod[s]) - ((double)p.d05[s]);
-            };
+            auto pil = [&](long long i) -> double { return s_pil[i]; };
             double adjfreq = fq;
             if (l > 1) adjfreq /= (lin[l] - lin[l - 1]) / p.linelen;
             int i = 0;
             while (i < len) {
-                // cheap float32 pre-test from the staged copy (the band is 200 kHz wide, float32 rounds at 0.02 Hz);
-                // samples near the band edges are re-tested in float64
-                float vf = s_pil[warp][i];
-                bool maybe = vf >= -300001.f && vf <= -99999.f;
-                if (maybe) {
-                    double v = pil(i);
-                    if (v >= -300000 && v <= -100000) {
-                        double zc;
-                        if (calczc(pil, len, i, 0.0, 10, &zc)) {
-                            double zcp = zc / (adjfreq / 3.75);
-                            if (n < PILOT_MAXOFF) my[n] = zcp - floor(zcp);
-                            ++n;
-                            i = (int)(zc + 1);
-                        }
+                double v = s_pil[i];
+                if (v >= -300000 && v <= -100000) {
+                    double zc;
+                    if (calczc(pil, len, i, 0.0, 10, &zc)) {
+                        double zcp = zc / (adjfreq / 3.75);
+                        if (n < PILOT_MAXOFF) my[n] = zcp - floor(zcp);
+                        ++n;
+                        i = (int)(zc + 1);
                     }
                 }
                 ++i;
@@ -452,8 +500,8 @@ __global__ void __launch_bounds__(32 * PILOT_WARPS) refine_pilot_kernel(const Pi
     // median of all offsets (np.median(alloffsets)): exact order statistics by multi-level histogram
     // selection (offsets are fractional parts in [0, 1)): 4096 bins over the current range, descend
     // into the bin holding the k-th value until it holds few enough values to sort.
-    __shared__ int s_hist[4096];
-    __shared__ double s_list[256];
+    int* s_hist = (int*)psm;                              // [4096]
+    double* s_list = (double*)(psm + 4096 * sizeof(int));   // [256]
     __shared__ int s_n, s_bin, s_before;
     __shared__ double s_tgt;
     int total = 0;
@@ -797,8 +845,13 @@ extern "C" int ldd_refine_hsync(ldd_handle* h, const float* d05_dev, long long n
     p.linelen = h->cfg.linelen; p.base = base_dev; p.winlen = winlen_dev; p.linecount = linecount_dev; p.ll_stride = ll_stride;
     p.linelocs1 = linelocs1_dev; p.linebad_in = linebad_dev; p.linelocs2 = linelocs2_dev; p.linebad_out = linebad_out_dev;
     p.status = status_dev;
-    LDD_LAUNCH(refine_hsync_kernel, dim3(nfields), dim3(128), 0, (cudaStream_t)stream, p);
-    return launch_status(h, "refine_hsync_kernel");
+    p.nfields = nfields;
+    const int maxll = ll_stride;        // linecount + 4 <= ll_stride
+    LDD_LAUNCH(refine_hsync_kernel, dim3((maxll + HS_WARPS - 1) / HS_WARPS, nfields), dim3(32 * HS_WARPS), 0, (cudaStream_t)stream, p);
+    int rc = launch_status(h, "refine_hsync_kernel");
+    if (rc) return rc;
+    LDD_LAUNCH(refine_hsync_fixup_kernel, dim3((nfields + 31) / 32), dim3(32), 0, (cudaStream_t)stream, p);
+    return launch_status(h, "refine_hsync_fixup_kernel");
 }
 
 extern "C" int ldd_refine_burst(ldd_handle* h, const float* burst_dev, long long n, const long long* base_dev,
@@ -837,7 +890,9 @@ extern "C" int ldd_refine_pilot(ldd_handle* h, const float* demod_dev, const flo
     p.demod = demod_dev; p.d05 = d05_dev; p.n = n; p.freq = h->cfg.freq_hz / 1e6; p.linelen = h->cfg.linelen;
     p.base = base_dev; p.linecount = linecount_dev; p.ll_stride = ll_stride; p.linelocs_in = linelocs_in_dev;
     p.linelocs_out = linelocs_out_dev; p.status = status_dev;
-    LDD_LAUNCH(refine_pilot_kernel, dim3(nfields), dim3(32 * PILOT_WARPS), 0, st, p, offs, cnt);
+    const size_t psmem = (size_t)PILOT_WARPS * PILOT_MAXLEN * sizeof(double);
+    cudaFuncSetAttribute(refine_pilot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+    LDD_LAUNCH(refine_pilot_kernel, dim3(nfields), dim3(32 * PILOT_WARPS), psmem, st, p, offs, cnt);
     return launch_status(h, "refine_pilot_kernel");
 }
 

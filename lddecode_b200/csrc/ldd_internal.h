@@ -57,6 +57,7 @@ struct DemodParams {
     int* flag_list;
     int* flag_count;
     double flag_margin;
+    int only05;                // re-run pass of the mixed lane: only demod_05 and the sync plane are produced
     const int* block_list;
     const int* block_count;
 };

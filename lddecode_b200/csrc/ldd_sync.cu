@@ -19,8 +19,35 @@ struct ArgMax {
     int idx;
 };
 
-// arg-max of ds[i .. i+len), first index among equal values; all 32 lanes get the result
+// arg-max of ds[i .. i+len), first index among equal values; all 32 lanes get the result.
+// The chase is a chain of dependent windows, so what matters is the number of memory round trips per
+// window: with len <= 32*PER all of a lane's loads are issued before the first comparison (one round
+// trip per window instead of one per four loads).
+template <int PER>
+__device__ inline ArgMax warp_argmax_batched(const double* __restrict__ ds, long long i, int len, int lane) {
+    double v[PER];
+    LDD_UNROLL
+    for (int q = 0; q < PER; ++q) {
+        int k = lane + 32 * q;
+        v[q] = k < len ? ds[i + k] : -1e300;
+    }
+    ArgMax b;
+    b.v = -1e300;
+    b.idx = 0x7fffffff;
+    LDD_UNROLL
+    for (int q = 0; q < PER; ++q)
+        if (v[q] > b.v) { b.v = v[q]; b.idx = lane + 32 * q; }
+    for (int d = 16; d > 0; d >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, b.v, d);
+        int oi = __shfl_xor_sync(0xffffffffu, b.idx, d);
+        if (ov > b.v || (ov == b.v && oi < b.idx)) { b.v = ov; b.idx = oi; }
+    }
+    return b;
+}
+
 __device__ inline ArgMax warp_argmax(const double* __restrict__ ds, long long i, int len, int lane) {
+    if (len <= 32 * 30) return warp_argmax_batched<30>(ds, i, len, lane);      // NTSC at 8fsc: 910
+    if (len <= 32 * 40) return warp_argmax_batched<40>(ds, i, len, lane);      // PAL at 8fsc: 1135, 40 MSPS: 1280
     ArgMax b;
     b.v = -1e300;
     b.idx = 0x7fffffff;

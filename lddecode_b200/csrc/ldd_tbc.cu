@@ -5,25 +5,30 @@
 // evaluated at outwidth equidistant points, times the line's wow factor, then scaled to uint16.
 //
 // The spline is solved in closed form instead of by a sequential tridiagonal sweep.  On unit
-// spacing its second derivatives satisfy M[i-1] + 4 M[i] + M[i+1] = 6 (y[i-1] - 2 y[i] + y[i+1]).
-// The inverse of the infinite (1,4,1) operator is g[k] = r^|k| / (2 sqrt 3), r = sqrt 3 - 2, so a
-// particular solution P is a short FIR over the line's samples and a halo of real neighbours
-// (|r|^24 = 2e-14, far below the float32 resolution of the input plane), computed by all threads in parallel; the two not-a-knot rows then fix the
-// homogeneous part alpha r^i + beta r^(n-i) by a 2x2 solve.  One CTA per output line.
+// spacing its second derivatives satisfy M[i-1] + 4 M[i] + M[i+1] = d[i], d[i] = 6 (y[i-1] - 2 y[i] + y[i+1]).
+// The inverse of the infinite (1,4,1) operator is g[k] = c r^|k|, c = 1 / (2 sqrt 3), r = sqrt 3 - 2, so a
+// particular solution is P = g * d = c (F + B - d) with the two one-pole recursions
+// F[i] = d[i] + r F[i-1] (causal) and B[i] = d[i] + r B[i+1] (anti-causal), run over the line's samples and a
+// halo of 32 real neighbours on each side (|r|^32 = 5e-19).  The recursions are evaluated chunk-parallel:
+// every thread owns 16 consecutive samples, reduces them to the two chunk sums, and takes its entry states
+// from the sums of its two neighbours on each side (|r|^16 = 7e-10 per chunk, so two neighbours are exact
+// in float64).  That is ~8 float64 operations per input sample instead of a 51-tap FIR.  The two
+// not-a-knot rows then fix the homogeneous part alpha r^i + beta r^(n-i) by a 2x2 solve.  One CTA per
+// output line.
 #include "ldd_internal.h"
 
 namespace ldd {
 
-constexpr int TBC_K = 24;                 // reach of the Green's function FIR: |r|^24 = 2e-14 (input is float32)
-constexpr int TBC_H = TBC_K + 1;          // halo samples needed on each side
+constexpr int TBC_H = 32;                 // halo samples on each side of the line
+constexpr int TBC_C = 16;                 // samples per thread chunk of the recursions
 constexpr int TBC_MAXD = 4032;            // longest input line span supported
 constexpr int TBC_THREADS = 256;
-constexpr int TBC_NTAPS = 2 * TBC_H + 1;  // taps of the y -> P filter
-constexpr int TBC_OPT = 9;                // outputs per thread and sweep of the register-tiled FIR (2271/9 < 256 threads)
+constexpr int TBC_MAXU = TBC_MAXD + 1 + 2 * TBC_H;           // staged samples y[-H .. dist+H]
+constexpr int TBC_MAXQ = (TBC_MAXU + TBC_C - 1) / TBC_C;     // chunks
+constexpr int TBC_NPOW = 64;              // r^64 = 4e-37: reach of the homogeneous correction
 
-// w[m] = 6 (g[m-1] - 2 g[m] + g[m+1]), g[k] = r^|k| / (2 sqrt 3) truncated to |k| <= K: set once per
-// process.  Constant memory lets the fully unrolled FIR take its taps as immediate constant-bank operands.
-__constant__ double c_tbc_taps[TBC_NTAPS];
+// r^i, i < TBC_NPOW: set once per process.
+__constant__ double c_tbc_rpow[TBC_NPOW];
 
 struct TbcParams {
     const float* plane;       // input plane
@@ -49,9 +54,10 @@ struct TbcParams {
 
 __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
     LDD_DYN_SMEM(smem_raw);
-    double* ys = (double*)smem_raw;                       // y[-H .. dist+H]
-    double* Ms = ys + (TBC_MAXD + 2 * TBC_H + TBC_OPT + 2);   // M[0 .. dist]
-    __shared__ double s_ab[2];
+    double* Ms = (double*)smem_raw;                       // M[-H .. dist+H] at index u = i + H
+    double* Lf = Ms + (TBC_MAXQ * TBC_C + 2);             // chunk sums of the causal recursion
+    double* Lb = Lf + (TBC_MAXQ + 2);                     // ... of the anti-causal one
+    float* ys = (float*)(Lb + (TBC_MAXQ + 2));            // y[-H .. dist+H] at index u, zero padded to a whole chunk
 
     const int tid = threadIdx.x;
     const int field = blockIdx.y, line = blockIdx.x;
@@ -70,51 +76,90 @@ __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
     }
     const double r = -0.26794919243112270647;      // sqrt(3) - 2
     const double c = 0.28867513459481288225;       // 1 / (2 sqrt 3)
-    // stage the samples (relative values; the spline is linear so plane_add is added at the end)
-    for (int i = tid; i < dist + 1 + 2 * TBC_H + TBC_OPT; i += TBC_THREADS) {
-        long long s = base + ib - TBC_H + i;
-        s = s < 0 ? 0 : (s >= p.n ? p.n - 1 : s);
-        ys[i] = (double)p.plane[s];
-    }
-    __syncthreads();
-    // P = w * y, register tiled: one shared-memory load feeds up to TBC_OPT accumulators, the taps are
-    // constant-bank operands (a plain tap-by-tap loop is bound by shared-memory bandwidth: 2 loads per FMA)
-    for (int i0 = tid * TBC_OPT; i0 <= dist; i0 += TBC_THREADS * TBC_OPT) {
-        double acc[TBC_OPT];
-        LDD_UNROLL
-        for (int o = 0; o < TBC_OPT; ++o) acc[o] = 0.0;
-        const double* y = ys + i0;                        // y[i0-H] ... ; output o uses y[o + m], m = 0..NTAPS-1
-        LDD_UNROLL
-        for (int t = 0; t < TBC_NTAPS + TBC_OPT - 1; ++t) {
-            const double yv = y[t];
-            LDD_UNROLL
-            for (int o = 0; o < TBC_OPT; ++o) {
-                const int m = t - o;
-                if (m >= 0 && m < TBC_NTAPS) acc[o] = fma(c_tbc_taps[m], yv, acc[o]);
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4, r16 = r8 * r8;   // r^16: entry-state weight of the second neighbour chunk
+    // stage the samples (relative values; the spline is linear so plane_add is added at the end).
+    // d[u] exists for u = 1 .. U-2; chunk q owns u = 1 + 16 q .. 16 + 16 q.
+    const int U = dist + 1 + 2 * TBC_H;
+    const int nq = (U - 2 + TBC_C - 1) / TBC_C;
+    {
+        const long long s0 = base + ib - TBC_H;
+        const float* src = p.plane + s0;
+        if (s0 >= 0 && s0 + U <= p.n) {
+            for (int i = tid; i < U; i += TBC_THREADS) ys[i] = src[i];
+        } else {
+            for (int i = tid; i < U; i += TBC_THREADS) {
+                long long s = s0 + i;
+                s = s < 0 ? 0 : (s >= p.n ? p.n - 1 : s);
+                ys[i] = p.plane[s];
             }
         }
+        for (int i = U + tid; i < nq * TBC_C + 2; i += TBC_THREADS) ys[i] = 0.f;
+    }
+    __syncthreads();
+    // chunk sums: Lf = sum r^(15-k) d[k], Lb = sum r^k d[k]
+    auto load_d = [&](int q, double* d) {
+        const float* y = ys + q * TBC_C;
+        double ym = (double)y[0], y0 = (double)y[1];
         LDD_UNROLL
-        for (int o = 0; o < TBC_OPT; ++o)
-            if (i0 + o <= dist) Ms[i0 + o] = acc[o];
+        for (int k = 0; k < TBC_C; ++k) {
+            const double yp = (double)y[k + 2];
+            const int u = 1 + q * TBC_C + k;
+            d[k] = (u <= U - 2) ? 6.0 * ((ym - 2.0 * y0) + yp) : 0.0;
+            ym = y0;
+            y0 = yp;
+        }
+    };
+    for (int q = tid; q < nq; q += TBC_THREADS) {
+        double d[TBC_C];
+        load_d(q, d);
+        double f = 0.0, bk = 0.0;
+        LDD_UNROLL
+        for (int k = 0; k < TBC_C; ++k) {
+            f = fma(f, r, d[k]);
+            bk = fma(bk, r, d[TBC_C - 1 - k]);
+        }
+        Lf[q] = f;
+        Lb[q] = bk;
     }
     __syncthreads();
-    if (tid == 0) {
-        double L = Ms[0] - 2.0 * Ms[1] + Ms[2];
-        double R = Ms[dist] - 2.0 * Ms[dist - 1] + Ms[dist - 2];
-        double A = (1.0 - r) * (1.0 - r);
-        double q = pow(r, (double)(dist - 2));
-        double den = A * (1.0 - q * q);
-        s_ab[0] = (-L + q * R) / den;
-        s_ab[1] = (-R + q * L) / den;
+    for (int q = tid; q < nq; q += TBC_THREADS) {
+        double d[TBC_C], F[TBC_C];
+        load_d(q, d);
+        double f = (q >= 1 ? Lf[q - 1] : 0.0) + (q >= 2 ? r16 * Lf[q - 2] : 0.0);
+        double bk = (q + 1 < nq ? Lb[q + 1] : 0.0) + (q + 2 < nq ? r16 * Lb[q + 2] : 0.0);
+        LDD_UNROLL
+        for (int k = 0; k < TBC_C; ++k) {
+            f = fma(f, r, d[k]);
+            F[k] = f;
+        }
+        double* M = Ms + 1 + q * TBC_C;
+        LDD_UNROLL
+        for (int k = TBC_C - 1; k >= 0; --k) {
+            bk = fma(bk, r, d[k]);
+            M[k] = c * ((F[k] + bk) - d[k]);
+        }
     }
     __syncthreads();
+    double* M0 = Ms + TBC_H;                              // M0[i], i = 0 .. dist
     {
-        const double alpha = s_ab[0], beta = s_ab[1];
-        for (int i = tid; i <= dist; i += TBC_THREADS) {
-            double corr = 0.0;
-            if (i < 64) corr += alpha * pow(r, (double)i);
-            if (dist - i < 64) corr += beta * pow(r, (double)(dist - i));
-            Ms[i] += corr;
+        // not-a-knot rows -> homogeneous part (every thread solves the 2x2 system for itself)
+        const double L = M0[0] - 2.0 * M0[1] + M0[2];
+        const double R = M0[dist] - 2.0 * M0[dist - 1] + M0[dist - 2];
+        const double A = (1.0 - r) * (1.0 - r);
+        const double q = (dist - 2 < TBC_NPOW) ? c_tbc_rpow[dist - 2] : 0.0;
+        const double den = A * (1.0 - q * q);
+        const double alpha = (-L + q * R) / den, beta = (-R + q * L) / den;
+        __syncthreads();                                  // all threads have read the uncorrected ends
+        if (tid < TBC_NPOW) {
+            const int i = tid;                            // front: both terms where they overlap
+            if (i <= dist) {
+                double corr = alpha * c_tbc_rpow[i];
+                if (dist - i < TBC_NPOW) corr += beta * c_tbc_rpow[dist - i];
+                M0[i] += corr;
+            }
+        } else if (tid < 2 * TBC_NPOW) {
+            const int k = tid - TBC_NPOW, i = dist - k;   // back: indices the front threads do not own
+            if (i >= TBC_NPOW) M0[i] += beta * c_tbc_rpow[k];
         }
     }
     __syncthreads();
@@ -123,15 +168,15 @@ __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
     const double stop = (e - b) + fb;
     const double step = (stop - fb) / (double)W;
     const double wowf = p.wow ? (e - b) / (double)p.linelen : 1.0;
-    const double* y0 = ys + TBC_H;
+    const float* y0 = ys + TBC_H;
     const double sixth = 1.0 / 6.0;
     for (int j = tid; j < W; j += TBC_THREADS) {
         double x = (double)j * step + fb;
         int i = (int)x;
         if (i > dist - 1) i = dist - 1;
         double t = x - (double)i, u = 1.0 - t;
-        double Mi = Ms[i], Mj = Ms[i + 1];
-        double S = Mi * u * u * u * sixth + Mj * t * t * t * sixth + (y0[i] - Mi * sixth) * u + (y0[i + 1] - Mj * sixth) * t;
+        double Mi = M0[i], Mj = M0[i + 1];
+        double S = Mi * u * u * u * sixth + Mj * t * t * t * sixth + ((double)y0[i] - Mi * sixth) * u + ((double)y0[i + 1] - Mj * sixth) * t;
         double hz = (S + p.plane_add) * wowf;
         size_t o = (size_t)field * (size_t)p.out_stride + (size_t)line * W + j;
         if (p.mode == 0) {
@@ -185,13 +230,12 @@ extern "C" int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n
     double clevel = (1.0 / colorlevel) / (1700000.0 / 140.0);
     p.clevel_k = (float)(327.67 * clevel);
     p.status = status_dev;
-    size_t smem = (size_t)(TBC_MAXD + 2 * TBC_H + TBC_OPT + 2 + TBC_MAXD + TBC_OPT + 2) * sizeof(double);
+    size_t smem = (size_t)(TBC_MAXQ * TBC_C + 2 + 2 * (TBC_MAXQ + 2)) * sizeof(double) + (size_t)(TBC_MAXQ * TBC_C + 4) * sizeof(float);
     if (!h->tbc_taps_set) {
-        const double r = -0.26794919243112270647, c = 0.28867513459481288225;
-        double taps[TBC_NTAPS];
-        auto g = [&](int q) -> double { int a = q < 0 ? -q : q; return a > TBC_K ? 0.0 : c * pow(r, (double)a); };
-        for (int m = 0; m < TBC_NTAPS; ++m) { int k = m - TBC_H; taps[m] = 6.0 * (g(k - 1) - 2.0 * g(k) + g(k + 1)); }
-        cudaMemcpyToSymbol(c_tbc_taps, taps, sizeof taps);
+        const double r = -0.26794919243112270647;
+        double rp[TBC_NPOW];
+        for (int i = 0; i < TBC_NPOW; ++i) rp[i] = pow(r, (double)i);
+        cudaMemcpyToSymbol(c_tbc_rpow, rp, sizeof rp);
         h->tbc_taps_set = true;
     }
     cudaFuncSetAttribute(tbc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -434,182 +434,142 @@ struct PilotParams {
 constexpr int PILOT_MAXOFF = 48;     // zero crossings kept per line (4.7 us of a 3.75 MHz pilot: ~17)
 constexpr int PILOT_MAXLEN = 192;    // samples in 4.7 us (<= 40 MSPS)
 
-constexpr int PILOT_WARPS = 32;
+constexpr int PILOT_WARPS = 8;       // lines per CTA of the per-line kernel
+constexpr int PILOT_MED_THREADS = 1024;
 
-__global__ void __launch_bounds__(32 * PILOT_WARPS) refine_pilot_kernel(const PilotParams p, double* ws_offsets /*[nfields][ll_stride][MAXOFF]*/,
-                                                                       int* ws_count /*[nfields][ll_stride]*/) {
-    // dynamic shared memory: first the staged pilot windows (float64 [PILOT_WARPS][PILOT_MAXLEN]), later
-    // (after a barrier) the selection histogram and list
-    LDD_DYN_SMEM(psm);
-    double* s_pil = (double*)psm + (size_t)(threadIdx.x >> 5) * PILOT_MAXLEN;   // pilot = flip(demod - demod_05), this warp's line
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Per line (one warp each, grid over all lines of all fields): the zero crossings of the pilot in the
+// 4.7 us before the line location, their phase offsets (sorted, for the line's median) and the count.
+__global__ void __launch_bounds__(32 * PILOT_WARPS) pilot_lines_kernel(const PilotParams p, double* ws_offsets /*[nfields][ll_stride][MAXOFF]*/,
+                                                                      int* ws_count /*[nfields][ll_stride]*/) {
+    __shared__ double s_win[PILOT_WARPS][PILOT_MAXLEN];     // pilot = flip(demod - demod_05) of this warp's line
+    __shared__ double s_off[PILOT_WARPS][PILOT_MAXOFF];
+    __shared__ int s_cnt[PILOT_WARPS];
+    const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = blockIdx.x * PILOT_WARPS + warp;
     const int nll = p.linecount[f] + 4;
+    if (l >= nll) return;
+    double* s_pil = s_win[warp];
+    double* so = s_off[warp];
     const long long base = p.base[f];
     const double* lin = p.linelocs_in + (size_t)f * p.ll_stride;
-    double* lout = p.linelocs_out + (size_t)f * p.ll_stride;
-    double* offs = ws_offsets + (size_t)f * p.ll_stride * PILOT_MAXOFF;
+    double* my = ws_offsets + ((size_t)f * p.ll_stride + l) * PILOT_MAXOFF;
     int* cnt = ws_count + (size_t)f * p.ll_stride;
     const double fq = p.freq;
-    for (int l = warp; l < nll; l += PILOT_WARPS) {
-        long long a = (long long)(lin[l] - fq * 4.7), b = (long long)lin[l];
-        int len = (int)(b - a);
-        double* my = offs + (size_t)l * PILOT_MAXOFF;
-        if (len <= 0 || len > PILOT_MAXLEN || base + a < 0 || base + b > p.n) {
-            if (lane == 0) { atomicOr(&p.status[f], 8); cnt[l] = 0; }
-            continue;
-        }
-        // coalesced staging; the two ire0 offsets cancel, the subtraction is done in float64 like the reference
-        for (int i = lane; i < len; i += 32) {
-            long long s = base + b - 1 - i;
-            s_pil[i] = ((double)p.demod[s]) - ((double)p.d05[s]);
-        }
-        __syncwarp();
-        if (lane == 0) {
-            int n = 0;
-            auto pil = [&](long long i) -> double { return s_pil[i]; };
-            double adjfreq = fq;
-            if (l > 1) adjfreq /= (lin[l] - lin[l - 1]) / p.linelen;
-            int i = 0;
-            while (i < len) {
-                double v = s_pil[i];
-                if (v >= -300000 && v <= -100000) {
-                    double zc;
-                    if (calczc(pil, len, i, 0.0, 10, &zc)) {
-                        double zcp = zc / (adjfreq / 3.75);
-                        if (n < PILOT_MAXOFF) my[n] = zcp - floor(zcp);
-                        ++n;
-                        i = (int)(zc + 1);
-                    }
+    long long a = (long long)(lin[l] - fq * 4.7), b = (long long)lin[l];
+    int len = (int)(b - a);
+    if (len <= 0 || len > PILOT_MAXLEN || base + a < 0 || base + b > p.n) {
+        if (lane == 0) { atomicOr(&p.status[f], 8); cnt[l] = 0; }
+        return;
+    }
+    // coalesced staging; the two ire0 offsets cancel, the subtraction is done in float64 like the reference
+    for (int i = lane; i < len; i += 32) {
+        long long s = base + b - 1 - i;
+        s_pil[i] = ((double)p.demod[s]) - ((double)p.d05[s]);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int n = 0;
+        auto pil = [&](long long i) -> double { return s_pil[i]; };
+        double adjfreq = fq;
+        if (l > 1) adjfreq /= (lin[l] - lin[l - 1]) / p.linelen;
+        int i = 0;
+        while (i < len) {
+            double v = s_pil[i];
+            if (v >= -300000 && v <= -100000) {
+                double zc;
+                if (calczc(pil, len, i, 0.0, 10, &zc)) {
+                    double zcp = zc / (adjfreq / 3.75);
+                    if (n < PILOT_MAXOFF) so[n] = zcp - floor(zcp);
+                    ++n;
+                    i = (int)(zc + 1);
                 }
-                ++i;
             }
-            if (n > PILOT_MAXOFF) { atomicOr(&p.status[f], 8); n = PILOT_MAXOFF; }
-            // "if len(offsets) >= 3": the dict has l+1 entries at this point
-            if (l + 1 >= 3) {
-                int m = n >= 2 ? n - 2 : 0;
-                for (int k = 0; k < m; ++k) my[k] = my[k + 1];
-                n = m;
-            } else {
-                n = 0;
-            }
-            cnt[l] = n;
+            ++i;
         }
-        __syncwarp();
+        if (n > PILOT_MAXOFF) { atomicOr(&p.status[f], 8); n = PILOT_MAXOFF; }
+        // "if len(offsets) >= 3": the dict has l+1 entries at this point; offsets[1:-1] are kept
+        s_cnt[warp] = (l + 1 >= 3 && n >= 2) ? n - 2 : 0;
+    }
+    __syncwarp();
+    const int n = s_cnt[warp];
+    // rank sort of so[1 .. n] into the workspace (ties keep their order)
+    for (int i = lane; i < n; i += 32) {
+        const double x = so[1 + i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const double y = so[1 + j];
+            rank += (y < x) || (y == x && j < i);
+        }
+        my[rank] = x;
+    }
+    if (lane == 0) cnt[l] = n;
+}
+
+// Per field: np.median over all kept offsets of the field (exact order statistics by a bitonic sort in
+// shared memory), the target phase, and the shifted line locations.
+__global__ void __launch_bounds__(PILOT_MED_THREADS) pilot_median_kernel(const PilotParams p, const double* ws_offsets, const int* ws_count) {
+    LDD_DYN_SMEM(psm);
+    double* s_val = (double*)psm;                         // [npow2]
+    __shared__ int s_start[320 + 8];
+    __shared__ int s_total;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int nll = p.linecount[f] + 4;
+    const double* lin = p.linelocs_in + (size_t)f * p.ll_stride;
+    double* lout = p.linelocs_out + (size_t)f * p.ll_stride;
+    const double* offs = ws_offsets + (size_t)f * p.ll_stride * PILOT_MAXOFF;
+    const int* cnt = ws_count + (size_t)f * p.ll_stride;
+    const double fq = p.freq;
+    if (tid < 32) {
+        // exclusive prefix of the line counts (nll <= 320 + 4: ten lines per lane)
+        int run = 0;
+        for (int l0 = 0; l0 < nll; l0 += 32) {
+            const int l = l0 + tid;
+            const int c = l < nll ? cnt[l] : 0;
+            int incl = c;
+            for (int d = 1; d < 32; d <<= 1) {
+                int up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (tid >= d) incl += up;
+            }
+            if (l < nll) s_start[l] = run + incl - c;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (tid == 0) s_total = run;
     }
     __syncthreads();
-    // median of all offsets (np.median(alloffsets)): exact order statistics by multi-level histogram
-    // selection (offsets are fractional parts in [0, 1)): 4096 bins over the current range, descend
-    // into the bin holding the k-th value until it holds few enough values to sort.
-    int* s_hist = (int*)psm;                              // [4096]
-    double* s_list = (double*)(psm + 4096 * sizeof(int));   // [256]
-    __shared__ int s_n, s_bin, s_before;
-    __shared__ double s_tgt;
-    int total = 0;
-    for (int l = 0; l < nll; ++l) total += cnt[l];
-    auto kth = [&](int k) -> double {
-        double lo = 0.0, width = 1.0;          // current range [lo, lo + width)
-        int kk = k;                              // rank inside the range
-        double result = 0.0;
-        for (int level = 0; level < 6; ++level) {
-            for (int i = tid; i < 4096; i += blockDim.x) s_hist[i] = 0;
-            if (tid == 0) s_n = 0;
-            __syncthreads();
-            const double scale = 4096.0 / width;
-            for (int l = tid; l < nll; l += blockDim.x) {
-                const double* my = offs + (size_t)l * PILOT_MAXOFF;
-                for (int q = 0; q < cnt[l]; ++q) {
-                    double v = my[q];
-                    if (v >= lo && v < lo + width) {
-                        int b = (int)((v - lo) * scale);
-                        b = b > 4095 ? 4095 : b;
-                        atomicAdd(&s_hist[b], 1);
-                    }
-                }
-            }
-            __syncthreads();
-            if (tid < 32) {
-                // warp 0: each lane sums 128 consecutive bins, exclusive prefix over lanes, then the lane
-                // whose span holds rank kk walks its bins
-                int part = 0;
-                for (int b = tid * 128; b < tid * 128 + 128; ++b) part += s_hist[b];
-                int incl = part;
-                for (int d = 1; d < 32; d <<= 1) {
-                    int up = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (tid >= d) incl += up;
-                }
-                int excl = incl - part;
-                bool mine = kk >= excl && kk < incl;
-                unsigned who = __ballot_sync(0xffffffffu, mine);
-                if (who == 0) {
-                    if (tid == 0) { s_bin = 4095; s_before = incl; }       // rank beyond the range's population
-                } else if (mine) {
-                    int cum = excl, b = tid * 128;
-                    for (; b < tid * 128 + 127; ++b) { if (cum + s_hist[b] > kk) break; cum += s_hist[b]; }
-                    s_bin = b;
-                    s_before = cum;
-                }
-            }
-            __syncthreads();
-            const int bin = s_bin, inbin = s_hist[bin];
-            const double blo = lo + (double)bin / scale, bhi = lo + (double)(bin + 1) / scale;
-            if (inbin <= 256 || level == 5) {
-                // gather the bin's values (re-binning decides membership, so edges are consistent)
-                for (int l = tid; l < nll; l += blockDim.x) {
-                    const double* my = offs + (size_t)l * PILOT_MAXOFF;
-                    for (int q = 0; q < cnt[l]; ++q) {
-                        double v = my[q];
-                        if (v >= lo && v < lo + width) {
-                            int b = (int)((v - lo) * scale);
-                            b = b > 4095 ? 4095 : b;
-                            if (b == bin) { int at = atomicAdd(&s_n, 1); if (at < 256) s_list[at] = v; }
-                        }
-                    }
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    int n = s_n < 256 ? s_n : 256;
-                    for (int i = 1; i < n; ++i) {
-                        double x = s_list[i];
-                        int j = i - 1;
-                        while (j >= 0 && s_list[j] > x) { s_list[j + 1] = s_list[j]; --j; }
-                        s_list[j + 1] = x;
-                    }
-                    int r = kk - s_before;
-                    r = r < 0 ? 0 : (r >= n ? n - 1 : r);
-                    s_list[0] = s_list[r];
-                }
-                __syncthreads();
-                result = s_list[0];
-                __syncthreads();
-                return result;
-            }
-            kk -= s_before;
-            lo = blo;
-            width = bhi - blo;
-            __syncthreads();
-        }
-        return result;
-    };
+    const int total = s_total;
+    int np2 = 2;
+    while (np2 < total) np2 <<= 1;
     double tgt = 0;
     if (total > 0) {
-        double med = (total & 1) ? kth(total / 2) : (kth(total / 2 - 1) + kth(total / 2)) / 2.0;
+        for (int i = tid; i < np2; i += PILOT_MED_THREADS) s_val[i] = 1e300;      // offsets are fractional parts, < 1
+        __syncthreads();
+        for (int l = tid; l < nll; l += PILOT_MED_THREADS) {
+            const int c = cnt[l], at = s_start[l];
+            const double* my = offs + (size_t)l * PILOT_MAXOFF;
+            for (int q = 0; q < c; ++q) s_val[at + q] = my[q];
+        }
+        __syncthreads();
+        for (int k = 2; k <= np2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (np2 >> 1); t += PILOT_MED_THREADS) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));     // element without bit j
+                    const int q = i | j;
+                    const bool up = (i & k) == 0;
+                    const double x = s_val[i], y = s_val[q];
+                    if ((x > y) == up) { s_val[i] = y; s_val[q] = x; }
+                }
+                __syncthreads();
+            }
+        }
+        const double med = (total & 1) ? s_val[total / 2] : (s_val[total / 2 - 1] + s_val[total / 2]) / 2.0;
         if (med >= 0.25 && med <= 0.75) tgt = .5;
     }
-    if (tid == 0) s_tgt = tgt;
-    __syncthreads();
-    tgt = s_tgt;
-    for (int l = tid; l < nll; l += blockDim.x) {
+    for (int l = tid; l < nll; l += PILOT_MED_THREADS) {
         double v = lin[l];
-        int n = cnt[l];
+        const int n = cnt[l];
         if (n > 0) {
-            double* my = offs + (size_t)l * PILOT_MAXOFF;
-            for (int i = 1; i < n; ++i) {          // sort the (short) list for its median
-                double x = my[i];
-                int j = i - 1;
-                while (j >= 0 && my[j] > x) { my[j + 1] = my[j]; --j; }
-                my[j + 1] = x;
-            }
-            double med = (n & 1) ? my[n / 2] : (my[n / 2 - 1] + my[n / 2]) / 2.0;
+            const double* my = offs + (size_t)l * PILOT_MAXOFF;    // sorted by pilot_lines_kernel
+            const double med = (n & 1) ? my[n / 2] : (my[n / 2 - 1] + my[n / 2]) / 2.0;
             v += (tgt - med) * (fq / 3.75) * .25;
         }
         lout[l] = v;
@@ -890,10 +850,15 @@ extern "C" int ldd_refine_pilot(ldd_handle* h, const float* demod_dev, const flo
     p.demod = demod_dev; p.d05 = d05_dev; p.n = n; p.freq = h->cfg.freq_hz / 1e6; p.linelen = h->cfg.linelen;
     p.base = base_dev; p.linecount = linecount_dev; p.ll_stride = ll_stride; p.linelocs_in = linelocs_in_dev;
     p.linelocs_out = linelocs_out_dev; p.status = status_dev;
-    const size_t psmem = (size_t)PILOT_WARPS * PILOT_MAXLEN * sizeof(double);
-    cudaFuncSetAttribute(refine_pilot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
-    LDD_LAUNCH(refine_pilot_kernel, dim3(nfields), dim3(32 * PILOT_WARPS), psmem, st, p, offs, cnt);
-    return launch_status(h, "refine_pilot_kernel");
+    if (ll_stride > 320 + 8) return LDD_EINVAL;
+    LDD_LAUNCH(pilot_lines_kernel, dim3((ll_stride + PILOT_WARPS - 1) / PILOT_WARPS, nfields), dim3(32 * PILOT_WARPS), 0, st, p, offs, cnt);
+    // bitonic sort buffer: all kept offsets of a field, padded to a power of two
+    size_t npow = 2;
+    while (npow < (size_t)ll_stride * PILOT_MAXOFF) npow <<= 1;
+    const size_t psmem = npow * sizeof(double);
+    cudaFuncSetAttribute(pilot_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+    LDD_LAUNCH(pilot_median_kernel, dim3(nfields), dim3(PILOT_MED_THREADS), psmem, st, p, (const double*)offs, (const int*)cnt);
+    return launch_status(h, "pilot kernels");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -102,6 +102,73 @@ __device__ inline void tangle(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __restrict_
     }
 }
 
+// Compile-time variants (M, NT constants): the table values of a batch of iterations are fetched before
+// the batch's arithmetic, so that a thread has several L2 round trips in flight instead of one per iteration.
+template <class T, bool PAD, int M, int NT>
+__device__ inline void untangle_static(Cx<T>* Z, const Cx<T>* __restrict__ WN, int tid) {
+    constexpr int IT = (M / 2) / NT, B = sizeof(T) == 4 ? IT : (IT % 4 == 0 ? 4 : 1);
+    const T half = (T)0.5;
+    LDD_UNROLL
+    for (int it0 = 0; it0 < IT; it0 += B) {
+        Cx<T> w[B];
+        LDD_UNROLL
+        for (int i = 0; i < B; ++i) w[i] = WN[tid + (it0 + i) * NT];
+        LDD_UNROLL
+        for (int i = 0; i < B; ++i) {
+            const int k = tid + (it0 + i) * NT;
+            if (it0 + i == 0 && k == 0) {
+                Cx<T> z = Z[0];
+                Z[0] = mk<T>(z.x + z.y, z.x - z.y);
+            } else {
+                const int ik = pidx<PAD>(k), im = pidx<PAD>(M - k);
+                Cx<T> a = Z[ik], b = conj(Z[im]);
+                Cx<T> E = scale(a + b, half);
+                Cx<T> Od = scale(mul_mj(a - b), half);
+                Cx<T> Tw = w[i] * Od;
+                Z[ik] = E + Tw;
+                Z[im] = conj(E - Tw);
+            }
+        }
+    }
+    if (tid == 0) Z[pidx<PAD>(M / 2)] = conj(Z[pidx<PAD>(M / 2)]);      // k = M/2 pairs with itself
+}
+
+template <class T, bool PAD, int M, int NT>
+__device__ inline void tangle_static(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __restrict__ F, const Cx<T>* __restrict__ WN, int tid) {
+    constexpr int IT = (M / 2) / NT, B = (IT % 4 == 0) ? (sizeof(T) == 4 ? 4 : 2) : 1;
+    const T half = (T)0.5;
+    LDD_UNROLL
+    for (int it0 = 0; it0 < IT; it0 += B) {
+        Cx<T> fa[B], fb[B], w[B];
+        LDD_UNROLL
+        for (int i = 0; i < B; ++i) {
+            const int k = tid + (it0 + i) * NT;
+            fa[i] = F[k];
+            fb[i] = F[M - k];
+            w[i] = WN[k];
+        }
+        LDD_UNROLL
+        for (int i = 0; i < B; ++i) {
+            const int k = tid + (it0 + i) * NT;
+            if (it0 + i == 0 && k == 0) {
+                Cx<T> d = D[0];
+                T y0 = d.x * fa[i].x, ym = d.y * fb[i].x;
+                Q[0] = mk<T>((y0 + ym) * half, -(y0 - ym) * half);
+            } else {
+                const int ik = pidx<PAD>(k), im = pidx<PAD>(M - k);
+                Cx<T> a = D[ik] * fa[i], b = conj(D[im] * fb[i]);
+                Cx<T> E = scale(a + b, half);
+                Cx<T> Od = mulc(scale(a - b, half), w[i]);
+                Cx<T> q = E + mul_pj(Od);
+                Cx<T> qm = conj(E) + mul_pj(conj(Od));
+                Q[ik] = conj(q);
+                Q[im] = conj(qm);
+            }
+        }
+    }
+    if (tid == 0) Q[pidx<PAD>(M / 2)] = D[pidx<PAD>(M / 2)] * F[M / 2];   // k = M/2: q = conj(a), stored conj(q)
+}
+
 // SP: the block arrays live in the global scratch and a padded shared-memory buffer is the ping-pong
 // partner of every length-M transform (every second Stockham pass stays on chip: the float64 lane is
 // bound by L2 traffic, ~7 TB/s chip-wide at 9 Gsamples/s).
@@ -128,9 +195,21 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         if (SP) sp = (Cx<T>*)smem;
     }
     const bool sp_ok = SP && ((CM ? static_npass(CM ? CM : 2) : p.plan_m.npass) & 1) == 0;
+    // compile-time plan for 8192 points on 512 threads: per-thread twiddles in shared memory
+    constexpr bool TW8K = (CM == 8192 && NT == 512 && sizeof(T) == 4);
+    Cx<T>* stw = nullptr;
+    if constexpr (TW8K) {
+        __shared__ Cx<T> s_tw[3 * NT];
+        stw = s_tw;
+        fft_tw_fill<T, CM, NT>(stw, WM, tid);
+        __syncthreads();
+    }
     // length-M transform of `a`; `other` is a free array usable as the partner when shared memory is not
     auto FFTM = [&](Cx<T>* a, Cx<T>* other) -> Cx<T>* {
-        if constexpr (CM != 0) {
+        if constexpr (TW8K) {
+            if (SP) return fft8k_run<T, PAD, true>(a, sp, stw, tid);
+            return fft8k_run<T, PAD, PAD>(a, other, stw, tid);
+        } else if constexpr (CM != 0) {
             if (SP && sp_ok) return fft_run_static<T, CM, NT, PAD, true>(a, sp, WM, tid);
             return fft_run_static<T, CM, NT, PAD, PAD>(a, other, WM, tid);
         } else {
@@ -165,7 +244,26 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         const int keep0 = p.blockcut, keep1 = p.blockcut + (int)copylen;
 
         // A. samples -> z[n] = x[2n] + j x[2n+1]
-        if (p.fmt == LDD_FMT_U8 && ((in0 & 1) == 0) && ((((uintptr_t)p.rf) & 1) == 0)) {
+        bool loaded = false;
+        if constexpr (CM != 0) {
+            if (p.fmt == LDD_FMT_U8 && ((((uintptr_t)p.rf + (uintptr_t)in0) & 3) == 0)) {
+                // four samples per 32-bit load, all loads of a thread in flight together
+                constexpr int IT = CM / 2 / NT;
+                const unsigned* r32 = (const unsigned*)((const unsigned char*)p.rf + in0);
+                unsigned v[IT];
+                LDD_UNROLL
+                for (int i = 0; i < IT; ++i) v[i] = r32[tid + i * NT];
+                LDD_UNROLL
+                for (int i = 0; i < IT; ++i) {
+                    const int n = 2 * (tid + i * NT);
+                    b0[IX(n)] = mk<T>((T)(int)(v[i] & 0xffu), (T)(int)((v[i] >> 8) & 0xffu));
+                    b0[IX(n + 1)] = mk<T>((T)(int)((v[i] >> 16) & 0xffu), (T)(int)(v[i] >> 24));
+                }
+                loaded = true;
+            }
+        }
+        if (loaded) {
+        } else if (p.fmt == LDD_FMT_U8 && ((in0 & 1) == 0) && ((((uintptr_t)p.rf) & 1) == 0)) {
             const unsigned short* r16 = (const unsigned short*)((const unsigned char*)p.rf + in0);
             for (int n = tid; n < M; n += nthr) {
                 unsigned v = r16[n];
@@ -184,7 +282,8 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         Cx<T>* X = FFTM(b0, b1);
         Cx<T>* f1 = (X == b0) ? b1 : b0;      // free
         Cx<T>* f2 = b2;                        // free
-        untangle<T, PAD>(X, M, WN, tid, nthr);
+        if constexpr (CM != 0) untangle_static<T, PAD, CM, NT>(X, WN, tid);
+        else untangle<T, PAD>(X, M, WN, tid, nthr);
         __syncthreads();
 
         // D. analog audio, phase 1 (lddecode_core.py:322-326): two length-A inverse transforms of a
@@ -235,26 +334,44 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         //    V[k] = (Y[k] - Y[k+M]) W_N^{-k}; stored conjugated for inverse-by-forward.
         Cx<T>* U = f1;
         Cx<T>* V = f2;
-        for (int k = tid; k <= M / 2; k += nthr) {
+        auto estep = [&](int k, Cx<T> h0, Cx<T> h1, Cx<T> h2, Cx<T> h3, Cx<T> w) {   // Hv[k], Hv[k+M], Hv[M-k], Hv[2M-k], WN[k]
             if (k == 0) {
                 Cx<T> x = X[0];
-                Cx<T> y0 = scale(Hv[0], x.x), y1 = scale(Hv[M], x.y);
+                Cx<T> y0 = scale(h0, x.x), y1 = scale(h1, x.y);
                 U[0] = conj(y0 + y1);
                 V[0] = conj(y0 - y1);
             } else {
                 const int ik = IX(k), im = IX(M - k);
                 Cx<T> xa = X[ik], xb = X[im];
-                Cx<T> y0 = xa * Hv[k], y1 = conj(xb) * Hv[k + M];
+                Cx<T> y0 = xa * h0, y1 = conj(xb) * h1;
                 U[ik] = conj(y0 + y1);
-                V[ik] = conj(mulc(y0 - y1, WN[k]));
+                V[ik] = conj(mulc(y0 - y1, w));
                 if (k != M - k) {
-                    Cx<T> z0 = xb * Hv[M - k], z1 = conj(xa) * Hv[2 * M - k];
+                    Cx<T> z0 = xb * h2, z1 = conj(xa) * h3;
                     U[im] = conj(z0 + z1);
                     // W_N^{-(M-k)} = -conj(W_N^{-k}) = -W_N^{k}
                     Cx<T> d = z0 - z1;
-                    V[im] = conj(mk<T>(-d.x, -d.y) * WN[k]);
+                    V[im] = conj(mk<T>(-d.x, -d.y) * w);
                 }
             }
+        };
+        if constexpr (CM != 0) {
+            constexpr int IT = CM / 2 / NT, B = (IT % 4 == 0) ? (sizeof(T) == 4 ? 4 : 2) : 1;
+            LDD_UNROLL
+            for (int it0 = 0; it0 < IT; it0 += B) {
+                Cx<T> h0[B], h1[B], h2[B], h3[B], w[B];
+                LDD_UNROLL
+                for (int i = 0; i < B; ++i) {
+                    const int k = tid + (it0 + i) * NT;
+                    h0[i] = Hv[k]; h1[i] = Hv[k + M]; h2[i] = Hv[M - k]; h3[i] = Hv[(2 * M - k) & (2 * M - 1)]; w[i] = WN[k];
+                }
+                LDD_UNROLL
+                for (int i = 0; i < B; ++i) estep(tid + (it0 + i) * NT, h0[i], h1[i], h2[i], h3[i], w[i]);
+            }
+            if (tid == 0) estep(M / 2, Hv[M / 2], Hv[M / 2 + M], Hv[M / 2], Hv[M / 2 + M], WN[M / 2]);
+        } else {
+            for (int k = tid; k <= M / 2; k += nthr)
+                estep(k, Hv[k], Hv[k + M], Hv[M - k], Hv[(2 * M - k) & (2 * M - 1)], WN[k]);
         }
         __syncthreads();
 
@@ -265,7 +382,8 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         Cx<T>* fv;
         if (SP && sp_ok) {
             // the two transforms are independent: run them pass by pass with one barrier per pass pair
-            if constexpr (CM != 0) fft_run_pair_static<T, CM, NT, PAD, true, PAD>(U, sp, V, X, WM, tid);
+            if constexpr (TW8K) fft8k_run_pair<T, PAD, true, PAD>(U, sp, V, X, stw, tid);
+            else if constexpr (CM != 0) fft_run_pair_static<T, CM, NT, PAD, true, PAD>(U, sp, V, X, WM, tid);
             else fft_run_pair<T, PAD, true, PAD>(U, sp, V, X, p.plan_m, WM, 1, tid, nthr);
             ru = U; rv = V; fu = X; fv = X;
         } else {
@@ -312,7 +430,8 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
             g1 = even ? land : oth;
             g2 = even ? oth : land;
         }
-        untangle<T, PAD>(D, M, WN, tid, nthr);
+        if constexpr (CM != 0) untangle_static<T, PAD, CM, NT>(D, WN, tid);
+        else untangle<T, PAD>(D, M, WN, tid, nthr);
         __syncthreads();
 
         // I. post filters.  Order: video, burst, (pilot), video05 last because its whole block feeds the sync scan.
@@ -320,7 +439,8 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         for (int oi = 0; oi < 4; ++oi) {
             const int m = (0x1320 >> (4 * oi)) & 15;           // 0, 2, 3, 1
             if ((m >= p.nfilt || p.only05) && m != 1) continue;
-            tangle<T, PAD>(D, g1, (const Cx<T>*)p.F[m], M, WN, tid, nthr);
+            if constexpr (CM != 0) tangle_static<T, PAD, CM, NT>(D, g1, (const Cx<T>*)p.F[m], WN, tid);
+            else tangle<T, PAD>(D, g1, (const Cx<T>*)p.F[m], M, WN, tid, nthr);
             __syncthreads();
             Cx<T>* r = FFTM(g1, g2);
             static_assert(LDD_P_DEMOD == 0 && LDD_P_DEMOD05 == 1 && LDD_P_BURST == 3 && LDD_P_PILOT == 4, "plane order");

@@ -165,6 +165,117 @@ __device__ inline void fft_run_pair_static(Cx<T>* a1, Cx<T>* b1, Cx<T>* a2, Cx<T
     }
 }
 
+// ---- compile-time plan with per-thread twiddles -------------------------------------------------
+// For M = 16 NT (8192 points, 512 threads: passes 16, 16, 16, 2) every thread works on the same butterfly
+// index in every transform, so the base twiddle of each pass is a per-thread constant.  `stw` holds them
+// (3 NT entries, filled once per CTA by fft_tw_fill): no table lookup in global memory is left in the passes.
+template <class T, int M, int NT>
+__device__ inline void fft_tw_fill(Cx<T>* stw, const Cx<T>* __restrict__ W, int tid) {
+    static_assert(M == 16 * NT && M == 8192, "per-thread twiddles: 8192 points on 512 threads");
+    constexpr int nb = M / 16;
+    stw[tid] = W[(tid & 15) * (nb / 16)];               // pass 2: Ns = 16
+    stw[NT + tid] = W[(tid & 255) * (nb / 256)];        // pass 3: Ns = 256
+    stw[2 * NT + tid] = W[tid];                         // pass 4 (radix 2, Ns = M/2): W^(tid + i NT) = W^tid * W16^i
+}
+
+// one radix-R butterfly per thread (j = tid, M / R == number of threads)
+template <class T, int R, int M, int Ns, bool PIN, bool POUT>
+__device__ inline void fft_pass_one(const Cx<T>* src, Cx<T>* dst, Cx<T> w1, int tid) {
+    constexpr int nb = M / R;
+    Cx<T> v[R];
+    LDD_UNROLL
+    for (int r = 0; r < R; ++r) v[r] = src[pidx<PIN>(tid + r * nb)];
+    if (Ns > 1) {
+        Cx<T> p[R];
+        p[1] = w1;
+        LDD_UNROLL
+        for (int r = 2; r < R; ++r) p[r] = (r & 1) ? p[r - 1] * p[1] : p[r / 2] * p[r / 2];
+        LDD_UNROLL
+        for (int r = 1; r < R; ++r) v[r] = v[r] * p[r];
+    }
+    Dft<T, R>::run(v);
+    const int k = tid & (Ns - 1);
+    const int j0 = (tid - k) * R + k;
+    LDD_UNROLL
+    for (int r = 0; r < R; ++r) dst[pidx<POUT>(j0 + r * Ns)] = v[r];
+}
+
+// e^{-2 pi i n / 16}
+template <class T> LDD_HD inline Cx<T> w16(int n) {
+    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173, h = (T)0.70710678118654752440;
+    switch (n & 7) {
+        case 0: return mk<T>((T)1, (T)0);
+        case 1: return mk<T>(c1, -s1);
+        case 2: return mk<T>(h, -h);
+        case 3: return mk<T>(s1, -c1);
+        case 4: return mk<T>((T)0, (T)-1);
+        case 5: return mk<T>(-s1, -c1);
+        case 6: return mk<T>(-h, -h);
+        default: return mk<T>(-c1, -s1);
+    }
+}
+
+// the final radix-2 pass (Ns = M/2): M / (2 NT) butterflies per thread, j = tid + i NT
+template <class T, int M, int NT, bool PIN, bool POUT>
+__device__ inline void fft_pass_last2(const Cx<T>* src, Cx<T>* dst, Cx<T> wt, int tid) {
+    constexpr int nb = M / 2, IT = nb / NT;
+    static_assert(IT == 8, "W16 constants");
+    constexpr int G = sizeof(T) == 4 ? IT : 2;            // butterflies loaded together (register budget)
+    LDD_UNROLL
+    for (int i0 = 0; i0 < IT; i0 += G) {
+        Cx<T> a[G], b[G];
+        LDD_UNROLL
+        for (int g = 0; g < G; ++g) {
+            a[g] = src[pidx<PIN>(tid + (i0 + g) * NT)];
+            b[g] = src[pidx<PIN>(tid + (i0 + g) * NT + nb)];
+        }
+        LDD_UNROLL
+        for (int g = 0; g < G; ++g) {
+            const int i = i0 + g;
+            Cx<T> t = b[g] * (i == 0 ? wt : wt * w16<T>(i));
+            dst[pidx<POUT>(tid + i * NT)] = a[g] + t;
+            dst[pidx<POUT>(tid + i * NT + nb)] = a[g] - t;
+        }
+    }
+}
+
+// 8192-point transform on 512 threads, twiddles from stw: a -> b -> a -> b -> a (result in a).  Ends with a barrier.
+template <class T, bool PA, bool PB>
+__device__ inline Cx<T>* fft8k_run(Cx<T>* a, Cx<T>* b, const Cx<T>* stw, int tid) {
+    constexpr int M = 8192, NT = 512;
+    fft_pass_one<T, 16, M, 1, PA, PB>(a, b, mk<T>((T)1, (T)0), tid);
+    __syncthreads();
+    fft_pass_one<T, 16, M, 16, PB, PA>(b, a, stw[tid], tid);
+    __syncthreads();
+    fft_pass_one<T, 16, M, 256, PA, PB>(a, b, stw[NT + tid], tid);
+    __syncthreads();
+    fft_pass_last2<T, M, NT, PB, PA>(b, a, stw[2 * NT + tid], tid);
+    __syncthreads();
+    return a;
+}
+
+// two independent transforms, one barrier per pass pair (results in a1, a2)
+template <class T, bool PA, bool PB1, bool PB2>
+__device__ inline void fft8k_run_pair(Cx<T>* a1, Cx<T>* b1, Cx<T>* a2, Cx<T>* b2, const Cx<T>* stw, int tid) {
+    constexpr int M = 8192, NT = 512;
+    const Cx<T> one = mk<T>((T)1, (T)0);
+    fft_pass_one<T, 16, M, 1, PA, PB1>(a1, b1, one, tid);
+    fft_pass_one<T, 16, M, 1, PA, PB2>(a2, b2, one, tid);
+    __syncthreads();
+    const Cx<T> w2 = stw[tid];
+    fft_pass_one<T, 16, M, 16, PB1, PA>(b1, a1, w2, tid);
+    fft_pass_one<T, 16, M, 16, PB2, PA>(b2, a2, w2, tid);
+    __syncthreads();
+    const Cx<T> w3 = stw[NT + tid];
+    fft_pass_one<T, 16, M, 256, PA, PB1>(a1, b1, w3, tid);
+    fft_pass_one<T, 16, M, 256, PA, PB2>(a2, b2, w3, tid);
+    __syncthreads();
+    const Cx<T> w4 = stw[2 * NT + tid];
+    fft_pass_last2<T, M, NT, PB1, PA>(b1, a1, w4, tid);
+    fft_pass_last2<T, M, NT, PB2, PA>(b2, a2, w4, tid);
+    __syncthreads();
+}
+
 constexpr int static_npass(int m) { int n = 0; while (m >= 16) { m /= 16; ++n; } return n + (m > 1 ? 1 : 0); }
 
 struct FftPlan {

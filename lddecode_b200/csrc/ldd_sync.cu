@@ -135,41 +135,60 @@ __global__ void __launch_bounds__(128) peaks_merge(PeakGeom g, const long long* 
     if (!ok) atomicOr(any_unmerged, 1);
 }
 
-// Phase 2b (all chains merged -- the normal case): prefix sum of the per-segment counts by one
-// warp, then every thread block copies its share.  One CTA.
-__global__ void __launch_bounds__(1024) peaks_gather(PeakGeom g, const long long* __restrict__ pos, const double* __restrict__ val,
-                                                     const int* __restrict__ hi, const int* __restrict__ lo,
-                                                     const int* __restrict__ any_unmerged, int* __restrict__ offs,
-                                                     long long* __restrict__ out_pos, double* __restrict__ out_val, int cap,
-                                                     int* __restrict__ out_count) {
+// Phase 2b (all chains merged -- the normal case): exclusive prefix sum of the per-segment counts by one
+// CTA (1024 segments per sweep), then a grid-wide copy with one warp per segment.
+__global__ void __launch_bounds__(1024) peaks_scan(PeakGeom g, const int* __restrict__ hi, const int* __restrict__ lo,
+                                                   const int* __restrict__ any_unmerged, int* __restrict__ offs,
+                                                   int* __restrict__ out_count) {
     if (*any_unmerged) return;                  // the sequential kernel below produces the list instead
-    const int tid = threadIdx.x;
-    if (tid < 32) {
-        int run = 0;
-        for (int base = 0; base < g.nseg; base += 32) {
-            int s = base + tid;
-            int n = 0;
-            if (s < g.nseg) { n = hi[s] - lo[s]; n = n > 0 ? n : 0; }
-            int incl = n;
-            for (int d = 1; d < 32; d <<= 1) {
-                int up = __shfl_up_sync(0xffffffffu, incl, d);
-                if (tid >= d) incl += up;
-            }
-            if (s < g.nseg) offs[s] = run + incl - n;
-            run += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (tid == 0) { out_count[0] = run; out_count[1] = 0; }
-    }
+    __shared__ int s_warp[32];
+    __shared__ int s_run;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_run = 0;
     __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
-    for (int s = warp; s < g.nseg; s += nwarp) {
-        const long long* p = pos + (size_t)s * g.cap_seg;
-        const double* v = val + (size_t)s * g.cap_seg;
-        const int l = lo[s], h = hi[s], o = offs[s];
-        for (int k = l + lane; k < h; k += 32) {
-            int d = o + (k - l);
-            if (d < cap) { out_pos[d] = p[k]; out_val[d] = v[k]; }
+    for (int base = 0; base < g.nseg; base += 1024) {
+        const int s = base + tid;
+        int n = 0;
+        if (s < g.nseg) { n = hi[s] - lo[s]; n = n > 0 ? n : 0; }
+        int incl = n;
+        for (int d = 1; d < 32; d <<= 1) {
+            int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
         }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane], wi = w;
+            for (int d = 1; d < 32; d <<= 1) {
+                int up = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += up;
+            }
+            s_warp[lane] = wi - w;              // exclusive over warps
+        }
+        __syncthreads();
+        const int run = s_run;
+        if (s < g.nseg) offs[s] = run + s_warp[warp] + incl - n;
+        __syncthreads();
+        if (tid == 1023) s_run = run + s_warp[warp] + incl;
+        __syncthreads();
+    }
+    if (tid == 0) { out_count[0] = s_run; out_count[1] = 0; }
+}
+
+__global__ void __launch_bounds__(256) peaks_copy(PeakGeom g, const long long* __restrict__ pos, const double* __restrict__ val,
+                                                  const int* __restrict__ hi, const int* __restrict__ lo,
+                                                  const int* __restrict__ any_unmerged, const int* __restrict__ offs,
+                                                  long long* __restrict__ out_pos, double* __restrict__ out_val, int cap) {
+    if (*any_unmerged) return;
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= g.nseg) return;
+    const long long* p = pos + (size_t)s * g.cap_seg;
+    const double* v = val + (size_t)s * g.cap_seg;
+    const int l = lo[s], h = hi[s], o = offs[s];
+    for (int k = l + lane; k < h; k += 32) {
+        int d = o + (k - l);
+        if (d < cap) { out_pos[d] = p[k]; out_val[d] = v[k]; }
     }
 }
 
@@ -294,8 +313,9 @@ extern "C" int ldd_sync_peaks(ldd_handle* h, const double* sync_dev, long long n
     LDD_LAUNCH(peaks_phase1, dim3((g.nseg + warps - 1) / warps), dim3(32 * warps), 0, st, sync_dev, g, pos, val, cnt, iend);
     LDD_LAUNCH(peaks_merge, dim3((g.nseg + 127) / 128), dim3(128), 0, st, g, (const long long*)pos, (const int*)cnt, hi, lo, merged,
                any_unmerged);
-    LDD_LAUNCH(peaks_gather, dim3(1), dim3(1024), 0, st, g, (const long long*)pos, (const double*)val, (const int*)hi,
-               (const int*)lo, (const int*)any_unmerged, offs, peaks_dev, vals_dev, cap, count_dev);
+    LDD_LAUNCH(peaks_scan, dim3(1), dim3(1024), 0, st, g, (const int*)hi, (const int*)lo, (const int*)any_unmerged, offs, count_dev);
+    LDD_LAUNCH(peaks_copy, dim3((g.nseg + 7) / 8), dim3(256), 0, st, g, (const long long*)pos, (const double*)val, (const int*)hi,
+               (const int*)lo, (const int*)any_unmerged, (const int*)offs, peaks_dev, vals_dev, cap);
     LDD_LAUNCH(peaks_phase2, dim3(1), dim3(32), 0, st, sync_dev, g, (const long long*)pos, (const double*)val,
                (const int*)cnt, (const long long*)iend, (const int*)any_unmerged, peaks_dev, vals_dev, cap, count_dev);
     return launch_status(h, "peaks_phase1/2");

@@ -467,25 +467,70 @@ __global__ void __launch_bounds__(32 * PILOT_WARPS) pilot_lines_kernel(const Pil
         s_pil[i] = ((double)p.demod[s]) - ((double)p.d05[s]);
     }
     __syncwarp();
-    if (lane == 0) {
-        int n = 0;
-        auto pil = [&](long long i) -> double { return s_pil[i]; };
-        double adjfreq = fq;
-        if (l > 1) adjfreq /= (lin[l] - lin[l - 1]) / p.linelen;
-        int i = 0;
-        while (i < len) {
-            double v = s_pil[i];
-            if (v >= -300000 && v <= -100000) {
-                double zc;
-                if (calczc(pil, len, i, 0.0, 10, &zc)) {
-                    double zcp = zc / (adjfreq / 3.75);
-                    if (n < PILOT_MAXOFF) so[n] = zcp - floor(zcp);
-                    ++n;
-                    i = (int)(zc + 1);
-                }
+    double adjfreq = fq;
+    if (l > 1) adjfreq /= (lin[l] - lin[l - 1]) / p.linelen;
+    // The reference walks the window sample by sample: at a sample in -300k..-100k Hz it looks for the first
+    // sample >= 0 among the next 10, records that zero crossing and continues behind it.  Every run of negative
+    // samples therefore yields its closing crossing x exactly when one of the (up to 10) run samples before x
+    // lies in that band -- a per-crossing test, done here by all lanes at once; the ballot keeps the order.
+    // (If an interpolated crossing lands exactly on x the reference also skips sample x+1: lane 0 then redoes
+    // the line with the sequential walk.)
+    const unsigned FULL = 0xffffffffu;
+    int nfound = 0;
+    bool redo = false;
+    for (int x0 = 0; x0 < len; x0 += 32) {
+        const int x = x0 + lane;
+        bool hit = false;
+        double off = 0.0;
+        if (x >= 1 && x < len && s_pil[x] >= 0.0 && s_pil[x - 1] < 0.0) {
+            for (int j = x - 1; j >= 0 && j >= x - 10; --j) {
+                const double v = s_pil[j];
+                if (!(v < 0.0)) break;
+                if (v >= -300000 && v <= -100000) { hit = true; break; }
             }
-            ++i;
+            if (hit) {
+                const double a = s_pil[x - 1], bb = s_pil[x];
+                const double zc = (double)(x - 1) + (-a / (-a + bb));
+                if (zc >= (double)x) redo = true;
+                const double zcp = zc / (adjfreq / 3.75);
+                off = zcp - floor(zcp);
+            }
         }
+        const unsigned m = __ballot_sync(FULL, hit);
+        if (hit) {
+            const int at = nfound + __popc(m & ((1u << lane) - 1u));
+            if (at < PILOT_MAXOFF) so[at] = off;
+        }
+        nfound += __popc(m);
+    }
+    redo = __any_sync(FULL, redo);
+    if (redo) {
+        __syncwarp();
+        if (lane == 0) {
+            int n = 0;
+            auto pil = [&](long long i) -> double { return s_pil[i]; };
+            int i = 0;
+            while (i < len) {
+                double v = s_pil[i];
+                if (v >= -300000 && v <= -100000) {
+                    double zc;
+                    if (calczc(pil, len, i, 0.0, 10, &zc)) {
+                        double zcp = zc / (adjfreq / 3.75);
+                        if (n < PILOT_MAXOFF) so[n] = zcp - floor(zcp);
+                        ++n;
+                        i = (int)(zc + 1);
+                    }
+                }
+                ++i;
+            }
+            s_cnt[warp] = n;
+        }
+        __syncwarp();
+        nfound = s_cnt[warp];
+        __syncwarp();
+    }
+    if (lane == 0) {
+        int n = nfound;
         if (n > PILOT_MAXOFF) { atomicOr(&p.status[f], 8); n = PILOT_MAXOFF; }
         // "if len(offsets) >= 3": the dict has l+1 entries at this point; offsets[1:-1] are kept
         s_cnt[warp] = (l + 1 >= 3 && n >= 2) ? n - 2 : 0;
@@ -519,12 +564,15 @@ __global__ void __launch_bounds__(PILOT_MED_THREADS) pilot_median_kernel(const P
     const double* offs = ws_offsets + (size_t)f * p.ll_stride * PILOT_MAXOFF;
     const int* cnt = ws_count + (size_t)f * p.ll_stride;
     const double fq = p.freq;
+    __shared__ int s_cnt[320 + 8];
+    for (int l = tid; l < nll; l += PILOT_MED_THREADS) s_cnt[l] = cnt[l];
+    __syncthreads();
     if (tid < 32) {
         // exclusive prefix of the line counts (nll <= 320 + 4: ten lines per lane)
         int run = 0;
         for (int l0 = 0; l0 < nll; l0 += 32) {
             const int l = l0 + tid;
-            const int c = l < nll ? cnt[l] : 0;
+            const int c = l < nll ? s_cnt[l] : 0;
             int incl = c;
             for (int d = 1; d < 32; d <<= 1) {
                 int up = __shfl_up_sync(0xffffffffu, incl, d);
@@ -541,12 +589,16 @@ __global__ void __launch_bounds__(PILOT_MED_THREADS) pilot_median_kernel(const P
     while (np2 < total) np2 <<= 1;
     double tgt = 0;
     if (total > 0) {
-        for (int i = tid; i < np2; i += PILOT_MED_THREADS) s_val[i] = 1e300;      // offsets are fractional parts, < 1
-        __syncthreads();
-        for (int l = tid; l < nll; l += PILOT_MED_THREADS) {
-            const int c = cnt[l], at = s_start[l];
-            const double* my = offs + (size_t)l * PILOT_MAXOFF;
-            for (int q = 0; q < c; ++q) s_val[at + q] = my[q];
+        for (int i = total + tid; i < np2; i += PILOT_MED_THREADS) s_val[i] = 1e300;      // offsets are fractional parts, < 1
+        // flat, coalesced sweep over the [nll][MAXOFF] workspace; the loads do not depend on the counts
+        const int nflat = nll * PILOT_MAXOFF;
+        LDD_UNROLL
+        for (int it = 0; it < (320 + 8) * PILOT_MAXOFF / PILOT_MED_THREADS + 1; ++it) {
+            const int e = tid + it * PILOT_MED_THREADS;
+            const int ec = e < nflat ? e : 0;
+            const double v = offs[ec];
+            const int l = ec / PILOT_MAXOFF, q = ec - l * PILOT_MAXOFF;
+            if (e < nflat && q < s_cnt[l]) s_val[s_start[l] + q] = v;
         }
         __syncthreads();
         for (int k = 2; k <= np2; k <<= 1) {
@@ -566,7 +618,7 @@ __global__ void __launch_bounds__(PILOT_MED_THREADS) pilot_median_kernel(const P
     }
     for (int l = tid; l < nll; l += PILOT_MED_THREADS) {
         double v = lin[l];
-        const int n = cnt[l];
+        const int n = s_cnt[l];
         if (n > 0) {
             const double* my = offs + (size_t)l * PILOT_MAXOFF;    // sorted by pilot_lines_kernel
             const double med = (n & 1) ? my[n / 2] : (my[n / 2 - 1] + my[n / 2]) / 2.0;

@@ -50,14 +50,33 @@ struct TbcParams {
     const float* burstlevel;  // NTSC final: [nfields][ll_stride] or NULL
     float clevel_k;           // float32(327.67 * clevel)
     int* status;              // [nfields]: OR of per-line error bits (1: window outside the plane / too long)
+    int maxd;                 // longest input span this launch has shared memory for (<= TBC_MAXD)
 };
+
+// int -> double and double -> int without the conversion pipe (0 <= v < 2^31): 2^52 + v has v in its low mantissa bits
+__device__ inline double tbc_i2d(int v) {
+#ifdef LDD_EMU
+    return (double)v;
+#else
+    return __hiloint2double(0x43300000, v) - 4503599627370496.0;
+#endif
+}
+__device__ inline int tbc_floor_nonneg(double x) {        // (int)x for 0 <= x < 2^31
+#ifdef LDD_EMU
+    return (int)x;
+#else
+    int i = __double2loint(x + 4503599627370496.0);       // round to nearest
+    return tbc_i2d(i) > x ? i - 1 : i;
+#endif
+}
 
 __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
     LDD_DYN_SMEM(smem_raw);
+    const int maxq = (p.maxd + 1 + 2 * TBC_H + TBC_C - 1) / TBC_C;
     double* Ms = (double*)smem_raw;                       // M[-H .. dist+H] at index u = i + H
-    double* Lf = Ms + (TBC_MAXQ * TBC_C + 2);             // chunk sums of the causal recursion
-    double* Lb = Lf + (TBC_MAXQ + 2);                     // ... of the anti-causal one
-    float* ys = (float*)(Lb + (TBC_MAXQ + 2));            // y[-H .. dist+H] at index u, zero padded to a whole chunk
+    double* ys = Ms + (maxq * TBC_C + 2);                 // y[-H .. dist+H] at index u, zero padded to a whole chunk (float64: converted once)
+    double* Lf = ys + (maxq * TBC_C + 4);                 // chunk sums of the causal recursion
+    double* Lb = Lf + (maxq + 2);                         // ... of the anti-causal one
 
     const int tid = threadIdx.x;
     const int field = blockIdx.y, line = blockIdx.x;
@@ -70,7 +89,7 @@ __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
     const int W = p.outwidth;
     char* outbase = (char*)p.out;
     const long long base = p.base ? p.base[field] : 0;
-    if (!(b >= 0.0) || dist < 3 || dist > TBC_MAXD || base + ib + dist + 1 > p.n || base + ib < 0) {
+    if (!(b >= 0.0) || dist < 3 || dist > p.maxd || base + ib + dist + 1 > p.n || base + ib < 0) {
         if (tid == 0) atomicOr(&p.status[field], 1);
         return;
     }
@@ -85,24 +104,24 @@ __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
         const long long s0 = base + ib - TBC_H;
         const float* src = p.plane + s0;
         if (s0 >= 0 && s0 + U <= p.n) {
-            for (int i = tid; i < U; i += TBC_THREADS) ys[i] = src[i];
+            for (int i = tid; i < U; i += TBC_THREADS) ys[i] = (double)src[i];
         } else {
             for (int i = tid; i < U; i += TBC_THREADS) {
                 long long s = s0 + i;
                 s = s < 0 ? 0 : (s >= p.n ? p.n - 1 : s);
-                ys[i] = p.plane[s];
+                ys[i] = (double)p.plane[s];
             }
         }
-        for (int i = U + tid; i < nq * TBC_C + 2; i += TBC_THREADS) ys[i] = 0.f;
+        for (int i = U + tid; i < nq * TBC_C + 2; i += TBC_THREADS) ys[i] = 0.0;
     }
     __syncthreads();
     // chunk sums: Lf = sum r^(15-k) d[k], Lb = sum r^k d[k]
     auto load_d = [&](int q, double* d) {
-        const float* y = ys + q * TBC_C;
-        double ym = (double)y[0], y0 = (double)y[1];
+        const double* y = ys + q * TBC_C;
+        double ym = y[0], y0 = y[1];
         LDD_UNROLL
         for (int k = 0; k < TBC_C; ++k) {
-            const double yp = (double)y[k + 2];
+            const double yp = y[k + 2];
             const int u = 1 + q * TBC_C + k;
             d[k] = (u <= U - 2) ? 6.0 * ((ym - 2.0 * y0) + yp) : 0.0;
             ym = y0;
@@ -168,15 +187,15 @@ __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
     const double stop = (e - b) + fb;
     const double step = (stop - fb) / (double)W;
     const double wowf = p.wow ? (e - b) / (double)p.linelen : 1.0;
-    const float* y0 = ys + TBC_H;
+    const double* y0 = ys + TBC_H;
     const double sixth = 1.0 / 6.0;
     for (int j = tid; j < W; j += TBC_THREADS) {
-        double x = (double)j * step + fb;
-        int i = (int)x;
+        double x = tbc_i2d(j) * step + fb;
+        int i = tbc_floor_nonneg(x);
         if (i > dist - 1) i = dist - 1;
-        double t = x - (double)i, u = 1.0 - t;
+        double t = x - tbc_i2d(i), u = 1.0 - t;
         double Mi = M0[i], Mj = M0[i + 1];
-        double S = Mi * u * u * u * sixth + Mj * t * t * t * sixth + ((double)y0[i] - Mi * sixth) * u + ((double)y0[i + 1] - Mj * sixth) * t;
+        double S = Mi * u * u * u * sixth + Mj * t * t * t * sixth + (y0[i] - Mi * sixth) * u + (y0[i + 1] - Mj * sixth) * t;
         double hz = (S + p.plane_add) * wowf;
         size_t o = (size_t)field * (size_t)p.out_stride + (size_t)line * W + j;
         if (p.mode == 0) {
@@ -186,7 +205,7 @@ __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
             red -= p.vsync_ire;
             double v = red * p.out_scale + p.out_off;
             v = v < 0.0 ? 0.0 : (v > 65535.0 ? 65535.0 : v);
-            unsigned short q16 = (unsigned short)(v + 0.5);
+            unsigned short q16 = (unsigned short)tbc_floor_nonneg(v + 0.5);
             if (p.burstlevel && line >= 1 && line < linecount - 1 && j < 2) {
                 // burst polarity / level markers (lddecode_core.py:1144-1154)
                 float bl = p.burstlevel[(size_t)field * p.ll_stride + line];
@@ -230,7 +249,12 @@ extern "C" int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n
     double clevel = (1.0 / colorlevel) / (1700000.0 / 140.0);
     p.clevel_k = (float)(327.67 * clevel);
     p.status = status_dev;
-    size_t smem = (size_t)(TBC_MAXQ * TBC_C + 2 + 2 * (TBC_MAXQ + 2)) * sizeof(double) + (size_t)(TBC_MAXQ * TBC_C + 4) * sizeof(float);
+    // shared memory for lines up to 25 % longer than nominal (longer ones are flagged in status like lines beyond
+    // TBC_MAXD): 50 KB per CTA for PAL at 8fsc, so four CTAs share an SM
+    p.maxd = c.linelen + c.linelen / 4 + 64;
+    if (p.maxd > TBC_MAXD) p.maxd = TBC_MAXD;
+    const int maxq = (p.maxd + 1 + 2 * TBC_H + TBC_C - 1) / TBC_C;
+    size_t smem = (size_t)(2 * maxq * TBC_C + 6 + 2 * (maxq + 2)) * sizeof(double);
     if (!h->tbc_taps_set) {
         const double r = -0.26794919243112270647;
         double rp[TBC_NPOW];

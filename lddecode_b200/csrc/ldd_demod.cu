@@ -17,6 +17,9 @@
 #include "ldd_internal.h"
 
 namespace ldd {
+#ifdef LDD_F32X2
+namespace x2 {      // second build of this file: complex add / subtract as packed FADD2 (ldd_fft.cuh), selected by LDD_F32X2=1
+#endif
 
 // The planes are written once and never re-read by this kernel: store them with the streaming
 // (evict-first) hint so that ~0.9 GB of output per second of video does not push the L2-resident
@@ -120,7 +123,7 @@ __device__ inline void untangle_static(Cx<T>* Z, const Cx<T>* __restrict__ WN, i
                 Cx<T> z = Z[0];
                 Z[0] = mk<T>(z.x + z.y, z.x - z.y);
             } else {
-                const int ik = pidx<PAD>(k), im = pidx<PAD>(M - k);
+                const int ik = pidx<PAD>(tid) + (it0 + i) * pstride<PAD>(NT), im = pidx<PAD>(M - tid) - (it0 + i) * pstride<PAD>(NT);
                 Cx<T> a = Z[ik], b = conj(Z[im]);
                 Cx<T> E = scale(a + b, half);
                 Cx<T> Od = scale(mul_mj(a - b), half);
@@ -155,7 +158,7 @@ __device__ inline void tangle_static(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __re
                 T y0 = d.x * fa[i].x, ym = d.y * fb[i].x;
                 Q[0] = mk<T>((y0 + ym) * half, -(y0 - ym) * half);
             } else {
-                const int ik = pidx<PAD>(k), im = pidx<PAD>(M - k);
+                const int ik = pidx<PAD>(tid) + (it0 + i) * pstride<PAD>(NT), im = pidx<PAD>(M - tid) - (it0 + i) * pstride<PAD>(NT);
                 Cx<T> a = D[ik] * fa[i], b = conj(D[im] * fb[i]);
                 Cx<T> E = scale(a + b, half);
                 Cx<T> Od = mulc(scale(a - b, half), w[i]);
@@ -334,14 +337,13 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         //    V[k] = (Y[k] - Y[k+M]) W_N^{-k}; stored conjugated for inverse-by-forward.
         Cx<T>* U = f1;
         Cx<T>* V = f2;
-        auto estep = [&](int k, Cx<T> h0, Cx<T> h1, Cx<T> h2, Cx<T> h3, Cx<T> w) {   // Hv[k], Hv[k+M], Hv[M-k], Hv[2M-k], WN[k]
+        auto estep = [&](int k, int ik, int im, Cx<T> h0, Cx<T> h1, Cx<T> h2, Cx<T> h3, Cx<T> w) {   // Hv[k], Hv[k+M], Hv[M-k], Hv[2M-k], WN[k]
             if (k == 0) {
                 Cx<T> x = X[0];
                 Cx<T> y0 = scale(h0, x.x), y1 = scale(h1, x.y);
                 U[0] = conj(y0 + y1);
                 V[0] = conj(y0 - y1);
             } else {
-                const int ik = IX(k), im = IX(M - k);
                 Cx<T> xa = X[ik], xb = X[im];
                 Cx<T> y0 = xa * h0, y1 = conj(xb) * h1;
                 U[ik] = conj(y0 + y1);
@@ -366,12 +368,13 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
                     h0[i] = Hv[k]; h1[i] = Hv[k + M]; h2[i] = Hv[M - k]; h3[i] = Hv[(2 * M - k) & (2 * M - 1)]; w[i] = WN[k];
                 }
                 LDD_UNROLL
-                for (int i = 0; i < B; ++i) estep(tid + (it0 + i) * NT, h0[i], h1[i], h2[i], h3[i], w[i]);
+                for (int i = 0; i < B; ++i)
+                    estep(tid + (it0 + i) * NT, IX(tid) + (it0 + i) * pstride<PAD>(NT), IX(M - tid) - (it0 + i) * pstride<PAD>(NT), h0[i], h1[i], h2[i], h3[i], w[i]);
             }
-            if (tid == 0) estep(M / 2, Hv[M / 2], Hv[M / 2 + M], Hv[M / 2], Hv[M / 2 + M], WN[M / 2]);
+            if (tid == 0) estep(M / 2, IX(M / 2), IX(M / 2), Hv[M / 2], Hv[M / 2 + M], Hv[M / 2], Hv[M / 2 + M], WN[M / 2]);
         } else {
             for (int k = tid; k <= M / 2; k += nthr)
-                estep(k, Hv[k], Hv[k + M], Hv[M - k], Hv[(2 * M - k) & (2 * M - 1)], WN[k]);
+                estep(k, IX(k), IX(M - k), Hv[k], Hv[k + M], Hv[M - k], Hv[(2 * M - k) & (2 * M - 1)], WN[k]);
         }
         __syncthreads();
 
@@ -596,4 +599,7 @@ int launch_demod_f32(const DemodParams& p, int grid, int threads, cudaStream_t s
     return launch_variant<float, 512, false>(p, grid, st, 0);
 }
 
+#ifdef LDD_F32X2
+}  // namespace x2
+#endif
 }  // namespace ldd

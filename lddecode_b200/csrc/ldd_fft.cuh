@@ -19,6 +19,21 @@ struct alignas(2 * sizeof(T)) Cx {
 template <class T> LDD_HD inline Cx<T> mk(T a, T b) { Cx<T> r; r.x = a; r.y = b; return r; }
 template <class T> LDD_HD inline Cx<T> operator+(Cx<T> a, Cx<T> b) { return mk<T>(a.x + b.x, a.y + b.y); }
 template <class T> LDD_HD inline Cx<T> operator-(Cx<T> a, Cx<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
+#if defined(__CUDA_ARCH__) && !defined(LDD_EMU) && defined(LDD_F32X2)
+// sm_100 packed float32 pairs: a complex add / subtract is one instruction (FADD2) instead of two
+__device__ inline unsigned long long cx_bits(Cx<float> a) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
+__device__ inline Cx<float> cx_from(unsigned long long r) { Cx<float> a; asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r)); return a; }
+template <> __device__ inline Cx<float> operator+(Cx<float> a, Cx<float> b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(cx_bits(a)), "l"(cx_bits(b)));
+    return cx_from(r);
+}
+template <> __device__ inline Cx<float> operator-(Cx<float> a, Cx<float> b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(cx_bits(a)), "l"(cx_bits(b)));
+    return cx_from(r);
+}
+#endif
 template <class T> LDD_HD inline Cx<T> operator*(Cx<T> a, Cx<T> b) { return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 template <class T> LDD_HD inline Cx<T> conj(Cx<T> a) { return mk<T>(a.x, -a.y); }
 template <class T> LDD_HD inline Cx<T> scale(Cx<T> a, T s) { return mk<T>(a.x * s, a.y * s); }
@@ -91,6 +106,9 @@ template <class T> struct Dft<T, 16> {
 // would put all 32 lanes on the same two banks).  Global-memory lane: identity.
 template <bool PAD> LDD_HD inline int pidx(int i) { return PAD ? i + (i >> 4) : i; }
 template <bool PAD> LDD_HD inline int pspan(int n) { return PAD ? n + (n >> 4) : n; }
+// pidx(i + n) - pidx(i) for n a multiple of 16: a compile-time element stride, so that a thread's accesses of a
+// pass are one base address plus immediate offsets
+template <bool PAD> LDD_HD constexpr int pstride(int n) { return PAD ? n + n / 16 : n; }
 
 // ---- one Stockham pass -------------------------------------------------------------------------
 // src, dst: length-M sequences.  Ns: product of the radices of the passes already done.
@@ -182,9 +200,11 @@ __device__ inline void fft_tw_fill(Cx<T>* stw, const Cx<T>* __restrict__ W, int 
 template <class T, int R, int M, int Ns, bool PIN, bool POUT>
 __device__ inline void fft_pass_one(const Cx<T>* src, Cx<T>* dst, Cx<T> w1, int tid) {
     constexpr int nb = M / R;
+    static_assert(nb % 16 == 0 && (Ns == 1 || Ns % 16 == 0), "padded strides");
     Cx<T> v[R];
+    const Cx<T>* s0 = src + pidx<PIN>(tid);
     LDD_UNROLL
-    for (int r = 0; r < R; ++r) v[r] = src[pidx<PIN>(tid + r * nb)];
+    for (int r = 0; r < R; ++r) v[r] = s0[r * pstride<PIN>(nb)];
     if (Ns > 1) {
         Cx<T> p[R];
         p[1] = w1;
@@ -196,8 +216,9 @@ __device__ inline void fft_pass_one(const Cx<T>* src, Cx<T>* dst, Cx<T> w1, int 
     Dft<T, R>::run(v);
     const int k = tid & (Ns - 1);
     const int j0 = (tid - k) * R + k;
+    Cx<T>* d0 = dst + pidx<POUT>(j0);
     LDD_UNROLL
-    for (int r = 0; r < R; ++r) dst[pidx<POUT>(j0 + r * Ns)] = v[r];
+    for (int r = 0; r < R; ++r) d0[Ns == 1 ? r : r * pstride<POUT>(Ns)] = v[r];     // Ns == 1: j0 = R tid, r < 16 stays in its group of 16
 }
 
 // e^{-2 pi i n / 16}
@@ -221,20 +242,22 @@ __device__ inline void fft_pass_last2(const Cx<T>* src, Cx<T>* dst, Cx<T> wt, in
     constexpr int nb = M / 2, IT = nb / NT;
     static_assert(IT == 8, "W16 constants");
     constexpr int G = sizeof(T) == 4 ? IT : 2;            // butterflies loaded together (register budget)
+    const Cx<T>* s0 = src + pidx<PIN>(tid);
+    Cx<T>* d0 = dst + pidx<POUT>(tid);
     LDD_UNROLL
     for (int i0 = 0; i0 < IT; i0 += G) {
         Cx<T> a[G], b[G];
         LDD_UNROLL
         for (int g = 0; g < G; ++g) {
-            a[g] = src[pidx<PIN>(tid + (i0 + g) * NT)];
-            b[g] = src[pidx<PIN>(tid + (i0 + g) * NT + nb)];
+            a[g] = s0[(i0 + g) * pstride<PIN>(NT)];
+            b[g] = s0[(i0 + g) * pstride<PIN>(NT) + pstride<PIN>(nb)];
         }
         LDD_UNROLL
         for (int g = 0; g < G; ++g) {
             const int i = i0 + g;
             Cx<T> t = b[g] * (i == 0 ? wt : wt * w16<T>(i));
-            dst[pidx<POUT>(tid + i * NT)] = a[g] + t;
-            dst[pidx<POUT>(tid + i * NT + nb)] = a[g] - t;
+            d0[i * pstride<POUT>(NT)] = a[g] + t;
+            d0[i * pstride<POUT>(NT) + pstride<POUT>(nb)] = a[g] - t;
         }
     }
 }

@@ -550,8 +550,8 @@ __global__ void __launch_bounds__(32 * PILOT_WARPS) pilot_lines_kernel(const Pil
     if (lane == 0) cnt[l] = n;
 }
 
-// Per field: np.median over all kept offsets of the field (exact order statistics by a bitonic sort in
-// shared memory), the target phase, and the shifted line locations.
+// Per field: np.median over all kept offsets of the field (exact order statistics by histogram selection over
+// the values gathered in shared memory), the target phase, and the shifted line locations.
 __global__ void __launch_bounds__(PILOT_MED_THREADS) pilot_median_kernel(const PilotParams p, const double* ws_offsets, const int* ws_count) {
     LDD_DYN_SMEM(psm);
     double* s_val = (double*)psm;                         // [npow2]
@@ -565,6 +565,11 @@ __global__ void __launch_bounds__(PILOT_MED_THREADS) pilot_median_kernel(const P
     const int* cnt = ws_count + (size_t)f * p.ll_stride;
     const double fq = p.freq;
     __shared__ int s_cnt[320 + 8];
+    __shared__ int s_hist[4096];
+    __shared__ double s_list[1024];
+    __shared__ int s_wsum[32];
+    __shared__ int s_n, s_bin, s_before, s_inrange;
+    __shared__ double s_result;
     for (int l = tid; l < nll; l += PILOT_MED_THREADS) s_cnt[l] = cnt[l];
     __syncthreads();
     if (tid < 32) {
@@ -585,11 +590,8 @@ __global__ void __launch_bounds__(PILOT_MED_THREADS) pilot_median_kernel(const P
     }
     __syncthreads();
     const int total = s_total;
-    int np2 = 2;
-    while (np2 < total) np2 <<= 1;
     double tgt = 0;
     if (total > 0) {
-        for (int i = total + tid; i < np2; i += PILOT_MED_THREADS) s_val[i] = 1e300;      // offsets are fractional parts, < 1
         // flat, coalesced sweep over the [nll][MAXOFF] workspace; the loads do not depend on the counts
         const int nflat = nll * PILOT_MAXOFF;
         LDD_UNROLL
@@ -601,19 +603,97 @@ __global__ void __launch_bounds__(PILOT_MED_THREADS) pilot_median_kernel(const P
             if (e < nflat && q < s_cnt[l]) s_val[s_start[l] + q] = v;
         }
         __syncthreads();
-        for (int k = 2; k <= np2; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < (np2 >> 1); t += PILOT_MED_THREADS) {
-                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));     // element without bit j
-                    const int q = i | j;
-                    const bool up = (i & k) == 0;
-                    const double x = s_val[i], y = s_val[q];
-                    if ((x > y) == up) { s_val[i] = y; s_val[q] = x; }
+        // k-th smallest of s_val[0 .. total): multi-level histogram selection (the offsets are fractional parts in
+        // [0, 1)): 4096 bins over the current range, descend into the bin that holds rank k until it holds few
+        // enough values to rank them directly.  Binning decides membership at every level, so edges are consistent.
+        auto kth = [&](int k) -> double {
+            double lo = 0.0, width = 1.0;
+            int kk = k;
+            for (int level = 0; level < 6; ++level) {
+                for (int i = tid; i < 4096; i += PILOT_MED_THREADS) s_hist[i] = 0;
+                if (tid == 0) s_n = 0;
+                __syncthreads();
+                const double scale = 4096.0 / width;
+                for (int i = tid; i < total; i += PILOT_MED_THREADS) {
+                    const double v = s_val[i];
+                    if (v >= lo && v < lo + width) {
+                        int bn = (int)((v - lo) * scale);
+                        bn = bn > 4095 ? 4095 : bn;
+                        atomicAdd(&s_hist[bn], 1);
+                    }
                 }
                 __syncthreads();
+                // block-wide exclusive prefix over the bins, four consecutive bins per thread
+                const int h0 = s_hist[4 * tid], h1 = s_hist[4 * tid + 1], h2 = s_hist[4 * tid + 2], h3 = s_hist[4 * tid + 3];
+                const int part = h0 + h1 + h2 + h3;
+                int incl = part;
+                for (int d = 1; d < 32; d <<= 1) {
+                    int up = __shfl_up_sync(0xffffffffu, incl, d);
+                    if ((tid & 31) >= d) incl += up;
+                }
+                if ((tid & 31) == 31) s_wsum[tid >> 5] = incl;
+                if (tid == 0) { s_bin = 4095; s_before = -1; }
+                __syncthreads();
+                if (tid < 32) {
+                    int w = s_wsum[tid], wi = w;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        int up = __shfl_up_sync(0xffffffffu, wi, d);
+                        if (tid >= d) wi += up;
+                    }
+                    s_wsum[tid] = wi - w;
+                    if (tid == 31) s_inrange = wi;
+                }
+                __syncthreads();
+                const int excl = s_wsum[tid >> 5] + incl - part;
+                if (kk >= excl && kk < excl + part) {
+                    int cum = excl, bn = 4 * tid;
+                    if (cum + h0 <= kk) { cum += h0; ++bn; if (cum + h1 <= kk) { cum += h1; ++bn; if (cum + h2 <= kk) { cum += h2; ++bn; } } }
+                    s_bin = bn;
+                    s_before = cum;
+                }
+                __syncthreads();
+                if (s_before < 0) {                       // rank beyond the range's population (cannot happen for 0 <= k < total)
+                    if (tid == 0) s_before = s_inrange - s_hist[4095];
+                    __syncthreads();
+                }
+                const int bin = s_bin, inbin = s_hist[bin], before = s_before;
+                const double blo = lo + (double)bin / scale, bhi = lo + (double)(bin + 1) / scale;
+                if (inbin <= 1024 || level == 5) {
+                    // gather the bin's members, rank them by counting (ties broken by position)
+                    for (int i = tid; i < total; i += PILOT_MED_THREADS) {
+                        const double v = s_val[i];
+                        if (v >= lo && v < lo + width) {
+                            int bn = (int)((v - lo) * scale);
+                            bn = bn > 4095 ? 4095 : bn;
+                            if (bn == bin) { int at = atomicAdd(&s_n, 1); if (at < 1024) s_list[at] = v; }
+                        }
+                    }
+                    __syncthreads();
+                    const int n = s_n < 1024 ? s_n : 1024;
+                    int r = kk - before;
+                    r = r < 0 ? 0 : (r >= n ? n - 1 : r);
+                    if (tid < n) {
+                        const double x = s_list[tid];
+                        int rank = 0;
+                        for (int j = 0; j < n; ++j) {
+                            const double y = s_list[j];
+                            rank += (y < x) || (y == x && j < tid);
+                        }
+                        if (rank == r) s_result = x;
+                    }
+                    __syncthreads();
+                    const double result = s_result;
+                    __syncthreads();
+                    return result;
+                }
+                kk -= before;
+                lo = blo;
+                width = bhi - blo;
+                __syncthreads();
             }
-        }
-        const double med = (total & 1) ? s_val[total / 2] : (s_val[total / 2 - 1] + s_val[total / 2]) / 2.0;
+            return 0.0;
+        };
+        const double med = (total & 1) ? kth(total / 2) : (kth(total / 2 - 1) + kth(total / 2)) / 2.0;
         if (med >= 0.25 && med <= 0.75) tgt = .5;
     }
     for (int l = tid; l < nll; l += PILOT_MED_THREADS) {
@@ -904,10 +984,8 @@ extern "C" int ldd_refine_pilot(ldd_handle* h, const float* demod_dev, const flo
     p.linelocs_out = linelocs_out_dev; p.status = status_dev;
     if (ll_stride > 320 + 8) return LDD_EINVAL;
     LDD_LAUNCH(pilot_lines_kernel, dim3((ll_stride + PILOT_WARPS - 1) / PILOT_WARPS, nfields), dim3(32 * PILOT_WARPS), 0, st, p, offs, cnt);
-    // bitonic sort buffer: all kept offsets of a field, padded to a power of two
-    size_t npow = 2;
-    while (npow < (size_t)ll_stride * PILOT_MAXOFF) npow <<= 1;
-    const size_t psmem = npow * sizeof(double);
+    // all kept offsets of a field
+    const size_t psmem = (size_t)ll_stride * PILOT_MAXOFF * sizeof(double);
     cudaFuncSetAttribute(pilot_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
     LDD_LAUNCH(pilot_median_kernel, dim3(nfields), dim3(PILOT_MED_THREADS), psmem, st, p, (const double*)offs, (const int*)cnt);
     return launch_status(h, "pilot kernels");

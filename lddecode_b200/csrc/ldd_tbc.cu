@@ -72,11 +72,14 @@ __device__ inline int tbc_floor_nonneg(double x) {        // (int)x for 0 <= x <
 
 __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
     LDD_DYN_SMEM(smem_raw);
+    // Both arrays are indexed by u = i + H through PX(u) = u + u/16: a thread owns 16 consecutive samples, and
+    // the padding slot per 16 puts the chunks of neighbouring threads 17 doubles apart (no bank conflicts).
     const int maxq = (p.maxd + 1 + 2 * TBC_H + TBC_C - 1) / TBC_C;
-    double* Ms = (double*)smem_raw;                       // M[-H .. dist+H] at index u = i + H
-    double* ys = Ms + (maxq * TBC_C + 2);                 // y[-H .. dist+H] at index u, zero padded to a whole chunk (float64: converted once)
-    double* Lf = ys + (maxq * TBC_C + 4);                 // chunk sums of the causal recursion
+    double* Ms = (double*)smem_raw;                       // M[-H .. dist+H]
+    double* ys = Ms + ((TBC_C + 1) * maxq + 4);           // y[-H .. dist+H], zero padded to a whole chunk (float64: converted once)
+    double* Lf = ys + ((TBC_C + 1) * maxq + 4);           // chunk sums of the causal recursion
     double* Lb = Lf + (maxq + 2);                         // ... of the anti-causal one
+#define PX(u) ((u) + ((u) >> 4))
 
     const int tid = threadIdx.x;
     const int field = blockIdx.y, line = blockIdx.x;
@@ -104,24 +107,24 @@ __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
         const long long s0 = base + ib - TBC_H;
         const float* src = p.plane + s0;
         if (s0 >= 0 && s0 + U <= p.n) {
-            for (int i = tid; i < U; i += TBC_THREADS) ys[i] = (double)src[i];
+            for (int i = tid; i < U; i += TBC_THREADS) ys[PX(i)] = (double)src[i];
         } else {
             for (int i = tid; i < U; i += TBC_THREADS) {
                 long long s = s0 + i;
                 s = s < 0 ? 0 : (s >= p.n ? p.n - 1 : s);
-                ys[i] = (double)p.plane[s];
+                ys[PX(i)] = (double)p.plane[s];
             }
         }
-        for (int i = U + tid; i < nq * TBC_C + 2; i += TBC_THREADS) ys[i] = 0.0;
+        for (int i = U + tid; i < nq * TBC_C + 2; i += TBC_THREADS) ys[PX(i)] = 0.0;
     }
     __syncthreads();
     // chunk sums: Lf = sum r^(15-k) d[k], Lb = sum r^k d[k]
     auto load_d = [&](int q, double* d) {
-        const double* y = ys + q * TBC_C;
+        const double* y = ys + q * (TBC_C + 1);              // PX(16 q + k) = 17 q + k for k < 16; k = 16, 17 sit behind the padding slot
         double ym = y[0], y0 = y[1];
         LDD_UNROLL
         for (int k = 0; k < TBC_C; ++k) {
-            const double yp = y[k + 2];
+            const double yp = y[k + 2 < TBC_C ? k + 2 : k + 3];
             const int u = 1 + q * TBC_C + k;
             d[k] = (u <= U - 2) ? 6.0 * ((ym - 2.0 * y0) + yp) : 0.0;
             ym = y0;
@@ -151,19 +154,19 @@ __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
             f = fma(f, r, d[k]);
             F[k] = f;
         }
-        double* M = Ms + 1 + q * TBC_C;
+        double* M = Ms + q * (TBC_C + 1);                   // M[k] <-> u = 1 + 16 q + k: PX = 17 q + 1 + k, behind the padding slot for k = 15
         LDD_UNROLL
         for (int k = TBC_C - 1; k >= 0; --k) {
             bk = fma(bk, r, d[k]);
-            M[k] = c * ((F[k] + bk) - d[k]);
+            M[k + 1 < TBC_C ? k + 1 : k + 2] = c * ((F[k] + bk) - d[k]);
         }
     }
     __syncthreads();
-    double* M0 = Ms + TBC_H;                              // M0[i], i = 0 .. dist
+#define M0(i) Ms[PX((i) + TBC_H)]
     {
         // not-a-knot rows -> homogeneous part (every thread solves the 2x2 system for itself)
-        const double L = M0[0] - 2.0 * M0[1] + M0[2];
-        const double R = M0[dist] - 2.0 * M0[dist - 1] + M0[dist - 2];
+        const double L = M0(0) - 2.0 * M0(1) + M0(2);
+        const double R = M0(dist) - 2.0 * M0(dist - 1) + M0(dist - 2);
         const double A = (1.0 - r) * (1.0 - r);
         const double q = (dist - 2 < TBC_NPOW) ? c_tbc_rpow[dist - 2] : 0.0;
         const double den = A * (1.0 - q * q);
@@ -174,11 +177,11 @@ __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
             if (i <= dist) {
                 double corr = alpha * c_tbc_rpow[i];
                 if (dist - i < TBC_NPOW) corr += beta * c_tbc_rpow[dist - i];
-                M0[i] += corr;
+                M0(i) += corr;
             }
         } else if (tid < 2 * TBC_NPOW) {
             const int k = tid - TBC_NPOW, i = dist - k;   // back: indices the front threads do not own
-            if (i >= TBC_NPOW) M0[i] += beta * c_tbc_rpow[k];
+            if (i >= TBC_NPOW) M0(i) += beta * c_tbc_rpow[k];
         }
     }
     __syncthreads();
@@ -187,15 +190,14 @@ __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
     const double stop = (e - b) + fb;
     const double step = (stop - fb) / (double)W;
     const double wowf = p.wow ? (e - b) / (double)p.linelen : 1.0;
-    const double* y0 = ys + TBC_H;
     const double sixth = 1.0 / 6.0;
     for (int j = tid; j < W; j += TBC_THREADS) {
         double x = tbc_i2d(j) * step + fb;
         int i = tbc_floor_nonneg(x);
         if (i > dist - 1) i = dist - 1;
         double t = x - tbc_i2d(i), u = 1.0 - t;
-        double Mi = M0[i], Mj = M0[i + 1];
-        double S = Mi * u * u * u * sixth + Mj * t * t * t * sixth + (y0[i] - Mi * sixth) * u + (y0[i + 1] - Mj * sixth) * t;
+        double Mi = M0(i), Mj = M0(i + 1);
+        double S = Mi * u * u * u * sixth + Mj * t * t * t * sixth + (ys[PX(i + TBC_H)] - Mi * sixth) * u + (ys[PX(i + 1 + TBC_H)] - Mj * sixth) * t;
         double hz = (S + p.plane_add) * wowf;
         size_t o = (size_t)field * (size_t)p.out_stride + (size_t)line * W + j;
         if (p.mode == 0) {
@@ -254,7 +256,7 @@ extern "C" int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n
     p.maxd = c.linelen + c.linelen / 4 + 64;
     if (p.maxd > TBC_MAXD) p.maxd = TBC_MAXD;
     const int maxq = (p.maxd + 1 + 2 * TBC_H + TBC_C - 1) / TBC_C;
-    size_t smem = (size_t)(2 * maxq * TBC_C + 6 + 2 * (maxq + 2)) * sizeof(double);
+    size_t smem = (size_t)(2 * ((TBC_C + 1) * maxq + 4) + 2 * (maxq + 2)) * sizeof(double);
     if (!h->tbc_taps_set) {
         const double r = -0.26794919243112270647;
         double rp[TBC_NPOW];

@@ -34,8 +34,37 @@ template <class T> struct Math;
 template <> struct Math<double> {
     static __device__ inline double atan2(double y, double x) { return ::atan2(y, x); }
 };
+// float32 atan2 for the FM discriminator: octant reduction to t = min/max in [0, 1], atan(t) = t + t^3 q(t^2)
+// with a degree-7 minimax q, quadrant fix-ups with two-part constants.  Maximum error 3.3e-7 rad (the same as a
+// 2-ulp library atan2f near pi) in about half the instructions; atan2(0, 0) = 0 like np.angle.
+__device__ inline float atan2_f32(float y, float x) {
+#ifdef LDD_EMU
+    return ::atan2f(y, x);
+#else
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(mx));
+    float t = mn * r;
+    t = fmaf(fmaf(-mx, t, mn), r, t);              // one Newton step on the quotient
+    t = mx > 0.f ? t : 0.f;
+    const float s = t * t;
+    float q = 3.866738873e-03f;
+    q = fmaf(q, s, -2.002674714e-02f);
+    q = fmaf(q, s, 4.891432077e-02f);
+    q = fmaf(q, s, -8.009681851e-02f);
+    q = fmaf(q, s, 1.086575910e-01f);
+    q = fmaf(q, s, -1.425704509e-01f);
+    q = fmaf(q, s, 1.999868155e-01f);
+    q = fmaf(q, s, -3.333332241e-01f);
+    float a = fmaf(t * s, q, t);
+    if (ay > ax) a = (1.57079637e+00f - a) + -4.37113883e-08f;
+    if (x < 0.f) a = (3.14159274e+00f - a) + -8.74227766e-08f;
+    return copysignf(a, y);
+#endif
+}
 template <> struct Math<float> {
-    static __device__ inline float atan2(float y, float x) { return ::atan2f(y, x); }
+    static __device__ inline float atan2(float y, float x) { return atan2_f32(y, x); }
 };
 
 // ---- raw sample fetch with the unpackers fused in (ddunpack.c / lddutils.py:131-229) -----------
@@ -398,24 +427,42 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
 
         // G. FM discriminator (lddutils.py:320-334): angle, neighbour difference, fold to [0, 2pi),
         //    scale to Hz; minus ire0; packed for the next real transform.
-        for (int n = tid; n < M; n += nthr) {
-            Cx<T> a = ru[IX(n)], b = rv[IX(n)];
-            ru[IX(n)] = mk<T>(Math<T>::atan2(-a.y, a.x), Math<T>::atan2(-b.y, b.x));
+        if constexpr (CM != 0) {
+            constexpr int IT = CM / NT;
+            LDD_UNROLL
+            for (int i = 0; i < IT; ++i) {
+                const int ix = IX(tid) + i * pstride<PAD>(NT);
+                Cx<T> a = ru[ix], b = rv[ix];
+                ru[ix] = mk<T>(Math<T>::atan2(-a.y, a.x), Math<T>::atan2(-b.y, b.x));
+            }
+        } else {
+            for (int n = tid; n < M; n += nthr) {
+                Cx<T> a = ru[IX(n)], b = rv[IX(n)];
+                ru[IX(n)] = mk<T>(Math<T>::atan2(-a.y, a.x), Math<T>::atan2(-b.y, b.x));
+            }
         }
         __syncthreads();
         {
             const T twopi = (T)6.283185307179586476925286766559;
             const T hz = (T)p.hz_per_rad, ire0 = (T)p.ire0;
-            for (int n = tid; n < M; n += nthr) {
-                Cx<T> a = ru[IX(n)];
+            auto diff = [&](int n, int ix, int ixm) {
+                Cx<T> a = ru[ix];
                 T d0 = (T)0;
                 if (n > 0) {
-                    d0 = a.x - ru[IX(n - 1)].y;
+                    d0 = a.x - ru[ixm].y;
                     if (d0 < 0) d0 += twopi;
                 }
                 T d1 = a.y - a.x;
                 if (d1 < 0) d1 += twopi;
-                rv[IX(n)] = mk<T>(d0 * hz - ire0, d1 * hz - ire0);
+                rv[ix] = mk<T>(d0 * hz - ire0, d1 * hz - ire0);
+            };
+            if constexpr (CM != 0) {
+                constexpr int IT = CM / NT;
+                LDD_UNROLL
+                for (int i = 0; i < IT; ++i)      // pidx(n - 1) = pidx(tid - 1) + i * pitch also for tid = 0 (arithmetic shift)
+                    diff(tid + i * NT, IX(tid) + i * pstride<PAD>(NT), IX(tid - 1) + i * pstride<PAD>(NT));
+            } else {
+                for (int n = tid; n < M; n += nthr) diff(n, IX(n), IX(n - 1));
             }
         }
         __syncthreads();

@@ -38,16 +38,6 @@ def build(force=False, verbose=False):
             sys.stderr.write(r.stdout)
             raise RuntimeError("nvcc failed on " + s)
         objs.append(o)
-        if s == "ldd_demod.cu":
-            # second build of the demodulation kernels with packed float32 pair arithmetic (namespace ldd::x2)
-            o2 = os.path.join(bdir, "ldd_demod_x2.o")
-            r = subprocess.run([NVCC] + FLAGS + ["-DLDD_F32X2", "-c", os.path.join(HERE, s), "-o", o2], stdout=subprocess.PIPE,
-                               stderr=subprocess.STDOUT, text=True)
-            log.append(r.stdout)
-            if r.returncode != 0:
-                sys.stderr.write(r.stdout)
-                raise RuntimeError("nvcc failed on " + s + " (x2)")
-            objs.append(o2)
     cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:

@@ -129,7 +129,6 @@ int ldd_create(const ldd_config* cfg, ldd_handle** out) {
     if (per_sm < 1) per_sm = 1;
     env = getenv("LDD_THREADS");
     h->threads = env ? atoi(env) : 512;
-    { const char* x2 = getenv("LDD_F32X2"); h->f32x2 = x2 && atoi(x2) != 0; }
     if (f64) { if (h->threads != 256 && h->threads != 512 && h->threads != 1024 && h->threads != 2256) h->threads = 512; }
     else { if (h->threads != 512 && h->threads != 1024) h->threads = 512; }
     env = getenv("LDD_RADIX_MAX");
@@ -362,9 +361,6 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
     }
     int rc;
     if (lane == 0) rc = launch_demod_f64(p, grid, h->threads, st, h->sp_bytes);
-#ifndef LDD_EMU
-    else if (h->f32x2) rc = x2::launch_demod_f32(p, grid, h->threads, st, h->smem_bytes);
-#endif
     else rc = launch_demod_f32(p, grid, h->threads, st, h->smem_bytes);
     if (mixed && rc == LDD_OK) {
         // second pass: float64 over the flagged blocks only; the list is read on the device, so there

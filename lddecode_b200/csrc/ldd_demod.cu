@@ -17,9 +17,6 @@
 #include "ldd_internal.h"
 
 namespace ldd {
-#ifdef LDD_F32X2
-namespace x2 {      // second build of this file: complex add / subtract as packed FADD2 (ldd_fft.cuh), selected by LDD_F32X2=1
-#endif
 
 // The planes are written once and never re-read by this kernel: store them with the streaming
 // (evict-first) hint so that ~0.9 GB of output per second of video does not push the L2-resident
@@ -646,7 +643,4 @@ int launch_demod_f32(const DemodParams& p, int grid, int threads, cudaStream_t s
     return launch_variant<float, 512, false>(p, grid, st, 0);
 }
 
-#ifdef LDD_F32X2
-}  // namespace x2
-#endif
 }  // namespace ldd

@@ -19,21 +19,6 @@ struct alignas(2 * sizeof(T)) Cx {
 template <class T> LDD_HD inline Cx<T> mk(T a, T b) { Cx<T> r; r.x = a; r.y = b; return r; }
 template <class T> LDD_HD inline Cx<T> operator+(Cx<T> a, Cx<T> b) { return mk<T>(a.x + b.x, a.y + b.y); }
 template <class T> LDD_HD inline Cx<T> operator-(Cx<T> a, Cx<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
-#if defined(__CUDA_ARCH__) && !defined(LDD_EMU) && defined(LDD_F32X2)
-// sm_100 packed float32 pairs: a complex add / subtract is one instruction (FADD2) instead of two
-__device__ inline unsigned long long cx_bits(Cx<float> a) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
-__device__ inline Cx<float> cx_from(unsigned long long r) { Cx<float> a; asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r)); return a; }
-template <> __device__ inline Cx<float> operator+(Cx<float> a, Cx<float> b) {
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(cx_bits(a)), "l"(cx_bits(b)));
-    return cx_from(r);
-}
-template <> __device__ inline Cx<float> operator-(Cx<float> a, Cx<float> b) {
-    unsigned long long r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(cx_bits(a)), "l"(cx_bits(b)));
-    return cx_from(r);
-}
-#endif
 template <class T> LDD_HD inline Cx<T> operator*(Cx<T> a, Cx<T> b) { return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 template <class T> LDD_HD inline Cx<T> conj(Cx<T> a) { return mk<T>(a.x, -a.y); }
 template <class T> LDD_HD inline Cx<T> scale(Cx<T> a, T s) { return mk<T>(a.x * s, a.y * s); }

@@ -67,10 +67,6 @@ inline int launch_status(ldd_handle* h, const char* what);
 
 int launch_demod_f64(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t sp_bytes);
 int launch_demod_f32(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t smem_bytes);
-namespace x2 {   // the same kernels built with packed float32 pair arithmetic (ldd_demod.cu compiled with -DLDD_F32X2)
-int launch_demod_f64(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t sp_bytes);
-int launch_demod_f32(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t smem_bytes);
-}
 
 }  // namespace ldd
 
@@ -104,7 +100,6 @@ struct ldd_handle {
     size_t flags_cap = 0;
     double flag_margin = 16.0;       // Hz
     long long last_nblocks = 0;
-    bool f32x2 = false;              // float32 lane built with packed pair arithmetic (LDD_F32X2=1)
     bool tbc_taps_set = false;       // __constant__ FIR taps uploaded for this handle's device
     size_t l2_window = 0;   // bytes of scratch covered by a persisting-L2 access policy window
     float l2_ratio = 1.0f;

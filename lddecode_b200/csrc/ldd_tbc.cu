@@ -70,7 +70,7 @@ __device__ inline int tbc_floor_nonneg(double x) {        // (int)x for 0 <= x <
 #endif
 }
 
-__global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
+__global__ void __launch_bounds__(TBC_THREADS, 3) tbc_kernel(const TbcParams p) {
     LDD_DYN_SMEM(smem_raw);
     // Both arrays are indexed by u = i + H through PX(u) = u + u/16: a thread owns 16 consecutive samples, and
     // the padding slot per 16 puts the chunks of neighbouring threads 17 doubles apart (no bank conflicts).
@@ -107,7 +107,21 @@ __global__ void __launch_bounds__(TBC_THREADS) tbc_kernel(const TbcParams p) {
         const long long s0 = base + ib - TBC_H;
         const float* src = p.plane + s0;
         if (s0 >= 0 && s0 + U <= p.n) {
-            for (int i = tid; i < U; i += TBC_THREADS) ys[PX(i)] = (double)src[i];
+            // all loads of a batch are issued before the first conversion: one memory round trip per 8 samples of a thread
+            constexpr int SB = 8;
+            for (int i0 = tid; i0 < U; i0 += SB * TBC_THREADS) {
+                float v[SB];
+                LDD_UNROLL
+                for (int k = 0; k < SB; ++k) {
+                    const int i = i0 + k * TBC_THREADS;
+                    v[k] = i < U ? src[i] : 0.f;
+                }
+                LDD_UNROLL
+                for (int k = 0; k < SB; ++k) {
+                    const int i = i0 + k * TBC_THREADS;
+                    if (i < U) ys[PX(i)] = (double)v[k];
+                }
+            }
         } else {
             for (int i = tid; i < U; i += TBC_THREADS) {
                 long long s = s0 + i;
@@ -265,6 +279,7 @@ extern "C" int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n
         h->tbc_taps_set = true;
     }
     cudaFuncSetAttribute(tbc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(tbc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);      // several CTAs of ~50 KB per SM
     cudaStream_t st = (cudaStream_t)stream;
     LDD_LAUNCH(tbc_kernel, dim3(max_linecount, nfields), dim3(TBC_THREADS), smem, st, p);
     return launch_status(h, "tbc_kernel");

@@ -138,3 +138,73 @@ def test_field_golden_mixed_lane(backend, golden, name):
     np.testing.assert_allclose(f.linelocs, g["field_linelocs"], rtol=0, atol=2e-3)
     d = f.dspicture.astype(np.int64) - g["field_dspicture"].astype(np.int64)
     assert np.abs(d).max() <= 1
+
+
+def test_pilot_refine_synthetic_against_oracle(backend):
+    """refine_linelocs_pilot (the per-line and the per-field kernel) on synthetic planes, including
+    crossings that land exactly on a sample (the reference then also skips the next sample: the kernel's
+    sequential re-walk), lines without any crossing, and many equal offsets (median selection with ties)."""
+    fs = 35.46895
+    rf = rfdecode.RFDecode(fs, "PAL", 16384, _backend=backend, precision="f64")
+    dec = O.Decoder(fs, "PAL", 16384, analog_audio=False)
+    be = backend
+    rng = np.random.default_rng(11)
+    linecount = 60
+    nll = linecount + 4
+    L = rf.linelen
+    n = (nll + 3) * L
+    for case in range(4):
+        k = np.arange(n)
+        phase = rng.uniform(0, 2 * np.pi)
+        pil = 220000.0 * np.sin(2 * np.pi * 3.75 / fs * k + phase)
+        if case == 1:
+            pil += rng.normal(0, 30000.0, n)
+        if case == 2:
+            pil[::7] = 0.0                                   # exact zeros: some close a negative run
+        if case == 3:
+            pil[: n // 2] = -5.0                              # no crossings on the first lines
+        d05 = rng.normal(0, 1000.0, n).astype(np.float32)
+        demod = (pil.astype(np.float32) + d05).astype(np.float32)
+        if case == 2:
+            demod[::7] = d05[::7]                             # demod - demod_05 == 0 exactly
+        ll2 = (np.arange(LL := field.LL_STRIDE) * (L + 0.37) + 2 * L + rng.uniform(0, 1)).astype(np.float64)
+        video = {"demod": demod.astype(np.float64), "demod_05": d05.astype(np.float64)}
+        ref = O.refine_pilot_pal(dec, video, ll2[:nll])
+        d_out = be.empty(LL, np.float64)
+        d_status = be.zeros(1, np.int32)
+        d_demod, d_d05, d_ll = be.to_device(demod), be.to_device(d05), be.to_device(ll2)
+        d_base, d_lc = be.to_device(np.zeros(1, dtype=np.int64)), be.to_device(np.array([linecount], dtype=np.int32))
+        rf._check(be.lib.ldd_refine_pilot(rf._h, be.ptr(d_demod), be.ptr(d_d05), n, be.ptr(d_base), be.ptr(d_lc), 1, LL,
+                                          be.ptr(d_ll), be.ptr(d_out), be.ptr(d_status), be.stream()))
+        be.synchronize()
+        assert int(be.to_host(d_status)[0]) == 0, case
+        np.testing.assert_allclose(be.to_host(d_out)[:nll], ref, rtol=0, atol=1e-9, err_msg=str(case))
+
+
+def test_tbc_random_geometry_against_oracle_spline(backend):
+    """ldd_tbc_fields in float64 mode on random planes and irregular line positions (short, long and
+    fractional spans) against the oracle's not-a-knot spline (lddutils.scale)."""
+    fs = 8 * 315 / 88
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, _backend=backend, precision="f64")
+    be = backend
+    rng = np.random.default_rng(5)
+    L, W = rf.linelen, rf.SysParams['outlinelen']
+    n = 40 * L
+    plane = np.cumsum(rng.normal(0, 20000.0, n)).astype(np.float32)
+    gaps = np.concatenate([rng.uniform(0.8, 1.2, 12) * L, [0.3 * L, 40.0, 7.5, 1.24 * L]])
+    ll = np.zeros(field.LL_STRIDE)
+    ll[: len(gaps) + 1] = 500.25 + np.concatenate([[0], np.cumsum(gaps)])
+    nlines = len(gaps)
+    d_out = be.empty(nlines * W, np.float64)
+    d_status = be.zeros(1, np.int32)
+    d_plane, d_ll, d_lc = be.to_device(plane), be.to_device(ll), be.to_device(np.array([nlines], dtype=np.int32))
+    rf._check(be.lib.ldd_tbc_fields(rf._h, be.ptr(d_plane), n, 0.0, None, be.ptr(d_ll), field.LL_STRIDE,
+                                    be.ptr(d_lc), 1, nlines, 0, 0.0, W, 1, 0,
+                                    be.ptr(d_out), nlines * W, None, 1.45, be.ptr(d_status), be.stream()))
+    be.synchronize()
+    assert int(be.to_host(d_status)[0]) == 0
+    got = be.to_host(d_out).reshape(nlines, W)
+    p64 = plane.astype(np.float64)
+    for l in range(nlines):
+        ref = O.scale(p64, ll[l], ll[l + 1], W) * ((ll[l + 1] - ll[l]) / L)
+        np.testing.assert_allclose(got[l], ref, rtol=0, atol=2e-6 * np.abs(p64).max())

@@ -139,18 +139,25 @@ __device__ inline void untangle_static(Cx<T>* Z, const Cx<T>* __restrict__ WN, i
     const T half = (T)0.5;
     LDD_UNROLL
     for (int it0 = 0; it0 < IT; it0 += B) {
-        Cx<T> w[B];
+        // table values and the shared-memory operands of the whole batch first (independent loads in flight), then
+        // the arithmetic and the stores (the compiler may not move a shared load above an earlier shared store)
+        Cx<T> w[B], za[B], zb[B];
         LDD_UNROLL
         for (int i = 0; i < B; ++i) w[i] = WN[tid + (it0 + i) * NT];
         LDD_UNROLL
         for (int i = 0; i < B; ++i) {
+            za[i] = Z[pidx<PAD>(tid) + (it0 + i) * pstride<PAD>(NT)];
+            zb[i] = Z[(it0 + i == 0 && tid == 0) ? 0 : pidx<PAD>(M - tid) - (it0 + i) * pstride<PAD>(NT)];    // k = 0 has no partner
+        }
+        LDD_UNROLL
+        for (int i = 0; i < B; ++i) {
             const int k = tid + (it0 + i) * NT;
             if (it0 + i == 0 && k == 0) {
-                Cx<T> z = Z[0];
+                Cx<T> z = za[i];
                 Z[0] = mk<T>(z.x + z.y, z.x - z.y);
             } else {
                 const int ik = pidx<PAD>(tid) + (it0 + i) * pstride<PAD>(NT), im = pidx<PAD>(M - tid) - (it0 + i) * pstride<PAD>(NT);
-                Cx<T> a = Z[ik], b = conj(Z[im]);
+                Cx<T> a = za[i], b = conj(zb[i]);
                 Cx<T> E = scale(a + b, half);
                 Cx<T> Od = scale(mul_mj(a - b), half);
                 Cx<T> Tw = w[i] * Od;
@@ -168,7 +175,7 @@ __device__ inline void tangle_static(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __re
     const T half = (T)0.5;
     LDD_UNROLL
     for (int it0 = 0; it0 < IT; it0 += B) {
-        Cx<T> fa[B], fb[B], w[B];
+        Cx<T> fa[B], fb[B], w[B], da[B], db[B];
         LDD_UNROLL
         for (int i = 0; i < B; ++i) {
             const int k = tid + (it0 + i) * NT;
@@ -178,14 +185,19 @@ __device__ inline void tangle_static(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __re
         }
         LDD_UNROLL
         for (int i = 0; i < B; ++i) {
+            da[i] = D[pidx<PAD>(tid) + (it0 + i) * pstride<PAD>(NT)];
+            db[i] = D[(it0 + i == 0 && tid == 0) ? 0 : pidx<PAD>(M - tid) - (it0 + i) * pstride<PAD>(NT)];
+        }
+        LDD_UNROLL
+        for (int i = 0; i < B; ++i) {
             const int k = tid + (it0 + i) * NT;
             if (it0 + i == 0 && k == 0) {
-                Cx<T> d = D[0];
+                Cx<T> d = da[i];
                 T y0 = d.x * fa[i].x, ym = d.y * fb[i].x;
                 Q[0] = mk<T>((y0 + ym) * half, -(y0 - ym) * half);
             } else {
                 const int ik = pidx<PAD>(tid) + (it0 + i) * pstride<PAD>(NT), im = pidx<PAD>(M - tid) - (it0 + i) * pstride<PAD>(NT);
-                Cx<T> a = D[ik] * fa[i], b = conj(D[im] * fb[i]);
+                Cx<T> a = da[i] * fa[i], b = conj(db[i] * fb[i]);
                 Cx<T> E = scale(a + b, half);
                 Cx<T> Od = mulc(scale(a - b, half), w[i]);
                 Cx<T> q = E + mul_pj(Od);
@@ -363,14 +375,13 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         //    V[k] = (Y[k] - Y[k+M]) W_N^{-k}; stored conjugated for inverse-by-forward.
         Cx<T>* U = f1;
         Cx<T>* V = f2;
-        auto estep = [&](int k, int ik, int im, Cx<T> h0, Cx<T> h1, Cx<T> h2, Cx<T> h3, Cx<T> w) {   // Hv[k], Hv[k+M], Hv[M-k], Hv[2M-k], WN[k]
+        auto estep = [&](int k, int ik, int im, Cx<T> xa, Cx<T> xb, Cx<T> h0, Cx<T> h1, Cx<T> h2, Cx<T> h3, Cx<T> w) {   // Hv[k], Hv[k+M], Hv[M-k], Hv[2M-k], WN[k]
             if (k == 0) {
-                Cx<T> x = X[0];
+                Cx<T> x = xa;
                 Cx<T> y0 = scale(h0, x.x), y1 = scale(h1, x.y);
                 U[0] = conj(y0 + y1);
                 V[0] = conj(y0 - y1);
             } else {
-                Cx<T> xa = X[ik], xb = X[im];
                 Cx<T> y0 = xa * h0, y1 = conj(xb) * h1;
                 U[ik] = conj(y0 + y1);
                 V[ik] = conj(mulc(y0 - y1, w));
@@ -387,20 +398,26 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
             constexpr int IT = CM / 2 / NT, B = (IT % 4 == 0) ? (sizeof(T) == 4 ? 4 : 2) : 1;
             LDD_UNROLL
             for (int it0 = 0; it0 < IT; it0 += B) {
-                Cx<T> h0[B], h1[B], h2[B], h3[B], w[B];
+                Cx<T> h0[B], h1[B], h2[B], h3[B], w[B], xa[B], xb[B];
                 LDD_UNROLL
                 for (int i = 0; i < B; ++i) {
                     const int k = tid + (it0 + i) * NT;
                     h0[i] = Hv[k]; h1[i] = Hv[k + M]; h2[i] = Hv[M - k]; h3[i] = Hv[(2 * M - k) & (2 * M - 1)]; w[i] = WN[k];
                 }
                 LDD_UNROLL
+                for (int i = 0; i < B; ++i) {
+                    xa[i] = X[IX(tid) + (it0 + i) * pstride<PAD>(NT)];
+                    xb[i] = X[(it0 + i == 0 && tid == 0) ? 0 : IX(M - tid) - (it0 + i) * pstride<PAD>(NT)];
+                }
+                LDD_UNROLL
                 for (int i = 0; i < B; ++i)
-                    estep(tid + (it0 + i) * NT, IX(tid) + (it0 + i) * pstride<PAD>(NT), IX(M - tid) - (it0 + i) * pstride<PAD>(NT), h0[i], h1[i], h2[i], h3[i], w[i]);
+                    estep(tid + (it0 + i) * NT, IX(tid) + (it0 + i) * pstride<PAD>(NT), IX(M - tid) - (it0 + i) * pstride<PAD>(NT), xa[i], xb[i],
+                          h0[i], h1[i], h2[i], h3[i], w[i]);
             }
-            if (tid == 0) estep(M / 2, IX(M / 2), IX(M / 2), Hv[M / 2], Hv[M / 2 + M], Hv[M / 2], Hv[M / 2 + M], WN[M / 2]);
+            if (tid == 0) estep(M / 2, IX(M / 2), IX(M / 2), X[IX(M / 2)], X[IX(M / 2)], Hv[M / 2], Hv[M / 2 + M], Hv[M / 2], Hv[M / 2 + M], WN[M / 2]);
         } else {
             for (int k = tid; k <= M / 2; k += nthr)
-                estep(k, IX(k), IX(M - k), Hv[k], Hv[k + M], Hv[M - k], Hv[(2 * M - k) & (2 * M - 1)], WN[k]);
+                estep(k, IX(k), IX(M - k), X[IX(k)], X[IX(k == 0 ? 0 : M - k)], Hv[k], Hv[k + M], Hv[M - k], Hv[(2 * M - k) & (2 * M - 1)], WN[k]);
         }
         __syncthreads();
 

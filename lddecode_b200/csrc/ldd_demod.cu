@@ -514,9 +514,26 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
             if (((keep0 | keep1) & 1) == 0 && ((o & 1) == 0) && ((((uintptr_t)out) & 7) == 0)) {
                 // whole (even, odd) sample pairs inside the kept region: one 8-byte streaming store each
                 float2* out2 = (float2*)(out + o) - keep0 / 2;
-                for (int n = keep0 / 2 + tid; n < keep1 / 2; n += nthr) {
-                    Cx<T> v = r[IX(n)];
-                    st_stream(&out2[n], make_float2((float)(v.x + addc), (float)(-v.y + addc)));
+                if (CM != 0) {
+                    // constant strides (pidx(n + NT) = pidx(n) + pitch for any n), unrolled in batches of five
+                    const int nlo = keep0 / 2 + tid, nhi = keep1 / 2;
+                    const Cx<T>* r0 = r + IX(nlo);
+                    float2* o0 = out2 + nlo;
+                    constexpr int SB = 5;
+                    for (int i0 = 0; nlo + i0 * NT < nhi; i0 += SB) {
+                        Cx<T> v[SB];
+                        LDD_UNROLL
+                        for (int i = 0; i < SB; ++i) v[i] = (nlo + (i0 + i) * NT < nhi) ? r0[(i0 + i) * pstride<PAD>(NT)] : mk<T>((T)0, (T)0);
+                        LDD_UNROLL
+                        for (int i = 0; i < SB; ++i)
+                            if (nlo + (i0 + i) * NT < nhi)
+                                st_stream(&o0[(i0 + i) * NT], make_float2((float)(v[i].x + addc), (float)(-v[i].y + addc)));
+                    }
+                } else {
+                    for (int n = keep0 / 2 + tid; n < keep1 / 2; n += nthr) {
+                        Cx<T> v = r[IX(n)];
+                        st_stream(&out2[n], make_float2((float)(v.x + addc), (float)(-v.y + addc)));
+                    }
                 }
             } else {
                 for (int n = tid; n < M; n += nthr) {

@@ -133,12 +133,24 @@ __global__ void __launch_bounds__(32 * HS_WARPS) refine_hsync_kernel(const Hsync
             if (end > len) end = len;
             const bool rising = d(start) < target;
             long long x = -1;
-            for (long long k0 = start; k0 < end; k0 += 32) {
-                long long k = k0 + lane;
-                bool hit = false;
-                if (k < end) { double v = d(k); hit = rising ? (v >= target) : (v <= target); }
-                unsigned m = __ballot_sync(FULL, hit);
-                if (m) { x = k0 + (__ffs(m) - 1); break; }
+            // all 401 samples of the scan are requested before the first comparison (one memory round trip
+            // instead of one per 32 samples)
+            constexpr int NR = 13;                          // 13 * 32 >= 401
+            float v32[NR];
+            LDD_UNROLL
+            for (int r = 0; r < NR; ++r) {
+                long long k = start + 32 * r + lane;
+                v32[r] = k < end ? p.d05[base + k] : 0.f;
+            }
+            LDD_UNROLL
+            for (int r = 0; r < NR; ++r) {
+                if (x < 0) {
+                    long long k = start + 32 * r + lane;
+                    bool hit = false;
+                    if (k < end) { double v = (double)v32[r] + p.ire0; hit = rising ? (v >= target) : (v <= target); }
+                    unsigned m = __ballot_sync(FULL, hit);
+                    if (m) x = start + 32 * r + (__ffs(m) - 1);
+                }
             }
             if (x > 0) {
                 double a = d(x - 1) - target, b = d(x) - target;
@@ -208,27 +220,36 @@ __global__ void __launch_bounds__(32 * HS_WARPS) refine_hsync_kernel(const Hsync
     }
 }
 
-// The sequential fix-ups of refine_linelocs_hsync (lddecode_core.py:769-787): one thread per field.
+// The sequential fix-ups of refine_linelocs_hsync (lddecode_core.py:769-787): one warp per field; the tables
+// are staged in shared memory with coalesced accesses, lane 0 walks them.
 __global__ void __launch_bounds__(32) refine_hsync_fixup_kernel(const HsyncParams p) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double s_l2[320 + 8];
+    __shared__ unsigned char s_bad[320 + 8];
+    const int f = blockIdx.x, lane = threadIdx.x;
     if (f >= p.nfields) return;
     const int nll = p.linecount[f] + 4;
     double* l2 = p.linelocs2 + (size_t)f * p.ll_stride;
     const unsigned char* bad = p.linebad_out + (size_t)f * p.ll_stride;
-    const double fq = p.freq;
-    for (int i = 11; i < nll; ++i)
-        if (bad[i]) { double gap = l2[i - 1] - l2[i - 2]; l2[i] = l2[i - 1] + gap; }
-    const double lo = p.linelen - fq * .2, hi = p.linelen + fq * .2;
-    for (int i = 9; i >= 0; --i) {
-        double gap = l2[i + 1] - l2[i];
-        if (!(gap >= lo && gap <= hi)) gap = p.linelen;
-        l2[i] = l2[i + 1] - gap;
+    for (int i = lane; i < nll; i += 32) { s_l2[i] = l2[i]; s_bad[i] = bad[i]; }
+    __syncwarp();
+    if (lane == 0) {
+        const double fq = p.freq;
+        for (int i = 11; i < nll; ++i)
+            if (s_bad[i]) { double gap = s_l2[i - 1] - s_l2[i - 2]; s_l2[i] = s_l2[i - 1] + gap; }
+        const double lo = p.linelen - fq * .2, hi = p.linelen + fq * .2;
+        for (int i = 9; i >= 0; --i) {
+            double gap = s_l2[i + 1] - s_l2[i];
+            if (!(gap >= lo && gap <= hi)) gap = p.linelen;
+            s_l2[i] = s_l2[i + 1] - gap;
+        }
+        for (int i = nll - 10; i < nll; ++i) {
+            double gap = s_l2[i] - s_l2[i - 1];
+            if (!(gap >= lo && gap <= hi)) gap = p.linelen;
+            s_l2[i] = s_l2[i - 1] + gap;
+        }
     }
-    for (int i = nll - 10; i < nll; ++i) {
-        double gap = l2[i] - l2[i - 1];
-        if (!(gap >= lo && gap <= hi)) gap = p.linelen;
-        l2[i] = l2[i - 1] + gap;
-    }
+    __syncwarp();
+    for (int i = lane; i < nll; i += 32) l2[i] = s_l2[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -932,6 +953,7 @@ extern "C" int ldd_refine_hsync(ldd_handle* h, const float* d05_dev, long long n
     if (!h || !d05_dev || !base_dev || !winlen_dev || !linecount_dev || !linelocs1_dev || !linebad_dev || !linelocs2_dev ||
         !linebad_out_dev || !status_dev) return LDD_EINVAL;
     if (nfields <= 0) return LDD_OK;
+    if (ll_stride > 320 + 8) return LDD_EINVAL;      // shared-memory tables of the fix-up kernel
     HsyncParams p;
     p.d05 = d05_dev; p.n = n; p.ire0 = h->cfg.ire0; p.hz_ire = h->cfg.hz_ire; p.freq = h->cfg.freq_hz / 1e6;
     p.linelen = h->cfg.linelen; p.base = base_dev; p.winlen = winlen_dev; p.linecount = linecount_dev; p.ll_stride = ll_stride;
@@ -942,7 +964,7 @@ extern "C" int ldd_refine_hsync(ldd_handle* h, const float* d05_dev, long long n
     LDD_LAUNCH(refine_hsync_kernel, dim3((maxll + HS_WARPS - 1) / HS_WARPS, nfields), dim3(32 * HS_WARPS), 0, (cudaStream_t)stream, p);
     int rc = launch_status(h, "refine_hsync_kernel");
     if (rc) return rc;
-    LDD_LAUNCH(refine_hsync_fixup_kernel, dim3((nfields + 31) / 32), dim3(32), 0, (cudaStream_t)stream, p);
+    LDD_LAUNCH(refine_hsync_fixup_kernel, dim3(nfields), dim3(32), 0, (cudaStream_t)stream, p);
     return launch_status(h, "refine_hsync_fixup_kernel");
 }
 

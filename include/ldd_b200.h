@@ -183,6 +183,15 @@ int ldd_sync_peaks(ldd_handle* h, const double* sync_dev, long long n, long long
 int ldd_sync_peaks_host(ldd_handle* h, const double* sync_host, long long n, long long start,
                         long long* peaks, double* vals, int cap, int* count);
 
+/* HOST function: the peak list of Field.get_syncpeaks for the window [b, b + wl) of a plane, cut out of the peak
+ * list gpeaks[0..ngpeaks) of a chase that covered the plane from sample gstart while i < gend (lddecode_core.py:497-516
+ * run once per capture instead of once per 1e6-sample read).  The window may start on a global peak or anywhere else:
+ * its own chase is reconstructed from what the global chase is known to have seen (empty half-line windows between
+ * peaks, arg-max windows at peaks).  Returns 1 and the index range [*k0, *k1) of gpeaks that is the window's list
+ * (positions relative to the plane; subtract b), or 0 when the samples themselves are needed to decide. */
+int ldd_window_peaks_from_global(const long long* gpeaks, int ngpeaks, long long gstart, long long gend,
+                                 long long b, long long wl, int linelen, int* k0, int* k1);
+
 /* ---- field location (lddecode_core.py:518-787, 889-957, 962-1021, 1054-1133) -------------------- */
 #define LDD_FIELD_NOVSYNC 0    /* len(vsyncs) == 0: not a field, nextfieldoffset = start + 200 lines          */
 #define LDD_FIELD_SHORT 1      /* one vsync / too few peaks after the second: jump, not valid                 */

@@ -1043,7 +1043,67 @@ bool window_from_global(const long long* gp, int ngp, long long b, long long wl,
     return true;
 }
 
+// A window that starts OFF the global chain (the second read of a capture starts `blockcut` samples before a peak,
+// lddecode_core.py:374-379).  Its own chase merges into the global one at its first peak; until then every step looks
+// at a half-line window, and what the global chase saw there is known from the global peak list alone: between two
+// global peaks p[k-1], p[k] the global chase stepped from s = p[k-1] + skip in half-line windows, all of them empty
+// (maximum <= 0.2) except the last one, G, whose first arg-max is p[k].  A local window that lies inside the empty
+// windows is empty; one that lies inside the empty windows plus G and contains p[k] finds p[k] (everything else in it
+// is <= 0.2 < val(p[k]), or inside G and therefore no larger, strictly smaller if earlier).  Anything else (samples the
+// global chase skipped, or part of G without its peak) cannot be decided here: return false and let the caller chase
+// on the samples.  gstart / gend: first sample and loop bound of the global chase (plane coordinates).
+bool window_offpeak_from_global(const long long* gp, int ngp, long long gstart, long long gend, long long b, long long wl, int L,
+                                int* k0_out, int* k1_out) {
+    const long long half = L / 2, skip = (long long)(L * .4);
+    const long long limit = b + wl - 2LL * L;
+    long long i = b;
+    if (i < gstart) return false;
+    int kmerge = -1;
+    for (int guard = 0; guard < 64 && i < limit; ++guard) {
+        // segment k: the global steps that follow peak k-1 (k = 0: the start of the global chase)
+        int k = (int)(std::upper_bound(gp, gp + ngp, i - skip) - gp);      // number of peaks with p + skip <= i
+        const long long s = k == 0 ? gstart : gp[k - 1] + skip;
+        if (i < s) return false;
+        const long long wend = i + half;
+        if (k == ngp) {
+            // after the last global peak: empty windows up to the end of the global chase's last step
+            if (gend <= s) return false;
+            const long long nsteps = (gend - s + half - 1) / half;         // steps at s + t*half < gend
+            if (wend > s + nsteps * half) return false;
+            i += half;
+            continue;
+        }
+        const long long T = (gp[k] - s) / half;
+        const long long g0 = s + T * half, g1 = g0 + half;                  // G = [g0, g1)
+        if (i >= g1) return false;                                           // inside the stretch the global chase skipped
+        if (wend <= g0) { i += half; continue; }                            // empty
+        if (wend <= g1 && gp[k] >= i && gp[k] < wend) { kmerge = k; break; }
+        return false;
+    }
+    if (kmerge < 0) {
+        if (i >= limit) { *k0_out = 0; *k1_out = 0; return true; }          // no peak at all before the loop bound
+        return false;
+    }
+    int k = kmerge + 1;
+    for (; k < ngp; ++k) {
+        long long i0 = gp[k - 1] + skip;
+        long long m = (gp[k] - i0) / half;
+        if (i0 + m * half >= limit) break;
+    }
+    *k0_out = kmerge;
+    *k1_out = k;
+    return true;
+}
+
 }  // namespace
+
+extern "C" int ldd_window_peaks_from_global(const long long* gpeaks, int ngpeaks, long long gstart, long long gend,
+                                            long long b, long long wl, int linelen, int* k0, int* k1) {
+    if (!gpeaks || !k0 || !k1 || ngpeaks < 0 || linelen < 4) return 0;
+    if (b == gstart) return 0;                       // the chase itself started here: the caller has the list already
+    if (window_from_global(gpeaks, ngpeaks, b, wl, linelen, k0, k1)) return 1;
+    return window_offpeak_from_global(gpeaks, ngpeaks, gstart, gend, b, wl, linelen, k0, k1) ? 1 : 0;
+}
 
 extern "C" int ldd_field_chain(ldd_handle* h, const long long* gpeaks, const double* gvals, int ngpeaks,
                                long long plane_len, long long plane_origin, long long ncap, long long readlen,
@@ -1088,6 +1148,9 @@ extern "C" int ldd_field_chain(ldd_handle* h, const long long* gpeaks, const dou
             k1 = k;
         } else {
             fast = window_from_global(gpeaks, ngpeaks, b, wl, L, &k0, &k1);
+            // (the global chase of the pipeline starts at plane sample 0 and runs while i < plane_len - 2 L)
+            if (!fast && !getenv("LDD_NO_OFFPEAK_FAST"))
+                fast = window_offpeak_from_global(gpeaks, ngpeaks, 0, plane_len - 2LL * L, b, wl, L, &k0, &k1);
         }
         if (fast) {
             rel.resize(k1 - k0);

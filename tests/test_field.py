@@ -208,3 +208,52 @@ def test_tbc_random_geometry_against_oracle_spline(backend):
     for l in range(nlines):
         ref = O.scale(p64, ll[l], ll[l + 1], W) * ((ll[l + 1] - ll[l]) / L)
         np.testing.assert_allclose(got[l], ref, rtol=0, atol=2e-6 * np.abs(p64).max())
+
+
+def test_window_peaks_from_global_matches_own_chase(backend):
+    """The host walk cuts a window's peak list out of the capture-wide chase (on a global peak, or off the chain:
+    the second read of a capture).  Whenever ldd_window_peaks_from_global decides, its answer must be the list the
+    window's own chase produces; and on regular video it must decide for a window that starts 1024 samples before
+    a peak (PAL: half a line > blockcut)."""
+    import ctypes as C
+    lib = backend.lib
+    rng = np.random.default_rng(3)
+    decided = 0
+    for L in (2270, 1820, 2540):
+        half, skip = L // 2, int(L * .4)
+        n = 120 * L
+        for kind in range(4):
+            ds = np.zeros(n)
+            if kind == 0:        # regular line sync peaks with mild noise
+                pos = (np.arange(5, 115) * L + rng.integers(-3, 4, 110)).astype(np.int64)
+            elif kind == 1:      # half-line pulses (vsync region) mixed with lines
+                pos = np.sort(np.concatenate([np.arange(5, 60) * L, 60 * L + np.arange(0, 40) * half, np.arange(81, 115) * L])).astype(np.int64)
+            elif kind == 2:      # irregular
+                pos = np.sort(rng.choice(np.arange(2 * L, n - 3 * L), 150, replace=False)).astype(np.int64)
+            else:                # noise floor close to the threshold plus peaks
+                pos = (np.arange(5, 115) * L).astype(np.int64)
+                ds += rng.uniform(0, 0.25, n)
+            for p in pos:
+                w = np.arange(-40, 41)
+                ds[p + w] = np.maximum(ds[p + w], (0.7 + 0.1 * rng.uniform()) * np.exp(-(w / 15.0) ** 2))
+            gpk = np.array(O.sync_peaks(ds, 0, L), dtype=np.int64)
+            gend = n - 2 * L
+            # (a window that starts ON a global peak is taken from the global list under the pipeline's documented
+            # assumption that no higher peak follows within half a line: only regular planes are asked that here)
+            starts = [int(p) - 1024 for p in gpk[5:60:3]] + list(rng.integers(L, n // 2, 25))
+            if kind in (0, 1):
+                starts += [int(p) for p in gpk[7:30:5]]
+            for b in starts:
+                wl = int(rng.integers(20 * L, 60 * L))
+                if b < 1 or b + wl > n or (kind >= 2 and b in gpk):
+                    continue
+                own = np.array(O.sync_peaks(ds[b:b + wl], 0, L), dtype=np.int64) + b
+                k0, k1 = C.c_int(0), C.c_int(0)
+                ok = lib.ldd_window_peaks_from_global(gpk.ctypes.data_as(C.c_void_p), len(gpk), 0, gend, int(b), wl, L,
+                                                      C.byref(k0), C.byref(k1))
+                if ok:
+                    decided += 1
+                    assert np.array_equal(gpk[k0.value:k1.value], own), (L, kind, b, wl)
+                elif kind == 0 and L == 2270 and b + 1024 in gpk:
+                    raise AssertionError("regular PAL video: a window 1024 samples before a peak must be decided")
+    assert decided > 100

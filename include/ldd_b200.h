@@ -183,6 +183,15 @@ int ldd_sync_peaks(ldd_handle* h, const double* sync_dev, long long n, long long
 int ldd_sync_peaks_host(ldd_handle* h, const double* sync_host, long long n, long long start,
                         long long* peaks, double* vals, int cap, int* count);
 
+/* Small transfers done by a kernel instead of the copy engines (page-locked host memory is device-addressable):
+ * the per-field tables going up and the peak list coming down are a few hundred KB each, but on the copy engines
+ * they queue behind the bulk capture upload / field download of a streaming decode (0.7 ms each at 36 MB).
+ * ldd_copy_small: nbytes from src to dst, either of which may be page-locked host memory or device memory.
+ * ldd_peaks_to_host: count_dev[0..1] and the first min(count_dev[0], cap) entries of the peak list. */
+int ldd_copy_small(void* dst, const void* src, size_t nbytes, void* stream);
+int ldd_peaks_to_host(const long long* peaks_dev, const double* vals_dev, const int* count_dev, int cap,
+                      long long* peaks_host, double* vals_host, int* count_host, void* stream);
+
 /* HOST function: the peak list of Field.get_syncpeaks for the window [b, b + wl) of a plane, cut out of the peak
  * list gpeaks[0..ngpeaks) of a chase that covered the plane from sample gstart while i < gend (lddecode_core.py:497-516
  * run once per capture instead of once per 1e6-sample read).  The window may start on a global peak or anywhere else:

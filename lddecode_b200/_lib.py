@@ -68,6 +68,8 @@ SIGNATURES = {
                                  C.c_void_p, C.c_void_p]),
     "ldd_window_peaks_from_global": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int,
                                               C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ldd_copy_small": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ldd_peaks_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldd_sync_peaks_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int,
                                       C.POINTER(C.c_int)]),
     "ldd_tbc_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,

@@ -321,6 +321,48 @@ extern "C" int ldd_sync_peaks(ldd_handle* h, const double* sync_dev, long long n
     return launch_status(h, "peaks_phase1/2");
 }
 
+// ---- small transfers by kernel (see include/ldd_b200.h) ------------------------------------------
+namespace ldd {
+__global__ void __launch_bounds__(256) copy_small_kernel(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src, size_t n) {
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16, step = (size_t)gridDim.x * blockDim.x * 16;
+    if (((((uintptr_t)dst) | ((uintptr_t)src)) & 15) == 0) {
+        for (size_t i = i0; i + 16 <= n; i += step) *(uint4*)(dst + i) = *(const uint4*)(src + i);
+        const size_t tail = n & ~(size_t)15;
+        if (blockIdx.x == 0 && threadIdx.x < (n & 15)) dst[tail + threadIdx.x] = src[tail + threadIdx.x];
+    } else {
+        for (size_t i = i0; i < n; i += step)
+            for (size_t k = i; k < i + 16 && k < n; ++k) dst[k] = src[k];
+    }
+}
+
+__global__ void __launch_bounds__(256) peaks_to_host_kernel(const long long* __restrict__ pk, const double* __restrict__ vl,
+                                                            const int* __restrict__ cnt, int cap, long long* __restrict__ hpk,
+                                                            double* __restrict__ hvl, int* __restrict__ hcnt) {
+    const int c = cnt[0] < cap ? cnt[0] : cap;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) { hcnt[0] = cnt[0]; hcnt[1] = cnt[1]; }
+    for (int i = t; i < c; i += gridDim.x * blockDim.x) { hpk[i] = pk[i]; hvl[i] = vl[i]; }
+}
+}  // namespace ldd
+
+extern "C" int ldd_copy_small(void* dst, const void* src, size_t nbytes, void* stream) {
+    if (!dst || !src) return LDD_EINVAL;
+    if (nbytes == 0) return LDD_OK;
+    size_t blocks = (nbytes / 16 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 64) blocks = 64;
+    LDD_LAUNCH(copy_small_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (unsigned char*)dst, (const unsigned char*)src, nbytes);
+    return cudaGetLastError() == cudaSuccess ? LDD_OK : LDD_ECUDA;
+}
+
+extern "C" int ldd_peaks_to_host(const long long* peaks_dev, const double* vals_dev, const int* count_dev, int cap,
+                                 long long* peaks_host, double* vals_host, int* count_host, void* stream) {
+    if (!peaks_dev || !vals_dev || !count_dev || !peaks_host || !vals_host || !count_host || cap < 0) return LDD_EINVAL;
+    LDD_LAUNCH(peaks_to_host_kernel, dim3(32), dim3(256), 0, (cudaStream_t)stream, peaks_dev, vals_dev, count_dev, cap, peaks_host,
+               vals_host, count_host);
+    return cudaGetLastError() == cudaSuccess ? LDD_OK : LDD_ECUDA;
+}
+
 // HOST restatement of the same chase for short windows whose samples are already in host memory (the
 // field walk's off-peak window starts, pipeline.py): comparisons only, so it returns exactly the list
 // the kernels above return for the same samples.

@@ -74,9 +74,9 @@ def sync_peaks_launch(rf, sync_buf, n, start=0, staging=None):
     pk, vl, cnt = st['pk'], st['vl'], st['cnt']
     rf._check(be.lib.ldd_sync_peaks(rf._h, be.ptr(sync_buf), int(n), int(start), be.ptr(pk), be.ptr(vl), st['cap'],
                                     be.ptr(cnt), be.stream()))
-    be.copy_async(st['h_cnt'], cnt)
-    be.copy_async(st['h_pk'][:cap], pk[:cap])
-    be.copy_async(st['h_vl'][:cap], vl[:cap])
+    # the list goes to pinned host memory through a kernel, not the copy engine (it would queue behind a field download)
+    rf._check(be.lib.ldd_peaks_to_host(be.ptr(pk), be.ptr(vl), be.ptr(cnt), st['cap'], be.ptr(st['h_pk']), be.ptr(st['h_vl']),
+                                       be.ptr(st['h_cnt']), be.stream()))
     return PendingPeaks(be, be.record_event(), st['h_pk'], st['h_vl'], st['h_cnt'], st)
 
 
@@ -161,7 +161,7 @@ def refine_and_tbc(rf, planes, plane_len, batch, colorlevel=1.45, colorphase=91.
     pk[o_bad:o_bad + n * LL_STRIDE] = np.ascontiguousarray(batch.linebad).reshape(-1)
     if staging is not None:
         d_pk = be.empty(npk, np.uint8)
-        be.copy_async(d_pk, staging['tbl'][:npk])
+        rf._check(be.lib.ldd_copy_small(be.ptr(d_pk), be.ptr(staging['tbl']), npk, be.stream()))     # not the copy engine: see ldd_b200.h
         staging['tbl_ev'] = be.record_event()
     else:
         d_pk = be.to_device(pk)

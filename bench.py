@@ -356,9 +356,9 @@ def run_ours(a):
         except Exception:
             pass
         # kernels of this library launched per step: demodulation (+ the float64 re-run of the mixed lane), 5 of the peak
-        # chase, hsync refinement + fix-up, pilot (per-line + per-field) or 2x burst, TBC, 2 of audio phase 2; one window
-        # of a capture starts off a peak and is chased on the host (no launch)
-        launches_per_step = a.ranges * ((2 if a.precision == "mixed" else 1) + 5 + 2 + 2 + 1 + (2 if audio else 0))
+        # chase + the peak list's copy to pinned memory, table upload, hsync refinement + fix-up, pilot (per-line +
+        # per-field) or 2x burst, TBC, 2 of audio phase 2
+        launches_per_step = a.ranges * ((2 if a.precision == "mixed" else 1) + 5 + 1 + 1 + 2 + 2 + 1 + (2 if audio else 0))
         line = dict(metric="rf_msamples_per_s_demod_tbc", value=value, unit="Msamples/s", n_gpus=world, steps=a.steps,
                     warmup=max(a.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype={"mixed": "f32+f64", "f64": "f64", "f32": "f32"}[a.precision], data="synthetic",

@@ -148,15 +148,48 @@ def workload_config(system, audio, gpus):
 
 # ---- clocks -----------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  In-process NVML queries every few ms (an
+    `nvidia-smi -lms` child stalls the driver for milliseconds per sample, which is visible in a 2 ms step); falls back
+    to nvidia-smi when pynvml is missing."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
-        self.rows = []
+    def __init__(self, index, period_s=0.01):
+        self.rows = []          # (time, sm_mhz, max_mhz, reasons bitmask)   [nvml]  or (time, csv line) [nvidia-smi]
         self.proc = None
         self.index = index
+        self.period = period_s
+        self.nvml = None
+        self._stop = False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            except Exception:
+                pass
+            h = None
+            if uuid:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    u = pynvml.nvmlDeviceGetUUID(hi)
+                    u = u.decode() if isinstance(u, bytes) else u
+                    if uuid in u:
+                        h = hi
+                        break
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml, self.h = pynvml, h
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -165,17 +198,41 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self._stop:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                try:
+                    r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.time(), sm, self.mx, r))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0=None, t1=None):
         """Summary of the samples taken between wall-clock times t0 and t1 (the timed region)."""
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self.nvml is not None:
+            self._stop = True
+            n = self.nvml
+            bits = [n.nvmlClocksThrottleReasonHwSlowdown, n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    n.nvmlClocksThrottleReasonSwThermalSlowdown, n.nvmlClocksThrottleReasonSwPowerCap]
+            rows = [r for r in self.rows if (t0 is None or r[0] >= t0 - 0.01) and (t1 is None or r[0] <= t1 + 0.01)]
+            reasons = sorted({nm for r in rows for nm, bit in zip(names, bits) if r[3] & bit})
+            sm = [r[1] for r in rows]
+            return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=self.mx, reasons=reasons, samples=len(sm),
+                        source="nvml")
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         rows = [r for (t, r) in self.rows if (t0 is None or t >= t0 - 0.11) and (t1 is None or t <= t1 + 0.11)]
         for r in rows:
             p = [x.strip() for x in r.split(",")]
@@ -190,7 +247,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), source="nvidia-smi")
 
 
 # ---- our arm ----------------------------------------------------------------------------------------

@@ -59,8 +59,8 @@ class CudaBackend:
         return self.torch.is_tensor(x) and x.is_cuda
 
     # -- streams / events / pinned staging (whole-capture pipeline)
-    def new_stream(self):
-        return self.torch.cuda.Stream(self.device)
+    def new_stream(self, high_priority=False):
+        return self.torch.cuda.Stream(self.device, priority=-1 if high_priority else 0)
 
     def stream_ctx(self, stream):
         return self.torch.cuda.stream(stream)
@@ -136,7 +136,7 @@ class EmuBackend:
         return False
 
     # -- streams / events: everything is synchronous in the emulation
-    def new_stream(self):
+    def new_stream(self, high_priority=False):
         return None
 
     def stream_ctx(self, stream):

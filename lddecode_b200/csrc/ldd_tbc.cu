@@ -70,7 +70,7 @@ __device__ inline int tbc_floor_nonneg(double x) {        // (int)x for 0 <= x <
 #endif
 }
 
-__global__ void __launch_bounds__(TBC_THREADS, 3) tbc_kernel(const TbcParams p) {
+__global__ void __launch_bounds__(TBC_THREADS, 4) tbc_kernel(const TbcParams p) {
     LDD_DYN_SMEM(smem_raw);
     // Both arrays are indexed by u = i + H through PX(u) = u + u/16: a thread owns 16 consecutive samples, and
     // the padding slot per 16 puts the chunks of neighbouring threads 17 doubles apart (no bank conflicts).
@@ -83,15 +83,16 @@ __global__ void __launch_bounds__(TBC_THREADS, 3) tbc_kernel(const TbcParams p) 
 
     const int tid = threadIdx.x;
     const int field = blockIdx.y, line = blockIdx.x;
+    // all four table reads are issued together (line + lineoffset + 1 < ll_stride for every line of the grid)
     const int linecount = p.linecount[field];
-    if (line >= linecount) return;
     const double* ll = p.linelocs + (size_t)field * p.ll_stride;
     const double b = ll[p.lineoffset + line] + p.lineloc_add, e = ll[p.lineoffset + line + 1] + p.lineloc_add;
+    const long long base = p.base ? p.base[field] : 0;
+    if (line >= linecount) return;
     const long long ib = (long long)b, ie = (long long)e;
     const int dist = (int)(ie - ib);
     const int W = p.outwidth;
     char* outbase = (char*)p.out;
-    const long long base = p.base ? p.base[field] : 0;
     if (!(b >= 0.0) || dist < 3 || dist > p.maxd || base + ib + dist + 1 > p.n || base + ib < 0) {
         if (tid == 0) atomicOr(&p.status[field], 1);
         return;
@@ -160,19 +161,20 @@ __global__ void __launch_bounds__(TBC_THREADS, 3) tbc_kernel(const TbcParams p) 
     __syncthreads();
     if (act) {
         const int q = tid;
-        double F[TBC_C];
         double f = (q >= 1 ? Lf[q - 1] : 0.0) + (q >= 2 ? r16 * Lf[q - 2] : 0.0);
         double bk = (q + 1 < nq ? Lb[q + 1] : 0.0) + (q + 2 < nq ? r16 * Lb[q + 2] : 0.0);
+        double* M = Ms + q * (TBC_C + 1);                   // M[k] <-> u = 1 + 16 q + k: PX = 17 q + 1 + k, behind the padding slot for k = 15
+        // forward sweep parks F - d in the thread's own slots of Ms, the backward sweep completes them (registers: only d)
         LDD_UNROLL
         for (int k = 0; k < TBC_C; ++k) {
             f = fma(f, r, d[k]);
-            F[k] = f - d[k];
+            M[k + 1 < TBC_C ? k + 1 : k + 2] = f - d[k];
         }
-        double* M = Ms + q * (TBC_C + 1);                   // M[k] <-> u = 1 + 16 q + k: PX = 17 q + 1 + k, behind the padding slot for k = 15
         LDD_UNROLL
         for (int k = TBC_C - 1; k >= 0; --k) {
             bk = fma(bk, r, d[k]);
-            M[k + 1 < TBC_C ? k + 1 : k + 2] = c * (F[k] + bk);
+            double* m = &M[k + 1 < TBC_C ? k + 1 : k + 2];
+            *m = c * (*m + bk);
         }
     }
     __syncthreads();
@@ -248,6 +250,7 @@ extern "C" int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n
     if (!h || !plane_dev || !linelocs_dev || !linecount_dev || !out_dev || !status_dev) return LDD_EINVAL;
     if (nfields <= 0 || max_linecount <= 0) return LDD_OK;
     if (outwidth < 1 || (mode != 0 && mode != 1)) return LDD_EINVAL;
+    if (lineoffset < 0 || lineoffset + max_linecount + 1 > ll_stride) return LDD_EINVAL;      // every CTA of the grid reads its two line positions
     const ldd_config& c = h->cfg;
     TbcParams p;
     p.plane = plane_dev; p.n = n; p.plane_add = plane_add;

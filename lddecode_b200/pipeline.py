@@ -21,6 +21,7 @@ instead of one grid per field, so demod_sync differs by the FPsync wrap term (< 
 peak indices, line tables and TBC output are compared against the reference flow in tests/.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -85,7 +86,7 @@ class HostStreamDecoder:
     def finish(self, pend):
         """Host walk, refinement and TBC of a launched chunk; starts the download of its fields."""
         be = self.be
-        res = self.cd._finish_range(self.cd.rf, pend)
+        res = self.cd._finish_range(self.cd.rf, pend, side=self.cd._side_stream() if self.cd.overlap_refine else None)
         j = self.nfin % 2
         self.nfin += 1
         nloc = len(res.located)
@@ -146,6 +147,8 @@ class CaptureDecoder:
         self._staging = {}
         self._lanes = None          # extra (RFDecode, stream, workspace, staging) sets of decode_pipelined
         self._lane2 = None          # second workspace of decode_stream / HostStreamDecoder
+        self._side = None
+        self.overlap_refine = os.environ.get("LDD_NO_REFINE_OVERLAP") is None
 
     def _lane(self, i):
         """Workspace + staging set i (0 = the default one); a second set lets the demodulation of the
@@ -174,7 +177,7 @@ class CaptureDecoder:
         while pend is not None:
             c = next(it, None)
             nxt = launch(c) if c is not None else None
-            yield self._finish_range(self.rf, pend)
+            yield self._finish_range(self.rf, pend, side=self._side_stream() if self.overlap_refine else None)
             pend = nxt
 
     def _buf(self, tag, n, dtype, ws=None):
@@ -254,9 +257,19 @@ class CaptureDecoder:
                 res.audio = {'audio_left': a1l, 'audio_right': a1r}
         return res
 
-    def _finish_range(self, rf, res, want_tables=False):
-        """Stage 2: host walk over the peak list, then the batched refine + TBC launches."""
+    def _side_stream(self):
+        """High-priority stream for the refine + TBC kernels of a streaming decode: the next capture's demodulation is
+        already enqueued on the main stream when they are launched; on their own stream they fill the SMs that the tail
+        of its float32 pass and its float64 re-run (one CTA on 4 % of the blocks) leave idle."""
+        if self._side is None:
+            self._side = self.rf._be.new_stream(high_priority=True)
+        return self._side
+
+    def _finish_range(self, rf, res, want_tables=False, side=None):
+        """Stage 2: host walk over the peak list, then the batched refine + TBC launches (on `side` when given; the
+        current stream is ordered behind them before this returns, so callers keep using the current stream)."""
         planes, total, r0, r1 = res.planes, res.plane_len, res.r0, res.r1
+        ready_ev = res.pending_peaks.ev                      # recorded behind the demodulation and the peak chase
         gpk, gvl = res.pending_peaks.result()
         res.pending_peaks = None
         res.gpeaks = gpk
@@ -279,8 +292,17 @@ class CaptureDecoder:
         if len(located):
             idx = owned[located]
             sub = F.FieldBatch.view(rf, batch, idx, np.fromiter((infos[i].linecount for i in idx), dtype=np.int32, count=len(idx)))
-            ref = F.refine_and_tbc(rf, planes, total, sub, self.colorlevel, self.colorphase, want_intermediates=want_tables,
-                                   staging=res.staging)
+            be = rf._be
+            if side is not None:
+                be.stream_wait_event(side, ready_ev)
+                with be.stream_ctx(side):
+                    ref = F.refine_and_tbc(rf, planes, total, sub, self.colorlevel, self.colorphase, want_intermediates=want_tables,
+                                           staging=res.staging)
+                    done = be.record_event()
+                be.stream_wait_event(be.current_stream_obj(), done)
+            else:
+                ref = F.refine_and_tbc(rf, planes, total, sub, self.colorlevel, self.colorphase, want_intermediates=want_tables,
+                                       staging=res.staging)
             res.refined = ref
             res.d_pic, res.d_status = ref.d_pic, ref.d_status
         return res

@@ -81,7 +81,7 @@ def main():
     be = rf._be
     stg = {}
     ms = timeit(lambda: F.sync_peaks_launch(rf, planes['demod_sync'], total, 0, stg))
-    rec("peaks_phase1+merge+gather (sync-peak chase)", ms, total * 8, "reads the float64 sync plane once")
+    rec("peak chase (peaks_phase1 + merge + scan + copy + list to pinned host memory)", ms, total * 8, "reads the float64 sync plane once")
     # refine + tbc on the located fields
     n = len(res.located)
     W = rf.SysParams['outlinelen']
@@ -94,12 +94,12 @@ def main():
     d_l2 = be.empty(n * F.LL_STRIDE, np.float64); d_b2 = be.empty(n * F.LL_STRIDE, np.uint8); d_st = be.zeros(n, np.int32)
     ms = timeit(lambda: lib.ldd_refine_hsync(rf._h, be.ptr(planes['demod_05']), total, be.ptr(d['base']), be.ptr(d['winlen']), be.ptr(d['linecount']),
                                              n, F.LL_STRIDE, be.ptr(d['linelocs1']), be.ptr(d['linebad']), be.ptr(d_l2), be.ptr(d_b2), be.ptr(d_st), be.stream()))
-    rec("refine_hsync_kernel", ms, lines * 4 * 650, "~650 demod_05 samples per line")
+    rec("refine_hsync_kernel + fix-up", ms, lines * 4 * 650, "~650 demod_05 samples per line")
     d_l3 = be.empty(n * F.LL_STRIDE, np.float64)
     if system == "PAL":
         ms = timeit(lambda: lib.ldd_refine_pilot(rf._h, be.ptr(planes['demod']), be.ptr(planes['demod_05']), total, be.ptr(d['base']), be.ptr(d['linecount']),
                                                  n, F.LL_STRIDE, be.ptr(d_l2), be.ptr(d_l3), be.ptr(d_st), be.stream()))
-        rec("refine_pilot_kernel", ms, lines * 8 * 167, "167 samples of two planes per line")
+        rec("pilot_lines_kernel + pilot_median_kernel", ms, lines * 8 * 167, "167 samples of two planes per line")
     else:
         d_bl = be.empty(n * F.LL_STRIDE, np.float32)
         ms = timeit(lambda: lib.ldd_refine_burst(rf._h, be.ptr(planes['demod_burst']), total, be.ptr(d['base']), be.ptr(d['linecount']),

@@ -154,7 +154,7 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index, period_s=0.01):
+    def __init__(self, index, period_s=0.02):
         self.rows = []          # (time, sm_mhz, max_mhz, reasons bitmask)   [nvml]  or (time, csv line) [nvidia-smi]
         self.proc = None
         self.index = index

@@ -271,34 +271,32 @@ struct BurstParams {
 constexpr int BURST_K = 32;          // same Green's function reach as the TBC kernel
 constexpr int BURST_FIRST = 20, BURST_N = 40;
 constexpr int BURST_WIN = 192;       // input samples staged per line (>= 2*(FIRST+N)*max step + K + margin)
-constexpr int BURST_WARPS = 32;      // one warp per line in flight, 1024 threads per field
+constexpr int BURST_WARPS = 8;       // lines per CTA of the per-line kernel
+constexpr int BURST_VOTE_THREADS = 512;
 
-__global__ void __launch_bounds__(32 * BURST_WARPS) refine_burst_kernel(const BurstParams p) {
-    LDD_DYN_SMEM(bsm);
-    double (*ys)[BURST_WIN] = (double (*)[BURST_WIN])bsm;
-    double (*Ms)[BURST_WIN] = ys + BURST_WARPS;
-    double (*bas)[BURST_N] = (double (*)[BURST_N])(Ms + BURST_WARPS);
-    __shared__ double taps[2 * BURST_K + 3];
-    __shared__ double phase[2][512];
-    __shared__ int s_group;
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// w[m] = 6 (g[m-1] - 2 g[m] + g[m+1]), g[k] = r^|k| / (2 sqrt 3) truncated to |k| <= BURST_K: set once per process.
+__constant__ double c_burst_taps[2 * BURST_K + 3];
+
+// Per line (one warp each, grid over all lines of all fields): the resampled burst, its level, and the two
+// phase candidates of the line (lddecode_core.py:1061-1110).  ws_phase: [nfields][2][ll_stride].
+__global__ void __launch_bounds__(32 * BURST_WARPS) burst_lines_kernel(const BurstParams p, double* ws_phase) {
+    __shared__ double ys[BURST_WARPS][BURST_WIN];
+    __shared__ double Ms[BURST_WARPS][BURST_WIN];
+    __shared__ double bas[BURST_WARPS][BURST_N];
+    const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = blockIdx.x * BURST_WARPS + warp;
     const int linecount = p.linecount[f], nll = linecount + 4;
+    if (l >= nll) return;
     const long long base = p.base[f];
     const double* lin = p.linelocs_in + (size_t)f * p.ll_stride;
-    double* lout = p.linelocs_out + (size_t)f * p.ll_stride;
     float* level = p.burstlevel + (size_t)f * p.ll_stride;
-    const double r = -0.26794919243112270647, c = 0.28867513459481288225;
-    for (int m = tid; m <= 2 * (BURST_K + 1); m += blockDim.x) {
-        int k = m - (BURST_K + 1);
-        auto g = [&](int q) -> double { int a = q < 0 ? -q : q; return a > BURST_K ? 0.0 : c * pow(r, (double)a); };
-        taps[m] = 6.0 * (g(k - 1) - 2.0 * g(k) + g(k + 1));
-    }
-    for (int i = tid; i < 512; i += blockDim.x) { phase[0][i] = 0.0; phase[1][i] = 0.0; }
-    for (int i = tid; i < nll; i += blockDim.x) level[i] = 0.f;
-    __syncthreads();
+    double* ph0 = ws_phase + (size_t)f * 2 * p.ll_stride;
+    double* ph1 = ph0 + p.ll_stride;
+    float lev_out = 0.f;
+    double p0 = 0.0, p1 = 0.0;
     const double hz_ire = 1700000.0 / 140.0;
     const int W = p.outwidth;
-    for (int l = warp; l < linecount; l += BURST_WARPS) {
+    if (l < linecount) {
         const double b = lin[l], e = lin[l + 1];
         const long long ib = (long long)b, ie = (long long)e;
         const int dist = (int)(ie - ib);
@@ -313,94 +311,102 @@ __global__ void __launch_bounds__(32 * BURST_WARPS) refine_burst_kernel(const Bu
         if (!ok) {
             // geometry the fast path does not cover (or the reference would raise): flag, leave the line "no burst"
             if (lane == 0) atomicOr(&p.status[f], 4);
-            continue;
-        }
-        for (int k = lane; k < ns; k += 32) {
-            long long s = base + ib + s0 + k;
-            s = s < 0 ? 0 : (s >= p.n ? p.n - 1 : s);
-            ys[warp][k] = (double)p.burst[s];
-        }
-        __syncwarp();
-        const int nm = i1 - i0 + 1;                         // M[i0 .. i1]
-        for (int k = lane; k < nm; k += 32) {
-            double acc = 0.0;
-            const double* y = &ys[warp][k];                 // y[(i0+k) - (K+1)] is ys[k]
-            for (int m = 0; m <= 2 * (BURST_K + 1); ++m) acc += taps[m] * y[m];
-            Ms[warp][k] = acc;
-        }
-        __syncwarp();
-        for (int j = lane; j < BURST_N; j += 32) {
-            double x = (double)(BURST_FIRST + j) * step + fb;
-            int i = (int)x;
-            double t = x - (double)i, u = 1.0 - t;
-            double Mi = Ms[warp][i - i0], Mj = Ms[warp][i + 1 - i0];
-            double yi = ys[warp][i - s0], yj = ys[warp][i + 1 - s0];
-            double S = Mi * u * u * u / 6.0 + Mj * t * t * t / 6.0 + (yi - Mi / 6.0) * u + (yj - Mj / 6.0) * t;
-            bas[warp][j] = S * wowf;
-        }
-        __syncwarp();
-        if (lane == 0) {
-            double* ba = bas[warp];
-            double mean = np_mean(ba, BURST_N);
-            for (int k = 0; k < BURST_N; ++k) ba[k] -= mean;
-            double mx = 0.0;
-            for (int k = 0; k < BURST_N; ++k) mx = fabs(ba[k]) > mx ? fabs(ba[k]) : mx;
-            float lev = (float)mx;
-            // np.std(ba): mean again, deviations, pairwise sum of squares
-            double m2 = np_mean(ba, BURST_N);
-            double dev[BURST_N];
-            for (int k = 0; k < BURST_N; ++k) { double q = ba[k] - m2; dev[k] = q * q; }
-            double sd = sqrt(np_sum(dev, BURST_N) / (double)BURST_N);
-            const float hz_ire32 = (float)hz_ire;
-            if ((lev / hz_ire32) > 30.f || (sd / hz_ire) < 3) {
-                level[l] = 0.f;
-            } else {
-                level[l] = lev;
-                const double thr = (double)(lev * 0.6f);
-                double offF[BURST_N], offT[BURST_N];
-                int nF = 0, nT = 0;
-                auto dat = [&](long long k) -> double { return ba[k]; };
-                int bi = 0;
-                while (bi < BURST_N) {
-                    if (fabs(ba[bi]) > thr) {
-                        double zc;
-                        if (calczc(dat, BURST_N, bi, 0.0, 10, &zc)) {
-                            double off = zc - ((floor(zc / 4) * 4) - 1);
-                            if (off > 3.5) off -= 4;
-                            if (ba[bi] > 0) offT[nT++] = off; else offF[nF++] = off;
-                            bi = (int)zc;
+        } else {
+            for (int k = lane; k < ns; k += 32) {
+                long long s = base + ib + s0 + k;
+                s = s < 0 ? 0 : (s >= p.n ? p.n - 1 : s);
+                ys[warp][k] = (double)p.burst[s];
+            }
+            __syncwarp();
+            const int nm = i1 - i0 + 1;                         // M[i0 .. i1]
+            for (int k = lane; k < nm; k += 32) {
+                double acc = 0.0;
+                const double* y = &ys[warp][k];                 // y[(i0+k) - (K+1)] is ys[k]
+                for (int m = 0; m <= 2 * (BURST_K + 1); ++m) acc += c_burst_taps[m] * y[m];
+                Ms[warp][k] = acc;
+            }
+            __syncwarp();
+            for (int j = lane; j < BURST_N; j += 32) {
+                double x = (double)(BURST_FIRST + j) * step + fb;
+                int i = (int)x;
+                double t = x - (double)i, u = 1.0 - t;
+                double Mi = Ms[warp][i - i0], Mj = Ms[warp][i + 1 - i0];
+                double yi = ys[warp][i - s0], yj = ys[warp][i + 1 - s0];
+                double S = Mi * u * u * u / 6.0 + Mj * t * t * t / 6.0 + (yi - Mi / 6.0) * u + (yj - Mj / 6.0) * t;
+                bas[warp][j] = S * wowf;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                double* ba = bas[warp];
+                double mean = np_mean(ba, BURST_N);
+                for (int k = 0; k < BURST_N; ++k) ba[k] -= mean;
+                double mx = 0.0;
+                for (int k = 0; k < BURST_N; ++k) mx = fabs(ba[k]) > mx ? fabs(ba[k]) : mx;
+                float lev = (float)mx;
+                // np.std(ba): mean again, deviations, pairwise sum of squares
+                double m2 = np_mean(ba, BURST_N);
+                double dev[BURST_N];
+                for (int k = 0; k < BURST_N; ++k) { double q = ba[k] - m2; dev[k] = q * q; }
+                double sd = sqrt(np_sum(dev, BURST_N) / (double)BURST_N);
+                const float hz_ire32 = (float)hz_ire;
+                if (!((lev / hz_ire32) > 30.f || (sd / hz_ire) < 3)) {
+                    lev_out = lev;
+                    const double thr = (double)(lev * 0.6f);
+                    double offF[BURST_N], offT[BURST_N];
+                    int nF = 0, nT = 0;
+                    auto dat = [&](long long k) -> double { return ba[k]; };
+                    int bi = 0;
+                    while (bi < BURST_N) {
+                        if (fabs(ba[bi]) > thr) {
+                            double zc;
+                            if (calczc(dat, BURST_N, bi, 0.0, 10, &zc)) {
+                                double off = zc - ((floor(zc / 4) * 4) - 1);
+                                if (off > 3.5) off -= 4;
+                                if (ba[bi] > 0) offT[nT++] = off; else offF[nF++] = off;
+                                bi = (int)zc;
+                            }
                         }
+                        ++bi;
                     }
-                    ++bi;
-                }
-                if (nF >= 3 && nT >= 3) {
-                    double mF = np_mean(offF + 1, nF - 2), mT = np_mean(offT + 1, nT - 2);
-                    if (l % 2) { phase[0][l] = 2 - mT; phase[1][l] = 2 - mF; }
-                    else { phase[0][l] = 2 - mF; phase[1][l] = 2 - mT; }
+                    if (nF >= 3 && nT >= 3) {
+                        double mF = np_mean(offF + 1, nF - 2), mT = np_mean(offT + 1, nT - 2);
+                        if (l % 2) { p0 = 2 - mT; p1 = 2 - mF; }
+                        else { p0 = 2 - mF; p1 = 2 - mT; }
+                    }
                 }
             }
         }
-        __syncwarp();
     }
+    if (lane == 0) { level[l] = lev_out; ph0[l] = p0; ph1[l] = p1; }
+}
+
+// Per field: the phase group vote (medians of both candidate columns over the lines that produced one,
+// lddecode_core.py:1112-1117), the shifted line positions and the interpolation of lines without burst.
+__global__ void __launch_bounds__(BURST_VOTE_THREADS) burst_vote_kernel(const BurstParams p, const double* ws_phase) {
+    __shared__ double phase[2][512];
+    __shared__ double col[2][512];
+    __shared__ double srt[2][512];
+    __shared__ int s_group, s_nc;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int linecount = p.linecount[f], nll = linecount + 4;
+    const double* lin = p.linelocs_in + (size_t)f * p.ll_stride;
+    double* lout = p.linelocs_out + (size_t)f * p.ll_stride;
+    float* level = p.burstlevel + (size_t)f * p.ll_stride;
+    const double* ph = ws_phase + (size_t)f * 2 * p.ll_stride;
+    for (int l = tid; l < nll; l += blockDim.x) { phase[0][l] = ph[l]; phase[1][l] = ph[p.ll_stride + l]; }
     __syncthreads();
-    // medians of both columns over lines that produced a phase (lddecode_core.py:1112-1117): compact,
-    // then rank-sort in parallel (each thread places one element), thread 0 reads the middles.
-    double* col0 = &ys[0][0];                 // the staging buffers are free now
-    double* col1 = col0 + 512;
-    double* srt0 = col1 + 512;
-    double* srt1 = srt0 + 512;
-    __shared__ int s_nc;
     if (tid == 0) {
         int nc = 0;
         for (int l = 0; l < nll; ++l)
-            if (phase[0][l] != 0 || phase[1][l] != 0) { col0[nc] = phase[0][l]; col1[nc] = phase[1][l]; ++nc; }
+            if (phase[0][l] != 0 || phase[1][l] != 0) { col[0][nc] = phase[0][l]; col[1][nc] = phase[1][l]; ++nc; }
         s_nc = nc;
     }
     __syncthreads();
     const int nc = s_nc;
+    // rank-sort both columns in parallel (each thread places one element), thread 0 reads the middles
     for (int t = tid; t < 2 * nc; t += blockDim.x) {
-        const double* c = t < nc ? col0 : col1;
-        double* d = t < nc ? srt0 : srt1;
+        const double* c = t < nc ? col[0] : col[1];
+        double* d = t < nc ? srt[0] : srt[1];
         const int me = t < nc ? t : t - nc;
         const double v = c[me];
         int rank = 0;
@@ -411,8 +417,8 @@ __global__ void __launch_bounds__(32 * BURST_WARPS) refine_burst_kernel(const Bu
     if (tid == 0) {
         int group = 1;
         if (nc > 0) {
-            double m0 = (nc & 1) ? srt0[nc / 2] : (srt0[nc / 2 - 1] + srt0[nc / 2]) / 2.0;
-            double m1 = (nc & 1) ? srt1[nc / 2] : (srt1[nc / 2 - 1] + srt1[nc / 2]) / 2.0;
+            double m0 = (nc & 1) ? srt[0][nc / 2] : (srt[0][nc / 2 - 1] + srt[0][nc / 2]) / 2.0;
+            double m1 = (nc & 1) ? srt[1][nc / 2] : (srt[1][nc / 2 - 1] + srt[1][nc / 2]) / 2.0;
             group = fabs(m0) < fabs(m1) ? 0 : 1;
         }
         s_group = group;
@@ -420,20 +426,25 @@ __global__ void __launch_bounds__(32 * BURST_WARPS) refine_burst_kernel(const Bu
     __syncthreads();
     const int group = s_group;
     const double k4 = p.freq / (4.0 * 315.0 / 88.0);
+    // the shifted positions go through shared memory (col[0] is free) for the sequential interpolation pass
+    double* lo = col[0];
+    float* lv_s = (float*)col[1];
     for (int l = tid; l < nll; l += blockDim.x) {
         float lv = level[l];
         if ((l & 1) == (group & 1)) lv = -lv;          // burstlevel[phasegroup::2] = -burstlevel[phasegroup::2]
         double adj = phase[group][l];
         double v = lin[l];
         if (fabs(adj) > 2) lv = 0.f; else v -= adj * k4 * 1;
-        level[l] = lv;
-        lout[l] = v;
+        lv_s[l] = lv;
+        lo[l] = v;
     }
     __syncthreads();
     if (tid == 0) {
         for (int l = 2; l < nll - 1; ++l)
-            if (level[l] == 0.f) lout[l] = (lout[l - 1] + lout[l + 1]) / 2;
+            if (lv_s[l] == 0.f) lo[l] = (lo[l - 1] + lo[l + 1]) / 2;
     }
+    __syncthreads();
+    for (int l = tid; l < nll; l += blockDim.x) { level[l] = lv_s[l]; lout[l] = lo[l]; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -979,10 +990,25 @@ extern "C" int ldd_refine_burst(ldd_handle* h, const float* burst_dev, long long
     p.burst = burst_dev; p.n = n; p.freq = h->cfg.freq_hz / 1e6; p.linelen = h->cfg.linelen; p.outwidth = h->cfg.outlinelen;
     p.base = base_dev; p.linecount = linecount_dev; p.ll_stride = ll_stride; p.linelocs_in = linelocs_in_dev;
     p.linelocs_out = linelocs_out_dev; p.burstlevel = burstlevel_dev; p.status = status_dev;
-    size_t bsmem = (size_t)BURST_WARPS * (2 * BURST_WIN + BURST_N) * sizeof(double);
-    cudaFuncSetAttribute(refine_burst_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
-    LDD_LAUNCH(refine_burst_kernel, dim3(nfields), dim3(32 * BURST_WARPS), bsmem, (cudaStream_t)stream, p);
-    return launch_status(h, "refine_burst_kernel");
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t need = (size_t)nfields * 2 * ll_stride * sizeof(double) + 64;
+    if (need > h->pilot_ws_bytes) {          // the per-line workspace is shared with the PAL pilot kernels (one system per handle)
+        if (h->pilot_ws) { cudaStreamSynchronize(st); cudaFree(h->pilot_ws); h->pilot_ws = nullptr; }
+        if (cudaMalloc(&h->pilot_ws, need) != cudaSuccess) { h->pilot_ws_bytes = 0; h->err = "cudaMalloc burst workspace"; return LDD_ENOMEM; }
+        h->pilot_ws_bytes = need;
+    }
+    if (!h->burst_taps_set) {
+        const double r = -0.26794919243112270647, c = 0.28867513459481288225;
+        double taps[2 * BURST_K + 3];
+        auto g = [&](int q) -> double { int a = q < 0 ? -q : q; return a > BURST_K ? 0.0 : c * pow(r, (double)a); };
+        for (int m = 0; m <= 2 * (BURST_K + 1); ++m) { int k = m - (BURST_K + 1); taps[m] = 6.0 * (g(k - 1) - 2.0 * g(k) + g(k + 1)); }
+        cudaMemcpyToSymbol(c_burst_taps, taps, sizeof taps);
+        h->burst_taps_set = true;
+    }
+    double* ws = (double*)h->pilot_ws;
+    LDD_LAUNCH(burst_lines_kernel, dim3((ll_stride + BURST_WARPS - 1) / BURST_WARPS, nfields), dim3(32 * BURST_WARPS), 0, st, p, ws);
+    LDD_LAUNCH(burst_vote_kernel, dim3(nfields), dim3(BURST_VOTE_THREADS), 0, st, p, (const double*)ws);
+    return launch_status(h, "burst kernels");
 }
 
 extern "C" int ldd_refine_pilot(ldd_handle* h, const float* demod_dev, const float* d05_dev, long long n,

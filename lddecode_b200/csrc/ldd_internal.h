@@ -100,7 +100,8 @@ struct ldd_handle {
     size_t flags_cap = 0;
     double flag_margin = 16.0;       // Hz
     long long last_nblocks = 0;
-    bool tbc_taps_set = false;       // __constant__ FIR taps uploaded for this handle's device
+    bool tbc_taps_set = false;
+    bool burst_taps_set = false;     // __constant__ spline taps of the burst kernels uploaded       // __constant__ FIR taps uploaded for this handle's device
     size_t l2_window = 0;   // bytes of scratch covered by a persisting-L2 access policy window
     float l2_ratio = 1.0f;
     // audio phase 2

@@ -313,8 +313,6 @@ def run_ours(a):
             t = sd.upload(cap_pin, ncap) if i + 2 < nsteps else None
             job = sd.finish(pend)                                   # ... under the host walk of step i; D2H of its fields
             pend = nxt
-            if job[0].audio is not None:
-                job[0].audio_host = (job[0].audio['audio_left'].cpu(), job[0].audio['audio_right'].cpu())
             if world > 1:
                 gatherer.gather(job[0])
             if prev is not None:
@@ -324,7 +322,8 @@ def run_ours(a):
         _, pics = sd.fetch(prev)
         if world > 1:
             gatherer.wait()
-        return pics.size
+        na = 0 if prev[0].audio_host is None else 16 * len(prev[0].audio_host[0])      # two float64 channels
+        return pics.size, na
 
     # the sampler is started before the warm-up: nvidia-smi's start-up stalls the driver for ~100 ms
     clocks = ClockSampler(local)
@@ -359,7 +358,7 @@ def run_ours(a):
     barrier()
     t0 = time.perf_counter()
     e0.record()
-    npic = run_e2e(a.steps)
+    npic, naudio = run_e2e(a.steps)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -422,7 +421,7 @@ def run_ours(a):
                     config=dict(workload_config(system, audio, world), precision=a.precision),
                     realtime_x=value / FS[system] / world, fields_per_step=nfields * world,
                     e2e=dict(value=e2e_val, unit="Msamples/s", h2d_bytes_per_step=int(ncap),
-                             d2h_bytes_per_step=int(npic * 2), wall_ms_per_step=wall_e2e / a.steps),
+                             d2h_bytes_per_step=int(npic * 2 + naudio), wall_ms_per_step=wall_e2e / a.steps),
                     gpu_launches=launches_per_step * a.steps,
                     roofline=dict(bound="hbm", kernel="demod_kernel (fused unpack+FFT+filter+IFFT+FM discriminator+post filters+sync scan)",
                                   achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,

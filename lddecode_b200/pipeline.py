@@ -48,7 +48,8 @@ class HostStreamDecoder:
 
     upload() takes a pinned host buffer (be.pinned).  fetch() returns the RangeResult and a host view
     [nfields, out_stride] of its uint16 fields that stays valid until the second-next finish(); the
-    RangeResult's device planes stay valid until the second-next launch()."""
+    RangeResult's device planes stay valid until the second-next launch().  With analog audio decoding on, the two
+    channels are downloaded with the fields: res.audio_host = (left, right) float64 views, valid as long as the fields."""
 
     def __init__(self, cd, fmt, ncap_max, max_fields=96, np_dtype=np.uint8):
         self.cd, self.fmt, self.max_fields = cd, fmt, max_fields
@@ -59,6 +60,7 @@ class HostStreamDecoder:
         self.d_in = [be.empty(ncap_max, np_dtype) for _ in range(2)]
         self.h_out = [be.pinned(max_fields * self.out_stride, np.uint16) for _ in range(2)]
         self.h_status = [be.pinned(max_fields, np.int32) for _ in range(2)]
+        self.h_audio = [None, None]         # pinned (left, right) float64 buffers, allocated on first use
         self.in_free = [None, None]         # event: the demodulation that read d_in[k] has finished
         self.nup = self.nlaunch = self.nfin = 0
 
@@ -93,12 +95,23 @@ class HostStreamDecoder:
         if nloc > self.max_fields:
             raise ValueError("max_fields too small")
         dev = None
-        if nloc:
+        res.audio_host = None
+        if nloc or res.audio is not None:
             done = be.record_event()
             be.stream_wait_event(self.down, done)
             with be.stream_ctx(self.down):
-                be.copy_async(self.h_out[j][:nloc * self.out_stride], res.d_pic[:nloc * self.out_stride])
-                be.copy_async(self.h_status[j][:nloc], res.d_status[:nloc])
+                if nloc:
+                    be.copy_async(self.h_out[j][:nloc * self.out_stride], res.d_pic[:nloc * self.out_stride])
+                    be.copy_async(self.h_status[j][:nloc], res.d_status[:nloc])
+                if res.audio is not None:
+                    # the two analog audio channels ride along (pinned, double-buffered like the fields)
+                    al, ar = res.audio['audio_left'], res.audio['audio_right']
+                    na = len(al)
+                    if self.h_audio[j] is None or len(self.h_audio[j][0]) < na:
+                        self.h_audio[j] = (be.pinned(na, np.float64), be.pinned(na, np.float64))
+                    be.copy_async(self.h_audio[j][0][:na], al)
+                    be.copy_async(self.h_audio[j][1][:na], ar)
+                    res.audio_host = (be.host_view(self.h_audio[j][0])[:na], be.host_view(self.h_audio[j][1])[:na])
                 dev = be.record_event()
         return (res, j, nloc, dev)
 

@@ -329,6 +329,13 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
     p.scratch_per_cta = h->scratch_per_cta;
     cudaStream_t st = (cudaStream_t)stream;
     int grid = (int)(nblocks < h->grid ? nblocks : h->grid);
+    if (grid > 0 && !getenv("LDD_FULL_GRID")) {
+        // Balanced persistent grid: the kernel takes ceil(nblocks / grid) rounds whatever the last round's fill, so the
+        // smallest grid with the same number of rounds costs nothing and leaves the remaining SMs to whatever else is
+        // enqueued (the refine / TBC kernels of the previous capture on their side stream, NCCL's gather kernels).
+        const long long rounds = (nblocks + grid - 1) / grid;
+        grid = (int)((nblocks + rounds - 1) / rounds);
+    }
     if (audio) {
         // the reference leaves the unwritten tail of output_audio at zero (lddecode_core.py:417-422)
         CUDA_TRY(h, cudaMemsetAsync(audio1_l_dev, 0, (size_t)audio1_len * sizeof(double), st));

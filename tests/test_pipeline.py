@@ -124,6 +124,27 @@ def test_host_stream_decoder_equals_decode(backend):
     assert not np.array_equal(got[0][0][2], got[1][0][2])
 
 
+def test_host_stream_decoder_downloads_audio(backend):
+    """With analog audio decoding on, HostStreamDecoder brings the two phase-2 channels to the host with the
+    fields; they equal the device result of decode() on the same chunk."""
+    fs = 8 * 315 / 88
+    n = 1300000
+    cap = synth.SynthRF("NTSC", fs, seed=12).generate(n)
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=True, _backend=backend, precision="mixed")
+    cd = pipeline.CaptureDecoder(rf)
+    ref = cd.decode(backend.to_device(cap), _lib.FMT_U8, n)
+    want = (backend.to_host(ref.audio['audio_left']).copy(), backend.to_host(ref.audio['audio_right']).copy())
+    p = backend.pinned(n, np.uint8)
+    backend.host_view(p)[:] = cap
+    sd = pipeline.HostStreamDecoder(cd, _lib.FMT_U8, n, max_fields=8)
+    outs = list(sd.run([(p, n), (p, n)]))
+    assert len(outs) == 2
+    for res, pics in outs:
+        assert res.audio_host is not None and len(res.audio_host[0]) == len(want[0]) > 1000
+    res, _ = outs[-1]
+    assert np.array_equal(res.audio_host[0], want[0]) and np.array_equal(res.audio_host[1], want[1])
+
+
 def test_two_rank_gloo_gather():
     """world_size 2 over gloo on the CPU (emulated kernels): shard, decode, gather on rank 0."""
     script = os.path.join(ROOT, "tests", "dist_worker.py")

@@ -23,8 +23,7 @@ constexpr int TBC_H = 32;                 // halo samples on each side of the li
 constexpr int TBC_C = 16;                 // samples per thread chunk of the recursions
 constexpr int TBC_MAXD = 4032;            // longest input line span supported
 constexpr int TBC_THREADS = 256;
-constexpr int TBC_MAXU = TBC_MAXD + 1 + 2 * TBC_H;           // staged samples y[-H .. dist+H]
-constexpr int TBC_MAXQ = (TBC_MAXU + TBC_C - 1) / TBC_C;     // chunks
+static_assert((TBC_MAXD + 2 * TBC_H - 1 + TBC_C - 1) / TBC_C <= TBC_THREADS, "one chunk per thread");
 constexpr int TBC_NPOW = 64;              // r^64 = 4e-37: reach of the homogeneous correction
 
 // r^i, i < TBC_NPOW: set once per process.
@@ -238,6 +237,8 @@ __global__ void __launch_bounds__(TBC_THREADS, 4) tbc_kernel(const TbcParams p) 
     }
 }
 
+#undef PX
+#undef M0
 }  // namespace ldd
 
 using namespace ldd;

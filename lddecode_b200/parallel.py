@@ -26,7 +26,8 @@ def needed_window(cd, ncap, r0, r1):
 
 class FieldGatherer:
     """Gathers the located fields of every rank on rank 0.  Buffers are allocated once; gather()
-    only enqueues device work (a copy into the send buffer and two asynchronous collectives), to_host()
+    only enqueues device work (a copy into the send buffer and ONE asynchronous collective: the per-field
+    metadata rides in the head of the same buffer as the pictures), to_host()
     turns the gathered buffers into a list of (readsample, istop, picture | None) ordered by read
     position; call it before the next gather() overwrites them."""
 
@@ -40,13 +41,22 @@ class FieldGatherer:
         self.stride = (rf.SysParams['frame_lines'] // 2 + 1) * self.W
         self.cuda = self.be.name == "cuda"
         dev = self.be.device if self.cuda else "cpu"
-        self.pic = torch.zeros(max_fields * self.stride * 2, dtype=torch.uint8, device=dev)       # uint16 as bytes
-        self.meta = torch.zeros((max_fields, 4), dtype=torch.int64, device=dev)                   # readsample, istop, linecount, status
+        self.meta_bytes = max_fields * 4 * 8                     # int64 [max_fields][4]: readsample, istop, linecount, status
+        self.buf = torch.zeros(self.meta_bytes + max_fields * self.stride * 2, dtype=torch.uint8, device=dev)
+
+        def split(b):
+            return b[:self.meta_bytes].view(torch.int64).view(max_fields, 4), b[self.meta_bytes:]      # (meta, uint16 pictures as bytes)
+        self.meta, self.pic = split(self.buf)
         if rank == 0 and world > 1:
-            self.pics = [torch.empty_like(self.pic) for _ in range(world)]
-            self.metas = [torch.empty_like(self.meta) for _ in range(world)]
+            self.bufs = [torch.empty_like(self.buf) for _ in range(world)]
+            parts = [split(b) for b in self.bufs]
+            self.metas, self.pics = [p[0] for p in parts], [p[1] for p in parts]
         else:
+            self.bufs = None
             self.pics, self.metas = [self.pic], [self.meta]
+        # host staging of the metadata: page-locked and double-buffered on CUDA (uploaded by a kernel, not the copy engine)
+        self._hmeta = [self.be.pinned(max_fields * 4, np.int64) for _ in range(2)] if self.cuda else None
+        self._n = 0
         self._work = []
 
     def gather(self, results):
@@ -54,27 +64,37 @@ class FieldGatherer:
         torch = self.torch
         if not isinstance(results, (list, tuple)):
             results = [results]
-        meta = np.full((self.max_fields, 4), -1, dtype=np.int64)
+        if self.cuda:
+            hm = self._hmeta[self._n % 2]
+            self._n += 1
+            meta = self.be.host_view(hm).reshape(self.max_fields, 4)
+            meta[:] = -1
+        else:
+            meta = np.full((self.max_fields, 4), -1, dtype=np.int64)
         k0 = 0
         spans = []
         for res in results:
             nloc = len(res.located)
             if k0 + nloc > self.max_fields:
                 raise ValueError("max_fields too small")
-            for k, j in enumerate(res.located):
-                info = res.infos[j]
-                meta[k0 + k] = (res.readsamples[j], info.istop, info.linecount, 0)
+            if nloc:
+                loc = np.asarray(res.located, dtype=np.intp)
+                meta[k0:k0 + nloc, 0] = np.asarray(res.readsamples)[loc]
+                meta[k0:k0 + nloc, 1] = np.fromiter((res.infos[j].istop for j in res.located), dtype=np.int64, count=nloc)
+                meta[k0:k0 + nloc, 2] = np.fromiter((res.infos[j].linecount for j in res.located), dtype=np.int64, count=nloc)
+                meta[k0:k0 + nloc, 3] = 0
             spans.append((k0, nloc, res))
             k0 += nloc
-        tm = torch.from_numpy(meta)
         self.wait()
         if self.cuda:
-            self.meta.copy_(tm, non_blocking=True)
+            be = self.be
+            be.lib.ldd_copy_small(be.ptr(self.buf), be.ptr(hm), self.meta_bytes, be.stream())
             for k0, nloc, res in spans:
                 if nloc:
                     self.meta[k0:k0 + nloc, 3] = res.d_status[:nloc].to(torch.int64)
                     self.pic[k0 * self.stride * 2:(k0 + nloc) * self.stride * 2] = res.d_pic[:nloc * self.stride].view(torch.uint8)
         else:
+            tm = torch.from_numpy(meta)
             for k0, nloc, res in spans:
                 if nloc:
                     tm[k0:k0 + nloc, 3] = torch.from_numpy(np.asarray(self.be.to_host(res.d_status)[:nloc], dtype=np.int64))
@@ -82,11 +102,10 @@ class FieldGatherer:
                         torch.from_numpy(self.be.to_host(res.d_pic)[:nloc * self.stride].view(np.uint8))
             self.meta.copy_(tm)
         if self.world > 1:
-            # asynchronous: the collectives run on the process group's own stream behind the copies
-            # above, so the next range's demodulation overlaps them; wait() orders the caller's
-            # stream (not the host) behind them
-            self._work = [self.dist.gather(self.pic, self.pics if self.rank == 0 else None, dst=0, async_op=True),
-                          self.dist.gather(self.meta, self.metas if self.rank == 0 else None, dst=0, async_op=True)]
+            # asynchronous: the collective runs on the process group's own stream behind the copies
+            # above, so the next range's demodulation overlaps it; wait() orders the caller's
+            # stream (not the host) behind it
+            self._work = [self.dist.gather(self.buf, self.bufs if self.rank == 0 else None, dst=0, async_op=True)]
 
     def wait(self):
         """Order the current stream behind the last gather (called before the send buffers are rewritten

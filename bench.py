@@ -325,7 +325,8 @@ def run_ours(a):
         na = 0 if prev[0].audio_host is None else 16 * len(prev[0].audio_host[0])      # two float64 channels
         return pics.size, na
 
-    # the sampler is started before the warm-up: nvidia-smi's start-up stalls the driver for ~100 ms
+    # the sampler is started before the warm-up (NVML initialisation, or nvidia-smi's start-up in the fallback, stalls
+    # the driver for ~100 ms)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define LDD_ABI_VERSION 1
+#define LDD_ABI_VERSION 2
 
 #define LDD_SYSTEM_NTSC 0
 #define LDD_SYSTEM_PAL 1
@@ -57,6 +57,8 @@ extern "C" {
 #define LDD_F_AUDIO_L 5    /* Filters['audio_lfilt'], already sliced: 2*blocklen/audio_fdiv1 entries */
 #define LDD_F_AUDIO_R 6    /* Filters['audio_rfilt'] */
 #define LDD_F_AUDIO_LPF2 7 /* Filters['audio_lpf2'], blocklen/4 entries */
+#define LDD_F_MTF 8        /* Filters['MTF'], blocklen complex128.  Once it is set, LDD_F_RFVIDEO is taken as Filters['RFVideo']
+                              alone (level 0) and ldd_set_mtf_level() applies MTF**level on the device */
 
 #define LDD_P_DEMOD 0
 #define LDD_P_DEMOD05 1
@@ -116,8 +118,13 @@ void ldd_destroy(ldd_handle* h);
 const char* ldd_last_error(ldd_handle* h);
 
 /* Upload one host-built frequency-domain table (interleaved re,im float64, n complex entries).
- * Synchronous.  Re-upload LDD_F_RFVIDEO whenever mtf_level changes (lddecode_core.py:292-293). */
+ * Synchronous (set-up time).  The MTF level is NOT baked into a table: see ldd_set_mtf_level. */
 int ldd_set_filter(ldd_handle* h, int id, const double* table, int n);
+
+/* RFVideo * MTF ** mtf_level (lddecode_core.py:290-293) for every later demodulation on `stream`: one small
+ * stream-ordered kernel, so following the reference's per-frame level changes on CAV discs (:1300-1306) costs neither
+ * a host-side complex power nor a blocking upload.  Needs LDD_F_RFVIDEO (level 0) and LDD_F_MTF. */
+int ldd_set_mtf_level(ldd_handle* h, double mtf_level, void* stream);
 
 /* ---- kernel (1): unpack.  Replaces ddunpack.c:11-36 and lddutils.py:150-229. ------------------ */
 /* words[nwords] (LE u32, dev) -> out[3*nwords] int16 = ((field)-512)<<6, exactly ddunpack.c */
@@ -168,6 +175,20 @@ int ldd_mixed_stats(ldd_handle* h, long long* flagged_blocks, long long* total_b
 /* RFDecode.audio_phase2 (lddecode_core.py:335-371): in[len] -> out[len/4], float64, dev. */
 int ldd_audio_phase2(ldd_handle* h, const double* in_l_dev, const double* in_r_dev, long long len,
                      double* out_l_dev, double* out_r_dev, void* stream);
+
+/* downscale_audio (lddecode_core.py:431-484), batched over fields: 48 kHz (or any rate) int16 L/R PCM resampled along the
+ * line positions from the phase-2 audio.  Output sample i of field f belongs to time arange[i] of the reference's
+ * np.arange(timeoffset, frametime + 1/freq, 1/freq): t0 = arange[0], t1 = arange[1] (numpy fills t0 + i * (t1 - t0) from
+ * i = 2 on), nout = len(arange) - 1, computed by the caller, who also carries arange[-1] - frametime into the next field.  linelocs [nfields][ll_stride]
+ * (+ lineloc_add) is Field.linelocs, nll its length (linecount + 4), audio_base_dev[f] the index of the field window's
+ * first audio sample in audio_*_dev (NULL: 0), scale the reference's `scale` argument (64).  out_dev receives
+ * 2 * nout[f] int16 at out_off[f].  status bit 16: an index left the arrays (the reference raises). */
+int ldd_downscale_audio(ldd_handle* h, const double* audio_l_dev, const double* audio_r_dev, long long audio_len,
+                        const long long* audio_base_dev, const double* linelocs_dev, int ll_stride,
+                        const int* nll_dev, const double* t0_dev, const double* t1_dev, const int* nout_dev,
+                        const long long* out_off_dev, int nfields, int max_nout, double lineloc_add, double scale,
+                        double line_period_us, double audio_lfreq, double audio_rfreq,
+                        short* out_dev, int* status_dev, void* stream);
 
 /* ---- kernel (4): sync-pulse peak list.  Bit-exact Field.get_syncpeaks (lddecode_core.py:497-516)
  * over sync_dev[0..n) (the float64 demod_sync plane) starting at index `start`, with the handle's
@@ -291,6 +312,101 @@ int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n, double pl
                    int max_linecount, int lineoffset, double lineloc_add, int outwidth, int wow, int mode,
                    void* out_dev, long long out_stride, const float* burstlevel_dev, double colorlevel,
                    int* status_dev, void* stream);
+
+/* The same with an explicit output layout: field f's line 0 starts at element out_off_dev[f] of out_dev (NULL:
+ * f * out_stride) and consecutive lines are line_stride elements apart (0: outwidth).  With line_stride = 2 * outwidth and
+ * the two fields of a frame at offsets 0 and outwidth this writes interleaved frames directly, i.e. Framer.formatoutput
+ * (lddecode_core.py:1238-1252) without a second pass over the pictures. */
+int ldd_tbc_fields_ex(ldd_handle* h, const float* plane_dev, long long n, double plane_add, const long long* base_dev,
+                      const double* linelocs_dev, int ll_stride, const int* linecount_dev, int nfields,
+                      int max_linecount, int lineoffset, double lineloc_add, int outwidth, int wow, int mode,
+                      void* out_dev, long long out_stride, const long long* out_off_dev, long long line_stride,
+                      const float* burstlevel_dev, double colorlevel, int* status_dev, void* stream);
+
+/* ---- VBI: Field.decodephillipscode (lddecode_core.py:814-834), batched.  For field f and code line lines[i]
+ * (SysParams['philips_codelines']) codes_dev[4 f + i] receives the 24-bit Philips code (first cell = bit 23, i.e. the six
+ * nibbles of the reference's `linecode`) or -1 where the reference returns None.  linelocs_dev is Field.linelocs at that
+ * point of Field.__init__ (linelocs2); base/winlen as in ldd_refine_hsync (NULL: the whole plane is one window). */
+int ldd_vbi_decode(ldd_handle* h, const float* demod_dev, long long n, const long long* base_dev,
+                   const long long* winlen_dev, const double* linelocs_dev, int ll_stride, int nfields,
+                   const int* lines, int nlines, int* codes_dev, void* stream);
+
+/* ---- whole-range pipeline: Framer.readfield's loop (lddecode_core.py:1194-1223) over a range of a capture in two calls.
+ * All buffers are the caller's.  One ldd_pipe per plane workspace; two of them software-pipeline a stream of ranges
+ * (launch k+1, then finish k).  A pipe is used from one thread. */
+typedef struct ldd_pipe ldd_pipe;
+
+typedef struct ldd_pipe_bufs {
+    /* device */
+    void* planes[5];            /* LDD_P_*: plane_cap float32 each, float64 for LDD_P_SYNC; [LDD_P_PILOT] PAL only */
+    long long plane_cap;
+    double* audio1_l;           /* phase-1 audio, audio1_cap each; NULL: audio off */
+    double* audio1_r;
+    long long audio1_cap;
+    double* audio2_l;           /* phase-2 audio, audio1_cap / 4 each */
+    double* audio2_r;
+    long long* peaks;           /* peak_cap */
+    double* peak_vals;          /* peak_cap */
+    int* peak_count;            /* 2 */
+    int peak_cap;
+    unsigned char* field_tables;    /* tables_bytes >= device_bytes of ldd_pipe_table_bytes */
+    long long tables_bytes;
+    /* page-locked host */
+    long long* h_peaks;         /* peak_cap */
+    double* h_peak_vals;        /* peak_cap */
+    int* h_peak_count;          /* 2 */
+    unsigned char* h_tables;    /* h_tables_bytes >= upload_bytes of ldd_pipe_table_bytes */
+    long long h_tables_bytes;
+    double* h_prefix;           /* prefix_cap samples of demod_sync for a window the capture-wide chase does not decide */
+    long long prefix_cap;       /* >= 40 * linelen */
+} ldd_pipe_bufs;
+
+typedef struct ldd_pipe_result {
+    int nwindows;               /* windows the walk read (every readfield iteration of the reference) */
+    int nowned;                 /* of those, read position in [r0, r1) */
+    int nlocated;               /* owned windows that are fields (LDD_FIELD_LOCATED): refined and resampled, in order */
+    int npeaks;                 /* peaks of the range-wide chase */
+    int nframes;                /* frame mode: complete frames written */
+    int prefix_windows;         /* windows that needed their own chase over a prefix (copied to the host) */
+    int ll_stride;
+    long long plane_origin, plane_len, walk_start;
+    long long audio1_len, audio2_len;
+    double lineloc_add;         /* FieldNTSC.apply_offsets term of the final line positions (0 for PAL) */
+    /* host arrays owned by the pipe, valid until its next finish; indexed by window */
+    const ldd_field* fields;
+    const long long* base;
+    const long long* winlen;
+    const long long* readsample;
+    const double* linelocs1;    /* [nwindows][ll_stride] */
+    const unsigned char* linebad;
+    const int* owned;           /* [nowned] window index */
+    const int* located;         /* [nlocated] index into owned[] */
+    const int* frame_of;        /* [nlocated] frame mode: frame index of the field, -1 = before the first frame */
+    const long long* gpeaks;    /* the range-wide peak list (page-locked buffers of ldd_pipe_bufs) */
+    const double* gvals;
+    /* device tables inside ldd_pipe_bufs.field_tables, row k <-> located[k] */
+    void* d_base; void* d_winlen; void* d_linecount; void* d_linelocs1;
+    void* d_linelocs2; void* d_linebad2; void* d_linelocs3; void* d_linelocs4; void* d_burstlevel;
+    void* d_final;              /* the line table the TBC used (before lineloc_add): linelocs4 NTSC, pilot-refined PAL */
+    void* d_vbi;                /* int [nlocated][4]: ldd_vbi_decode codes of the three code lines */
+} ldd_pipe_result;
+
+int ldd_pipe_table_bytes(int max_fields, long long* upload_bytes, long long* device_bytes);
+/* field_samples: int(freq_hz / FPS / 2), the nominal field length (range planning). */
+int ldd_pipe_create(ldd_handle* h, const ldd_pipe_bufs* bufs, int max_fields, long long field_samples, ldd_pipe** out);
+void ldd_pipe_destroy(ldd_pipe* p);
+/* Stage 1, asynchronous on `stream`.  rf_dev holds capture samples [rf_base, rf_base + rf_len) in format fmt; ncap_total is the
+ * length of the whole capture (the reference stops when a read would pass its end); the range owns the fields whose read
+ * position is in [r0, r1).  readlen = Framer.readlen.  mtf_level is applied when LDD_F_MTF is set. */
+int ldd_pipe_launch(ldd_pipe* p, const void* rf_dev, int fmt, long long rf_base, long long rf_len, long long ncap_total,
+                    long long r0, long long r1, long long readlen, double mtf_level, int audio_phase2, void* stream);
+/* Stage 2: blocks until the peak list of stage 1 is in host memory (not until the stream is idle), walks, and enqueues
+ * refinement + VBI + TBC on refine_stream; main_stream (the stream of stage 1) is ordered behind them.  pic_dev receives
+ * the uint16 fields: frame_mode 0 -> field k at k * pic_stride; frame_mode 1 -> interleaved frames of pic_stride
+ * elements each (fields paired by parity as Framer.readframe does for CLV; fields before the first frame land in slot
+ * pic_cap - 1).  pic_cap = fields / frames pic_dev can hold; status_dev [max_fields] gets the per-field error bits. */
+int ldd_pipe_finish(ldd_pipe* p, double colorlevel, double colorphase, int frame_mode, void* pic_dev, long long pic_stride,
+                    long long pic_cap, int* status_dev, void* refine_stream, void* main_stream, ldd_pipe_result* out);
 
 #ifdef __cplusplus
 }

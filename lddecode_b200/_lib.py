@@ -10,10 +10,10 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_PATH = os.path.join(HERE, "libldd_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 SYSTEM = {"NTSC": 0, "PAL": 1}
 FMT_U8, FMT_S16, FMT_U16, FMT_R30, FMT_LDS40 = range(5)
-F_RFVIDEO, F_VIDEO, F_VIDEO05, F_BURST, F_PILOT, F_AUDIO_L, F_AUDIO_R, F_AUDIO_LPF2 = range(8)
+F_RFVIDEO, F_VIDEO, F_VIDEO05, F_BURST, F_PILOT, F_AUDIO_L, F_AUDIO_R, F_AUDIO_LPF2, F_MTF = range(9)
 P_DEMOD, P_DEMOD05, P_SYNC, P_BURST, P_PILOT = range(5)
 PREC_F64, PREC_F32, PREC_MIXED = 0, 1, 2
 OK, EINVAL, ESHORT, ECUDA, ENOMEM, ECAP = 0, -1, -2, -3, -4, -5
@@ -94,6 +94,50 @@ class FieldInfo(C.Structure):
                 ("vsyncs", (C.c_int * 3) * 4), ("nextfieldoffset", C.c_longlong), ("tbcstart", C.c_longlong),
                 ("med_hsync", C.c_double), ("hsync_tolerance", C.c_double)]
 
+
+class PipeBufs(C.Structure):
+    _fields_ = [("planes", C.c_void_p * 5), ("plane_cap", C.c_longlong),
+                ("audio1_l", C.c_void_p), ("audio1_r", C.c_void_p), ("audio1_cap", C.c_longlong),
+                ("audio2_l", C.c_void_p), ("audio2_r", C.c_void_p),
+                ("peaks", C.c_void_p), ("peak_vals", C.c_void_p), ("peak_count", C.c_void_p), ("peak_cap", C.c_int),
+                ("field_tables", C.c_void_p), ("tables_bytes", C.c_longlong),
+                ("h_peaks", C.c_void_p), ("h_peak_vals", C.c_void_p), ("h_peak_count", C.c_void_p),
+                ("h_tables", C.c_void_p), ("h_tables_bytes", C.c_longlong),
+                ("h_prefix", C.c_void_p), ("prefix_cap", C.c_longlong)]
+
+
+class PipeResult(C.Structure):
+    _fields_ = [("nwindows", C.c_int), ("nowned", C.c_int), ("nlocated", C.c_int), ("npeaks", C.c_int), ("nframes", C.c_int),
+                ("prefix_windows", C.c_int), ("ll_stride", C.c_int),
+                ("plane_origin", C.c_longlong), ("plane_len", C.c_longlong), ("walk_start", C.c_longlong),
+                ("audio1_len", C.c_longlong), ("audio2_len", C.c_longlong), ("lineloc_add", C.c_double),
+                ("fields", C.POINTER(FieldInfo)), ("base", C.POINTER(C.c_longlong)), ("winlen", C.POINTER(C.c_longlong)),
+                ("readsample", C.POINTER(C.c_longlong)), ("linelocs1", C.POINTER(C.c_double)), ("linebad", C.POINTER(C.c_ubyte)),
+                ("owned", C.POINTER(C.c_int)), ("located", C.POINTER(C.c_int)), ("frame_of", C.POINTER(C.c_int)),
+                ("gpeaks", C.POINTER(C.c_longlong)), ("gvals", C.POINTER(C.c_double)),
+                ("d_base", C.c_void_p), ("d_winlen", C.c_void_p), ("d_linecount", C.c_void_p), ("d_linelocs1", C.c_void_p),
+                ("d_linelocs2", C.c_void_p), ("d_linebad2", C.c_void_p), ("d_linelocs3", C.c_void_p), ("d_linelocs4", C.c_void_p),
+                ("d_burstlevel", C.c_void_p), ("d_final", C.c_void_p), ("d_vbi", C.c_void_p)]
+
+
+SIGNATURES.update({
+    "ldd_set_mtf_level": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
+    "ldd_downscale_audio": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                      C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldd_tbc_fields_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                    C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p,
+                                    C.c_longlong, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
+    "ldd_vbi_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_void_p]),
+    "ldd_pipe_table_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "ldd_pipe_create": (C.c_int, [C.c_void_p, C.POINTER(PipeBufs), C.c_int, C.c_longlong, C.POINTER(C.c_void_p)]),
+    "ldd_pipe_destroy": (None, [C.c_void_p]),
+    "ldd_pipe_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong,
+                                  C.c_longlong, C.c_longlong, C.c_double, C.c_int, C.c_void_p]),
+    "ldd_pipe_finish": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.POINTER(PipeResult)]),
+})
 
 WINDOW_PEAKS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.POINTER(C.c_void_p),
                               C.POINTER(C.c_void_p), C.POINTER(C.c_int))

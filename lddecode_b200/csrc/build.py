@@ -7,7 +7,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ["ldd_api.cu", "ldd_demod.cu", "ldd_unpack.cu", "ldd_audio.cu", "ldd_sync.cu", "ldd_tbc.cu", "ldd_field.cu"]
+SOURCES = ["ldd_api.cu", "ldd_demod.cu", "ldd_unpack.cu", "ldd_audio.cu", "ldd_sync.cu", "ldd_tbc.cu", "ldd_field.cu", "ldd_vbi.cu",
+           "ldd_pipe.cu"]
 OUT = os.path.join(PKG, "libldd_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

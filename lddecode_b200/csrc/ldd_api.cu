@@ -55,6 +55,26 @@ std::vector<Cx<double>> roots(int n, int count) {
     return t;
 }
 
+// Hv = RFVideo * MTF ** level (lddecode_core.py:290-293) on the device, float64 and float32 copies: a level change
+// (the reference adapts it per CAV frame, :1300-1306) is one tiny stream-ordered kernel instead of a host-side
+// complex power over N entries and a blocking upload.  level 0 / 1 are exact like numpy's integer-power path;
+// other levels are exp(level * log z) as libm's cpow.
+__global__ void hv_kernel(const Cx<double>* __restrict__ rf, const Cx<double>* __restrict__ mtf, double level,
+                          Cx<double>* hv64, Cx<float>* hv32, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    Cx<double> m = mk<double>(1.0, 0.0);
+    if (level == 1.0) m = mtf[k];
+    else if (level != 0.0) {
+        const Cx<double> z = mtf[k];
+        const double mag = exp(level * log(hypot(z.x, z.y))), ang = level * atan2(z.y, z.x);
+        m = mk<double>(mag * cos(ang), mag * sin(ang));
+    }
+    const Cx<double> v = rf[k] * m;
+    hv64[k] = v;
+    hv32[k] = mk<float>((float)v.x, (float)v.y);
+}
+
 }  // namespace
 
 extern "C" {
@@ -186,6 +206,8 @@ void ldd_destroy(ldd_handle* h) {
     cudaFree(h->scratch);
     cudaFree(h->d_lpf2);
     cudaFree(h->d_WNfull);
+    cudaFree(h->d_rfbase);
+    cudaFree(h->d_mtf);
     cudaFree(h->scratch64);
     cudaFree(h->d_flags);
     cudaFree(h->peak_ws);
@@ -204,6 +226,17 @@ int ldd_set_filter(ldd_handle* h, int id, const double* table, int n) {
             t.assign(src, src + N);
             int rc = upload_both(h, t, h->d_Hv);
             if (rc) return rc;
+            // kept as the base of ldd_set_mtf_level
+            h->mtf_level_set = 0.0;
+            if (!h->d_rfbase) CUDA_TRY(h, cudaMalloc(&h->d_rfbase, (size_t)N * sizeof(Cx<double>)));
+            CUDA_TRY(h, cudaMemcpy(h->d_rfbase, table, (size_t)N * sizeof(Cx<double>), cudaMemcpyHostToDevice));
+            break;
+        }
+        case LDD_F_MTF: {
+            if (n != N) return fail(h, LDD_EINVAL, "MTF table needs %d entries", N);
+            h->mtf_level_set = -1e300;       // forces the next ldd_set_mtf_level to run
+            if (!h->d_mtf) CUDA_TRY(h, cudaMalloc(&h->d_mtf, (size_t)N * sizeof(Cx<double>)));
+            CUDA_TRY(h, cudaMemcpy(h->d_mtf, table, (size_t)N * sizeof(Cx<double>), cudaMemcpyHostToDevice));
             break;
         }
         case LDD_F_VIDEO: case LDD_F_VIDEO05: case LDD_F_BURST: case LDD_F_PILOT: {
@@ -245,6 +278,18 @@ int ldd_set_filter(ldd_handle* h, int id, const double* table, int n) {
     }
     h->have_filter[id] = true;
     return LDD_OK;
+}
+
+int ldd_set_mtf_level(ldd_handle* h, double level, void* stream) {
+    if (!h) return LDD_EINVAL;
+    if (!h->have_filter[LDD_F_RFVIDEO] || !h->have_filter[LDD_F_MTF] || !h->d_rfbase || !h->d_mtf)
+        return fail(h, LDD_EINVAL, "ldd_set_mtf_level needs the RFVideo (level 0) and MTF tables");
+    if (h->mtf_level_set == level) return LDD_OK;          // a handle serves one stream user: nothing to order against
+    const int N = h->cfg.blocklen;
+    h->mtf_level_set = level;
+    LDD_LAUNCH(hv_kernel, dim3((N + 255) / 256), dim3(256), 0, (cudaStream_t)stream, (const Cx<double>*)h->d_rfbase,
+               (const Cx<double>*)h->d_mtf, level, (Cx<double>*)h->d_Hv[0], (Cx<float>*)h->d_Hv[1], N);
+    return launch_status(h, "hv_kernel");
 }
 
 int ldd_demod_range_query(ldd_handle* h, long long start, long long length, ldd_range* out) {

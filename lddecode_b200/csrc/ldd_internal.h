@@ -107,6 +107,9 @@ struct ldd_handle {
     // audio phase 2
     void* d_lpf2;     // Cx<double>[N/4]
     void* d_WNfull;   // e^{-2 pi i k/N}, k<N (double) for the phase-2 transforms
+    void* d_rfbase = nullptr;   // Filters['RFVideo'] as uploaded (complex128), base of ldd_set_mtf_level
+    void* d_mtf = nullptr;      // Filters['MTF'] (complex128)
+    double mtf_level_set = 0.0; // level d_Hv currently holds
     // workspace of the peak search (grown on demand)
     void* peak_ws = nullptr;
     size_t peak_ws_bytes = 0;

@@ -46,6 +46,8 @@ struct TbcParams {
     double ire0, hz_ire, vsync_ire, out_scale, out_off;
     void* out;                // [nfields][out_stride]
     long long out_stride;
+    const long long* field_off; // [nfields] element offset of each field's line 0 in out (NULL: field * out_stride)
+    long long line_stride;    // elements between consecutive lines of a field (outwidth, or 2 * outwidth for a frame)
     const float* burstlevel;  // NTSC final: [nfields][ll_stride] or NULL
     float clevel_k;           // float32(327.67 * clevel)
     int* status;              // [nfields]: OR of per-line error bits (1: window outside the plane / too long)
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(TBC_THREADS, 4) tbc_kernel(const TbcParams p) 
         const double Mi6 = Mi * sixth, Mj6 = Mj * sixth;
         double S = u * fma(Mi6, fma(u, u, -1.0), ys[PX(i + TBC_H)]) + t * fma(Mj6, fma(t, t, -1.0), ys[PX(i + 1 + TBC_H)]);
         double hz = (S + p.plane_add) * wowf;
-        size_t o = (size_t)field * (size_t)p.out_stride + (size_t)line * W + j;
+        size_t o = (p.field_off ? (size_t)p.field_off[field] : (size_t)field * (size_t)p.out_stride) + (size_t)line * (size_t)p.line_stride + j;
         if (p.mode == 0) {
             ((double*)outbase)[o] = hz;
         } else {
@@ -243,11 +245,11 @@ __global__ void __launch_bounds__(TBC_THREADS, 4) tbc_kernel(const TbcParams p) 
 
 using namespace ldd;
 
-extern "C" int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n, double plane_add,
-                              const long long* base_dev, const double* linelocs_dev, int ll_stride, const int* linecount_dev, int nfields,
-                              int max_linecount, int lineoffset, double lineloc_add, int outwidth, int wow, int mode,
-                              void* out_dev, long long out_stride, const float* burstlevel_dev, double colorlevel,
-                              int* status_dev, void* stream) {
+extern "C" int ldd_tbc_fields_ex(ldd_handle* h, const float* plane_dev, long long n, double plane_add,
+                                 const long long* base_dev, const double* linelocs_dev, int ll_stride, const int* linecount_dev, int nfields,
+                                 int max_linecount, int lineoffset, double lineloc_add, int outwidth, int wow, int mode,
+                                 void* out_dev, long long out_stride, const long long* out_off_dev, long long line_stride,
+                                 const float* burstlevel_dev, double colorlevel, int* status_dev, void* stream) {
     if (!h || !plane_dev || !linelocs_dev || !linecount_dev || !out_dev || !status_dev) return LDD_EINVAL;
     if (nfields <= 0 || max_linecount <= 0) return LDD_OK;
     if (outwidth < 1 || (mode != 0 && mode != 1)) return LDD_EINVAL;
@@ -267,6 +269,7 @@ extern "C" int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n
         p.out_off = 256.0;
     }
     p.out = out_dev; p.out_stride = out_stride;
+    p.field_off = out_off_dev; p.line_stride = line_stride > 0 ? line_stride : outwidth;
     p.burstlevel = burstlevel_dev;
     // np.uint16(327.67 * clevel * np.abs(float32 burstlevel)): python-float product, then float32 arithmetic
     double clevel = (1.0 / colorlevel) / (1700000.0 / 140.0);
@@ -290,4 +293,14 @@ extern "C" int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n
     cudaStream_t st = (cudaStream_t)stream;
     LDD_LAUNCH(tbc_kernel, dim3(max_linecount, nfields), dim3(TBC_THREADS), smem, st, p);
     return launch_status(h, "tbc_kernel");
+}
+
+extern "C" int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n, double plane_add,
+                              const long long* base_dev, const double* linelocs_dev, int ll_stride, const int* linecount_dev, int nfields,
+                              int max_linecount, int lineoffset, double lineloc_add, int outwidth, int wow, int mode,
+                              void* out_dev, long long out_stride, const float* burstlevel_dev, double colorlevel,
+                              int* status_dev, void* stream) {
+    return ldd_tbc_fields_ex(h, plane_dev, n, plane_add, base_dev, linelocs_dev, ll_stride, linecount_dev, nfields, max_linecount,
+                             lineoffset, lineloc_add, outwidth, wow, mode, out_dev, out_stride, nullptr, 0, burstlevel_dev, colorlevel,
+                             status_dev, stream);
 }

@@ -218,42 +218,25 @@ def refine_and_tbc(rf, planes, plane_len, batch, colorlevel=1.45, colorphase=91.
     return out
 
 
-# ---- VBI (lddecode_core.py:814-884): scalar host code on three fetched lines per field -----------
-def _calczc(data, start, target, count=10):
-    s = int(start)
-    n = int(count + 1)
-    if s < 0 or s >= len(data):
+# ---- VBI (lddecode_core.py:814-884): the cell walk runs on the device (ldd_vbi_decode), the code interpretation here
+def code_nibbles(code):
+    """24-bit Philips code -> the reference's `linecode` list of six nibbles (None for -1)."""
+    code = int(code)
+    if code < 0:
         return None
-    rising = data[s] < target
-    win = data[s:s + n]
-    hits = np.where(win >= target)[0] if rising else np.where(win <= target)[0]
-    if len(hits) == 0:
-        return None
-    x = s + hits[0]
-    if x == 0:
-        return None
-    a = data[x - 1] - target
-    b = data[x] - target
-    return x - 1 + (-a / (-a + b))
+    return [(code >> s) & 15 for s in (20, 16, 12, 8, 4, 0)]
 
 
-def decode_philips_line(rf, seg, seg_start, linestart):
-    """decodephillipscode on `seg`, a host copy of demod[seg_start : ...] (absolute Hz)."""
-    fq = rf.freq
-    thr = rf.iretohz(50)
-    rel = linestart - seg_start
-    cur = _calczc(seg, int(rel + 2 * fq), thr, count=int(12 * fq))
-    zcs = []
-    while cur is not None:
-        zcs.append((cur, seg[int(cur - 0.5 * fq)] < thr))
-        cur = _calczc(seg, cur + 1.9 * fq, thr, count=int(0.2 * fq))
-    if len(zcs) != 24:
-        return None
-    gaps = np.diff([z[0] for z in zcs]) / fq
-    if not (np.min(gaps) > 1.85 and np.max(gaps) < 2.15):
-        return None
-    bits = [int(z[1]) for z in zcs]
-    return [bits[b] * 8 + bits[b + 1] * 4 + bits[b + 2] * 2 + bits[b + 3] for b in range(0, 24, 4)]
+def vbi_decode_device(rf, demod_buf, n, d_linelocs, nfields, d_base=None, d_winlen=None):
+    """ldd_vbi_decode for `nfields` line tables [nfields][LL_STRIDE] -> device int32 [nfields][4] (enqueued)."""
+    be = rf._be
+    lines = rf.SysParams['philips_codelines']
+    arr = (C.c_int * len(lines))(*lines)
+    d_codes = be.empty(4 * nfields, np.int32)
+    rf._check(be.lib.ldd_vbi_decode(rf._h, be.ptr(demod_buf), int(n), be.ptr(d_base) if d_base is not None else None,
+                                    be.ptr(d_winlen) if d_winlen is not None else None, be.ptr(d_linelocs), LL_STRIDE,
+                                    int(nfields), arr, len(lines), be.ptr(d_codes), be.stream()))
+    return d_codes
 
 
 def process_philips(rf, linecode):
@@ -283,6 +266,43 @@ def process_philips(rf, linecode):
     return vbi
 
 
+def downscale_audio(audio, lineinfo, rf, linecount, timeoffset=0, freq=48000.0, scale=64):
+    """lddecode_core.downscale_audio (lddecode_core.py:431-484) on the device (ldd_downscale_audio).
+
+    audio: the phase-2 audio of the field's window -- a dict of device buffers (DeviceDemod.audio) or the host record
+    array RFDecode.demod returns.  Returns (int16 interleaved L/R samples, time offset to carry into the next field).
+    Like the reference it assumes a total decimation of `scale` (64: the 40 MSPS default)."""
+    be = rf._be
+    frametime = (rf.SysParams['line_period'] * linecount) / 1000000
+    soundgap = 1 / freq
+    arange = np.arange(timeoffset, frametime + soundgap, soundgap, dtype=np.double)
+    n = len(arange) - 1
+    if n < 1:
+        return np.zeros(0, dtype=np.int16), (arange[-1] - frametime if len(arange) else timeoffset)
+    if isinstance(audio, dict):
+        al, ar = audio['audio_left'], audio['audio_right']
+    else:
+        al = be.to_device(np.ascontiguousarray(audio['audio_left'], dtype=np.float64))
+        ar = be.to_device(np.ascontiguousarray(audio['audio_right'], dtype=np.float64))
+    ll = np.zeros(LL_STRIDE, dtype=np.float64)
+    nll = min(len(lineinfo), LL_STRIDE)
+    ll[:nll] = np.asarray(lineinfo, dtype=np.float64)[:nll]
+    out = be.empty(2 * n, np.int16)
+    st = be.zeros(1, np.int32)
+    SP = rf.SysParams
+    # the small per-field arguments (kept referenced until the call has been enqueued)
+    d = [be.to_device(x) for x in (ll, np.array([nll], dtype=np.int32), arange[0:1].copy(), arange[1:2].copy(),
+                                   np.array([n], dtype=np.int32), np.zeros(1, dtype=np.int64))]
+    rf._check(be.lib.ldd_downscale_audio(
+        rf._h, be.ptr(al), be.ptr(ar), len(al), None, be.ptr(d[0]), LL_STRIDE, be.ptr(d[1]), be.ptr(d[2]), be.ptr(d[3]),
+        be.ptr(d[4]), be.ptr(d[5]), 1, n, 0.0, float(scale), float(SP['line_period']), float(SP['audio_lfreq']),
+        float(SP['audio_rfreq']), be.ptr(out), be.ptr(st), be.stream()))
+    be.synchronize()
+    if be.to_host(st)[0] & 16:
+        raise IndexError("downscale_audio: index outside the line table / audio array")
+    return be.to_host(out), arange[-1] - frametime
+
+
 # ---- drop-in classes -----------------------------------------------------------------------------
 class Field:
     """Field(rf, rawdecode, start, audio_offset=0): rawdecode is what RFDecode.demod_device returned
@@ -306,6 +326,8 @@ class Field:
         self.colorlevel, self.colorphase = colorlevel, colorphase
         self.burstlevel = None
         self._planes, self._n = self._device_planes(rawdecode)
+        # phase-2 audio of the window: device buffers (DeviceDemod) or the host record array of RFDecode.demod
+        self._audio = rawdecode.audio if isinstance(rawdecode, DeviceDemod) else rawdecode[1]
         be = rf._be
 
         self.peaklist, self._peakvals = self.get_syncpeaks(with_values=True)
@@ -387,18 +409,14 @@ class Field:
         return v
 
     def _decode_vbi(self):
-        rf = self.rf
+        rf, be = self.rf, self.rf._be
         self.isclv = False
-        self.linecode = {}
         self.framenr = None
-        for l in rf.SysParams['philips_codelines']:
-            ls = self.linelocs[l]
-            a = int(ls) - 64
-            seg = self._plane_slice_host('demod', a, a + rf.linelen + 128)
-            try:
-                self.linecode[l] = decode_philips_line(rf, seg, max(a, 0), ls)
-            except IndexError:
-                self.linecode[l] = None
+        ll = np.zeros(LL_STRIDE, dtype=np.float64)
+        ll[:len(self.linelocs)] = self.linelocs
+        d_ll = be.to_device(ll)
+        codes = be.to_host(vbi_decode_device(rf, self._planes['demod'], self._n, d_ll, 1))
+        self.linecode = {l: code_nibbles(codes[i]) for i, l in enumerate(rf.SysParams['philips_codelines'])}
         self.vbi = process_philips(rf, self.linecode)
 
     # -- reference API
@@ -432,7 +450,15 @@ class Field:
         be.synchronize()
         if be.to_host(d_st)[0] & 1:
             raise ValueError("line window outside the decoded data")
+        if audio:
+            self._downscale_audio(lineinfo)
         return be.to_host(out), self.dsaudio
+
+    def _downscale_audio(self, lineinfo):
+        """The audio half of Field.downscale (lddecode_core.py:809-810)."""
+        if self.rf.decode_analog_audio and self._audio is not None:
+            self.dsaudio, self.audio_next_offset = downscale_audio(self._audio, lineinfo, self.rf, self.linecount,
+                                                                   self.audio_next_offset)
 
     def _finish(self, ref, nll):
         pass
@@ -453,6 +479,17 @@ class FieldNTSC(Field):
         self.linelocs = self.linelocs4 + ref.lineloc_add
         W = self.outlinelen
         self.dspicture = be.to_host(ref.d_pic)[:self.linecount * W].copy()
+        try:
+            self._downscale_audio(self.linelocs)          # downscale(final=True) -> audio=True (lddecode_core.py:1136, 1188)
+        except IndexError:
+            print("ERROR: Unable to decode frame, skipping")
+            self.valid = False
+
+    def downscale(self, lineoffset=1, final=False, *args, **kwargs):
+        """FieldNTSC.downscale (lddecode_core.py:1135-1159); final=True returns the uint16 picture of the constructor."""
+        if final:
+            return self.dspicture, self.dsaudio
+        return super().downscale(lineoffset=lineoffset, *args, **kwargs)
 
     def apply_offsets(self, linelocs, phaseoffset, picoffset=0):
         return np.array(linelocs) + picoffset + (phaseoffset * (self.rf.freq / (4 * 315 / 88)))
@@ -460,6 +497,13 @@ class FieldNTSC(Field):
 
 class FieldPAL(Field):
     full = True
+
+    def downscale(self, final=False, *args, **kwargs):
+        """FieldPAL.downscale (lddecode_core.py:1023-1035): lineoffset 3; final=True returns the constructor's picture."""
+        if final:
+            return self.dspicture, self.dsaudio
+        kwargs.setdefault('lineoffset', 3)
+        return super().downscale(*args, **kwargs)
 
     def _finish(self, ref, nll):
         be = self.rf._be
@@ -470,3 +514,8 @@ class FieldPAL(Field):
         self.linelocs = ref.final[0][:nll].copy()
         W = self.outlinelen
         self.dspicture = be.to_host(ref.d_pic)[:self.linecount * W].copy()
+        try:
+            self._downscale_audio(self.linelocs)          # downscale(final=True) -> audio=True (lddecode_core.py:1024, 1045)
+        except IndexError:
+            print("ERROR: Unable to decode frame, skipping")
+            self.valid = False

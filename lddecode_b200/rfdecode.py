@@ -279,14 +279,13 @@ class RFDecode:
         self._mtf_uploaded = None
 
     def _set_mtf(self, mtf_level):
-        """RFVideo * MTF**mtf_level (lddecode_core.py:290-293); re-uploaded only when the level changes."""
-        if self._mtf_uploaded == mtf_level:
-            return
-        t = self.Filters['RFVideo']
-        if mtf_level != 0:
-            t = t * self.Filters['MTF'] ** mtf_level
-        self._set_filter(_lib.F_RFVIDEO, t)
-        self._mtf_uploaded = mtf_level
+        """RFVideo * MTF**mtf_level (lddecode_core.py:290-293).  The two tables are uploaded once; a level change is
+        one small kernel on the current stream (ldd_set_mtf_level), stream-ordered with the demodulations around it."""
+        if self._mtf_uploaded is None:
+            self._set_filter(_lib.F_RFVIDEO, self.Filters['RFVideo'])
+            self._set_filter(_lib.F_MTF, self.Filters['MTF'])
+            self._mtf_uploaded = True
+        self._check(self._be.lib.ldd_set_mtf_level(self._h, float(mtf_level), self._be.stream()))     # no-op when unchanged
 
     def __del__(self):
         try:

@@ -30,7 +30,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FS = {"NTSC": 8 * 315 / 88, "PAL": 35.46895}
-RANGES = [1]
 BLOCKLEN = 16384                     # the reference's default blocklen_ (lddecode_core.py:120)
 TAIL = 1100000                       # so the last 1e6-sample read succeeds
 
@@ -39,17 +38,17 @@ def one_second(system):
     return int(round(FS[system] * 1e6))
 
 
-def synth_capture(system, n, seed):
+def synth_capture(system, n, seed, bits=8):
     """Seeded synthetic capture, cached under .bench_cache/ (generation is ~1.2 s per Msample)."""
     from lddecode_b200 import synth
     cdir = os.path.join(ROOT, ".bench_cache")
-    path = os.path.join(cdir, "%s_%d_%d.npy" % (system, n, seed))
+    path = os.path.join(cdir, "%s_%d_%d%s.npy" % (system, n, seed, "" if bits == 8 else "_%dbit" % bits))
     if os.path.exists(path):
         try:
             return np.load(path)
         except Exception:
             pass
-    cap = synth.SynthRF(system, FS[system], seed=seed).generate(n)
+    cap = synth.SynthRF(system, FS[system], seed=seed, bits=bits).generate(n)
     try:
         os.makedirs(cdir, exist_ok=True)
         tmp = path + ".%d.tmp.npy" % os.getpid()
@@ -132,18 +131,18 @@ def run_reference(a):
     sample = "%d processes x %d %s fields per step (identical captures; demod 1e6 + Field decode per field)" % (cores, nfields, system)
     line = dict(impl="reference", metric="rf_msamples_per_s_demod_tbc", value=value, unit="Msamples/s", n_gpus=a.gpus,
                 steps=a.steps, warmup=a.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f64", data="synthetic", config=workload_config(system, audio, a.gpus),
+                dtype="f64", data="synthetic", config=workload_config(system, audio, a.gpus, a.fmt),
                 cpu_baseline=dict(value=value, unit="Msamples/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit="Msamples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 realtime_x=value / FS[system])
     print(json.dumps(line), flush=True)
 
 
-def workload_config(system, audio, gpus):
-    return dict(workload="%s synthetic 8-bit RF, 1 s at 8fsc (%.3f MSPS) per GPU, %s demod + sync + TBC to uint16 4fsc"
-                         % (system, FS[system], "video+audio" if audio else "video"),
-                blocklen=BLOCKLEN, readlen=1000000, ranges_per_step=RANGES[0], parallelism="block-range shards, one 1-s shard per GPU (x%d)" % gpus,
-                l2="per step 36 MB in + ~0.9 GB of planes written: working set exceeds the 126 MB L2, no flush needed")
+def workload_config(system, audio, gpus, fmt="u8"):
+    return dict(workload="%s synthetic %s RF, 1 s at 8fsc (%.3f MSPS) per GPU, %s demod + sync + TBC to uint16 4fsc"
+                         % (system, FMT_NAMES[fmt], FS[system], "video + both analog audio channels" if audio else "video"),
+                blocklen=BLOCKLEN, readlen=1000000, parallelism="block-range shards, one 1-s shard per GPU (x%d)" % gpus,
+                l2="per step ~30-46 MB in + ~0.7-0.9 GB of planes written: working set exceeds the 126 MB L2, no flush needed")
 
 
 # ---- clocks -----------------------------------------------------------------------------------------
@@ -251,29 +250,102 @@ class ClockSampler:
 
 
 # ---- our arm ----------------------------------------------------------------------------------------
-def run_ours(a):
-    import torch
-    import torch.distributed as dist
-    from lddecode_b200 import _lib, parallel, pipeline, rfdecode
+FMT_NAMES = {"u8": "8-bit", "r30": "ddpack 10-bit packed (.r30, 3 samples / 4 bytes)", "lds": "10-bit packed (.lds, 4 samples / 5 bytes)",
+             "u16": "10-bit unpacked uint16"}
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != a.gpus:
-        if world == 1 and a.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (a.gpus, a.gpus))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    system, audio = a.system, a.audio
+
+def make_capture(system, fmt, ncap, seed):
+    """(sample array for checks, bytes as the capture file holds them, library format id, samples)."""
+    from lddecode_b200 import _lib, synth
+    if fmt == "u8":
+        cap = synth_capture(system, ncap, seed)
+        return cap, cap, _lib.FMT_U8, ncap
+    ncap = ncap // 12 * 12                                        # whole .r30 words and .lds groups
+    s10 = synth_capture(system, ncap, seed, bits=10)
+    if fmt == "u16":
+        return s10, s10, _lib.FMT_U16, ncap
+    if fmt == "r30":
+        return s10, synth.pack_r30(s10).view(np.uint8), _lib.FMT_R30, ncap
+    return s10, synth.pack_lds(s10), _lib.FMT_LDS40, ncap
+
+
+def golden_field(system, fmt, seed):
+    """The reference's own first field of this capture (tests/golden/make_bench_golden.py), or None."""
+    key = {("PAL", "u8", 1): "PAL_u8_seed1", ("NTSC", "u8", 0): "NTSC_u8_seed0"}.get((system, fmt, seed))
+    if key is None and system == "NTSC" and fmt in ("r30", "lds", "u16") and seed == 0:
+        key = "NTSC_10bit_seed0"
+    if key is None:
+        return None
+    try:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "bench_fields.npz"))
+        return g[key + "_pic"], int(g[key + "_next"]), int(g[key + "_istop"])
+    except Exception:
+        return None
+
+
+def check_result(cd, res, system, fmt, seed, what):
+    """Outside the timed region: every located field of the step must be clean (no error bits from any kernel), the
+    field cadence must be the system's, and the first field must be the reference's own decode of these bytes (+-1 LSB)."""
+    be = cd.rf._be
+    be.synchronize()
+    nloc = len(res.located)
+    if nloc == 0:
+        raise SystemExit("bench self-check failed (%s): no field located" % what)
+    st = be.to_host(res.d_status)[:nloc]
+    if np.any(st & 15):
+        raise SystemExit("bench self-check failed (%s): field status bits %s" % (what, sorted(set(int(x) for x in st if x & 15))))
+    infos = res.infos[np.asarray(res.located)]
+    tops = infos['istop']
+    if np.any(tops[1:] == tops[:-1]):
+        raise SystemExit("bench self-check failed (%s): field parity does not alternate" % what)
+    out = dict(fields=int(nloc), status_clean=True, golden="none")
+    g = golden_field(system, fmt, seed)
+    if g is not None:
+        gpic, gnext, gtop = g
+        j = res.located[0]
+        W = cd.rf.SysParams['outlinelen']
+        n = int(res.infos[j].linecount) * W
+        pic = be.to_host(res.d_pic[:res.out_stride])[:n].astype(np.int64)
+        if int(res.readsamples[j]) != 0 or int(res.infos[j].nextfieldoffset) != gnext or int(res.infos[j].istop) != gtop or n != len(gpic):
+            raise SystemExit("bench self-check failed (%s): first field geometry differs from the reference's" % what)
+        d = np.abs(pic - gpic.astype(np.int64))
+        if d.max() > 1:
+            raise SystemExit("bench self-check failed (%s): first field differs from the reference by %d LSB" % (what, int(d.max())))
+        out["golden"] = "first field == reference's FieldPAL/FieldNTSC output within +-1 LSB (%.2f %% of samples differ by 1)" % (100.0 * float(np.mean(d > 0)))
+    return out
+
+
+def pin_rank_to_gpu_numa(local):
+    """Run this rank on the CPUs next to its GPU (NVML's ideal CPU set intersected with what the cgroup allows)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        ideal = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = ideal & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+        return sorted(use)[:2] + ["..."] + sorted(use)[-1:] if use else None
+    except Exception:
+        return None
+
+
+def measure(a, system, audio, fmt, rank, world, local, dist, clocks_rank0=None, roofline=True):
+    """One workload through the resident and the end-to-end path.  Returns the result dict on rank 0."""
+    import torch
+    from lddecode_b200 import parallel, pipeline, rfdecode
+
     ncap = one_second(system) + TAIL
-    cap = synth_capture(system, ncap, 1 + rank if system == "PAL" else rank)
+    seed = (1 + rank) if system == "PAL" else rank
+    chk, raw, fmt_id, ncap = make_capture(system, fmt, ncap, seed)
     rf = rfdecode.RFDecode(FS[system], system, BLOCKLEN, decode_analog_audio=audio, device=local, precision=a.precision)
     cd = pipeline.CaptureDecoder(rf, max_fields=256)
     be = rf._be
-    cap_dev = torch.from_numpy(cap).cuda()
-    cap_pin = torch.from_numpy(cap).pin_memory()
-    stream = torch.cuda.current_stream()
+    cap_dev = torch.from_numpy(raw).cuda()
+    cap_pin = torch.from_numpy(raw).pin_memory()
+    nraw = len(raw)
     max_fields = 64
 
     def barrier():
@@ -284,58 +356,41 @@ def run_ours(a):
     gatherer = parallel.FieldGatherer(cd, rank, world, max_fields, dist) if world > 1 else None
 
     def run_resident(nsteps):
-        # K decodes of the HBM-resident capture through CaptureDecoder.decode_stream: the demodulation of
-        # step k+1 is enqueued before the host walks the fields of step k (same results as decode())
+        # K decodes of the HBM-resident capture through CaptureDecoder.decode_stream: the demodulation of step k+1 is
+        # enqueued before the host walks the fields of step k (same results as decode()); with several ranks every
+        # step's fields are written into the gather's send buffer and collected on rank 0 over NCCL
         res = None
-        if a.ranges > 1:
-            for _ in range(nsteps):
-                res = cd.decode_pipelined(cap_dev, _lib.FMT_U8, ncap, a.ranges)
-                if world > 1:
-                    gatherer.gather(res)
-            return res
-        for res in cd.decode_stream((cap_dev, _lib.FMT_U8, ncap) for _ in range(nsteps)):
-            if world > 1:
-                gatherer.gather(res)    # NCCL gather of the uint16 fields + positions into rank 0's HBM
-        return [res]
+        for res in cd.decode_stream(((cap_dev, fmt_id, ncap) for _ in range(nsteps)), sink=gatherer):
+            pass
+        return res
 
-    # end to end: the public host-buffer API (pipeline.HostStreamDecoder).  Every step uploads its
-    # capture from pinned host memory and downloads its uint16 fields into pinned host memory; the
-    # upload of step k+1 and the download of step k-1 overlap the decode of step k.
-    sd = pipeline.HostStreamDecoder(cd, _lib.FMT_U8, ncap, max_fields)
+    # end to end: the public host-buffer API (pipeline.HostStreamDecoder).  Every step uploads its capture -- the
+    # bytes of the capture file, packed formats stay packed -- from pinned host memory and downloads its uint16 fields
+    # (and audio) into pinned host memory; the upload of step k+1 and the download of step k-1 overlap the decode of
+    # step k.  Each rank delivers its own fields to its host buffers (no gather on top: that would deliver them twice).
+    sd = pipeline.HostStreamDecoder(cd, fmt_id, ncap, max_fields, np_dtype=raw.dtype, nbytes_max=nraw)
 
     def run_e2e(nsteps):
-        npic = 0
-        pend = sd.launch(sd.upload(cap_pin, ncap))                  # H2D of the first step's input
-        t = sd.upload(cap_pin, ncap) if nsteps > 1 else None
+        pend = sd.launch(sd.upload(cap_pin, ncap, nraw))            # H2D of the first step's input
+        t = sd.upload(cap_pin, ncap, nraw) if nsteps > 1 else None
         prev = None
         for i in range(nsteps):
             nxt = sd.launch(t) if t is not None else None           # demodulation of step i+1 ...
-            t = sd.upload(cap_pin, ncap) if i + 2 < nsteps else None
+            t = sd.upload(cap_pin, ncap, nraw) if i + 2 < nsteps else None
             job = sd.finish(pend)                                   # ... under the host walk of step i; D2H of its fields
             pend = nxt
-            if world > 1:
-                gatherer.gather(job[0])
             if prev is not None:
-                _, pics = sd.fetch(prev)                            # host reads the previous step's result
-                npic = pics.size
+                sd.fetch(prev)                                      # host reads the previous step's result
             prev = job
-        _, pics = sd.fetch(prev)
-        if world > 1:
-            gatherer.wait()
-        na = 0 if prev[0].audio_host is None else 16 * len(prev[0].audio_host[0])      # two float64 channels
-        return pics.size, na
+        res, pics = sd.fetch(prev)
+        na = 0 if res.audio_host is None else 16 * len(res.audio_host[0])      # two float64 channels
+        return res, pics, na
 
-    # the sampler is started before the warm-up (NVML initialisation, or nvidia-smi's start-up in the fallback, stalls
-    # the driver for ~100 ms)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-        time.sleep(0.5)
     # warm-up
-    res = None
     res = run_resident(max(a.warmup, 3))
     torch.cuda.synchronize()
-    nfields = sum(len(r.located) for r in res)
+    nfields = len(res.located)
+    verify = check_result(cd, res, system, fmt, seed, "%s resident" % system)
     # samples of the capture demodulated and decoded per step (each counted once: neither the block
     # overlaps nor the halos that neighbouring ranges demodulate twice are counted)
     S_ = cd.stride
@@ -346,38 +401,49 @@ def run_ours(a):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.time()
     e0.record()
-    run_resident(a.steps)
+    res = run_resident(a.steps)
     if world > 1:
         gatherer.wait()
     e1.record()
     barrier()
-    tw1 = time.time()
     ms_total = e0.elapsed_time(e1)
+    check_result(cd, res, system, fmt, seed, "%s resident, timed run" % system)
 
     # end-to-end timing (host buffers)
-    run_e2e(2)
+    run_e2e(3)
     barrier()
     t0 = time.perf_counter()
     e0.record()
-    npic, naudio = run_e2e(a.steps)
+    res, pics, naudio = run_e2e(a.steps)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
     wall_e2e = (time.perf_counter() - t0) * 1e3
-    clk = clocks.stop(tw0, time.time()) if rank == 0 else None
+    tw1 = time.time()
+    npic = pics.size
+    if np.any(res.status_host & 15):
+        raise SystemExit("bench self-check failed (%s e2e): field status bits" % system)
+    g = golden_field(system, fmt, seed)
+    if g is not None:
+        d = np.abs(pics[0, :len(g[0])].astype(np.int64) - g[0].astype(np.int64))
+        if d.max() > 1:
+            raise SystemExit("bench self-check failed (%s e2e): downloaded field differs from the reference by %d LSB" % (system, int(d.max())))
 
-    # dominant kernel alone: the fused block demodulation
-    planes_total = demod_only(cd, cap_dev, ncap)
-    planes_total = demod_only(cd, cap_dev, ncap)
-    torch.cuda.synchronize()
-    kt = []
-    for _ in range(max(a.steps, 5)):
-        e0.record()
-        planes_total = demod_only(cd, cap_dev, ncap)
-        e1.record()
+    out = None
+    k_ms = planes_total = None
+    if roofline:
+        # dominant kernel alone: the fused block demodulation (both passes of the mixed lane)
+        planes_total = demod_only(cd, cap_dev, fmt_id, ncap)
+        planes_total = demod_only(cd, cap_dev, fmt_id, ncap)
         torch.cuda.synchronize()
-        kt.append(e0.elapsed_time(e1))
-    k_ms = float(np.mean(kt))
+        kt = []
+        for _ in range(max(a.steps, 5)):
+            e0.record()
+            planes_total = demod_only(cd, cap_dev, fmt_id, ncap)
+            e1.record()
+            torch.cuda.synchronize()
+            kt.append(e0.elapsed_time(e1))
+        k_ms = float(np.mean(kt))
 
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e], device="cuda", dtype=torch.float64)
@@ -393,42 +459,92 @@ def run_ours(a):
         ms_step = ms_total / a.steps
         value = consumed_all / (ms_step / 1e3) / 1e6
         e2e_val = consumed_all / (ms_e2e / a.steps / 1e3) / 1e6
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        nplanes32 = 4 if system == "PAL" else 3
-        N, S = BLOCKLEN, BLOCKLEN - 1056
-        bytes_per_sample = N / S + 4 * nplanes32 + 8 + (2 * 8 / (16 if system == "PAL" else 8) if audio else 0)
-        achieved = bytes_per_sample * planes_total / (k_ms / 1e3) / 1e9
-        # per range: demod, 4 peak kernels (+4 for the one window that starts off a peak), hsync, pilot | 2x burst, tbc, 2 audio
-        traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_demod_traffic.json")))
-            key = "%s_%s" % (system, a.precision)
-            if key in tj:
-                traffic = tj[key]["dram_bytes_per_launch"]
-        except Exception:
-            pass
         # kernels of this library launched per step: demodulation (+ the float64 re-run of the mixed lane), 5 of the peak
-        # chase + the peak list's copy to pinned memory, table upload, hsync refinement + fix-up, pilot (per-line +
-        # per-field) or 2x burst, TBC, 2 of audio phase 2
-        launches_per_step = a.ranges * ((2 if a.precision == "mixed" else 1) + 5 + 1 + 1 + 2 + 2 + 1 + (2 if audio else 0))
-        line = dict(metric="rf_msamples_per_s_demod_tbc", value=value, unit="Msamples/s", n_gpus=world, steps=a.steps,
-                    warmup=max(a.warmup, 3), ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+        # chase + the peak list's copy to pinned memory, audio phase 2, table upload, hsync refinement + fix-up, VBI
+        # decode, pilot (per-line + per-field) or 2 x (burst lines + vote), TBC, + the gather's metadata upload
+        launches_per_step = (2 if a.precision == "mixed" else 1) + 5 + 1 + (1 if audio else 0) + 1 + 2 + 1 + \
+            (2 if system == "PAL" else 4) + 1 + (1 if world > 1 else 0)
+        out = dict(value=value, ms_per_step=ms_step, realtime_x=value / FS[system] / world, fields_per_step=nfields * world,
+                   e2e=dict(value=e2e_val, unit="Msamples/s", h2d_bytes_per_step=int(nraw * raw.dtype.itemsize),
+                            d2h_bytes_per_step=int(npic * 2 + naudio), wall_ms_per_step=wall_e2e / a.steps),
+                   gpu_launches=launches_per_step * a.steps, self_check=verify, window=(tw0, tw1))
+        if roofline:
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except Exception:
+                pass
+            peak = float(peaks.get("hbm_gbs", 6650.0))
+            nplanes32 = 4 if system == "PAL" else 3
+            N, S = BLOCKLEN, BLOCKLEN - 1056
+            b_in = {"u8": 1.0, "u16": 2.0, "r30": 4 / 3, "lds": 1.25}[fmt]
+            # algorithmic bytes per RF sample of this kernel: overlapped input, float32 planes, the float64
+            # sync plane, phase-1 audio (two float64 channels at fs/8 NTSC, fs/16 PAL)
+            bytes_per_sample = b_in * N / S + 4 * nplanes32 + 8 + (2 * 8 / (16 if system == "PAL" else 8) if audio else 0)
+            achieved = bytes_per_sample * planes_total / (k_ms / 1e3) / 1e9
+            traffic = None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "demod_traffic.json")))
+                key = "%s_%s_%s%s" % (system, fmt, a.precision, "_audio" if audio else "")
+                if key in tj:
+                    traffic = tj[key]["dram_bytes_per_launch"]
+            except Exception:
+                pass
+            out["roofline"] = dict(bound="hbm", kernel="demod_kernel (fused unpack+FFT+filter+IFFT+FM discriminator+post filters+sync scan)",
+                                   achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                                   bytes_per_sample=bytes_per_sample, kernel_ms=k_ms, kernel_msamples_per_s=planes_total / k_ms / 1e3,
+                                   peak_source="MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s")
+    del sd, cd, rf, cap_dev, cap_pin, gatherer
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (a.gpus, a.gpus))
+    torch.cuda.set_device(local)
+    numa = pin_rank_to_gpu_numa(local) if world > 1 else None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if a.scaling == "strong":
+        return run_strong(a, rank, world, local, dist)
+    system, audio, fmt = a.system, a.audio, a.fmt
+    # the sampler is started before the warm-up (NVML initialisation, or nvidia-smi's start-up in the fallback, stalls
+    # the driver for ~100 ms)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.5)
+    m = measure(a, system, audio, fmt, rank, world, local, dist)
+    extra = []
+    if a.extra and world == 1:
+        # BASELINE.json configs[2]: NTSC, both analog audio channels, 10-bit packed input -- the heaviest configuration
+        # of the path (burst refinement x2, two audio stages), measured the same way in the same run
+        for xs, xa, xf in (("NTSC", True, "lds"),):
+            if (xs, xa, xf) == (system, audio, fmt):
+                continue
+            x = measure(a, xs, xa, xf, rank, world, local, dist)
+            x.pop("window", None)
+            extra.append(dict(config=workload_config(xs, xa, world, xf), metric="rf_msamples_per_s_demod_tbc", unit="Msamples/s", **x))
+    if rank == 0:
+        tw0, tw1 = m.pop("window")
+        clk = clocks.stop(tw0, tw1)
+        line = dict(metric="rf_msamples_per_s_demod_tbc", value=m.pop("value"), unit="Msamples/s", n_gpus=world, steps=a.steps,
+                    warmup=max(a.warmup, 3), ms_per_step=m.pop("ms_per_step"), higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype={"mixed": "f32+f64", "f64": "f64", "f32": "f32"}[a.precision], data="synthetic",
-                    config=dict(workload_config(system, audio, world), precision=a.precision),
-                    realtime_x=value / FS[system] / world, fields_per_step=nfields * world,
-                    e2e=dict(value=e2e_val, unit="Msamples/s", h2d_bytes_per_step=int(ncap),
-                             d2h_bytes_per_step=int(npic * 2 + naudio), wall_ms_per_step=wall_e2e / a.steps),
-                    gpu_launches=launches_per_step * a.steps,
-                    roofline=dict(bound="hbm", kernel="demod_kernel (fused unpack+FFT+filter+IFFT+FM discriminator+post filters+sync scan)",
-                                  achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                                  bytes_per_sample=bytes_per_sample, kernel_ms=k_ms, kernel_msamples_per_s=planes_total / k_ms / 1e3,
-                                  peak_source="MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"),
-                    clocks=clk)
+                    config=workload_config(system, audio, world, fmt), precision=a.precision, **m)
+        line["clocks"] = clk
+        if numa:
+            line["cpu_affinity"] = numa
+        if extra:
+            line["other_workloads"] = extra
         if world == 1 and not a.skip_cpu:
             line["cpu_baseline"] = cpu_baseline(system, audio)
         print(json.dumps(line), flush=True)
@@ -437,7 +553,7 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
-def demod_only(cd, cap_dev, ncap):
+def demod_only(cd, cap_dev, fmt_id, ncap):
     """One launch of the demodulation kernel over the whole capture (what the roofline entry times)."""
     rf, be = cd.rf, cd.rf._be
     rf._set_mtf(cd.mtf_level)
@@ -457,8 +573,7 @@ def demod_only(cd, cap_dev, ncap):
         if not hasattr(cd, "_bench_audio"):
             cd._bench_audio = (be.empty(alen, np.float64), be.empty(alen, np.float64))
         a1 = cd._bench_audio
-    from lddecode_b200 import _lib
-    rf._check(be.lib.ldd_demod_blocks(rf._h, be.ptr(cap_dev), _lib.FMT_U8, 0, int(ncap), 0, int(nblocks), int(total), parr,
+    rf._check(be.lib.ldd_demod_blocks(rf._h, be.ptr(cap_dev), fmt_id, 0, int(ncap), 0, int(nblocks), int(total), parr,
                                       be.ptr(a1[0]) if a1 else None, be.ptr(a1[1]) if a1 else None, int(alen), be.stream()))
     return total
 
@@ -474,11 +589,13 @@ def main():
     ap.add_argument("--precision", default="mixed", choices=["f64", "f32", "mixed"],
                     help="demodulation lane (DESIGN.md 3.1); 'mixed' is the library default")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--ranges", type=int, default=1,
-                    help="read-position ranges a step's capture is pipelined over (measured on B200: 1 is fastest -- the "
-                         "persistent demodulation kernel of one range blocks the small kernels of the other)")
+    ap.add_argument("--fmt", default="u8", choices=["u8", "u16", "r30", "lds"], help="capture sample format fed to the decoder")
+    ap.add_argument("--no-extra", dest="extra", action="store_false",
+                    help="N=1: skip the second workload (NTSC + both audio channels from packed .lds, BASELINE configs[2])")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: one 1-s shard per GPU; strong: ONE capture of --seconds sharded by block range (configs[3])")
+    ap.add_argument("--seconds", type=float, default=8.0, help="--scaling strong: length of the capture")
     a = ap.parse_args()
-    RANGES[0] = a.ranges
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -25,11 +25,16 @@ def needed_window(cd, ncap, r0, r1):
 
 
 class FieldGatherer:
-    """Gathers the located fields of every rank on rank 0.  Buffers are allocated once; gather()
-    only enqueues device work (a copy into the send buffer and ONE asynchronous collective: the per-field
-    metadata rides in the head of the same buffer as the pictures), to_host()
-    turns the gathered buffers into a list of (readsample, istop, picture | None) ordered by read
-    position; call it before the next gather() overwrites them."""
+    """Gathers the located fields of every rank on rank 0: ONE asynchronous collective per step.
+
+    Send buffers are double-buffered and handed to the decoder as the TBC kernel's destination (buffers()), so a
+    step's pictures are written straight into the buffer the collective sends -- no staging copy -- and the
+    collective of step k only has to be over before step k+2 writes the same buffer: ranks are never
+    stream-ordered behind the slowest rank's previous step.  Per-field metadata (read position, parity, line
+    count) rides in the head of the same buffer.  to_host() turns the gathered buffers of the LAST gather() into a
+    list of (readsample, istop, picture | None) ordered by read position."""
+
+    NBUF = 2
 
     def __init__(self, cd, rank, world, max_fields, dist=None):
         import torch
@@ -41,91 +46,107 @@ class FieldGatherer:
         self.stride = (rf.SysParams['frame_lines'] // 2 + 1) * self.W
         self.cuda = self.be.name == "cuda"
         dev = self.be.device if self.cuda else "cpu"
-        self.meta_bytes = max_fields * 4 * 8                     # int64 [max_fields][4]: readsample, istop, linecount, status
-        self.buf = torch.zeros(self.meta_bytes + max_fields * self.stride * 2, dtype=torch.uint8, device=dev)
-
-        def split(b):
-            return b[:self.meta_bytes].view(torch.int64).view(max_fields, 4), b[self.meta_bytes:]      # (meta, uint16 pictures as bytes)
-        self.meta, self.pic = split(self.buf)
+        F = max_fields
+        self.meta_bytes = F * 3 * 8                               # int64 [F][3]: readsample, istop, linecount
+        self.status_off = self.meta_bytes                         # int32 [F]: the kernels' error bits
+        self.pic_off = (self.status_off + 4 * F + 255) // 256 * 256
+        nbytes = self.pic_off + F * self.stride * 2
+        self.send = [torch.zeros(nbytes, dtype=torch.uint8, device=dev) for _ in range(self.NBUF)]
+        self.recv = None
         if rank == 0 and world > 1:
-            self.bufs = [torch.empty_like(self.buf) for _ in range(world)]
-            parts = [split(b) for b in self.bufs]
-            self.metas, self.pics = [p[0] for p in parts], [p[1] for p in parts]
-        else:
-            self.bufs = None
-            self.pics, self.metas = [self.pic], [self.meta]
-        # host staging of the metadata: page-locked and double-buffered on CUDA (uploaded by a kernel, not the copy engine)
-        self._hmeta = [self.be.pinned(max_fields * 4, np.int64) for _ in range(2)] if self.cuda else None
+            self.recv = [[torch.empty_like(self.send[0]) for _ in range(world)] for _ in range(self.NBUF)]
+        # host staging of the metadata: page-locked on CUDA (uploaded by a kernel, not the copy engine)
+        self._hmeta = [self.be.pinned(F * 3, np.int64) for _ in range(self.NBUF)] if self.cuda else None
         self._n = 0
-        self._work = []
+        self._work = [None] * self.NBUF
+        self._last = None
 
-    def gather(self, results):
-        """results: one RangeResult or the list decode_pipelined returns."""
+    def _views(self, b):
         torch = self.torch
-        if not isinstance(results, (list, tuple)):
-            results = [results]
-        if self.cuda:
-            hm = self._hmeta[self._n % 2]
-            self._n += 1
-            meta = self.be.host_view(hm).reshape(self.max_fields, 4)
-            meta[:] = -1
-        else:
-            meta = np.full((self.max_fields, 4), -1, dtype=np.int64)
-        k0 = 0
-        spans = []
-        for res in results:
-            nloc = len(res.located)
-            if k0 + nloc > self.max_fields:
-                raise ValueError("max_fields too small")
-            if nloc:
-                loc = np.asarray(res.located, dtype=np.intp)
-                meta[k0:k0 + nloc, 0] = np.asarray(res.readsamples)[loc]
-                meta[k0:k0 + nloc, 1] = np.fromiter((res.infos[j].istop for j in res.located), dtype=np.int64, count=nloc)
-                meta[k0:k0 + nloc, 2] = np.fromiter((res.infos[j].linecount for j in res.located), dtype=np.int64, count=nloc)
-                meta[k0:k0 + nloc, 3] = 0
-            spans.append((k0, nloc, res))
-            k0 += nloc
-        self.wait()
+        F = self.max_fields
+        meta = b[:self.meta_bytes].view(torch.int64).view(F, 3)
+        status = b[self.status_off:self.status_off + 4 * F].view(torch.int32)
+        pic = b[self.pic_off:].view(torch.uint16)
+        return meta, status, pic
+
+    def buffers(self, stream=None):
+        """(pictures uint16 [max_fields * stride], status int32 [max_fields]) of the next gather(): pass them to the
+        decoder as pic_out / status_out.  Orders `stream` (default: the current stream) -- the stream whose kernels will
+        write the buffer -- behind the collective that last sent it."""
+        k = self._n % self.NBUF
+        w = self._work[k]
+        if w is not None:
+            if stream is not None and self.cuda:
+                with self.be.stream_ctx(stream):
+                    w.wait()
+            else:
+                w.wait()
+            self._work[k] = None
+        _, status, pic = self._views(self.send[k])
+        return pic, status
+
+    def gather(self, res):
+        """res: the RangeResult whose pictures were written into buffers() (or any RangeResult: its pictures are then
+        copied into the send buffer)."""
+        torch = self.torch
+        k = self._n % self.NBUF
+        pic, status = self.buffers()
+        self._n += 1
+        buf = self.send[k]
+        nloc = len(res.located)
+        if nloc > self.max_fields:
+            raise ValueError("max_fields too small")
+        meta = self.be.host_view(self._hmeta[k]).reshape(self.max_fields, 3) if self.cuda else np.empty((self.max_fields, 3), dtype=np.int64)
+        meta[:] = -1
+        if nloc:
+            loc = np.asarray(res.located, dtype=np.intp)
+            infos = res.infos[loc]
+            meta[:nloc, 0] = np.asarray(res.readsamples)[loc]
+            meta[:nloc, 1] = infos['istop']
+            meta[:nloc, 2] = infos['linecount']
+            in_place = self.cuda and res.d_pic is not None and res.d_pic.data_ptr() == pic.data_ptr()
+            if not in_place:
+                # decoded into the decoder's own buffer: stage it
+                n = nloc * self.stride
+                if self.cuda:
+                    pic.view(torch.uint8)[:2 * n] = res.d_pic[:n].view(torch.uint8)
+                    status[:nloc] = res.d_status[:nloc]
+                else:
+                    pic[:n] = torch.from_numpy(np.ascontiguousarray(self.be.to_host(res.d_pic)[:n]).view(np.int16)).view(torch.uint16)
+                    status[:nloc] = torch.from_numpy(np.asarray(self.be.to_host(res.d_status)[:nloc], dtype=np.int32))
         if self.cuda:
             be = self.be
-            be.lib.ldd_copy_small(be.ptr(self.buf), be.ptr(hm), self.meta_bytes, be.stream())
-            for k0, nloc, res in spans:
-                if nloc:
-                    self.meta[k0:k0 + nloc, 3] = res.d_status[:nloc].to(torch.int64)
-                    self.pic[k0 * self.stride * 2:(k0 + nloc) * self.stride * 2] = res.d_pic[:nloc * self.stride].view(torch.uint8)
+            be.lib.ldd_copy_small(be.ptr(buf), be.ptr(self._hmeta[k]), self.meta_bytes, be.stream())
         else:
-            tm = torch.from_numpy(meta)
-            for k0, nloc, res in spans:
-                if nloc:
-                    tm[k0:k0 + nloc, 3] = torch.from_numpy(np.asarray(self.be.to_host(res.d_status)[:nloc], dtype=np.int64))
-                    self.pic[k0 * self.stride * 2:(k0 + nloc) * self.stride * 2] = \
-                        torch.from_numpy(self.be.to_host(res.d_pic)[:nloc * self.stride].view(np.uint8))
-            self.meta.copy_(tm)
+            buf[:self.meta_bytes] = torch.from_numpy(meta.reshape(-1).view(np.uint8))
+        self._last = k
         if self.world > 1:
-            # asynchronous: the collective runs on the process group's own stream behind the copies
-            # above, so the next range's demodulation overlaps it; wait() orders the caller's
-            # stream (not the host) behind it
-            self._work = [self.dist.gather(self.buf, self.bufs if self.rank == 0 else None, dst=0, async_op=True)]
+            # asynchronous: the collective runs on the process group's own stream behind the work enqueued above,
+            # so the next range's demodulation overlaps it
+            self._work[k] = self.dist.gather(buf, self.recv[k] if self.rank == 0 else None, dst=0, async_op=True)
 
     def wait(self):
-        """Order the current stream behind the last gather (called before the send buffers are rewritten
-        and before the gathered buffers are read)."""
-        for w in self._work:
-            w.wait()
-        self._work = []
+        """Order the current stream behind every outstanding gather."""
+        for k, w in enumerate(self._work):
+            if w is not None:
+                w.wait()
+                self._work[k] = None
 
     def to_host(self):
         self.wait()
-        if self.rank != 0:
+        if self.rank != 0 or self._last is None:
             return None
+        bufs = self.recv[self._last] if self.recv is not None else [self.send[self._last]]
         out = []
-        for g in range(len(self.pics)):
-            m = self.metas[g].cpu().numpy()
-            p = self.pics[g].cpu().numpy().view(np.uint16).reshape(self.max_fields, self.stride)
+        for b in bufs:
+            meta, status, pic = self._views(b)
+            m = meta.cpu().numpy()
+            st = status.cpu().numpy()
+            p = pic.cpu().view(self.torch.int16).numpy().view(np.uint16).reshape(self.max_fields, self.stride)
             for k in range(self.max_fields):
                 if m[k, 0] < 0:
                     break
-                ok = (m[k, 3] & 15) == 0
+                ok = (st[k] & 15) == 0
                 out.append((int(m[k, 0]), int(m[k, 1]), p[k, :m[k, 2] * self.W].copy() if ok else None))
         out.sort(key=lambda t: t[0])
         return out

@@ -9,6 +9,11 @@ runs on the host over the ~16 K peaks per second of video (ldd_field_chain), and
 are refined and resampled in a handful of batched launches.  Only the peak list crosses to the host
 in the middle.
 
+A step is two calls into the library (include/ldd_b200.h, ldd_pipe_launch / ldd_pipe_finish): the
+first enqueues demodulation + peak chase (+ audio), the second waits for the peak list, walks, and
+enqueues refinement + VBI + TBC from preallocated tables.  This module only owns the buffers (torch
+tensors) and hands their addresses over; no per-field Python runs in the steady state.
+
 Ranges make the same code serve a single GPU (one range), captures larger than HBM (ranges one
 after the other) and multi-GPU sharding (one range per rank, parallel.py): a range owns the
 fields whose read position lies in [r0, r1); it starts walking 1.6 fields early so that its read
@@ -29,11 +34,160 @@ from . import _lib
 from . import field as F
 
 READLEN = 1000000        # Framer.readlen (lddecode_core.py:1319, 1324)
+LL = F.LL_STRIDE
+
+# numpy view of the library's ldd_field records
+FIELD_DTYPE = np.dtype([('stage', 'i4'), ('istop', 'i4'), ('linecount', 'i4'), ('npeaks', 'i4'), ('nvsyncs', 'i4'),
+                        ('vsyncs', 'i4', (4, 3)), ('_pad', 'i4'), ('nextfieldoffset', 'i8'), ('tbcstart', 'i8'),
+                        ('med_hsync', 'f8'), ('hsync_tolerance', 'f8')])
+assert FIELD_DTYPE.itemsize == C.sizeof(_lib.FieldInfo)
+
+
+def _host_array(ptr, n, ctype, dtype):
+    """numpy copy of n elements at a ctypes pointer (host memory owned by the library)."""
+    if n <= 0 or not bool(ptr):
+        return np.zeros(0, dtype=dtype)
+    return np.frombuffer((ctype * n).from_address(C.addressof(ptr.contents)), dtype=dtype).copy()
+
+
+class Refined:
+    """Line tables of the located fields of a range: device views, fetched to the host on first access."""
+
+    def __init__(self, res):
+        self._res = res
+        self.lineloc_add = res.lineloc_add
+        self.out_stride = res.out_stride
+        self.d_pic, self.d_status = res.d_pic, res.d_status
+        self._cache = {}
+
+    def _fetch(self, name, ptr, dtype):
+        if name not in self._cache:
+            res = self._res
+            res._live()
+            slot, n = res.slot, len(res.located)
+            be = slot.be
+            be.synchronize()
+            off = ptr - slot.tables_addr
+            nbytes = n * LL * np.dtype(dtype).itemsize
+            self._cache[name] = be.to_host(slot.d_tables[off:off + nbytes]).view(dtype).reshape(n, LL).copy()
+        return self._cache[name]
+
+    @property
+    def status(self):
+        be = self._res.slot.be
+        be.synchronize()
+        return be.to_host(self.d_status)[:len(self._res.located)]
+
+    linelocs2 = property(lambda s: s._fetch('l2', s._res.pr.d_linelocs2, np.float64))
+    linebad = property(lambda s: s._fetch('bad2', s._res.pr.d_linebad2, np.uint8))
+    linelocs3 = property(lambda s: s._fetch('l3', s._res.pr.d_linelocs3, np.float64))
+    linelocs4 = property(lambda s: s._fetch('l4', s._res.pr.d_linelocs4, np.float64))
+    burstlevel = property(lambda s: s._fetch('bl', s._res.pr.d_burstlevel, np.float32))
+    final = property(lambda s: s._fetch('final', s._res.pr.d_final, np.float64))
 
 
 class RangeResult:
-    """Fields owned by one range.  Device buffers: d_pic uint16 [nfields][out_stride], d_status."""
-    pass
+    """Fields owned by one range.  Device buffers: d_pic uint16 [nlocated][out_stride], d_status int32.
+
+    Host tables (infos, readsamples, base, linelocs1, gpeaks) are copied out of the library's arrays when the
+    result is built; device-side line tables come over on first access of `refined.*`."""
+
+    # -- per owned window
+    @property
+    def infos(self):
+        return self._infos
+
+    def _live(self):
+        if self.slot.generation != self._generation:
+            raise RuntimeError("this RangeResult's workspace has been reused by a later decode")
+
+    @property
+    def gpeaks(self):
+        if self._gpeaks is None:
+            self._live()
+            self._gpeaks = _host_array(self.pr.gpeaks, self._npeaks, C.c_longlong, np.int64)
+        return self._gpeaks
+
+    @property
+    def linelocs1(self):
+        if self._l1 is None:
+            self._live()
+            allrows = _host_array(self.pr.linelocs1, self._nwin_all * LL, C.c_double, np.float64).reshape(-1, LL)
+            self._l1 = allrows[self._owned]
+        return self._l1
+
+    def vbi_codes(self):
+        """int32 [nlocated][3]: the 24-bit Philips codes of the three code lines (-1 = None), decoded on the device."""
+        slot, n = self.slot, len(self.located)
+        be = slot.be
+        be.synchronize()
+        off = self.pr.d_vbi - slot.tables_addr
+        return be.to_host(slot.d_tables[off:off + 16 * n]).view(np.int32).reshape(n, 4)[:, :3].copy()
+
+
+class PipeSlot:
+    """One plane workspace of a CaptureDecoder plus the library's ldd_pipe on it."""
+
+    def __init__(self, cd, rf, plane_cap, max_fields):
+        be = self.be = rf._be
+        self.rf, self.plane_cap, self.max_fields = rf, int(plane_cap), int(max_fields)
+        lib = be.lib
+        from .rfdecode import VIDEO_FIELDS, _PLANE_OF
+        self.planes = {n: be.empty(self.plane_cap, np.float64 if n == 'demod_sync' else np.float32) for n in VIDEO_FIELDS[rf.system]}
+        b = _lib.PipeBufs()
+        for n, t in self.planes.items():
+            b.planes[_PLANE_OF[n]] = be.ptr(t).value
+        b.plane_cap = self.plane_cap
+        self.a1 = self.a2 = None
+        if rf.decode_analog_audio:
+            ds = rf.blocklen // len(rf.Filters['audio_lfilt'])
+            acap = self.plane_cap // ds + 16
+            self.a1 = (be.empty(acap, np.float64), be.empty(acap, np.float64))
+            self.a2 = (be.empty(acap // 4 + 16, np.float64), be.empty(acap // 4 + 16, np.float64))
+            b.audio1_l, b.audio1_r, b.audio1_cap = be.ptr(self.a1[0]), be.ptr(self.a1[1]), acap
+            b.audio2_l, b.audio2_r = be.ptr(self.a2[0]), be.ptr(self.a2[1])
+        cap = int(self.plane_cap // int(rf.linelen * .4)) + 64
+        self.pk = (be.empty(cap, np.int64), be.empty(cap, np.float64), be.zeros(2, np.int32))
+        self.h_pk = (be.pinned(cap, np.int64), be.pinned(cap, np.float64), be.pinned(2, np.int32))
+        b.peaks, b.peak_vals, b.peak_count, b.peak_cap = be.ptr(self.pk[0]), be.ptr(self.pk[1]), be.ptr(self.pk[2]), cap
+        b.h_peaks, b.h_peak_vals, b.h_peak_count = be.ptr(self.h_pk[0]), be.ptr(self.h_pk[1]), be.ptr(self.h_pk[2])
+        up, dev = C.c_longlong(0), C.c_longlong(0)
+        rf._check(lib.ldd_pipe_table_bytes(self.max_fields, C.byref(up), C.byref(dev)))
+        self.d_tables = be.empty(dev.value, np.uint8)
+        self.h_tables = be.pinned(up.value, np.uint8)
+        self.tables_addr = be.ptr(self.d_tables).value
+        b.field_tables, b.tables_bytes = self.tables_addr, dev.value
+        b.h_tables, b.h_tables_bytes = be.ptr(self.h_tables), up.value
+        pre = 40 * rf.linelen + 64
+        self.h_prefix = be.pinned(pre, np.float64)
+        b.h_prefix, b.prefix_cap = be.ptr(self.h_prefix), pre
+        self.bufs = b
+        self.out_stride = (rf.SysParams['frame_lines'] // 2 + 1) * rf.SysParams['outlinelen']
+        self.d_pic = be.empty(self.max_fields * self.out_stride, np.uint16)
+        self.d_status = be.zeros(self.max_fields, np.int32)
+        h = C.c_void_p()
+        rf._check(lib.ldd_pipe_create(rf._h, C.byref(b), self.max_fields, int(cd.field_samples), C.byref(h)))
+        self.h = h
+        self.result = _lib.PipeResult()
+        self.generation = 0
+
+    def close(self):
+        if self.h is not None:
+            self.be.lib.ldd_pipe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Pending:
+    """A launched range: ldd_pipe_launch has been enqueued on `slot`."""
+
+    def __init__(self, slot, rf, r0, r1, ncap_total):
+        self.slot, self.rf, self.r0, self.r1, self.ncap_total = slot, rf, r0, r1, ncap_total
 
 
 class HostStreamDecoder:
@@ -46,31 +200,36 @@ class HostStreamDecoder:
         for res, pics in sd.run(chunks): ...                    # or, step by step:
         t = sd.upload(buf, n); p = sd.launch(t); job = sd.finish(p); res, pics = sd.fetch(job)
 
-    upload() takes a pinned host buffer (be.pinned).  fetch() returns the RangeResult and a host view
-    [nfields, out_stride] of its uint16 fields that stays valid until the second-next finish(); the
-    RangeResult's device planes stay valid until the second-next launch().  With analog audio decoding on, the two
-    channels are downloaded with the fields: res.audio_host = (left, right) float64 views, valid as long as the fields."""
+    upload() takes a pinned host buffer (be.pinned) holding the chunk's bytes in the capture's own format
+    (u8, s16/u16, packed .r30 / .lds: the unpack is fused into the demodulation's block load).  fetch()
+    returns the RangeResult and a host view [nfields, out_stride] of its uint16 fields that stays valid
+    until the second-next finish(); the RangeResult's device planes stay valid until the second-next
+    launch().  With analog audio decoding on, the two channels are downloaded with the fields:
+    res.audio_host = (left, right) float64 views, valid as long as the fields."""
 
-    def __init__(self, cd, fmt, ncap_max, max_fields=96, np_dtype=np.uint8):
+    def __init__(self, cd, fmt, ncap_max, max_fields=96, np_dtype=np.uint8, nbytes_max=None):
         self.cd, self.fmt, self.max_fields = cd, fmt, max_fields
         rf = cd.rf
         be = self.be = rf._be
         self.up, self.down = be.new_stream(), be.new_stream()
         self.out_stride = (rf.SysParams['frame_lines'] // 2 + 1) * rf.SysParams['outlinelen']
-        self.d_in = [be.empty(ncap_max, np_dtype) for _ in range(2)]
+        nelem = ncap_max if nbytes_max is None else nbytes_max
+        self.d_in = [be.empty(nelem, np_dtype) for _ in range(2)]
         self.h_out = [be.pinned(max_fields * self.out_stride, np.uint16) for _ in range(2)]
         self.h_status = [be.pinned(max_fields, np.int32) for _ in range(2)]
         self.h_audio = [None, None]         # pinned (left, right) float64 buffers, allocated on first use
         self.in_free = [None, None]         # event: the demodulation that read d_in[k] has finished
         self.nup = self.nlaunch = self.nfin = 0
 
-    def upload(self, host_buf, n):
+    def upload(self, host_buf, n, nelem=None):
+        """n: samples of the chunk; nelem: elements of host_buf to copy (defaults to n; packed formats differ)."""
         be, k = self.be, self.nup % 2
         self.nup += 1
+        ne = n if nelem is None else nelem
         if self.in_free[k] is not None:
             be.stream_wait_event(self.up, self.in_free[k])
         with be.stream_ctx(self.up):
-            be.copy_async(self.d_in[k][:n], host_buf[:n])
+            be.copy_async(self.d_in[k][:ne], host_buf[:ne])
             ev = be.record_event()
         return (k, int(n), ev)
 
@@ -79,16 +238,15 @@ class HostStreamDecoder:
         be, cd = self.be, self.cd
         k, n, ev = ticket
         be.stream_wait_event(be.current_stream_obj(), ev)
-        ws, staging = cd._lane(self.nlaunch % 2)
+        pend = cd._launch(cd.rf, cd._slot(self.nlaunch % 2, n), self.d_in[k], self.fmt, 0, n, n, 0, n + 1)
         self.nlaunch += 1
-        pend = cd._launch_demod(cd.rf, ws, staging, self.d_in[k], self.fmt, 0, n, n, 0, n + 1)
         self.in_free[k] = be.record_event()
         return pend
 
     def finish(self, pend):
         """Host walk, refinement and TBC of a launched chunk; starts the download of its fields."""
         be = self.be
-        res = self.cd._finish_range(self.cd.rf, pend, side=self.cd._side_stream() if self.cd.overlap_refine else None)
+        res = self.cd._finish(pend, side=self.cd._side_stream() if self.cd.overlap_refine else None)
         j = self.nfin % 2
         self.nfin += 1
         nloc = len(res.located)
@@ -113,6 +271,8 @@ class HostStreamDecoder:
                     be.copy_async(self.h_audio[j][1][:na], ar)
                     res.audio_host = (be.host_view(self.h_audio[j][0])[:na], be.host_view(self.h_audio[j][1])[:na])
                 dev = be.record_event()
+            # the slot's picture buffer is rewritten by its next finish(): order that behind this download
+            res.slot.pic_free = dev
         return (res, j, nloc, dev)
 
     def decode(self, ticket):
@@ -126,7 +286,7 @@ class HostStreamDecoder:
         return res, self.be.host_view(self.h_out[j])[:nloc * self.out_stride].reshape(nloc, self.out_stride)
 
     def run(self, chunks):
-        """chunks: iterable of (pinned host buffer, length).  Yields (RangeResult, host pictures) per chunk."""
+        """chunks: iterable of (pinned host buffer, samples[, elements]).  Yields (RangeResult, host pictures) per chunk."""
         it = iter(chunks)
         up = lambda: (lambda c: self.upload(*c) if c is not None else None)(next(it, None))
         t = up()
@@ -153,56 +313,60 @@ class CaptureDecoder:
         self.colorlevel, self.colorphase = colorlevel, colorphase
         self.max_fields = max_fields
         self.field_samples = int(rf.freq_hz / rf.SysParams['FPS'] / 2)
-        # Plane / audio buffers are kept and reused across calls (a 1-s PAL range needs 0.9 GB of
-        # planes; re-allocating that per call stalls on cudaMalloc).  Results of decode_range
-        # therefore stay valid until the next call on the same CaptureDecoder.
-        self._ws = {}
-        self._staging = {}
-        self._lanes = None          # extra (RFDecode, stream, workspace, staging) sets of decode_pipelined
-        self._lane2 = None          # second workspace of decode_stream / HostStreamDecoder
+        # Plane workspaces (a 1-s PAL range needs 0.9 GB of planes) are kept and reused across calls; results of
+        # decode_range therefore stay valid until the next call that uses the same slot (decode / decode_range:
+        # slot 0; the streaming decoders alternate between slots 0 and 1).
+        self._slots = {}
+        self._lanes = None          # extra (RFDecode, stream, slot key) sets of decode_pipelined
         self._side = None
         self.overlap_refine = os.environ.get("LDD_NO_REFINE_OVERLAP") is None
 
-    def _lane(self, i):
-        """Workspace + staging set i (0 = the default one); a second set lets the demodulation of the
-        next capture run while the fields of the current one are still being walked and resampled."""
-        if i == 0:
-            return self._ws, self._staging
-        if self._lane2 is None:
-            self._lane2 = ({}, {})
-        return self._lane2
+    # -- workspaces
+    def _slot(self, key, ncap_window, rf=None):
+        """Plane workspace `key`, big enough for a range over a capture window of ncap_window samples."""
+        rf = rf or self.rf
+        need = int(ncap_window) + 2 * rf.blocklen
+        s = self._slots.get(key)
+        if s is None or s.plane_cap < need or s.rf is not rf:
+            if s is not None:
+                rf._be.synchronize()
+                s.close()
+            cap = int(need * 1.02) + 16
+            nf = min(self.max_fields, cap // (100 * rf.linelen) + 16)
+            s = PipeSlot(self, rf, cap, nf)
+            s.pic_free = None
+            self._slots[key] = s
+        return s
 
-    def decode_stream(self, captures):
+    def decode_stream(self, captures, sink=None):
         """Software-pipelined decode() of a sequence of device-resident captures [(cap_dev, fmt, ncap), ...]:
         capture k+1 is demodulated while the host walks capture k (one stream, two plane workspaces).
-        Yields one RangeResult per capture; its device buffers stay valid until the second-next launch."""
+        Yields one RangeResult per capture; its device buffers stay valid until the second-next launch.
+        sink (parallel.FieldGatherer): every capture's pictures are written straight into the sink's send buffer
+        and gathered."""
         it = iter(captures)
         k = 0
 
         def launch(c):
             nonlocal k
-            ws, staging = self._lane(k % 2)
+            slot = self._slot(k % 2, c[2])
             k += 1
-            return self._launch_demod(self.rf, ws, staging, c[0], c[1], 0, c[2], c[2], 0, c[2] + 1)
+            return self._launch(self.rf, slot, c[0], c[1], 0, c[2], c[2], 0, c[2] + 1)
 
         c = next(it, None)
         pend = launch(c) if c is not None else None
         while pend is not None:
             c = next(it, None)
             nxt = launch(c) if c is not None else None
-            yield self._finish_range(self.rf, pend, side=self._side_stream() if self.overlap_refine else None)
+            side = self._side_stream() if self.overlap_refine else None
+            if sink is not None:
+                pic, status = sink.buffers(side)
+                res = self._finish(pend, side=side, pic_out=pic, status_out=status)
+                sink.gather(res)
+            else:
+                res = self._finish(pend, side=side)
+            yield res
             pend = nxt
-
-    def _buf(self, tag, n, dtype, ws=None):
-        ws = self._ws if ws is None else ws
-        key = (tag, np.dtype(dtype).str)
-        b = ws.get(key)
-        if b is None or len(b) < n:
-            b = None
-            ws.pop(key, None)
-            b = self.rf._be.empty(int(n * 1.02) + 16, dtype)
-            ws[key] = b
-        return b[:n]
 
     @property
     def stride(self):
@@ -210,7 +374,9 @@ class CaptureDecoder:
         return rf.blocklen - rf.blockcut - rf.blockcut_end
 
     def plan_range(self, ncap_total, r0, r1):
-        """Block grid for the range owning read positions [r0, r1): (first_block, nblocks, walk_start)."""
+        """Block grid for the range owning read positions [r0, r1): (first_block, nblocks, walk_start).
+        (The library plans the same way inside ldd_pipe_launch; this copy serves callers that have to cut the
+        capture window a range needs, parallel.needed_window.)"""
         rf = self.rf
         S, N, bc = self.stride, rf.blocklen, rf.blockcut
         walk_start = 0 if r0 <= 0 else max(0, r0 - int(1.6 * self.field_samples))
@@ -225,50 +391,22 @@ class CaptureDecoder:
 
         cap_dev holds capture samples [cap_base, cap_base + cap_len) in format fmt; ncap_total is the
         length of the whole capture (the reference stops when a read would pass its end)."""
-        pend = self._launch_demod(self.rf, self._ws, self._staging, cap_dev, fmt, cap_base, cap_len, ncap_total, r0, r1,
-                                  audio_phase2)
-        return self._finish_range(self.rf, pend, want_tables)
+        pend = self._launch(self.rf, self._slot(0, cap_len), cap_dev, fmt, cap_base, cap_len, ncap_total, r0, r1, audio_phase2)
+        return self._finish(pend)
 
-    def _launch_demod(self, rf, ws, staging, cap_dev, fmt, cap_base, cap_len, ncap_total, r0, r1, audio_phase2=True):
+    def _launch(self, rf, slot, cap_dev, fmt, cap_base, cap_len, ncap_total, r0, r1, audio_phase2=True):
         """Stage 1 (asynchronous): demodulate the range's blocks, chase the sync peaks, start their copy
-        to pinned host memory."""
+        to pinned host memory, run the second audio stage."""
         be = rf._be
-        S, N = self.stride, rf.blocklen
-        first_block, nblocks, walk_start = self.plan_range(ncap_total, r0, r1)
-        avail_end = min(cap_base + cap_len, ncap_total)
-        while nblocks > 0 and first_block + (nblocks - 1) * S + N > avail_end:
-            nblocks -= 1
-        if first_block < cap_base:
-            raise ValueError("capture window does not cover the range's halo")
-        total = nblocks * S
-        res = RangeResult()
-        res.r0, res.r1, res.plane_origin, res.plane_len = r0, r1, first_block, total
-        res.ncap_total, res.walk_start = ncap_total, walk_start
-        res.staging = staging
-        rf._set_mtf(self.mtf_level)
-        planes, parr = rf._alloc_planes(max(total, 1), alloc=lambda name, n, dt: self._buf("plane_" + name, n, dt, ws))
-        a1l = a1r = None
-        alen = 0
-        if rf.decode_analog_audio:
-            ds = N // len(rf.Filters['audio_lfilt'])
-            alen = total // ds
-            a1l, a1r = self._buf("a1l", max(alen, 1), np.float64, ws), self._buf("a1r", max(alen, 1), np.float64, ws)
-        if nblocks:
-            rf._check(be.lib.ldd_demod_blocks(rf._h, be.ptr(cap_dev), fmt, int(cap_base), int(cap_len), int(first_block),
-                                              int(nblocks), int(total), parr, be.ptr(a1l) if a1l is not None else None,
-                                              be.ptr(a1r) if a1r is not None else None, int(alen), be.stream()))
-        res.planes = planes
-        # sync-peak chase over the whole plane; its result is the only device->host hop of the path
-        res.pending_peaks = F.sync_peaks_launch(rf, planes['demod_sync'], total, 0, staging)
-        # the second audio stage does not depend on the walk: enqueue it behind the chase so that it
-        # runs while the host walks the fields
-        res.audio = None
-        if rf.decode_analog_audio:
-            if audio_phase2 and alen > rf.blocklen:
-                res.audio = rf._audio_phase2_device(a1l, a1r, alen)
-            else:
-                res.audio = {'audio_left': a1l, 'audio_right': a1r}
-        return res
+        rf._set_mtf(self.mtf_level)           # uploads the tables on first use; the level itself is set by the library
+        if slot.pic_free is not None:
+            # a streaming download of this slot's previous pictures may still be running
+            be.stream_wait_event(be.current_stream_obj(), slot.pic_free)
+            slot.pic_free = None
+        rf._check(be.lib.ldd_pipe_launch(slot.h, be.ptr(cap_dev), int(fmt), int(cap_base), int(cap_len), int(ncap_total),
+                                         int(r0), int(r1), int(self.readlen), float(self.mtf_level), int(bool(audio_phase2)),
+                                         be.stream()))
+        return Pending(slot, rf, r0, r1, ncap_total)
 
     def _side_stream(self):
         """High-priority stream for the refine + TBC kernels of a streaming decode: the next capture's demodulation is
@@ -278,46 +416,56 @@ class CaptureDecoder:
             self._side = self.rf._be.new_stream(high_priority=True)
         return self._side
 
-    def _finish_range(self, rf, res, want_tables=False, side=None):
-        """Stage 2: host walk over the peak list, then the batched refine + TBC launches (on `side` when given; the
-        current stream is ordered behind them before this returns, so callers keep using the current stream)."""
-        planes, total, r0, r1 = res.planes, res.plane_len, res.r0, res.r1
-        ready_ev = res.pending_peaks.ev                      # recorded behind the demodulation and the peak chase
-        gpk, gvl = res.pending_peaks.result()
-        res.pending_peaks = None
-        res.gpeaks = gpk
-        batch, infos, readsamples = self._walk(rf, planes, total, res.plane_origin, res.ncap_total, res.walk_start, r1,
-                                               r0 > 0, gpk, gvl, res.staging)
-        n_all = len(infos)
-        stages = np.fromiter((f.stage for f in infos), dtype=np.int32, count=n_all)
-        owned = np.nonzero((readsamples >= r0) & (readsamples < r1))[0]
-        res.infos = [infos[i] for i in owned]
-        res.readsamples = readsamples[owned]
-        res.base = batch.base[owned]
-        res.linelocs1 = batch.linelocs1[owned]
-        res.nwindows = len(owned)
-        loc_mask = stages[owned] == _lib.FIELD_LOCATED
-        located = np.nonzero(loc_mask)[0]
-        res.located = [int(j) for j in located]
-        res.refined = None
-        res.d_pic = res.d_status = None
-        res.out_stride = (rf.SysParams['frame_lines'] // 2 + 1) * rf.SysParams['outlinelen']
-        if len(located):
-            idx = owned[located]
-            sub = F.FieldBatch.view(rf, batch, idx, np.fromiter((infos[i].linecount for i in idx), dtype=np.int32, count=len(idx)))
-            be = rf._be
-            if side is not None:
-                be.stream_wait_event(side, ready_ev)
-                with be.stream_ctx(side):
-                    ref = F.refine_and_tbc(rf, planes, total, sub, self.colorlevel, self.colorphase, want_intermediates=want_tables,
-                                           staging=res.staging)
-                    done = be.record_event()
-                be.stream_wait_event(be.current_stream_obj(), done)
+    def _finish(self, pend, side=None, pic_out=None, status_out=None, frame_mode=False, pic_stride=None, pic_cap=None):
+        """Stage 2: ldd_pipe_finish (host walk over the peak list, then the batched refine + VBI + TBC launches, on
+        `side` when given; the current stream is ordered behind them).  pic_out / status_out: device buffers that
+        receive the pictures instead of the slot's own (e.g. a collective's send buffer)."""
+        slot, rf = pend.slot, pend.rf
+        be = rf._be
+        main = be.stream()
+        ref = C.c_void_p(side.cuda_stream) if side is not None else main
+        d_pic = slot.d_pic if pic_out is None else pic_out
+        d_status = slot.d_status if status_out is None else status_out
+        stride = slot.out_stride if pic_stride is None else int(pic_stride)
+        cap = (len(d_pic) // stride) if pic_cap is None else int(pic_cap)
+        pr = slot.result
+        rf._check(be.lib.ldd_pipe_finish(slot.h, float(self.colorlevel), float(self.colorphase), int(bool(frame_mode)), be.ptr(d_pic),
+                                         stride, cap, be.ptr(d_status), ref, main, C.byref(pr)))
+        res = RangeResult()
+        res.slot, res.pr = slot, pr
+        res.r0, res.r1, res.ncap_total = pend.r0, pend.r1, pend.ncap_total
+        res.plane_origin, res.plane_len, res.walk_start = pr.plane_origin, pr.plane_len, pr.walk_start
+        total = pr.plane_len
+        res.planes = {n: t[:total] for n, t in slot.planes.items()}
+        res.audio = None
+        if slot.a1 is not None:
+            if pr.audio2_len:
+                res.audio = {'audio_left': slot.a2[0][:pr.audio2_len], 'audio_right': slot.a2[1][:pr.audio2_len]}
             else:
-                ref = F.refine_and_tbc(rf, planes, total, sub, self.colorlevel, self.colorphase, want_intermediates=want_tables,
-                                       staging=res.staging)
-            res.refined = ref
-            res.d_pic, res.d_status = ref.d_pic, ref.d_status
+                res.audio = {'audio_left': slot.a1[0][:pr.audio1_len], 'audio_right': slot.a1[1][:pr.audio1_len]}
+        nw = pr.nwindows
+        res._nwin_all = nw
+        fields = _host_array(pr.fields, nw, _lib.FieldInfo, np.uint8).view(FIELD_DTYPE) if nw else np.zeros(0, dtype=FIELD_DTYPE)
+        owned = _host_array(pr.owned, pr.nowned, C.c_int, np.int32)
+        res._owned = owned
+        res._infos = fields[owned].view(np.recarray)
+        res.readsamples = _host_array(pr.readsample, nw, C.c_longlong, np.int64)[owned]
+        res.base = _host_array(pr.base, nw, C.c_longlong, np.int64)[owned]
+        res.nwindows = int(pr.nowned)
+        res.located = [int(j) for j in _host_array(pr.located, pr.nlocated, C.c_int, np.int32)]
+        res.frame_of = _host_array(pr.frame_of, pr.nlocated, C.c_int, np.int32) if frame_mode else None
+        res.nframes = int(pr.nframes)
+        res.prefix_windows = int(pr.prefix_windows)
+        res._gpeaks = res._l1 = None
+        res._npeaks = int(pr.npeaks)
+        slot.generation += 1
+        res._generation = slot.generation
+        res.lineloc_add = pr.lineloc_add
+        res.out_stride = stride
+        nloc = len(res.located)
+        res.d_pic = d_pic[:(cap if frame_mode else nloc) * stride] if nloc else None
+        res.d_status = d_status[:nloc] if nloc else None
+        res.refined = Refined(res) if nloc else None
         return res
 
     def decode_pipelined(self, cap_dev, fmt, ncap, nranges=2):
@@ -328,26 +476,24 @@ class CaptureDecoder:
         from . import parallel, rfdecode
         rf0, be = self.rf, self.rf._be
         if self._lanes is None or len(self._lanes) < nranges:
-            lanes = [(rf0, None, self._ws, self._staging)] if self._lanes is None else self._lanes
+            lanes = list(self._lanes or [])
             while len(lanes) < nranges:
-                rfk = rfdecode.RFDecode(rf0.freq, rf0.system, rf0.blocklen, rf0.decode_analog_audio, precision=rf0.precision,
-                                        _backend=be)
-                lanes.append((rfk, be.new_stream(), {}, {}))
-            if lanes[0][1] is None:
-                lanes[0] = (rf0, be.new_stream(), self._ws, self._staging)
+                rfk = rf0 if not lanes else rfdecode.RFDecode(rf0.freq, rf0.system, rf0.blocklen, rf0.decode_analog_audio,
+                                                              precision=rf0.precision, _backend=be)
+                lanes.append((rfk, be.new_stream(), ('lane', len(lanes))))
             self._lanes = lanes
         main = be.current_stream_obj()
         bounds = parallel.shard_bounds(ncap, nranges)
         pend = []
-        for (rfk, sk, ws, stg), (r0, r1) in zip(self._lanes, bounds):
+        for (rfk, sk, key), (r0, r1) in zip(self._lanes, bounds):
             if sk is not None:
                 be.wait_stream(sk, main)
             with be.stream_ctx(sk):
-                pend.append(self._launch_demod(rfk, ws, stg, cap_dev, fmt, 0, ncap, ncap, r0, r1))
+                pend.append(self._launch(rfk, self._slot(key, ncap, rfk), cap_dev, fmt, 0, ncap, ncap, r0, r1))
         out = []
-        for (rfk, sk, ws, stg), p in zip(self._lanes, pend):
+        for (rfk, sk, key), p in zip(self._lanes, pend):
             with be.stream_ctx(sk):
-                out.append(self._finish_range(rfk, p))
+                out.append(self._finish(p))
             if sk is not None:
                 be.wait_stream(main, sk)
         return out
@@ -356,62 +502,17 @@ class CaptureDecoder:
         """The whole capture as one range."""
         return self.decode_range(cap_dev, fmt, 0, ncap, ncap, 0, ncap + 1, want_tables, audio_phase2)
 
-    # -- host walk
-    def _walk(self, rf, planes, total, plane_origin, ncap_total, first_readsample, stop_readsample, tolerant, gpk, gvl,
-              staging=None):
-        be = rf._be
-        cb_staging = staging.setdefault('cb', {}) if staging is not None else {}
-        mf = self.max_fields
-        fields = (_lib.FieldInfo * mf)()
-        batch = F.FieldBatch(rf, mf)
-        readsample = np.zeros(mf, dtype=np.int64)
-        nf = C.c_int(0)
-        keep = {}
-        gpk = np.ascontiguousarray(gpk, dtype=np.int64)
-        gvl = np.ascontiguousarray(gvl, dtype=np.float64)
-
-        L = rf.linelen
-        half, skip = L // 2, int(L * .4)
-
-        def window_peaks(ctx, b, wl, ppk, pvl, pn):
-            # This window does not start on a peak of the range's chase (second read of a capture,
-            # range starts).  Chase a short prefix by itself; from the first peak it shares with the
-            # range's chase on, the two lists are the same, cut at the reference's loop bound.
-            b, wl = int(b), int(wl)
-            pk = vl = None
-            npre = min(wl, 40 * L)
-            spk, svl = F.sync_peaks_prefix_host(rf, planes['demod_sync'][b:b + npre], npre, cb_staging)
-            pos = np.searchsorted(gpk, spk + b)
-            common = np.nonzero(gpk[np.minimum(pos, len(gpk) - 1)] == spk + b)[0] if len(gpk) else np.zeros(0, dtype=np.int64)
-            if len(common):
-                k = int(common[0])
-                m = int(pos[k])
-                pk = np.concatenate([spk[:k], gpk[m:] - b])
-                vl = np.concatenate([svl[:k], gvl[m:]])
-                # a peak belongs to the window's list iff the step that found it started below the bound
-                limit = wl - 2 * L
-                i0 = np.concatenate([[0], pk[:-1] + skip])
-                istep = i0 + ((pk - i0) // half) * half
-                stop = np.nonzero(istep >= limit)[0]
-                n = int(stop[0]) if len(stop) else len(pk)
-                pk, vl = pk[:n], vl[:n]
-            else:
-                pk, vl = F.sync_peaks_device(rf, planes['demod_sync'][b:b + wl], wl, 0)
-            keep['pk'], keep['vl'] = np.ascontiguousarray(pk, dtype=np.int64), np.ascontiguousarray(vl, dtype=np.float64)
-            ppk[0] = keep['pk'].ctypes.data
-            pvl[0] = keep['vl'].ctypes.data
-            pn[0] = len(pk)
-            return 0
-
-        cb = _lib.WINDOW_PEAKS_FN(window_peaks)
-        rf._check(be.lib.ldd_field_chain(rf._h, F._h(gpk), F._h(gvl), len(gpk), int(total), int(plane_origin), int(ncap_total),
-                                         int(self.readlen), int(first_readsample), int(stop_readsample), int(bool(tolerant)), mf,
-                                         C.cast(cb, C.c_void_p), None, C.cast(fields, C.c_void_p), F._h(batch.base),
-                                         F._h(batch.winlen), F._h(readsample), F._h(batch.linelocs1.reshape(-1)),
-                                         F._h(batch.linebad.reshape(-1)), F.LL_STRIDE, C.byref(nf)))
-        n = nf.value
-        infos = [fields[i] for i in range(n)]
-        return batch, infos, readsample[:n].copy()
+    def decode_frames(self, cap_dev, fmt, ncap):
+        """The whole capture as interleaved uint16 frames written by the TBC kernel itself (Framer.formatoutput,
+        lddecode_core.py:1238-1252; fields paired by parity as Framer.readframe does for CLV discs).  Returns
+        (RangeResult, frames uint16 device view [nframes][frame_lines * outlinelen])."""
+        rf = self.rf
+        slot = self._slot(0, ncap)
+        fstride = rf.SysParams['frame_lines'] * rf.SysParams['outlinelen']
+        pend = self._launch(rf, slot, cap_dev, fmt, 0, ncap, ncap, 0, ncap + 1)
+        cap = len(slot.d_pic) // fstride
+        res = self._finish(pend, frame_mode=True, pic_stride=fstride, pic_cap=cap)
+        return res, slot.d_pic[:res.nframes * fstride].reshape(-1, fstride)
 
     # -- host copies
     def pictures(self, res):

@@ -514,7 +514,14 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if a.scaling == "strong":
-        return run_strong(a, rank, world, local, dist)
+        out = run_strong(a, rank, world, local, dist)
+        if rank == 0:
+            out.update(warmup=2, vs_baseline=None, dtype={"mixed": "f32+f64", "f64": "f64", "f32": "f32"}[a.precision], data="synthetic")
+            print(json.dumps(out), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     system, audio, fmt = a.system, a.audio, a.fmt
     # the sampler is started before the warm-up (NVML initialisation, or nvidia-smi's start-up in the fallback, stalls
     # the driver for ~100 ms)
@@ -533,6 +540,11 @@ def run_ours(a):
             x = measure(a, xs, xa, xf, rank, world, local, dist)
             x.pop("window", None)
             extra.append(dict(config=workload_config(xs, xa, world, xf), metric="rf_msamples_per_s_demod_tbc", unit="Msamples/s", **x))
+    strong = None
+    if world > 1 and a.extra:
+        # BASELINE.json configs[3] in the same run: ONE NTSC CLV capture (1 s per GPU, so every rank still has a
+        # second of work) sharded by block range with halos -- the north-star split, next to the weak-scaling headline
+        strong = run_strong(a, rank, world, local, dist, seconds=float(world), steps=max(3, a.steps // 4))
     if rank == 0:
         tw0, tw1 = m.pop("window")
         clk = clocks.stop(tw0, tw1)
@@ -543,6 +555,8 @@ def run_ours(a):
         line["clocks"] = clk
         if numa:
             line["cpu_affinity"] = numa
+        if strong is not None:
+            extra.append(strong)
         if extra:
             line["other_workloads"] = extra
         if world == 1 and not a.skip_cpu:
@@ -551,6 +565,86 @@ def run_ours(a):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_strong(a, rank, world, local, dist, seconds=None, steps=None):
+    """BASELINE.json configs[3]: ONE NTSC CLV capture of `seconds` sharded by contiguous read-position ranges (block
+    ranges + halos) over the ranks; only the per-field outputs cross NVLink (NCCL gather to rank 0).  The capture is the
+    tiled synthetic one (lddecode_b200.synth.TiledCapture: a pure function of the sample index), every rank generates
+    the window its shard needs in its own HBM (untimed) and decodes it chunk by chunk (~1 s of capture per chunk, two
+    plane workspaces, chunk k+1 demodulated under the host walk of chunk k).  A step = the whole capture once."""
+    import torch
+    from lddecode_b200 import _lib, parallel, pipeline, rfdecode, synth
+    seconds = a.seconds if seconds is None else seconds
+    steps = a.steps if steps is None else steps
+    fs = FS["NTSC"]
+    T = int(round(seconds * fs * 1e6))
+    ncap = T + TAIL
+    rf = rfdecode.RFDecode(fs, "NTSC", BLOCKLEN, decode_analog_audio=a.audio, device=local, precision=a.precision)
+    cd = pipeline.CaptureDecoder(rf, max_fields=256)
+    R0, R1 = parallel.shard_bounds(ncap, world)[rank]
+    lo, hi = parallel.needed_window(cd, ncap, R0, R1)
+    tc = synth.TiledCapture(seed=2, device="cuda")
+    cap_dev = tc.generate(lo, hi - lo)
+    torch.cuda.synchronize()
+    chunk = one_second("NTSC")
+    edges = list(range(R0, min(R1, ncap), chunk))
+    ranges = [(cap_dev, _lib.FMT_U8, lo, hi - lo, ncap, r0, min(r0 + chunk, R1)) for r0 in edges]
+    ranges[-1] = ranges[-1][:6] + (R1,)
+    max_fields = 80
+    gatherer = parallel.FieldGatherer(cd, rank, world, max_fields, dist) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_once():
+        nf, last = 0, None
+        for res in cd.decode_stream(iter(ranges), sink=gatherer):
+            nf += len(res.located)
+            last = res
+        return nf, last
+
+    nf, last = run_once()
+    run_once()
+    torch.cuda.synchronize()
+    st = rf._be.to_host(last.d_status)[:len(last.located)] if last.located else np.zeros(0, dtype=np.int32)
+    if np.any(st & 15):
+        raise SystemExit("bench self-check failed (strong): field status bits")
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        run_once()
+    if world > 1:
+        gatherer.wait()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    nft = torch.tensor([float(nf)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        dist.all_reduce(nft, op=dist.ReduceOp.SUM)
+    out = None
+    if rank == 0:
+        ms_step = ms / steps
+        # every sample of the capture counted once (halos that neighbouring shards / chunks demodulate twice are not)
+        value = T / (ms_step / 1e3) / 1e6
+        out = dict(metric="rf_msamples_per_s_demod_tbc", value=value, unit="Msamples/s", n_gpus=world, steps=steps,
+                   ms_per_step=ms_step, higher_is_better=True, scaling="strong", realtime_x=value / fs,
+                   fields_per_step=int(nft[0]), capture_seconds=seconds,
+                   config=dict(workload="NTSC CLV synthetic 8-bit RF, ONE capture of %.1f s (%.2f Gsamples, tiled 2-frame template, "
+                                        "running carrier phase), sharded by block range with halos over %d GPU(s), %s demod + sync + TBC"
+                                        % (seconds, T / 1e9, world, "video + both analog audio channels" if a.audio else "video"),
+                               blocklen=BLOCKLEN, readlen=1000000, chunk_samples=chunk, chunks_per_rank=len(ranges),
+                               parallelism="read-position ranges [g T/G, (g+1) T/G) per rank, walk starts 1.6 fields early, "
+                                           "demodulates one read length past the end; NCCL gather of uint16 fields to rank 0"))
+    del cap_dev, gatherer, cd, rf
+    torch.cuda.empty_cache()
+    return out
 
 
 def demod_only(cd, cap_dev, fmt_id, ncap):

@@ -118,12 +118,19 @@ class EmuBackend:
         return np.ascontiguousarray(arr).copy()
 
     def to_host(self, buf):
+        if hasattr(buf, "data_ptr"):
+            import torch
+            if buf.dtype == torch.uint16:
+                return buf.view(torch.int16).numpy().view(np.uint16).copy()
+            return buf.numpy().copy()
         return np.array(buf, copy=True)
 
     def dtype_of(self, np_dtype):
         return np.dtype(np_dtype)
 
     def ptr(self, buf):
+        if hasattr(buf, "data_ptr"):                # a torch CPU tensor (the gloo gather's send buffers)
+            return C.c_void_p(buf.data_ptr())
         return C.c_void_p(buf.ctypes.data)
 
     def stream(self):

@@ -241,6 +241,258 @@ __global__ void __launch_bounds__(TBC_THREADS, 4) tbc_kernel(const TbcParams p) 
 
 #undef PX
 #undef M0
+
+// ---------------------------------------------------------------------------------------------
+// float32 variant for uint16 output (the float32 / mixed lanes): the same closed-form spline, with
+//   * the line's samples brought in by ONE bulk asynchronous copy (cp.async.bulk + mbarrier, the 1-D form of TMA)
+//     straight into an unpadded shared array -- persistent CTAs walk over the lines and the copy of the next line
+//     runs under the arithmetic of the current one (double-buffered staging);
+//   * 17 samples per thread chunk instead of 16: with an odd chunk length consecutive threads' chunks start 17 banks
+//     apart, so the unpadded array the bulk copy needs is conflict-free without a padding slot;
+//   * float32 recursions and evaluation (the plane is float32 already; a uint16 step is 21-34 Hz, the float32 spline
+//     is good to a fraction of a Hz), float64 only for the sample positions (a float32 position at 2300 samples would
+//     be 2e-4 samples off: 10 Hz on a steep edge).
+// Output within +-1 LSB of the float64 kernel (a sample moves only when it sits within ~1e-2 LSB of a rounding
+// boundary).  The float64 kernel above stays the one for the exact lane and for float64 (Hz) output.
+constexpr int TBF_C = 17;
+constexpr int TBF_THREADS = 256;
+constexpr int TBF_MAXU = TBF_C * TBF_THREADS;            // 4352 staged samples at most
+
+struct TbfGeom {            // one work item (field, line), filled by thread 0 when it issues the item's copy
+    double b, e;
+    long long src0;         // plane index of staged sample 0 (16-byte aligned element index when bulk)
+    int field, line, dist, lead;   // lead = TBC_H + alignment shift: staged index of line sample 0
+    int U;                  // staged samples
+    int state;              // 0: nothing to do (line >= linecount), 1: bulk copy in flight, 2: load by hand, 3: bad geometry
+};
+
+#ifndef LDD_EMU
+__device__ inline unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ inline void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ inline void mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ inline void bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ inline void mbar_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
+
+__global__ void __launch_bounds__(TBF_THREADS, 4) tbc_f32_kernel(const TbcParams p, int nitems, int lines_per_field, int maxu) {
+    LDD_DYN_SMEM(smem_raw);
+    float* ysb[2];
+    ysb[0] = (float*)smem_raw;
+    ysb[1] = ysb[0] + maxu;
+    float* Ms = ysb[1] + maxu;
+    float* Lf = Ms + maxu + 32;                      // the last chunk's slots may reach past the staged samples
+    float* Lb = Lf + TBF_THREADS;
+    __shared__ TbfGeom geom[2];
+    __shared__ unsigned long long mbar[2];           // 8-byte aligned by type
+    const int tid = threadIdx.x;
+    const float r = -0.26794919243112270647f, c = 0.28867513459481288225f;
+
+    // Thread 0 runs the copies.  The table values of an item (two line positions, window base, line count) are
+    // fetched one iteration before they are needed, so issuing a copy never waits for global memory.
+    struct Pre { double b, e; long long base; int lc, field, line; };
+    auto prefetch = [&](int w) {
+        Pre q;
+        q.lc = -1; q.b = q.e = 0.0; q.base = 0; q.field = q.line = 0;
+        if (w < nitems) {
+            q.field = w / lines_per_field;
+            q.line = w - q.field * lines_per_field;
+            const double* ll = p.linelocs + (size_t)q.field * p.ll_stride;
+            q.lc = p.linecount[q.field];
+            q.b = ll[p.lineoffset + q.line];
+            q.e = ll[p.lineoffset + q.line + 1];
+            q.base = p.base ? p.base[q.field] : 0;
+        }
+        return q;
+    };
+    auto issue = [&](const Pre& q, int buf) {
+        TbfGeom g;
+        g.state = 0; g.field = q.field; g.line = q.line;
+        if (q.lc >= 0 && q.line < q.lc) {
+            g.b = q.b + p.lineloc_add;
+            g.e = q.e + p.lineloc_add;
+            const long long ib = (long long)g.b, ie = (long long)g.e;
+            g.dist = (int)(ie - ib);
+            const long long s0 = q.base + ib - TBC_H;
+            if (!(g.b >= 0.0) || g.dist < 3 || g.dist > p.maxd || q.base + ib + g.dist + 1 > p.n || q.base + ib < 0) {
+                g.state = 3;
+            } else {
+                const int shift = (int)(s0 & 3);
+                const long long a0 = s0 - shift;
+                const int U = (g.dist + 1 + 2 * TBC_H + shift + 3) & ~3;
+                g.src0 = s0; g.lead = TBC_H; g.U = g.dist + 1 + 2 * TBC_H; g.state = 2;       // by hand: window at a plane edge
+#ifndef LDD_EMU
+                if (a0 >= 0 && a0 + U <= p.n && U <= maxu && (((uintptr_t)p.plane) & 15) == 0) {
+                    g.src0 = a0; g.lead = TBC_H + shift; g.U = U; g.state = 1;
+                    mbar_expect_tx(&mbar[buf], (unsigned)U * 4u);
+                    bulk_g2s(ysb[buf], p.plane + a0, (unsigned)U * 4u, &mbar[buf]);
+                }
+#endif
+            }
+        }
+        geom[buf] = g;
+    };
+
+    if (tid == 0) {
+#ifndef LDD_EMU
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+    }
+    __syncthreads();
+    Pre pre;
+    if (tid == 0) {
+        issue(prefetch(blockIdx.x), 0);
+        pre = prefetch(blockIdx.x + gridDim.x);
+    }
+    __syncthreads();
+    unsigned phase[2] = {0u, 0u};
+    int cur = 0;
+    for (int w = blockIdx.x; w < nitems; w += gridDim.x, cur ^= 1) {
+        // the next item's copy runs under this item's arithmetic (its buffer was released by the barrier that ended
+        // the previous iteration)
+        if (tid == 0) {
+            issue(pre, cur ^ 1);
+            pre = prefetch(w + 2 * gridDim.x);
+        }
+        const TbfGeom g = geom[cur];
+        float* ys = ysb[cur];
+        if (g.state == 0 || g.state == 3) {
+            if (g.state == 3 && tid == 0) atomicOr(&p.status[g.field], 1);
+            __syncthreads();
+            continue;
+        }
+        if (g.state == 1) {
+#ifndef LDD_EMU
+            mbar_wait(&mbar[cur], phase[cur]);
+            phase[cur] ^= 1u;
+#endif
+        } else {
+            for (int i = tid; i < g.U; i += TBF_THREADS) {
+                long long s = g.src0 + i;
+                s = s < 0 ? 0 : (s >= p.n ? p.n - 1 : s);
+                ys[i] = p.plane[s];
+            }
+            __syncthreads();
+        }
+        const int U = g.U, dist = g.dist;
+        // d[u] for u = 1 .. U-2; chunk q owns u = 1 + 17 q .. 17 + 17 q.  Beyond the staged samples the right-hand side
+        // is taken as zero: that only changes the homogeneous part, which the not-a-knot solve absorbs.
+        const int nq = (U - 2 + TBF_C - 1) / TBF_C;
+        float d[TBF_C];
+        const bool act = tid < nq;
+        if (act) {
+            const int u0 = 1 + TBF_C * tid;
+            float ym = ys[u0 - 1], y0 = ys[u0];
+            LDD_UNROLL
+            for (int k = 0; k < TBF_C; ++k) {
+                const int u = u0 + k;
+                const float yp = (u + 1 < U) ? ys[u + 1] : 0.f;
+                d[k] = (u < U - 1) ? 6.f * (fmaf(-2.f, y0, ym) + yp) : 0.f;
+                ym = y0;
+                y0 = yp;
+            }
+            float f = 0.f, bk = 0.f;
+            LDD_UNROLL
+            for (int k = 0; k < TBF_C; ++k) {
+                f = fmaf(f, r, d[k]);
+                bk = fmaf(bk, r, d[TBF_C - 1 - k]);
+            }
+            Lf[tid] = f;
+            Lb[tid] = bk;
+        }
+        __syncthreads();
+        if (act) {
+            // r^17 = 2e-10: one neighbour chunk is exact in float32
+            float f = tid >= 1 ? Lf[tid - 1] : 0.f;
+            float bk = tid + 1 < nq ? Lb[tid + 1] : 0.f;
+            float* M = Ms + 1 + TBF_C * tid;
+            LDD_UNROLL
+            for (int k = 0; k < TBF_C; ++k) {
+                f = fmaf(f, r, d[k]);
+                M[k] = f - d[k];
+            }
+            LDD_UNROLL
+            for (int k = TBF_C - 1; k >= 0; --k) {
+                bk = fmaf(bk, r, d[k]);
+                M[k] = c * (M[k] + bk);
+            }
+        }
+        __syncthreads();
+        const int lead = g.lead;
+        {
+            // not-a-knot rows -> homogeneous part alpha r^i + beta r^(dist-i)
+            const float* Mz = Ms + lead;
+            const float L = Mz[0] - 2.f * Mz[1] + Mz[2];
+            const float R = Mz[dist] - 2.f * Mz[dist - 1] + Mz[dist - 2];
+            const float A = (1.f - r) * (1.f - r);
+            const float q = (dist - 2 < TBC_NPOW) ? (float)c_tbc_rpow[dist - 2] : 0.f;
+            const float den = A * (1.f - q * q);
+            const float alpha = (-L + q * R) / den, beta = (-R + q * L) / den;
+            __syncthreads();
+            if (tid < TBC_NPOW) {
+                const int i = tid;
+                if (i <= dist) {
+                    float corr = alpha * (float)c_tbc_rpow[i];
+                    if (dist - i < TBC_NPOW) corr += beta * (float)c_tbc_rpow[dist - i];
+                    Ms[lead + i] += corr;
+                }
+            } else if (tid < 2 * TBC_NPOW) {
+                const int k = tid - TBC_NPOW, i = dist - k;
+                if (i >= TBC_NPOW) Ms[lead + i] += beta * (float)c_tbc_rpow[k];
+            }
+        }
+        __syncthreads();
+        // evaluate: positions in float64, polynomial in float32, the affine map to the uint16 scale folded into one FMA
+        const double ibd = (double)(long long)g.b;
+        const double fb = g.b - ibd;
+        const double stop = (g.e - g.b) + fb;
+        const int W = p.outwidth;
+        const double step = (stop - fb) / (double)W;
+        const double wowf = p.wow ? (g.e - g.b) / (double)p.linelen : 1.0;
+        // v = ((S + add) wow - ire0) / hz_ire - vsync_ire) * out_scale + out_off  =  S * ka + kb
+        const double k1 = p.out_scale / p.hz_ire;
+        const float ka = (float)(wowf * k1);
+        const float kb = (float)((p.plane_add * wowf - p.ire0) * k1 - p.vsync_ire * p.out_scale + p.out_off);
+        const float sixth = 1.f / 6.f;
+        const int field = g.field, line = g.line;
+        const int linecount = p.linecount[field];
+        unsigned short* outl = (unsigned short*)p.out + (p.field_off ? (size_t)p.field_off[field] : (size_t)field * (size_t)p.out_stride) +
+                               (size_t)line * (size_t)p.line_stride;
+        const float* Mz = Ms + lead;
+        const float* yz = ys + lead;
+        for (int j = tid; j < W; j += TBF_THREADS) {
+            const double x = tbc_i2d(j) * step + fb;
+            int i = tbc_floor_nonneg(x);
+            if (i > dist - 1) i = dist - 1;
+            const float t = (float)(x - tbc_i2d(i)), u = 1.f - t;
+            const float Mi6 = Mz[i] * sixth, Mj6 = Mz[i + 1] * sixth;
+            const float S = u * fmaf(Mi6, fmaf(u, u, -1.f), yz[i]) + t * fmaf(Mj6, fmaf(t, t, -1.f), yz[i + 1]);
+            float v = fmaf(S, ka, kb);
+            v = v < 0.f ? 0.f : (v > 65535.f ? 65535.f : v);
+            unsigned short q16 = (unsigned short)(int)(v + 0.5f);
+            if (p.burstlevel && line >= 1 && line < linecount - 1 && j < 2) {
+                float bl = p.burstlevel[(size_t)field * p.ll_stride + line];
+                if (j == 0) q16 = bl > 0.f ? 16384 : 32768;
+                else q16 = (unsigned short)(p.clevel_k * fabsf(bl));
+            }
+            outl[j] = q16;
+        }
+        __syncthreads();        // everybody is done with ys[cur] / Ms before the next iteration's copy and recursions
+    }
+}
+
 }  // namespace ldd
 
 using namespace ldd;
@@ -288,9 +540,25 @@ extern "C" int ldd_tbc_fields_ex(ldd_handle* h, const float* plane_dev, long lon
         cudaMemcpyToSymbol(c_tbc_rpow, rp, sizeof rp);
         h->tbc_taps_set = true;
     }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 1 && c.precision != LDD_PREC_F64 && !getenv("LDD_TBC_F64")) {
+        // float32 lanes: bulk-copy staged, persistent CTAs
+        int maxu = (p.maxd + 1 + 2 * TBC_H + 3 + 3) & ~3;
+        if (maxu > TBF_MAXU) { maxu = TBF_MAXU; p.maxd = TBF_MAXU - 2 * TBC_H - 8; }
+        const size_t smem32 = (size_t)(3 * maxu + 32 + 2 * TBF_THREADS) * sizeof(float);
+        cudaFuncSetAttribute(tbc_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+        cudaFuncSetAttribute(tbc_f32_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        const int nitems = nfields * max_linecount;
+        int per_sm = (int)((h->smem_optin + 1024) / (smem32 + 1024));
+        if (per_sm > 4) per_sm = 4;                  // 64 registers x 256 threads: four CTAs per SM
+        if (per_sm < 1) per_sm = 1;
+        int grid = h->sm_count * per_sm;
+        if (grid > nitems) grid = nitems;
+        LDD_LAUNCH(tbc_f32_kernel, dim3(grid), dim3(TBF_THREADS), smem32, st, p, nitems, max_linecount, maxu);
+        return launch_status(h, "tbc_f32_kernel");
+    }
     cudaFuncSetAttribute(tbc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(tbc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);      // several CTAs of ~50 KB per SM
-    cudaStream_t st = (cudaStream_t)stream;
     LDD_LAUNCH(tbc_kernel, dim3(max_linecount, nfields), dim3(TBC_THREADS), smem, st, p);
     return launch_status(h, "tbc_kernel");
 }

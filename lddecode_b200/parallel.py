@@ -104,7 +104,7 @@ class FieldGatherer:
             meta[:nloc, 0] = np.asarray(res.readsamples)[loc]
             meta[:nloc, 1] = infos['istop']
             meta[:nloc, 2] = infos['linecount']
-            in_place = self.cuda and res.d_pic is not None and res.d_pic.data_ptr() == pic.data_ptr()
+            in_place = res.d_pic is not None and hasattr(res.d_pic, "data_ptr") and res.d_pic.data_ptr() == pic.data_ptr()
             if not in_place:
                 # decoded into the decoder's own buffer: stage it
                 n = nloc * self.stride

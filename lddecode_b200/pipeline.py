@@ -339,7 +339,9 @@ class CaptureDecoder:
         return s
 
     def decode_stream(self, captures, sink=None):
-        """Software-pipelined decode() of a sequence of device-resident captures [(cap_dev, fmt, ncap), ...]:
+        """Software-pipelined decode() of a sequence of device-resident captures [(cap_dev, fmt, ncap), ...] or of ranges
+        of one resident capture window [(cap_dev, fmt, cap_base, cap_len, ncap_total, r0, r1), ...] (decode_range's
+        arguments: how a shard that is longer than the plane workspace is worked through):
         capture k+1 is demodulated while the host walks capture k (one stream, two plane workspaces).
         Yields one RangeResult per capture; its device buffers stay valid until the second-next launch.
         sink (parallel.FieldGatherer): every capture's pictures are written straight into the sink's send buffer
@@ -349,9 +351,14 @@ class CaptureDecoder:
 
         def launch(c):
             nonlocal k
-            slot = self._slot(k % 2, c[2])
+            if len(c) == 3:                       # a whole capture as one range
+                c = (c[0], c[1], 0, c[2], c[2], 0, c[2] + 1)
+            cap_dev, fmt, cap_base, cap_len, ncap_total, r0, r1 = c
+            # plane workspace for the range's own block grid (not for the whole resident window)
+            span = min(cap_len, (r1 - r0) + self.readlen + int(1.6 * self.field_samples) + 4 * self.rf.blocklen)
+            slot = self._slot(k % 2, span)
             k += 1
-            return self._launch(self.rf, slot, c[0], c[1], 0, c[2], c[2], 0, c[2] + 1)
+            return self._launch(self.rf, slot, cap_dev, fmt, cap_base, cap_len, ncap_total, r0, r1)
 
         c = next(it, None)
         pend = launch(c) if c is not None else None
@@ -399,10 +406,6 @@ class CaptureDecoder:
         to pinned host memory, run the second audio stage."""
         be = rf._be
         rf._set_mtf(self.mtf_level)           # uploads the tables on first use; the level itself is set by the library
-        if slot.pic_free is not None:
-            # a streaming download of this slot's previous pictures may still be running
-            be.stream_wait_event(be.current_stream_obj(), slot.pic_free)
-            slot.pic_free = None
         rf._check(be.lib.ldd_pipe_launch(slot.h, be.ptr(cap_dev), int(fmt), int(cap_base), int(cap_len), int(ncap_total),
                                          int(r0), int(r1), int(self.readlen), float(self.mtf_level), int(bool(audio_phase2)),
                                          be.stream()))
@@ -424,6 +427,11 @@ class CaptureDecoder:
         be = rf._be
         main = be.stream()
         ref = C.c_void_p(side.cuda_stream) if side is not None else main
+        if slot.pic_free is not None and pic_out is None:
+            # a streaming download of this slot's previous pictures may still be running: the stream that rewrites
+            # them (not the demodulation of the next capture) waits for it
+            be.stream_wait_event(side if side is not None else be.current_stream_obj(), slot.pic_free)
+            slot.pic_free = None
         d_pic = slot.d_pic if pic_out is None else pic_out
         d_status = slot.d_status if status_out is None else status_out
         stride = slot.out_stride if pic_stride is None else int(pic_stride)

@@ -83,7 +83,7 @@ class SynthRF:
     CHUNK = 1 << 20
 
     def __init__(self, system="NTSC", fs_mhz=None, seed=0, bits=8, audio=True, clv=False,
-                 frame0=1, lead_lines=20, noise=0.5, random_luma=True):
+                 frame0=1, lead_lines=20, noise=0.5, random_luma=True, tile_frames=0):
         self.sp = sp = SYSTEMS[system]
         self.system = system
         if fs_mhz is None:
@@ -95,6 +95,7 @@ class SynthRF:
         self.frame0 = frame0
         self.noise = noise
         self.seed = seed
+        self.tile_frames = tile_frames        # > 0: picture content and codes repeat every tile_frames frames (TiledCapture)
         self.random_luma = random_luma
         self.slots = _slot_table(sp)
         self.kind = _line_kind(sp)
@@ -129,6 +130,8 @@ class SynthRF:
         th = (hl - ihl) * self.halfline * 1e6          # microseconds inside the half-line slot
         frame = np.floor(ihl / self.nhl).astype(np.int64)
         pos = (ihl - frame * self.nhl).astype(np.int64)
+        if self.tile_frames:
+            frame = frame % self.tile_frames
         typ = self.slots[pos]
         H_us = sp["line_period"] * 1e6
         half_us = H_us / 2
@@ -236,6 +239,95 @@ class SynthRF:
 
 def synth_capture(system="NTSC", nsamples=1200000, **kw):
     return SynthRF(system, **kw).generate(nsamples)
+
+
+class TiledCapture:
+    """An arbitrarily long NTSC CLV capture that is never materialised: a two-frame
+    baseband template -- the four-field colour sequence, 2 * 525 * 1820 = 1 911 000 samples at 8fsc, so the tiling is
+    period-exact -- FM-modulated ON THE DEVICE with a running carrier phase (no phase jump at tile seams), plus the two
+    analog audio carriers (closed-form phase) and seeded noise.  Sample n of the capture is a pure function of n, so
+    any window can be generated anywhere: every rank generates its own shard in HBM, and the parity tests regenerate
+    the windows they check on the host side of the same function.
+
+    Test / benchmark tooling built on torch ops; not part of the decoder and never timed."""
+
+    CHUNK = 1 << 24                                   # samples generated per pass (bounds the temporaries)
+
+    def __init__(self, seed=2, device="cuda", noise=0.5):
+        import torch
+        self.torch = torch
+        self.device = torch.device(device)
+        self.seed, self.noise = seed, noise
+        sp = NTSC
+        self.fs = 8 * 315e6 / 88
+        self.P = 2 * 525 * 1820
+        gen = SynthRF("NTSC", self.fs / 1e6, seed=seed, clv=True, audio=False, noise=0.0, tile_frames=2)
+        # three periods of filtered, pre-emphasised baseband; the middle one is the periodic steady state
+        hz, _ = gen._baseband_ire(0, 3 * self.P)
+        hz = sps.lfilter(gen.lpf[0], gen.lpf[1], hz)
+        hz = sps.lfilter(gen.emp[0], gen.emp[1], hz)
+        hz = hz[self.P:2 * self.P]
+        # phase advance up to and including sample t of the period, in cycles (float64; < 6e5 cycles per period)
+        cyc = np.cumsum(hz / self.fs)
+        self.cycles_per_period = float(cyc[-1])
+        self.tmpl = torch.from_numpy(cyc).to(self.device)
+        self.sp = sp
+
+    def generate(self, n0, n, out=None):
+        """Samples [n0, n0 + n) as a uint8 tensor on the device."""
+        torch = self.torch
+        if out is None:
+            out = torch.empty(n, dtype=torch.uint8, device=self.device)
+        done = 0
+        while done < n:
+            a = n0 + done
+            m = min(self.CHUNK, n - done)
+            out[done:done + m] = self._chunk(a, m)
+            done += m
+        return out
+
+    @staticmethod
+    def _mix64(torch, z):
+        """splitmix64 finaliser on int64 tensors (wrapping arithmetic, logical shifts by masking)."""
+        def s64(c):
+            return c - (1 << 64) if c >= (1 << 63) else c
+        z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * s64(0xBF58476D1CE4E5B9)
+        z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * s64(0x94D049BB133111EB)
+        return z ^ ((z >> 31) & ((1 << 33) - 1))
+
+    def _gauss(self, idx):
+        """N(0, 1) per sample as a pure function of (seed, sample index): counter-based hash + Box-Muller."""
+        torch = self.torch
+        k = (self.seed * 0x9E3779B97F4A7C15) & ((1 << 64) - 1)
+        k = k - (1 << 64) if k >= (1 << 63) else k              # as a signed 64-bit value (tensor arithmetic wraps)
+        a = self._mix64(torch, idx * 2 + 1 + k)
+        b = self._mix64(torch, idx * 2 + 2 + k)
+        u1 = (((a >> 11) & ((1 << 53) - 1)).to(torch.float64) + 0.5) / float(1 << 53)
+        u2 = ((b >> 11) & ((1 << 53) - 1)).to(torch.float64) / float(1 << 53)
+        return torch.sqrt(-2.0 * torch.log(u1)) * torch.cos(2 * np.pi * u2)
+
+    def _chunk(self, a, m):
+        torch = self.torch
+        dev = self.device
+        idx = torch.arange(a, a + m, dtype=torch.int64, device=dev)
+        tile = idx // self.P
+        t = idx - tile * self.P
+        # carrier phase in cycles, reduced before the sine: tile * frac(cycles per period) + template
+        fracp = self.cycles_per_period - np.floor(self.cycles_per_period)
+        cyc = self.tmpl[t] + torch.frac(tile.to(torch.float64) * fracp)
+        rf = 100.0 * torch.sin(2 * np.pi * torch.frac(cyc))
+        # audio carriers: f / fs = 146.25 / 1820 and 178.75 / 1820 cycles per sample (exactly periodic over 4 lines = 7280
+        # samples); FM by 1 kHz / 400 Hz tones with 50 kHz deviation: phase = carrier - (dev / f_tone) cos(2 pi f_tone t)
+        k4 = (idx % 7280).to(torch.float64)
+        # tone phases: f_tone / fs = 11 / 315000 (1 kHz) and 11 / 787500 (400 Hz) cycles per sample
+        p1 = ((idx * 11) % 315000).to(torch.float64) / 315000.0
+        p2 = ((idx * 11) % 787500).to(torch.float64) / 787500.0
+        pl = 146.25 / 1820.0 * k4 - (50000.0 / 1000.0) / (2 * np.pi) * torch.cos(2 * np.pi * p1)
+        pr = 178.75 / 1820.0 * k4 - (50000.0 / 400.0) / (2 * np.pi) * torch.cos(2 * np.pi * p2)
+        rf = rf + 10.0 * (torch.sin(2 * np.pi * torch.frac(pl)) + torch.sin(2 * np.pi * torch.frac(pr)))
+        if self.noise > 0:
+            rf = rf + self.noise * self._gauss(idx)
+        return torch.clamp(torch.round(rf) + 128.0, 0, 255).to(torch.uint8)
 
 
 # -- 10-bit packers (test-vector generators; inverse of the loaders in lddutils.py:150-229) -----

@@ -145,9 +145,9 @@ def test_block_geometry_sweep_parity(cuda_backend, blocklen, blockcut, precision
     fs = FS["NTSC"]
     need = 3 * blocklen + 60000
     cap = synth.SynthRF("NTSC", fs, seed=31).generate(need)
-    audio = blocklen <= 65536                           # audio_phase2 needs len >= blocklen
-    rf = rfdecode.RFDecode(fs, "NTSC", blocklen, decode_analog_audio=audio, precision=precision, _backend=cuda_backend)
-    dec = O.Decoder(fs, "NTSC", blocklen, analog_audio=audio)
+    # video planes only: a three-block window is shorter than audio_phase2's minimum (blocklen phase-1 samples)
+    rf = rfdecode.RFDecode(fs, "NTSC", blocklen, decode_analog_audio=False, precision=precision, _backend=cuda_backend)
+    dec = O.Decoder(fs, "NTSC", blocklen, analog_audio=False)
     if blockcut != 1024:
         rf.set_blockcut(blockcut)
         dec.blockcut = blockcut
@@ -155,10 +155,7 @@ def test_block_geometry_sweep_parity(cuda_backend, blocklen, blockcut, precision
     rfdecode.loader = lambda f, s, k: cap[s:s + k] if s + k <= len(cap) else None
     start = blockcut + 4321
     out = rf.demod(None, start, length, 1)
-    if audio and (length + blockcut) // (blocklen // len(rf.Filters['audio_lfilt'])) < blocklen:
-        pass                                            # too short for phase 2: the reference raises; not this test's subject
-    ov, oa = O.demod(dec, lambda s, k: cap[s:s + k] if s + k <= len(cap) else None, start, length, 1) if not audio else \
-        _oracle_demod_video_only(dec, cap, start, length)
+    ov, oa = O.demod(dec, lambda s, k: cap[s:s + k] if s + k <= len(cap) else None, start, length, 1)
     assert out is not None
     video = out[0]
     assert len(video) == len(ov["demod"])
@@ -169,13 +166,3 @@ def test_block_geometry_sweep_parity(cuda_backend, blocklen, blockcut, precision
         else:
             np.testing.assert_allclose(video[p], ov[p], rtol=tol, atol=4.0 if precision == "mixed" else 0.2)
     assert O.sync_peaks(video["demod_sync"], 0, rf.linelen) == O.sync_peaks(ov["demod_sync"], 0, dec.linelen)
-
-
-def _oracle_demod_video_only(dec, cap, start, length):
-    """O.demod without its audio phase 2 (which needs more phase-1 samples than a 2-block window has)."""
-    saved = dec.analog_audio
-    try:
-        dec.analog_audio = False
-        return O.demod(dec, lambda s, k: cap[s:s + k] if s + k <= len(cap) else None, start, length, 1)
-    finally:
-        dec.analog_audio = saved

@@ -154,3 +154,14 @@ def test_two_rank_gloo_gather():
                        env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "GATHER_OK 4" in r.stdout, r.stdout[-3000:]
+
+
+def test_two_rank_strong_scaling_gloo():
+    """world_size 2 over gloo: one tiled capture sharded by block range, chunked per rank, gathered per chunk."""
+    script = os.path.join(ROOT, "tests", "dist_strong_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", script],
+                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "STRONG_OK" in r.stdout, r.stdout[-3000:]

@@ -9,7 +9,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
-from lddecode_b200 import pipeline, rfdecode
+from lddecode_b200 import _lib, pipeline, rfdecode
 
 lanes = [a for a in sys.argv[1:] if a in ("f32", "f64", "mixed")] or ["mixed"]
 system = "NTSC" if "NTSC" in sys.argv else "PAL"
@@ -20,13 +20,13 @@ for lane in lanes:
     rf = rfdecode.RFDecode(bench.FS[system], system, bench.BLOCKLEN, decode_analog_audio=audio, device=0, precision=lane)
     cd = pipeline.CaptureDecoder(rf)
     for _ in range(3):
-        total = bench.demod_only(cd, cap_dev, ncap)
+        total = bench.demod_only(cd, cap_dev, _lib.FMT_U8, ncap)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ts = []
     for _ in range(10):
         e0.record()
-        bench.demod_only(cd, cap_dev, ncap)
+        bench.demod_only(cd, cap_dev, _lib.FMT_U8, ncap)
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))

@@ -64,11 +64,21 @@ h_out.copy_(d_out, non_blocking=True); torch.cuda.synchronize()
 e0.record(); h_out.copy_(d_out, non_blocking=True); e1.record(); torch.cuda.synchronize()
 print("D2H 36 MB alone: %.3f ms (%.1f GB/s)" % (e0.elapsed_time(e1), (36 << 20) / e0.elapsed_time(e1) / 1e6))
 
-for obj, names in ((sd, ("upload", "launch", "finish", "fetch")), (cd, ("_walk", "_launch_demod"))):
+for obj, names in ((sd, ("upload", "launch", "finish", "fetch")), (cd, ("_launch", "_finish"))):
     for n in names:
         wrap(obj, n)
-wrap(pipeline.F, "refine_and_tbc")
-wrap(pipeline.F.PendingPeaks, "result", "peaks_wait")
+# inside _finish: the library call (peak wait + walk + launches) against the Python around it
+_orig = rf._be.lib.ldd_pipe_finish
+
+
+def _timed_finish(*a):
+    t = time.perf_counter()
+    r = _orig(*a)
+    acc["ldd_pipe_finish"] = acc.get("ldd_pipe_finish", 0.0) + time.perf_counter() - t
+    return r
+
+
+rf._be.lib.ldd_pipe_finish = _timed_finish
 N = 30
 torch.cuda.synchronize()
 t0 = time.perf_counter()

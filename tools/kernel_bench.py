@@ -66,8 +66,8 @@ def main():
     for prec in ("f64", "f32", "mixed"):
         rf = rfdecode.RFDecode(bench.FS[system], system, 16384, decode_analog_audio=False, precision=prec)
         cd = pipeline.CaptureDecoder(rf, max_fields=256)
-        total = bench.demod_only(cd, cap_dev, ncap)
-        ms = timeit(lambda: bench.demod_only(cd, cap_dev, ncap))
+        total = bench.demod_only(cd, cap_dev, _lib.FMT_U8, ncap)
+        ms = timeit(lambda: bench.demod_only(cd, cap_dev, _lib.FMT_U8, ncap))
         nplanes32 = 4 if system == "PAL" else 3
         bps = 16384 / 15328 + 4 * nplanes32 + 8
         rec("demod_kernel<%s> (fused block demodulation, N=16384)" % prec, ms, bps * total, "%.2f B per sample; %.0f Msamples/s" % (bps, total / ms / 1e3))
@@ -109,7 +109,14 @@ def main():
     ms = timeit(lambda: lib.ldd_tbc_fields(rf._h, be.ptr(planes['demod']), total, float(rf.SysParams['ire0']), be.ptr(d['base']), be.ptr(d_l3), F.LL_STRIDE,
                                            be.ptr(d['linecount']), n, int(sub.linecount.max()), 3 if system == "PAL" else 1, 0.0, W, 1, 1, be.ptr(d_pic),
                                            res.out_stride, None, 1.45, be.ptr(d_st), be.stream()))
-    rec("tbc_kernel (not-a-knot spline resample -> uint16)", ms, lines * (rf.linelen * 4 + W * 2), "4 B per input sample of the line + 2 B per output sample")
+    import ctypes
+    rec("tbc_f32_kernel (not-a-knot spline resample -> uint16, bulk-copy staged, default lane)", ms, lines * (rf.linelen * 4 + W * 2), "4 B per input sample of the line + 2 B per output sample")
+    os.environ["LDD_TBC_F64"] = "1"
+    ms = timeit(lambda: lib.ldd_tbc_fields(rf._h, be.ptr(planes['demod']), total, float(rf.SysParams['ire0']), be.ptr(d['base']), be.ptr(d_l3), F.LL_STRIDE,
+                                           be.ptr(d['linecount']), n, int(sub.linecount.max()), 3 if system == "PAL" else 1, 0.0, W, 1, 1, be.ptr(d_pic),
+                                           res.out_stride, None, 1.45, be.ptr(d_st), be.stream()))
+    del os.environ["LDD_TBC_F64"]
+    rec("tbc_kernel (float64 spline, exact lane)", ms, lines * (rf.linelen * 4 + W * 2), "4 B per input sample of the line + 2 B per output sample")
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "kernel_bench_%s.json" % system), "w"), indent=1)
 
 

@@ -587,10 +587,12 @@ def run_strong(a, rank, world, local, dist, seconds=None, steps=None):
     tc = synth.TiledCapture(seed=2, device="cuda")
     cap_dev = tc.generate(lo, hi - lo)
     torch.cuda.synchronize()
-    chunk = one_second("NTSC")
-    edges = list(range(R0, min(R1, ncap), chunk))
-    ranges = [(cap_dev, _lib.FMT_U8, lo, hi - lo, ncap, r0, min(r0 + chunk, R1)) for r0 in edges]
-    ranges[-1] = ranges[-1][:6] + (R1,)
+    # the same number of chunks on every rank (one gather per chunk): ~1 s of capture each, at most 1.25 s
+    shard = ncap // world + 1
+    nch = max(1, -(-shard // int(1.25 * one_second("NTSC"))))
+    chunk = -(-shard // nch)
+    edges = [R0 + i * chunk for i in range(nch)] + [R1]
+    ranges = [(cap_dev, _lib.FMT_U8, lo, hi - lo, ncap, edges[i], edges[i + 1]) for i in range(nch)]
     max_fields = 80
     gatherer = parallel.FieldGatherer(cd, rank, world, max_fields, dist) if world > 1 else None
 

@@ -271,113 +271,135 @@ struct BurstParams {
 constexpr int BURST_K = 32;          // same Green's function reach as the TBC kernel
 constexpr int BURST_FIRST = 20, BURST_N = 40;
 constexpr int BURST_WIN = 192;       // input samples staged per line (>= 2*(FIRST+N)*max step + K + margin)
-constexpr int BURST_WARPS = 8;       // lines per CTA of the per-line kernel
+constexpr int BURST_WARPS = 8;       // warps per CTA of the per-line kernel
+constexpr int BURST_LPW = 4;         // lines per warp: the CTA covers 32 lines, one per lane of warp 0 in the scalar phase
+constexpr int BURST_LPC = BURST_WARPS * BURST_LPW;
+constexpr int BURST_PITCH = BURST_N + 1;   // row pitch of the per-line sample arrays (odd: lanes on different lines do not collide)
 constexpr int BURST_VOTE_THREADS = 512;
 
 // w[m] = 6 (g[m-1] - 2 g[m] + g[m+1]), g[k] = r^|k| / (2 sqrt 3) truncated to |k| <= BURST_K: set once per process.
 __constant__ double c_burst_taps[2 * BURST_K + 3];
 
-// Per line (one warp each, grid over all lines of all fields): the resampled burst, its level, and the two
-// phase candidates of the line (lddecode_core.py:1061-1110).  ws_phase: [nfields][2][ll_stride].
+// Per line: the resampled burst, its level, and the two phase candidates of the line (lddecode_core.py:1061-1110).
+// ws_phase: [nfields][2][ll_stride].  Two phases per CTA of 32 lines: (A) warp-cooperative, four lines per warp -- stage
+// the line's window, second derivatives of the spline where the 40 output samples fall, the 40 samples; (B) the
+// scalar statistics and the zero-crossing walk of the reference, one LINE PER LANE of warp 0 (they are sequential per
+// line but independent between lines; one lane per warp doing them was most of this kernel's time).
 __global__ void __launch_bounds__(32 * BURST_WARPS) burst_lines_kernel(const BurstParams p, double* ws_phase) {
     __shared__ double ys[BURST_WARPS][BURST_WIN];
     __shared__ double Ms[BURST_WARPS][BURST_WIN];
-    __shared__ double bas[BURST_WARPS][BURST_N];
+    __shared__ double bas[BURST_LPC][BURST_PITCH];
+    __shared__ double sq[BURST_LPC][BURST_PITCH];
+    __shared__ unsigned char s_ok[BURST_LPC];
     const int f = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int l = blockIdx.x * BURST_WARPS + warp;
     const int linecount = p.linecount[f], nll = linecount + 4;
-    if (l >= nll) return;
     const long long base = p.base[f];
     const double* lin = p.linelocs_in + (size_t)f * p.ll_stride;
+    const int W = p.outwidth;
+    // ---- phase A
+    for (int q = 0; q < BURST_LPW; ++q) {
+        const int slot = warp * BURST_LPW + q;
+        const int l = blockIdx.x * BURST_LPC + slot;
+        bool ok = false;
+        if (l < linecount) {
+            const double b = lin[l], e = lin[l + 1];
+            const long long ib = (long long)b, ie = (long long)e;
+            const int dist = (int)(ie - ib);
+            const double fb = b - (double)ib;
+            const double step = (((e - b) + fb) - fb) / (double)W;
+            const double wowf = (e - b) / (double)p.linelen;
+            // input samples needed: x in [fb + 20 step, fb + 59 step] -> indices i0..i1+1, M needs +-(K+1) more
+            const int i0 = (int)(fb + BURST_FIRST * step), i1 = (int)(fb + (BURST_FIRST + BURST_N - 1) * step) + 1;
+            const int s0 = i0 - (BURST_K + 1);                 // first staged sample (line-relative, may be < 0)
+            const int ns = (i1 - i0 + 1) + 2 * (BURST_K + 1);
+            ok = (b >= 0.0) && dist >= 3 && ns <= BURST_WIN && i1 <= dist && i0 >= 30 && ib + dist + 1 <= p.n;
+            if (!ok) {
+                // geometry the fast path does not cover (or the reference would raise): flag, leave the line "no burst"
+                if (lane == 0) atomicOr(&p.status[f], 4);
+            } else {
+                for (int k = lane; k < ns; k += 32) {
+                    long long s = base + ib + s0 + k;
+                    s = s < 0 ? 0 : (s >= p.n ? p.n - 1 : s);
+                    ys[warp][k] = (double)p.burst[s];
+                }
+                __syncwarp();
+                const int nm = i1 - i0 + 1;                         // M[i0 .. i1]
+                for (int k = lane; k < nm; k += 32) {
+                    double acc = 0.0;
+                    const double* y = &ys[warp][k];                 // y[(i0+k) - (K+1)] is ys[k]
+                    for (int m = 0; m <= 2 * (BURST_K + 1); ++m) acc += c_burst_taps[m] * y[m];
+                    Ms[warp][k] = acc;
+                }
+                __syncwarp();
+                for (int j = lane; j < BURST_N; j += 32) {
+                    double x = (double)(BURST_FIRST + j) * step + fb;
+                    int i = (int)x;
+                    double t = x - (double)i, u = 1.0 - t;
+                    double Mi = Ms[warp][i - i0], Mj = Ms[warp][i + 1 - i0];
+                    double yi = ys[warp][i - s0], yj = ys[warp][i + 1 - s0];
+                    double S = Mi * u * u * u / 6.0 + Mj * t * t * t / 6.0 + (yi - Mi / 6.0) * u + (yj - Mj / 6.0) * t;
+                    bas[slot][j] = S * wowf;
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0) s_ok[slot] = ok ? 1 : 0;
+    }
+    __syncthreads();
+    // ---- phase B: lane <-> line
+    if (warp != 0) return;
+    const int l = blockIdx.x * BURST_LPC + lane;
+    if (l >= nll) return;
     float* level = p.burstlevel + (size_t)f * p.ll_stride;
     double* ph0 = ws_phase + (size_t)f * 2 * p.ll_stride;
     double* ph1 = ph0 + p.ll_stride;
     float lev_out = 0.f;
     double p0 = 0.0, p1 = 0.0;
     const double hz_ire = 1700000.0 / 140.0;
-    const int W = p.outwidth;
-    if (l < linecount) {
-        const double b = lin[l], e = lin[l + 1];
-        const long long ib = (long long)b, ie = (long long)e;
-        const int dist = (int)(ie - ib);
-        const double fb = b - (double)ib;
-        const double step = (((e - b) + fb) - fb) / (double)W;
-        const double wowf = (e - b) / (double)p.linelen;
-        // input samples needed: x in [fb + 20 step, fb + 59 step] -> indices i0..i1+1, M needs +-(K+1) more
-        const int i0 = (int)(fb + BURST_FIRST * step), i1 = (int)(fb + (BURST_FIRST + BURST_N - 1) * step) + 1;
-        const int s0 = i0 - (BURST_K + 1);                 // first staged sample (line-relative, may be < 0)
-        const int ns = (i1 - i0 + 1) + 2 * (BURST_K + 1);
-        bool ok = (b >= 0.0) && dist >= 3 && ns <= BURST_WIN && i1 <= dist && i0 >= 30 && ib + dist + 1 <= p.n;
-        if (!ok) {
-            // geometry the fast path does not cover (or the reference would raise): flag, leave the line "no burst"
-            if (lane == 0) atomicOr(&p.status[f], 4);
-        } else {
-            for (int k = lane; k < ns; k += 32) {
-                long long s = base + ib + s0 + k;
-                s = s < 0 ? 0 : (s >= p.n ? p.n - 1 : s);
-                ys[warp][k] = (double)p.burst[s];
-            }
-            __syncwarp();
-            const int nm = i1 - i0 + 1;                         // M[i0 .. i1]
-            for (int k = lane; k < nm; k += 32) {
-                double acc = 0.0;
-                const double* y = &ys[warp][k];                 // y[(i0+k) - (K+1)] is ys[k]
-                for (int m = 0; m <= 2 * (BURST_K + 1); ++m) acc += c_burst_taps[m] * y[m];
-                Ms[warp][k] = acc;
-            }
-            __syncwarp();
-            for (int j = lane; j < BURST_N; j += 32) {
-                double x = (double)(BURST_FIRST + j) * step + fb;
-                int i = (int)x;
-                double t = x - (double)i, u = 1.0 - t;
-                double Mi = Ms[warp][i - i0], Mj = Ms[warp][i + 1 - i0];
-                double yi = ys[warp][i - s0], yj = ys[warp][i + 1 - s0];
-                double S = Mi * u * u * u / 6.0 + Mj * t * t * t / 6.0 + (yi - Mi / 6.0) * u + (yj - Mj / 6.0) * t;
-                bas[warp][j] = S * wowf;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                double* ba = bas[warp];
-                double mean = np_mean(ba, BURST_N);
-                for (int k = 0; k < BURST_N; ++k) ba[k] -= mean;
-                double mx = 0.0;
-                for (int k = 0; k < BURST_N; ++k) mx = fabs(ba[k]) > mx ? fabs(ba[k]) : mx;
-                float lev = (float)mx;
-                // np.std(ba): mean again, deviations, pairwise sum of squares
-                double m2 = np_mean(ba, BURST_N);
-                double dev[BURST_N];
-                for (int k = 0; k < BURST_N; ++k) { double q = ba[k] - m2; dev[k] = q * q; }
-                double sd = sqrt(np_sum(dev, BURST_N) / (double)BURST_N);
-                const float hz_ire32 = (float)hz_ire;
-                if (!((lev / hz_ire32) > 30.f || (sd / hz_ire) < 3)) {
-                    lev_out = lev;
-                    const double thr = (double)(lev * 0.6f);
-                    double offF[BURST_N], offT[BURST_N];
-                    int nF = 0, nT = 0;
-                    auto dat = [&](long long k) -> double { return ba[k]; };
-                    int bi = 0;
-                    while (bi < BURST_N) {
-                        if (fabs(ba[bi]) > thr) {
-                            double zc;
-                            if (calczc(dat, BURST_N, bi, 0.0, 10, &zc)) {
-                                double off = zc - ((floor(zc / 4) * 4) - 1);
-                                if (off > 3.5) off -= 4;
-                                if (ba[bi] > 0) offT[nT++] = off; else offF[nF++] = off;
-                                bi = (int)zc;
-                            }
-                        }
-                        ++bi;
-                    }
-                    if (nF >= 3 && nT >= 3) {
-                        double mF = np_mean(offF + 1, nF - 2), mT = np_mean(offT + 1, nT - 2);
-                        if (l % 2) { p0 = 2 - mT; p1 = 2 - mF; }
-                        else { p0 = 2 - mF; p1 = 2 - mT; }
+    if (l < linecount && s_ok[lane]) {
+        double* ba = bas[lane];
+        double* dev = sq[lane];
+        double mean = np_mean(ba, BURST_N);
+        for (int k = 0; k < BURST_N; ++k) ba[k] -= mean;
+        double mx = 0.0;
+        for (int k = 0; k < BURST_N; ++k) mx = fabs(ba[k]) > mx ? fabs(ba[k]) : mx;
+        float lev = (float)mx;
+        // np.std(ba): mean again, deviations, pairwise sum of squares
+        double m2 = np_mean(ba, BURST_N);
+        for (int k = 0; k < BURST_N; ++k) { double q = ba[k] - m2; dev[k] = q * q; }
+        double sd = sqrt(np_sum(dev, BURST_N) / (double)BURST_N);
+        const float hz_ire32 = (float)hz_ire;
+        if (!((lev / hz_ire32) > 30.f || (sd / hz_ire) < 3)) {
+            lev_out = lev;
+            const double thr = (double)(lev * 0.6f);
+            // phase offsets of the falling / rising crossings, kept in the (now free) deviation row: F from the
+            // front, T from the back
+            double* offF = dev;
+            double offT[BURST_N / 2 + 1];
+            int nF = 0, nT = 0;
+            auto dat = [&](long long k) -> double { return ba[k]; };
+            int bi = 0;
+            while (bi < BURST_N) {
+                if (fabs(ba[bi]) > thr) {
+                    double zc;
+                    if (calczc(dat, BURST_N, bi, 0.0, 10, &zc)) {
+                        double off = zc - ((floor(zc / 4) * 4) - 1);
+                        if (off > 3.5) off -= 4;
+                        if (ba[bi] > 0) { if (nT < BURST_N / 2 + 1) offT[nT] = off; ++nT; } else { if (nF < BURST_N) offF[nF] = off; ++nF; }
+                        bi = (int)zc;
                     }
                 }
+                ++bi;
+            }
+            if (nT > BURST_N / 2 + 1) nT = BURST_N / 2 + 1;
+            if (nF >= 3 && nT >= 3) {
+                double mF = np_mean(offF + 1, nF - 2), mT = np_mean(offT + 1, nT - 2);
+                if (l % 2) { p0 = 2 - mT; p1 = 2 - mF; }
+                else { p0 = 2 - mF; p1 = 2 - mT; }
             }
         }
     }
-    if (lane == 0) { level[l] = lev_out; ph0[l] = p0; ph1[l] = p1; }
+    level[l] = lev_out; ph0[l] = p0; ph1[l] = p1;
 }
 
 // Per field: the phase group vote (medians of both candidate columns over the lines that produced one,
@@ -1006,7 +1028,7 @@ extern "C" int ldd_refine_burst(ldd_handle* h, const float* burst_dev, long long
         h->burst_taps_set = true;
     }
     double* ws = (double*)h->pilot_ws;
-    LDD_LAUNCH(burst_lines_kernel, dim3((ll_stride + BURST_WARPS - 1) / BURST_WARPS, nfields), dim3(32 * BURST_WARPS), 0, st, p, ws);
+    LDD_LAUNCH(burst_lines_kernel, dim3((ll_stride + BURST_LPC - 1) / BURST_LPC, nfields), dim3(32 * BURST_WARPS), 0, st, p, ws);
     LDD_LAUNCH(burst_vote_kernel, dim3(nfields), dim3(BURST_VOTE_THREADS), 0, st, p, (const double*)ws);
     return launch_status(h, "burst kernels");
 }

@@ -177,6 +177,10 @@ int ldd_create(const ldd_config* cfg, ldd_handle** out) {
         // second pass of the mixed lane: float64, global scratch, one CTA per SM
         h->scratch64_per_cta = (size_t)3 * M * sizeof(Cx<double>);
         CUDA_TRY(h, cudaMalloc(&h->scratch64, (size_t)h->sm_count * h->scratch64_per_cta));
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_queue, 2 * sizeof(int)));
+        const char* es = getenv("LDD_SPARE_SMS");
+        if (es) h->spare_sms = atoi(es);
+        if (h->spare_sms < 0 || h->spare_sms > 64) h->spare_sms = 4;
         const char* em = getenv("LDD_FLAG_MARGIN_HZ");
         if (em) h->flag_margin = atof(em);
     }
@@ -210,6 +214,7 @@ void ldd_destroy(ldd_handle* h) {
     cudaFree(h->d_mtf);
     cudaFree(h->scratch64);
     cudaFree(h->d_flags);
+    cudaFree(h->d_queue);
     cudaFree(h->peak_ws);
     cudaFree(h->pilot_ws);
     delete h;
@@ -412,23 +417,36 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
         p.flag_margin = h->flag_margin;
     }
     int rc;
-    if (lane == 0) rc = launch_demod_f64(p, grid, h->threads, st, h->sp_bytes);
-    else rc = launch_demod_f32(p, grid, h->threads, st, h->smem_bytes);
-    if (mixed && rc == LDD_OK) {
-        // second pass: float64 over the flagged blocks only; the list is read on the device, so there
-        // is no host round trip -- an idle launch costs a few microseconds when nothing was flagged
-        DemodParams q = p;
+    h->last_fused = false;
+    DemodParams q = p;
+    if (mixed) {
+        // float64 parameter set of the re-run: only the sync decision (demod_05 -> demod_sync) is redone -- the float32
+        // planes of a flagged block are as good as those of its neighbours
         q.WM = h->d_WM[0]; q.WN = h->d_WN[0]; q.Hv = h->d_Hv[0];
         for (int m = 0; m < nfilt; ++m) q.F[m] = h->d_F[m][0];
         q.AL = h->d_AL[0]; q.AR = h->d_AR[0];
         q.scratch = h->scratch64; q.scratch_per_cta = h->scratch64_per_cta;
-        q.flag_list = nullptr; q.flag_count = nullptr;
-        q.block_count = h->d_flags; q.block_list = h->d_flags + 1;
-        // the float32 planes of a flagged block are as good as those of its neighbours: only the sync decision
-        // (demod_05 -> demod_sync) is redone
+        q.flag_list = nullptr; q.flag_count = nullptr; q.flag_margin = 0.0;
         q.only05 = 1; q.A = 0;
-        int g64 = (int)(nblocks < h->sm_count ? nblocks : h->sm_count);
-        rc = launch_demod_f64(q, g64, 512, st, h->sp_bytes);
+    }
+    if (mixed && h->d_queue && demod_mixed_fused_ok(p, h->threads, h->smem_bytes, h->sp_bytes)) {
+        // one launch: dynamic block queue, flagged blocks re-run in float64 by the CTA that found them
+        CUDA_TRY(h, cudaMemsetAsync(h->d_queue, 0, 2 * sizeof(int), st));
+        p.flag_list = nullptr; p.flag_count = nullptr;
+        int g = (int)(nblocks < h->sm_count ? nblocks : h->sm_count);
+        if (!getenv("LDD_FULL_GRID") && g > 8) g -= h->spare_sms;      // a few SMs stay free for the side-stream kernels / NCCL
+        rc = launch_demod_mixed(p, q, h->d_queue, g, st, h->smem_bytes);
+        h->last_fused = true;
+    } else {
+        if (lane == 0) rc = launch_demod_f64(p, grid, h->threads, st, h->sp_bytes);
+        else rc = launch_demod_f32(p, grid, h->threads, st, h->smem_bytes);
+        if (mixed && rc == LDD_OK) {
+            // second pass: float64 over the flagged blocks only; the list is read on the device, so there
+            // is no host round trip -- an idle launch costs a few microseconds when nothing was flagged
+            q.block_count = h->d_flags; q.block_list = h->d_flags + 1;
+            int g64 = (int)(nblocks < h->sm_count ? nblocks : h->sm_count);
+            rc = launch_demod_f64(q, g64, 512, st, h->sp_bytes);
+        }
     }
 #ifndef LDD_EMU
     if (h->l2_window) {
@@ -446,7 +464,7 @@ int ldd_mixed_stats(ldd_handle* h, long long* flagged_blocks, long long* total_b
     *total_blocks = h->last_nblocks;
     if (h->cfg.precision != LDD_PREC_MIXED || !h->d_flags) return LDD_OK;
     int n = 0;
-    CUDA_TRY(h, cudaMemcpy(&n, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemcpy(&n, h->last_fused ? h->d_queue + 1 : h->d_flags, sizeof(int), cudaMemcpyDeviceToHost));
     *flagged_blocks = n;
     return LDD_OK;
 }

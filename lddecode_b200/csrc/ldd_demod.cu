@@ -215,8 +215,32 @@ __device__ inline void tangle_static(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __re
 // bound by L2 traffic, ~7 TB/s chip-wide at 9 Gsamples/s).
 // CM != 0: the transform length M is the compile-time constant CM (and blockDim.x == NT, plan = radix 16
 // while possible): the default block length gets fully constant-folded indexing.
-template <class T, int NT, bool PAD, int MINB = 1, bool SP = false, int CM = 0>
-__global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
+// Per-kernel constants of the sync scan (step J): a thread owns CH consecutive samples.
+struct ScanConsts {
+    int CH;
+    double c, Ach, A32, AchLane, AchLane1, cN, cn0;
+};
+
+__device__ inline ScanConsts scan_consts(const DemodParams& p, int N, int nthr, int tid) {
+    ScanConsts k;
+    k.CH = N / nthr;           // N and nthr are powers of two, CH >= 1
+    const int lane = tid & 31;
+    k.c = p.fp_c;
+    k.Ach = pow(k.c, (double)k.CH);
+    k.A32 = pow(k.Ach, 32.0);
+    k.AchLane = pow(k.Ach, (double)lane);
+    k.AchLane1 = pow(k.Ach, (double)(lane + 1));
+    k.cN = pow(k.c, (double)N);
+    k.cn0 = pow(k.c, (double)(tid * k.CH));
+    return k;
+}
+
+// One block of N samples through the whole chain.  smem: the dynamic shared memory of the CTA (block arrays when PAD,
+// the ping-pong partner when SP); scratch_slot: this CTA's slice of the global scratch (when !PAD); stw: per-thread
+// twiddles (compile-time plan, float32).  Returns (block-uniform) whether a demod_05 sample of the block lies within
+// p.flag_margin of a sync threshold (p.flag_margin > 0 only).  Ends with a barrier.
+template <class T, int NT, bool PAD, bool SP, int CM>
+__device__ inline int demod_block(const DemodParams& p, const int blk, char* smem, void* scratch_slot, Cx<T>* stw, const ScanConsts& sc) {
     const int tid = threadIdx.x, nthr = CM ? NT : (int)blockDim.x;
     const int M = CM ? CM : p.M, N = CM ? 2 * CM : p.N;
     const Cx<T>* WM = (const Cx<T>*)p.WM;
@@ -226,25 +250,16 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
     // PAD <=> the block arrays live in shared memory (decided at compile time so that the compiler can
     // keep every derived pointer in the shared address space: LDS/STS with 32-bit addresses instead of
     // generic loads with 64-bit address arithmetic)
-    LDD_DYN_SMEM(smem);
     Cx<T>* b0;
     Cx<T>* sp = nullptr;
     if (PAD) {
         b0 = (Cx<T>*)smem;
     } else {
-        b0 = (Cx<T>*)((char*)p.scratch + (size_t)blockIdx.x * p.scratch_per_cta);
+        b0 = (Cx<T>*)scratch_slot;
         if (SP) sp = (Cx<T>*)smem;
     }
     const bool sp_ok = SP && ((CM ? static_npass(CM ? CM : 2) : p.plan_m.npass) & 1) == 0;
-    // compile-time plan for 8192 points on 512 threads: per-thread twiddles in shared memory
     constexpr bool TW8K = (CM == 8192 && NT == 512 && sizeof(T) == 4);
-    Cx<T>* stw = nullptr;
-    if constexpr (TW8K) {
-        __shared__ Cx<T> s_tw[3 * NT];
-        stw = s_tw;
-        fft_tw_fill<T, CM, NT>(stw, WM, tid);
-        __syncthreads();
-    }
     // length-M transform of `a`; `other` is a free array usable as the partner when shared memory is not
     auto FFTM = [&](Cx<T>* a, Cx<T>* other) -> Cx<T>* {
         if constexpr (TW8K) {
@@ -263,19 +278,11 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
 #define IX(i) pidx<PAD>(i)
     __shared__ double s_warp[32];
     __shared__ double s_total;
-
-    // constants of the sync scan (step J): a thread owns CH consecutive samples
-    const int CH = N / nthr;           // N and nthr are powers of two, CH >= 1
+    const int CH = sc.CH;
     const int lane = tid & 31, warp = tid >> 5;
-    const double c = p.fp_c;
-    const double Ach = pow(c, (double)CH);
-    const double A32 = pow(Ach, 32.0);
-    const double AchLane = pow(Ach, (double)lane), AchLane1 = pow(Ach, (double)(lane + 1));
-    const double cN = pow(c, (double)N), cn0 = pow(c, (double)(tid * CH));
-
-    const int nwork = p.block_list ? *p.block_count : p.nblocks;
-    for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
-        const int blk = p.block_list ? p.block_list[wi] : wi;
+    const double c = sc.c, Ach = sc.Ach, A32 = sc.A32, AchLane = sc.AchLane, AchLane1 = sc.AchLane1, cN = sc.cN, cn0 = sc.cn0;
+    int flagged = 0;
+    {
         const long long in0 = p.first_sample + (long long)blk * p.stride;
         const long long o = (long long)blk * p.stride;
         long long copylen = p.stride;
@@ -575,12 +582,9 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
                 acc = c * acc + (p.fp_b0 * s + p.fp_b1 * sprev);
                 sprev = s;
                 // mixed lane: is this float32 sample close enough to a threshold that float64 could decide otherwise?
-                if (p.flag_list) near |= (fabs(v - p.sync_lo) < p.flag_margin) | (fabs(v - p.sync_hi) < p.flag_margin);
+                if (p.flag_margin > 0.0) near |= (fabs(v - p.sync_lo) < p.flag_margin) | (fabs(v - p.sync_hi) < p.flag_margin);
             }
-            if (p.flag_list) {
-                int any = __syncthreads_or(near);
-                if (any && tid == 0) { int at = atomicAdd(p.flag_count, 1); p.flag_list[at] = blk; }
-            }
+            if (p.flag_margin > 0.0) flagged = __syncthreads_or(near);
             // inclusive scan of the affine maps y -> Ach*y + acc over threads
             double incl = acc, mult = Ach;
             for (int d = 1; d < 32; d <<= 1) {
@@ -625,6 +629,61 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
         }
         __syncthreads();
     }
+    return flagged;
+#undef IX
+}
+
+// Persistent kernel of the single-precision lanes and of the exact lane: CTA b takes blocks b, b + grid, ...; with a
+// block list (second pass of the two-launch mixed lane) it takes the list's entries instead.
+template <class T, int NT, bool PAD, int MINB = 1, bool SP = false, int CM = 0>
+__global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
+    const int tid = threadIdx.x, nthr = CM ? NT : (int)blockDim.x;
+    LDD_DYN_SMEM(smem);
+    constexpr bool TW8K = (CM == 8192 && NT == 512 && sizeof(T) == 4);
+    Cx<T>* stw = nullptr;
+    if constexpr (TW8K) {
+        // compile-time plan for 8192 points on 512 threads: per-thread twiddles in shared memory
+        __shared__ Cx<T> s_tw[3 * NT];
+        stw = s_tw;
+        fft_tw_fill<T, CM, NT>(stw, (const Cx<T>*)p.WM, tid);
+        __syncthreads();
+    }
+    const ScanConsts sc = scan_consts(p, CM ? 2 * CM : p.N, nthr, tid);
+    void* slot = PAD ? nullptr : (void*)((char*)p.scratch + (size_t)blockIdx.x * p.scratch_per_cta);
+    const int nwork = p.block_list ? *p.block_count : p.nblocks;
+    for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+        const int blk = p.block_list ? p.block_list[wi] : wi;
+        const int fl = demod_block<T, NT, PAD, SP, CM>(p, blk, smem, slot, stw, sc);
+        if (p.flag_list && fl && tid == 0) { int at = atomicAdd(p.flag_count, 1); p.flag_list[at] = blk; }
+    }
+}
+
+// Mixed lane, default block length, ONE launch: blocks are handed out by an atomic counter; a CTA runs a block in float32
+// in shared memory and, when the block holds a demod_05 sample inside the guard band of a sync threshold, straight away
+// again in float64 (only demod_05 -> demod_sync; the float64 lane's arrays go to this CTA's slice of the L2-resident
+// scratch and the ping-pong partner into the shared memory the float32 arrays just vacated).  No second launch with its
+// single under-filled wave, and CTAs that drew re-runs simply draw fewer blocks.  pq: the float64 parameter set.
+template <int NT, int CM>
+__global__ void __launch_bounds__(NT, 1) demod_mixed_kernel(const DemodParams pf, const DemodParams pq, int* queue) {
+    const int tid = threadIdx.x;
+    LDD_DYN_SMEM(smem);
+    __shared__ Cx<float> s_tw[3 * NT];
+    __shared__ int s_blk;
+    fft_tw_fill<float, CM, NT>(s_tw, (const Cx<float>*)pf.WM, tid);
+    __syncthreads();
+    const ScanConsts sc = scan_consts(pf, 2 * CM, NT, tid);
+    void* slot64 = (void*)((char*)pq.scratch + (size_t)blockIdx.x * pq.scratch_per_cta);
+    for (;;) {
+        if (tid == 0) s_blk = atomicAdd(queue, 1);
+        __syncthreads();
+        const int blk = s_blk;
+        if (blk >= pf.nblocks) break;
+        const int fl = demod_block<float, NT, true, false, CM>(pf, blk, smem, nullptr, s_tw, sc);
+        if (fl) {
+            if (tid == 0) atomicAdd(queue + 1, 1);                    // statistics: blocks re-run
+            demod_block<double, NT, false, true, CM>(pq, blk, smem, slot64, nullptr, sc);
+        }
+    }
 }
 
 static int check_launch(const char* what) {
@@ -665,6 +724,17 @@ int launch_demod_f64(const DemodParams& p, int grid, int threads, cudaStream_t s
         case 2256: return launch_variant<double, 256, false, 2>(p, grid, st, 0);      // 2 CTAs of 256 threads per SM
         default: return launch_variant<double, 256, false>(p, grid, st, 0);
     }
+}
+
+bool demod_mixed_fused_ok(const DemodParams& p, int threads, size_t smem_bytes, size_t sp_bytes) {
+    return threads == 512 && smem_bytes && sp_bytes && sp_bytes <= smem_bytes && static_plan_ok(p, 8192) && !getenv("LDD_MIXED_TWO_LAUNCH");
+}
+
+int launch_demod_mixed(const DemodParams& pf, const DemodParams& pq, int* queue, int grid, cudaStream_t st, size_t smem_bytes) {
+    void (*kern)(const DemodParams, const DemodParams, int*) = demod_mixed_kernel<512, 8192>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    LDD_LAUNCH(kern, dim3(grid), dim3(512), smem_bytes, st, pf, pq, queue);
+    return check_launch("demod_mixed_kernel");
 }
 
 int launch_demod_f32(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t smem_bytes) {

@@ -67,6 +67,8 @@ inline int launch_status(ldd_handle* h, const char* what);
 
 int launch_demod_f64(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t sp_bytes);
 int launch_demod_f32(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t smem_bytes);
+bool demod_mixed_fused_ok(const DemodParams& p, int threads, size_t smem_bytes, size_t sp_bytes);
+int launch_demod_mixed(const DemodParams& pf, const DemodParams& pq, int* queue, int grid, cudaStream_t st, size_t smem_bytes);
 
 }  // namespace ldd
 
@@ -97,6 +99,9 @@ struct ldd_handle {
     void* scratch64 = nullptr;       // float64 scratch of the mixed lane's second pass
     size_t scratch64_per_cta = 0;
     int* d_flags = nullptr;          // [0] = count, [1..] = block indices
+    int* d_queue = nullptr;          // fused mixed kernel: [0] = next block to hand out, [1] = blocks re-run in float64
+    bool last_fused = false;
+    int spare_sms = 4;               // SMs the fused kernel leaves to concurrent streams
     size_t flags_cap = 0;
     double flag_margin = 16.0;       // Hz
     long long last_nblocks = 0;

@@ -96,6 +96,10 @@ int ldd_create(const ldd_config* cfg, ldd_handle** out) {
     if (!is_pow2(cfg->blocklen) || cfg->blocklen < 4096 || cfg->blocklen > 262144) return LDD_EINVAL;
     if (cfg->blockcut < 0 || cfg->blockcut_end < 0 || cfg->blockcut + cfg->blockcut_end >= cfg->blocklen / 2) return LDD_EINVAL;
     if (cfg->system != LDD_SYSTEM_NTSC && cfg->system != LDD_SYSTEM_PAL) return LDD_EINVAL;
+    // The refinement / TBC kernels stage fixed windows per line (4.7 us of pilot, 4 us around an hsync edge, the 40 burst
+    // samples, a line of up to 1.25 x nominal length): sized for 21 .. 40.5 MSPS (8fsc NTSC / PAL and the reference's
+    // 40 MSPS default).  Outside that range fields would be flagged invalid at run time: refuse the configuration instead.
+    if (!(cfg->freq_hz >= 21.0e6 && cfg->freq_hz <= 40.5e6) || cfg->linelen < 1200 || cfg->linelen > 2700 || cfg->outlinelen < 600) return LDD_EINVAL;
     if (ldd_device_count() <= cfg->device) return LDD_ECUDA;
     ldd_handle* h = new (std::nothrow) ldd_handle();
     if (!h) return LDD_ENOMEM;
@@ -320,7 +324,7 @@ int ldd_demod_range_query(ldd_handle* h, long long start, long long length, ldd_
 static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_base, long long rf_len,
                      long long first_sample, long long nblocks, long long total_out, int blockcut, long long S,
                      void* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev,
-                     long long audio1_len, void* stream) {
+                     long long audio1_len, void* stream, bool pad_last = false) {
     if (!h || !rf_dev || !planes_dev || nblocks < 0 || total_out < 0) return LDD_EINVAL;
     const ldd_config& c = h->cfg;
     const int N = c.blocklen, M = N / 2;
@@ -337,7 +341,7 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
     if (rf_base % group) return fail(h, LDD_EINVAL, "rf_base must be a multiple of %d for this format", group);
     if (nblocks == 0) return LDD_OK;
     long long last_needed = first_sample + (nblocks - 1) * S + N;
-    if (first_sample < rf_base || last_needed > rf_base + rf_len)
+    if (first_sample < rf_base || (pad_last ? last_needed - N >= rf_base + rf_len : last_needed > rf_base + rf_len))
         return fail(h, LDD_ESHORT, "capture too short: need [%lld,%lld), have [%lld,%lld)", first_sample, last_needed,
                     rf_base, rf_base + rf_len);
     for (int pidx = 0; pidx < (pal ? 5 : 4); ++pidx)
@@ -354,6 +358,7 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
     if (p.A) { p.plan_a = make_plan(p.A, h->radix_max); p.wstride_a = M / p.A; p.audio_ds = N / p.A; }
     p.rf = rf_dev; p.fmt = fmt;
     p.first_sample = first_sample - rf_base;
+    p.rf_limit = rf_len;
     p.stride = S;
     p.nblocks = (int)nblocks;
     p.WM = h->d_WM[lane]; p.WN = h->d_WN[lane]; p.Hv = h->d_Hv[lane];
@@ -478,6 +483,23 @@ int ldd_demod_blocks(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
     return run_demod(h, rf_dev, fmt, rf_base, rf_len, first_sample, nblocks, total_out, h->cfg.blockcut, S,
                      planes_dev, audio1_l_dev, audio1_r_dev, audio1_len, stream);
 }
+
+}  // extern "C"
+
+// ldd_demod_blocks whose LAST block may reach past the end of the capture (it reads zeros there): the range planner of
+// ldd_pipe_launch uses it where a capture does not end on the block grid, so that the planes cover every window the
+// reference can still read (its windows end at least blockcut_end samples before the end of the capture).
+int ldd::demod_blocks_padded(ldd_handle* h, const void* rf_dev, int fmt, long long rf_base, long long rf_len,
+                             long long first_sample, long long nblocks, long long total_out,
+                             void* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev,
+                             long long audio1_len, void* stream) {
+    if (!h) return LDD_EINVAL;
+    const long long S = h->cfg.blocklen - h->cfg.blockcut - h->cfg.blockcut_end;
+    return run_demod(h, rf_dev, fmt, rf_base, rf_len, first_sample, nblocks, total_out, h->cfg.blockcut, S,
+                     planes_dev, audio1_l_dev, audio1_r_dev, audio1_len, stream, true);
+}
+
+extern "C" {
 
 int ldd_demodblock(ldd_handle* h, const void* rf_dev, int fmt, long long rf_len,
                    void* const* planes_dev, double* audio_l_dev, double* audio_r_dev, void* stream) {

@@ -293,7 +293,20 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
 
         // A. samples -> z[n] = x[2n] + j x[2n+1]
         bool loaded = false;
+        if (in0 + N > p.rf_limit) {
+            // the last block of a capture whose end does not fall on the block grid: zeros beyond the end (the range
+            // planner only lets such a block in where the reference's own last window still has real samples to read)
+            for (int n = tid; n < M; n += nthr) {
+                const long long s = in0 + 2 * n;
+                const int s0 = s < p.rf_limit ? fetch_sample(p.rf, p.fmt, s) : 0;
+                const int s1 = s + 1 < p.rf_limit ? fetch_sample(p.rf, p.fmt, s + 1) : 0;
+                b0[IX(n)] = mk<T>((T)s0, (T)s1);
+            }
+            loaded = true;
+        }
         if constexpr (CM != 0) {
+            if (loaded) {
+            } else
             if (p.fmt == LDD_FMT_U8 && ((((uintptr_t)p.rf + (uintptr_t)in0) & 3) == 0)) {
                 // four samples per 32-bit load, all loads of a thread in flight together
                 constexpr int IT = CM / 2 / NT;

@@ -1236,5 +1236,12 @@ extern "C" int ldd_field_chain(ldd_handle* h, const long long* gpeaks, const dou
         readsample = next;
     }
     *nfields_out = nf;
+    if (nf >= max_fields && readsample < stop_readsample) {
+        // the table is full: an error only if the walk would have gone on (the next window is readable and on the planes)
+        ldd_range r;
+        if (ldd_demod_range_query(h, readsample, readlen, &r) == LDD_OK && r.last_needed <= ncap && r.first_sample - plane_origin >= 0 &&
+            r.first_sample - plane_origin + r.total_out <= plane_len)
+            return fail_msg(h, LDD_ECAP, "ldd_field_chain: max_fields reached before the end of the range");
+    }
     return LDD_OK;
 }

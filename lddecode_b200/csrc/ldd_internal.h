@@ -21,6 +21,7 @@ struct DemodParams {
     // input
     const void* rf;              // device pointer to the capture (format fmt)
     int fmt;
+    long long rf_limit;          // samples available in rf (relative to rf[0]); a block reaching past it reads zeros there
     long long first_sample;      // capture sample index of block 0
     long long stride;            // N - blockcut - blockcut_end
     int nblocks;
@@ -67,6 +68,10 @@ inline int launch_status(ldd_handle* h, const char* what);
 
 int launch_demod_f64(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t sp_bytes);
 int launch_demod_f32(const DemodParams& p, int grid, int threads, cudaStream_t st, size_t smem_bytes);
+int demod_blocks_padded(ldd_handle* h, const void* rf_dev, int fmt, long long rf_base, long long rf_len,
+                        long long first_sample, long long nblocks, long long total_out,
+                        void* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev,
+                        long long audio1_len, void* stream);
 bool demod_mixed_fused_ok(const DemodParams& p, int threads, size_t smem_bytes, size_t sp_bytes);
 int launch_demod_mixed(const DemodParams& pf, const DemodParams& pq, int* queue, int grid, cudaStream_t st, size_t smem_bytes);
 

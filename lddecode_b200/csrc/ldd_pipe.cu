@@ -228,6 +228,14 @@ int ldd_pipe_launch(ldd_pipe* p, const void* rf_dev, int fmt, long long rf_base,
     const long long avail_end = std::min(rf_base + rf_len, ncap_total);
     while (nblocks > 0 && first_block + (nblocks - 1) * S + N > avail_end) --nblocks;
     if (first_block < rf_base) return pfail(p, LDD_EINVAL, "capture window does not cover the range's halo");
+    // The range reaches the end of the capture and the capture does not end on the block grid: one more block, zeros past
+    // the end.  Without it the planes stop up to one block stride short of the last window the reference still reads.
+    bool pad_last = false;
+    if (nblocks > 0 && need_end == ncap_total && avail_end == ncap_total && first_block + (nblocks - 1) * S + N < ncap_total &&
+        (nblocks + 1) * S <= p->b.plane_cap) {
+        ++nblocks;
+        pad_last = true;
+    }
     const long long total = nblocks * S;
     if (total > p->b.plane_cap) return pfail(p, LDD_ECAP, "plane buffers too small for this range");
     p->r0 = r0; p->r1 = r1; p->ncap_total = ncap_total; p->readlen = readlen;
@@ -244,8 +252,8 @@ int ldd_pipe_launch(ldd_pipe* p, const void* rf_dev, int fmt, long long rf_base,
         if (alen > p->b.audio1_cap) return pfail(p, LDD_ECAP, "audio buffers too small for this range");
     }
     if (nblocks) {
-        rc = ldd_demod_blocks(h, rf_dev, fmt, rf_base, rf_len, first_block, nblocks, total, p->b.planes,
-                              audio ? p->b.audio1_l : nullptr, audio ? p->b.audio1_r : nullptr, alen, stream);
+        rc = (pad_last ? demod_blocks_padded : ldd_demod_blocks)(h, rf_dev, fmt, rf_base, rf_len, first_block, nblocks, total, p->b.planes,
+                                                                 audio ? p->b.audio1_l : nullptr, audio ? p->b.audio1_r : nullptr, alen, stream);
         if (rc) return rc;
     }
     // sync-peak chase over the whole plane; its list is the only device -> host hop in the middle of the path.  It goes

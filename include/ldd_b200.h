@@ -126,6 +126,18 @@ int ldd_set_filter(ldd_handle* h, int id, const double* table, int n);
  * a host-side complex power nor a blocking upload.  Needs LDD_F_RFVIDEO (level 0) and LDD_F_MTF. */
 int ldd_set_mtf_level(ldd_handle* h, double mtf_level, void* stream);
 
+/* Per-block MTF level for whole-range decodes of CAV discs, where the reference lowers mtf_level by 1e-4 with every
+ * frame (Framer.readframe, lddecode_core.py:1300-1306: the level used for a frame is 1 - framenr/10000 of the frame
+ * before it).  After this call a block whose kept samples are centred in the n-th frame period after capture sample
+ * pos0_sample (n may be negative) is demodulated with level max(L0 + n * step_per_period, 0), L0 being the level of
+ * ldd_set_mtf_level -- the level of the frame that starts at pos0_sample.  period_samples = 0 switches the ramp off
+ * (every block uses L0, the behaviour of RFDecode.demod).  Blocks centred before capture sample hold_until_sample use
+ * hold_level instead: the reference decodes the FIRST frame of a run with its start-up level (Framer.mtf_level = 1,
+ * lddecode_core.py:1334) whatever the disc position; pass -1e300 for none.  The correction MTF^(n step) is applied inside
+ * the kernel as a third-order series in n*step*log(MTF): keep |n * step| below ~1e-2 (re-base L0 and pos0 per range). */
+int ldd_set_mtf_ramp(ldd_handle* h, double pos0_sample, double period_samples, double step_per_period,
+                     double hold_until_sample, double hold_level);
+
 /* ---- kernel (1): unpack.  Replaces ddunpack.c:11-36 and lddutils.py:150-229. ------------------ */
 /* words[nwords] (LE u32, dev) -> out[3*nwords] int16 = ((field)-512)<<6, exactly ddunpack.c */
 int ldd_unpack_r30_ddunpack(const uint32_t* words_dev, size_t nwords, int16_t* out_dev, void* stream);

@@ -122,6 +122,7 @@ class PipeResult(C.Structure):
 
 SIGNATURES.update({
     "ldd_set_mtf_level": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
+    "ldd_set_mtf_ramp": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),
     "ldd_downscale_audio": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
                                       C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -216,6 +216,7 @@ void ldd_destroy(ldd_handle* h) {
     cudaFree(h->d_WNfull);
     cudaFree(h->d_rfbase);
     cudaFree(h->d_mtf);
+    cudaFree(h->d_lnM[0]); cudaFree(h->d_lnM[1]);
     cudaFree(h->scratch64);
     cudaFree(h->d_flags);
     cudaFree(h->d_queue);
@@ -246,6 +247,11 @@ int ldd_set_filter(ldd_handle* h, int id, const double* table, int n) {
             h->mtf_level_set = -1e300;       // forces the next ldd_set_mtf_level to run
             if (!h->d_mtf) CUDA_TRY(h, cudaMalloc(&h->d_mtf, (size_t)N * sizeof(Cx<double>)));
             CUDA_TRY(h, cudaMemcpy(h->d_mtf, table, (size_t)N * sizeof(Cx<double>), cudaMemcpyHostToDevice));
+            // principal logarithm, for the per-block level ramp (numpy's complex power is exp(level * log z) as well)
+            t.resize(N);
+            for (int k = 0; k < N; ++k) t[k] = mk<double>(std::log(std::hypot(src[k].x, src[k].y)), std::atan2(src[k].y, src[k].x));
+            int rc = upload_both(h, t, h->d_lnM);
+            if (rc) return rc;
             break;
         }
         case LDD_F_VIDEO: case LDD_F_VIDEO05: case LDD_F_BURST: case LDD_F_PILOT: {
@@ -299,6 +305,15 @@ int ldd_set_mtf_level(ldd_handle* h, double level, void* stream) {
     LDD_LAUNCH(hv_kernel, dim3((N + 255) / 256), dim3(256), 0, (cudaStream_t)stream, (const Cx<double>*)h->d_rfbase,
                (const Cx<double>*)h->d_mtf, level, (Cx<double>*)h->d_Hv[0], (Cx<float>*)h->d_Hv[1], N);
     return launch_status(h, "hv_kernel");
+}
+
+int ldd_set_mtf_ramp(ldd_handle* h, double pos0_sample, double period_samples, double step_per_period,
+                     double hold_until_sample, double hold_level) {
+    if (!h || period_samples < 0.0) return LDD_EINVAL;
+    if (period_samples > 0.0 && !h->d_lnM[0]) return fail(h, LDD_EINVAL, "ldd_set_mtf_ramp needs the MTF table (LDD_F_MTF)");
+    h->ramp_pos0 = pos0_sample; h->ramp_period = period_samples; h->ramp_step = step_per_period;
+    h->ramp_hold_until = hold_until_sample; h->ramp_hold_level = hold_level;
+    return LDD_OK;
 }
 
 int ldd_demod_range_query(ldd_handle* h, long long start, long long length, ldd_range* out) {
@@ -362,6 +377,13 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
     p.stride = S;
     p.nblocks = (int)nblocks;
     p.WM = h->d_WM[lane]; p.WN = h->d_WN[lane]; p.Hv = h->d_Hv[lane];
+    p.lnM = h->d_lnM[lane];
+    if (h->ramp_period > 0.0 && h->d_lnM[0] && blockcut == c.blockcut) {
+        // plane sample k of this launch <-> capture sample first_sample + blockcut + k
+        p.mtf_pos0 = h->ramp_pos0 - (double)(first_sample + blockcut);
+        p.mtf_period = h->ramp_period; p.mtf_step = h->ramp_step; p.mtf_level0 = h->mtf_level_set;
+        p.mtf_hold_until = h->ramp_hold_until - (double)(first_sample + blockcut); p.mtf_hold_level = h->ramp_hold_level;
+    }
     const double rel[4] = {1.0, 1.0, 0.0, 0.0};
     for (int m = 0; m < nfilt; ++m) {
         p.F[m] = h->d_F[m][lane];
@@ -427,7 +449,7 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
     if (mixed) {
         // float64 parameter set of the re-run: only the sync decision (demod_05 -> demod_sync) is redone -- the float32
         // planes of a flagged block are as good as those of its neighbours
-        q.WM = h->d_WM[0]; q.WN = h->d_WN[0]; q.Hv = h->d_Hv[0];
+        q.WM = h->d_WM[0]; q.WN = h->d_WN[0]; q.Hv = h->d_Hv[0]; q.lnM = h->d_lnM[0];
         for (int m = 0; m < nfilt; ++m) q.F[m] = h->d_F[m][0];
         q.AL = h->d_AL[0]; q.AR = h->d_AR[0];
         q.scratch = h->scratch64; q.scratch_per_cta = h->scratch64_per_cta;

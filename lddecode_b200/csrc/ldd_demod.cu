@@ -391,6 +391,29 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
             __syncthreads();
         }
 
+        // Per-block MTF level (CAV discs: the reference lowers mtf_level by 1e-4 per frame, lddecode_core.py:1300-1306):
+        // the table holds RFVideo * MTF^L0; a block whose frame is n frames past the ramp's origin needs MTF^(L0 + n step),
+        // i.e. Hv * exp(delta ln MTF) with |delta ln MTF| < 0.05 -- a third-order series (error < 3e-7 relative at the
+        // largest delta the host lets through before it re-bases L0).
+        T dl = (T)0;
+        if (p.mtf_period > 0.0) {
+            const double centre = (double)o + 0.5 * (double)p.stride;
+            double dlt = p.mtf_step * floor((centre - p.mtf_pos0) / p.mtf_period);
+            if (dlt < -p.mtf_level0) dlt = -p.mtf_level0;                    // max(level, 0)
+            if (centre < p.mtf_hold_until) dlt = p.mtf_hold_level - p.mtf_level0;   // the decode's first frame: start-up level
+            dl = (T)dlt;
+        }
+        const Cx<T>* LnM = (const Cx<T>*)p.lnM;
+        auto HV = [&](int k) -> Cx<T> {
+            Cx<T> hv = Hv[k];
+            if (dl != (T)0) {
+                const Cx<T> z = scale(LnM[k], dl);
+                const Cx<T> z2 = z * z;
+                const Cx<T> e = mk<T>((T)1 + z.x, z.y) + scale(z2, (T)0.5) + scale(z2 * z, (T)(1.0 / 6.0));
+                hv = hv * e;
+            }
+            return hv;
+        };
         // E. Y = X_full * Hv, split into even/odd output samples: U[k] = Y[k] + Y[k+M],
         //    V[k] = (Y[k] - Y[k+M]) W_N^{-k}; stored conjugated for inverse-by-forward.
         Cx<T>* U = f1;
@@ -422,7 +445,7 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
                 LDD_UNROLL
                 for (int i = 0; i < B; ++i) {
                     const int k = tid + (it0 + i) * NT;
-                    h0[i] = Hv[k]; h1[i] = Hv[k + M]; h2[i] = Hv[M - k]; h3[i] = Hv[(2 * M - k) & (2 * M - 1)]; w[i] = WN[k];
+                    h0[i] = HV(k); h1[i] = HV(k + M); h2[i] = HV(M - k); h3[i] = HV((2 * M - k) & (2 * M - 1)); w[i] = WN[k];
                 }
                 LDD_UNROLL
                 for (int i = 0; i < B; ++i) {
@@ -434,10 +457,10 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
                     estep(tid + (it0 + i) * NT, IX(tid) + (it0 + i) * pstride<PAD>(NT), IX(M - tid) - (it0 + i) * pstride<PAD>(NT), xa[i], xb[i],
                           h0[i], h1[i], h2[i], h3[i], w[i]);
             }
-            if (tid == 0) estep(M / 2, IX(M / 2), IX(M / 2), X[IX(M / 2)], X[IX(M / 2)], Hv[M / 2], Hv[M / 2 + M], Hv[M / 2], Hv[M / 2 + M], WN[M / 2]);
+            if (tid == 0) estep(M / 2, IX(M / 2), IX(M / 2), X[IX(M / 2)], X[IX(M / 2)], HV(M / 2), HV(M / 2 + M), HV(M / 2), HV(M / 2 + M), WN[M / 2]);
         } else {
             for (int k = tid; k <= M / 2; k += nthr)
-                estep(k, IX(k), IX(M - k), X[IX(k)], X[IX(k == 0 ? 0 : M - k)], Hv[k], Hv[k + M], Hv[M - k], Hv[(2 * M - k) & (2 * M - 1)], WN[k]);
+                estep(k, IX(k), IX(M - k), X[IX(k)], X[IX(k == 0 ? 0 : M - k)], HV(k), HV(k + M), HV(M - k), HV((2 * M - k) & (2 * M - 1)), WN[k]);
         }
         __syncthreads();
 

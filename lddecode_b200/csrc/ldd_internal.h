@@ -29,6 +29,13 @@ struct DemodParams {
     const void* WM;              // e^{-2 pi i k/M}, k<M
     const void* WN;              // e^{-2 pi i k/N}, k<M
     const void* Hv;              // RFVideo * MTF^level, N entries
+    const void* lnM;             // log(MTF), N entries (per-block level ramp; may be NULL when mtf_period == 0)
+    double mtf_pos0;             // plane sample where the ramp's origin frame starts
+    double mtf_period;           // samples per frame; 0: every block uses the table as it is
+    double mtf_step;             // level change per frame (-1e-4)
+    double mtf_level0;           // level baked into Hv (the level of the origin frame)
+    double mtf_hold_until;       // blocks centred before this plane sample use mtf_hold_level (the decode's first frame)
+    double mtf_hold_level;
     const void* F[4];            // FVideo, FVideo05 (pre-rolled), FVideoBurst, FVideoPilot; k<=M; scaled 1/M
     const void* AL;              // audio_lfilt / audio_rfilt, A entries
     const void* AR;
@@ -120,6 +127,9 @@ struct ldd_handle {
     void* d_rfbase = nullptr;   // Filters['RFVideo'] as uploaded (complex128), base of ldd_set_mtf_level
     void* d_mtf = nullptr;      // Filters['MTF'] (complex128)
     double mtf_level_set = 0.0; // level d_Hv currently holds
+    void* d_lnM[2] = {nullptr, nullptr};   // log(Filters['MTF']), complex128 / complex64
+    double ramp_pos0 = 0.0, ramp_period = 0.0, ramp_step = 0.0;   // ldd_set_mtf_ramp (capture coordinates)
+    double ramp_hold_until = -1e300, ramp_hold_level = 0.0;
     // workspace of the peak search (grown on demand)
     void* peak_ws = nullptr;
     size_t peak_ws_bytes = 0;

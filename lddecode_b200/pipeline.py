@@ -320,6 +320,12 @@ class CaptureDecoder:
         self._lanes = None          # extra (RFDecode, stream, slot key) sets of decode_pipelined
         self._side = None
         self.overlap_refine = os.environ.get("LDD_NO_REFINE_OVERLAP") is None
+        # CAV discs: follow the reference's per-frame MTF adaptation (Framer.readframe, lddecode_core.py:1300-1306)
+        self.cav_follow = False
+        self.cav_state = None       # (capture sample where a frame starts, mtf level the reference uses for that frame)
+        self.cav_hold = None        # (capture sample where the run's first frame ends, the start-up level it is decoded with)
+        self._cav_pending = []      # VBI codes of finished ranges on their way to the host
+        self._cav_first = None      # where the first complete frame of the run ends
 
     # -- workspaces
     def _slot(self, key, ncap_window, rf=None):
@@ -406,8 +412,11 @@ class CaptureDecoder:
         to pinned host memory, run the second audio stage."""
         be = rf._be
         rf._set_mtf(self.mtf_level)           # uploads the tables on first use; the level itself is set by the library
+        level = self.mtf_level
+        if self.cav_follow:
+            level = self._cav_apply(rf, max(r0, cap_base))
         rf._check(be.lib.ldd_pipe_launch(slot.h, be.ptr(cap_dev), int(fmt), int(cap_base), int(cap_len), int(ncap_total),
-                                         int(r0), int(r1), int(self.readlen), float(self.mtf_level), int(bool(audio_phase2)),
+                                         int(r0), int(r1), int(self.readlen), float(level), int(bool(audio_phase2)),
                                          be.stream()))
         return Pending(slot, rf, r0, r1, ncap_total)
 
@@ -474,7 +483,85 @@ class CaptureDecoder:
         res.d_pic = d_pic[:(cap if frame_mode else nloc) * stride] if nloc else None
         res.d_status = d_status[:nloc] if nloc else None
         res.refined = Refined(res) if nloc else None
+        if self.cav_follow and nloc:
+            self._cav_collect(res, side)
         return res
+
+    # -- CAV: per-frame MTF level (lddecode_core.py:1300-1306) predicted from the frame numbers already decoded
+    def _cav_apply(self, rf, start_sample):
+        """Sets the library's per-block level ramp for a range that starts at capture sample start_sample; returns the
+        level to bake in (the level of the frame that contains start_sample).  Without a decoded frame number yet the
+        ramp is off and the level is self.mtf_level (the reference's start value)."""
+        self._cav_drain(block=len(self._cav_pending) >= 2)
+        if self.cav_state is None:
+            rf.set_mtf_ramp(0.0, 0.0, 0.0)
+            return self.mtf_level
+        pos, level = self.cav_state
+        period = rf.freq_hz / rf.SysParams['FPS']
+        n0 = np.floor((start_sample - pos) / period)
+        hold = self.cav_hold if self.cav_hold is not None else (-1e300, 1.0)
+        rf.set_mtf_ramp(pos + n0 * period, period, -1e-4, hold[0], hold[1])
+        return max(level - 1e-4 * n0, 0.0)
+
+    def _cav_collect(self, res, side):
+        """Starts the copy of a finished range's VBI codes to page-locked memory (behind its refinement kernels)."""
+        slot, be = res.slot, res.slot.be
+        nloc = len(res.located)
+        if getattr(slot, 'h_vbi', None) is None:
+            slot.h_vbi = be.pinned(16 * slot.max_fields, np.uint8)
+        off = res.pr.d_vbi - slot.tables_addr
+        with be.stream_ctx(side):
+            res.slot.rf._check(be.lib.ldd_copy_small(be.ptr(slot.h_vbi), be.ptr(slot.d_tables[off:off + 16 * nloc]), 16 * nloc, be.stream()))
+            ev = be.record_event()
+        loc = np.asarray(res.located, dtype=np.intp)
+        self._cav_pending.append((ev, slot, nloc, res.readsamples[loc].copy(), res.infos[loc].copy()))
+
+    def _cav_drain(self, block=False):
+        be = self.rf._be
+        while self._cav_pending:
+            ev, slot, nloc, rs, infos = self._cav_pending[0]
+            if ev is not None and not block and not ev.query():
+                return
+            if ev is not None:
+                be.wait_event(ev)
+            self._cav_pending.pop(0)
+            block = False
+            codes = be.host_view(slot.h_vbi)[:16 * nloc].view(np.int32).reshape(nloc, 4).copy()
+            self._cav_update(rs, infos, codes)
+
+    def _cav_update(self, readsamples, infos, codes):
+        """Framer.readframe's rule on a range's fields: after a complete frame (first field istop == topfirst, then its
+        partner) whose LAST field carries a CAV frame number, the next frame is decoded with max(1 - framenr/10000, 0)."""
+        rf = self.rf
+        top = int(bool(rf.SysParams['topfirst']))
+        lines = rf.SysParams['philips_codelines']
+        k = 0
+        while k + 1 < len(infos):
+            if int(infos[k].istop) == top and int(infos[k + 1].istop) != top:
+                vbi = F.process_philips(rf, {l: F.code_nibbles(codes[k + 1][i]) for i, l in enumerate(lines)})
+                if not vbi['isclv'] and vbi['framenr'] is not None:
+                    # the next frame's first read starts 10 lines before its vertical interval (Field.nextfieldoffset,
+                    # lddecode_core.py:926); this frame's last picture lines end there: switch the level at the interval
+                    nxt = int(readsamples[k + 1]) + int(infos[k + 1].nextfieldoffset) + 10 * rf.linelen
+                    self.cav_state = (nxt, max(1 - vbi['framenr'] / 10000, 0))
+                    if self._cav_first is None:
+                        self._cav_first = nxt
+                k += 2
+            else:
+                k += 1
+
+    def prime_cav(self, cap_dev, fmt, cap_base, cap_len, ncap_total, r0=0):
+        """Decodes the first frame at r0 (synchronously) to learn the disc position, so that the ranges that follow get
+        the reference's level for every frame.  Returns the state (frame start sample, level) or None (CLV / no code)."""
+        self.cav_follow = True
+        self._cav_first = None
+        nfr = int(2.6 * 2 * self.field_samples)
+        res = self.decode_range(cap_dev, fmt, cap_base, cap_len, ncap_total, r0, min(r0 + nfr, ncap_total + 1))
+        self._cav_drain(block=True)
+        if self.cav_state is not None:
+            # the run's first frame keeps the start-up level (Framer.mtf_level = 1 until the first frame number is read)
+            self.cav_hold = (self._cav_first, self.mtf_level)
+        return self.cav_state
 
     def decode_pipelined(self, cap_dev, fmt, ncap, nranges=2):
         """The whole capture as `nranges` read-position ranges on their own streams and handles, so that

@@ -287,6 +287,15 @@ class RFDecode:
             self._mtf_uploaded = True
         self._check(self._be.lib.ldd_set_mtf_level(self._h, float(mtf_level), self._be.stream()))     # no-op when unchanged
 
+    def set_mtf_ramp(self, pos0_sample=0.0, period_samples=0.0, step_per_period=0.0, hold_until_sample=-1e300, hold_level=1.0):
+        """Per-block MTF level for whole-range decodes of CAV discs (ldd_set_mtf_ramp): blocks in the n-th frame period
+        after capture sample pos0_sample use max(mtf_level + n * step_per_period, 0); blocks before hold_until_sample use
+        hold_level (the reference's start-up level for the first frame of a run).  period_samples = 0: off."""
+        if self._mtf_uploaded is None:
+            self._set_mtf(0)
+        self._check(self._be.lib.ldd_set_mtf_ramp(self._h, float(pos0_sample), float(period_samples), float(step_per_period),
+                                                  float(hold_until_sample), float(hold_level)))
+
     def __del__(self):
         try:
             if self._h is not None:

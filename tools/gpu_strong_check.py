@@ -36,7 +36,7 @@ def main():
     ncap = int(round(seconds * fs * 1e6)) + 1100000
     tc = synth.TiledCapture(seed=2, device="cuda")
     rf = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=False, device=local)
-    cd = pipeline.CaptureDecoder(rf, max_fields=512)
+    cd = pipeline.CaptureDecoder(rf, max_fields=4096)
     R0, R1 = parallel.shard_bounds(ncap, world)[rank]
     lo, hi = parallel.needed_window(cd, ncap, R0, R1)
     win = tc.generate(lo, hi - lo)

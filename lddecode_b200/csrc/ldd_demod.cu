@@ -215,6 +215,9 @@ __device__ inline void tangle_static(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __re
 // bound by L2 traffic, ~7 TB/s chip-wide at 9 Gsamples/s).
 // CM != 0: the transform length M is the compile-time constant CM (and blockDim.x == NT, plan = radix 16
 // while possible): the default block length gets fully constant-folded indexing.
+struct TrueTag { static constexpr bool value = true; };
+struct FalseTag { static constexpr bool value = false; };
+
 // Per-kernel constants of the sync scan (step J): a thread owns CH consecutive samples.
 struct ScanConsts {
     int CH;
@@ -404,15 +407,12 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
             dl = (T)dlt;
         }
         const Cx<T>* LnM = (const Cx<T>*)p.lnM;
-        auto HV = [&](int k) -> Cx<T> {
-            Cx<T> hv = Hv[k];
-            if (dl != (T)0) {
-                const Cx<T> z = scale(LnM[k], dl);
-                const Cx<T> z2 = z * z;
-                const Cx<T> e = mk<T>((T)1 + z.x, z.y) + scale(z2, (T)0.5) + scale(z2 * z, (T)(1.0 / 6.0));
-                hv = hv * e;
-            }
-            return hv;
+        // (two instances of step E under one block-uniform branch, so that the common case keeps its code)
+        auto HVr = [&](int k, Cx<T> hv) -> Cx<T> {
+            const Cx<T> z = scale(LnM[k], dl);
+            const Cx<T> z2 = z * z;
+            const Cx<T> e = mk<T>((T)1 + z.x, z.y) + scale(z2, (T)0.5) + scale(z2 * z, (T)(1.0 / 6.0));
+            return hv * e;
         };
         // E. Y = X_full * Hv, split into even/odd output samples: U[k] = Y[k] + Y[k+M],
         //    V[k] = (Y[k] - Y[k+M]) W_N^{-k}; stored conjugated for inverse-by-forward.
@@ -437,31 +437,40 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
                 }
             }
         };
-        if constexpr (CM != 0) {
-            constexpr int IT = CM / 2 / NT, B = (IT % 4 == 0) ? (sizeof(T) == 4 ? 4 : 2) : 1;
-            LDD_UNROLL
-            for (int it0 = 0; it0 < IT; it0 += B) {
-                Cx<T> h0[B], h1[B], h2[B], h3[B], w[B], xa[B], xb[B];
+        auto stepE = [&](auto ramp) {
+            auto HV = [&](int k) -> Cx<T> {
+                Cx<T> hv = Hv[k];
+                if constexpr (decltype(ramp)::value) hv = HVr(k, hv);
+                return hv;
+            };
+            if constexpr (CM != 0) {
+                constexpr int IT = CM / 2 / NT, B = (IT % 4 == 0) ? (sizeof(T) == 4 ? 4 : 2) : 1;
                 LDD_UNROLL
-                for (int i = 0; i < B; ++i) {
-                    const int k = tid + (it0 + i) * NT;
-                    h0[i] = HV(k); h1[i] = HV(k + M); h2[i] = HV(M - k); h3[i] = HV((2 * M - k) & (2 * M - 1)); w[i] = WN[k];
+                for (int it0 = 0; it0 < IT; it0 += B) {
+                    Cx<T> h0[B], h1[B], h2[B], h3[B], w[B], xa[B], xb[B];
+                    LDD_UNROLL
+                    for (int i = 0; i < B; ++i) {
+                        const int k = tid + (it0 + i) * NT;
+                        h0[i] = HV(k); h1[i] = HV(k + M); h2[i] = HV(M - k); h3[i] = HV((2 * M - k) & (2 * M - 1)); w[i] = WN[k];
+                    }
+                    LDD_UNROLL
+                    for (int i = 0; i < B; ++i) {
+                        xa[i] = X[IX(tid) + (it0 + i) * pstride<PAD>(NT)];
+                        xb[i] = X[(it0 + i == 0 && tid == 0) ? 0 : IX(M - tid) - (it0 + i) * pstride<PAD>(NT)];
+                    }
+                    LDD_UNROLL
+                    for (int i = 0; i < B; ++i)
+                        estep(tid + (it0 + i) * NT, IX(tid) + (it0 + i) * pstride<PAD>(NT), IX(M - tid) - (it0 + i) * pstride<PAD>(NT), xa[i], xb[i],
+                              h0[i], h1[i], h2[i], h3[i], w[i]);
                 }
-                LDD_UNROLL
-                for (int i = 0; i < B; ++i) {
-                    xa[i] = X[IX(tid) + (it0 + i) * pstride<PAD>(NT)];
-                    xb[i] = X[(it0 + i == 0 && tid == 0) ? 0 : IX(M - tid) - (it0 + i) * pstride<PAD>(NT)];
-                }
-                LDD_UNROLL
-                for (int i = 0; i < B; ++i)
-                    estep(tid + (it0 + i) * NT, IX(tid) + (it0 + i) * pstride<PAD>(NT), IX(M - tid) - (it0 + i) * pstride<PAD>(NT), xa[i], xb[i],
-                          h0[i], h1[i], h2[i], h3[i], w[i]);
+                if (tid == 0) estep(M / 2, IX(M / 2), IX(M / 2), X[IX(M / 2)], X[IX(M / 2)], HV(M / 2), HV(M / 2 + M), HV(M / 2), HV(M / 2 + M), WN[M / 2]);
+            } else {
+                for (int k = tid; k <= M / 2; k += nthr)
+                    estep(k, IX(k), IX(M - k), X[IX(k)], X[IX(k == 0 ? 0 : M - k)], HV(k), HV(k + M), HV(M - k), HV((2 * M - k) & (2 * M - 1)), WN[k]);
             }
-            if (tid == 0) estep(M / 2, IX(M / 2), IX(M / 2), X[IX(M / 2)], X[IX(M / 2)], HV(M / 2), HV(M / 2 + M), HV(M / 2), HV(M / 2 + M), WN[M / 2]);
-        } else {
-            for (int k = tid; k <= M / 2; k += nthr)
-                estep(k, IX(k), IX(M - k), X[IX(k)], X[IX(k == 0 ? 0 : M - k)], HV(k), HV(k + M), HV(M - k), HV((2 * M - k) & (2 * M - 1)), WN[k]);
-        }
+        };
+        if (dl != (T)0) stepE(TrueTag{});
+        else stepE(FalseTag{});
         __syncthreads();
 
         // F. h[2n] = conj(ru[n]), h[2n+1] = conj(rv[n]) (up to a positive scale)

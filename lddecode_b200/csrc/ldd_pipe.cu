@@ -236,7 +236,9 @@ int ldd_pipe_launch(ldd_pipe* p, const void* rf_dev, int fmt, long long rf_base,
         ++nblocks;
         pad_last = true;
     }
-    const long long total = nblocks * S;
+    long long total = nblocks * S;
+    // a padded last block: the planes end where the capture ends (what lies beyond is the transform of zeros)
+    if (pad_last && total > ncap_total - first_block - bc) total = ncap_total - first_block - bc;
     if (total > p->b.plane_cap) return pfail(p, LDD_ECAP, "plane buffers too small for this range");
     p->r0 = r0; p->r1 = r1; p->ncap_total = ncap_total; p->readlen = readlen;
     p->plane_origin = first_block; p->plane_len = total; p->walk_start = walk_start;

@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(TBC_THREADS, 4) tbc_kernel(const TbcParams p) 
 // boundary).  The float64 kernel above stays the one for the exact lane and for float64 (Hz) output.
 constexpr int TBF_C = 17;
 constexpr int TBF_THREADS = 256;
+constexpr int TBF_NPOW = 24;                            // reach of the homogeneous (not-a-knot) correction in float32
 constexpr int TBF_MAXU = TBF_C * TBF_THREADS;            // 4352 staged samples at most
 
 struct TbfGeom {            // one work item (field, line), filled by thread 0 when it issues the item's copy
@@ -285,7 +286,7 @@ __device__ inline void mbar_wait(void* bar, unsigned parity) {
 }
 #endif
 
-__global__ void __launch_bounds__(TBF_THREADS, 4) tbc_f32_kernel(const TbcParams p, int nitems, int lines_per_field, int maxu) {
+__global__ void __launch_bounds__(TBF_THREADS, 5) tbc_f32_kernel(const TbcParams p, int nitems, int lines_per_field, int maxu) {
     LDD_DYN_SMEM(smem_raw);
     float* ysb[2];
     ysb[0] = (float*)smem_raw;
@@ -295,6 +296,8 @@ __global__ void __launch_bounds__(TBF_THREADS, 4) tbc_f32_kernel(const TbcParams
     float* Lb = Lf + TBF_THREADS;
     __shared__ TbfGeom geom[2];
     __shared__ unsigned long long mbar[2];           // 8-byte aligned by type
+    __shared__ float s_rpow[TBF_NPOW + 2];           // r^i: |r|^24 = 2e-14, far below float32 resolution
+    if (threadIdx.x < TBF_NPOW + 2) s_rpow[threadIdx.x] = (float)c_tbc_rpow[threadIdx.x];
     const int tid = threadIdx.x;
     const float r = -0.26794919243112270647f, c = 0.28867513459481288225f;
 
@@ -334,6 +337,7 @@ __global__ void __launch_bounds__(TBF_THREADS, 4) tbc_f32_kernel(const TbcParams
 #ifndef LDD_EMU
                 if (a0 >= 0 && a0 + U <= p.n && U <= maxu && (((uintptr_t)p.plane) & 15) == 0) {
                     g.src0 = a0; g.lead = TBC_H + shift; g.U = U; g.state = 1;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic reads of this buffer before the async write
                     mbar_expect_tx(&mbar[buf], (unsigned)U * 4u);
                     bulk_g2s(ysb[buf], p.plane + a0, (unsigned)U * 4u, &mbar[buf]);
                 }
@@ -431,29 +435,20 @@ __global__ void __launch_bounds__(TBF_THREADS, 4) tbc_f32_kernel(const TbcParams
         }
         __syncthreads();
         const int lead = g.lead;
+        // not-a-knot rows -> homogeneous part alpha r^i + beta r^(dist-i): every thread solves the 2x2 system for itself
+        // and adds the correction to the (few) values it reads near the line's ends -- nothing is written back, so the
+        // recursions' result needs no further barrier
+        float alpha, beta;
         {
-            // not-a-knot rows -> homogeneous part alpha r^i + beta r^(dist-i)
             const float* Mz = Ms + lead;
             const float L = Mz[0] - 2.f * Mz[1] + Mz[2];
             const float R = Mz[dist] - 2.f * Mz[dist - 1] + Mz[dist - 2];
             const float A = (1.f - r) * (1.f - r);
-            const float q = (dist - 2 < TBC_NPOW) ? (float)c_tbc_rpow[dist - 2] : 0.f;
+            const float q = (dist - 2 < TBF_NPOW) ? s_rpow[dist - 2] : 0.f;
             const float den = A * (1.f - q * q);
-            const float alpha = (-L + q * R) / den, beta = (-R + q * L) / den;
-            __syncthreads();
-            if (tid < TBC_NPOW) {
-                const int i = tid;
-                if (i <= dist) {
-                    float corr = alpha * (float)c_tbc_rpow[i];
-                    if (dist - i < TBC_NPOW) corr += beta * (float)c_tbc_rpow[dist - i];
-                    Ms[lead + i] += corr;
-                }
-            } else if (tid < 2 * TBC_NPOW) {
-                const int k = tid - TBC_NPOW, i = dist - k;
-                if (i >= TBC_NPOW) Ms[lead + i] += beta * (float)c_tbc_rpow[k];
-            }
+            alpha = (-L + q * R) / den;
+            beta = (-R + q * L) / den;
         }
-        __syncthreads();
         // evaluate: positions in float64, polynomial in float32, the affine map to the uint16 scale folded into one FMA
         const double ibd = (double)(long long)g.b;
         const double fb = g.b - ibd;
@@ -477,7 +472,10 @@ __global__ void __launch_bounds__(TBF_THREADS, 4) tbc_f32_kernel(const TbcParams
             int i = tbc_floor_nonneg(x);
             if (i > dist - 1) i = dist - 1;
             const float t = (float)(x - tbc_i2d(i)), u = 1.f - t;
-            const float Mi6 = Mz[i] * sixth, Mj6 = Mz[i + 1] * sixth;
+            float Mi = Mz[i], Mj = Mz[i + 1];
+            if (i < TBF_NPOW) { Mi = fmaf(alpha, s_rpow[i], Mi); Mj = fmaf(alpha, s_rpow[i + 1], Mj); }
+            if (dist - i <= TBF_NPOW) { Mi = fmaf(beta, s_rpow[dist - i], Mi); Mj = fmaf(beta, s_rpow[dist - i - 1], Mj); }
+            const float Mi6 = Mi * sixth, Mj6 = Mj * sixth;
             const float S = u * fmaf(Mi6, fmaf(u, u, -1.f), yz[i]) + t * fmaf(Mj6, fmaf(t, t, -1.f), yz[i + 1]);
             float v = fmaf(S, ka, kb);
             v = v < 0.f ? 0.f : (v > 65535.f ? 65535.f : v);
@@ -550,7 +548,7 @@ extern "C" int ldd_tbc_fields_ex(ldd_handle* h, const float* plane_dev, long lon
         cudaFuncSetAttribute(tbc_f32_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         const int nitems = nfields * max_linecount;
         int per_sm = (int)((h->smem_optin + 1024) / (smem32 + 1024));
-        if (per_sm > 4) per_sm = 4;                  // 64 registers x 256 threads: four CTAs per SM
+        if (per_sm > 5) per_sm = 5;                  // 48 registers x 256 threads: five CTAs per SM
         if (per_sm < 1) per_sm = 1;
         int grid = h->sm_count * per_sm;
         if (grid > nitems) grid = nitems;

@@ -353,7 +353,8 @@ def measure(a, system, audio, fmt, rank, world, local, dist, clocks_rank0=None, 
             dist.barrier()
         torch.cuda.synchronize()
 
-    gatherer = parallel.FieldGatherer(cd, rank, world, max_fields, dist) if world > 1 else None
+    # (LDD_BENCH_NO_GATHER: diagnostic runs that separate the collective's cost from the rest of a multi-GPU step)
+    gatherer = parallel.FieldGatherer(cd, rank, world, max_fields, dist) if world > 1 and not os.environ.get("LDD_BENCH_NO_GATHER") else None
 
     def run_resident(nsteps):
         # K decodes of the HBM-resident capture through CaptureDecoder.decode_stream: the demodulation of step k+1 is
@@ -402,7 +403,7 @@ def measure(a, system, audio, fmt, rank, world, local, dist, clocks_rank0=None, 
     tw0 = time.time()
     e0.record()
     res = run_resident(a.steps)
-    if world > 1:
+    if gatherer is not None:
         gatherer.wait()
     e1.record()
     barrier()

@@ -629,7 +629,9 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
                 // mixed lane: is this float32 sample close enough to a threshold that float64 could decide otherwise?
                 if (p.flag_margin > 0.0) near |= (fabs(v - p.sync_lo) < p.flag_margin) | (fabs(v - p.sync_hi) < p.flag_margin);
             }
-            if (p.flag_margin > 0.0) flagged = __syncthreads_or(near);
+            // (a block that reaches past the end of the capture is always re-run: next to the zero padding the analytic
+            // signal fades out and its angle is rounding noise, so float32 decisions there mean nothing)
+            if (p.flag_margin > 0.0) flagged = __syncthreads_or(near | (in0 + N > p.rf_limit));
             // inclusive scan of the affine maps y -> Ach*y + acc over threads
             double incl = acc, mult = Ach;
             for (int d = 1; d < 32; d <<= 1) {

@@ -263,6 +263,7 @@ struct TbfGeom {            // one work item (field, line), filled by thread 0 w
     double b, e;
     long long src0;         // plane index of staged sample 0 (16-byte aligned element index when bulk)
     int field, line, dist, lead;   // lead = TBC_H + alignment shift: staged index of line sample 0
+    int lc;                 // the field's line count (burst markers)
     int U;                  // staged samples
     int state;              // 0: nothing to do (line >= linecount), 1: bulk copy in flight, 2: load by hand, 3: bad geometry
 };
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(TBF_THREADS, 5) tbc_f32_kernel(const TbcParams
     };
     auto issue = [&](const Pre& q, int buf) {
         TbfGeom g;
-        g.state = 0; g.field = q.field; g.line = q.line;
+        g.state = 0; g.field = q.field; g.line = q.line; g.lc = q.lc;
         if (q.lc >= 0 && q.line < q.lc) {
             g.b = q.b + p.lineloc_add;
             g.e = q.e + p.lineloc_add;
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(TBF_THREADS, 5) tbc_f32_kernel(const TbcParams
         const float kb = (float)((p.plane_add * wowf - p.ire0) * k1 - p.vsync_ire * p.out_scale + p.out_off);
         const float sixth = 1.f / 6.f;
         const int field = g.field, line = g.line;
-        const int linecount = p.linecount[field];
+        const int linecount = g.lc;
         unsigned short* outl = (unsigned short*)p.out + (p.field_off ? (size_t)p.field_off[field] : (size_t)field * (size_t)p.out_stride) +
                                (size_t)line * (size_t)p.line_stride;
         const float* Mz = Ms + lead;

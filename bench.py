@@ -354,7 +354,7 @@ def measure(a, system, audio, fmt, rank, world, local, dist, clocks_rank0=None, 
         torch.cuda.synchronize()
 
     # (LDD_BENCH_NO_GATHER: diagnostic runs that separate the collective's cost from the rest of a multi-GPU step)
-    gatherer = parallel.FieldGatherer(cd, rank, world, max_fields, dist) if world > 1 and not os.environ.get("LDD_BENCH_NO_GATHER") else None
+    gatherer = parallel.make_gatherer(cd, rank, world, max_fields, dist) if world > 1 and not os.environ.get("LDD_BENCH_NO_GATHER") else None
 
     def run_resident(nsteps):
         # K decodes of the HBM-resident capture through CaptureDecoder.decode_stream: the demodulation of step k+1 is
@@ -466,6 +466,8 @@ def measure(a, system, audio, fmt, rank, world, local, dist, clocks_rank0=None, 
         launches_per_step = (2 if a.precision == "mixed" else 1) + 5 + 1 + (1 if audio else 0) + 1 + 2 + 1 + \
             (2 if system == "PAL" else 4) + 1 + (1 if world > 1 else 0)
         out = dict(value=value, ms_per_step=ms_step, realtime_x=value / FS[system] / world, fields_per_step=nfields * world,
+                   gather=(None if gatherer is None else ("peer stores over NVLink into rank 0's buffer (no collective kernel)"
+                                                           if type(gatherer).__name__ == "PeerGatherer" else "NCCL gather")),
                    e2e=dict(value=e2e_val, unit="Msamples/s", h2d_bytes_per_step=int(nraw * raw.dtype.itemsize),
                             d2h_bytes_per_step=int(npic * 2 + naudio), wall_ms_per_step=wall_e2e / a.steps),
                    gpu_launches=launches_per_step * a.steps, self_check=verify, window=(tw0, tw1))
@@ -595,7 +597,7 @@ def run_strong(a, rank, world, local, dist, seconds=None, steps=None):
     edges = [R0 + i * chunk for i in range(nch)] + [R1]
     ranges = [(cap_dev, _lib.FMT_U8, lo, hi - lo, ncap, edges[i], edges[i + 1]) for i in range(nch)]
     max_fields = 80
-    gatherer = parallel.FieldGatherer(cd, rank, world, max_fields, dist) if world > 1 else None
+    gatherer = parallel.make_gatherer(cd, rank, world, max_fields, dist) if world > 1 else None
 
     def barrier():
         if world > 1:

@@ -343,6 +343,20 @@ int ldd_vbi_decode(ldd_handle* h, const float* demod_dev, long long n, const lon
                    const long long* winlen_dev, const double* linelocs_dev, int ll_stride, int nfields,
                    const int* lines, int nlines, int* codes_dev, void* stream);
 
+/* ---- peer memory for the multi-GPU gather (one process per GPU, NVLink / NVSwitch).  The gather of per-field outputs to
+ * the root rank needs no collective kernel on the root: the root allocates its receive buffer with
+ * ldd_peer_alloc and publishes the 64-byte handle, every other rank maps it (ldd_peer_open) and passes addresses inside it
+ * to ldd_pipe_finish as the TBC kernel's destination -- fields are stored straight into the root's HBM.  ldd_peer_signal
+ * (a stream-ordered flag write behind a system-wide fence) and ldd_peer_wait (a kernel that spins until n flags, `stride`
+ * ints apart, have reached `value`) order producers and consumer; ldd_peer_read is a blocking device-to-host copy. */
+int ldd_peer_alloc(size_t nbytes, void** dev_ptr, unsigned char* handle64);
+int ldd_peer_open(const unsigned char* handle64, void** dev_ptr);
+int ldd_peer_close(void* dev_ptr);
+int ldd_peer_free(void* dev_ptr);
+int ldd_peer_read(void* host_dst, const void* dev_src, size_t nbytes);
+int ldd_peer_signal(int* flag_dev, int value, void* stream);
+int ldd_peer_wait(const int* flags_dev, int n, int stride, int value, void* stream);
+
 /* ---- whole-range pipeline: Framer.readfield's loop (lddecode_core.py:1194-1223) over a range of a capture in two calls.
  * All buffers are the caller's.  One ldd_pipe per plane workspace; two of them software-pipeline a stream of ranges
  * (launch k+1, then finish k).  A pipe is used from one thread. */

@@ -131,6 +131,13 @@ SIGNATURES.update({
                                     C.c_longlong, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "ldd_vbi_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                  C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_void_p]),
+    "ldd_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "ldd_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ldd_peer_close": (C.c_int, [C.c_void_p]),
+    "ldd_peer_free": (C.c_int, [C.c_void_p]),
+    "ldd_peer_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ldd_peer_signal": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "ldd_peer_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ldd_pipe_table_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "ldd_pipe_create": (C.c_int, [C.c_void_p, C.POINTER(PipeBufs), C.c_int, C.c_longlong, C.POINTER(C.c_void_p)]),
     "ldd_pipe_destroy": (None, [C.c_void_p]),

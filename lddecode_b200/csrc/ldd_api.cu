@@ -542,3 +542,84 @@ int ldd_demod_range(ldd_handle* h, const void* rf_dev, int fmt, long long rf_bas
 }
 
 }  // extern "C"
+
+// ---- peer memory (one process per GPU): the root rank exposes its gather buffer, the other ranks map it and let their
+// TBC kernels store fields straight into it over NVLink; flags in the same buffer order producers and consumer ----------
+namespace {
+
+__global__ void peer_signal_kernel(volatile int* flag, int value) {
+    __threadfence_system();                 // everything this stream wrote before is visible system-wide first
+    *flag = value;
+    __threadfence_system();
+}
+
+__global__ void peer_wait_kernel(const volatile int* flags, int n, int stride, int value) {
+    // one thread per flag; spins until flags[i * stride] >= value
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    while (flags[(size_t)i * stride] < value) {
+#ifndef LDD_EMU
+        __nanosleep(200);
+#endif
+    }
+    __threadfence_system();
+}
+
+}  // namespace
+
+extern "C" {
+
+int ldd_peer_alloc(size_t nbytes, void** dev_ptr, unsigned char* handle64) {
+    if (!dev_ptr || !handle64 || nbytes == 0) return LDD_EINVAL;
+#ifdef LDD_EMU
+    return LDD_ECUDA;
+#else
+    if (cudaMalloc(dev_ptr, nbytes) != cudaSuccess) return LDD_ENOMEM;
+    cudaMemset(*dev_ptr, 0, nbytes);
+    cudaIpcMemHandle_t hd;
+    if (cudaIpcGetMemHandle(&hd, *dev_ptr) != cudaSuccess) { cudaFree(*dev_ptr); *dev_ptr = nullptr; return LDD_ECUDA; }
+    static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &hd, 64);
+    return LDD_OK;
+#endif
+}
+
+int ldd_peer_open(const unsigned char* handle64, void** dev_ptr) {
+    if (!dev_ptr || !handle64) return LDD_EINVAL;
+#ifdef LDD_EMU
+    return LDD_ECUDA;
+#else
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    return cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess ? LDD_OK : LDD_ECUDA;
+#endif
+}
+
+int ldd_peer_close(void* dev_ptr) {
+#ifdef LDD_EMU
+    return LDD_ECUDA;
+#else
+    return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? LDD_OK : LDD_ECUDA;
+#endif
+}
+
+int ldd_peer_free(void* dev_ptr) { return cudaFree(dev_ptr) == cudaSuccess ? LDD_OK : LDD_ECUDA; }
+
+int ldd_peer_read(void* host_dst, const void* dev_src, size_t nbytes) {
+    if (!host_dst || !dev_src) return LDD_EINVAL;
+    return cudaMemcpy(host_dst, dev_src, nbytes, cudaMemcpyDeviceToHost) == cudaSuccess ? LDD_OK : LDD_ECUDA;
+}
+
+int ldd_peer_signal(int* flag_dev, int value, void* stream) {
+    if (!flag_dev) return LDD_EINVAL;
+    LDD_LAUNCH(peer_signal_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (volatile int*)flag_dev, value);
+    return cudaGetLastError() == cudaSuccess ? LDD_OK : LDD_ECUDA;
+}
+
+int ldd_peer_wait(const int* flags_dev, int n, int stride, int value, void* stream) {
+    if (!flags_dev || n < 1 || stride < 1) return LDD_EINVAL;
+    LDD_LAUNCH(peer_wait_kernel, dim3((n + 31) / 32), dim3(32), 0, (cudaStream_t)stream, (const volatile int*)flags_dev, n, stride, value);
+    return cudaGetLastError() == cudaSuccess ? LDD_OK : LDD_ECUDA;
+}
+
+}  // extern "C"

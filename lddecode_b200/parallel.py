@@ -5,6 +5,8 @@ decode_range: own block range + halos, no data-path collective); the only exchan
 of the per-field outputs (uint16 TBC fields, read positions, parity, status) to rank 0, over NCCL
 on NVLink when the backend is CUDA (gloo in the CPU tests).  SURVEY.md section 8e.
 """
+import ctypes as C
+
 import numpy as np
 
 from . import _lib
@@ -150,6 +152,202 @@ class FieldGatherer:
                 out.append((int(m[k, 0]), int(m[k, 1]), p[k, :m[k, 2] * self.W].copy() if ok else None))
         out.sort(key=lambda t: t[0])
         return out
+
+
+class RawBuf:
+    """A typed view of device memory that torch does not own (here: the root rank's gather buffer, mapped through
+    CUDA IPC).  Just enough of a tensor's surface for the decoder: data_ptr(), len(), slicing, a host copy."""
+
+    def __init__(self, lib, ptr, n, dtype):
+        self.lib, self.ptr, self.n, self.dtype = lib, int(ptr), int(n), np.dtype(dtype)
+
+    def data_ptr(self):
+        return self.ptr
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, sl):
+        a, b, st = sl.indices(self.n)
+        assert st == 1
+        return RawBuf(self.lib, self.ptr + a * self.dtype.itemsize, max(b - a, 0), self.dtype)
+
+    def to_host(self):
+        out = np.empty(self.n, dtype=self.dtype)
+        if self.n:
+            rc = self.lib.ldd_peer_read(out.ctypes.data_as(C.c_void_p), C.c_void_p(self.ptr), out.nbytes)
+            if rc:
+                raise RuntimeError("ldd_peer_read failed (%d)" % rc)
+        return out
+
+    def cpu(self):
+        import torch
+        return torch.from_numpy(self.to_host())
+
+
+class PeerGatherer:
+    """The gather of per-field outputs to rank 0 WITHOUT a collective: rank 0 publishes its receive buffer (CUDA IPC),
+    every rank maps it and hands the decoder an address inside it as the TBC kernel's destination (buffers()), so the
+    resampling kernel of rank g stores its uint16 fields straight into rank 0's HBM over NVLink -- compute and transfer
+    are one kernel, rank 0 spends no SMs on receiving, and there is no staging copy anywhere.  Per-field metadata and a
+    per-rank step flag follow on the same stream (ldd_copy_small, ldd_peer_signal).  Flow control: NBUF slots per rank;
+    before a rank's kernels write slot k for step s they wait (on the device) until rank 0 has released step s - NBUF
+    of that slot, which it does when it moves on to step s itself (or when its consumer calls to_host()).
+    Same interface as FieldGatherer."""
+
+    NBUF = 2
+    HEADER = 4096
+
+    def __init__(self, cd, rank, world, max_fields, dist):
+        import torch
+        self.torch = torch
+        self.cd, self.rank, self.world, self.max_fields, self.dist = cd, rank, world, max_fields, dist
+        rf = cd.rf
+        self.be = be = rf._be
+        self.lib = be.lib
+        self.W = rf.SysParams['outlinelen']
+        self.stride = (rf.SysParams['frame_lines'] // 2 + 1) * self.W
+        F = max_fields
+        self.meta_bytes = F * 3 * 8
+        self.status_off = self.meta_bytes
+        self.pic_off = (self.status_off + 4 * F + 255) // 256 * 256
+        self.slot_bytes = (self.pic_off + F * self.stride * 2 + 255) // 256 * 256
+        total = self.HEADER + self.NBUF * world * self.slot_bytes
+        handle = (C.c_ubyte * 64)()
+        base = C.c_void_p()
+        rc = 0
+        if rank == 0:
+            rc = self.lib.ldd_peer_alloc(total, C.byref(base), handle)
+        box = [bytes(handle) if rc == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            rc = -1
+            if box[0] is not None:
+                hb = (C.c_ubyte * 64).from_buffer_copy(box[0])
+                rc = self.lib.ldd_peer_open(hb, C.byref(base))
+        # every rank learns whether every rank has the mapping (so that nobody is left waiting in a collective)
+        ok = torch.tensor([1 if rc == 0 else 0], device=be.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        self.base = base.value if rc == 0 else 0
+        if int(ok[0]) != 1:
+            self.close(collective=False)
+            raise RuntimeError("peer mapping of rank 0's gather buffer failed on some rank")
+        self._hmeta = [be.pinned(F * 3, np.int64) for _ in range(self.NBUF)]
+        self._step = 0
+        self._last = None
+        self._cache = None
+
+    # header: ack[k] at 4 k ; flags[k][r] at 256 + 4 (k world + r)
+    def _ack(self, k):
+        return self.base + 4 * k
+
+    def _flag(self, k, r):
+        return self.base + 256 + 4 * (k * self.world + r)
+
+    def _slot(self, k, r):
+        return self.base + self.HEADER + (k * self.world + r) * self.slot_bytes
+
+    def buffers(self, stream=None):
+        """(pictures, status) of the next gather() inside rank 0's buffer; orders `stream` behind rank 0's release of
+        the slot's previous contents."""
+        be = self.be
+        s = self._step + 1
+        if self._cache is not None and self._cache[0] == s:
+            return self._cache[1], self._cache[2]
+        k = s % self.NBUF
+        st = C.c_void_p(stream.cuda_stream) if stream is not None else be.stream()
+        if self.rank == 0:
+            if s > self.NBUF:
+                self.lib.ldd_peer_signal(C.c_void_p(self._ack(k)), s - self.NBUF, st)       # slot k's old contents may go
+        elif s > self.NBUF:
+            self.lib.ldd_peer_wait(C.c_void_p(self._ack(k)), 1, 1, s - self.NBUF, st)
+        slot = self._slot(k, self.rank)
+        pic = RawBuf(self.lib, slot + self.pic_off, self.max_fields * self.stride, np.uint16)
+        status = RawBuf(self.lib, slot + self.status_off, self.max_fields, np.int32)
+        self._cache = (s, pic, status)
+        return pic, status
+
+    def gather(self, res):
+        be = self.be
+        pic, status = self.buffers()
+        self._step += 1
+        s = self._step
+        k = s % self.NBUF
+        nloc = len(res.located)
+        if nloc > self.max_fields:
+            raise ValueError("max_fields too small")
+        meta = be.host_view(self._hmeta[k]).reshape(self.max_fields, 3)
+        meta[:] = -1
+        if nloc:
+            loc = np.asarray(res.located, dtype=np.intp)
+            infos = res.infos[loc]
+            meta[:nloc, 0] = np.asarray(res.readsamples)[loc]
+            meta[:nloc, 1] = infos['istop']
+            meta[:nloc, 2] = infos['linecount']
+            if res.d_pic.data_ptr() != pic.data_ptr():
+                # decoded into the decoder's own buffer: copy it over (the decode_stream(sink=...) path never does)
+                n = nloc * self.stride
+                self.lib.ldd_copy_small(be.ptr(pic), be.ptr(res.d_pic), 2 * n, be.stream())
+                self.lib.ldd_copy_small(be.ptr(status), be.ptr(res.d_status), 4 * nloc, be.stream())
+        slot = self._slot(k, self.rank)
+        self.lib.ldd_copy_small(C.c_void_p(slot), be.ptr(self._hmeta[k]), self.meta_bytes, be.stream())
+        self.lib.ldd_peer_signal(C.c_void_p(self._flag(k, self.rank)), s, be.stream())
+        self._last = (k, s)
+
+    def wait(self):
+        """Rank 0: orders the current stream behind the arrival of every rank's last step."""
+        if self.rank == 0 and self._last is not None:
+            k, s = self._last
+            self.lib.ldd_peer_wait(C.c_void_p(self._flag(k, 0)), self.world, 1, s, self.be.stream())
+
+    def to_host(self):
+        """Collective over the ranks: rank 0 returns the fields of the last gather(), ordered by read position."""
+        self.wait()
+        self.be.synchronize()
+        out = None
+        if self.rank == 0 and self._last is not None:
+            k, s = self._last
+            out = []
+            F = self.max_fields
+            for r in range(self.world):
+                raw = RawBuf(self.lib, self._slot(k, r), self.slot_bytes, np.uint8).to_host()
+                m = raw[:self.meta_bytes].view(np.int64).reshape(F, 3)
+                st = raw[self.status_off:self.status_off + 4 * F].view(np.int32)
+                p = raw[self.pic_off:self.pic_off + 2 * F * self.stride].view(np.uint16).reshape(F, self.stride)
+                for i in range(F):
+                    if m[i, 0] < 0:
+                        break
+                    ok = (st[i] & 15) == 0
+                    out.append((int(m[i, 0]), int(m[i, 1]), p[i, :m[i, 2] * self.W].copy() if ok else None))
+            out.sort(key=lambda t: t[0])
+        self.dist.barrier()
+        return out
+
+    def close(self, collective=True):
+        if collective:
+            self.dist.barrier()
+        if self.base:
+            if self.rank == 0:
+                self.be.synchronize()
+                self.lib.ldd_peer_free(C.c_void_p(self.base))
+            else:
+                self.be.synchronize()
+                self.lib.ldd_peer_close(C.c_void_p(self.base))
+            self.base = 0
+
+
+def make_gatherer(cd, rank, world, max_fields, dist, mode=None):
+    """FieldGatherer (NCCL gather) or PeerGatherer (stores over NVLink straight into rank 0's buffer; CUDA only).
+    mode: 'nccl' | 'p2p' | None = environment LDD_GATHER, default 'p2p' on CUDA with a fall back to NCCL."""
+    import os
+    mode = mode or os.environ.get("LDD_GATHER", "p2p")
+    if mode == "p2p" and cd.rf._be.name == "cuda" and world > 1:
+        import torch
+        try:
+            return PeerGatherer(cd, rank, world, max_fields, dist)       # fails on every rank together or on none
+        except RuntimeError:
+            pass
+    return FieldGatherer(cd, rank, world, max_fields, dist)
 
 
 def gather_fields(cd, res, rank, world, max_fields, dist=None):

@@ -25,7 +25,7 @@ def main():
     cd = pipeline.CaptureDecoder(rf)
     r0, r1 = parallel.shard_bounds(ncap, world)[rank]
     lo, hi = parallel.needed_window(cd, ncap, r0, r1)
-    g = parallel.FieldGatherer(cd, rank, world, 8, dist)
+    g = parallel.make_gatherer(cd, rank, world, 8, dist)
     for _ in range(3):                                   # buffers are reused across gathers
         res = cd.decode_range(torch.from_numpy(cap[lo:hi]).cuda(), _lib.FMT_U8, lo, hi - lo, ncap, r0, r1)
         g.gather(res)

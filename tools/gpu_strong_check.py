@@ -43,7 +43,7 @@ def main():
     nch = 2
     step = ((ncap // world) + nch) // nch
     edges = [R0 + i * step for i in range(nch)] + [R1]
-    g = parallel.FieldGatherer(cd, rank, world, 96, dist)
+    g = parallel.make_gatherer(cd, rank, world, 96, dist)
     got = []
     for res in cd.decode_stream(iter([(win, _lib.FMT_U8, lo, hi - lo, ncap, edges[i], edges[i + 1]) for i in range(nch)]), sink=g):
         part = g.to_host()

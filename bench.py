@@ -466,8 +466,9 @@ def measure(a, system, audio, fmt, rank, world, local, dist, clocks_rank0=None, 
         launches_per_step = (2 if a.precision == "mixed" else 1) + 5 + 1 + (1 if audio else 0) + 1 + 2 + 1 + \
             (2 if system == "PAL" else 4) + 1 + (1 if world > 1 else 0)
         out = dict(value=value, ms_per_step=ms_step, realtime_x=value / FS[system] / world, fields_per_step=nfields * world,
-                   gather=(None if gatherer is None else ("peer stores over NVLink into rank 0's buffer (no collective kernel)"
-                                                           if type(gatherer).__name__ == "PeerGatherer" else "NCCL gather")),
+                   gather=(None if gatherer is None else "NCCL gather" if type(gatherer).__name__ != "PeerGatherer" else
+                           "one DMA transfer per step over NVLink into rank 0's mapped buffer (no collective kernel)" if gatherer.push
+                           else "TBC kernels store over NVLink into rank 0's mapped buffer (no collective kernel)"),
                    e2e=dict(value=e2e_val, unit="Msamples/s", h2d_bytes_per_step=int(nraw * raw.dtype.itemsize),
                             d2h_bytes_per_step=int(npic * 2 + naudio), wall_ms_per_step=wall_e2e / a.steps),
                    gpu_launches=launches_per_step * a.steps, self_check=verify, window=(tw0, tw1))

@@ -348,12 +348,15 @@ int ldd_vbi_decode(ldd_handle* h, const float* demod_dev, long long n, const lon
  * ldd_peer_alloc and publishes the 64-byte handle, every other rank maps it (ldd_peer_open) and passes addresses inside it
  * to ldd_pipe_finish as the TBC kernel's destination -- fields are stored straight into the root's HBM.  ldd_peer_signal
  * (a stream-ordered flag write behind a system-wide fence) and ldd_peer_wait (a kernel that spins until n flags, `stride`
- * ints apart, have reached `value`) order producers and consumer; ldd_peer_read is a blocking device-to-host copy. */
+ * ints apart, have reached `value`) order producers and consumer; ldd_peer_read is a blocking device-to-host copy.
+ * ldd_peer_copy is the alternative to storing through the mapping from a kernel: one stream-ordered DMA transfer
+ * (copy engine over NVLink, no SMs on either side) from a local buffer into the mapped one. */
 int ldd_peer_alloc(size_t nbytes, void** dev_ptr, unsigned char* handle64);
 int ldd_peer_open(const unsigned char* handle64, void** dev_ptr);
 int ldd_peer_close(void* dev_ptr);
 int ldd_peer_free(void* dev_ptr);
 int ldd_peer_read(void* host_dst, const void* dev_src, size_t nbytes);
+int ldd_peer_copy(void* dst_dev, const void* src_dev, size_t nbytes, void* stream);
 int ldd_peer_signal(int* flag_dev, int value, void* stream);
 int ldd_peer_wait(const int* flags_dev, int n, int stride, int value, void* stream);
 

@@ -136,6 +136,7 @@ SIGNATURES.update({
     "ldd_peer_close": (C.c_int, [C.c_void_p]),
     "ldd_peer_free": (C.c_int, [C.c_void_p]),
     "ldd_peer_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ldd_peer_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ldd_peer_signal": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ldd_peer_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ldd_pipe_table_bytes": (C.c_int, [C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),

@@ -610,6 +610,19 @@ int ldd_peer_read(void* host_dst, const void* dev_src, size_t nbytes) {
     return cudaMemcpy(host_dst, dev_src, nbytes, cudaMemcpyDeviceToHost) == cudaSuccess ? LDD_OK : LDD_ECUDA;
 }
 
+int ldd_peer_copy(void* dst_dev, const void* src_dev, size_t nbytes, void* stream) {
+    // one DMA transfer between two device allocations (either may be a peer mapping): the copy engines move it over
+    // NVLink, no SM of either GPU is involved
+    if (!dst_dev || !src_dev) return LDD_EINVAL;
+    if (nbytes == 0) return LDD_OK;
+#ifdef LDD_EMU
+    memcpy(dst_dev, src_dev, nbytes);
+    return LDD_OK;
+#else
+    return cudaMemcpyAsync(dst_dev, src_dev, nbytes, cudaMemcpyDefault, (cudaStream_t)stream) == cudaSuccess ? LDD_OK : LDD_ECUDA;
+#endif
+}
+
 int ldd_peer_signal(int* flag_dev, int value, void* stream) {
     if (!flag_dev) return LDD_EINVAL;
     LDD_LAUNCH(peer_signal_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, (volatile int*)flag_dev, value);

@@ -186,22 +186,31 @@ class RawBuf:
 
 
 class PeerGatherer:
-    """The gather of per-field outputs to rank 0 WITHOUT a collective: rank 0 publishes its receive buffer (CUDA IPC),
-    every rank maps it and hands the decoder an address inside it as the TBC kernel's destination (buffers()), so the
-    resampling kernel of rank g stores its uint16 fields straight into rank 0's HBM over NVLink -- compute and transfer
-    are one kernel, rank 0 spends no SMs on receiving, and there is no staging copy anywhere.  Per-field metadata and a
-    per-rank step flag follow on the same stream (ldd_copy_small, ldd_peer_signal).  Flow control: NBUF slots per rank;
-    before a rank's kernels write slot k for step s they wait (on the device) until rank 0 has released step s - NBUF
-    of that slot, which it does when it moves on to step s itself (or when its consumer calls to_host()).
-    Same interface as FieldGatherer."""
+    """The gather of per-field outputs to rank 0 WITHOUT a collective: rank 0 publishes its receive buffer (CUDA IPC) and
+    every rank maps it.  Two ways of filling it:
+
+    * push=False ("p2p"): the decoder gets an address inside the mapping as the TBC kernel's destination (buffers()), so
+      the resampling kernel of rank g stores its uint16 fields straight into rank 0's HBM over NVLink -- compute and
+      transfer are one kernel and there is no staging copy.  Measured on 8 B200s this LOSES to the NCCL gather (170 vs
+      185 Gsamples/s): seven ranks' remote stores keep their TBC CTAs resident ~3x longer, SMs the next range's
+      demodulation wants.
+    * push=True ("push"): the TBC kernel writes a local send buffer (double-buffered, as with NCCL) and ONE DMA transfer
+      per step (ldd_peer_copy on a copy stream: copy engine over NVLink) moves the used part of it into the rank's slot
+      of rank 0's buffer -- no SM of either GPU takes part in the transfer.
+
+    Per-field metadata and a per-rank step flag follow on the same stream (ldd_copy_small, ldd_peer_signal).  Flow
+    control: NBUF slots per rank; before slot k is written for step s the writer waits (on the device) until rank 0 has
+    released step s - NBUF of that slot, which it does when it moves on to step s itself (or when its consumer calls
+    to_host()).  Same interface as FieldGatherer."""
 
     NBUF = 2
     HEADER = 4096
 
-    def __init__(self, cd, rank, world, max_fields, dist):
+    def __init__(self, cd, rank, world, max_fields, dist, push=False):
         import torch
         self.torch = torch
         self.cd, self.rank, self.world, self.max_fields, self.dist = cd, rank, world, max_fields, dist
+        self.push = bool(push)
         rf = cd.rf
         self.be = be = rf._be
         self.lib = be.lib
@@ -236,6 +245,10 @@ class PeerGatherer:
         self._step = 0
         self._last = None
         self._cache = None
+        if self.push:
+            self.local = [torch.zeros(self.slot_bytes, dtype=torch.uint8, device=be.device) for _ in range(self.NBUF)]
+            self.copy_stream = be.new_stream()
+            self.copy_done = [None] * self.NBUF
 
     # header: ack[k] at 4 k ; flags[k][r] at 256 + 4 (k world + r)
     def _ack(self, k):
@@ -259,8 +272,18 @@ class PeerGatherer:
         if self.rank == 0:
             if s > self.NBUF:
                 self.lib.ldd_peer_signal(C.c_void_p(self._ack(k)), s - self.NBUF, st)       # slot k's old contents may go
-        elif s > self.NBUF:
+        elif s > self.NBUF and not self.push:
             self.lib.ldd_peer_wait(C.c_void_p(self._ack(k)), 1, 1, s - self.NBUF, st)
+        if self.push:
+            # the kernels write the local buffer; it is free again when its previous transfer is over
+            if self.copy_done[k] is not None:
+                be.stream_wait_event(stream if stream is not None else be.current_stream_obj(), self.copy_done[k])
+                self.copy_done[k] = None
+            b = self.local[k]
+            pic = b[self.pic_off:self.pic_off + 2 * self.max_fields * self.stride].view(self.torch.uint16)
+            status = b[self.status_off:self.status_off + 4 * self.max_fields].view(self.torch.int32)
+            self._cache = (s, pic, status)
+            return pic, status
         slot = self._slot(k, self.rank)
         pic = RawBuf(self.lib, slot + self.pic_off, self.max_fields * self.stride, np.uint16)
         status = RawBuf(self.lib, slot + self.status_off, self.max_fields, np.int32)
@@ -290,8 +313,22 @@ class PeerGatherer:
                 self.lib.ldd_copy_small(be.ptr(pic), be.ptr(res.d_pic), 2 * n, be.stream())
                 self.lib.ldd_copy_small(be.ptr(status), be.ptr(res.d_status), 4 * nloc, be.stream())
         slot = self._slot(k, self.rank)
-        self.lib.ldd_copy_small(C.c_void_p(slot), be.ptr(self._hmeta[k]), self.meta_bytes, be.stream())
-        self.lib.ldd_peer_signal(C.c_void_p(self._flag(k, self.rank)), s, be.stream())
+        if self.push:
+            self.lib.ldd_copy_small(be.ptr(self.local[k]), be.ptr(self._hmeta[k]), self.meta_bytes, be.stream())
+            ready = be.record_event()
+            be.stream_wait_event(self.copy_stream, ready)
+            cs = C.c_void_p(self.copy_stream.cuda_stream)
+            if self.rank != 0 and s > self.NBUF:
+                self.lib.ldd_peer_wait(C.c_void_p(self._ack(k)), 1, 1, s - self.NBUF, cs)
+            rc = self.lib.ldd_peer_copy(C.c_void_p(slot), be.ptr(self.local[k]), self.pic_off + 2 * nloc * self.stride, cs)
+            if rc:
+                raise RuntimeError("ldd_peer_copy failed (%d)" % rc)
+            self.lib.ldd_peer_signal(C.c_void_p(self._flag(k, self.rank)), s, cs)
+            with be.stream_ctx(self.copy_stream):
+                self.copy_done[k] = be.record_event()
+        else:
+            self.lib.ldd_copy_small(C.c_void_p(slot), be.ptr(self._hmeta[k]), self.meta_bytes, be.stream())
+            self.lib.ldd_peer_signal(C.c_void_p(self._flag(k, self.rank)), s, be.stream())
         self._last = (k, s)
 
     def wait(self):
@@ -336,15 +373,18 @@ class PeerGatherer:
             self.base = 0
 
 
+DEFAULT_GATHER = "nccl"      # measured on 8 B200s: NCCL 185, kernel stores through the mapping 170 Gsamples/s
+
+
 def make_gatherer(cd, rank, world, max_fields, dist, mode=None):
-    """FieldGatherer (NCCL gather) or PeerGatherer (stores over NVLink straight into rank 0's buffer; CUDA only).
-    mode: 'nccl' | 'p2p' | None = environment LDD_GATHER, default 'p2p' on CUDA with a fall back to NCCL."""
+    """FieldGatherer (NCCL gather) or PeerGatherer (rank 0's buffer mapped by every rank; CUDA only).
+    mode: 'nccl' | 'push' (one DMA transfer per step into the mapping) | 'p2p' (TBC kernels store through the mapping) |
+    None = environment LDD_GATHER, default DEFAULT_GATHER; the peer modes fall back to NCCL when the mapping fails."""
     import os
-    mode = mode or os.environ.get("LDD_GATHER", "p2p")
-    if mode == "p2p" and cd.rf._be.name == "cuda" and world > 1:
-        import torch
+    mode = mode or os.environ.get("LDD_GATHER", DEFAULT_GATHER)
+    if mode in ("p2p", "push") and cd.rf._be.name == "cuda" and world > 1:
         try:
-            return PeerGatherer(cd, rank, world, max_fields, dist)       # fails on every rank together or on none
+            return PeerGatherer(cd, rank, world, max_fields, dist, push=(mode == "push"))   # fails on every rank together or on none
         except RuntimeError:
             pass
     return FieldGatherer(cd, rank, world, max_fields, dist)

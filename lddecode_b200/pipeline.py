@@ -221,8 +221,10 @@ class HostStreamDecoder:
         self.in_free = [None, None]         # event: the demodulation that read d_in[k] has finished
         self.nup = self.nlaunch = self.nfin = 0
 
-    def upload(self, host_buf, n, nelem=None):
-        """n: samples of the chunk; nelem: elements of host_buf to copy (defaults to n; packed formats differ)."""
+    def upload(self, host_buf, n, nelem=None, window=None):
+        """n: samples of the chunk; nelem: elements of host_buf to copy (defaults to n; packed formats differ).
+        window = (cap_base, ncap_total, r0, r1): the chunk holds samples [cap_base, cap_base + n) of a longer capture and
+        is decoded as the range [r0, r1) of it (decode_range's arguments); default: the chunk is a capture by itself."""
         be, k = self.be, self.nup % 2
         self.nup += 1
         ne = n if nelem is None else nelem
@@ -231,14 +233,15 @@ class HostStreamDecoder:
         with be.stream_ctx(self.up):
             be.copy_async(self.d_in[k][:ne], host_buf[:ne])
             ev = be.record_event()
-        return (k, int(n), ev)
+        return (k, int(n), ev, window)
 
     def launch(self, ticket):
         """Enqueue the demodulation and the sync-peak chase of an uploaded chunk."""
         be, cd = self.be, self.cd
-        k, n, ev = ticket
+        k, n, ev, window = ticket
         be.stream_wait_event(be.current_stream_obj(), ev)
-        pend = cd._launch(cd.rf, cd._slot(self.nlaunch % 2, n), self.d_in[k], self.fmt, 0, n, n, 0, n + 1)
+        cap_base, ncap_total, r0, r1 = window if window is not None else (0, n, 0, n + 1)
+        pend = cd._launch(cd.rf, cd._slot(self.nlaunch % 2, n), self.d_in[k], self.fmt, cap_base, n, ncap_total, r0, r1)
         self.nlaunch += 1
         self.in_free[k] = be.record_event()
         return pend
@@ -303,6 +306,113 @@ class HostStreamDecoder:
                 yield self.fetch(prev)
             prev, pend = job, nxt
         yield self.fetch(prev)
+
+
+# bytes per `group` samples of the capture formats (lddutils.py:131-229)
+FILE_FORMATS = {_lib.FMT_U8: (1, 1, np.uint8), _lib.FMT_S16: (2, 1, np.int16), _lib.FMT_U16: (2, 1, np.uint16),
+                _lib.FMT_R30: (4, 3, np.uint8), _lib.FMT_LDS40: (5, 4, np.uint8)}
+FORMAT_OF_SUFFIX = {".lds": _lib.FMT_LDS40, ".r30": _lib.FMT_R30, ".r16": _lib.FMT_S16, ".raw": _lib.FMT_U8, ".u8": _lib.FMT_U8}
+
+
+class FileStreamDecoder:
+    """Decodes a capture FILE from start to end (the reference's loaders, lddutils.py:131-229, and
+    the frame loop of lddecode.py:88-98): a reader thread fills page-locked buffers with the file's own bytes (packed
+    10-bit formats stay packed: the unpack is fused into the demodulation's block load), HostStreamDecoder uploads,
+    decodes and downloads them as consecutive read-position ranges of ONE capture, so the fields that come out are
+    exactly those of decoding the whole file at once, in order, whatever the chunk size.
+
+        for res, pics in FileStreamDecoder(cd, "side1.lds"):          # pics: uint16 [nfields, out_stride] host view
+            for k, j in enumerate(res.located): write(pics[k, :res.infos[j].linecount * outlinelen])
+    """
+
+    def __init__(self, cd, path, fmt=None, chunk_samples=None, first_sample=0, nsamples=None, max_fields=None):
+        import os as _os
+        self.cd, self.path = cd, path
+        self.fmt = FORMAT_OF_SUFFIX[_os.path.splitext(path)[1].lower()] if fmt is None else fmt
+        self.bpg, self.group, self.np_dtype = FILE_FORMATS[self.fmt]
+        rf = cd.rf
+        fsize = _os.path.getsize(path)
+        total = fsize // self.bpg * self.group                         # samples in the file
+        self.ncap = total if nsamples is None else min(total, first_sample + nsamples)
+        self.first = first_sample
+        # chunk = the read positions one range owns; ~1 s by default, a multiple of 12 samples (whole .r30 / .lds groups)
+        C_ = int(chunk_samples or rf.freq_hz)
+        self.chunk = max(C_ // 12 * 12, 12 * rf.blocklen)
+        r0s = list(range(first_sample, max(self.ncap - 1, first_sample + 1), self.chunk))
+        self.ranges = [(r0, min(r0 + self.chunk, self.ncap + 1) if i + 1 < len(r0s) else self.ncap + 1) for i, r0 in enumerate(r0s)]
+        from . import parallel
+        self.windows = []
+        span = 0
+        for r0, r1 in self.ranges:
+            lo, hi = parallel.needed_window(cd, self.ncap, r0, r1)
+            lo = lo // 12 * 12
+            hi = min(self.ncap, -(-hi // 12) * 12)
+            self.windows.append((lo, hi))
+            span = max(span, hi - lo)
+        self.span = span
+        fields = max_fields or int(self.chunk / cd.field_samples) + 8
+        elem = np.dtype(self.np_dtype).itemsize
+        self.nelem_max = -(-span // self.group) * self.bpg // elem + 16
+        self.sd = HostStreamDecoder(cd, self.fmt, span, fields, np_dtype=self.np_dtype, nbytes_max=self.nelem_max)
+        self.be = rf._be
+        self.nbuf = 4
+        self.bufs = [self.be.pinned(self.nelem_max, self.np_dtype) for _ in range(self.nbuf)]
+
+    def _reader(self, free_q, full_q):
+        elem = np.dtype(self.np_dtype).itemsize
+        try:
+            with open(self.path, "rb", buffering=0) as f:
+                for i, (lo, hi) in enumerate(self.windows):
+                    b = free_q.get()
+                    if b is None:
+                        return
+                    nbytes = -(-(hi - lo) // self.group) * self.bpg
+                    f.seek(lo // self.group * self.bpg)
+                    view = memoryview(self.be.host_view(self.bufs[b]).view(np.uint8))[:nbytes]
+                    got = 0
+                    while got < nbytes:
+                        m = f.readinto(view[got:])
+                        if not m:
+                            break
+                        got += m
+                    full_q.put((i, b, got // elem))
+        finally:
+            full_q.put(None)
+
+    def __iter__(self):
+        import queue
+        import threading
+        free_q, full_q = queue.Queue(), queue.Queue()
+        for b in range(self.nbuf):
+            free_q.put(b)
+        th = threading.Thread(target=self._reader, args=(free_q, full_q), daemon=True)
+        th.start()
+        sd = self.sd
+
+        def next_launch():
+            """Next chunk the reader has ready -> (launched range, its host buffer), or None at the end of the file."""
+            item = full_q.get()
+            if item is None:
+                return None
+            i, b, nelem = item
+            (lo, hi), (r0, r1) = self.windows[i], self.ranges[i]
+            return sd.launch(sd.upload(self.bufs[b], hi - lo, nelem, window=(lo, self.ncap, r0, r1))), b
+
+        try:
+            pend, prev = next_launch(), None
+            while pend is not None:
+                nxt = next_launch()                   # the GPU demodulates chunk k+1 ...
+                job = sd.finish(pend[0])              # ... while the host walks chunk k (waits for its peak list, so its
+                free_q.put(pend[1])                   # upload is over: the reader may refill the buffer)
+                if prev is not None:
+                    yield sd.fetch(prev)
+                prev, pend = job, nxt
+            if prev is not None:
+                yield sd.fetch(prev)
+        finally:
+            free_q.put(None)
+            # the reader may sit in full_q.put / free_q.get: both queues are unbounded and the sentinel ends it
+            th.join(timeout=5)
 
 
 class CaptureDecoder:

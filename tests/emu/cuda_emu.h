@@ -83,6 +83,7 @@ static inline int __syncthreads_or(int pred) {
 }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
+static inline void __threadfence_system() {}
 
 template <class T>
 static inline T emu_xchg(T v, int src) {

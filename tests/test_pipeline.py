@@ -145,6 +145,36 @@ def test_host_stream_decoder_downloads_audio(backend):
     assert np.array_equal(res.audio_host[0], want[0]) and np.array_equal(res.audio_host[1], want[1])
 
 
+@pytest.mark.parametrize("fmt", ["lds", "u8"])
+def test_file_stream_decoder_equals_whole_decode(backend, tmp_path, fmt):
+    """FileStreamDecoder (reader thread -> page-locked buffers -> HostStreamDecoder, the file worked through as
+    consecutive read-position ranges of one capture; lddutils.py:131-229 loaders, lddecode.py:88-98 loop) yields exactly
+    the fields of decoding the whole file at once, in order, from packed .lds bytes and from 8-bit samples."""
+    fs = 8 * 315 / 88
+    n = 2400000
+    if fmt == "lds":
+        s = synth.SynthRF("NTSC", fs, seed=21, bits=10).generate(n)
+        raw, f, path = synth.pack_lds(s), _lib.FMT_LDS40, tmp_path / "cap.lds"
+    else:
+        s = synth.SynthRF("NTSC", fs, seed=21).generate(n)
+        raw, f, path = s, _lib.FMT_U8, tmp_path / "cap.u8"
+    raw.tofile(str(path))
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=False, _backend=backend, precision="mixed")
+    cd = pipeline.CaptureDecoder(rf)
+    want = cd.pictures(cd.decode(backend.to_device(raw), f, n))
+    assert len(want) >= 3
+    fsd = pipeline.FileStreamDecoder(cd, str(path), chunk_samples=700000)
+    assert fsd.fmt == f and fsd.ncap == n and len(fsd.ranges) == 4
+    got = []
+    for res, pics in fsd:
+        assert not np.any(res.status_host & 15)
+        got += [(int(res.readsamples[j]), int(res.infos[j].istop), pics[k, :res.infos[j].linecount * 910].copy())
+                for k, j in enumerate(res.located)]
+    assert [g[0] for g in got] == [w[0] for w in want]
+    for a, b in zip(got, want):
+        assert a[1] == b[1] and np.array_equal(a[2], b[2])
+
+
 def test_two_rank_gloo_gather():
     """world_size 2 over gloo on the CPU (emulated kernels): shard, decode, gather on rank 0."""
     script = os.path.join(ROOT, "tests", "dist_worker.py")

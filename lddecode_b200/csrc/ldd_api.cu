@@ -75,6 +75,29 @@ __global__ void hv_kernel(const Cx<double>* __restrict__ rf, const Cx<double>* _
     hv32[k] = mk<float>((float)v.x, (float)v.y);
 }
 
+// dst[part M + pos(k)] = src[part M + k] for nparts parts of M = 8192 entries (ldd_fft2.cuh's digit-permuted order), the
+// `tail` entries behind them copied as they are
+template <class T>
+__global__ void permute_kernel(const Cx<T>* __restrict__ src, Cx<T>* __restrict__ dst, int nparts, int tail) {
+    const int M = f2::M;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nparts * M) dst[(k / M) * M + f2::pos_of_idx(k % M)] = src[k];
+    else if (k < nparts * M + tail) dst[k] = src[k];
+}
+
+// (re)builds the permuted float32 copy (and, for the mixed lane, the float64 one) on `stream`; no-op for other block lengths
+int permuted_copy(ldd_handle* h, void* const* src /*[2]: float64, float32*/, void** dst32, void** dst64, int nparts, int tail, cudaStream_t stream) {
+    if (h->cfg.blocklen != 2 * f2::M || !src[1]) return LDD_OK;
+    const int n = nparts * f2::M + tail;
+    if (!*dst32) CUDA_TRY(h, cudaMalloc(dst32, (size_t)n * sizeof(Cx<float>)));
+    LDD_LAUNCH(permute_kernel<float>, dim3((n + 255) / 256), dim3(256), 0, stream, (const Cx<float>*)src[1], (Cx<float>*)*dst32, nparts, tail);
+    if (dst64 && h->cfg.precision == LDD_PREC_MIXED && src[0]) {
+        if (!*dst64) CUDA_TRY(h, cudaMalloc(dst64, (size_t)n * sizeof(Cx<double>)));
+        LDD_LAUNCH(permute_kernel<double>, dim3((n + 255) / 256), dim3(256), 0, stream, (const Cx<double>*)src[0], (Cx<double>*)*dst64, nparts, tail);
+    }
+    return launch_status(h, "permute_kernel");
+}
+
 }  // namespace
 
 extern "C" {
@@ -217,6 +240,9 @@ void ldd_destroy(ldd_handle* h) {
     cudaFree(h->d_rfbase);
     cudaFree(h->d_mtf);
     cudaFree(h->d_lnM[0]); cudaFree(h->d_lnM[1]);
+    cudaFree(h->d_HvP); cudaFree(h->d_lnMP);
+    cudaFree(h->d_HvP64); cudaFree(h->d_lnMP64); cudaFree(h->d_FP64_05);
+    for (int m = 0; m < 4; ++m) cudaFree(h->d_FP[m]);
     cudaFree(h->scratch64);
     cudaFree(h->d_flags);
     cudaFree(h->d_queue);
@@ -236,6 +262,8 @@ int ldd_set_filter(ldd_handle* h, int id, const double* table, int n) {
             t.assign(src, src + N);
             int rc = upload_both(h, t, h->d_Hv);
             if (rc) return rc;
+            rc = permuted_copy(h, h->d_Hv, &h->d_HvP, &h->d_HvP64, 2, 0, 0);
+            if (rc) return rc;
             // kept as the base of ldd_set_mtf_level
             h->mtf_level_set = 0.0;
             if (!h->d_rfbase) CUDA_TRY(h, cudaMalloc(&h->d_rfbase, (size_t)N * sizeof(Cx<double>)));
@@ -251,6 +279,8 @@ int ldd_set_filter(ldd_handle* h, int id, const double* table, int n) {
             t.resize(N);
             for (int k = 0; k < N; ++k) t[k] = mk<double>(std::log(std::hypot(src[k].x, src[k].y)), std::atan2(src[k].y, src[k].x));
             int rc = upload_both(h, t, h->d_lnM);
+            if (rc) return rc;
+            rc = permuted_copy(h, h->d_lnM, &h->d_lnMP, &h->d_lnMP64, 2, 0, 0);
             if (rc) return rc;
             break;
         }
@@ -271,6 +301,8 @@ int ldd_set_filter(ldd_handle* h, int id, const double* table, int n) {
             }
             h->dc[m] = src[0].x;
             int rc = upload_both(h, t, h->d_F[m]);
+            if (rc) return rc;
+            rc = permuted_copy(h, h->d_F[m], &h->d_FP[m], m == 1 ? &h->d_FP64_05 : nullptr, 1, 1, 0);
             if (rc) return rc;
             break;
         }
@@ -304,7 +336,9 @@ int ldd_set_mtf_level(ldd_handle* h, double level, void* stream) {
     h->mtf_level_set = level;
     LDD_LAUNCH(hv_kernel, dim3((N + 255) / 256), dim3(256), 0, (cudaStream_t)stream, (const Cx<double>*)h->d_rfbase,
                (const Cx<double>*)h->d_mtf, level, (Cx<double>*)h->d_Hv[0], (Cx<float>*)h->d_Hv[1], N);
-    return launch_status(h, "hv_kernel");
+    int rc = launch_status(h, "hv_kernel");
+    if (rc) return rc;
+    return permuted_copy(h, h->d_Hv, &h->d_HvP, &h->d_HvP64, 2, 0, (cudaStream_t)stream);
 }
 
 int ldd_set_mtf_ramp(ldd_handle* h, double pos0_sample, double period_samples, double step_per_period,
@@ -378,6 +412,13 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
     p.nblocks = (int)nblocks;
     p.WM = h->d_WM[lane]; p.WN = h->d_WN[lane]; p.Hv = h->d_Hv[lane];
     p.lnM = h->d_lnM[lane];
+    // the in-place float32 block (ldd_demod8k.cuh) runs when its permuted tables exist; LDD_STOCKHAM_BLOCK=1 keeps the
+    // out-of-place plan (comparison runs)
+    if (!getenv("LDD_STOCKHAM_BLOCK")) {
+        p.HvP = h->d_HvP; p.lnMP = h->d_lnMP;
+        for (int m = 0; m < nfilt; ++m) p.FP[m] = h->d_FP[m];
+        for (int m = 0; m < nfilt; ++m) if (!p.FP[m]) p.HvP = nullptr;
+    }
     if (h->ramp_period > 0.0 && h->d_lnM[0] && blockcut == c.blockcut) {
         // plane sample k of this launch <-> capture sample first_sample + blockcut + k
         p.mtf_pos0 = h->ramp_pos0 - (double)(first_sample + blockcut);
@@ -455,6 +496,12 @@ static int run_demod(ldd_handle* h, const void* rf_dev, int fmt, long long rf_ba
         q.scratch = h->scratch64; q.scratch_per_cta = h->scratch64_per_cta;
         q.flag_list = nullptr; q.flag_count = nullptr; q.flag_margin = 0.0;
         q.only05 = 1; q.A = 0;
+        // float64 permuted tables: the re-run takes the in-place block too (LDD_STOCKHAM_RERUN=1: the generic float64 block)
+        q.HvP = nullptr; q.lnMP = nullptr;
+        for (int m = 0; m < 4; ++m) q.FP[m] = nullptr;
+        if (p.HvP && h->d_HvP64 && h->d_FP64_05 && !getenv("LDD_STOCKHAM_RERUN")) {
+            q.HvP = h->d_HvP64; q.lnMP = h->d_lnMP64; q.FP[1] = h->d_FP64_05;
+        }
     }
     if (mixed && h->d_queue && demod_mixed_fused_ok(p, h->threads, h->smem_bytes, h->sp_bytes)) {
         // one launch: dynamic block queue, flagged blocks re-run in float64 by the CTA that found them

@@ -27,6 +27,17 @@ template <class U> __device__ inline void st_stream(U* p, U v) { *p = v; }
 template <class U> __device__ inline void st_stream(U* p, U v) { __stcs(p, v); }
 #endif
 
+// Phase timing (profiling builds only: -DLDD_PHASE_TIMING; tools/gpu_demod_phases.py): thread 0 of every CTA adds the
+// clock cycles between consecutive marks to g_phase[lane offset + phase].
+#ifdef LDD_PHASE_TIMING
+__device__ unsigned long long g_phase[64];
+#define PHASE_BEGIN() long long ph_last = clock64()
+#define PHASE(i) do { if (threadIdx.x == 0) { long long ph_t = clock64(); atomicAdd(&g_phase[(sizeof(T) == 8 ? 32 : 0) + (i)], (unsigned long long)(ph_t - ph_last)); ph_last = ph_t; } } while (0)
+#else
+#define PHASE_BEGIN()
+#define PHASE(i)
+#endif
+
 template <class T> struct Math;
 template <> struct Math<double> {
     static __device__ inline double atan2(double y, double x) { return ::atan2(y, x); }
@@ -133,8 +144,10 @@ __device__ inline void tangle(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __restrict_
 
 // Compile-time variants (M, NT constants): the table values of a batch of iterations are fetched before
 // the batch's arithmetic, so that a thread has several L2 round trips in flight instead of one per iteration.
+// wb != nullptr: *wb = W_N^tid, the twiddles W_N^(tid + j NT) are products with constants instead of table loads
+// (M / 2 / NT == 8 only: the float32 lane of the default block length).
 template <class T, bool PAD, int M, int NT>
-__device__ inline void untangle_static(Cx<T>* Z, const Cx<T>* __restrict__ WN, int tid) {
+__device__ inline void untangle_static(Cx<T>* Z, const Cx<T>* __restrict__ WN, int tid, const Cx<T>* wb = nullptr) {
     constexpr int IT = (M / 2) / NT, B = sizeof(T) == 4 ? IT : (IT % 4 == 0 ? 4 : 1);
     const T half = (T)0.5;
     LDD_UNROLL
@@ -142,8 +155,14 @@ __device__ inline void untangle_static(Cx<T>* Z, const Cx<T>* __restrict__ WN, i
         // table values and the shared-memory operands of the whole batch first (independent loads in flight), then
         // the arithmetic and the stores (the compiler may not move a shared load above an earlier shared store)
         Cx<T> w[B], za[B], zb[B];
-        LDD_UNROLL
-        for (int i = 0; i < B; ++i) w[i] = WN[tid + (it0 + i) * NT];
+        if (IT == 8 && wb) {
+            const Cx<T> base = *wb;
+            LDD_UNROLL
+            for (int i = 0; i < B; ++i) w[i] = wn_of<T>(base, it0 + i);
+        } else {
+            LDD_UNROLL
+            for (int i = 0; i < B; ++i) w[i] = WN[tid + (it0 + i) * NT];
+        }
         LDD_UNROLL
         for (int i = 0; i < B; ++i) {
             za[i] = Z[pidx<PAD>(tid) + (it0 + i) * pstride<PAD>(NT)];
@@ -170,9 +189,12 @@ __device__ inline void untangle_static(Cx<T>* Z, const Cx<T>* __restrict__ WN, i
 }
 
 template <class T, bool PAD, int M, int NT>
-__device__ inline void tangle_static(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __restrict__ F, const Cx<T>* __restrict__ WN, int tid) {
+__device__ inline void tangle_static(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __restrict__ F, const Cx<T>* __restrict__ WN, int tid,
+                                     const Cx<T>* wb = nullptr) {
     constexpr int IT = (M / 2) / NT, B = (IT % 4 == 0) ? (sizeof(T) == 4 ? 4 : 2) : 1;
     const T half = (T)0.5;
+    const bool cw = IT == 8 && wb;
+    const Cx<T> wbase = cw ? *wb : mk<T>((T)1, (T)0);
     LDD_UNROLL
     for (int it0 = 0; it0 < IT; it0 += B) {
         Cx<T> fa[B], fb[B], w[B], da[B], db[B];
@@ -181,7 +203,7 @@ __device__ inline void tangle_static(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __re
             const int k = tid + (it0 + i) * NT;
             fa[i] = F[k];
             fb[i] = F[M - k];
-            w[i] = WN[k];
+            w[i] = cw ? wn_of<T>(wbase, it0 + i) : WN[k];
         }
         LDD_UNROLL
         for (int i = 0; i < B; ++i) {
@@ -215,8 +237,6 @@ __device__ inline void tangle_static(const Cx<T>* D, Cx<T>* Q, const Cx<T>* __re
 // bound by L2 traffic, ~7 TB/s chip-wide at 9 Gsamples/s).
 // CM != 0: the transform length M is the compile-time constant CM (and blockDim.x == NT, plan = radix 16
 // while possible): the default block length gets fully constant-folded indexing.
-struct TrueTag { static constexpr bool value = true; };
-struct FalseTag { static constexpr bool value = false; };
 
 // Per-kernel constants of the sync scan (step J): a thread owns CH consecutive samples.
 struct ScanConsts {
@@ -238,12 +258,132 @@ __device__ inline ScanConsts scan_consts(const DemodParams& p, int N, int nthr, 
     return k;
 }
 
+struct TrueTag { static constexpr bool value = true; };
+struct FalseTag { static constexpr bool value = false; };
+
+// Tables of the sync recursion's input term (shared memory, filled once per CTA): the term b0 s[n] + b1 s[n-1] takes four
+// values, and four steps of the recursion from a zero state take 32 (five consecutive decisions).
+struct ScanTab {
+    double u[4];       // index s[n] << 1 | s[n-1]
+    double q[32];      // index bits 0..4 = s[n-1], s[n], .., s[n+3]: ((u_n c + u_n+1) c + u_n+2) c + u_n+3
+    double c4;         // c^4
+};
+__device__ inline void scan_tab_fill(ScanTab& tb, const DemodParams& p, int tid) {
+    const double c = p.fp_c;
+    if (tid < 4) tb.u[tid] = ((tid & 2) ? p.fp_b0 : 0.0) + ((tid & 1) ? p.fp_b1 : 0.0);
+    if (tid < 32) {
+        double a = 0.0;
+        for (int j = 0; j < 4; ++j) {
+            const int two = (tid >> j) & 3;
+            a = fma(c, a, ((two & 2) ? p.fp_b0 : 0.0) + ((two & 1) ? p.fp_b1 : 0.0));
+        }
+        tb.q[tid] = a;
+    }
+    if (tid == 0) tb.c4 = (c * c) * (c * c);
+}
+
+// Step J for 32 samples per thread (the default block length on 512 threads), shared by every lane so that equal sync
+// decisions give bit-equal demod_sync planes: `mask` holds this thread's 32 decisions (bit i = sample 32 tid + i); the
+// recursion y[n] = c y[n-1] + (b0 s[n] + b1 s[n-1]) runs in float64.  Its input term is looked up by the decision bits
+// (tb.u); the chunk sums advance four samples per step (tb.q).  ys: float64 staging of N + N/32 doubles for the
+// coalesced store.  Contains barriers.
+__device__ inline void sync_scan32(const DemodParams& p, const ScanConsts& sc, const ScanTab& tb, unsigned mask, double* ys, int keep0,
+                                   int keep1, long long o, double* s_warp, double* s_total, unsigned* s_last) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+    const double c = sc.c;
+    typedef float T;
+    PHASE_BEGIN();
+    // decision of the sample before this thread's chunk (circular)
+    unsigned up = __shfl_up_sync(0xffffffffu, mask, 1);
+    if (lane == 31) s_last[warp] = mask;
+    __syncthreads();
+    PHASE(16);
+    if (lane == 0) up = s_last[warp == 0 ? (nthr >> 5) - 1 : warp - 1];
+    const unsigned long long m2 = ((unsigned long long)mask << 1) | (unsigned long long)(up >> 31);     // bit i: s[i-1], bit i+1: s[i]
+    double acc = 0.0;
+    {
+        const double c4 = tb.c4;
+        double q[8];
+        LDD_UNROLL
+        for (int g = 0; g < 8; ++g) q[g] = tb.q[(unsigned)(m2 >> (4 * g)) & 31u];
+        LDD_UNROLL
+        for (int g = 0; g < 8; ++g) acc = fma(c4, acc, q[g]);
+    }
+    PHASE(17);
+    // inclusive scan of the affine maps y -> Ach*y + acc over threads
+    double incl = acc, mult = sc.Ach;
+    for (int d = 1; d < 32; d <<= 1) {
+        double upv = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += mult * upv;
+        mult *= mult;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    PHASE(18);
+    // state entering this warp (zero initial state): carry_w = sum_{v<w} A32^(w-1-v) s_warp[v], by a scan over the warp
+    // sums that every warp repeats for itself (the sequential loop cost the last warp 15 dependent steps)
+    double carry;
+    {
+        const int nw = nthr >> 5;
+        double ci = lane < nw ? s_warp[lane] : 0.0, cm = sc.A32;
+        for (int d = 1; d < nw; d <<= 1) {
+            double upv = __shfl_up_sync(0xffffffffu, ci, d);
+            if (lane >= d) ci += cm * upv;
+            cm *= cm;
+        }
+        carry = __shfl_sync(0xffffffffu, ci, warp > 0 ? warp - 1 : 0);
+        if (warp == 0) carry = 0.0;
+    }
+    if (tid == nthr - 1) {
+        double tot = sc.AchLane1 * carry + incl;
+        *s_total = tot / (1.0 - sc.cN);     // periodic steady state y[-1]
+    }
+    __syncthreads();
+    PHASE(19);
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    double st = (lane == 0 ? 0.0 : excl) + sc.AchLane * carry + sc.cn0 * *s_total;
+    double* yt = ys + 33 * tid;          // n + (n >> 5) for n = 32 tid + i
+    LDD_UNROLL
+    for (int i0 = 0; i0 < 32; i0 += 8) {
+        double u[8];
+        LDD_UNROLL
+        for (int i = 0; i < 8; ++i) u[i] = tb.u[(unsigned)(m2 >> (i0 + i)) & 3u];
+        LDD_UNROLL
+        for (int i = 0; i < 8; ++i) {
+            st = fma(c, st, u[i]);
+            yt[i0 + i] = st;
+        }
+    }
+    __syncthreads();
+    PHASE(20);
+    // coalesced copy of the kept samples (ys index n + (n >> 5); 512 consecutive samples per round)
+    double* outk = (double*)p.plane[LDD_P_SYNC] + o - keep0;
+    constexpr int SB = 6;
+    for (int n0 = keep0 + tid; n0 < keep1; n0 += SB * nthr) {
+        double v[SB];
+        LDD_UNROLL
+        for (int i = 0; i < SB; ++i) {
+            const int n = n0 + i * nthr;
+            v[i] = n < keep1 ? ys[n + (n >> 5)] : 0.0;
+        }
+        LDD_UNROLL
+        for (int i = 0; i < SB; ++i) {
+            const int n = n0 + i * nthr;
+            if (n < keep1) st_stream(&outk[n], v[i]);
+        }
+    }
+    PHASE(21);
+}
+
+#include "ldd_demod8k.cuh"
+
 // One block of N samples through the whole chain.  smem: the dynamic shared memory of the CTA (block arrays when PAD,
 // the ping-pong partner when SP); scratch_slot: this CTA's slice of the global scratch (when !PAD); stw: per-thread
 // twiddles (compile-time plan, float32).  Returns (block-uniform) whether a demod_05 sample of the block lies within
 // p.flag_margin of a sync threshold (p.flag_margin > 0 only).  Ends with a barrier.
 template <class T, int NT, bool PAD, bool SP, int CM>
-__device__ inline int demod_block(const DemodParams& p, const int blk, char* smem, void* scratch_slot, Cx<T>* stw, const ScanConsts& sc) {
+__device__ inline int demod_block(const DemodParams& p, const int blk, char* smem, void* scratch_slot, Cx<T>* stw, const ScanConsts& sc,
+                                  const ScanTab* stab) {
     const int tid = threadIdx.x, nthr = CM ? NT : (int)blockDim.x;
     const int M = CM ? CM : p.M, N = CM ? 2 * CM : p.N;
     const Cx<T>* WM = (const Cx<T>*)p.WM;
@@ -281,10 +421,12 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
 #define IX(i) pidx<PAD>(i)
     __shared__ double s_warp[32];
     __shared__ double s_total;
+    __shared__ unsigned s_last[32];
     const int CH = sc.CH;
     const int lane = tid & 31, warp = tid >> 5;
     const double c = sc.c, Ach = sc.Ach, A32 = sc.A32, AchLane = sc.AchLane, AchLane1 = sc.AchLane1, cN = sc.cN, cn0 = sc.cn0;
     int flagged = 0;
+    PHASE_BEGIN();
     {
         const long long in0 = p.first_sample + (long long)blk * p.stride;
         const long long o = (long long)blk * p.stride;
@@ -341,14 +483,18 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
             }
         }
         __syncthreads();
+        PHASE(0);
 
         // B/C. X = rfft(x)
         Cx<T>* X = FFTM(b0, b1);
+        PHASE(1);
         Cx<T>* f1 = (X == b0) ? b1 : b0;      // free
         Cx<T>* f2 = b2;                        // free
-        if constexpr (CM != 0) untangle_static<T, PAD, CM, NT>(X, WN, tid);
+        const Cx<T>* wnb = TW8K ? stw + 3 * NT + tid : nullptr;         // this thread's W_N^tid (float32 lane, default block length)
+        if constexpr (CM != 0) untangle_static<T, PAD, CM, NT>(X, WN, tid, wnb);
         else untangle<T, PAD>(X, M, WN, tid, nthr);
         __syncthreads();
+        PHASE(2);
 
         // D. analog audio, phase 1 (lddecode_core.py:322-326): two length-A inverse transforms of a
         //    slice of X, FM discriminator at freq_arf, + audio_lowfreq.
@@ -392,6 +538,7 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
                 }
             }
             __syncthreads();
+            PHASE(3);
         }
 
         // Per-block MTF level (CAV discs: the reference lowers mtf_level by 1e-4 per frame, lddecode_core.py:1300-1306):
@@ -451,7 +598,9 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
                     LDD_UNROLL
                     for (int i = 0; i < B; ++i) {
                         const int k = tid + (it0 + i) * NT;
-                        h0[i] = HV(k); h1[i] = HV(k + M); h2[i] = HV(M - k); h3[i] = HV((2 * M - k) & (2 * M - 1)); w[i] = WN[k];
+                        h0[i] = HV(k); h1[i] = HV(k + M); h2[i] = HV(M - k); h3[i] = HV((2 * M - k) & (2 * M - 1));
+                        if constexpr (TW8K) w[i] = wn_of<T>(*wnb, it0 + i);
+                        else w[i] = WN[k];
                     }
                     LDD_UNROLL
                     for (int i = 0; i < B; ++i) {
@@ -472,6 +621,7 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
         if (dl != (T)0) stepE(TrueTag{});
         else stepE(FalseTag{});
         __syncthreads();
+        PHASE(4);
 
         // F. h[2n] = conj(ru[n]), h[2n+1] = conj(rv[n]) (up to a positive scale)
         Cx<T>* ru;
@@ -490,6 +640,7 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
             rv = FFTM(V, fu);
             fv = (rv == V) ? fu : V;
         }
+        PHASE(5);
 
         // G. FM discriminator (lddutils.py:320-334): angle, neighbour difference, fold to [0, 2pi),
         //    scale to Hz; minus ire0; packed for the next real transform.
@@ -508,6 +659,7 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
             }
         }
         __syncthreads();
+        PHASE(6);
         {
             const T twopi = (T)6.283185307179586476925286766559;
             const T hz = (T)p.hz_per_rad, ire0 = (T)p.ire0;
@@ -532,9 +684,11 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
             }
         }
         __syncthreads();
+        PHASE(7);
 
         // H. D = rfft(demod - ire0)
         Cx<T>* D = FFTM(rv, ru);
+        PHASE(8);
         // the two free arrays; the filtered block lands in g1 for an even number of passes and in g2 for an
         // odd one: make that an end array (b0 or b2) so that step J finds two adjacent free arrays
         Cx<T>* g1 = (D == rv) ? ru : rv;
@@ -546,19 +700,22 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
             g1 = even ? land : oth;
             g2 = even ? oth : land;
         }
-        if constexpr (CM != 0) untangle_static<T, PAD, CM, NT>(D, WN, tid);
+        if constexpr (CM != 0) untangle_static<T, PAD, CM, NT>(D, WN, tid, wnb);
         else untangle<T, PAD>(D, M, WN, tid, nthr);
         __syncthreads();
+        PHASE(9);
 
         // I. post filters.  Order: video, burst, (pilot), video05 last because its whole block feeds the sync scan.
         Cx<T>* r05 = nullptr;
         for (int oi = 0; oi < 4; ++oi) {
             const int m = (0x1320 >> (4 * oi)) & 15;           // 0, 2, 3, 1
             if ((m >= p.nfilt || p.only05) && m != 1) continue;
-            if constexpr (CM != 0) tangle_static<T, PAD, CM, NT>(D, g1, (const Cx<T>*)p.F[m], WN, tid);
+            if constexpr (CM != 0) tangle_static<T, PAD, CM, NT>(D, g1, (const Cx<T>*)p.F[m], WN, tid, wnb);
             else tangle<T, PAD>(D, g1, (const Cx<T>*)p.F[m], M, WN, tid, nthr);
             __syncthreads();
+            PHASE(10);
             Cx<T>* r = FFTM(g1, g2);
+            PHASE(11);
             static_assert(LDD_P_DEMOD == 0 && LDD_P_DEMOD05 == 1 && LDD_P_BURST == 3 && LDD_P_PILOT == 4, "plane order");
             float* out = (float*)p.plane[m < 2 ? m : m + 1];
             const T addc = (T)p.addc[m];
@@ -598,6 +755,7 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
             }
             if (m == 1) r05 = r;
             __syncthreads();
+            PHASE(12);
         }
 
         // J. sync: s[n] = lo <= demod_05[n] <= hi (lddecode_core.py:308); demod_sync = circular
@@ -613,6 +771,22 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
                 return v + add;
             };
             auto insync = [&](double v) -> double { return (v >= p.sync_lo && v <= p.sync_hi) ? 1.0 : 0.0; };
+            double* ys_fast = nullptr;
+            if (PAD) ys_fast = (r05 == b0) ? (double*)b1 : (r05 == b2) ? (double*)b0 : nullptr;
+            else if (SP && (const void*)r05 != (const void*)sp) ys_fast = (double*)sp;
+            if (CH == 32 && ys_fast && stab) {
+                // default geometry: decisions into a bit mask, recursion and store by the code every lane shares
+                unsigned mask = 0u;
+                int near = 0;
+                for (int i = 0; i < 32; ++i) {
+                    const double v = val05(n0 + i);
+                    if (v >= p.sync_lo && v <= p.sync_hi) mask |= (1u << i);
+                    if (p.flag_margin > 0.0) near |= (fabs(v - p.sync_lo) < p.flag_margin) | (fabs(v - p.sync_hi) < p.flag_margin);
+                }
+                if (p.flag_margin > 0.0) flagged = __syncthreads_or(near | (in0 + N > p.rf_limit));
+                sync_scan32(p, sc, *stab, mask, ys_fast, keep0, keep1, o, s_warp, &s_total, s_last);
+                PHASE(13);
+            } else {
             double sprev = insync(val05(n0 - 1));
             const double sprev0 = sprev;
             // the binary decisions of this thread's chunk, evaluated once (CH <= 64), else re-evaluated
@@ -641,6 +815,7 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
             }
             if (lane == 31) s_warp[warp] = incl;
             __syncthreads();
+            PHASE(13);
             double carry = 0.0;                 // state entering this warp (zero initial state)
             for (int w = 0; w < warp; ++w) carry = A32 * carry + s_warp[w];
             if (tid == nthr - 1) {
@@ -670,15 +845,26 @@ __device__ inline int demod_block(const DemodParams& p, const int blk, char* sme
             }
             if (ys) {
                 __syncthreads();
+                PHASE(14);
                 double* outk = out + o - keep0;
                 for (int n = keep0 + tid; n < keep1; n += nthr) st_stream(&outk[n], ys[n + (n >> 5)]);
             }
+            }
         }
         __syncthreads();
+        PHASE(15);
     }
     return flagged;
 #undef IX
 }
+
+// shared-memory twiddle constants of the float32 lane at the default block length: of the in-place block or of the
+// compile-time Stockham plan (one or the other per launch)
+union CstBuf {
+    d8::Consts c;
+    d8::Consts64 c64;
+    Cx<float> tw[4 * 512];
+};
 
 // Persistent kernel of the single-precision lanes and of the exact lane: CTA b takes blocks b, b + grid, ...; with a
 // block list (second pass of the two-launch mixed lane) it takes the list's entries instead.
@@ -688,19 +874,38 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
     LDD_DYN_SMEM(smem);
     constexpr bool TW8K = (CM == 8192 && NT == 512 && sizeof(T) == 4);
     Cx<T>* stw = nullptr;
+    bool inplace = false;           // the in-place block of ldd_demod8k.cuh (needs the permuted tables)
+    d8::Consts* cst = nullptr;
     if constexpr (TW8K) {
-        // compile-time plan for 8192 points on 512 threads: per-thread twiddles in shared memory
-        __shared__ Cx<T> s_tw[3 * NT];
-        stw = s_tw;
-        fft_tw_fill<T, CM, NT>(stw, (const Cx<T>*)p.WM, tid);
+        // per-thread twiddles in shared memory: of the in-place block, or of the compile-time Stockham plan
+        __shared__ CstBuf s_cst;
+        inplace = PAD && p.HvP != nullptr;
+        if (inplace) {
+            cst = &s_cst.c;
+            d8::consts_fill(*cst, (const Cx<float>*)p.WM, (const Cx<float>*)p.WN, tid);
+        } else {
+            stw = (Cx<T>*)s_cst.tw;
+            fft_tw_fill<T, CM, NT>(stw, (const Cx<T>*)p.WM, tid, (const Cx<T>*)p.WN);
+        }
         __syncthreads();
     }
     const ScanConsts sc = scan_consts(p, CM ? 2 * CM : p.N, nthr, tid);
     void* slot = PAD ? nullptr : (void*)((char*)p.scratch + (size_t)blockIdx.x * p.scratch_per_cta);
     const int nwork = p.block_list ? *p.block_count : p.nblocks;
+    __shared__ double s8_warp[32];
+    __shared__ double s8_total;
+    __shared__ unsigned s8_last[32];
+    __shared__ ScanTab s_stab;
+    scan_tab_fill(s_stab, p, tid);
+    __syncthreads();
     for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
         const int blk = p.block_list ? p.block_list[wi] : wi;
-        const int fl = demod_block<T, NT, PAD, SP, CM>(p, blk, smem, slot, stw, sc);
+        int fl;
+        if constexpr (TW8K) {
+            if (inplace) fl = d8::demod_block8k(p, blk, smem, *cst, sc, s_stab, s8_warp, &s8_total, s8_last);
+            else fl = demod_block<T, NT, PAD, SP, CM>(p, blk, smem, slot, stw, sc, &s_stab);
+        } else
+        fl = demod_block<T, NT, PAD, SP, CM>(p, blk, smem, slot, stw, sc, &s_stab);
         if (p.flag_list && fl && tid == 0) { int at = atomicAdd(p.flag_count, 1); p.flag_list[at] = blk; }
     }
 }
@@ -714,24 +919,57 @@ template <int NT, int CM>
 __global__ void __launch_bounds__(NT, 1) demod_mixed_kernel(const DemodParams pf, const DemodParams pq, int* queue) {
     const int tid = threadIdx.x;
     LDD_DYN_SMEM(smem);
-    __shared__ Cx<float> s_tw[3 * NT];
+    __shared__ CstBuf s_cst;
     __shared__ int s_blk;
-    fft_tw_fill<float, CM, NT>(s_tw, (const Cx<float>*)pf.WM, tid);
+    __shared__ double s8_warp[32];
+    __shared__ double s8_total;
+    __shared__ unsigned s8_last[32];
+    __shared__ ScanTab s_stab;
+    scan_tab_fill(s_stab, pf, tid);
+    const bool inplace = pf.HvP != nullptr;      // the in-place block of ldd_demod8k.cuh (needs the permuted tables)
+    Cx<float>* s_tw = s_cst.tw;
+    d8::Consts* cst = &s_cst.c;
+    if (inplace) d8::consts_fill(*cst, (const Cx<float>*)pf.WM, (const Cx<float>*)pf.WN, tid);
+    else fft_tw_fill<float, CM, NT>(s_tw, (const Cx<float>*)pf.WM, tid, (const Cx<float>*)pf.WN);
     __syncthreads();
     const ScanConsts sc = scan_consts(pf, 2 * CM, NT, tid);
     void* slot64 = (void*)((char*)pq.scratch + (size_t)blockIdx.x * pq.scratch_per_cta);
     for (;;) {
         if (tid == 0) s_blk = atomicAdd(queue, 1);
         __syncthreads();
-        const int blk = s_blk;
-        if (blk >= pf.nblocks) break;
-        const int fl = demod_block<float, NT, true, false, CM>(pf, blk, smem, nullptr, s_tw, sc);
+        if (s_blk >= pf.nblocks) break;
+        // highest block first: the block that reaches past the end of the capture is always re-run, and by the slow
+        // generic float64 block (below) -- it must not be the last one drawn
+        const int blk = pf.nblocks - 1 - s_blk;
+        const int fl = inplace ? d8::demod_block8k(pf, blk, smem, *cst, sc, s_stab, s8_warp, &s8_total, s8_last)
+                               : demod_block<float, NT, true, false, CM>(pf, blk, smem, nullptr, s_tw, sc, &s_stab);
         if (fl) {
             if (tid == 0) atomicAdd(queue + 1, 1);                    // statistics: blocks re-run
-            demod_block<double, NT, false, true, CM>(pq, blk, smem, slot64, nullptr, sc);
+            // (a block that reads zeros past the end of the capture decides on rounding noise there: it keeps the generic
+            // block, whose noise is the exact lane's, so that the two lanes' sync planes stay bit-identical)
+            if (inplace && pq.HvP && pf.first_sample + (long long)blk * pf.stride + 2 * CM <= pf.rf_limit) {
+                // float64 on the in-place transforms (one array in shared memory); its constants borrow the float32 ones' room
+                d8::rerun8k(pq, blk, smem, (Cx<double>*)slot64, s_cst.c64, sc, s_stab, s8_warp, &s8_total, s8_last);
+                d8::consts_fill(*cst, (const Cx<float>*)pf.WM, (const Cx<float>*)pf.WN, tid);
+                __syncthreads();
+            } else {
+                demod_block<double, NT, false, true, CM>(pq, blk, smem, slot64, nullptr, sc, &s_stab);
+            }
         }
     }
 }
+
+#ifdef LDD_PHASE_TIMING
+}  // namespace ldd
+// profiling builds only: copies out (and clears) the 64 phase counters
+extern "C" int ldd_debug_phases(unsigned long long* out64) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out64, ldd::g_phase, sizeof(unsigned long long) * 64) != cudaSuccess) return LDD_ECUDA;
+    unsigned long long z[64] = {0};
+    return cudaMemcpyToSymbol(ldd::g_phase, z, sizeof z) == cudaSuccess ? LDD_OK : LDD_ECUDA;
+}
+namespace ldd {
+#endif
 
 static int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();

@@ -172,14 +172,33 @@ __device__ inline void fft_run_pair_static(Cx<T>* a1, Cx<T>* b1, Cx<T>* a2, Cx<T
 // For M = 16 NT (8192 points, 512 threads: passes 16, 16, 16, 2) every thread works on the same butterfly
 // index in every transform, so the base twiddle of each pass is a per-thread constant.  `stw` holds them
 // (3 NT entries, filled once per CTA by fft_tw_fill): no table lookup in global memory is left in the passes.
+// (`stw` has 4 NT entries; the last NT hold W_2M^tid, the base of the untangle / tangle twiddles: wn_of.)
 template <class T, int M, int NT>
-__device__ inline void fft_tw_fill(Cx<T>* stw, const Cx<T>* __restrict__ W, int tid) {
+__device__ inline void fft_tw_fill(Cx<T>* stw, const Cx<T>* __restrict__ W, int tid, const Cx<T>* __restrict__ WN = nullptr) {
     static_assert(M == 16 * NT && M == 8192, "per-thread twiddles: 8192 points on 512 threads");
     constexpr int nb = M / 16;
     stw[tid] = W[(tid & 15) * (nb / 16)];               // pass 2: Ns = 16
     stw[NT + tid] = W[(tid & 255) * (nb / 256)];        // pass 3: Ns = 256
     stw[2 * NT + tid] = W[tid];                         // pass 4 (radix 2, Ns = M/2): W^(tid + i NT) = W^tid * W16^i
+    if (WN) stw[3 * NT + tid] = WN[tid];
 }
+
+// e^{-2 pi i n / 32}, n in [0, 8)
+template <class T> LDD_HD inline Cx<T> w32(int n) {
+    switch (n & 7) {
+        case 0: return mk<T>((T)1, (T)0);
+        case 1: return mk<T>((T)0.98078528040323043058, (T)-0.19509032201612824808);
+        case 2: return mk<T>((T)0.92387953251128675613, (T)-0.38268343236508977173);
+        case 3: return mk<T>((T)0.83146961230254523567, (T)-0.55557023301960217765);
+        case 4: return mk<T>((T)0.70710678118654752440, (T)-0.70710678118654752440);
+        case 5: return mk<T>((T)0.55557023301960217765, (T)-0.83146961230254523567);
+        case 6: return mk<T>((T)0.38268343236508977173, (T)-0.92387953251128675613);
+        default: return mk<T>((T)0.19509032201612824808, (T)-0.98078528040323043058);
+    }
+}
+// W_N^(tid + j NT) for N = 32 NT from the thread's base W_N^tid (j < 8, a compile-time constant after unrolling):
+// one product instead of a table load from L2
+template <class T> LDD_HD inline Cx<T> wn_of(Cx<T> base, int j) { return j == 0 ? base : base * w32<T>(j); }
 
 // one radix-R butterfly per thread (j = tid, M / R == number of threads)
 template <class T, int R, int M, int Ns, bool PIN, bool POUT>

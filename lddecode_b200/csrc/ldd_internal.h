@@ -1,6 +1,7 @@
 // Internal declarations shared by the translation units of libldd_b200.so.
 #pragma once
 #include "ldd_fft.cuh"
+#include "ldd_fft2.cuh"
 #include "../../include/ldd_b200.h"
 
 #include <string>
@@ -37,6 +38,11 @@ struct DemodParams {
     double mtf_hold_until;       // blocks centred before this plane sample use mtf_hold_level (the decode's first frame)
     double mtf_hold_level;
     const void* F[4];            // FVideo, FVideo05 (pre-rolled), FVideoBurst, FVideoPilot; k<=M; scaled 1/M
+    // float32 copies in the digit-permuted order of the in-place transforms (ldd_fft2.cuh; N = 16384 only, else NULL):
+    // HvP[p] = Hv[idx(p)], HvP[M + p] = Hv[M + idx(p)]; lnMP likewise; FP[m][p] = F[m][idx(p)], FP[m][M] = F[m][M]
+    const void* HvP;
+    const void* lnMP;
+    const void* FP[4];
     const void* AL;              // audio_lfilt / audio_rfilt, A entries
     const void* AR;
     double addc[4];              // added to the inverse transform of filter m before the store
@@ -95,6 +101,12 @@ struct ldd_handle {
     void* d_WN[2];
     void* d_Hv[2];
     void* d_F[4][2];
+    void* d_HvP = nullptr;       // permuted float32 copies (block length 16384): see DemodParams
+    void* d_lnMP = nullptr;
+    void* d_FP[4] = {nullptr, nullptr, nullptr, nullptr};
+    void* d_HvP64 = nullptr;     // the same in float64 for the mixed lane's re-run (RF filter, log MTF, FVideo05)
+    void* d_lnMP64 = nullptr;
+    void* d_FP64_05 = nullptr;
     void* d_AL[2];
     void* d_AR[2];
     double dc[4];

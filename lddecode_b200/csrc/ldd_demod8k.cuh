@@ -148,35 +148,93 @@ __device__ inline int demod_block8k(const DemodParams& p, const int blk, char* s
     const C* __restrict__ HvP = (const C*)p.HvP;
     const C* __restrict__ LnP = (const C*)p.lnMP;
 
-    // A. samples -> z[n] = x[2n] + j x[2n+1], stage 1 of the forward transform on the way into b0
+    // A. samples -> z[n] = x[2n] + j x[2n+1], stage 1 of the forward transform on the way into b0.  A thread takes the
+    //    sample groups g = tid + 512 i (four samples = z[2g], z[2g+1]) and their partners 2048 groups on; the arithmetic is
+    //    the same whatever the format and alignment (only the fetch differs), so that packed and unpacked captures, and
+    //    differently aligned shards of one capture, give bit-equal planes.
     {
-        C za[8], zb[8];
-        if (in0 + N <= p.rf_limit && p.fmt == LDD_FMT_U8 && ((((uintptr_t)p.rf + (uintptr_t)in0) & 1) == 0)) {
-            const unsigned short* r16 = (const unsigned short*)((const unsigned char*)p.rf + in0);
-            unsigned va[8], vb[8];
+        C za[4][2], zb[4][2];            // [i][e]: z[n], z[n + 4096] for n = 2 g + e
+        const bool full = in0 + N <= p.rf_limit;
+        const unsigned char* rfb = (const unsigned char*)p.rf;
+        if (full && p.fmt == LDD_FMT_U8 && ((((uintptr_t)rfb + (uintptr_t)in0) & 3) == 0)) {
+            // 8-bit samples: one aligned 32-bit word per group
+            const unsigned* r32 = (const unsigned*)(rfb + in0);
+            unsigned va[4], vb[4];
             LDD_UNROLL
-            for (int i = 0; i < 8; ++i) { va[i] = r16[tid + i * NT]; vb[i] = r16[tid + i * NT + M / 2]; }
+            for (int i = 0; i < 4; ++i) { va[i] = r32[tid + i * NT]; vb[i] = r32[tid + i * NT + 2048]; }
             LDD_UNROLL
-            for (int i = 0; i < 8; ++i) {
-                za[i] = mk<float>((float)(int)(va[i] & 0xffu), (float)(int)(va[i] >> 8));
-                zb[i] = mk<float>((float)(int)(vb[i] & 0xffu), (float)(int)(vb[i] >> 8));
+            for (int i = 0; i < 4; ++i) {
+                za[i][0] = mk<float>((float)(int)(va[i] & 0xffu), (float)(int)((va[i] >> 8) & 0xffu));
+                za[i][1] = mk<float>((float)(int)((va[i] >> 16) & 0xffu), (float)(int)(va[i] >> 24));
+                zb[i][0] = mk<float>((float)(int)(vb[i] & 0xffu), (float)(int)((vb[i] >> 8) & 0xffu));
+                zb[i][1] = mk<float>((float)(int)((vb[i] >> 16) & 0xffu), (float)(int)(vb[i] >> 24));
+            }
+        } else if (full && p.fmt == LDD_FMT_LDS40 && (in0 & 3) == 0 && ((((uintptr_t)rfb) & 3) == 0) && in0 + N + 4 <= p.rf_limit) {
+            // 4 x 10 bit in 5 bytes (.lds): group g = bytes [5 g, 5 g + 5) of the block, taken from the two aligned words
+            // that hold them
+            const unsigned char* gb = rfb + (in0 >> 2) * 5;
+            const unsigned off0 = (unsigned)((uintptr_t)gb & 3);
+            const unsigned* w32 = (const unsigned*)(gb - off0);
+            unsigned la[4][2], lb[4][2];
+            LDD_UNROLL
+            for (int i = 0; i < 4; ++i) {
+                const unsigned ba = off0 + 5u * (unsigned)(tid + i * NT), bb = ba + 5u * 2048u;
+                la[i][0] = w32[ba >> 2]; la[i][1] = w32[(ba >> 2) + 1];
+                lb[i][0] = w32[bb >> 2]; lb[i][1] = w32[(bb >> 2) + 1];
+            }
+            auto unpack = [](unsigned w0, unsigned w1, unsigned byteoff, C* out2) {
+                const unsigned long long v = (((unsigned long long)w1 << 32) | w0) >> (8 * (byteoff & 3));
+                const unsigned c0 = (unsigned)v & 0xffu, c1 = (unsigned)(v >> 8) & 0xffu, c2 = (unsigned)(v >> 16) & 0xffu,
+                               c3 = (unsigned)(v >> 24) & 0xffu, c4 = (unsigned)(v >> 32) & 0xffu;
+                out2[0] = mk<float>((float)(int)((c0 << 2) | (c1 >> 6)), (float)(int)(((c1 & 0x3fu) << 4) | (c2 >> 4)));
+                out2[1] = mk<float>((float)(int)(((c2 & 0xfu) << 6) | (c3 >> 2)), (float)(int)(((c3 & 3u) << 8) | c4));
+            };
+            LDD_UNROLL
+            for (int i = 0; i < 4; ++i) {
+                const unsigned ba = off0 + 5u * (unsigned)(tid + i * NT);
+                unpack(la[i][0], la[i][1], ba, za[i]);
+                unpack(lb[i][0], lb[i][1], ba + 5u * 2048u, zb[i]);
+            }
+        } else if (full) {
+            // any other format / alignment: one fetch per sample
+            LDD_UNROLL
+            for (int i = 0; i < 4; ++i) {
+                const long long s1 = in0 + 4 * (tid + i * NT), s2 = s1 + M;
+                LDD_UNROLL
+                for (int e = 0; e < 2; ++e) {
+                    za[i][e] = mk<float>((float)fetch_sample(p.rf, p.fmt, s1 + 2 * e), (float)fetch_sample(p.rf, p.fmt, s1 + 2 * e + 1));
+                    zb[i][e] = mk<float>((float)fetch_sample(p.rf, p.fmt, s2 + 2 * e), (float)fetch_sample(p.rf, p.fmt, s2 + 2 * e + 1));
+                }
             }
         } else {
-            // any format; a block that reaches past the end of the capture reads zeros there
+            // a block that reaches past the end of the capture reads zeros there
+            auto fz = [&](long long sidx) -> float { return sidx < p.rf_limit ? (float)fetch_sample(p.rf, p.fmt, sidx) : 0.f; };
             LDD_UNROLL
-            for (int i = 0; i < 8; ++i) {
-                const long long sa = in0 + 2 * (tid + i * NT), sb = sa + M;
-                const int a0 = sa < p.rf_limit ? fetch_sample(p.rf, p.fmt, sa) : 0, a1 = sa + 1 < p.rf_limit ? fetch_sample(p.rf, p.fmt, sa + 1) : 0;
-                const int c0 = sb < p.rf_limit ? fetch_sample(p.rf, p.fmt, sb) : 0, c1 = sb + 1 < p.rf_limit ? fetch_sample(p.rf, p.fmt, sb + 1) : 0;
-                za[i] = mk<float>((float)a0, (float)a1);
-                zb[i] = mk<float>((float)c0, (float)c1);
+            for (int i = 0; i < 4; ++i) {
+                const long long s1 = in0 + 4 * (tid + i * NT), s2 = s1 + M;
+                LDD_UNROLL
+                for (int e = 0; e < 2; ++e) {
+                    za[i][e] = mk<float>(fz(s1 + 2 * e), fz(s1 + 2 * e + 1));
+                    zb[i][e] = mk<float>(fz(s2 + 2 * e), fz(s2 + 2 * e + 1));
+                }
             }
         }
+        // stage 1 for n = 2 g + e = (2 tid + e) + 1024 i: W_8192^n = W_8192^(2 tid + e) W_8^i
+        const C wa = tw.w1 * tw.w1;
+        const C wb = wa * mk<float>(0.99999970586288221916f, -0.00076699031874270453f);       // W_8192^1
+        const int ixe = PXi(2 * tid);
         LDD_UNROLL
-        for (int i = 0; i < 8; ++i) {
-            const C w = i == 0 ? tw.w1 : tw.w1 * w16<float>(i);
-            b0[ix0 + i * P512] = za[i] + zb[i];
-            b0[ix0 + i * P512 + P4096] = (za[i] - zb[i]) * w;
+        for (int i = 0; i < 4; ++i) {
+            LDD_UNROLL
+            for (int e = 0; e < 2; ++e) {
+                C w = e ? wb : wa;
+                if (i == 1) w = mk<float>((w.x + w.y) * 0.70710678118654752440f, (w.y - w.x) * 0.70710678118654752440f);      // * W_8
+                if (i == 2) w = mul_mj(w);
+                if (i == 3) w = mk<float>((w.y - w.x) * 0.70710678118654752440f, -(w.x + w.y) * 0.70710678118654752440f);     // * W_8^3
+                const int ix = ixe + e + i * f2::pst<PK>(1024);
+                b0[ix] = za[i][e] + zb[i][e];
+                b0[ix + P4096] = (za[i][e] - zb[i][e]) * w;
+            }
         }
     }
     __syncthreads();

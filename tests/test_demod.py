@@ -4,6 +4,8 @@ against the golden vectors recorded from the reference and against the oracle on
 Tolerances (BASELINE.json north_star): demodulated Hz within 1e-4 relative of the float64
 reference -- the float64 lane is held to 1e-7 here (float32 plane storage relative to ire0 is
 the only loss); demod_sync within 1e-6 absolute; audio within 1e-4 relative (held to 1e-9)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -180,3 +182,59 @@ def test_mixed_lane_sync_is_the_float64_lane(backend, golden, name):
     ire0 = 8100000.0 if _system(g) == "NTSC" else 7100000.0
     rel = np.abs(out["mixed"]["demod"].astype(np.float64) - out["f64"]["demod"]) / (np.abs(out["f64"]["demod"].astype(np.float64) + ire0))
     assert rel.max() < 1e-6                       # bar: 1e-4
+
+
+def test_inplace_transforms_against_host_fft(tmp_path):
+    """The in-place DIF / DIT transform pair of the default block length (ldd_fft2.cuh) and the Stockham plan
+    (ldd_fft.cuh), each against a float64 host FFT: spectrum (through the digit permutation) and round trip.
+    tools/fft_bench.cu is the same program the B200 micro-benchmark runs; here it is compiled for the CPU emulation."""
+    import re
+    import subprocess
+    exe = str(tmp_path / "fft_bench_emu")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-DLDD_EMU", "-I", os.path.join(root, "tests", "emu"), "-I",
+                           os.path.join(root, "lddecode_b200", "csrc"), "-x", "c++", os.path.join(root, "tools", "fft_bench.cu"),
+                           os.path.join(root, "tests", "emu", "cuda_emu.cpp"), "-o", exe, "-Wno-unknown-pragmas"])
+    out = subprocess.run([exe, "1", "1"], stdout=subprocess.PIPE, text=True, check=True).stdout
+    rows = re.findall(r"(\S+)\s+check: spectrum max err (\S+) \(max \|X\| (\S+)\), round trip max err (\S+)", out)
+    assert [r[0] for r in rows] == ["stockham", "inplace/1", "inplace/2"], out
+    for name, e1, mx, e2 in rows:
+        assert float(e1) < 1e-6 * 8192 ** 0.5 * float(mx) and float(e2) < 1e-5, (name, e1, mx, e2)
+
+
+@pytest.mark.parametrize("system,audio", [("PAL", False), ("NTSC", True)])
+def test_inplace_block_equals_stockham_block(backend, system, audio, monkeypatch):
+    """The float32 block of the default block length on in-place transforms (ldd_demod8k.cuh) against the Stockham block
+    it replaced (LDD_STOCKHAM_BLOCK=1): planes and audio equal to float32 rounding, the sync plane bit for bit; and the
+    mixed lane's float64 re-run on in-place transforms against the generic float64 block (LDD_STOCKHAM_RERUN=1) with a
+    guard band wide enough to send many blocks through it: sync plane and demod_05 bit for bit."""
+    from lddecode_b200 import _lib
+    fs = 8 * 315 / 88 if system == "NTSC" else 35.46895
+    cap = synth.SynthRF(system, fs, seed=3).generate(150000)
+    dev = backend.to_device(cap)
+
+    def run(prec):
+        rf = rfdecode.RFDecode(fs, system, 16384, decode_analog_audio=audio, _backend=backend, precision=prec)
+        out = rf.demod_device(dev, _lib.FMT_U8, 0, len(cap), 2000, 120000, 1 if audio else 0, phase2=False).to_recarrays()
+        return out, rf
+
+    monkeypatch.delenv("LDD_STOCKHAM_BLOCK", raising=False)
+    new, _ = run("f32")
+    monkeypatch.setenv("LDD_STOCKHAM_BLOCK", "1")
+    old, _ = run("f32")
+    monkeypatch.delenv("LDD_STOCKHAM_BLOCK")
+    assert np.array_equal(new[0]["demod_sync"], old[0]["demod_sync"])
+    for name in new[0].dtype.names:
+        if name != "demod_sync":
+            np.testing.assert_allclose(new[0][name], old[0][name], rtol=1e-6, atol=1.0, err_msg=name)
+    if audio:
+        for name in new[1].dtype.names:
+            np.testing.assert_allclose(new[1][name], old[1][name], rtol=2e-6, err_msg=name)
+    monkeypatch.setenv("LDD_FLAG_MARGIN_HZ", "400")
+    a, rfa = run("mixed")
+    flagged, total = rfa.mixed_stats()
+    assert 0 < flagged <= total
+    monkeypatch.setenv("LDD_STOCKHAM_RERUN", "1")
+    b, _ = run("mixed")
+    assert np.array_equal(a[0]["demod_sync"], b[0]["demod_sync"])
+    assert np.array_equal(a[0]["demod_05"], b[0]["demod_05"])

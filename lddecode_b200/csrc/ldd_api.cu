@@ -75,25 +75,36 @@ __global__ void hv_kernel(const Cx<double>* __restrict__ rf, const Cx<double>* _
     hv32[k] = mk<float>((float)v.x, (float)v.y);
 }
 
-// dst[part M + pos(k)] = src[part M + k] for nparts parts of M = 8192 entries (ldd_fft2.cuh's digit-permuted order), the
-// `tail` entries behind them copied as they are
+// dst[part stride + pos(k)] = src[part M + k] for nparts parts of M = 8192 entries (ldd_fft2.cuh's digit-permuted order),
+// the `tail` entries behind them copied as they are.  padded: positions in the block arrays' padded layout (one slot after
+// every 16, stride = 8704 per part), so that a part is ONE contiguous range in global and in shared memory and a single
+// bulk copy brings it in (ldd_demod8k.cuh).
 template <class T>
-__global__ void permute_kernel(const Cx<T>* __restrict__ src, Cx<T>* __restrict__ dst, int nparts, int tail) {
-    const int M = f2::M;
+__global__ void permute_kernel(const Cx<T>* __restrict__ src, Cx<T>* __restrict__ dst, int nparts, int tail, int padded) {
+    const int M = f2::M, stride = padded ? f2::span<1>() : M;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < nparts * M) dst[(k / M) * M + f2::pos_of_idx(k % M)] = src[k];
-    else if (k < nparts * M + tail) dst[k] = src[k];
+    if (k < nparts * M) {
+        const int pos = f2::pos_of_idx(k % M);
+        dst[(k / M) * stride + (padded ? f2::pix<1>(pos) : pos)] = src[k];
+    } else if (k < nparts * M + tail) {
+        dst[nparts * stride + (k - nparts * M)] = src[k];
+    }
 }
 
-// (re)builds the permuted float32 copy (and, for the mixed lane, the float64 one) on `stream`; no-op for other block lengths
+// (re)builds the permuted float32 copy (padded layout) and, for the mixed lane, the float64 one (plain) on `stream`; no-op
+// for other block lengths
 int permuted_copy(ldd_handle* h, void* const* src /*[2]: float64, float32*/, void** dst32, void** dst64, int nparts, int tail, cudaStream_t stream) {
     if (h->cfg.blocklen != 2 * f2::M || !src[1]) return LDD_OK;
     const int n = nparts * f2::M + tail;
-    if (!*dst32) CUDA_TRY(h, cudaMalloc(dst32, (size_t)n * sizeof(Cx<float>)));
-    LDD_LAUNCH(permute_kernel<float>, dim3((n + 255) / 256), dim3(256), 0, stream, (const Cx<float>*)src[1], (Cx<float>*)*dst32, nparts, tail);
+    if (!*dst32) {
+        const size_t bytes = ((size_t)nparts * f2::span<1>() + tail) * sizeof(Cx<float>);
+        CUDA_TRY(h, cudaMalloc(dst32, bytes));
+        CUDA_TRY(h, cudaMemset(*dst32, 0, bytes));
+    }
+    LDD_LAUNCH(permute_kernel<float>, dim3((n + 255) / 256), dim3(256), 0, stream, (const Cx<float>*)src[1], (Cx<float>*)*dst32, nparts, tail, 1);
     if (dst64 && h->cfg.precision == LDD_PREC_MIXED && src[0]) {
         if (!*dst64) CUDA_TRY(h, cudaMalloc(dst64, (size_t)n * sizeof(Cx<double>)));
-        LDD_LAUNCH(permute_kernel<double>, dim3((n + 255) / 256), dim3(256), 0, stream, (const Cx<double>*)src[0], (Cx<double>*)*dst64, nparts, tail);
+        LDD_LAUNCH(permute_kernel<double>, dim3((n + 255) / 256), dim3(256), 0, stream, (const Cx<double>*)src[0], (Cx<double>*)*dst64, nparts, tail, 0);
     }
     return launch_status(h, "permute_kernel");
 }

@@ -896,13 +896,16 @@ __global__ void __launch_bounds__(NT, MINB) demod_kernel(const DemodParams p) {
     __shared__ double s8_total;
     __shared__ unsigned s8_last[32];
     __shared__ ScanTab s_stab;
+    __shared__ unsigned long long s_bars[2];
+    d8::Stage stg;
+    d8::stage_init(stg, s_bars, tid);
     scan_tab_fill(s_stab, p, tid);
     __syncthreads();
     for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
         const int blk = p.block_list ? p.block_list[wi] : wi;
         int fl;
         if constexpr (TW8K) {
-            if (inplace) fl = d8::demod_block8k(p, blk, smem, *cst, sc, s_stab, s8_warp, &s8_total, s8_last);
+            if (inplace) fl = d8::demod_block8k(p, blk, smem, *cst, sc, s_stab, stg, s8_warp, &s8_total, s8_last);
             else fl = demod_block<T, NT, PAD, SP, CM>(p, blk, smem, slot, stw, sc, &s_stab);
         } else
         fl = demod_block<T, NT, PAD, SP, CM>(p, blk, smem, slot, stw, sc, &s_stab);
@@ -925,6 +928,9 @@ __global__ void __launch_bounds__(NT, 1) demod_mixed_kernel(const DemodParams pf
     __shared__ double s8_total;
     __shared__ unsigned s8_last[32];
     __shared__ ScanTab s_stab;
+    __shared__ unsigned long long s_bars[2];
+    d8::Stage stg;
+    d8::stage_init(stg, s_bars, tid);
     scan_tab_fill(s_stab, pf, tid);
     const bool inplace = pf.HvP != nullptr;      // the in-place block of ldd_demod8k.cuh (needs the permuted tables)
     Cx<float>* s_tw = s_cst.tw;
@@ -936,12 +942,13 @@ __global__ void __launch_bounds__(NT, 1) demod_mixed_kernel(const DemodParams pf
     void* slot64 = (void*)((char*)pq.scratch + (size_t)blockIdx.x * pq.scratch_per_cta);
     for (;;) {
         if (tid == 0) s_blk = atomicAdd(queue, 1);
+        d8::stage_fence();          // (a float64 re-run wrote the arrays the next block's table staging lands in)
         __syncthreads();
         if (s_blk >= pf.nblocks) break;
         // highest block first: the block that reaches past the end of the capture is always re-run, and by the slow
         // generic float64 block (below) -- it must not be the last one drawn
         const int blk = pf.nblocks - 1 - s_blk;
-        const int fl = inplace ? d8::demod_block8k(pf, blk, smem, *cst, sc, s_stab, s8_warp, &s8_total, s8_last)
+        const int fl = inplace ? d8::demod_block8k(pf, blk, smem, *cst, sc, s_stab, stg, s8_warp, &s8_total, s8_last)
                                : demod_block<float, NT, true, false, CM>(pf, blk, smem, nullptr, s_tw, sc, &s_stab);
         if (fl) {
             if (tid == 0) atomicAdd(queue + 1, 1);                    // statistics: blocks re-run

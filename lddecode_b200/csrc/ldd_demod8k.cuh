@@ -41,6 +41,56 @@ __device__ inline void consts_fill(Consts& S, const C* __restrict__ WM, const C*
     if (tid < 18) S.row[tid / 9][tid % 9] = WN[(tid / 9) + 2 * (tid % 9)];
 }
 
+// Bulk-asynchronous (TMA) staging of filter tables: a table part is SPAN contiguous entries in global memory, in the block
+// arrays' own padded layout, and lands in an array that is dead at that point; the step that applies the table then
+// reads it from the very slots it overwrites.  Two mbarriers (RF filter table, first post filter pair), their phase
+// parities live across the blocks of a CTA.
+struct Stage {
+    unsigned long long* bars;      // [2] in shared memory
+    unsigned ph_e, ph_f;
+};
+__device__ inline void stage_init(Stage& st, unsigned long long* bars, int tid) {
+    st.bars = bars;
+    st.ph_e = st.ph_f = 0u;
+#ifndef LDD_EMU
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+#endif
+}
+// two table parts into two arrays (thread 0 issues; the caller has passed a CTA barrier behind the arrays' last use, with
+// stage_fence() in front of it on every thread)
+__device__ inline void stage_issue(unsigned long long* bar, C* dst0, const C* src0, C* dst1, const C* src1, int tid) {
+#ifdef LDD_EMU
+    for (int i = tid; i < SPAN; i += NT) {
+        dst0[i] = src0[i];
+        if (dst1) dst1[i] = src1[i];
+    }
+#else
+    if (tid == 0) {
+        const unsigned bytes = (unsigned)(SPAN * sizeof(C));
+        mbar_expect_tx(bar, dst1 ? 2 * bytes : bytes);
+        bulk_g2s(dst0, src0, bytes, bar);
+        if (dst1) bulk_g2s(dst1, src1, bytes, bar);
+    }
+#endif
+}
+__device__ inline void stage_fence() {
+#ifndef LDD_EMU
+    fence_proxy_async();
+#endif
+}
+__device__ inline void stage_wait(unsigned long long* bar, unsigned& parity) {
+#ifndef LDD_EMU
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+#else
+    (void)bar; (void)parity;
+#endif
+}
+
 // One (k, M-k) pair of a spectrum in permuted order: positions p (index k) and pp (index M - k), w = W_N^k.
 // kind 0: a proper pair; 1: k = 0 (p = 0, holds the packed X[0], X[M]); 2: k = M/2 (p = 8, pairs with itself).
 struct Item {
@@ -122,7 +172,7 @@ __device__ inline void dit_pair(C* a, C* b, const f2::Tw& tw, int tid) {
 
 // The whole block.  smem: 3 * SPAN complex.  Returns (block-uniform) the mixed lane's flag.  Ends with a barrier.
 __device__ inline int demod_block8k(const DemodParams& p, const int blk, char* smem, const Consts& S, const ScanConsts& sc,
-                                    const ScanTab& stab, double* s_warp, double* s_total, unsigned* s_last) {
+                                    const ScanTab& stab, Stage& stg, double* s_warp, double* s_total, unsigned* s_last) {
     const int tid = threadIdx.x, half = tid >> 8;
     C* const b0 = (C*)smem;
     C* const b1 = b0 + SPAN;
@@ -147,6 +197,14 @@ __device__ inline int demod_block8k(const DemodParams& p, const int blk, char* s
 
     const C* __restrict__ HvP = (const C*)p.HvP;
     const C* __restrict__ LnP = (const C*)p.lnMP;
+    // the RF filter table of step E: entries k < M into b1, k >= M into b2, under the sample load and the first transform
+    // (both arrays are free: the previous block ended with a barrier; with analog audio on they are the audio step's
+    // workspace and step E reads the table from global memory)
+    const bool pre_e = p.A == 0;
+    if (pre_e) stage_issue(&stg.bars[0], b1, HvP, b2, HvP + SPAN, tid);
+#ifdef LDD_EMU
+    if (pre_e) __syncthreads();
+#endif
 
     // A. samples -> z[n] = x[2n] + j x[2n+1], stage 1 of the forward transform on the way into b0.  A thread takes the
     //    sample groups g = tid + 512 i (four samples = z[2g], z[2g+1]) and their partners 2048 groups on; the arithmetic is
@@ -242,6 +300,7 @@ __device__ inline int demod_block8k(const DemodParams& p, const int blk, char* s
 
     // B. X = rfft(x): stages 2-4, spectrum in permuted order in b0
     f2::dif_234<PK>(b0, tw, tid);
+    if (pre_e) stage_wait(&stg.bars[0], stg.ph_e);
     f2::half_sync(half);
     PHASE(1);
 
@@ -289,10 +348,15 @@ __device__ inline int demod_block8k(const DemodParams& p, const int blk, char* s
             LDD_UNROLL
             for (int i = 0; i < 4; ++i) {
                 I[i] = pair_item(S, WN, tid, it0 + i);
-                h0[i] = HvP[I[i].p]; h1[i] = HvP[M + I[i].p]; h2[i] = HvP[I[i].pp]; h3[i] = HvP[M + I[i].pp];
+                const int ip = PXi(I[i].p), iq = PXi(I[i].pp);
+                if (fused) {         // staged (pre_e): the table sits in the slots of b1 / b2 this thread is about to overwrite
+                    h0[i] = b1[ip]; h1[i] = b2[ip]; h2[i] = b1[iq]; h3[i] = b2[iq];
+                } else {
+                    h0[i] = HvP[ip]; h1[i] = HvP[SPAN + ip]; h2[i] = HvP[iq]; h3[i] = HvP[SPAN + iq];
+                }
                 if constexpr (RAMP) {
-                    h0[i] = ramp(h0[i], LnP[I[i].p]); h1[i] = ramp(h1[i], LnP[M + I[i].p]);
-                    h2[i] = ramp(h2[i], LnP[I[i].pp]); h3[i] = ramp(h3[i], LnP[M + I[i].pp]);
+                    h0[i] = ramp(h0[i], LnP[ip]); h1[i] = ramp(h1[i], LnP[SPAN + ip]);
+                    h2[i] = ramp(h2[i], LnP[iq]); h3[i] = ramp(h3[i], LnP[SPAN + iq]);
                 }
             }
             LDD_UNROLL
@@ -306,8 +370,8 @@ __device__ inline int demod_block8k(const DemodParams& p, const int blk, char* s
         }
         if (tid == 255) {
             const Item I = self_item();
-            C h0 = HvP[8], h1 = HvP[M + 8];
-            if constexpr (RAMP) { h0 = ramp(h0, LnP[8]); h1 = ramp(h1, LnP[M + 8]); }
+            C h0 = fused ? b1[PXi(8)] : HvP[PXi(8)], h1 = fused ? b2[PXi(8)] : HvP[SPAN + PXi(8)];
+            if constexpr (RAMP) { h0 = ramp(h0, LnP[PXi(8)]); h1 = ramp(h1, LnP[SPAN + PXi(8)]); }
             C xa = b0[PXi(8)], xb = xa;
             if (fused) untangle_pair(I, xa, xa, xa, xb);
             e_pair(I, xa, xb, h0, h1, h0, h1);
@@ -460,12 +524,21 @@ __device__ inline int demod_block8k(const DemodParams& p, const int blk, char* s
             b1[ix + P4096] = (x1[i] - x2[i]) * w;
         }
     }
+    stage_fence();
     __syncthreads();
     PHASE(7);
+    // the first post filter pair's tables into the arrays they will be applied in (b0: video, b2: burst; both dead now),
+    // under the next transform
+    const bool pre_f = !p.only05;
+    if (pre_f) stage_issue(&stg.bars[1], b0, (const C*)p.FP[0], b2, (const C*)p.FP[2], tid);
+#ifdef LDD_EMU
+    if (pre_f) __syncthreads();
+#endif
 
     // H. D = rfft(demod - ire0): stages 2-4 in b1, untangle in place (the same thread owns a pair here and in the
     //    post-filter step, so no barrier is needed between them)
     f2::dif_234<PK>(b1, tw, tid);
+    if (pre_f) stage_wait(&stg.bars[1], stg.ph_f);
     f2::half_sync(half);
     PHASE(8);
     LDD_UNROLL
@@ -520,12 +593,22 @@ __device__ inline int demod_block8k(const DemodParams& p, const int blk, char* s
         for (int it0 = 0; it0 < 8; it0 += 4) {
             Item I[4];
             C fa1[4], fb1[4], fa2[4], fb2[4], da[4], db[4];
+            const bool staged = set == 0 && pre_f;        // the tables sit in the slots of b2 / b0 this thread overwrites below
             LDD_UNROLL
             for (int i = 0; i < 4; ++i) {
                 I[i] = pair_item(S, WN, tid, it0 + i);
-                const int pp = I[i].kind == 1 ? M : I[i].pp;           // k = 0 pairs with F[M], kept behind the permuted table
-                fa2[i] = Fb[I[i].p]; fb2[i] = Fb[pp];
-                if (Fa) { fa1[i] = Fa[I[i].p]; fb1[i] = Fa[pp]; }
+                const int ip = PXi(I[i].p), iq = PXi(I[i].pp);
+                if (staged) {
+                    fa2[i] = b2[ip]; fb2[i] = b2[iq];
+                    if (Fa) { fa1[i] = b0[ip]; fb1[i] = b0[iq]; }
+                } else {
+                    fa2[i] = Fb[ip]; fb2[i] = Fb[iq];
+                    if (Fa) { fa1[i] = Fa[ip]; fb1[i] = Fa[iq]; }
+                }
+                if (I[i].kind == 1) {                      // k = 0 pairs with F[M], kept behind the permuted table
+                    fb2[i] = Fb[SPAN];
+                    if (Fa) fb1[i] = Fa[SPAN];
+                }
             }
             LDD_UNROLL
             for (int i = 0; i < 4; ++i) { da[i] = b1[PXi(I[i].p)]; db[i] = b1[PXi(I[i].pp)]; }
@@ -538,8 +621,10 @@ __device__ inline int demod_block8k(const DemodParams& p, const int blk, char* s
         if (tid == 255) {
             const Item I = self_item();
             const C d = b1[PXi(8)];
-            tangle_pair(I, d, d, Fb[8], Fb[8], b2);
-            if (Fa) tangle_pair(I, d, d, Fa[8], Fa[8], b0);
+            const bool staged = set == 0 && pre_f;
+            const C f2v = staged ? b2[PXi(8)] : Fb[PXi(8)], f1v = Fa ? (staged ? b0[PXi(8)] : Fa[PXi(8)]) : f2v;
+            tangle_pair(I, d, d, f2v, f2v, b2);
+            if (Fa) tangle_pair(I, d, d, f1v, f1v, b0);
         }
         f2::half_sync(half);
         PHASE(10);
@@ -613,6 +698,7 @@ __device__ inline int demod_block8k(const DemodParams& p, const int blk, char* s
         PHASE(13);
         sync_scan32(p, sc, stab, mask, (double*)b0, keep0, keep1, o, s_warp, s_total, s_last);
     }
+    stage_fence();
     __syncthreads();
     PHASE(15);
     return flagged;

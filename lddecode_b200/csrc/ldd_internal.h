@@ -2,6 +2,7 @@
 #pragma once
 #include "ldd_fft.cuh"
 #include "ldd_fft2.cuh"
+#include "ldd_async.cuh"
 #include "../../include/ldd_b200.h"
 
 #include <string>
@@ -39,7 +40,9 @@ struct DemodParams {
     double mtf_hold_level;
     const void* F[4];            // FVideo, FVideo05 (pre-rolled), FVideoBurst, FVideoPilot; k<=M; scaled 1/M
     // float32 copies in the digit-permuted order of the in-place transforms (ldd_fft2.cuh; N = 16384 only, else NULL):
-    // HvP[p] = Hv[idx(p)], HvP[M + p] = Hv[M + idx(p)]; lnMP likewise; FP[m][p] = F[m][idx(p)], FP[m][M] = F[m][M]
+    // in the block arrays' padded layout PX(p) = p + p/16, SPAN = 8704 entries per part (one bulk copy per part):
+    // HvP[PX(p)] = Hv[idx(p)], HvP[SPAN + PX(p)] = Hv[M + idx(p)]; lnMP likewise; FP[m][PX(p)] = F[m][idx(p)],
+    // FP[m][SPAN] = F[m][M].  (The float64 parameter set of the mixed lane's re-run: plain, index p, F[M] at index M.)
     const void* HvP;
     const void* lnMP;
     const void* FP[4];

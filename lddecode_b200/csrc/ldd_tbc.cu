@@ -268,24 +268,6 @@ struct TbfGeom {            // one work item (field, line), filled by thread 0 w
     int state;              // 0: nothing to do (line >= linecount), 1: bulk copy in flight, 2: load by hand, 3: bad geometry
 };
 
-#ifndef LDD_EMU
-__device__ inline unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ inline void mbar_init(void* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ inline void mbar_expect_tx(void* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ inline void bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ inline void mbar_wait(void* bar, unsigned parity) {
-    asm volatile(
-        "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
-        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-#endif
 
 __global__ void __launch_bounds__(TBF_THREADS, 5) tbc_f32_kernel(const TbcParams p, int nitems, int lines_per_field, int maxu) {
     LDD_DYN_SMEM(smem_raw);

@@ -432,12 +432,21 @@ __global__ void __launch_bounds__(TBF_THREADS, 5) tbc_f32_kernel(const TbcParams
             alpha = (-L + q * R) / den;
             beta = (-R + q * L) / den;
         }
-        // evaluate: positions in float64, polynomial in float32, the affine map to the uint16 scale folded into one FMA
+        // evaluate: polynomial in float32, the affine map to the uint16 scale folded into one FMA.  Positions
+        // x_j = fb + j step (np.linspace) need ~1e-5 samples at x ~ 2300, which a float32 x does not have; split instead:
+        // step = si + dd with si its nearest integer (2 for a nominal line), x_j = j si + (fb + j dd), and the bracket -- a
+        // few samples at most for any line the kernel accepts -- is a float32 FMA of two-part constants: no float64 and
+        // no 64-bit conversion per output sample.  Where that rounds across an integer the neighbouring interval is
+        // evaluated at t = 1 - eps instead of t = eps, which the spline's continuity makes the same value.
         const double ibd = (double)(long long)g.b;
         const double fb = g.b - ibd;
         const double stop = (g.e - g.b) + fb;
         const int W = p.outwidth;
         const double step = (stop - fb) / (double)W;
+        const int si = (int)(step + 0.5);
+        const double dd = step - (double)si;
+        const float d_hi = (float)dd, d_lo = (float)(dd - (double)d_hi);
+        const float fb_hi = (float)fb, fb_lo = (float)(fb - (double)fb_hi);
         const double wowf = p.wow ? (g.e - g.b) / (double)p.linelen : 1.0;
         // v = ((S + add) wow - ire0) / hz_ire - vsync_ire) * out_scale + out_off  =  S * ka + kb
         const double k1 = p.out_scale / p.hz_ire;
@@ -451,10 +460,14 @@ __global__ void __launch_bounds__(TBF_THREADS, 5) tbc_f32_kernel(const TbcParams
         const float* Mz = Ms + lead;
         const float* yz = ys + lead;
         for (int j = tid; j < W; j += TBF_THREADS) {
-            const double x = tbc_i2d(j) * step + fb;
-            int i = tbc_floor_nonneg(x);
-            if (i > dist - 1) i = dist - 1;
-            const float t = (float)(x - tbc_i2d(i)), u = 1.f - t;
+            const float jf = (float)j;
+            const float gx = fmaf(jf, d_hi, fb_hi) + fmaf(jf, d_lo, fb_lo);
+            const float fl = floorf(gx);
+            float t = gx - fl;
+            int i = j * si + (int)fl;
+            if (i > dist - 1) { t += (float)(i - (dist - 1)); i = dist - 1; }      // np.linspace's last points: beyond the last interval's start
+            if (i < 0) { t += (float)i; i = 0; }
+            const float u = 1.f - t;
             float Mi = Mz[i], Mj = Mz[i + 1];
             if (i < TBF_NPOW) { Mi = fmaf(alpha, s_rpow[i], Mi); Mj = fmaf(alpha, s_rpow[i + 1], Mj); }
             if (dist - i <= TBF_NPOW) { Mi = fmaf(beta, s_rpow[dist - i], Mi); Mj = fmaf(beta, s_rpow[dist - i - 1], Mj); }

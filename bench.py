@@ -463,7 +463,8 @@ def measure(a, system, audio, fmt, rank, world, local, dist, clocks_rank0=None, 
         # kernels of this library launched per step: demodulation (+ the float64 re-run of the mixed lane), 5 of the peak
         # chase + the peak list's copy to pinned memory, audio phase 2, table upload, hsync refinement + fix-up, VBI
         # decode, pilot (per-line + per-field) or 2 x (burst lines + vote), TBC, + the gather's metadata upload
-        launches_per_step = (2 if a.precision == "mixed" else 1) + 5 + 1 + (1 if audio else 0) + 1 + 2 + 1 + \
+        # (the mixed lane at the default block length is ONE launch: float64 re-runs happen inside the fused kernel)
+        launches_per_step = (2 if a.precision == "mixed" and BLOCKLEN != 16384 else 1) + 5 + 1 + (1 if audio else 0) + 1 + 2 + 1 + \
             (2 if system == "PAL" else 4) + 1 + (1 if world > 1 else 0)
         out = dict(value=value, ms_per_step=ms_step, realtime_x=value / FS[system] / world, fields_per_step=nfields * world,
                    gather=(None if gatherer is None else "NCCL gather" if type(gatherer).__name__ != "PeerGatherer" else

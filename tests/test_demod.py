@@ -239,3 +239,28 @@ def test_inplace_block_equals_stockham_block(backend, system, audio, monkeypatch
     b, _ = run("mixed")
     assert np.array_equal(a[0]["demod_sync"], b[0]["demod_sync"])
     np.testing.assert_allclose(a[0]["demod_05"], b[0]["demod_05"], rtol=2e-7, atol=0)
+
+
+def test_packed_captures_equal_unpacked_in_the_default_lane(backend):
+    """The float32 block of the default lane fetches 8-bit and .lds samples as aligned words and everything else sample by
+    sample, but its arithmetic is the same for every format and alignment: .lds, .r30 and 16-bit captures of the same
+    10-bit samples give bit-equal planes and audio, and so does a capture window that starts at an odd byte."""
+    from lddecode_b200 import _lib
+    fs = 8 * 315 / 88
+    s10 = synth.SynthRF("NTSC", fs, seed=5, bits=10).generate(120000)
+    n = len(s10) // 12 * 12
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=True, _backend=backend, precision="mixed")
+    outs = {}
+    for name, packed, f in (("u16", s10, _lib.FMT_U16), ("lds", synth.pack_lds(s10), _lib.FMT_LDS40), ("r30", synth.pack_r30(s10), _lib.FMT_R30)):
+        outs[name] = rf.demod_device(backend.to_device(packed), f, 0, n, 4000, 90000, 1, phase2=False).to_recarrays()
+    for name in ("lds", "r30"):
+        for p in outs["u16"][0].dtype.names:
+            assert np.array_equal(outs[name][0][p], outs["u16"][0][p]), (name, p)
+        assert np.array_equal(outs[name][1]["audio_left"], outs["u16"][1]["audio_left"]), name
+    # 8-bit: word-aligned window against the same samples at an odd offset of a longer buffer (sample-by-sample fetch)
+    s8 = synth.SynthRF("NTSC", fs, seed=6).generate(100001)
+    a = rf.demod_device(backend.to_device(s8[1:]), _lib.FMT_U8, 0, 100000, 2000, 70000, 1, phase2=False).to_recarrays()
+    dev = backend.to_device(s8)
+    b = rf.demod_device(dev[1:], _lib.FMT_U8, 0, 100000, 2000, 70000, 1, phase2=False).to_recarrays()
+    for p in a[0].dtype.names:
+        assert np.array_equal(a[0][p], b[0][p]), p

@@ -152,12 +152,6 @@ __device__ inline void untangle_pair(const Item& I, C za, C zb, C& xa, C& xb) {
     }
 }
 
-struct Blk {
-    C* b0;
-    C* b1;
-    C* b2;
-};
-
 // stages 4-2 of the DIT transform of one or two arrays (before: own warp's data complete; after: needs a CTA barrier)
 __device__ inline void dit_pair(C* a, C* b, const f2::Tw& tw, int tid) {
     f2::stage4<PK>(a, tid);

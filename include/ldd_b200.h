@@ -384,7 +384,7 @@ typedef struct ldd_pipe_bufs {
     long long* h_peaks;         /* peak_cap */
     double* h_peak_vals;        /* peak_cap */
     int* h_peak_count;          /* 2 */
-    unsigned char* h_tables;    /* h_tables_bytes >= upload_bytes of ldd_pipe_table_bytes */
+    unsigned char* h_tables;    /* h_tables_bytes >= upload_bytes of ldd_pipe_table_bytes (field tables + PCM tables) */
     long long h_tables_bytes;
     double* h_prefix;           /* prefix_cap samples of demod_sync for a window the capture-wide chase does not decide */
     long long prefix_cap;       /* >= 40 * linelen */
@@ -436,6 +436,28 @@ int ldd_pipe_launch(ldd_pipe* p, const void* rf_dev, int fmt, long long rf_base,
  * pic_cap - 1).  pic_cap = fields / frames pic_dev can hold; status_dev [max_fields] gets the per-field error bits. */
 int ldd_pipe_finish(ldd_pipe* p, double colorlevel, double colorphase, int frame_mode, void* pic_dev, long long pic_stride,
                     long long pic_cap, int* status_dev, void* refine_stream, void* main_stream, ldd_pipe_result* out);
+
+/* Optional stage 3, asynchronous on `stream` (the main stream of stages 1 and 2): the 48 kHz PCM of the located fields of
+ * the last ldd_pipe_finish, i.e. downscale_audio (lddecode_core.py:431-484) per field as Field.downscale(audio=True) calls
+ * it (:809-810) on the final line positions, from the range's phase-2 audio (ldd_pipe_launch with audio_phase2 = 1).
+ * The reference resamples each field from the audio of that field's own read window; its sample idx there lies at
+ * (window start / decimation + idx) of the range's audio, in general between two samples, and is read by four-point
+ * Lagrange interpolation (a window that starts on the range's audio grid gets the reference's very sample).  The time
+ * offsets are chained on the host:
+ *   LDD_PCM_CHAIN_FIELDS  every field starts where the previous one ended (audio_next_offset -> audio_offset);
+ *   LDD_PCM_CHAIN_FRAMER  as Framer.readframe does for CLV discs (:1203, 1260-1289): all fields of one readframe call use the
+ *                         offset the call started with, the field that closes the frame hands its audio_next_offset on,
+ *                         and fields ahead of the first frame are dropped while bit 1 of *frame_state is set.
+ * *audio_offset (seconds) and *frame_state (bit 0: a frame is open, bit 1: Framer's `firstframe`) are read and updated,
+ * so consecutive ranges of one capture continue each other; start with 0.0 and 2.  out_dev receives interleaved L/R
+ * int16, field k at out_off[k] .. out_off[k+1] (host array of nlocated + 1 entries, filled before the call returns;
+ * an empty span = dropped field); status_dev [nlocated] gets bit 4 (16) where an index left the line table or the audio.
+ * scale = the reference's `scale` argument (64), freq_hz its `freq` (48000). */
+#define LDD_PCM_CHAIN_FIELDS 0
+#define LDD_PCM_CHAIN_FRAMER 1
+int ldd_pipe_pcm(ldd_pipe* p, double freq_hz, double scale, double line_period_us, double audio_lfreq, double audio_rfreq,
+                 int chain, double* audio_offset, int* frame_state, short* out_dev, long long out_cap, long long* out_off,
+                 int* status_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -146,7 +146,11 @@ SIGNATURES.update({
                                   C.c_longlong, C.c_longlong, C.c_double, C.c_int, C.c_void_p]),
     "ldd_pipe_finish": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.POINTER(PipeResult)]),
+    "ldd_pipe_pcm": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+                               C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p, C.c_longlong, C.POINTER(C.c_longlong),
+                               C.c_void_p, C.c_void_p]),
 })
+PCM_CHAIN_FIELDS, PCM_CHAIN_FRAMER = 0, 1
 
 WINDOW_PEAKS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.POINTER(C.c_void_p),
                               C.POINTER(C.c_void_p), C.POINTER(C.c_int))

@@ -82,7 +82,10 @@ struct PcmParams {
     long long audio_len;
     const long long* abase;      // [nfields] index of the window's audio sample 0 in audio_l/r (NULL: 0)
     const double* linelocs;      // [nfields][ll_stride]
-    const int* nll;              // [nfields] entries of the field's line table (linecount + 4)
+    const int* nll;              // [nfields] entries of the field's line table (linecount + 4), less nll_add
+    int nll_add;
+    const double* fbase;         // range-wide audio (ldd_pipe_pcm): [nfields] position of the window's audio sample 0 in
+                                 // audio_l/r, in audio samples and in general fractional; NULL: the audio is the window's own
     const double* t0;            // [nfields] arange start
     const double* t1;            // [nfields] arange's second value, t0 + 1/freq (np.arange fills start + i * (t1 - t0) from i = 2 on)
     const int* nout;             // [nfields] stereo samples to produce
@@ -97,8 +100,9 @@ __global__ void __launch_bounds__(256) pcm_kernel(const PcmParams p) {
     const int f = blockIdx.y;
     const int n = p.nout[f];
     const double* ll = p.linelocs + (size_t)f * p.ll_stride;
-    const int nll = p.nll[f];
+    const int nll = p.nll[f] + p.nll_add;
     const long long ab = p.abase ? p.abase[f] : 0;
+    const double fb = p.fbase ? p.fbase[f] : 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double t0 = p.t0[f], t1 = p.t1[f];
         const double t = i == 0 ? t0 : (i == 1 ? t1 : t0 + (double)i * (t1 - t0));
@@ -113,11 +117,35 @@ __global__ void __launch_bounds__(256) pcm_kernel(const PcmParams p) {
             double sampleloc = cur;
             sampleloc += (nxt - cur) * (linenum - floor(linenum));
             const double swow = (nxt - cur) / p.linelen;
-            const long long idx = (long long)(sampleloc / p.scale) + ab;
-            if (idx < 0 || idx >= p.audio_len) {
+            long long idx = (long long)(sampleloc / p.scale) + ab;
+            double l = 0.0, r = 0.0;
+            bool ok;
+            if (p.fbase) {
+                // The reference reads sample idx of the window's own phase-2 audio.  On the range-wide audio that instant
+                // lies at x = fbase + idx, between two samples when the window does not start on the range's audio
+                // grid: four-point Lagrange interpolation there (weights 0, 1, 0, 0 when x is whole, i.e. the very
+                // sample the reference reads).
+                const double x = fb + (double)idx;
+                const double xf = floor(x), u = x - xf;
+                idx = (long long)xf;
+                ok = idx >= 1 && idx + 2 < p.audio_len;
+                if (ok) {
+                    const double w0 = -u * (u - 1.0) * (u - 2.0) * (1.0 / 6.0), w1 = (u + 1.0) * (u - 1.0) * (u - 2.0) * 0.5;
+                    const double w2 = -(u + 1.0) * u * (u - 2.0) * 0.5, w3 = (u + 1.0) * u * (u - 1.0) * (1.0 / 6.0);
+                    if (u == 0.0) {
+                        l = p.audio_l[idx]; r = p.audio_r[idx];
+                    } else {
+                        l = w0 * p.audio_l[idx - 1] + w1 * p.audio_l[idx] + w2 * p.audio_l[idx + 1] + w3 * p.audio_l[idx + 2];
+                        r = w0 * p.audio_r[idx - 1] + w1 * p.audio_r[idx] + w2 * p.audio_r[idx + 1] + w3 * p.audio_r[idx + 2];
+                    }
+                }
+            } else {
+                ok = idx >= 0 && idx < p.audio_len;
+                if (ok) { l = p.audio_l[idx]; r = p.audio_r[idx]; }
+            }
+            if (!ok) {
                 atomicOr(&p.status[f], 16);
             } else {
-                double l = p.audio_l[idx], r = p.audio_r[idx];
                 l *= swow; r *= swow;
                 l -= p.lfreq; r -= p.rfreq;
                 // int(np.round(x * 32767 / 150000)): round half to even; np.clip(-32766, 32766)
@@ -136,6 +164,23 @@ __global__ void __launch_bounds__(256) pcm_kernel(const PcmParams p) {
 }  // namespace ldd
 
 using namespace ldd;
+
+// ldd_pipe_pcm's launch: the audio is the range's own (audio sample 0 <-> plane sample 0), fbase_dev[f] the field window's
+// first plane sample divided by the total audio decimation, linecount_dev the fields' line counts (tables hold 4 more).
+int ldd::pcm_range_launch(ldd_handle* h, const double* audio_l, const double* audio_r, long long audio_len, const double* fbase_dev,
+                          const double* linelocs_dev, int ll_stride, const int* linecount_dev, const double* t0_dev,
+                          const double* t1_dev, const int* nout_dev, const long long* out_off_dev, int nfields, int max_nout,
+                          double lineloc_add, double scale, double line_period_us, double lfreq, double rfreq, short* out_dev,
+                          int* status_dev, cudaStream_t st) {
+    if (nfields <= 0 || max_nout <= 0) return LDD_OK;
+    PcmParams p;
+    p.audio_l = audio_l; p.audio_r = audio_r; p.audio_len = audio_len; p.abase = nullptr; p.fbase = fbase_dev;
+    p.linelocs = linelocs_dev; p.nll = linecount_dev; p.nll_add = 4; p.t0 = t0_dev; p.t1 = t1_dev; p.nout = nout_dev;
+    p.out_off = out_off_dev; p.ll_stride = ll_stride; p.lineloc_add = lineloc_add; p.line_period = line_period_us;
+    p.linelen = (double)h->cfg.linelen; p.scale = scale; p.lfreq = lfreq; p.rfreq = rfreq; p.out = out_dev; p.status = status_dev;
+    LDD_LAUNCH(pcm_kernel, dim3((max_nout + 255) / 256, nfields), dim3(256), 0, st, p);
+    return launch_status(h, "pcm_kernel");
+}
 
 extern "C" int ldd_audio_phase2(ldd_handle* h, const double* in_l_dev, const double* in_r_dev, long long len,
                                 double* out_l_dev, double* out_r_dev, void* stream) {
@@ -174,7 +219,7 @@ extern "C" int ldd_downscale_audio(ldd_handle* h, const double* audio_l_dev, con
     if (nfields <= 0 || max_nout <= 0) return LDD_OK;
     PcmParams p;
     p.audio_l = audio_l_dev; p.audio_r = audio_r_dev; p.audio_len = audio_len; p.abase = audio_base_dev;
-    p.linelocs = linelocs_dev; p.nll = nll_dev; p.t0 = t0_dev; p.t1 = t1_dev; p.nout = nout_dev; p.out_off = out_off_dev;
+    p.linelocs = linelocs_dev; p.nll = nll_dev; p.nll_add = 0; p.fbase = nullptr; p.t0 = t0_dev; p.t1 = t1_dev; p.nout = nout_dev; p.out_off = out_off_dev;
     p.ll_stride = ll_stride; p.lineloc_add = lineloc_add;
     // SysParams line_period / audio_lfreq / audio_rfreq (lddecode_core.py:43-44, 51, 62, 72-73) come from the caller
     p.line_period = line_period_us;

@@ -88,6 +88,11 @@ int demod_blocks_padded(ldd_handle* h, const void* rf_dev, int fmt, long long rf
                         long long first_sample, long long nblocks, long long total_out,
                         void* const* planes_dev, double* audio1_l_dev, double* audio1_r_dev,
                         long long audio1_len, void* stream);
+int pcm_range_launch(ldd_handle* h, const double* audio_l, const double* audio_r, long long audio_len, const double* fbase_dev,
+                     const double* linelocs_dev, int ll_stride, const int* linecount_dev, const double* t0_dev,
+                     const double* t1_dev, const int* nout_dev, const long long* out_off_dev, int nfields, int max_nout,
+                     double lineloc_add, double scale, double line_period_us, double lfreq, double rfreq, short* out_dev,
+                     int* status_dev, cudaStream_t st);
 bool demod_mixed_fused_ok(const DemodParams& p, int threads, size_t smem_bytes, size_t sp_bytes);
 int launch_demod_mixed(const DemodParams& pf, const DemodParams& pq, int* queue, int grid, cudaStream_t st, size_t smem_bytes);
 

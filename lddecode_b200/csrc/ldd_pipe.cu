@@ -7,6 +7,8 @@
 //                     lddecode_core.py:1194-1223, via ldd_field_chain), fills the per-field tables in page-locked
 //                     memory and enqueues upload, hsync / burst | pilot refinement, VBI decode and TBC for all located
 //                     fields from preallocated device tables.  Returns while those kernels run.
+//   ldd_pipe_pcm      (optional, after finish) 48 kHz PCM of the located fields from the range's phase-2 audio, with the
+//                     time offsets chained the way Framer.readframe chains them (lddecode_core.py:1203, 1283-1289).
 //
 // The reference does this per field in Python (Framer.readfield -> RFDecode.demod -> FieldNTSC/FieldPAL.__init__);
 // here the host's share of a step is the walk (~10 us per field) plus a dozen launches.  All buffers are the
@@ -28,7 +30,10 @@ struct TableLayout {
     // upload part (host -> device in one copy)
     size_t o_base, o_winlen, o_l1, o_linecount, o_bad, o_outoff, upload_bytes;
     // device-only part
-    size_t o_l2, o_bad2, o_l3, o_l4, o_bl, o_vbi, o_status_unused, total_bytes;
+    size_t o_l2, o_bad2, o_l3, o_l4, o_bl, o_vbi, o_status_unused;
+    // tables of ldd_pipe_pcm: on the device at o_pcm, in the page-locked staging behind the upload part; r_* are offsets
+    // inside that region
+    size_t o_pcm, r_t0, r_t1, r_fbase, r_off, r_nout, pcm_bytes, total_bytes;
 };
 
 TableLayout layout(int F) {
@@ -49,6 +54,13 @@ TableLayout layout(int F) {
     t.o_bl = take((size_t)F * LL * 4);
     t.o_vbi = take((size_t)F * 4 * 4);
     t.o_status_unused = o;
+    t.o_pcm = o;
+    t.r_t0 = take((size_t)F * 8) - t.o_pcm;
+    t.r_t1 = take((size_t)F * 8) - t.o_pcm;
+    t.r_fbase = take((size_t)F * 8) - t.o_pcm;
+    t.r_off = take((size_t)F * 8) - t.o_pcm;
+    t.r_nout = take((size_t)F * 4) - t.o_pcm;
+    t.pcm_bytes = o - t.o_pcm;
     t.total_bytes = o;
     return t;
 }
@@ -64,6 +76,13 @@ struct ldd_pipe {
     cudaEvent_t ev_peaks = nullptr;     // recorded behind the peak list's copy to page-locked memory
     cudaEvent_t ev_upload = nullptr;    // the table upload from h_tables has executed
     cudaEvent_t ev_done = nullptr;      // refine + TBC of the last finish
+    cudaEvent_t ev_pcm = nullptr;       // the PCM tables' upload has executed
+    bool pcm_pending = false;
+    // what ldd_pipe_pcm needs of the last finish
+    bool finished = false;
+    const void* fin_final = nullptr;
+    const void* fin_linecount = nullptr;
+    double fin_lineloc_add = 0.0;
     cudaStream_t side = nullptr;        // prefix copies of off-chain windows
     bool upload_pending = false;
     long long audio1_len = 0, audio2_len = 0;
@@ -160,7 +179,7 @@ extern "C" {
 int ldd_pipe_table_bytes(int max_fields, long long* upload_bytes, long long* device_bytes) {
     if (max_fields < 1) return LDD_EINVAL;
     TableLayout t = layout(max_fields);
-    if (upload_bytes) *upload_bytes = (long long)t.upload_bytes;
+    if (upload_bytes) *upload_bytes = (long long)(t.upload_bytes + t.pcm_bytes);
     if (device_bytes) *device_bytes = (long long)t.total_bytes;
     return LDD_OK;
 }
@@ -177,7 +196,7 @@ int ldd_pipe_create(ldd_handle* h, const ldd_pipe_bufs* bufs, int max_fields, lo
         return LDD_EINVAL;
     }
     TableLayout t = layout(max_fields);
-    if ((size_t)bufs->tables_bytes < t.total_bytes || (size_t)bufs->h_tables_bytes < t.upload_bytes) {
+    if ((size_t)bufs->tables_bytes < t.total_bytes || (size_t)bufs->h_tables_bytes < t.upload_bytes + t.pcm_bytes) {
         h->err = "ldd_pipe_create: table buffers too small (ldd_pipe_table_bytes)";
         return LDD_ECAP;
     }
@@ -191,6 +210,7 @@ int ldd_pipe_create(ldd_handle* h, const ldd_pipe_bufs* bufs, int max_fields, lo
     if (cudaEventCreateWithFlags(&p->ev_peaks, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_upload, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_pcm, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess) {
         h->err = "ldd_pipe_create: event / stream creation failed";
         delete p;
@@ -207,6 +227,7 @@ void ldd_pipe_destroy(ldd_pipe* p) {
     if (p->ev_peaks) cudaEventDestroy(p->ev_peaks);
     if (p->ev_upload) cudaEventDestroy(p->ev_upload);
     if (p->ev_done) cudaEventDestroy(p->ev_done);
+    if (p->ev_pcm) cudaEventDestroy(p->ev_pcm);
     if (p->side) cudaStreamDestroy(p->side);
 #endif
     delete p;
@@ -282,6 +303,7 @@ int ldd_pipe_finish(ldd_pipe* p, double colorlevel, double colorphase, int frame
     if (!p || !out || !pic_dev || !status_dev) return LDD_EINVAL;
     if (!p->launched) return pfail(p, LDD_EINVAL, "ldd_pipe_finish without ldd_pipe_launch");
     p->launched = false;
+    p->finished = false;
     ldd_handle* h = p->h;
     const ldd_config& c = h->cfg;
     const bool pal = c.system == LDD_SYSTEM_PAL;
@@ -321,7 +343,8 @@ int ldd_pipe_finish(ldd_pipe* p, double colorlevel, double colorphase, int frame
     const double shift33 = colorphase * (3.14159265358979323846 / 180.0);
     out->lineloc_add = pal ? 0.0 : (shift33 - 8) * ((c.freq_hz / 1e6) / (4.0 * 315.0 / 88.0));
     out->frame_of = nullptr;
-    if (n == 0) return LDD_OK;
+    p->fin_final = out->d_final; p->fin_linecount = out->d_linecount; p->fin_lineloc_add = out->lineloc_add;
+    if (n == 0) { p->finished = true; return LDD_OK; }
     // ---- per-field tables of the located fields -> page-locked staging
     if (p->upload_pending) { cudaEventSynchronize(p->ev_upload); p->upload_pending = false; }
     unsigned char* ht = p->b.h_tables;
@@ -406,7 +429,81 @@ int ldd_pipe_finish(ldd_pipe* p, double colorlevel, double colorphase, int frame
         cudaEventRecord(p->ev_done, rs);
         cudaStreamWaitEvent(ms, p->ev_done, 0);
     }
+    p->finished = true;
     return LDD_OK;
+}
+
+int ldd_pipe_pcm(ldd_pipe* p, double freq_hz, double scale, double line_period_us, double audio_lfreq, double audio_rfreq,
+                 int chain, double* audio_offset, int* frame_state, short* out_dev, long long out_cap, long long* out_off,
+                 int* status_dev, void* stream) {
+    if (!p || !audio_offset || !frame_state || !out_dev || !out_off || !status_dev || freq_hz <= 0 || scale <= 0 ||
+        line_period_us <= 0 || (chain != LDD_PCM_CHAIN_FIELDS && chain != LDD_PCM_CHAIN_FRAMER))
+        return LDD_EINVAL;
+    if (!p->finished) return pfail(p, LDD_EINVAL, "ldd_pipe_pcm without ldd_pipe_finish");
+    if (p->audio2_len <= 0 || !p->b.audio2_l || !p->b.audio2_r) return pfail(p, LDD_EINVAL, "ldd_pipe_pcm needs the range's phase-2 audio");
+    ldd_handle* h = p->h;
+    const ldd_config& c = h->cfg;
+    const int n = (int)p->located.size();
+    out_off[0] = 0;
+    if (n == 0) return LDD_OK;
+    const TableLayout& t = p->lay;
+    if (p->pcm_pending) { cudaEventSynchronize(p->ev_pcm); p->pcm_pending = false; }
+    unsigned char* hp = p->b.h_tables + t.upload_bytes;
+    double* ht0 = (double*)(hp + t.r_t0);
+    double* ht1 = (double*)(hp + t.r_t1);
+    double* hfb = (double*)(hp + t.r_fbase);
+    long long* hoff = (long long*)(hp + t.r_off);
+    int* hn = (int*)(hp + t.r_nout);
+    // plane samples per phase-2 audio sample: the first stage keeps every (N / A)-th, the second every 4th
+    const double dec = 4.0 * (double)(c.blocklen / h->A);
+    const int topfirst = c.system == LDD_SYSTEM_PAL ? 0 : 1;
+    const double soundgap = 1.0 / freq_hz;
+    double off = *audio_offset;
+    bool open = (*frame_state & 1) != 0, first = (*frame_state & 2) != 0;
+    int maxn = 0;
+    for (int k = 0; k < n; ++k) {
+        const int w = p->owned[p->located[k]];
+        const ldd_field& f = p->fields[w];
+        // np.arange(timeoffset, frametime + soundgap, soundgap): ceil((stop - start) / step) values start + i * ((start +
+        // step) - start); the field produces one sample less and hands on arange[-1] - frametime (lddecode_core.py:432-438, 482)
+        const double frametime = (line_period_us * (double)f.linecount) / 1000000.0;
+        const double stop = frametime + soundgap;
+        const double lenf = std::ceil((stop - off) / soundgap);
+        const long long len = lenf > 0 ? (long long)lenf : 0;
+        const double t1 = off + soundgap, delta = t1 - off;
+        const double last = len <= 1 ? off : (len == 2 ? t1 : off + (double)(len - 1) * delta);
+        const double next = len >= 1 ? last - frametime : off;
+        bool include = true, closes = false;
+        if (chain == LDD_PCM_CHAIN_FRAMER) {
+            // Framer.readframe (lddecode_core.py:1260-1289), CLV pairing: every field of a call is built with the offset
+            // the call started with; a field whose parity is `topfirst` opens the frame, the next one closes it and the
+            // closing field's offset is carried on; fields ahead of the very first frame are not written
+            if (f.istop == topfirst) open = true;
+            else if (open) closes = true;
+            include = open || closes || !first;
+        }
+        ht0[k] = off; ht1[k] = t1;
+        hfb[k] = (double)p->base[w] / dec;
+        hn[k] = include && len > 1 ? (int)(len - 1) : 0;
+        hoff[k] = out_off[k];
+        out_off[k + 1] = out_off[k] + 2LL * hn[k];
+        maxn = std::max(maxn, hn[k]);
+        if (chain == LDD_PCM_CHAIN_FIELDS) off = next;
+        else if (closes) { off = next; open = false; first = false; }
+    }
+    if (out_off[n] > out_cap) return pfail(p, LDD_ECAP, "PCM buffer too small");
+    *audio_offset = off;
+    *frame_state = (open ? 1 : 0) | (first ? 2 : 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* dp = p->b.field_tables + t.o_pcm;
+    int rc = ldd_copy_small(dp, hp, t.pcm_bytes, st);
+    if (rc) return pfail(p, rc, "PCM table upload failed");
+    cudaEventRecord(p->ev_pcm, st);
+    p->pcm_pending = true;
+    return pcm_range_launch(h, p->b.audio2_l, p->b.audio2_r, p->audio2_len, (const double*)(dp + t.r_fbase), (const double*)p->fin_final,
+                            LL, (const int*)p->fin_linecount, (const double*)(dp + t.r_t0), (const double*)(dp + t.r_t1),
+                            (const int*)(dp + t.r_nout), (const long long*)(dp + t.r_off), n, maxn, p->fin_lineloc_add, scale,
+                            line_period_us, audio_lfreq, audio_rfreq, out_dev, status_dev, st);
 }
 
 }  // extern "C"

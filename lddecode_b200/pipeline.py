@@ -719,6 +719,41 @@ class CaptureDecoder:
         res = self._finish(pend, frame_mode=True, pic_stride=fstride, pic_cap=cap)
         return res, slot.d_pic[:res.nframes * fstride].reshape(-1, fstride)
 
+    # -- 48 kHz PCM of a range (SURVEY section 8f-1 in pipeline mode)
+    def pcm(self, res, audio_offset=0.0, frame_state=2, chain='framer', freq=48000.0, scale=64):
+        """int16 L/R PCM of the located fields of `res` (the latest result of its workspace, decoded with the analog
+        audio on): downscale_audio (lddecode_core.py:431-484) per field on the final line positions, on the device, from
+        the range's phase-2 audio (ldd_pipe_pcm).  chain='framer': time offsets as Framer.readframe carries them for CLV
+        discs (every field of a frame starts at the offset the frame started with, fields ahead of the first frame are
+        dropped while bit 1 of frame_state is set); chain='fields': every field continues the previous one.
+        Returns (list of int16 arrays | None for a dropped or flagged field, audio_offset, frame_state) -- pass the two
+        state values to the next range of the same capture."""
+        res._live()
+        slot, rf = res.slot, res.slot.rf
+        be = rf._be
+        n = len(res.located)
+        if n == 0:
+            return [], audio_offset, frame_state
+        SP = rf.SysParams
+        per_field = int((SP['line_period'] * (SP['frame_lines'] // 2 + 1) / 1e6) * freq) + 4
+        cap = 2 * per_field * n
+        if getattr(slot, 'd_pcm', None) is None or len(slot.d_pcm) < cap:
+            slot.d_pcm = be.empty(cap, np.int16)
+        st = be.zeros(n, np.int32)
+        off = (C.c_longlong * (n + 1))()
+        ao, fs = C.c_double(float(audio_offset)), C.c_int(int(frame_state))
+        rf._check(be.lib.ldd_pipe_pcm(slot.h, float(freq), float(scale), float(SP['line_period']), float(SP['audio_lfreq']),
+                                      float(SP['audio_rfreq']), _lib.PCM_CHAIN_FRAMER if chain == 'framer' else _lib.PCM_CHAIN_FIELDS,
+                                      C.byref(ao), C.byref(fs), be.ptr(slot.d_pcm), cap, off, be.ptr(st), be.stream()))
+        be.synchronize()
+        pcm = be.to_host(slot.d_pcm[:max(int(off[n]), 1)])
+        bad = be.to_host(st)
+        out = []
+        for k in range(n):
+            a, b = int(off[k]), int(off[k + 1])
+            out.append(pcm[a:b].copy() if b > a and not (bad[k] & 16) else None)
+        return out, ao.value, fs.value
+
     # -- host copies
     def pictures(self, res):
         """uint16 TBC fields of the located windows -> list of (readsample, istop, array | None)."""

@@ -694,6 +694,60 @@ def decode_field(dec, video, start=0, colorlevel=1.45, colorphase=91.5, full=Tru
     return r
 
 
+# ---- 48 kHz PCM along the line positions (lddecode_core.py:431-484) ---------------------------------
+def downscale_audio(dec, audio, lineinfo, linecount, timeoffset=0.0, freq=48000.0, scale=64):
+    """downscale_audio (lddecode_core.py:431-484): audio = phase-2 audio of the field's read window, lineinfo = the
+    field's final line positions.  Returns (int16 interleaved L/R, time offset for the next field)."""
+    SP = dec.SP
+    frametime = (SP["line_period"] * linecount) / 1000000
+    soundgap = 1 / freq
+    times = np.arange(timeoffset, frametime + soundgap, soundgap, dtype=np.double)
+    n = len(times) - 1
+    out = np.zeros(2 * max(n, 0), dtype=np.int32)
+    for i in range(n):
+        linenum = ((times[i] * 1000000) / SP["line_period"]) + 1
+        li = int(linenum)
+        cur = lineinfo[li]
+        nxt = lineinfo[li + 1] if li + 1 < len(lineinfo) else cur + dec.linelen
+        loc = cur + (nxt - cur) * (linenum - np.floor(linenum))
+        wow = (nxt - cur) / dec.linelen
+        k = int(loc / scale)
+        out[2 * i] = int(np.round((audio["audio_left"][k] * wow - SP["audio_lfreq"]) * 32767 / 150000))
+        out[2 * i + 1] = int(np.round((audio["audio_right"][k] * wow - SP["audio_rfreq"]) * 32767 / 150000))
+    return np.clip(out, -32766, 32766).astype(np.int16), times[-1] - frametime
+
+
+def framer_audio_walk(dec, loader, nfields, readlen=1000000, mtf_level=1, firstframe=True):
+    """The audio side of Framer.readframe called in a loop (lddecode_core.py:1194-1223, 1256-1289; CLV pairing by field
+    parity): every field of one readframe call is built with the Framer's audio_offset as the call found it, the field that
+    closes the frame hands its audio_next_offset on, and fields read ahead of the very first frame are not written.
+    Returns [(readsample, FieldResult, pcm | None)] for the first nfields valid fields, and the final audio_offset."""
+    topfirst = dec.SP["topfirst"]
+    out, offset, rs, fieldcount = [], 0.0, 0, 0
+    while len(out) < nfields:
+        d = demod(dec, loader, rs, readlen, mtf_level)
+        if d is None:
+            break
+        f = decode_field(dec, d[0], 0)
+        here = rs
+        rs += f.nextfieldoffset
+        if not f.valid:
+            if len(f.peaklist) < 100:                # readfield's jumps over unreadable stretches (:1208-1213)
+                rs = here + int(dec.freq_hz * 10)
+            elif len(f.vsyncs) == 0:
+                rs = here + int(dec.freq_hz * 1)
+            continue
+        pcm, nxt = downscale_audio(dec, d[1], f.linelocs, f.linecount, offset)
+        if f.istop == topfirst:
+            fieldcount = 1
+        elif fieldcount == 1:
+            fieldcount = 2
+        out.append((here, f, pcm if (fieldcount or not firstframe) else None))
+        if fieldcount == 2:
+            offset, fieldcount, firstframe = nxt, 0, False
+    return out, offset
+
+
 # ---- integer unpackers (ddunpack.c:11-36, lddutils.py:150-229) -----------------------------------
 def unpack_r30_raw(words, offset, n):
     """lddutils.py:150-173: three 10-bit fields per LE u32, raw 0..1023 as int16."""

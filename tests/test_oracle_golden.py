@@ -94,6 +94,29 @@ def test_field_matches_reference(golden, stitched, name):
     assert np.array_equal(np.array(codes), g["field_linecode"])
 
 
+def test_downscale_audio_matches_reference(golden, stitched):
+    """downscale_audio on the reference's own phase-2 audio and line table: identical int16 PCM and carried offset."""
+    g = golden("ntsc")
+    dec, (video, audio) = stitched("ntsc")
+    ref_audio = {"audio_left": g["audio_left"], "audio_right": g["audio_right"]}
+    pcm, nxt = O.downscale_audio(dec, ref_audio, g["field_linelocs"], int(g["field_linecount"]), 0)
+    assert pcm.dtype == np.int16 and np.array_equal(pcm, g["field_dsaudio"])
+    assert nxt == float(g["field_audio_next_offset"])
+    pcm2, _ = O.downscale_audio(dec, audio, g["field_linelocs"], int(g["field_linecount"]), 0)       # the oracle's own audio
+    assert np.abs(pcm2.astype(np.int64) - g["field_dsaudio"]).max() <= 1
+
+
+def test_framer_audio_walk_matches_reference_frame(golden):
+    """The Framer.readframe audio chain of the oracle against the frame recorded from the reference's own Framer."""
+    g = golden("ntsc_frame")
+    dec = O.Decoder(float(g["fs_mhz"]), "NTSC", int(g["blocklen"]))
+    fields, offset = O.framer_audio_walk(dec, _loader(g["capture"]), 2)
+    assert [f.linecount for _, f, _ in fields] == list(g["field_readlens"])
+    con = np.concatenate([p for _, _, p in fields if p is not None])
+    assert len(con) == len(g["conaudio"]) and np.abs(con.astype(np.int64) - g["conaudio"]).max() <= 1
+    np.testing.assert_allclose(offset, float(g["audio_offset"]), rtol=0, atol=1e-12)
+
+
 @pytest.mark.parametrize("name", ["ntsc", "pal"])
 def test_scale_and_notaknot_restatement(golden, stitched, name):
     """scale() == reference scale(); the written-out not-a-knot spline equals it to <1e-6 Hz."""

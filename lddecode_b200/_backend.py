@@ -35,6 +35,9 @@ class CudaBackend:
     def zeros(self, n, dtype):
         return self.torch.zeros(int(n), dtype=_NP2TORCH[np.dtype(dtype)], device=self.device)
 
+    def fill_zero(self, buf):
+        buf.zero_()
+
     def to_device(self, arr):
         arr = np.ascontiguousarray(arr)
         t = self.torch.from_numpy(arr)
@@ -113,6 +116,9 @@ class EmuBackend:
 
     def zeros(self, n, dtype):
         return np.zeros(int(n), dtype=dtype)
+
+    def fill_zero(self, buf):
+        buf[...] = 0
 
     def to_device(self, arr):
         return np.ascontiguousarray(arr).copy()

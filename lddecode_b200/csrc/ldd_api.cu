@@ -334,6 +334,10 @@ int ldd_set_filter(ldd_handle* h, int id, const double* table, int n) {
         default:
             return fail(h, LDD_EINVAL, "unknown filter id %d", id);
     }
+    // The copies above are staged from pageable memory and the permuted copies are built on the legacy stream; the
+    // kernels that read the tables run on the caller's (non-blocking) streams, which the legacy stream does not order.
+    // A table upload is set-up work: wait until it is in place.
+    CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)0));
     h->have_filter[id] = true;
     return LDD_OK;
 }

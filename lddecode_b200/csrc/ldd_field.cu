@@ -1025,6 +1025,7 @@ extern "C" int ldd_refine_burst(ldd_handle* h, const float* burst_dev, long long
         auto g = [&](int q) -> double { int a = q < 0 ? -q : q; return a > BURST_K ? 0.0 : c * pow(r, (double)a); };
         for (int m = 0; m <= 2 * (BURST_K + 1); ++m) { int k = m - (BURST_K + 1); taps[m] = 6.0 * (g(k - 1) - 2.0 * g(k) + g(k + 1)); }
         cudaMemcpyToSymbol(c_burst_taps, taps, sizeof taps);
+        cudaStreamSynchronize((cudaStream_t)0);      // staged from pageable memory; the kernels run on non-blocking streams
         h->burst_taps_set = true;
     }
     double* ws = (double*)h->pilot_ws;

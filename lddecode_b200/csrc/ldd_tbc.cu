@@ -532,6 +532,7 @@ extern "C" int ldd_tbc_fields_ex(ldd_handle* h, const float* plane_dev, long lon
         double rp[TBC_NPOW];
         for (int i = 0; i < TBC_NPOW; ++i) rp[i] = pow(r, (double)i);
         cudaMemcpyToSymbol(c_tbc_rpow, rp, sizeof rp);
+        cudaStreamSynchronize((cudaStream_t)0);      // staged from pageable memory; the kernels run on non-blocking streams
         h->tbc_taps_set = true;
     }
     cudaStream_t st = (cudaStream_t)stream;

@@ -183,6 +183,11 @@ class PipeSlot:
             pass
 
 
+def split_pcm(pcm, off, status):
+    """Per-field views of a range's PCM: None where the field was dropped (empty span) or an index left the tables."""
+    return [pcm[off[k]:off[k + 1]] if off[k + 1] > off[k] and not (status[k] & 16) else None for k in range(len(off) - 1)]
+
+
 class Pending:
     """A launched range: ldd_pipe_launch has been enqueued on `slot`."""
 
@@ -205,10 +210,15 @@ class HostStreamDecoder:
     returns the RangeResult and a host view [nfields, out_stride] of its uint16 fields that stays valid
     until the second-next finish(); the RangeResult's device planes stay valid until the second-next
     launch().  With analog audio decoding on, the two channels are downloaded with the fields:
-    res.audio_host = (left, right) float64 views, valid as long as the fields."""
+    res.audio_host = (left, right) float64 views, valid as long as the fields.  pcm=True (chunks that are consecutive
+    ranges of ONE capture, as FileStreamDecoder feeds them): the 48 kHz PCM of every chunk's fields comes down as well,
+    chained from chunk to chunk as Framer.readframe chains it: res.pcm_host = list of int16 views (None: dropped field)."""
 
-    def __init__(self, cd, fmt, ncap_max, max_fields=96, np_dtype=np.uint8, nbytes_max=None):
+    def __init__(self, cd, fmt, ncap_max, max_fields=96, np_dtype=np.uint8, nbytes_max=None, pcm=False):
         self.cd, self.fmt, self.max_fields = cd, fmt, max_fields
+        self.want_pcm = bool(pcm) and bool(cd.rf.decode_analog_audio)
+        self.pcm_state = (0.0, 2)           # (audio_offset, frame_state) carried from chunk to chunk
+        self.h_pcm = [None, None]
         rf = cd.rf
         be = self.be = rf._be
         self.up, self.down = be.new_stream(), be.new_stream()
@@ -257,6 +267,12 @@ class HostStreamDecoder:
             raise ValueError("max_fields too small")
         dev = None
         res.audio_host = None
+        pcm_job = None
+        if self.want_pcm and nloc and res.audio is not None and res.pr.audio2_len:
+            d_pcm, off, d_pst, ao, fst = self.cd.pcm_enqueue(res, *self.pcm_state)
+            self.pcm_state = (ao, fst)
+            pcm_job = (d_pcm, off, d_pst)
+        res._pcm_off = None
         if nloc or res.audio is not None:
             done = be.record_event()
             be.stream_wait_event(self.down, done)
@@ -273,6 +289,14 @@ class HostStreamDecoder:
                     be.copy_async(self.h_audio[j][0][:na], al)
                     be.copy_async(self.h_audio[j][1][:na], ar)
                     res.audio_host = (be.host_view(self.h_audio[j][0])[:na], be.host_view(self.h_audio[j][1])[:na])
+                if pcm_job is not None:
+                    d_pcm, off, d_pst = pcm_job
+                    if self.h_pcm[j] is None:
+                        self.h_pcm[j] = (be.pinned(len(d_pcm), np.int16), be.pinned(self.max_fields, np.int32))
+                    npcm = max(off[-1], 1)
+                    be.copy_async(self.h_pcm[j][0][:npcm], d_pcm[:npcm])
+                    be.copy_async(self.h_pcm[j][1][:nloc], d_pst)
+                    res._pcm_off = off
                 dev = be.record_event()
             # the slot's picture buffer is rewritten by its next finish(): order that behind this download
             res.slot.pic_free = dev
@@ -286,6 +310,9 @@ class HostStreamDecoder:
         if dev is not None:
             self.be.wait_event(dev)
         res.status_host = self.be.host_view(self.h_status[j])[:nloc]
+        res.pcm_host = [] if self.want_pcm else None
+        if res._pcm_off is not None:
+            res.pcm_host = split_pcm(self.be.host_view(self.h_pcm[j][0]), res._pcm_off, self.be.host_view(self.h_pcm[j][1]))
         return res, self.be.host_view(self.h_out[j])[:nloc * self.out_stride].reshape(nloc, self.out_stride)
 
     def run(self, chunks):
@@ -323,9 +350,11 @@ class FileStreamDecoder:
 
         for res, pics in FileStreamDecoder(cd, "side1.lds"):          # pics: uint16 [nfields, out_stride] host view
             for k, j in enumerate(res.located): write(pics[k, :res.infos[j].linecount * outlinelen])
-    """
 
-    def __init__(self, cd, path, fmt=None, chunk_samples=None, first_sample=0, nsamples=None, max_fields=None):
+    pcm=True (analog audio on): res.pcm_host holds the int16 L/R PCM of every field (None: a field ahead of the first
+    frame), chained over the whole file as Framer.readframe chains it -- what lddecode.py:98 writes to the .pcm file."""
+
+    def __init__(self, cd, path, fmt=None, chunk_samples=None, first_sample=0, nsamples=None, max_fields=None, pcm=False):
         import os as _os
         self.cd, self.path = cd, path
         self.fmt = FORMAT_OF_SUFFIX[_os.path.splitext(path)[1].lower()] if fmt is None else fmt
@@ -353,7 +382,7 @@ class FileStreamDecoder:
         fields = max_fields or int(self.chunk / cd.field_samples) + 8
         elem = np.dtype(self.np_dtype).itemsize
         self.nelem_max = -(-span // self.group) * self.bpg // elem + 16
-        self.sd = HostStreamDecoder(cd, self.fmt, span, fields, np_dtype=self.np_dtype, nbytes_max=self.nelem_max)
+        self.sd = HostStreamDecoder(cd, self.fmt, span, fields, np_dtype=self.np_dtype, nbytes_max=self.nelem_max, pcm=pcm)
         self.be = rf._be
         self.nbuf = 4
         self.bufs = [self.be.pinned(self.nelem_max, self.np_dtype) for _ in range(self.nbuf)]
@@ -720,6 +749,32 @@ class CaptureDecoder:
         return res, slot.d_pic[:res.nframes * fstride].reshape(-1, fstride)
 
     # -- 48 kHz PCM of a range (SURVEY section 8f-1 in pipeline mode)
+    def pcm_enqueue(self, res, audio_offset=0.0, frame_state=2, chain='framer', freq=48000.0, scale=64):
+        """Asynchronous part of pcm(): enqueues ldd_pipe_pcm for `res` on the current stream.  Returns
+        (device int16 buffer, offsets [nlocated + 1] into it, device status [nlocated], audio_offset, frame_state)."""
+        res._live()
+        slot, rf = res.slot, res.slot.rf
+        be = rf._be
+        n = len(res.located)
+        if n == 0:
+            return None, [0], None, audio_offset, frame_state
+        if res.audio is None or not res.pr.audio2_len:
+            raise ValueError("pcm() needs a range decoded with the analog audio and its second stage on")
+        SP = rf.SysParams
+        per_field = int((SP['line_period'] * (SP['frame_lines'] // 2 + 1) / 1e6) * freq) + 4
+        cap = 2 * per_field * slot.max_fields
+        if getattr(slot, 'd_pcm', None) is None or len(slot.d_pcm) < cap:
+            slot.d_pcm = be.empty(cap, np.int16)
+            slot.d_pcm_status = be.zeros(slot.max_fields, np.int32)
+        off = (C.c_longlong * (n + 1))()
+        ao, fs = C.c_double(float(audio_offset)), C.c_int(int(frame_state))
+        be.fill_zero(slot.d_pcm_status[:n])
+        rf._check(be.lib.ldd_pipe_pcm(slot.h, float(freq), float(scale), float(SP['line_period']), float(SP['audio_lfreq']),
+                                      float(SP['audio_rfreq']), _lib.PCM_CHAIN_FRAMER if chain == 'framer' else _lib.PCM_CHAIN_FIELDS,
+                                      C.byref(ao), C.byref(fs), be.ptr(slot.d_pcm), cap, off, be.ptr(slot.d_pcm_status),
+                                      be.stream()))
+        return slot.d_pcm, [int(x) for x in off], slot.d_pcm_status[:n], ao.value, fs.value
+
     def pcm(self, res, audio_offset=0.0, frame_state=2, chain='framer', freq=48000.0, scale=64):
         """int16 L/R PCM of the located fields of `res` (the latest result of its workspace, decoded with the analog
         audio on): downscale_audio (lddecode_core.py:431-484) per field on the final line positions, on the device, from
@@ -728,31 +783,12 @@ class CaptureDecoder:
         dropped while bit 1 of frame_state is set); chain='fields': every field continues the previous one.
         Returns (list of int16 arrays | None for a dropped or flagged field, audio_offset, frame_state) -- pass the two
         state values to the next range of the same capture."""
-        res._live()
-        slot, rf = res.slot, res.slot.rf
-        be = rf._be
-        n = len(res.located)
-        if n == 0:
+        be = res.slot.rf._be
+        d_pcm, off, d_st, audio_offset, frame_state = self.pcm_enqueue(res, audio_offset, frame_state, chain, freq, scale)
+        if d_pcm is None:
             return [], audio_offset, frame_state
-        SP = rf.SysParams
-        per_field = int((SP['line_period'] * (SP['frame_lines'] // 2 + 1) / 1e6) * freq) + 4
-        cap = 2 * per_field * n
-        if getattr(slot, 'd_pcm', None) is None or len(slot.d_pcm) < cap:
-            slot.d_pcm = be.empty(cap, np.int16)
-        st = be.zeros(n, np.int32)
-        off = (C.c_longlong * (n + 1))()
-        ao, fs = C.c_double(float(audio_offset)), C.c_int(int(frame_state))
-        rf._check(be.lib.ldd_pipe_pcm(slot.h, float(freq), float(scale), float(SP['line_period']), float(SP['audio_lfreq']),
-                                      float(SP['audio_rfreq']), _lib.PCM_CHAIN_FRAMER if chain == 'framer' else _lib.PCM_CHAIN_FIELDS,
-                                      C.byref(ao), C.byref(fs), be.ptr(slot.d_pcm), cap, off, be.ptr(st), be.stream()))
         be.synchronize()
-        pcm = be.to_host(slot.d_pcm[:max(int(off[n]), 1)])
-        bad = be.to_host(st)
-        out = []
-        for k in range(n):
-            a, b = int(off[k]), int(off[k + 1])
-            out.append(pcm[a:b].copy() if b > a and not (bad[k] & 16) else None)
-        return out, ao.value, fs.value
+        return split_pcm(be.to_host(d_pcm[:max(off[-1], 1)]), off, be.to_host(d_st)), audio_offset, frame_state
 
     # -- host copies
     def pictures(self, res):

@@ -224,6 +224,35 @@ def test_file_stream_decoder_equals_whole_decode(backend, tmp_path, fmt):
         assert a[1] == b[1] and np.array_equal(a[2], b[2])
 
 
+def test_file_stream_decoder_pcm(backend, tmp_path):
+    """FileStreamDecoder(pcm=True): the 48 kHz PCM of the file's fields, chained from chunk to chunk as Framer.readframe
+    chains it -- the sample counts, the dropped fields and the final offset of the whole-capture decode; values within the
+    block-edge ripple of the second audio stage (its blocks are anchored per range)."""
+    fs = 8 * 315 / 88
+    n = 2400000
+    s = synth.SynthRF("NTSC", fs, seed=21, bits=10).generate(n)
+    raw, path = synth.pack_lds(s), tmp_path / "cap.lds"
+    raw.tofile(str(path))
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, _backend=backend)
+    cd = pipeline.CaptureDecoder(rf)
+    res = cd.decode(backend.to_device(raw), _lib.FMT_LDS40, n)
+    want, want_off, want_state = cd.pcm(res)
+    assert len(want) >= 3 and sum(w is not None for w in want) >= 3
+    fsd = pipeline.FileStreamDecoder(cd, str(path), chunk_samples=700000, pcm=True)
+    got = []
+    for r, pics in fsd:
+        assert not np.any(r.status_host & 15)
+        got += [None if p is None else p.copy() for p in r.pcm_host]
+    assert fsd.sd.pcm_state == (want_off, want_state)
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert len(a) == len(b)
+            d = np.abs(a.astype(np.int64) - b.astype(np.int64))
+            assert d.max() <= 32 and d.mean() <= 1.5
+
+
 def test_two_rank_gloo_gather():
     """world_size 2 over gloo on the CPU (emulated kernels): shard, decode, gather on rank 0."""
     script = os.path.join(ROOT, "tests", "dist_worker.py")

@@ -57,6 +57,39 @@ def test_pipeline_matches_reference_flow(backend, system, precision):
         assert np.abs(d).max() <= 1 and np.count_nonzero(d) <= frac * d.size
 
 
+@pytest.mark.parametrize("system", ["NTSC", "PAL"])
+def test_pipeline_at_40_msps_from_packed_lds(backend, system):
+    """The reference's default sample rate (RFDecode(inputfreq=40), lddecode_core.py:120) and the native rate of the
+    Domesday Duplicator's packed .lds format (lddutils.py:190-229): line length, filter tables, audio decimation (64) and
+    every staging window differ from the 8fsc cases.  Whole chain in the default lane from packed bytes, both audio
+    channels on, against the oracle walk: read positions, peak counts and integer line tables equal, TBC +-1 LSB,
+    PCM of the first window +-1 LSB."""
+    fs = 40.0
+    ncap = int(fs * 1e6 / (30 if system == "NTSC" else 25) * 1.65) // 4 * 4
+    s10 = synth.SynthRF(system, fs, seed=5, bits=10).generate(ncap)
+    rf = rfdecode.RFDecode(fs, system, 16384, _backend=backend)
+    cd = pipeline.CaptureDecoder(rf)
+    res = cd.decode(backend.to_device(synth.pack_lds(s10)), _lib.FMT_LDS40, ncap)
+    pics = cd.pictures(res)
+    dec = O.Decoder(fs, system, 16384, analog_audio=True)
+    ref = _oracle_walk(dec, s10)
+    assert res.nwindows == len(ref) >= 2 and len(res.located) == len(ref)
+    for k, (readsample, f) in enumerate(ref):
+        info = res.infos[k]
+        assert int(res.readsamples[k]) == readsample and f.valid and info.stage == _lib.FIELD_LOCATED
+        assert info.nextfieldoffset == f.nextfieldoffset and info.npeaks == len(f.peaklist)
+        nll = f.linecount + 4
+        np.testing.assert_array_equal(res.linelocs1[k][:nll], np.array(f.linelocs1))
+        np.testing.assert_allclose(res.refined.final[k][:nll] + res.refined.lineloc_add, f.linelocs, rtol=0, atol=2e-3)
+        d = pics[k][2].astype(np.int64) - f.dspicture.astype(np.int64)
+        assert np.abs(d).max() <= 1
+    assert not np.any(res.refined.status)
+    pcm, _, _ = cd.pcm(res, chain='fields')
+    ld = lambda a, n: s10[a:a + n] if a + n <= ncap else None
+    want, _ = O.downscale_audio(dec, O.demod(dec, ld, 0, 1000000, 1)[1], ref[0][1].linelocs, ref[0][1].linecount, 0.0)
+    assert len(pcm[0]) == len(want) and np.abs(pcm[0].astype(np.int64) - want.astype(np.int64)).max() <= 1
+
+
 @pytest.mark.parametrize("system,nranges", [("NTSC", 2), ("PAL", 1)])
 def test_pipeline_pcm_against_framer_audio(backend, system, nranges):
     """48 kHz PCM of a range (ldd_pipe_pcm) against the reference's per-field PCM chained as Framer.readframe chains it

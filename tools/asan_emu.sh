@@ -30,5 +30,15 @@ for name in ('ntsc', 'pal'):
         print(name, prec, 'valid', f.valid)
     res = pipeline.CaptureDecoder(rf, max_fields=16).decode(be.to_device(cap), 0, len(cap))
     print(name, 'pipeline windows', res.nwindows)
+# the reference's default rate from packed .lds bytes, both audio channels, range PCM (longest lines, other staging windows)
+from lddecode_b200 import synth
+for system in ('NTSC', 'PAL'):
+    n = int(40e6 / (30 if system == 'NTSC' else 25) * 1.1) // 4 * 4
+    s10 = synth.SynthRF(system, 40.0, seed=5, bits=10).generate(n)
+    rf = rfdecode.RFDecode(40.0, system, 16384, _backend=be)
+    cd = pipeline.CaptureDecoder(rf, max_fields=16)
+    res = cd.decode(be.to_device(synth.pack_lds(s10)), _lib.FMT_LDS40, n)
+    pcm, _, _ = cd.pcm(res, chain='fields')
+    print(system, '40 MSPS .lds: located', len(res.located), 'pcm', [None if p is None else len(p) for p in pcm])
 print('ASAN_CLEAN')
 PY

@@ -263,6 +263,13 @@ int ldd_field_locate(ldd_handle* h, const long long* peaks, const double* vals, 
                      long long window_len, long long start, ldd_field* out,
                      double* linelocs1, unsigned char* linebad, int ll_cap);
 
+/* HOST function: Field.determine_field(peaknum) (lddecode_core.py:544-588) on its own, for callers that step through the
+ * reference's methods one by one: *line0 = peak index of the last regular hsync before peaknum (-1: None, also for
+ * peaknum < 11 where the reference returns None), *vote = the parity vote.  med_hsync / hsync_tolerance as returned by
+ * ldd_field_locate (Field.get_hsync_median). */
+int ldd_field_vote(ldd_handle* h, const long long* peaks, const double* vals, int npeaks, long long window_len,
+                   double med_hsync, double hsync_tolerance, int peaknum, int* line0, int* vote);
+
 /* HOST function: the field-to-field walk of Framer.readfield (lddecode_core.py:1194-1223) over planes
  * that were demodulated on one block grid (ldd_demod_blocks with first_sample = plane_origin, so that
  * plane index k <-> capture sample plane_origin + blockcut + k).  gpeaks/gvals: the peak list of

@@ -796,6 +796,33 @@ struct Locator {
         if (pk[k] > wlen) return false;
         return val[k] >= med - tol && val[k] <= med + tol;
     }
+
+    // determine_field (lddecode_core.py:544-588) for peaknum >= 11: the last regular hsync before the vertical interval and
+    // the parity vote from the line gaps either side of it.  False when no regular hsync precedes it (line0 is None: the
+    // reference's caller skips such a candidate).
+    bool field_vote(int i, long long* line0_out, int* vote_out) const {
+        int vote = 0;
+        long long line0 = -1;
+        bool have0 = false;
+        for (int k = i - 1; k > i - 20; --k) {
+            if (regular(k)) {
+                line0 = k; have0 = true;
+                long long kk = k < 0 ? k + np : k;
+                if (kk + 1 < np && (pk[kk + 1] - pk[kk]) > linelen * .75) vote -= 1;
+                break;
+            }
+        }
+        for (int k = i; k < i + 20; ++k) {
+            if (regular(k)) {
+                if (k >= 1 && (pk[k] - pk[k - 1]) > linelen * .75) vote += pal ? -1 : 1;
+                break;
+            }
+        }
+        if (pal) vote += 1;
+        *line0_out = line0;
+        *vote_out = vote;
+        return have0;
+    }
 };
 
 }  // namespace
@@ -837,22 +864,7 @@ extern "C" int ldd_field_locate(ldd_handle* h, const long long* peaks, const dou
                 if (i < 11) { out->stage = LDD_FIELD_CRASH; return LDD_OK; }      // the reference raises TypeError here
                 int vote = 0;
                 long long line0 = -1;
-                bool have0 = false;
-                for (int k = i - 1; k > i - 20; --k) {
-                    if (lc.regular(k)) {
-                        line0 = k; have0 = true;
-                        long long kk = k < 0 ? k + npeaks : k;
-                        if (kk + 1 < npeaks && (peaks[kk + 1] - peaks[kk]) > L * .75) vote -= 1;
-                        break;
-                    }
-                }
-                for (int k = i; k < i + 20; ++k) {
-                    if (lc.regular(k)) {
-                        if (k >= 1 && (peaks[k] - peaks[k - 1]) > L * .75) vote += lc.pal ? -1 : 1;
-                        break;
-                    }
-                }
-                if (lc.pal) vote += 1;
+                const bool have0 = lc.field_vote(i, &line0, &vote);
                 if (have0) vs.push_back({(long long)i, line0, (long long)vote});
             }
             prev = v;
@@ -976,6 +988,19 @@ extern "C" int ldd_field_locate(ldd_handle* h, const long long* peaks, const dou
     }
     for (int i = 0; i < 10 && i < nll; ++i) linebad[i] = 0;
     out->stage = LDD_FIELD_LOCATED;
+    return LDD_OK;
+}
+
+extern "C" int ldd_field_vote(ldd_handle* h, const long long* peaks, const double* vals, int npeaks, long long window_len,
+                              double med_hsync, double hsync_tolerance, int peaknum, int* line0, int* vote) {
+    if (!h || !peaks || !vals || !line0 || !vote || npeaks < 0) return LDD_EINVAL;
+    *line0 = -1; *vote = 0;
+    if (peaknum < 11) return LDD_OK;                  // the reference returns None
+    Locator lc{peaks, vals, npeaks, window_len, h->cfg.linelen, h->cfg.system == LDD_SYSTEM_PAL};
+    lc.med = med_hsync; lc.tol = hsync_tolerance;
+    long long l0 = -1;
+    lc.field_vote(peaknum, &l0, vote);
+    *line0 = (int)l0;
     return LDD_OK;
 }
 

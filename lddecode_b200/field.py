@@ -337,9 +337,10 @@ class Field:
         if info.stage == _lib.FIELD_CRASH:
             raise TypeError("cannot unpack non-iterable NoneType object")      # what the reference does here
         self.nextfieldoffset = int(info.nextfieldoffset)
+        if len(self.peaklist) >= 200:          # determine_vsyncs calls get_hsync_median from there on (lddecode_core.py:595-598)
+            self.med_hsync, self.hsync_tolerance = info.med_hsync, info.hsync_tolerance
         if info.stage in (_lib.FIELD_NOVSYNC, _lib.FIELD_SHORT):
             return
-        self.med_hsync, self.hsync_tolerance = info.med_hsync, info.hsync_tolerance
         self.istop = info.istop
         self.linecount = info.linecount
         if info.stage == _lib.FIELD_BADLINES:
@@ -430,6 +431,77 @@ class Field:
         pk, vl = sync_peaks_device(self.rf, self._planes['demod_sync'], self._n, self.start)
         return (list(pk), vl) if with_values else list(pk)
 
+    # -- the reference's per-step methods (lddecode_core.py:518-787, 814-884), for callers that walk through a field by
+    # hand as the reference's notebooks do.  Each one re-runs its step through the library on this field's data.
+    def _locate(self):
+        return locate(self.rf, self.peaklist, self._peakvals, self._n, self.start)
+
+    def get_hsync_median(self):
+        info, _, _ = self._locate()
+        self.med_hsync, self.hsync_tolerance = info.med_hsync, info.hsync_tolerance
+        return self.med_hsync, self.hsync_tolerance
+
+    def is_regular_hsync(self, peaknum):
+        if peaknum >= len(self.peaklist) or self.peaklist[peaknum] > self._n:
+            return False
+        return bool(self.med_hsync - self.hsync_tolerance <= self._peakvals[peaknum] <= self.med_hsync + self.hsync_tolerance)
+
+    def determine_field(self, peaknum):
+        if peaknum < 11:
+            return None
+        pk = np.ascontiguousarray(self.peaklist, dtype=np.int64)
+        vl = np.ascontiguousarray(self._peakvals, dtype=np.float64)
+        line0, vote = C.c_int(-1), C.c_int(0)
+        self.rf._check(self.rf._be.lib.ldd_field_vote(self.rf._h, _h(pk), _h(vl), len(pk), int(self._n), float(self.med_hsync),
+                                                      float(self.hsync_tolerance), int(peaknum), C.byref(line0), C.byref(vote)))
+        return (line0.value if line0.value >= 0 else None), vote.value
+
+    def determine_vsyncs(self):
+        info, _, _ = self._locate()
+        if len(self.peaklist) >= 200:
+            self.med_hsync, self.hsync_tolerance = info.med_hsync, info.hsync_tolerance
+        return [(info.vsyncs[i][0], info.vsyncs[i][1], bool(info.vsyncs[i][2])) for i in range(min(info.nvsyncs, 4))]
+
+    def compute_linelocs(self):
+        info, ll1, bad = self._locate()
+        if info.stage != _lib.FIELD_LOCATED:
+            raise ValueError("compute_linelocs: the field's line grid cannot be built (stage %d)" % info.stage)
+        nll = info.linecount + 4
+        return list(ll1[:nll]), [bool(x) for x in bad[:nll]]
+
+    def refine_linelocs_hsync(self):
+        """lddecode_core.py:715-787 on self.linelocs1 / self.linebad; like the reference it updates self.linebad."""
+        nll = self.linecount + 4
+        batch = FieldBatch(self.rf, 1)
+        batch.linecount[0], batch.winlen[0] = self.linecount, self._n
+        batch.linelocs1[0][:nll] = self.linelocs1
+        batch.linebad[0][:nll] = np.asarray(self.linebad, dtype=np.uint8)
+        ref = self._refine_hsync_only(batch)
+        self.linebad = [bool(x) for x in ref.linebad[0][:nll]]
+        return list(ref.linelocs2[0][:nll])
+
+    def decodephillipscode(self, linenum):
+        """lddecode_core.py:814-834 for any line of self.linelocs: list of six nibbles or None."""
+        rf, be = self.rf, self.rf._be
+        ll = np.zeros(LL_STRIDE, dtype=np.float64)
+        ll[:len(self.linelocs)] = self.linelocs
+        d_codes = be.empty(4, np.int32)
+        arr = (C.c_int * 1)(int(linenum))
+        rf._check(be.lib.ldd_vbi_decode(rf._h, be.ptr(self._planes['demod']), int(self._n), None, None, be.ptr(be.to_device(ll)),
+                                        LL_STRIDE, 1, arr, 1, be.ptr(d_codes), be.stream()))
+        be.synchronize()
+        return code_nibbles(be.to_host(d_codes)[0])
+
+    def processphilipscode(self):
+        self.vbi = process_philips(self.rf, self.linecode)
+
+    def _line_tables_device(self, lineinfo):
+        be = self.rf._be
+        ll = np.zeros(LL_STRIDE, dtype=np.float64)
+        ll[:len(lineinfo)] = lineinfo
+        return (be.to_device(ll), be.to_device(np.zeros(1, dtype=np.int64)), be.to_device(np.array([self.linecount], dtype=np.int32)),
+                be.zeros(1, np.int32))
+
     def downscale(self, lineoffset=1, lineinfo=None, outwidth=None, wow=True, channel='demod', audio=False):
         """Field.downscale (lddecode_core.py:789-812): float64 Hz, linecount * outwidth samples."""
         rf, be = self.rf, self.rf._be
@@ -494,9 +566,36 @@ class FieldNTSC(Field):
     def apply_offsets(self, linelocs, phaseoffset, picoffset=0):
         return np.array(linelocs) + picoffset + (phaseoffset * (self.rf.freq / (4 * 315 / 88)))
 
+    def refine_linelocs_burst(self, linelocs2):
+        """lddecode_core.py:1054-1133: one burst-phase pass over the given line table -> (linelocs, burstlevel)."""
+        rf, be = self.rf, self.rf._be
+        nll = self.linecount + 4
+        d_ll, d_base, d_lc, d_st = self._line_tables_device(linelocs2)
+        d_out, d_bl = be.empty(LL_STRIDE, np.float64), be.zeros(LL_STRIDE, np.float32)
+        rf._check(be.lib.ldd_refine_burst(rf._h, be.ptr(self._planes['demod_burst']), int(self._n), be.ptr(d_base), be.ptr(d_lc),
+                                          1, LL_STRIDE, be.ptr(d_ll), be.ptr(d_out), be.ptr(d_bl), be.ptr(d_st), be.stream()))
+        be.synchronize()
+        if be.to_host(d_st)[0] & (1 | 4):
+            raise IndexError("refine_linelocs_burst: a burst window lies outside the decoded data")
+        return be.to_host(d_out)[:nll].copy(), be.to_host(d_bl)[:nll].copy()
+
 
 class FieldPAL(Field):
     full = True
+
+    def refine_linelocs_pilot(self, linelocs=None):
+        """lddecode_core.py:962-1021: pilot-phase alignment of a line table (default: self.linelocs2)."""
+        rf, be = self.rf, self.rf._be
+        nll = self.linecount + 4
+        d_ll, d_base, d_lc, d_st = self._line_tables_device(self.linelocs2 if linelocs is None else linelocs)
+        d_out = be.empty(LL_STRIDE, np.float64)
+        rf._check(be.lib.ldd_refine_pilot(rf._h, be.ptr(self._planes['demod']), be.ptr(self._planes['demod_05']), int(self._n),
+                                          be.ptr(d_base), be.ptr(d_lc), 1, LL_STRIDE, be.ptr(d_ll), be.ptr(d_out), be.ptr(d_st),
+                                          be.stream()))
+        be.synchronize()
+        if be.to_host(d_st)[0] & (1 | 8):
+            raise IndexError("refine_linelocs_pilot: a pilot window lies outside the decoded data")
+        return be.to_host(d_out)[:nll].copy()
 
     def downscale(self, final=False, *args, **kwargs):
         """FieldPAL.downscale (lddecode_core.py:1023-1035): lineoffset 3; final=True returns the constructor's picture."""

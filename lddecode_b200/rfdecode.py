@@ -66,6 +66,13 @@ _REL_IRE0 = ('demod', 'demod_05')      # planes the library stores relative to i
 _FMT_OF_DTYPE = {np.dtype('uint8'): _lib.FMT_U8, np.dtype('int16'): _lib.FMT_S16, np.dtype('uint16'): _lib.FMT_U16}
 
 
+def calclinelen(SP, mult, mhz):
+    """lddecode_core.py:23-27."""
+    if type(mhz) == str:
+        mhz = SP[mhz]
+    return int(np.round(SP['line_period'] * mhz * mult))
+
+
 def filtfft(filt, blocklen):
     """Frequency response of a (b, a) filter on `blocklen` points of the unit circle (lddutils.py:256-257)."""
     return sps.freqz(filt[0], filt[1], blocklen, whole=1)[1]
@@ -409,6 +416,19 @@ class RFDecode:
         rng.total_out = N
         audio = None if al is None else {'audio_left': al, 'audio_right': ar}
         return DeviceDemod(self, planes, audio, rng).to_recarrays()
+
+    def runfilter_audio_phase2(self, frame_audio, start):
+        """RFDecode.runfilter_audio_phase2 (lddecode_core.py:335-346): ONE block of the second audio stage, blocklen
+        phase-1 samples from `start` -> blocklen/4 samples, nothing cut.  (ldd_audio_phase2 over blocklen + 1 samples is
+        exactly that block: the first block is kept whole and the re-anchored last block is the same block.)"""
+        N = self.blocklen
+        n = len(frame_audio['audio_left'])
+        if start < 0 or start + N > n:
+            raise ValueError("runfilter_audio_phase2: the block leaves the array (the reference raises on the shape mismatch)")
+        pad = lambda ch: np.concatenate([np.asarray(frame_audio[ch][start:start + N], dtype=np.float64), [0.0]])
+        out = self._audio_phase2_device(self._be.to_device(pad('audio_left')), self._be.to_device(pad('audio_right')), N + 1)
+        return np.rec.array([self._be.to_host(out['audio_left']), self._be.to_host(out['audio_right'])],
+                            names=['audio_left', 'audio_right'])
 
     def audio_phase2(self, field_audio):
         """RFDecode.audio_phase2 (lddecode_core.py:348-371) on a host record array."""

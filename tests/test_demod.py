@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from lddecode_b200 import rfdecode, synth
+from lddecode_b200 import _lib, rfdecode, synth
 from oracle import ldd_oracle as O
 
 RTOL_HZ = 1e-7
@@ -75,6 +75,29 @@ def test_demod_stitched_golden(backend, golden, name):
     np.testing.assert_allclose(a2["audio_left"], g["demod2_audio_left"], rtol=1e-9)
     # short read -> None, like the reference (lddecode_core.py:386-392)
     assert rf.demod(None, len(cap) - 5000, 100000, 0) is None
+
+
+def test_runfilter_audio_phase2_one_block(backend, golden):
+    """RFDecode.runfilter_audio_phase2 (lddecode_core.py:335-346): one block of the second audio stage.  Block 0 is the head
+    of the reference's own audio_phase2 output (it keeps the first block whole, :353-355); any other start against the
+    oracle's restatement of the same lines."""
+    g = golden("ntsc")
+    N = int(g["blocklen"])
+    rf = rfdecode.RFDecode(float(g["fs_mhz"]), "NTSC", N, _backend=backend, precision="f64")
+    cap = g["capture"]
+    a1 = rf.demod_device(backend.to_device(cap), _lib.FMT_U8, 0, len(cap), 0, int(g["demod_length"]), 1, phase2=False).audio_recarray()
+    out = rf.runfilter_audio_phase2(a1, 0)
+    assert len(out) == N // 4
+    np.testing.assert_allclose(out["audio_left"], g["audio_left"][:N // 4], rtol=1e-9)
+    np.testing.assert_allclose(out["audio_right"], g["audio_right"][:N // 4], rtol=1e-9)
+    dec = O.Decoder(float(g["fs_mhz"]), "NTSC", N)
+    want = O._audio2_block(dec, a1, 5001)
+    out = rf.runfilter_audio_phase2(a1, 5001)
+    np.testing.assert_allclose(out["audio_left"], want["audio_left"], rtol=1e-9)
+    np.testing.assert_allclose(out["audio_right"], want["audio_right"], rtol=1e-9)
+    with pytest.raises(ValueError):
+        rf.runfilter_audio_phase2(a1, len(a1) - N + 1)
+    assert rfdecode.calclinelen(rf.SysParams, 4, 'fsc_mhz') == rf.SysParams['outlinelen'] == 910
 
 
 def test_sync_decisions_bit_exact_vs_oracle(backend):

@@ -50,6 +50,53 @@ def test_field_golden(backend, golden, name):
 
 
 @pytest.mark.parametrize("name", ["ntsc", "pal"])
+def test_reference_step_methods(backend, golden, name):
+    """The reference's per-step methods on the drop-in classes (get_hsync_median, is_regular_hsync, determine_field,
+    determine_vsyncs, compute_linelocs, refine_linelocs_hsync, decodephillipscode, processphilipscode,
+    refine_linelocs_burst | refine_linelocs_pilot; lddecode_core.py:518-787, 814-884, 962-1021, 1054-1133), called one
+    by one the way the reference's constructors chain them, against the vectors recorded from the reference."""
+    g = golden(name)
+    rf, dd, system = _setup(backend, g, name)
+    f = (field.FieldNTSC if system == "NTSC" else field.FieldPAL)(rf, dd, 0)
+    med, tol = f.get_hsync_median()
+    np.testing.assert_allclose(med, g["field_med_hsync"], rtol=1e-12)
+    np.testing.assert_allclose(tol, g["field_hsync_tolerance"], rtol=1e-9)
+    vs = f.determine_vsyncs()
+    assert [list(map(int, v)) for v in vs] == [list(v) for v in g["field_vsyncs"]]
+    # determine_field / is_regular_hsync against the oracle's restatement on every candidate around the first interval
+    dec = O.Decoder(float(g["fs_mhz"]), system, int(g["blocklen"]))
+    ds = np.zeros(f._n)
+    ds[np.array(f.peaklist)] = f._peakvals
+    for k in list(range(0, 14)) + list(range(vs[0][0] - 12, vs[0][0] + 12)) + [len(f.peaklist) - 1, len(f.peaklist) + 3]:
+        assert f.is_regular_hsync(k) == O._regular(ds, f.peaklist, k, med, tol)
+        if k < len(f.peaklist) - 20:
+            assert f.determine_field(k) == O._field_vote(dec, ds, f.peaklist, k, med, tol)
+    ll1, bad = f.compute_linelocs()
+    np.testing.assert_array_equal(np.array(ll1), g["field_linelocs1"])
+    f.linelocs1, f.linebad = ll1, bad
+    ll2 = f.refine_linelocs_hsync()
+    np.testing.assert_allclose(ll2, g["field_linelocs2"], rtol=0, atol=1e-5)
+    assert np.array_equal(np.array(f.linebad, dtype=np.int8), g["field_linebad"])
+    f.linelocs = ll2
+    codes = [f.decodephillipscode(l) for l in rf.SysParams["philips_codelines"]]
+    assert np.array_equal(np.array([[-1] * 6 if c is None else c for c in codes]), g["field_linecode"])
+    assert f.decodephillipscode(100) is None                                         # a picture line carries no code
+    f.linecode = dict(zip(rf.SysParams["philips_codelines"], codes))
+    f.processphilipscode()
+    assert f.vbi["framenr"] == int(g["field_framenr"])
+    if system == "NTSC":
+        ll3, bl = f.refine_linelocs_burst(ll2)
+        np.testing.assert_allclose(ll3, g["field_linelocs3"], rtol=0, atol=1e-5)
+        ll4, bl = f.refine_linelocs_burst(ll3)
+        np.testing.assert_allclose(ll4, g["field_linelocs4"], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(bl, g["field_burstlevel"], rtol=3e-7, atol=0)
+        np.testing.assert_allclose(f.apply_offsets(ll4, 91.5 * (np.pi / 180) - 8), g["field_linelocs"], rtol=0, atol=1e-5)
+    else:
+        np.testing.assert_allclose(f.refine_linelocs_pilot(), g["field_linelocs"], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(f.refine_linelocs_pilot(ll2), g["field_linelocs"], rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["ntsc", "pal"])
 def test_downscale_float_matches_scale(backend, golden, name):
     """Field.downscale in float64 mode equals the reference's lddutils.scale per line."""
     g = golden(name)

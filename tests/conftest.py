@@ -11,8 +11,33 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_xdist_auto_num_workers(config):
+    """Worker processes for `-n auto` (pytest.ini): none on a GPU box, a handful for the CPU-only suite."""
+    env = os.environ.get("LDD_TEST_WORKERS")
+    if env is not None:
+        return max(int(env), 0)
+    if _have_gpu():
+        return 0
+    return max(1, min(6, (os.cpu_count() or 2) - 1))
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    if not hasattr(config, "workerinput") and not _have_gpu():
+        # the controller builds the emulated library once, before the workers (which would race for its object files) start
+        try:
+            from emu_util import emu_backend
+            emu_backend()
+        except Exception:
+            pass
 
 
 @pytest.fixture(scope="session")

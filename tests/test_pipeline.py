@@ -139,6 +139,27 @@ def test_pipeline_pcm_against_framer_audio(backend, system, nranges):
     assert offset == t
 
 
+def test_empty_and_ragged_captures(backend):
+    """Captures that are empty, shorter than a block, end off the block grid or are a sample short of the first read
+    (Framer.readfield returns None when RFDecode.demod does, lddecode_core.py:386-392, 1199-1201): no window, no crash;
+    the first window appears exactly where the oracle's demod of the first read succeeds."""
+    fs = 8 * 315 / 88
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, _backend=backend)
+    cd = pipeline.CaptureDecoder(rf)
+    cap = synth.SynthRF("NTSC", fs, seed=3).generate(1100000)
+    dec = O.Decoder(fs, "NTSC", 16384, analog_audio=False)
+    stride = 16384 - 1024 - dec.blockcut_end
+    need = (1000001 // stride) * stride + 16384                              # the last block demod(0, 1e6) reads ends here
+    for n in (0, 1, 100, 16383, 16384, 16385, 40001, 999999, 1000001, need - 1, need, need + 1, 1100000):
+        res = cd.decode(backend.to_device(cap[:max(n, 1)]), _lib.FMT_U8, n)
+        want = 1 if n >= need else 0
+        assert res.nwindows == want, n
+        assert len(cd.pictures(res)) == len(res.located) == want
+    for n, ok in ((need - 1, False), (need, True)):
+        ld = lambda s, k: cap[s:s + k] if s + k <= n else None
+        assert (O.demod(dec, ld, 0, 1000000, 1) is not None) == ok
+
+
 def test_ranges_are_bit_identical_to_one_range(backend):
     """Two read-position ranges (what two GPUs or two chunks would do), the second holding only the
     part of the capture it needs, give exactly the fields of the single-range decode."""

@@ -271,8 +271,11 @@ def downscale_audio(audio, lineinfo, rf, linecount, timeoffset=0, freq=48000.0, 
 
     audio: the phase-2 audio of the field's window -- a dict of device buffers (DeviceDemod.audio) or the host record
     array RFDecode.demod returns.  Returns (int16 interleaved L/R samples, time offset to carry into the next field).
-    Like the reference it assumes a total decimation of `scale` (64: the 40 MSPS default)."""
+    Like the reference it assumes a total decimation of `scale` (64: right from 32 MSPS up, twice the true factor at
+    8fsc NTSC, where the reference therefore plays the audio at half speed); scale=None uses the decoder's true factor."""
     be = rf._be
+    if scale is None:
+        scale = rf.audio_decimation
     frametime = (rf.SysParams['line_period'] * linecount) / 1000000
     soundgap = 1 / freq
     arange = np.arange(timeoffset, frametime + soundgap, soundgap, dtype=np.double)

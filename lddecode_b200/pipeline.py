@@ -761,6 +761,8 @@ class CaptureDecoder:
         if res.audio is None or not res.pr.audio2_len:
             raise ValueError("pcm() needs a range decoded with the analog audio and its second stage on")
         SP = rf.SysParams
+        if scale is None:                   # the decoder's true decimation instead of the reference's fixed 64
+            scale = rf.audio_decimation
         per_field = int((SP['line_period'] * (SP['frame_lines'] // 2 + 1) / 1e6) * freq) + 4
         cap = 2 * per_field * slot.max_fields
         if getattr(slot, 'd_pcm', None) is None or len(slot.d_pcm) < cap:
@@ -781,6 +783,7 @@ class CaptureDecoder:
         the range's phase-2 audio (ldd_pipe_pcm).  chain='framer': time offsets as Framer.readframe carries them for CLV
         discs (every field of a frame starts at the offset the frame started with, fields ahead of the first frame are
         dropped while bit 1 of frame_state is set); chain='fields': every field continues the previous one.
+        scale: the reference's `scale` argument (64, whatever the sample rate); None = the decoder's true decimation.
         Returns (list of int16 arrays | None for a dropped or flagged field, audio_offset, frame_state) -- pass the two
         state values to the next range of the same capture."""
         be = res.slot.rf._be

@@ -222,6 +222,13 @@ class RFDecode:
         d75freq = 1000000 / (2 * np.pi * 75)
         SF['audio_deemp2'] = filtfft(sps.butter(1, [d75freq / (SF['freq_aud2'] / 2)], btype='lowpass'), N // 4)
 
+    @property
+    def audio_decimation(self):
+        """RF samples per sample of the phase-2 audio demod() returns: the first stage keeps 2 * blocklen / audio_fdiv1 bins
+        of the block's spectrum (lddecode_core.py:253-259), the second every fourth sample (:271, 343) -- 32 at 8fsc NTSC,
+        64 from 32 MSPS up.  (downscale_audio's scale=64 and Filters['audio_fdiv'] assume the latter.)"""
+        return 4 * (self.blocklen // len(self.Filters['audio_lfilt']))
+
     def iretohz(self, ire):
         return self.SysParams['ire0'] + (self.SysParams['hz_ire'] * ire)
 

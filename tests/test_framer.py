@@ -57,6 +57,45 @@ def test_reference_framer_over_dropin_classes(backend, golden, precision, device
     np.testing.assert_allclose(fr.audio_offset, float(g["audio_offset"]), rtol=0, atol=1e-12)
 
 
+@pytest.mark.skipif(not refshim.available(), reason="needs /root/reference (build container only)")
+def test_reference_findframe_over_dropin_classes(backend, monkeypatch):
+    """Seek: the reference's own findframe (lddecode_core.py:1338-1378: a Framer with
+    full_decode=False, i.e. the base Field class and its VBI decode, read frame by frame) over the drop-in RFDecode /
+    Field returns what the all-reference run returns, and the frame it locks on carries the same frame number and next
+    read position.  (The target is the frame the first read finds: on this synthetic disc both fields of a frame carry
+    the picture number, on which the reference's own CAV pairing rule (:1273-1274) never closes a frame.)"""
+    import contextlib
+    import io
+    from lddecode_b200 import synth
+    core = refshim.load_reference()
+    fs = 8 * 315 / 88
+    spf = int(fs * 1e6 / 29.97)
+    cap = synth.SynthRF("NTSC", fs, seed=11, frame0=100).generate(2 * spf + 1100000)          # CAV: frame numbers on lines 16-18
+    mem = refshim.MemFile(b"")
+    # the reference by itself
+    core.loader = refshim.make_array_loader(cap)
+    ref_rf = core.RFDecode(fs, "NTSC")
+    with contextlib.redirect_stdout(io.StringIO()):
+        fr = core.Framer(ref_rf, full_decode=False)
+        want_rv = fr.readframe(mem, 0, CAV=False)
+        want_nr = fr.vbi["framenr"]
+        want = core.findframe(mem, ref_rf, want_nr)
+    # the reference's findframe / Framer over our classes
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, _backend=backend)
+    rfdecode.loader = _mem_loader(cap)
+    monkeypatch.setattr(core, "FieldNTSC", field.FieldNTSC)
+    monkeypatch.setattr(core, "FieldPAL", field.FieldPAL)
+    monkeypatch.setattr(core, "Field", field.Field)
+    with contextlib.redirect_stdout(io.StringIO()):
+        fr = core.Framer(rf, full_decode=False)
+        assert fr.FieldClass is field.Field
+        got_rv = fr.readframe(mem, 0, CAV=False)
+        got = core.findframe(mem, rf, want_nr)
+    assert want_nr is not None and fr.vbi["framenr"] == want_nr
+    assert got_rv[2] == want_rv[2] and [f.istop for f in got_rv[3]] == [f.istop for f in want_rv[3]]
+    assert got == want and want > 0
+
+
 def test_downscale_audio_golden(backend, golden):
     """Field-level PCM (lddecode_core.py:431-484) on the reference's own line table, host record array and device
     buffers as input."""

@@ -129,6 +129,12 @@ def test_pipeline_pcm_against_framer_audio(backend, system, nranges):
             assert d.max() <= 32 and d.mean() <= 1.5, (k, d.max(), d.mean())
     # every field continuing the previous one: the offsets numpy's arange gives
     res = cd.decode(backend.to_device(cap), _lib.FMT_U8, ncap)
+    # scale=None: the decoder's true audio decimation.  The synthetic left channel is a 1 kHz tone; with the reference's
+    # fixed scale=64 an 8fsc capture (true factor 32) plays at half speed, a 35.5 MSPS one (64) at speed.
+    assert rf.audio_decimation == (32 if system == "NTSC" else 64)
+    tone = lambda p: np.argmax(np.abs(np.fft.rfft(p[0::2].astype(np.float64) * np.hanning(len(p) // 2)))[1:]) + 1
+    k64, ktrue = [(lambda p: tone(p) * 48000.0 * 2 / len(p))(cd.pcm(res, 0.0, 2, chain='fields', scale=sc)[0][1]) for sc in (64, None)]
+    assert abs(ktrue - 1000.0) < 70.0 and abs(k64 - (500.0 if system == "NTSC" else 1000.0)) < 70.0
     pcm, offset, _ = cd.pcm(res, 0.0, 2, chain='fields')
     t = 0.0
     for j, p in zip(res.located, pcm):

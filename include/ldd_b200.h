@@ -462,6 +462,12 @@ int ldd_pipe_finish(ldd_pipe* p, double colorlevel, double colorphase, int frame
  * scale = the reference's `scale` argument (64), freq_hz its `freq` (48000). */
 #define LDD_PCM_CHAIN_FIELDS 0
 #define LDD_PCM_CHAIN_FRAMER 1
+/* HOST function: the offset chain of ldd_pipe_pcm by itself, over the line counts and parities of nfields consecutive
+ * fields -- what a rank of a sharded decode runs over the fields of the ranks before it to learn the state its own range
+ * starts with (audio_next_offset is a prefix over per-field line counts).  nout (may be NULL)
+ * receives the stereo samples every field contributes. */
+int ldd_pcm_chain(int system, double freq_hz, double line_period_us, int chain, int nfields, const int* linecount,
+                  const int* istop, double* audio_offset, int* frame_state, int* nout);
 int ldd_pipe_pcm(ldd_pipe* p, double freq_hz, double scale, double line_period_us, double audio_lfreq, double audio_rfreq,
                  int chain, double* audio_offset, int* frame_state, short* out_dev, long long out_cap, long long* out_off,
                  int* status_dev, void* stream);

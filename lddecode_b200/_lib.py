@@ -148,6 +148,8 @@ SIGNATURES.update({
                                   C.c_void_p, C.c_void_p, C.POINTER(PipeResult)]),
     "ldd_field_vote": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_double, C.c_int,
                                  C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ldd_pcm_chain": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_double),
+                                C.POINTER(C.c_int), C.c_void_p]),
     "ldd_pipe_pcm": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
                                C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p, C.c_longlong, C.POINTER(C.c_longlong),
                                C.c_void_p, C.c_void_p]),

@@ -103,6 +103,39 @@ struct ldd_pipe {
 
 namespace {
 
+// The time-offset chain of the fields' PCM.  One field: np.arange(timeoffset, frametime + soundgap, soundgap) has
+// ceil((stop - start) / step) values start + i * ((start + step) - start); the field produces one sample less and hands on
+// arange[-1] - frametime (lddecode_core.py:432-438, 482).  LDD_PCM_CHAIN_FRAMER is Framer.readframe (:1203, 1260-1289) with
+// the CLV pairing: every field of a call is built with the offset the call started with; a field whose parity is
+// `topfirst` opens the frame, the next one closes it and the closing field's offset is carried on; fields ahead of the
+// very first frame are not written.
+struct PcmChain {
+    double off;
+    bool open, first;
+    // returns the stereo samples the field contributes; *t0 / *t1 = the first two values of its arange
+    int step(int linecount, int istop, int topfirst, double freq_hz, double line_period_us, int chain, double* t0, double* t1) {
+        const double soundgap = 1.0 / freq_hz;
+        const double frametime = (line_period_us * (double)linecount) / 1000000.0;
+        const double stop = frametime + soundgap;
+        const double lenf = std::ceil((stop - off) / soundgap);
+        const long long len = lenf > 0 ? (long long)lenf : 0;
+        const double second = off + soundgap, delta = second - off;
+        const double last = len <= 1 ? off : (len == 2 ? second : off + (double)(len - 1) * delta);
+        const double next = len >= 1 ? last - frametime : off;
+        bool include = true, closes = false;
+        if (chain == LDD_PCM_CHAIN_FRAMER) {
+            if (istop == topfirst) open = true;
+            else if (open) closes = true;
+            include = open || closes || !first;
+        }
+        *t0 = off; *t1 = second;
+        const int nout = include && len > 1 ? (int)(len - 1) : 0;
+        if (chain == LDD_PCM_CHAIN_FIELDS) off = next;
+        else if (closes) { off = next; open = false; first = false; }
+        return nout;
+    }
+};
+
 int pfail(ldd_pipe* p, int code, const char* msg) {
     if (p && p->h) p->h->err = msg;
     return code;
@@ -433,6 +466,23 @@ int ldd_pipe_finish(ldd_pipe* p, double colorlevel, double colorphase, int frame
     return LDD_OK;
 }
 
+int ldd_pcm_chain(int system, double freq_hz, double line_period_us, int chain, int nfields, const int* linecount,
+                  const int* istop, double* audio_offset, int* frame_state, int* nout) {
+    if (!audio_offset || !frame_state || nfields < 0 || (nfields && (!linecount || !istop)) || freq_hz <= 0 || line_period_us <= 0 ||
+        (chain != LDD_PCM_CHAIN_FIELDS && chain != LDD_PCM_CHAIN_FRAMER))
+        return LDD_EINVAL;
+    PcmChain ch{*audio_offset, (*frame_state & 1) != 0, (*frame_state & 2) != 0};
+    const int topfirst = system == LDD_SYSTEM_PAL ? 0 : 1;
+    for (int k = 0; k < nfields; ++k) {
+        double t0, t1;
+        const int n = ch.step(linecount[k], istop[k], topfirst, freq_hz, line_period_us, chain, &t0, &t1);
+        if (nout) nout[k] = n;
+    }
+    *audio_offset = ch.off;
+    *frame_state = (ch.open ? 1 : 0) | (ch.first ? 2 : 0);
+    return LDD_OK;
+}
+
 int ldd_pipe_pcm(ldd_pipe* p, double freq_hz, double scale, double line_period_us, double audio_lfreq, double audio_rfreq,
                  int chain, double* audio_offset, int* frame_state, short* out_dev, long long out_cap, long long* out_off,
                  int* status_dev, void* stream) {
@@ -457,40 +507,21 @@ int ldd_pipe_pcm(ldd_pipe* p, double freq_hz, double scale, double line_period_u
     // plane samples per phase-2 audio sample: the first stage keeps every (N / A)-th, the second every 4th
     const double dec = 4.0 * (double)(c.blocklen / h->A);
     const int topfirst = c.system == LDD_SYSTEM_PAL ? 0 : 1;
-    const double soundgap = 1.0 / freq_hz;
-    double off = *audio_offset;
-    bool open = (*frame_state & 1) != 0, first = (*frame_state & 2) != 0;
+    PcmChain ch{*audio_offset, (*frame_state & 1) != 0, (*frame_state & 2) != 0};
     int maxn = 0;
     for (int k = 0; k < n; ++k) {
         const int w = p->owned[p->located[k]];
         const ldd_field& f = p->fields[w];
-        // np.arange(timeoffset, frametime + soundgap, soundgap): ceil((stop - start) / step) values start + i * ((start +
-        // step) - start); the field produces one sample less and hands on arange[-1] - frametime (lddecode_core.py:432-438, 482)
-        const double frametime = (line_period_us * (double)f.linecount) / 1000000.0;
-        const double stop = frametime + soundgap;
-        const double lenf = std::ceil((stop - off) / soundgap);
-        const long long len = lenf > 0 ? (long long)lenf : 0;
-        const double t1 = off + soundgap, delta = t1 - off;
-        const double last = len <= 1 ? off : (len == 2 ? t1 : off + (double)(len - 1) * delta);
-        const double next = len >= 1 ? last - frametime : off;
-        bool include = true, closes = false;
-        if (chain == LDD_PCM_CHAIN_FRAMER) {
-            // Framer.readframe (lddecode_core.py:1260-1289), CLV pairing: every field of a call is built with the offset
-            // the call started with; a field whose parity is `topfirst` opens the frame, the next one closes it and the
-            // closing field's offset is carried on; fields ahead of the very first frame are not written
-            if (f.istop == topfirst) open = true;
-            else if (open) closes = true;
-            include = open || closes || !first;
-        }
-        ht0[k] = off; ht1[k] = t1;
+        double t0, t1;
+        hn[k] = ch.step(f.linecount, f.istop, topfirst, freq_hz, line_period_us, chain, &t0, &t1);
+        ht0[k] = t0; ht1[k] = t1;
         hfb[k] = (double)p->base[w] / dec;
-        hn[k] = include && len > 1 ? (int)(len - 1) : 0;
         hoff[k] = out_off[k];
         out_off[k + 1] = out_off[k] + 2LL * hn[k];
         maxn = std::max(maxn, hn[k]);
-        if (chain == LDD_PCM_CHAIN_FIELDS) off = next;
-        else if (closes) { off = next; open = false; first = false; }
     }
+    const double off = ch.off;
+    const bool open = ch.open, first = ch.first;
     if (out_off[n] > out_cap) return pfail(p, LDD_ECAP, "PCM buffer too small");
     *audio_offset = off;
     *frame_state = (open ? 1 : 0) | (first ? 2 : 0);

@@ -395,3 +395,44 @@ def gather_fields(cd, res, rank, world, max_fields, dist=None):
     g = FieldGatherer(cd, rank, world, max_fields, dist)
     g.gather(res)
     return g.to_host()
+
+
+def pcm_chain(rf, linecounts, istops, audio_offset=0.0, frame_state=2, chain='framer', freq=48000.0):
+    """ldd_pcm_chain: run the PCM time-offset chain over fields given by (linecount, istop) -> (samples per field,
+    audio_offset, frame_state) after the last of them."""
+    n = len(linecounts)
+    lc = (C.c_int * max(n, 1))(*[int(x) for x in linecounts])
+    tp = (C.c_int * max(n, 1))(*[int(x) for x in istops])
+    nout = (C.c_int * max(n, 1))()
+    ao, fs = C.c_double(float(audio_offset)), C.c_int(int(frame_state))
+    rf._check(rf._be.lib.ldd_pcm_chain(_lib.SYSTEM[rf.system], float(freq),
+                                       float(rf.SysParams['line_period']), _lib.PCM_CHAIN_FRAMER if chain == 'framer' else _lib.PCM_CHAIN_FIELDS,
+                                       n, lc, tp, C.byref(ao), C.byref(fs), nout))
+    return [int(nout[k]) for k in range(n)], ao.value, fs.value
+
+
+def sharded_pcm(cd, res, rank, world, dist, chain='framer', freq=48000.0, scale=64):
+    """48 kHz PCM of a capture sharded over the ranks (one read-position range each, `res` = this rank's decode_range with
+    the analog audio on).  The time offset a field starts with is a prefix over the line counts and parities of all fields
+    before it, so the ranks first exchange those few integers (all_gather_object), every rank
+    runs the chain over the fields of the ranks before it (ldd_pcm_chain, host) and resamples its own fields from its
+    own audio (ldd_pipe_pcm); the samples are then gathered on rank 0.  Returns on rank 0 the list of
+    (readsample, int16 L/R array | None) ordered by read position, None elsewhere."""
+    rf = cd.rf
+    mine = [(int(res.infos[j].linecount), int(res.infos[j].istop)) for j in res.located]
+    every = [None] * world
+    if world > 1:
+        dist.all_gather_object(every, mine)
+    else:
+        every[0] = mine
+    before = [f for r in range(rank) for f in every[r]]
+    _, offset, state = pcm_chain(rf, [f[0] for f in before], [f[1] for f in before], 0.0, 2, chain, freq)
+    pcm, _, _ = cd.pcm(res, offset, state, chain=chain, freq=freq, scale=scale)
+    out = [(int(res.readsamples[j]), p) for j, p in zip(res.located, pcm)]
+    if world == 1:
+        return out
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(out, parts, dst=0)
+    if rank != 0:
+        return None
+    return sorted([x for part in parts for x in part], key=lambda x: x[0])

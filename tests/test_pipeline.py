@@ -314,7 +314,8 @@ def test_file_stream_decoder_pcm(backend, tmp_path):
 
 
 def test_two_rank_gloo_gather():
-    """world_size 2 over gloo on the CPU (emulated kernels): shard, decode, gather on rank 0."""
+    """world_size 2 over gloo on the CPU (emulated kernels): shard, decode, gather on rank 0; the sharded capture's PCM
+    with the offset chain carried across the ranks (parallel.sharded_pcm)."""
     script = os.path.join(ROOT, "tests", "dist_worker.py")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
@@ -322,6 +323,7 @@ def test_two_rank_gloo_gather():
                        env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "GATHER_OK 4" in r.stdout, r.stdout[-3000:]
+    assert "PCM_OK 4" in r.stdout, r.stdout[-3000:]
 
 
 def test_two_rank_strong_scaling_gloo():

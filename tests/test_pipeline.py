@@ -145,6 +145,45 @@ def test_pipeline_pcm_against_framer_audio(backend, system, nranges):
     assert offset == t
 
 
+def test_error_behaviour_of_the_c_abi(backend):
+    """Calls that cannot be served fail with an LDD_E* code and a message instead of decoding something else: sample rates
+    the staging windows do not cover, tables of the wrong size, a second audio stage shorter than a block (the reference
+    raises there, lddecode_core.py:337), PCM without audio / before a finish / with an unknown chain, a PCM buffer that
+    is too small."""
+    import ctypes as C
+    fs = 8 * 315 / 88
+    for bad_fs in (42.0, 45.0):
+        with pytest.raises(_lib.LddError):
+            rfdecode.RFDecode(bad_fs, "NTSC", 16384, _backend=backend)
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, _backend=backend)
+    lib = backend.lib
+    with pytest.raises(_lib.LddError):
+        rf._set_filter(_lib.F_AUDIO_LPF2, np.zeros(100, dtype=np.complex128))
+    with pytest.raises(_lib.LddError):
+        rf.audio_phase2(np.rec.array([np.zeros(1000), np.zeros(1000)], names=['audio_left', 'audio_right']))
+    ao, st = C.c_double(0.0), C.c_int(2)
+    assert lib.ldd_pcm_chain(0, 48000.0, 63.5, 7, 0, None, None, C.byref(ao), C.byref(st), None) == -1        # LDD_EINVAL: chain
+    assert lib.ldd_pcm_chain(0, 0.0, 63.5, 0, 0, None, None, C.byref(ao), C.byref(st), None) == -1
+    assert lib.ldd_pcm_chain(0, 48000.0, 63.5, 0, 0, None, None, C.byref(ao), C.byref(st), None) == 0 and ao.value == 0.0
+    cap = synth.SynthRF("NTSC", fs, seed=3).generate(1100000)
+    rf_mute = rfdecode.RFDecode(fs, "NTSC", 16384, decode_analog_audio=False, _backend=backend)
+    cd = pipeline.CaptureDecoder(rf_mute)
+    res = cd.decode(backend.to_device(cap), _lib.FMT_U8, len(cap))
+    assert len(res.located) == 1
+    with pytest.raises(ValueError):
+        cd.pcm(res)                                             # decoded without the analog audio
+    cd = pipeline.CaptureDecoder(rf)
+    slot = cd._slot(0, len(cap))
+    off = (C.c_longlong * 8)()
+    buf, stat = backend.empty(16, np.int16), backend.zeros(8, np.int32)
+    args = (48000.0, 64.0, 63.5, 2.3e6, 2.8e6, 1, C.byref(ao), C.byref(st), backend.ptr(buf), 16, off, backend.ptr(stat), backend.stream())
+    assert lib.ldd_pipe_pcm(slot.h, *args) == -1                # no finish yet
+    res = cd.decode(backend.to_device(cap), _lib.FMT_U8, len(cap))
+    assert lib.ldd_pipe_pcm(slot.h, *args) == _lib.ECAP         # 16 int16 do not hold a field's samples
+    assert ao.value == 0.0 and st.value == 2                    # ... and the state is untouched
+    assert len(cd.pcm(res, chain='fields')[0][0]) == 1606
+
+
 def test_empty_and_ragged_captures(backend):
     """Captures that are empty, shorter than a block, end off the block grid or are a sample short of the first read
     (Framer.readfield returns None when RFDecode.demod does, lddecode_core.py:386-392, 1199-1201): no window, no crash;

@@ -324,8 +324,13 @@ int ldd_refine_pilot(ldd_handle* h, const float* demod_dev, const float* d05_dev
  *   mode 1                 out_dev = uint16 TBC samples; when burstlevel_dev (float32 [nfields][ll_stride]) is
  *                          given the NTSC burst markers are written into samples 0/1 of lines 1..linecount-2
  *   out_stride             elements between consecutive fields in out_dev
- *   status_dev             [nfields] int, caller-zeroed; bit 0 set when a line's window leaves the plane or
- *                          is degenerate (the reference raises and marks the field invalid) */
+ *   status_dev             [nfields] int, caller-zeroed; bit 0 (1) set when a line was not resampled, together with
+ *                          LDD_ST_LINE_LONG (32) when the only reason was a line longer than the staging window of this
+ *                          pass (1.25 x nominal; lddutils.scale takes any length: ldd_tbc_long_lines does those lines) or
+ *                          LDD_ST_LINE_BAD (64) when its window leaves the plane or is degenerate (the reference raises
+ *                          and marks the field invalid) */
+#define LDD_ST_LINE_LONG 32
+#define LDD_ST_LINE_BAD 64
 int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n, double plane_add, const long long* base_dev,
                    const double* linelocs_dev, int ll_stride, const int* linecount_dev, int nfields,
                    int max_linecount, int lineoffset, double lineloc_add, int outwidth, int wow, int mode,
@@ -341,6 +346,16 @@ int ldd_tbc_fields_ex(ldd_handle* h, const float* plane_dev, long long n, double
                       int max_linecount, int lineoffset, double lineloc_add, int outwidth, int wow, int mode,
                       void* out_dev, long long out_stride, const long long* out_off_dev, long long line_stride,
                       const float* burstlevel_dev, double colorlevel, int* status_dev, void* stream);
+
+/* Second pass for the rare lines the pass above left out as too long for its staging window (status 1 | LDD_ST_LINE_LONG;
+ * they come from fields whose line location partly failed -- the reference resamples whatever span it is given,
+ * lddutils.py:83-97): same arguments, exact float64 kernel with room for spans up to 4032 samples, only those lines are
+ * touched.  status_dev: a zeroed array of its own; a field that comes back 0 is complete. */
+int ldd_tbc_long_lines(ldd_handle* h, const float* plane_dev, long long n, double plane_add, const long long* base_dev,
+                       const double* linelocs_dev, int ll_stride, const int* linecount_dev, int nfields,
+                       int max_linecount, int lineoffset, double lineloc_add, int outwidth, int wow, int mode,
+                       void* out_dev, long long out_stride, const long long* out_off_dev, long long line_stride,
+                       const float* burstlevel_dev, double colorlevel, int* status_dev, void* stream);
 
 /* ---- VBI: Field.decodephillipscode (lddecode_core.py:814-834), batched.  For field f and code line lines[i]
  * (SysParams['philips_codelines']) codes_dev[4 f + i] receives the 24-bit Philips code (first cell = bit 23, i.e. the six
@@ -443,6 +458,9 @@ int ldd_pipe_launch(ldd_pipe* p, const void* rf_dev, int fmt, long long rf_base,
  * pic_cap - 1).  pic_cap = fields / frames pic_dev can hold; status_dev [max_fields] gets the per-field error bits. */
 int ldd_pipe_finish(ldd_pipe* p, double colorlevel, double colorphase, int frame_mode, void* pic_dev, long long pic_stride,
                     long long pic_cap, int* status_dev, void* refine_stream, void* main_stream, ldd_pipe_result* out);
+/* ldd_tbc_long_lines over the fields of the last ldd_pipe_finish (same pictures, same layout): for ranges whose status came
+ * back with 1 | LDD_ST_LINE_LONG and without LDD_ST_LINE_BAD.  status_dev: zeroed [nlocated] of its own. */
+int ldd_pipe_long_lines(ldd_pipe* p, int* status_dev, void* stream);
 
 /* Optional stage 3, asynchronous on `stream` (the main stream of stages 1 and 2): the 48 kHz PCM of the located fields of
  * the last ldd_pipe_finish, i.e. downscale_audio (lddecode_core.py:431-484) per field as Field.downscale(audio=True) calls

@@ -129,6 +129,10 @@ SIGNATURES.update({
     "ldd_tbc_fields_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                     C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p,
                                     C.c_longlong, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
+    "ldd_tbc_long_lines": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                     C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p,
+                                     C.c_longlong, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
+    "ldd_pipe_long_lines": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldd_vbi_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                  C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_void_p]),
     "ldd_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
@@ -155,6 +159,7 @@ SIGNATURES.update({
                                C.c_void_p, C.c_void_p]),
 })
 PCM_CHAIN_FIELDS, PCM_CHAIN_FRAMER = 0, 1
+ST_LINE_LONG, ST_LINE_BAD = 32, 64
 
 WINDOW_PEAKS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.POINTER(C.c_void_p),
                               C.POINTER(C.c_void_p), C.POINTER(C.c_int))

@@ -833,7 +833,8 @@ using namespace ldd;
 extern "C" int ldd_field_locate(ldd_handle* h, const long long* peaks, const double* vals, int npeaks,
                                 long long window_len, long long start, ldd_field* out,
                                 double* linelocs1, unsigned char* linebad, int ll_cap) {
-    if (!h || !peaks || !vals || !out || npeaks < 0) return LDD_EINVAL;
+    // a window without a single peak (silence, lead-in, an unreadable stretch) is a legitimate input: its list is empty
+    if (!h || !out || npeaks < 0 || (npeaks > 0 && (!peaks || !vals))) return LDD_EINVAL;
     const ldd_config& c = h->cfg;
     memset(out, 0, sizeof *out);
     out->npeaks = npeaks;

@@ -83,6 +83,10 @@ struct ldd_pipe {
     const void* fin_final = nullptr;
     const void* fin_linecount = nullptr;
     double fin_lineloc_add = 0.0;
+    // the TBC launch of the last finish, for ldd_pipe_long_lines
+    struct { const float* plane; long long plen; const long long* base; const double* ll; const int* lc; int n, maxlc, lineoffset;
+             double add; void* pic; long long pic_stride; const long long* off; long long line_stride; const float* bl;
+             double colorlevel; } tbc = {};
     cudaStream_t side = nullptr;        // prefix copies of off-chain windows
     bool upload_pending = false;
     long long audio1_len = 0, audio2_len = 0;
@@ -450,12 +454,16 @@ int ldd_pipe_finish(ldd_pipe* p, double colorlevel, double colorphase, int frame
         rc = ldd_tbc_fields_ex(h, pl_demod, plen, c.ire0, d_base, (const double*)out->d_linelocs4, LL, d_lc, n, maxlc, 1, out->lineloc_add,
                                W, 1, 1, pic_dev, pic_stride, (const long long*)(dt + t.o_outoff), line_stride,
                                (const float*)out->d_burstlevel, colorlevel, status_dev, rs);
+        p->tbc = {pl_demod, plen, d_base, (const double*)out->d_linelocs4, d_lc, n, maxlc, 1, out->lineloc_add, pic_dev, pic_stride,
+                  (const long long*)(dt + t.o_outoff), line_stride, (const float*)out->d_burstlevel, colorlevel};
     } else {
         rc = ldd_refine_pilot(h, pl_demod, pl_d05, plen, d_base, d_lc, n, LL, (const double*)out->d_linelocs2, (double*)out->d_linelocs3,
                               status_dev, rs);
         if (rc) return rc;
         rc = ldd_tbc_fields_ex(h, pl_demod, plen, c.ire0, d_base, (const double*)out->d_linelocs3, LL, d_lc, n, maxlc, 3, 0.0, W, 1, 1,
                                pic_dev, pic_stride, (const long long*)(dt + t.o_outoff), line_stride, nullptr, colorlevel, status_dev, rs);
+        p->tbc = {pl_demod, plen, d_base, (const double*)out->d_linelocs3, d_lc, n, maxlc, 3, 0.0, pic_dev, pic_stride,
+                  (const long long*)(dt + t.o_outoff), line_stride, nullptr, colorlevel};
     }
     if (rc) return rc;
     if (rs != ms) {
@@ -464,6 +472,15 @@ int ldd_pipe_finish(ldd_pipe* p, double colorlevel, double colorphase, int frame
     }
     p->finished = true;
     return LDD_OK;
+}
+
+int ldd_pipe_long_lines(ldd_pipe* p, int* status_dev, void* stream) {
+    if (!p || !status_dev) return LDD_EINVAL;
+    if (!p->finished) return pfail(p, LDD_EINVAL, "ldd_pipe_long_lines without ldd_pipe_finish");
+    if (p->located.empty()) return LDD_OK;
+    const auto& a = p->tbc;
+    return ldd_tbc_long_lines(p->h, a.plane, a.plen, p->h->cfg.ire0, a.base, a.ll, LL, a.lc, a.n, a.maxlc, a.lineoffset, a.add,
+                              p->h->cfg.outlinelen, 1, 1, a.pic, a.pic_stride, a.off, a.line_stride, a.bl, a.colorlevel, status_dev, stream);
 }
 
 int ldd_pcm_chain(int system, double freq_hz, double line_period_us, int chain, int nfields, const int* linecount,

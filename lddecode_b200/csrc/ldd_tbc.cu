@@ -50,9 +50,15 @@ struct TbcParams {
     long long line_stride;    // elements between consecutive lines of a field (outwidth, or 2 * outwidth for a frame)
     const float* burstlevel;  // NTSC final: [nfields][ll_stride] or NULL
     float clevel_k;           // float32(327.67 * clevel)
-    int* status;              // [nfields]: OR of per-line error bits (1: window outside the plane / too long)
+    int* status;              // [nfields]: OR of per-line error bits: 1 = a line was not resampled, plus 32 when the only
+                              // reason was a span longer than this launch's maxd (<= TBC_MAXD: ldd_tbc_long_lines can still
+                              // do it) or 64 for any other reason (window outside the plane, degenerate, > TBC_MAXD)
     int maxd;                 // longest input span this launch has shared memory for (<= TBC_MAXD)
+    int min_dist;             // long-lines pass: only lines with a span above this are done (0: all)
 };
+
+// status bits of a line that cannot be resampled by this launch (see TbcParams::status)
+__device__ inline int tbc_skip_bits(bool geom_ok, int dist) { return (geom_ok && dist <= TBC_MAXD) ? (1 | 32) : (1 | 64); }
 
 // int -> double and double -> int without the conversion pipe (0 <= v < 2^31): 2^52 + v has v in its low mantissa bits
 __device__ inline double tbc_i2d(int v) {
@@ -94,8 +100,10 @@ __global__ void __launch_bounds__(TBC_THREADS, 4) tbc_kernel(const TbcParams p) 
     const int dist = (int)(ie - ib);
     const int W = p.outwidth;
     char* outbase = (char*)p.out;
-    if (!(b >= 0.0) || dist < 3 || dist > p.maxd || base + ib + dist + 1 > p.n || base + ib < 0) {
-        if (tid == 0) atomicOr(&p.status[field], 1);
+    if (dist <= p.min_dist) return;                      // long-lines pass: the first pass has done this line
+    const bool geom_ok = b >= 0.0 && dist >= 3 && base + ib + dist + 1 <= p.n && base + ib >= 0;
+    if (!geom_ok || dist > p.maxd) {
+        if (tid == 0) atomicOr(&p.status[field], tbc_skip_bits(geom_ok, dist));
         return;
     }
     const double r = -0.26794919243112270647;      // sqrt(3) - 2
@@ -265,7 +273,7 @@ struct TbfGeom {            // one work item (field, line), filled by thread 0 w
     int field, line, dist, lead;   // lead = TBC_H + alignment shift: staged index of line sample 0
     int lc;                 // the field's line count (burst markers)
     int U;                  // staged samples
-    int state;              // 0: nothing to do (line >= linecount), 1: bulk copy in flight, 2: load by hand, 3: bad geometry
+    int state;              // 0: nothing to do (line >= linecount), 1: bulk copy in flight, 2: load by hand, 3: not resampled (status bits in U)
 };
 
 
@@ -310,8 +318,10 @@ __global__ void __launch_bounds__(TBF_THREADS, 5) tbc_f32_kernel(const TbcParams
             const long long ib = (long long)g.b, ie = (long long)g.e;
             g.dist = (int)(ie - ib);
             const long long s0 = q.base + ib - TBC_H;
-            if (!(g.b >= 0.0) || g.dist < 3 || g.dist > p.maxd || q.base + ib + g.dist + 1 > p.n || q.base + ib < 0) {
+            const bool geom_ok = g.b >= 0.0 && g.dist >= 3 && q.base + ib + g.dist + 1 <= p.n && q.base + ib >= 0;
+            if (!geom_ok || g.dist > p.maxd) {
                 g.state = 3;
+                g.U = tbc_skip_bits(geom_ok, g.dist);        // the status bits ride in U (no samples are staged)
             } else {
                 const int shift = (int)(s0 & 3);
                 const long long a0 = s0 - shift;
@@ -356,7 +366,7 @@ __global__ void __launch_bounds__(TBF_THREADS, 5) tbc_f32_kernel(const TbcParams
         const TbfGeom g = geom[cur];
         float* ys = ysb[cur];
         if (g.state == 0 || g.state == 3) {
-            if (g.state == 3 && tid == 0) atomicOr(&p.status[g.field], 1);
+            if (g.state == 3 && tid == 0) atomicOr(&p.status[g.field], g.U);
             __syncthreads();
             continue;
         }
@@ -491,11 +501,11 @@ __global__ void __launch_bounds__(TBF_THREADS, 5) tbc_f32_kernel(const TbcParams
 
 using namespace ldd;
 
-extern "C" int ldd_tbc_fields_ex(ldd_handle* h, const float* plane_dev, long long n, double plane_add,
-                                 const long long* base_dev, const double* linelocs_dev, int ll_stride, const int* linecount_dev, int nfields,
-                                 int max_linecount, int lineoffset, double lineloc_add, int outwidth, int wow, int mode,
-                                 void* out_dev, long long out_stride, const long long* out_off_dev, long long line_stride,
-                                 const float* burstlevel_dev, double colorlevel, int* status_dev, void* stream) {
+static int tbc_launch(ldd_handle* h, const float* plane_dev, long long n, double plane_add,
+                      const long long* base_dev, const double* linelocs_dev, int ll_stride, const int* linecount_dev, int nfields,
+                      int max_linecount, int lineoffset, double lineloc_add, int outwidth, int wow, int mode,
+                      void* out_dev, long long out_stride, const long long* out_off_dev, long long line_stride,
+                      const float* burstlevel_dev, double colorlevel, int* status_dev, void* stream, bool long_only) {
     if (!h || !plane_dev || !linelocs_dev || !linecount_dev || !out_dev || !status_dev) return LDD_EINVAL;
     if (nfields <= 0 || max_linecount <= 0) return LDD_OK;
     if (outwidth < 1 || (mode != 0 && mode != 1)) return LDD_EINVAL;
@@ -525,6 +535,16 @@ extern "C" int ldd_tbc_fields_ex(ldd_handle* h, const float* plane_dev, long lon
     // TBC_MAXD): 50 KB per CTA for PAL at 8fsc, so four CTAs share an SM
     p.maxd = c.linelen + c.linelen / 4 + 64;
     if (p.maxd > TBC_MAXD) p.maxd = TBC_MAXD;
+    p.min_dist = 0;
+    const bool f32_lane = mode == 1 && c.precision != LDD_PREC_F64 && !getenv("LDD_TBC_F64");
+    int maxu = (p.maxd + 1 + 2 * TBC_H + 3 + 3) & ~3;
+    if (f32_lane && maxu > TBF_MAXU) { maxu = TBF_MAXU; p.maxd = TBF_MAXU - 2 * TBC_H - 8; }
+    if (long_only) {
+        // second pass (ldd_tbc_long_lines): the exact kernel with shared memory for the longest span it supports, over the
+        // lines the first pass left out because they were longer than ITS shared memory
+        p.min_dist = p.maxd;
+        p.maxd = TBC_MAXD;
+    }
     const int maxq = (p.maxd + 1 + 2 * TBC_H + TBC_C - 1) / TBC_C;
     size_t smem = (size_t)(2 * ((TBC_C + 1) * maxq + 4) + 2 * (maxq + 2)) * sizeof(double);
     if (!h->tbc_taps_set) {
@@ -536,10 +556,8 @@ extern "C" int ldd_tbc_fields_ex(ldd_handle* h, const float* plane_dev, long lon
         h->tbc_taps_set = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == 1 && c.precision != LDD_PREC_F64 && !getenv("LDD_TBC_F64")) {
+    if (f32_lane && !long_only) {
         // float32 lanes: bulk-copy staged, persistent CTAs
-        int maxu = (p.maxd + 1 + 2 * TBC_H + 3 + 3) & ~3;
-        if (maxu > TBF_MAXU) { maxu = TBF_MAXU; p.maxd = TBF_MAXU - 2 * TBC_H - 8; }
         const size_t smem32 = (size_t)(3 * maxu + 32 + 2 * TBF_THREADS) * sizeof(float);
         cudaFuncSetAttribute(tbc_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
         cudaFuncSetAttribute(tbc_f32_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -556,6 +574,26 @@ extern "C" int ldd_tbc_fields_ex(ldd_handle* h, const float* plane_dev, long lon
     cudaFuncSetAttribute(tbc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);      // several CTAs of ~50 KB per SM
     LDD_LAUNCH(tbc_kernel, dim3(max_linecount, nfields), dim3(TBC_THREADS), smem, st, p);
     return launch_status(h, "tbc_kernel");
+}
+
+extern "C" int ldd_tbc_fields_ex(ldd_handle* h, const float* plane_dev, long long n, double plane_add,
+                                 const long long* base_dev, const double* linelocs_dev, int ll_stride, const int* linecount_dev, int nfields,
+                                 int max_linecount, int lineoffset, double lineloc_add, int outwidth, int wow, int mode,
+                                 void* out_dev, long long out_stride, const long long* out_off_dev, long long line_stride,
+                                 const float* burstlevel_dev, double colorlevel, int* status_dev, void* stream) {
+    return tbc_launch(h, plane_dev, n, plane_add, base_dev, linelocs_dev, ll_stride, linecount_dev, nfields, max_linecount, lineoffset,
+                      lineloc_add, outwidth, wow, mode, out_dev, out_stride, out_off_dev, line_stride, burstlevel_dev, colorlevel,
+                      status_dev, stream, false);
+}
+
+extern "C" int ldd_tbc_long_lines(ldd_handle* h, const float* plane_dev, long long n, double plane_add,
+                                  const long long* base_dev, const double* linelocs_dev, int ll_stride, const int* linecount_dev, int nfields,
+                                  int max_linecount, int lineoffset, double lineloc_add, int outwidth, int wow, int mode,
+                                  void* out_dev, long long out_stride, const long long* out_off_dev, long long line_stride,
+                                  const float* burstlevel_dev, double colorlevel, int* status_dev, void* stream) {
+    return tbc_launch(h, plane_dev, n, plane_add, base_dev, linelocs_dev, ll_stride, linecount_dev, nfields, max_linecount, lineoffset,
+                      lineloc_add, outwidth, wow, mode, out_dev, out_stride, out_off_dev, line_stride, burstlevel_dev, colorlevel,
+                      status_dev, stream, true);
 }
 
 extern "C" int ldd_tbc_fields(ldd_handle* h, const float* plane_dev, long long n, double plane_add,

@@ -208,6 +208,20 @@ def refine_and_tbc(rf, planes, plane_len, batch, colorlevel=1.45, colorphase=91.
     if want_intermediates:
         be.synchronize()
         out.status = be.to_host(d_status)
+        need = ((out.status & _lib.ST_LINE_LONG) != 0) & ((out.status & _lib.ST_LINE_BAD) == 0)
+        if need.any():
+            # lines longer than the staging window of the TBC pass (the reference's scale() takes any span,
+            # lddutils.py:83-97): second pass with the exact kernel, in place
+            d_st2 = be.zeros(n, np.int32)
+            ntsc = rf.system == 'NTSC'
+            rf._check(lib.ldd_tbc_long_lines(rf._h, be.ptr(planes['demod']), int(plane_len), ire0, be.ptr(d_base), be.ptr(out.d_final),
+                                             LL_STRIDE, be.ptr(d_lc), n, maxlc, 1 if ntsc else 3, out.lineloc_add, W, 1, 1,
+                                             be.ptr(d_pic), out.out_stride, None, 0, be.ptr(out.d_burstlevel) if ntsc else None,
+                                             float(colorlevel), be.ptr(d_st2), st))
+            be.synchronize()
+            done = need & (be.to_host(d_st2) == 0)
+            out.status = np.array(out.status)
+            out.status[done] &= ~(1 | _lib.ST_LINE_LONG)
         out.linelocs2 = be.to_host(d_l2).reshape(n, LL_STRIDE)
         out.linebad = be.to_host(d_bad2).reshape(n, LL_STRIDE)
         out.final = be.to_host(out.d_final).reshape(n, LL_STRIDE)

@@ -310,6 +310,16 @@ class HostStreamDecoder:
         if dev is not None:
             self.be.wait_event(dev)
         res.status_host = self.be.host_view(self.h_status[j])[:nloc]
+        if nloc and np.any(res.status_host & _lib.ST_LINE_LONG):
+            # rare: lines longer than the TBC's staging window; second pass in place, then those fields come down again
+            st = self.cd.repair_long_lines(res, res.status_host)
+            fixed = np.nonzero(st != res.status_host)[0]
+            if len(fixed):
+                pic = self.be.to_host(res.d_pic[:nloc * self.out_stride]).reshape(nloc, self.out_stride)
+                hv = self.be.host_view(self.h_out[j])[:nloc * self.out_stride].reshape(nloc, self.out_stride)
+                for k in fixed:
+                    hv[k] = pic[k]
+                res.status_host[:] = st
         res.pcm_host = [] if self.want_pcm else None
         if res._pcm_off is not None:
             res.pcm_host = split_pcm(self.be.host_view(self.h_pcm[j][0]), res._pcm_off, self.be.host_view(self.h_pcm[j][1]))
@@ -793,6 +803,32 @@ class CaptureDecoder:
         be.synchronize()
         return split_pcm(be.to_host(d_pcm[:max(off[-1], 1)]), off, be.to_host(d_st)), audio_offset, frame_state
 
+    # -- lines too long for the TBC's staging window (fields whose line location partly failed)
+    def repair_long_lines(self, res, st=None):
+        """Fields of `res` whose status says 1 | ST_LINE_LONG without ST_LINE_BAD had lines longer than 1.25 x nominal,
+        which the TBC pass leaves out; the reference resamples any span (lddutils.py:83-97).  Runs the second pass
+        (ldd_pipe_long_lines: exact kernel, spans up to 4032 samples) over the range's pictures in place and clears the
+        bits of the fields it completes, on the device and in the returned host copy.  Synchronous; a no-op (no launch)
+        when no field is flagged, which is the normal case."""
+        be = res.slot.rf._be
+        if res.d_status is None:
+            return np.zeros(0, dtype=np.int32)
+        if st is None:
+            be.synchronize()
+            st = be.to_host(res.d_status)
+        st = np.array(st[:len(res.located)], dtype=np.int32)
+        need = ((st & _lib.ST_LINE_LONG) != 0) & ((st & _lib.ST_LINE_BAD) == 0)
+        if not need.any() or res.slot.generation != res._generation:
+            return st
+        d2 = be.zeros(len(st), np.int32)
+        res.slot.rf._check(be.lib.ldd_pipe_long_lines(res.slot.h, be.ptr(d2), be.stream()))
+        be.synchronize()
+        done = need & (be.to_host(d2) == 0)
+        st[done] &= ~(1 | _lib.ST_LINE_LONG)
+        be.copy_async(res.d_status, be.to_device(st))
+        be.synchronize()
+        return st
+
     # -- host copies
     def pictures(self, res):
         """uint16 TBC fields of the located windows -> list of (readsample, istop, array | None)."""
@@ -800,8 +836,8 @@ class CaptureDecoder:
         if res.d_pic is None:
             return []
         be.synchronize()
+        st = self.repair_long_lines(res)
         pic = be.to_host(res.d_pic).reshape(len(res.located), res.out_stride)
-        st = be.to_host(res.d_status)
         W = rf.SysParams['outlinelen']
         out = []
         for k, j in enumerate(res.located):

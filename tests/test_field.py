@@ -257,6 +257,62 @@ def test_tbc_random_geometry_against_oracle_spline(backend):
         np.testing.assert_allclose(got[l], ref, rtol=0, atol=2e-6 * np.abs(p64).max())
 
 
+@pytest.mark.parametrize("precision,mode", [("f64", 0), ("mixed", 1), ("f64", 1)])
+def test_tbc_long_lines_second_pass(backend, precision, mode):
+    """Lines longer than the staging window of the TBC pass (1.25 x nominal; they come from fields whose line location partly
+    failed, and lddutils.scale resamples any span): the first pass leaves them out with status 1 | LDD_ST_LINE_LONG and does
+    every other line, ldd_tbc_long_lines does exactly those lines (exact kernel, spans up to 4032 samples) and nothing
+    else; a span beyond that and a window outside the plane are LDD_ST_LINE_BAD in both passes."""
+    fs = 8 * 315 / 88
+    rf = rfdecode.RFDecode(fs, "NTSC", 16384, _backend=backend, precision=precision)
+    be = backend
+    rng = np.random.default_rng(8)
+    L, W = rf.linelen, rf.SysParams['outlinelen']
+    n = 60 * L
+    SP = rf.SysParams
+    plane = (np.cumsum(rng.normal(0, 9000.0, n)) * 0.02 + 400000.0 * np.sin(np.arange(n) * 0.01)).astype(np.float32)
+    add = float(SP['ire0']) if mode == 1 else 0.0
+
+    def run(gaps, first=500.25):
+        ll = np.zeros(field.LL_STRIDE)
+        ll[: len(gaps) + 1] = first + np.concatenate([[0], np.cumsum(gaps)])
+        nl = len(gaps)
+        d_out = be.zeros(nl * W, np.uint16 if mode else np.float64)
+        d_plane, d_ll, d_lc = be.to_device(plane), be.to_device(ll), be.to_device(np.array([nl], dtype=np.int32))
+        outs = []
+        for fn in (be.lib.ldd_tbc_fields_ex, be.lib.ldd_tbc_long_lines):
+            d_st = be.zeros(1, np.int32)
+            rf._check(fn(rf._h, be.ptr(d_plane), n, add, None, be.ptr(d_ll), field.LL_STRIDE, be.ptr(d_lc), 1, nl, 0, 0.0, W, 1, mode,
+                         be.ptr(d_out), nl * W, None, 0, None, 1.45, be.ptr(d_st), be.stream()))
+            be.synchronize()
+            outs.append((int(be.to_host(d_st)[0]), be.to_host(d_out).reshape(nl, W).copy()))
+        return ll, outs
+
+    gaps = [1.0 * L, 1.3 * L, 0.9 * L, 1.9 * L, 4000.0, 1.1 * L, 1.26 * L + 70]
+    long_lines = [1, 3, 4, 6]
+    ll, ((st1, out1), (st2, out2)) = run(gaps)
+    assert st1 == (1 | _lib.ST_LINE_LONG) and st2 == 0
+    p64 = plane.astype(np.float64) + add
+    for l in range(len(gaps)):
+        hz = O.scale(p64, ll[l], ll[l + 1], W) * ((ll[l + 1] - ll[l]) / L)
+        if mode == 0:
+            ref, tol = hz, 2e-6 * np.abs(p64).max()
+        else:
+            ire = (hz - SP['ire0']) / SP['hz_ire'] - SP['vsync_ire']
+            ref, tol = np.uint16(np.clip(ire * ((0xc800 - 0x0400) / (100 - SP['vsync_ire'])) + 1024, 0, 65535) + 0.5).astype(np.float64), 1.0
+        if l in long_lines:
+            assert not np.any(out1[l])                                     # left alone by the first pass ...
+            assert np.abs(out2[l].astype(np.float64) - ref).max() <= tol   # ... and done by the second
+        else:
+            assert np.abs(out1[l].astype(np.float64) - ref).max() <= tol
+            assert np.array_equal(out1[l], out2[l])                        # untouched by the second pass
+    # beyond the exact kernel's reach, or outside the plane: not resampled by either pass
+    for gaps, first in (([1.0 * L, 4100.0, 1.0 * L], 500.25), ([1.0 * L, 1.0 * L], n - 1.5 * L)):
+        _, ((st1, _), (st2, _)) = run(gaps, first)
+        assert st1 == (1 | _lib.ST_LINE_BAD) and st2 in (0, 1 | _lib.ST_LINE_BAD)
+    assert st2 == 0                      # (the short lines of the last case are none of the second pass's business)
+
+
 def test_window_peaks_from_global_matches_own_chase(backend):
     """The host walk cuts a window's peak list out of the capture-wide chase (on a global peak, or off the chain:
     the second read of a capture).  Whenever ldd_window_peaks_from_global decides, its answer must be the list the

@@ -135,6 +135,48 @@ def test_damaged_capture_matches_oracle_walk(backend, system):
         assert nf >= 2
 
 
+def test_unreadable_and_noisy_captures_follow_the_reference(backend):
+    """Two things a fuzzing campaign over the emulated kernels found (round 2), both on captures the reference copes with:
+    (a) a stretch without a single sync peak (lead-in, spin-up, silence): Field finds no vsync and Framer.readfield jumps
+    10 s ahead (lddecode_core.py:1208-1210) -- the walk used to fail on the empty peak list;
+    (b) a very noisy field whose line location partly failed and left lines longer than 1.25 x nominal: the reference
+    resamples whatever span it is given (lddutils.py:83-97), the TBC pass leaves such lines to a second pass
+    (ldd_tbc_long_lines) instead of giving the field up.  A field whose line table is not even monotonic is invalid in the
+    reference too (scale() raises inside the constructor's try block)."""
+    fs = FS["PAL"]
+    rf = rfdecode.RFDecode(fs, "PAL", 16384, decode_analog_audio=False, _backend=backend, precision="f64")
+    cd = pipeline.CaptureDecoder(rf)
+    dec = O.Decoder(fs, "PAL", 16384, analog_audio=False)
+    # (a) noise only, and a capture that is silent
+    rng = np.random.default_rng(12)
+    for cap in (rng.integers(0, 256, 2200000).astype(np.uint8), np.full(1200000, 128, dtype=np.uint8)):
+        res = cd.decode(backend.to_device(cap), _lib.FMT_U8, len(cap))
+        f = O.decode_field(dec, O.demod(dec, lambda s, n: cap[s:s + n] if s + n <= len(cap) else None, 0, 1000000, 1)[0], 0)
+        assert not f.valid and len(f.peaklist) < 100
+        assert res.nwindows == 1 and len(res.located) == 0                     # the next read would start 10 s on
+        assert int(res.infos[0].npeaks) == len(f.peaklist) and res.infos[0].stage == _lib.FIELD_NOVSYNC
+    # (b) heavy noise on a disc running 1 % fast
+    ncap = 2377018
+    cap = synth.SynthRF("PAL", fs * 1.0101, seed=314, bits=10, noise=15.0, lead_lines=26).generate(ncap)
+    res = cd.decode(backend.to_device(cap), _lib.FMT_U16, ncap)
+    backend.synchronize()
+    raw = backend.to_host(res.d_status).copy()
+    pics = cd.pictures(res)
+    assert len(pics) == 2 and np.any(raw & _lib.ST_LINE_LONG)
+    seen_long = 0
+    for k, (rs, istop, pic) in enumerate(pics):
+        d = O.demod(dec, lambda s, n: cap[s:s + n] if s + n <= ncap else None, rs, 1000000, 1)
+        f = O.decode_field(dec, d[0], 0)
+        assert (pic is not None) == bool(f.valid), (k, raw[k])
+        if pic is None:
+            continue
+        spans = np.diff(np.array(f.linelocs))[3:3 + f.linecount]
+        seen_long += int(np.sum(spans > 1.25 * rf.linelen + 64))
+        assert np.abs(pic.astype(np.int64) - f.dspicture.astype(np.int64)).max() <= 1
+    assert seen_long >= 1
+    assert not np.any(res.refined.status[[k for k, p in enumerate(pics) if p[2] is not None]])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("precision", ["f64", "mixed"])
 @pytest.mark.parametrize("blocklen,blockcut", [(65536, 1024), (131072, 1024), (262144, 1024), (16384, 512), (16384, 2048),

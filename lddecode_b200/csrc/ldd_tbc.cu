@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(TBC_THREADS, 4) tbc_kernel(const TbcParams p) 
     const int dist = (int)(ie - ib);
     const int W = p.outwidth;
     char* outbase = (char*)p.out;
-    if (dist <= p.min_dist) return;                      // long-lines pass: the first pass has done this line
+    if (p.min_dist > 0 && dist <= p.min_dist) return;    // long-lines pass: the first pass has dealt with this line
     const bool geom_ok = b >= 0.0 && dist >= 3 && base + ib + dist + 1 <= p.n && base + ib >= 0;
     if (!geom_ok || dist > p.maxd) {
         if (tid == 0) atomicOr(&p.status[field], tbc_skip_bits(geom_ok, dist));

@@ -307,7 +307,8 @@ def test_tbc_long_lines_second_pass(backend, precision, mode):
             assert np.abs(out1[l].astype(np.float64) - ref).max() <= tol
             assert np.array_equal(out1[l], out2[l])                        # untouched by the second pass
     # beyond the exact kernel's reach, or outside the plane: not resampled by either pass
-    for gaps, first in (([1.0 * L, 4100.0, 1.0 * L], 500.25), ([1.0 * L, 1.0 * L], n - 1.5 * L)):
+    for gaps, first in (([1.0 * L, 4100.0, 1.0 * L], 500.25), ([1.0 * L, -0.5 * L, 1.0 * L], 500.25), ([1.0 * L, 1.5, 1.0 * L], 500.25),
+                        ([1.0 * L, 1.0 * L], n - 1.5 * L)):
         _, ((st1, _), (st2, _)) = run(gaps, first)
         assert st1 == (1 | _lib.ST_LINE_BAD) and st2 in (0, 1 | _lib.ST_LINE_BAD)
     assert st2 == 0                      # (the short lines of the last case are none of the second pass's business)

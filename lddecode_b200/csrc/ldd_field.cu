@@ -310,37 +310,49 @@ __global__ void __launch_bounds__(32 * BURST_WARPS) burst_lines_kernel(const Bur
             const double wowf = (e - b) / (double)p.linelen;
             // input samples needed: x in [fb + 20 step, fb + 59 step] -> indices i0..i1+1, M needs +-(K+1) more
             const int i0 = (int)(fb + BURST_FIRST * step), i1 = (int)(fb + (BURST_FIRST + BURST_N - 1) * step) + 1;
-            const int s0 = i0 - (BURST_K + 1);                 // first staged sample (line-relative, may be < 0)
-            const int ns = (i1 - i0 + 1) + 2 * (BURST_K + 1);
-            ok = (b >= 0.0) && dist >= 3 && ns <= BURST_WIN && i1 <= dist && i0 >= 30 && ib + dist + 1 <= p.n;
+            ok = (b >= 0.0) && dist >= 3 && i1 <= dist && i0 >= 16 && ib + dist + 1 <= p.n;      // i0: |r|^16 = 7e-10 of the line-start boundary term
             if (!ok) {
                 // geometry the fast path does not cover (or the reference would raise): flag, leave the line "no burst"
                 if (lane == 0) atomicOr(&p.status[f], 4);
             } else {
-                for (int k = lane; k < ns; k += 32) {
-                    long long s = base + ib + s0 + k;
-                    s = s < 0 ? 0 : (s >= p.n ? p.n - 1 : s);
-                    ys[warp][k] = (double)p.burst[s];
+                // The 40 samples are produced in passes over the staging window: one pass for any line up to ~1.6 x
+                // nominal, several (jn outputs each) for a longer one -- the reference resamples whatever span the line
+                // table gives it.  A pass over outputs [j0, j1) stages inputs c0 - (K+1) .. c1 + (K+1).
+                int jn = BURST_N;
+                if ((i1 - i0 + 1) + 2 * (BURST_K + 1) > BURST_WIN) {
+                    jn = (int)((double)(BURST_WIN - 2 * (BURST_K + 1) - 3) / step) + 1;
+                    if (jn > BURST_N) jn = BURST_N;
                 }
-                __syncwarp();
-                const int nm = i1 - i0 + 1;                         // M[i0 .. i1]
-                for (int k = lane; k < nm; k += 32) {
-                    double acc = 0.0;
-                    const double* y = &ys[warp][k];                 // y[(i0+k) - (K+1)] is ys[k]
-                    for (int m = 0; m <= 2 * (BURST_K + 1); ++m) acc += c_burst_taps[m] * y[m];
-                    Ms[warp][k] = acc;
+                for (int j0 = 0; j0 < BURST_N; j0 += jn) {
+                    const int j1 = j0 + jn < BURST_N ? j0 + jn : BURST_N;
+                    const int c0 = (int)(fb + (BURST_FIRST + j0) * step), c1 = (int)(fb + (BURST_FIRST + j1 - 1) * step) + 1;
+                    const int s0 = c0 - (BURST_K + 1);             // first staged sample (line-relative, may be < 0)
+                    const int ns = (c1 - c0 + 1) + 2 * (BURST_K + 1);
+                    for (int k = lane; k < ns; k += 32) {
+                        long long s = base + ib + s0 + k;
+                        s = s < 0 ? 0 : (s >= p.n ? p.n - 1 : s);
+                        ys[warp][k] = (double)p.burst[s];
+                    }
+                    __syncwarp();
+                    const int nm = c1 - c0 + 1;                     // M[c0 .. c1]
+                    for (int k = lane; k < nm; k += 32) {
+                        double acc = 0.0;
+                        const double* y = &ys[warp][k];             // y[(c0+k) - (K+1)] is ys[k]
+                        for (int m = 0; m <= 2 * (BURST_K + 1); ++m) acc += c_burst_taps[m] * y[m];
+                        Ms[warp][k] = acc;
+                    }
+                    __syncwarp();
+                    for (int j = j0 + lane; j < j1; j += 32) {
+                        double x = (double)(BURST_FIRST + j) * step + fb;
+                        int i = (int)x;
+                        double t = x - (double)i, u = 1.0 - t;
+                        double Mi = Ms[warp][i - c0], Mj = Ms[warp][i + 1 - c0];
+                        double yi = ys[warp][i - s0], yj = ys[warp][i + 1 - s0];
+                        double S = Mi * u * u * u / 6.0 + Mj * t * t * t / 6.0 + (yi - Mi / 6.0) * u + (yj - Mj / 6.0) * t;
+                        bas[slot][j] = S * wowf;
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
-                for (int j = lane; j < BURST_N; j += 32) {
-                    double x = (double)(BURST_FIRST + j) * step + fb;
-                    int i = (int)x;
-                    double t = x - (double)i, u = 1.0 - t;
-                    double Mi = Ms[warp][i - i0], Mj = Ms[warp][i + 1 - i0];
-                    double yi = ys[warp][i - s0], yj = ys[warp][i + 1 - s0];
-                    double S = Mi * u * u * u / 6.0 + Mj * t * t * t / 6.0 + (yi - Mi / 6.0) * u + (yj - Mj / 6.0) * t;
-                    bas[slot][j] = S * wowf;
-                }
-                __syncwarp();
             }
         }
         if (lane == 0) s_ok[slot] = ok ? 1 : 0;

@@ -96,6 +96,30 @@ def test_reference_step_methods(backend, golden, name):
         np.testing.assert_allclose(f.refine_linelocs_pilot(ll2), g["field_linelocs"], rtol=0, atol=1e-5)
 
 
+def test_burst_refinement_on_abnormal_line_spans(backend, golden):
+    """refine_linelocs_burst on a line table with spans the fast path's staging window does not hold in one piece (1.7 x
+    and 3.2 x nominal: the 40 burst samples are then produced in several passes) and a short one (0.6 x), against the
+    oracle's restatement of lddecode_core.py:1054-1133 -- the reference resamples whatever span it is given."""
+    g = golden("ntsc")
+    rf, dd, system = _setup(backend, g, "ntsc")
+    f = field.FieldNTSC(rf, dd, 0)
+    L = rf.linelen
+    ll = np.array(f.linelocs2)
+    ll[100:] += 0.7 * L
+    ll[150:] += 2.2 * L
+    ll[200:] -= 0.4 * L
+    dec = O.Decoder(float(g["fs_mhz"]), "NTSC", int(g["blocklen"]))
+    cap = g["capture"]
+    video, _ = O.demod(dec, lambda a, n: cap[a:a + n] if a + n <= len(cap) else None, 0, int(g["demod_length"]), 1)
+    want3, wantbl = O.refine_burst_ntsc(dec, video["demod_burst"], list(ll), f.linecount)
+    got3, gotbl = f.refine_linelocs_burst(ll)
+    np.testing.assert_allclose(got3, want3, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(gotbl, np.asarray(wantbl, dtype=np.float32), rtol=3e-6, atol=0)
+    want4, _ = O.refine_burst_ntsc(dec, video["demod_burst"], list(want3), f.linecount)
+    got4, _ = f.refine_linelocs_burst(got3)
+    np.testing.assert_allclose(got4, want4, rtol=0, atol=1e-5)
+
+
 @pytest.mark.parametrize("name", ["ntsc", "pal"])
 def test_downscale_float_matches_scale(backend, golden, name):
     """Field.downscale in float64 mode equals the reference's lddutils.scale per line."""
